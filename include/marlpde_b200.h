@@ -1,0 +1,153 @@
+/*
+ * marlpde_b200.h — C ABI of the B200-native integrator for L'Heureux's five coupled
+ * diagenetic equations (aragonite CA, calcite CC, pore-water cCa and cCO3, porosity Phi).
+ *
+ * This is the drop-in boundary for the ONE hot path of
+ * astro-turing/Integrating-diagenetic-equations-using-Python ("the reference"):
+ *
+ *   reference interface                                   replaced by
+ *   ---------------------------------------------------   ---------------------------------
+ *   LMAHeureuxPorosityDiff.fun_numba / pde_rhs            marlpde_rhs_batch[_dev]
+ *     (marlpde/LHeureux_model.py:290-359, :361-522)
+ *   LMAHeureuxPorosityDiff.fun (NumPy backend, :162-288)  marlpde_rhs_batch[_dev] (same maths)
+ *   scipy.integrate.solve_ivp(method="RK45", ...)         marlpde_rk45_integrate[_dev]
+ *     call site marlpde/Evolve_scenario.py:104-109
+ *   7 event monitors (LHeureux_model.py:524-593)          event outputs of marlpde_rk45_integrate*
+ *   derived constants of __init__ (:31-72, :130-133)      marlpde_column_params (filled by the host
+ *                                                          mirror, one struct per sediment column)
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types. `*_dev` entry points take DEVICE pointers
+ *     and a cudaStream_t passed as void* (0 = default stream) and never allocate or synchronise;
+ *     the un-suffixed entry points take HOST pointers, pick `device`, do their own
+ *     H2D/D2H copies and synchronise before returning.
+ *   - state layout: y[column][field][cell], fields in the reference's order
+ *     CA, CC, cCa, cCO3, Phi (Evolve_scenario.py:64-65), float64, C-contiguous.
+ *   - every function returns MARLPDE_OK (0) or a negative MARLPDE_E* code;
+ *     marlpde_last_error() returns a thread-local human readable message.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ *     with MARLPDE_ENODEVICE.
+ */
+#ifndef MARLPDE_B200_H
+#define MARLPDE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MARLPDE_ABI_VERSION 1
+#define MARLPDE_NFIELDS 5
+#define MARLPDE_NEVENTS 7
+
+/* return codes */
+#define MARLPDE_OK 0
+#define MARLPDE_EINVAL (-1)     /* bad argument */
+#define MARLPDE_ENODEVICE (-2)  /* no usable CUDA device */
+#define MARLPDE_ECUDA (-3)      /* CUDA runtime error (see marlpde_last_error) */
+#define MARLPDE_EUNSUPPORTED (-4) /* shape not supported by this build (e.g. n_cells too large) */
+
+/* per-column integration status, mirrors solve_ivp's sol.status (scipy/integrate/_ivp/ivp.py) */
+#define MARLPDE_STATUS_FINISHED 0       /* reached t_bound                                  */
+#define MARLPDE_STATUS_STEP_TOO_SMALL (-1) /* "Required step size is less than spacing between numbers." */
+#define MARLPDE_STATUS_NONFINITE (-2)   /* state became non-finite and the step size collapsed */
+#define MARLPDE_STATUS_STEP_BUDGET 1    /* max_steps attempts used up; (t, h_abs, y) are resumable */
+
+/*
+ * Per-column constants: exactly the scalars the reference passes into pde_rhs
+ * (LHeureux_model.py:346-359) after deriving them in __init__ (:31-72, :87-88, :130-133),
+ * plus the Dirichlet values of the top boundary (:26-30) and the grid spacing of
+ * CartesianGrid([[0, max_depth/Xstar]], [N]) (Evolve_scenario.py:40).
+ * The two Heaviside masks (Evolve_scenario.py:51-54) are an interval of cells:
+ * not_too_deep*not_too_shallow == 1 on [mask_lo, mask_hi), 0 elsewhere.
+ */
+typedef struct marlpde_column_params {
+  double bc_top[MARLPDE_NFIELDS]; /* CA0, CC0, cCa0, cCO30, Phi0 */
+  double dx;          /* (max_depth/Xstar)/N                         */
+  double inv_dx;      /* 1/dx                                        */
+  double inv_dx2;     /* dx**-2                                      */
+  double delta_x;     /* x[1]-x[0] of the cell centres (:23-24)      */
+  double presum, rhorat, Da, lambda_;
+  double dCa, dCO3, delta, KRat;
+  double nu1, nu2, m1, m2, n1, n2;
+  double dPhi_fixed, Peclet_min, Peclet_max;
+  int32_t FV_switch;
+  int32_t mask_lo, mask_hi;
+  int32_t reserved;
+} marlpde_column_params;
+
+/* Options of one batched Dormand-Prince RK45 integration (scipy RK45 semantics). */
+typedef struct marlpde_rk45_options {
+  double t_bound;      /* end time (t_span[1]); direction is forward only              */
+  double rtol, atol;   /* scale = atol + rtol*max(|y|,|y_new|)                         */
+  double max_step;     /* +inf for none                                                */
+  int64_t max_steps;   /* step-attempt budget per column per call (<=0: unlimited)     */
+  int32_t n_eval;      /* number of t_eval points (may be 0)                           */
+  int32_t event_capacity; /* slots per (column,event) in event_times (may be 0)       */
+  int32_t flags;       /* MARLPDE_FLAG_*                                               */
+  int32_t reserved;
+} marlpde_rk45_options;
+
+#define MARLPDE_FLAG_EVENTS 1u   /* monitor the 7 events and locate their roots */
+
+/* Per-column integrator state: input (start/resume point) and output (end point). */
+typedef struct marlpde_column_state {
+  double t;            /* in: start time;  out: time reached                          */
+  double h_abs;        /* in: first_step (or the h_abs to resume with); out: next h   */
+  int64_t n_accepted;  /* counters are accumulated across resumed calls               */
+  int64_t n_rejected;
+  int64_t nfev;
+  int32_t status;      /* out: MARLPDE_STATUS_*                                        */
+  int32_t next_eval;   /* in/out: index of the next t_eval point to be sampled         */
+} marlpde_column_state;
+
+typedef struct marlpde_device_info {
+  char name[128];
+  int32_t sm_count;
+  int32_t cc_major, cc_minor;
+  int32_t max_smem_per_block; /* opt-in bytes */
+  int64_t total_mem;
+} marlpde_device_info;
+
+int marlpde_abi_version(void);
+const char* marlpde_last_error(void);
+int marlpde_device_count(void);
+int marlpde_get_device_info(int device, marlpde_device_info* info);
+
+/* Largest n_cells the on-chip (shared-memory resident) RK45 kernel accepts, and the
+ * number of columns one CTA integrates side by side for a given n_cells. */
+int marlpde_rk45_max_cells(void);
+int marlpde_rk45_columns_per_cta(int n_cells);
+
+/* ---- single RHS call for a batch of columns (replaces fun_numba/pde_rhs) -------------- */
+int marlpde_rhs_batch_dev(const double* d_y, const marlpde_column_params* d_params,
+                          int n_columns, int n_cells, double* d_out, void* stream);
+int marlpde_rhs_batch(const double* y, const marlpde_column_params* params,
+                      int n_columns, int n_cells, double* out, int device);
+
+/* ---- batched adaptive RK45 (replaces solve_ivp(method="RK45") per column) ---------------
+ *  d_y        [n_columns][5][n_cells]   in: state at state[c].t;  out: state at the time reached
+ *  d_state    [n_columns]               in/out, see marlpde_column_state
+ *  d_t_eval   [n_eval]                  increasing sample times within [t0, t_bound] (may be NULL)
+ *  d_snapshots[n_columns][n_eval][5][n_cells]  dense-output samples (quartic interpolant, as
+ *                                       scipy RkDenseOutput); rows >= state.next_eval are untouched
+ *  d_event_counts[n_columns][7]         number of roots found per monitor (accumulated)
+ *  d_event_times [n_columns][7][event_capacity]  root times (first event_capacity kept)
+ *  d_queue    one int32 work counter, must be 0 on entry (the kernel claims columns from it)
+ */
+int marlpde_rk45_integrate_dev(double* d_y, const marlpde_column_params* d_params,
+                               marlpde_column_state* d_state, int n_columns, int n_cells,
+                               const marlpde_rk45_options* opts, const double* d_t_eval,
+                               double* d_snapshots, int32_t* d_event_counts,
+                               double* d_event_times, int32_t* d_queue, void* stream);
+int marlpde_rk45_integrate(double* y, const marlpde_column_params* params,
+                           marlpde_column_state* state, int n_columns, int n_cells,
+                           const marlpde_rk45_options* opts, const double* t_eval,
+                           double* snapshots, int32_t* event_counts, double* event_times,
+                           int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARLPDE_B200_H */

@@ -1,0 +1,218 @@
+// cabi.cu — the extern "C" boundary declared in include/marlpde_b200.h.
+// Host-pointer entry points stage through device memory and synchronise; *_dev entry points
+// only enqueue work on the caller's stream.  There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/marlpde_b200.h"
+#include "rk45_persistent.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(MARLPDE_ECUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+#define CU(call)                                         \
+  do {                                                   \
+    cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);  \
+  } while (0)
+
+struct DevProps {
+  int sm_count = 0;
+  int smem_optin = 0;
+  bool ok = false;
+};
+
+int current_props(DevProps& p) {
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&p.sm_count, cudaDevAttrMultiProcessorCount, dev));
+  CU(cudaDeviceGetAttribute(&p.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  p.ok = true;
+  return MARLPDE_OK;
+}
+
+// RAII device buffer for the host-pointer entry points
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+  template <typename T> T* as() { return static_cast<T*>(p); }
+};
+
+int select_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(MARLPDE_ENODEVICE, "no CUDA device available (%s); this library has no CPU path",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(MARLPDE_EINVAL, "device %d out of range [0,%d)", device, n);
+  CU(cudaSetDevice(device));
+  return MARLPDE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int marlpde_abi_version(void) { return MARLPDE_ABI_VERSION; }
+
+const char* marlpde_last_error(void) { return g_err; }
+
+int marlpde_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int marlpde_get_device_info(int device, marlpde_device_info* info) {
+  if (!info) return fail(MARLPDE_EINVAL, "info is NULL");
+  int n = marlpde_device_count();
+  if (n == 0) return fail(MARLPDE_ENODEVICE, "no CUDA device available");
+  if (device < 0 || device >= n) return fail(MARLPDE_EINVAL, "device %d out of range [0,%d)", device, n);
+  cudaDeviceProp p;
+  CU(cudaGetDeviceProperties(&p, device));
+  std::memset(info, 0, sizeof(*info));
+  std::strncpy(info->name, p.name, sizeof(info->name) - 1);
+  info->sm_count = p.multiProcessorCount;
+  info->cc_major = p.major;
+  info->cc_minor = p.minor;
+  info->max_smem_per_block = (int32_t)p.sharedMemPerBlockOptin;
+  info->total_mem = (int64_t)p.totalGlobalMem;
+  return MARLPDE_OK;
+}
+
+int marlpde_rk45_max_cells(void) { return marlpde::kRk45MaxThreads; }
+
+int marlpde_rk45_columns_per_cta(int n_cells) {
+  // 227 KB is the sm_100 opt-in limit per CTA; the launcher re-checks against the real device.
+  return marlpde::rk45_columns_per_cta(n_cells, 227 * 1024);
+}
+
+int marlpde_rhs_batch_dev(const double* d_y, const marlpde_column_params* d_params, int n_columns,
+                          int n_cells, double* d_out, void* stream) {
+  if (n_columns < 0 || n_cells < 2) return fail(MARLPDE_EINVAL, "need n_columns >= 0 and n_cells >= 2");
+  if (n_columns == 0) return MARLPDE_OK;
+  if (!d_y || !d_params || !d_out) return fail(MARLPDE_EINVAL, "NULL device pointer");
+  cudaError_t e = marlpde::launch_rhs_batch(d_y, d_params, n_columns, n_cells, d_out, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "rhs_batch launch");
+  return MARLPDE_OK;
+}
+
+int marlpde_rhs_batch(const double* y, const marlpde_column_params* params, int n_columns, int n_cells,
+                      double* out, int device) {
+  if (n_columns < 0 || n_cells < 2) return fail(MARLPDE_EINVAL, "need n_columns >= 0 and n_cells >= 2");
+  if (n_columns == 0) return MARLPDE_OK;
+  if (!y || !params || !out) return fail(MARLPDE_EINVAL, "NULL pointer");
+  int rc = select_device(device);
+  if (rc) return rc;
+  const size_t nb = sizeof(double) * 5 * (size_t)n_cells * n_columns;
+  DevBuf dy, dp, dout;
+  CU(dy.alloc(nb));
+  CU(dout.alloc(nb));
+  CU(dp.alloc(sizeof(marlpde_column_params) * (size_t)n_columns));
+  CU(cudaMemcpy(dy.p, y, nb, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dp.p, params, sizeof(marlpde_column_params) * (size_t)n_columns, cudaMemcpyHostToDevice));
+  rc = marlpde_rhs_batch_dev(dy.as<double>(), dp.as<marlpde_column_params>(), n_columns, n_cells,
+                             dout.as<double>(), nullptr);
+  if (rc) return rc;
+  CU(cudaMemcpy(out, dout.p, nb, cudaMemcpyDeviceToHost));
+  return MARLPDE_OK;
+}
+
+static int check_rk45_args(int n_columns, int n_cells, const marlpde_rk45_options* opts) {
+  if (!opts) return fail(MARLPDE_EINVAL, "opts is NULL");
+  if (n_columns < 0) return fail(MARLPDE_EINVAL, "n_columns < 0");
+  if (n_cells < 32 || n_cells > marlpde::kRk45MaxThreads)
+    return fail(MARLPDE_EUNSUPPORTED, "on-chip RK45 kernel supports 32 <= n_cells <= %d (got %d)",
+                marlpde::kRk45MaxThreads, n_cells);
+  if (!(opts->rtol > 0.0) || !(opts->atol >= 0.0)) return fail(MARLPDE_EINVAL, "need rtol > 0, atol >= 0");
+  if (!(opts->max_step > 0.0)) return fail(MARLPDE_EINVAL, "max_step must be positive (use +inf for none)");
+  if (opts->n_eval < 0 || opts->event_capacity < 0) return fail(MARLPDE_EINVAL, "negative n_eval/event_capacity");
+  return MARLPDE_OK;
+}
+
+int marlpde_rk45_integrate_dev(double* d_y, const marlpde_column_params* d_params, marlpde_column_state* d_state,
+                               int n_columns, int n_cells, const marlpde_rk45_options* opts,
+                               const double* d_t_eval, double* d_snapshots, int32_t* d_event_counts,
+                               double* d_event_times, int32_t* d_queue, void* stream) {
+  int rc = check_rk45_args(n_columns, n_cells, opts);
+  if (rc) return rc;
+  if (n_columns == 0) return MARLPDE_OK;
+  if (!d_y || !d_params || !d_state || !d_queue) return fail(MARLPDE_EINVAL, "NULL device pointer");
+  if (opts->n_eval > 0 && (!d_t_eval || !d_snapshots)) return fail(MARLPDE_EINVAL, "n_eval > 0 needs t_eval and snapshots");
+  (void)d_event_counts;
+  (void)d_event_times;
+  DevProps props;
+  rc = current_props(props);
+  if (rc) return rc;
+  if (marlpde::rk45_columns_per_cta(n_cells, props.smem_optin) <= 0)
+    return fail(MARLPDE_EUNSUPPORTED, "n_cells=%d does not fit %d bytes of shared memory", n_cells, props.smem_optin);
+  cudaError_t e = marlpde::launch_rk45(d_y, d_params, d_state, n_columns, n_cells, *opts, d_t_eval, d_snapshots,
+                                       d_queue, props.sm_count, props.smem_optin, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "rk45 launch");
+  return MARLPDE_OK;
+}
+
+int marlpde_rk45_integrate(double* y, const marlpde_column_params* params, marlpde_column_state* state,
+                           int n_columns, int n_cells, const marlpde_rk45_options* opts, const double* t_eval,
+                           double* snapshots, int32_t* event_counts, double* event_times, int device) {
+  int rc = check_rk45_args(n_columns, n_cells, opts);
+  if (rc) return rc;
+  if (n_columns == 0) return MARLPDE_OK;
+  if (!y || !params || !state) return fail(MARLPDE_EINVAL, "NULL pointer");
+  if (opts->n_eval > 0 && (!t_eval || !snapshots)) return fail(MARLPDE_EINVAL, "n_eval > 0 needs t_eval and snapshots");
+  rc = select_device(device);
+  if (rc) return rc;
+  const size_t nb_y = sizeof(double) * 5 * (size_t)n_cells * n_columns;
+  const size_t nb_snap = nb_y * (size_t)opts->n_eval;
+  const size_t nb_ec = sizeof(int32_t) * MARLPDE_NEVENTS * (size_t)n_columns;
+  const size_t nb_et = sizeof(double) * MARLPDE_NEVENTS * (size_t)opts->event_capacity * n_columns;
+  DevBuf dy, dp, ds, dte, dsnap, dq, dec, det;
+  CU(dy.alloc(nb_y));
+  CU(dp.alloc(sizeof(marlpde_column_params) * (size_t)n_columns));
+  CU(ds.alloc(sizeof(marlpde_column_state) * (size_t)n_columns));
+  CU(dte.alloc(sizeof(double) * (size_t)opts->n_eval));
+  CU(dsnap.alloc(nb_snap));
+  CU(dq.alloc(sizeof(int32_t)));
+  CU(dec.alloc(nb_ec));
+  CU(det.alloc(nb_et));
+  CU(cudaMemcpy(dy.p, y, nb_y, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dp.p, params, sizeof(marlpde_column_params) * (size_t)n_columns, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ds.p, state, sizeof(marlpde_column_state) * (size_t)n_columns, cudaMemcpyHostToDevice));
+  if (opts->n_eval) CU(cudaMemcpy(dte.p, t_eval, sizeof(double) * (size_t)opts->n_eval, cudaMemcpyHostToDevice));
+  if (snapshots && nb_snap) CU(cudaMemcpy(dsnap.p, snapshots, nb_snap, cudaMemcpyHostToDevice));
+  CU(cudaMemset(dq.p, 0, sizeof(int32_t)));
+  if (event_counts) CU(cudaMemcpy(dec.p, event_counts, nb_ec, cudaMemcpyHostToDevice));
+  else CU(cudaMemset(dec.p, 0, nb_ec));
+  if (event_times && nb_et) CU(cudaMemcpy(det.p, event_times, nb_et, cudaMemcpyHostToDevice));
+  rc = marlpde_rk45_integrate_dev(dy.as<double>(), dp.as<marlpde_column_params>(), ds.as<marlpde_column_state>(),
+                                  n_columns, n_cells, opts, dte.as<double>(), dsnap.as<double>(),
+                                  dec.as<int32_t>(), det.as<double>(), dq.as<int32_t>(), nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(y, dy.p, nb_y, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(state, ds.p, sizeof(marlpde_column_state) * (size_t)n_columns, cudaMemcpyDeviceToHost));
+  if (snapshots && nb_snap) CU(cudaMemcpy(snapshots, dsnap.p, nb_snap, cudaMemcpyDeviceToHost));
+  if (event_counts) CU(cudaMemcpy(event_counts, dec.p, nb_ec, cudaMemcpyDeviceToHost));
+  if (event_times && nb_et) CU(cudaMemcpy(event_times, det.p, nb_et, cudaMemcpyDeviceToHost));
+  return MARLPDE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+// lheureux_device.cuh — per-cell right-hand side of L'Heureux's five diagenetic equations,
+// written for sm_100a fp64.  One call = one depth cell of one sediment column.
+//
+// Computes what the reference computes in LMAHeureuxPorosityDiff.pde_rhs
+// (marlpde/LHeureux_model.py:413-520) after its 13 py-pde stencil operators (:372-384):
+//   upwinded CA/CC advection by the sign of U (:418-423), Fiadeiro-Veronis weighted
+//   gradients for cCa, cCO3, Phi (:433-469), thresholded dissolution/precipitation
+//   rates coA, coC (:479-491) and the five rate formulas (:497-520).
+//
+// B200-first choices (not a transliteration):
+//   * the three stencils per field are formed from (minus, centre, plus) register values;
+//     ghost cells are synthesised by the edge threads, never stored;
+//   * of each pair of real powers ((1-min(x,1))^a, (max(x,1)-1)^b) at most one is non-zero,
+//     so one exp(e*log(.)) replaces two pow() calls, and it is skipped altogether where the
+//     dissolution mask zeroes it;
+//   * coth(Pe)-1/Pe is evaluated from one expm1 as (Pe(em+2)-em)/(Pe em): one division;
+//   * 1/Phi, 1/(1-Phi), 1/den are formed once and reused (the reference divides 27 times).
+// Rounding differs from the CPU path at the 1e-16 level (FMA contraction, reciprocal reuse);
+// the parity gate is |delta| <= 1e-12 * term-magnitude (tests/test_rhs_parity.py).
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+
+#include "../../include/marlpde_b200.h"
+
+namespace marlpde {
+
+// Derived per-column constants kept in shared memory by the kernels (broadcast reads).
+struct ColumnConsts {
+  double bc_top[5];
+  double inv_dx, inv_dx2;
+  double presum, rhorat, Da, lambda_, Da_lambda;
+  double dCa, dCO3, delta, KRat;
+  double nu1, nu2, m1, m2, n1, n2;
+  double dPhi;
+  double kPeCa, kPeCO3, kPePhi;   // delta_x/(2 dCa), delta_x/(2 dCO3), delta_x/(2 dPhi)
+  double Pe_min, Pe_max;
+  int32_t FV_switch, mask_lo, mask_hi, n_cells;
+};
+
+__host__ __device__ inline void make_consts(const marlpde_column_params& p, int n_cells, ColumnConsts& c) {
+  for (int f = 0; f < 5; ++f) c.bc_top[f] = p.bc_top[f];
+  c.inv_dx = p.inv_dx;
+  c.inv_dx2 = p.inv_dx2;
+  c.presum = p.presum;
+  c.rhorat = p.rhorat;
+  c.Da = p.Da;
+  c.lambda_ = p.lambda_;
+  c.Da_lambda = p.Da * p.lambda_;
+  c.dCa = p.dCa;
+  c.dCO3 = p.dCO3;
+  c.delta = p.delta;
+  c.KRat = p.KRat;
+  c.nu1 = p.nu1;
+  c.nu2 = p.nu2;
+  c.m1 = p.m1;
+  c.m2 = p.m2;
+  c.n1 = p.n1;
+  c.n2 = p.n2;
+  c.dPhi = p.dPhi_fixed;
+  c.kPeCa = p.delta_x / (2.0 * p.dCa);
+  c.kPeCO3 = p.delta_x / (2.0 * p.dCO3);
+  c.kPePhi = p.delta_x / (2.0 * p.dPhi_fixed);
+  c.Pe_min = p.Peclet_min;
+  c.Pe_max = p.Peclet_max;
+  c.FV_switch = p.FV_switch;
+  c.mask_lo = p.mask_lo;
+  c.mask_hi = p.mask_hi;
+  c.n_cells = n_cells;
+}
+
+// x^e for x >= 0 (the clamps of LHeureux_model.py:480-484 guarantee it), 0^e = 0 for e > 0.
+__device__ __forceinline__ double pow_nonneg(double x, double e) {
+  double r = exp(e * log(x));      // log(0) = -inf -> exp(-inf) = 0 ; NaN propagates
+  return (x == 0.0 && e == 0.0) ? 1.0 : r;
+}
+
+// Fiadeiro-Veronis weight, LHeureux_model.py:437-442 (calculate_sigma :147-160).
+__device__ __forceinline__ double fv_sigma(double Pe, double W, double Pe_min, double Pe_max) {
+  const double a = fabs(Pe);
+  if (a < Pe_min) return 0.0;
+  if (a > Pe_max) return (W > 0.0) ? 1.0 : ((W < 0.0) ? -1.0 : W);  // np.sign (keeps NaN / 0)
+  if (!(a <= Pe_max)) return Pe;                                   // NaN Peclet -> NaN weight
+  const double em = expm1(2.0 * Pe);                                 // coth = 1 + 2/em
+  return (Pe * (em + 2.0) - em) / (Pe * em);
+}
+
+struct CellRates {
+  double r[5];   // dCA/dt, dCC/dt, dcCa/dt, dcCO3/dt, dPhi/dt
+  double U, W;   // advection velocities at this cell (feed the event monitors e5, e6)
+};
+
+// c = centre values, m = cell i-1 (or top ghost), p = cell i+1 (or bottom ghost), field order
+// CA, CC, cCa, cCO3, Phi.  `in_mask` = not_too_deep*not_too_shallow != 0 for this cell.
+__device__ __forceinline__ void cell_rhs(const ColumnConsts& k, const double c[5], const double m[5],
+                                         const double p[5], bool in_mask, CellRates& out) {
+  const double CA = c[0], CC = c[1], cCa = c[2], cCO3 = c[3], Phi = c[4];
+
+  // ---- porosity-dependent velocities (:414-431)
+  const double rPhi = 1.0 / Phi;
+  const double F = 1.0 - exp(10.0 - 10.0 * rPhi);
+  const double omP = 1.0 - Phi;
+  const double Phi2 = Phi * Phi;
+  const double U = k.presum + k.rhorat * (Phi2 * Phi) * F / omP;
+  const double W = k.presum - k.rhorat * Phi2 * F;
+  const double den = 1.0 - 2.0 * log(Phi);
+  const double rden = 1.0 / den;
+
+  // ---- solids: first-order upwind by the sign of U (:418-423)
+  const bool back = U > 0.0;
+  const double gCA = (back ? (CA - m[0]) : (p[0] - CA)) * k.inv_dx;
+  const double gCC = (back ? (CC - m[1]) : (p[1] - CC)) * k.inv_dx;
+
+  // ---- Fiadeiro-Veronis weights (:433-462)
+  double sCa = 0.0, sCO3 = 0.0, sPhi = 0.0;
+  if (k.FV_switch) {
+    const double Wden = W * den;
+    sCa = fv_sigma(Wden * k.kPeCa, W, k.Pe_min, k.Pe_max);
+    sCO3 = fv_sigma(Wden * k.kPeCO3, W, k.Pe_min, k.Pe_max);
+    sPhi = fv_sigma(W * k.kPePhi, W, k.Pe_min, k.Pe_max);
+  }
+  // g = 0.5((1-s) gf + (1+s) gb) = 0.5 (gf + gb) - 0.5 s (gf - gb)   (:464-469)
+  const double hdx = 0.5 * k.inv_dx;
+  const double gCa = ((1.0 - sCa) * (p[2] - cCa) + (1.0 + sCa) * (cCa - m[2])) * hdx;
+  const double gCO3 = ((1.0 - sCO3) * (p[3] - cCO3) + (1.0 + sCO3) * (cCO3 - m[3])) * hdx;
+  const double gPhi = ((1.0 - sPhi) * (p[4] - Phi) + (1.0 + sPhi) * (Phi - m[4])) * hdx;
+  const double lapCa = (m[2] - 2.0 * cCa + p[2]) * k.inv_dx2;
+  const double lapCO3 = (m[3] - 2.0 * cCO3 + p[3]) * k.inv_dx2;
+  const double lapPhi = (m[4] - 2.0 * Phi + p[4]) * k.inv_dx2;
+
+  // ---- tortuosity-corrected diffusion (:471-477)
+  const double h1 = Phi * rden;
+  const double h2 = gPhi * (2.0 + den) * (rden * rden);
+  const double HCa = k.dCa * (h2 * gCa + h1 * lapCa);
+  const double HCO3 = k.dCO3 * (h2 * gCO3 + h1 * lapCO3);
+
+  // ---- reaction terms (:479-493): one real power per saturation product
+  const double two = cCa * cCO3;
+  const double three = two * k.KRat;
+  double coA;
+  if (three < 1.0) {
+    coA = in_mask ? CA * pow_nonneg(1.0 - three, k.m2) : CA * 0.0;
+  } else {
+    coA = -CA * k.nu1 * pow_nonneg(three - 1.0, k.m1);      // also carries NaN
+  }
+  double coC;
+  if (two < 1.0) {
+    coC = -CC * k.nu2 * pow_nonneg(1.0 - two, k.n2);
+  } else {
+    coC = CC * pow_nonneg(two - 1.0, k.n1);
+  }
+  const double h3 = coA - k.lambda_ * coC;
+  const double dWdx = -k.rhorat * gPhi * (2.0 * Phi * F + 10.0 * (F - 1.0));
+  const double react = k.Da * omP * h3;
+
+  out.r[0] = -U * gCA - k.Da * ((1.0 - CA) * coA + k.lambda_ * CA * coC);
+  out.r[1] = -U * gCC + k.Da * (k.lambda_ * (1.0 - CC) * coC + CC * coA);
+  out.r[2] = (HCa + react * (k.delta - cCa)) * rPhi - W * gCa;
+  out.r[3] = (HCO3 + react * (k.delta - cCO3)) * rPhi - W * gCO3;
+  out.r[4] = -(dWdx * Phi + W * gPhi) + k.dPhi * lapPhi + react;
+  out.U = U;
+  out.W = W;
+}
+
+// Load the (minus, centre, plus) triple for one cell from a field-major column in memory
+// (global or shared), synthesising the py-pde ghost cells (LHeureux_model.py:26-30):
+//   top, all fields:        value v        -> ghost = 2 v - a_0
+//   bottom, CA and CC:      curvature 0    -> ghost = 2 a_{N-1} - a_{N-2}
+//   bottom, cCa cCO3 Phi:   derivative 0   -> ghost = a_{N-1}
+template <typename Load>
+__device__ __forceinline__ void load_triple(const ColumnConsts& k, int cell, Load&& at, double c[5],
+                                            double m[5], double p[5]) {
+  const int n = k.n_cells;
+  const int im = cell > 0 ? cell - 1 : 0;
+  const int ip = cell < n - 1 ? cell + 1 : n - 1;
+#pragma unroll
+  for (int f = 0; f < 5; ++f) {
+    c[f] = at(f, cell);
+    m[f] = at(f, im);
+    p[f] = at(f, ip);
+  }
+  if (cell == 0) {
+#pragma unroll
+    for (int f = 0; f < 5; ++f) m[f] = 2.0 * k.bc_top[f] - c[f];
+  }
+  if (cell == n - 1) {
+    p[0] = 2.0 * c[0] - m[0];
+    p[1] = 2.0 * c[1] - m[1];
+    p[2] = c[2];
+    p[3] = c[3];
+    p[4] = c[4];
+  }
+}
+
+}  // namespace marlpde

@@ -1,0 +1,418 @@
+// rk45_persistent.cu — batched adaptive Dormand-Prince 5(4) for sediment columns, sm_100a.
+//
+// Replaces the loop `scipy.integrate.solve_ivp(eq.fun_numba, ..., method="RK45")`
+// (reference call site marlpde/Evolve_scenario.py:104-109; algorithm: scipy/integrate/_ivp/rk.py
+// `RungeKutta._step_impl`, `rk_step`, `RkDenseOutput`; ivp.py main loop for t_eval sampling).
+//
+// Design (B200-first):
+//   * persistent CTAs, one per SM; each CTA integrates C columns side by side ("slots"),
+//     thread <-> (slot, depth cell), so N=200 gives 600 of 608 lanes busy;
+//   * the whole integration of a column happens on-chip: state y and the running
+//     y_new / error accumulators live in registers, stage derivatives K1..K6 and a
+//     double-buffered stage-input tile live in shared memory (64 kB per column at N=200);
+//     HBM is touched only to load y0 and to store snapshots / the final state;
+//   * every column runs its own adaptive controller (own t, h, accept/reject); the error
+//     norm is a warp-shuffle reduction segmented by slot plus one shared-memory hop, summed
+//     in a fixed order so that all threads of a column take bit-identical decisions;
+//   * one block barrier per RHS evaluation (the stage tile is double buffered) and one for
+//     the norm: 7 barriers per step attempt;
+//   * finished slots claim the next column from a global atomic queue, so columns with
+//     different step counts do not leave SMs idle.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "lheureux_device.cuh"
+#include "rk45_persistent.cuh"
+
+namespace marlpde {
+
+namespace dp {  // Dormand-Prince coefficients, as scipy RK45.{A,B,E,P}
+constexpr double a21 = 1.0 / 5.0;
+constexpr double a31 = 3.0 / 40.0, a32 = 9.0 / 40.0;
+constexpr double a41 = 44.0 / 45.0, a42 = -56.0 / 15.0, a43 = 32.0 / 9.0;
+constexpr double a51 = 19372.0 / 6561.0, a52 = -25360.0 / 2187.0, a53 = 64448.0 / 6561.0,
+                 a54 = -212.0 / 729.0;
+constexpr double a61 = 9017.0 / 3168.0, a62 = -355.0 / 33.0, a63 = 46732.0 / 5247.0,
+                 a64 = 49.0 / 176.0, a65 = -5103.0 / 18656.0;
+constexpr double b1 = 35.0 / 384.0, b3 = 500.0 / 1113.0, b4 = 125.0 / 192.0,
+                 b5 = -2187.0 / 6784.0, b6 = 11.0 / 84.0;
+constexpr double e1 = -71.0 / 57600.0, e3 = 71.0 / 16695.0, e4 = -71.0 / 1920.0,
+                 e5 = 17253.0 / 339200.0, e6 = -22.0 / 525.0, e7 = 1.0 / 40.0;
+// dense output P[s][j], s = stage 1..7 (row 2 is zero), j = 0..3
+__constant__ double P[7][4] = {
+    {1.0, -8048581381.0 / 2820520608.0, 8663915743.0 / 2820520608.0, -12715105075.0 / 11282082432.0},
+    {0.0, 0.0, 0.0, 0.0},
+    {0.0, 131558114200.0 / 32700410799.0, -68118460800.0 / 10900136933.0, 87487479700.0 / 32700410799.0},
+    {0.0, -1754552775.0 / 470086768.0, 14199869525.0 / 1410260304.0, -10690763975.0 / 1880347072.0},
+    {0.0, 127303824393.0 / 49829197408.0, -318862633887.0 / 49829197408.0, 701980252875.0 / 199316789632.0},
+    {0.0, -282668133.0 / 205662961.0, 2019193451.0 / 616988883.0, -1453857185.0 / 822651844.0},
+    {0.0, 40617522.0 / 29380423.0, -110615467.0 / 29380423.0, 69997945.0 / 29380423.0}};
+constexpr double SAFETY = 0.9, MIN_FACTOR = 0.2, MAX_FACTOR = 10.0;
+}  // namespace dp
+
+// ---- shared memory carve-up -------------------------------------------------------------
+// K[6][5][T] | tile[2][5][T] | red[nwarps][2] | consts[C] | slot_col[C] | svc flag
+struct SmemLayout {
+  int T;        // C * N, padded to a multiple of 32
+  int nwarps;
+  int C;
+  size_t off_K, off_tile, off_red, off_consts, off_slot, total;
+};
+
+__host__ __device__ inline SmemLayout smem_layout(int C, int N) {
+  SmemLayout L;
+  L.C = C;
+  L.T = ((C * N + 31) / 32) * 32;
+  L.nwarps = L.T / 32;
+  size_t o = 0;
+  L.off_K = o;      o += sizeof(double) * 6 * 5 * (size_t)L.T;
+  L.off_tile = o;   o += sizeof(double) * 2 * 5 * (size_t)L.T;
+  L.off_red = o;    o += sizeof(double) * 2 * (size_t)L.nwarps;
+  L.off_consts = o; o += ((sizeof(ColumnConsts) + 15) / 16 * 16) * (size_t)C;
+  L.off_slot = o;   o += sizeof(int) * (size_t)(C + 4);
+  L.total = (o + 15) / 16 * 16;
+  return L;
+}
+
+int rk45_columns_per_cta(int n_cells, int smem_budget) {
+  if (n_cells < 32 || n_cells > kRk45MaxThreads) return 0;
+  int C = kRk45MaxThreads / n_cells;
+  while (C > 0 && smem_layout(C, n_cells).total > (size_t)smem_budget) --C;
+  return C;
+}
+
+size_t rk45_smem_bytes(int C, int n_cells) { return smem_layout(C, n_cells).total; }
+
+__global__ void __launch_bounds__(kRk45MaxThreads, 1)
+rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __restrict__ g_params,
+                       marlpde_column_state* __restrict__ g_state, int n_columns, int N, int C,
+                       marlpde_rk45_options opt, const double* __restrict__ g_t_eval,
+                       double* __restrict__ g_snap, int32_t* __restrict__ g_queue) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SmemLayout L = smem_layout(C, N);
+  const int T = L.T;
+  double* const sK = reinterpret_cast<double*>(smem_raw + L.off_K);        // [6][5][T]
+  double* const sTile = reinterpret_cast<double*>(smem_raw + L.off_tile);  // [2][5][T]
+  double* const sRed = reinterpret_cast<double*>(smem_raw + L.off_red);    // [nwarps][2]
+  const size_t consts_stride = (sizeof(ColumnConsts) + 15) / 16 * 16;
+  int* const sSlotCol = reinterpret_cast<int*>(smem_raw + L.off_slot);     // [C]
+  int* const sSvc = sSlotCol + C;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const bool active = tid < C * N;
+  const int slot = active ? tid / N : C;          // C = "no slot" for the padding lanes
+  const int cell = active ? tid - slot * N : 0;
+  const int base = slot * N;                       // first tile index of my column
+  const ColumnConsts& kc = *reinterpret_cast<const ColumnConsts*>(
+      smem_raw + L.off_consts + consts_stride * (active ? slot : 0));
+  // warp-segmented reduction bookkeeping
+  const int slotLo = (warp * 32 < C * N) ? (warp * 32) / N : C;
+  const int slotHi = (warp * 32 + 31 < C * N) ? (warp * 32 + 31) / N : C;
+  const bool straddle = slotLo != slotHi;
+  const int firstWarp = base >> 5;
+  const int lastWarp = (base + N - 1) >> 5;
+
+  // per-thread column state
+  int col = -1;                 // column index being integrated by my slot, -1 = idle
+  bool exhausted = false;       // the work queue ran dry
+  double y[5] = {0, 0, 0, 0, 0};
+  double t = 0.0, h_abs = 0.0, h = 0.0, t_new = 0.0, min_step = 0.0;
+  bool rejected = false;
+  int next_eval = 0;
+  long long n_acc = 0, n_rej = 0, nfev = 0, attempts_here = 0;
+
+  auto tileAt = [&](int b, int f, int i) -> double& { return sTile[(b * 5 + f) * T + i]; };
+  auto KAt = [&](int s, int f) -> double& { return sK[(s * 5 + f) * T + tid]; };
+
+  // RHS of my cell from stage tile `b`
+  auto eval_rhs = [&](int b, CellRates& out) {
+    double c[5], m[5], p[5];
+    load_triple(kc, cell, [&](int f, int i) { return tileAt(b, f, base + i); }, c, m, p);
+    cell_rhs(kc, c, m, p, cell >= kc.mask_lo && cell < kc.mask_hi, out);
+  };
+
+  // scipy _step_impl preamble for a new step + first attempt set-up. Returns false when the
+  // step size underflows (TOO_SMALL_STEP).
+  auto begin_step = [&]() {
+    min_step = 10.0 * fabs(nextafter(t, (double)INFINITY) - t);
+    if (h_abs > opt.max_step) h_abs = opt.max_step;
+    else if (h_abs < min_step) h_abs = min_step;
+    rejected = false;
+  };
+  auto begin_attempt = [&]() -> bool {
+    if (h_abs < min_step) return false;
+    h = h_abs;
+    t_new = t + h;
+    if (t_new - opt.t_bound > 0.0) t_new = opt.t_bound;
+    h = t_new - t;
+    h_abs = fabs(h);
+    return true;
+  };
+  auto retire = [&](int status) {  // store the column's end point and free the slot
+#pragma unroll
+    for (int f = 0; f < 5; ++f) g_y[((size_t)col * 5 + f) * N + cell] = y[f];
+    if (cell == 0) {
+      marlpde_column_state st;
+      st.t = t;
+      st.h_abs = h_abs;
+      st.n_accepted = n_acc;
+      st.n_rejected = n_rej;
+      st.nfev = nfev;
+      st.status = status;
+      st.next_eval = next_eval;
+      g_state[col] = st;
+    }
+    col = -1;
+  };
+  auto write_stage2 = [&]() {
+#pragma unroll
+    for (int f = 0; f < 5; ++f) tileAt(1, f, tid) = fma(h * dp::a21, KAt(0, f), y[f]);
+  };
+
+  if (tid == 0) *sSvc = 0;
+  __syncthreads();
+
+  for (;;) {
+    // ================= stage 2 input + slot service =======================================
+    if (col >= 0) write_stage2();
+    if (active && cell == 0 && col < 0 && !exhausted) *sSvc = 1;
+    const int nlive = __syncthreads_count(col >= 0);
+    if (*sSvc) {
+      // -- claim columns for idle slots
+      if (active && cell == 0 && col < 0 && !exhausted) {
+        const int c = atomicAdd(g_queue, 1);
+        sSlotCol[slot] = c < n_columns ? c : -1;
+      }
+      __syncthreads();
+      if (tid == 0) *sSvc = 0;
+      bool fresh = false;
+      if (active && col < 0 && !exhausted) {
+        col = sSlotCol[slot];
+        if (col < 0) {
+          exhausted = true;
+        } else {
+          fresh = true;
+          if (cell == 0) {
+            ColumnConsts tmp;
+            make_consts(g_params[col], N, tmp);
+            *const_cast<ColumnConsts*>(&kc) = tmp;
+          }
+          const marlpde_column_state st = g_state[col];
+          t = st.t;
+          h_abs = st.h_abs;
+          n_acc = st.n_accepted;
+          n_rej = st.n_rejected;
+          nfev = st.nfev;
+          next_eval = st.next_eval;
+          attempts_here = 0;
+#pragma unroll
+          for (int f = 0; f < 5; ++f) {
+            y[f] = g_y[((size_t)col * 5 + f) * N + cell];
+            tileAt(0, f, tid) = y[f];
+          }
+        }
+      }
+      __syncthreads();
+      if (fresh) {
+        if (t >= opt.t_bound) {            // nothing to integrate
+          retire(MARLPDE_STATUS_FINISHED);
+        } else {
+          CellRates r;
+          eval_rhs(0, r);
+#pragma unroll
+          for (int f = 0; f < 5; ++f) KAt(0, f) = r.r[f];
+          nfev += 1;
+          begin_step();
+          if (begin_attempt()) write_stage2();
+          else retire(MARLPDE_STATUS_STEP_TOO_SMALL);
+        }
+      }
+      __syncthreads();
+      continue;  // re-evaluate liveness / further idle slots at the top
+    }
+    if (nlive == 0) break;
+
+    // ================= stages 2..6 ========================================================
+    const bool live = col >= 0;
+    double accY[5], accE[5];
+    CellRates r;
+    if (live) {
+      // K2 = f(tile 1)
+      eval_rhs(1, r);
+#pragma unroll
+      for (int f = 0; f < 5; ++f) {
+        const double k1 = KAt(0, f), k2 = r.r[f];
+        KAt(1, f) = k2;
+        accY[f] = dp::b1 * k1;
+        accE[f] = dp::e1 * k1;
+        tileAt(0, f, tid) = fma(h, fma(dp::a32, k2, dp::a31 * k1), y[f]);
+      }
+    }
+    __syncthreads();
+    if (live) {
+      // K3 = f(tile 0)
+      eval_rhs(0, r);
+#pragma unroll
+      for (int f = 0; f < 5; ++f) {
+        const double k3 = r.r[f];
+        KAt(2, f) = k3;
+        accY[f] = fma(dp::b3, k3, accY[f]);
+        accE[f] = fma(dp::e3, k3, accE[f]);
+        const double s = fma(dp::a43, k3, fma(dp::a42, KAt(1, f), dp::a41 * KAt(0, f)));
+        tileAt(1, f, tid) = fma(h, s, y[f]);
+      }
+    }
+    __syncthreads();
+    if (live) {
+      // K4 = f(tile 1)
+      eval_rhs(1, r);
+#pragma unroll
+      for (int f = 0; f < 5; ++f) {
+        const double k4 = r.r[f];
+        KAt(3, f) = k4;
+        accY[f] = fma(dp::b4, k4, accY[f]);
+        accE[f] = fma(dp::e4, k4, accE[f]);
+        const double s = fma(dp::a54, k4, fma(dp::a53, KAt(2, f), fma(dp::a52, KAt(1, f), dp::a51 * KAt(0, f))));
+        tileAt(0, f, tid) = fma(h, s, y[f]);
+      }
+    }
+    __syncthreads();
+    if (live) {
+      // K5 = f(tile 0)
+      eval_rhs(0, r);
+#pragma unroll
+      for (int f = 0; f < 5; ++f) {
+        const double k5 = r.r[f];
+        KAt(4, f) = k5;
+        accY[f] = fma(dp::b5, k5, accY[f]);
+        accE[f] = fma(dp::e5, k5, accE[f]);
+        const double s = fma(dp::a65, k5, fma(dp::a64, KAt(3, f), fma(dp::a63, KAt(2, f),
+                         fma(dp::a62, KAt(1, f), dp::a61 * KAt(0, f)))));
+        tileAt(1, f, tid) = fma(h, s, y[f]);
+      }
+    }
+    __syncthreads();
+    if (live) {
+      // K6 = f(tile 1);  y_new = y + h * sum b_j K_j
+      eval_rhs(1, r);
+#pragma unroll
+      for (int f = 0; f < 5; ++f) {
+        const double k6 = r.r[f];
+        KAt(5, f) = k6;
+        accY[f] = fma(dp::b6, k6, accY[f]);
+        accE[f] = fma(dp::e6, k6, accE[f]);
+        tileAt(0, f, tid) = fma(h, accY[f], y[f]);
+      }
+    }
+    __syncthreads();
+    double part = 0.0;
+    if (live) {
+      // K7 = f(y_new) ; error estimate
+      eval_rhs(0, r);
+#pragma unroll
+      for (int f = 0; f < 5; ++f) {
+        const double ynew = fma(h, accY[f], y[f]);
+        const double err = h * fma(dp::e7, r.r[f], accE[f]);
+        const double scale = fma(fmax(fabs(y[f]), fabs(ynew)), opt.rtol, opt.atol);
+        const double q = err / scale;
+        part = fma(q, q, part);
+      }
+    }
+    // ---- segmented warp reduction of sum((err/scale)^2) per slot
+    {
+      double a = (slot == slotLo) ? part : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      double b = 0.0;
+      if (straddle) {
+        b = (slot == slotHi) ? part : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (lane == 0) {
+        sRed[warp * 2 + 0] = a;
+        sRed[warp * 2 + 1] = b;
+      }
+    }
+    __syncthreads();
+    if (live) {
+      double sum = 0.0;
+      for (int w = firstWarp; w <= lastWarp; ++w) {
+        const int lo = (w * 32) / N;
+        sum += sRed[w * 2 + (lo == slot ? 0 : 1)];
+      }
+      const double err_norm = sqrt(sum / (double)(5 * N));
+      nfev += 6;
+      attempts_here += 1;
+      if (err_norm < 1.0) {
+        double factor = dp::MAX_FACTOR;
+        if (err_norm != 0.0) factor = fmin(dp::MAX_FACTOR, dp::SAFETY * exp(-0.2 * log(err_norm)));
+        if (rejected) factor = fmin(1.0, factor);
+        // ---- dense output for t_eval points in (t, t_new] (ivp.py: searchsorted side='right')
+        while (next_eval < opt.n_eval) {
+          const double te = g_t_eval[next_eval];
+          if (!(te <= t_new)) break;
+          const double x = (te - t) / h;
+#pragma unroll
+          for (int f = 0; f < 5; ++f) {
+            double q[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              double s = dp::P[0][j] * KAt(0, f);
+#pragma unroll
+              for (int st = 2; st < 6; ++st) s = fma(dp::P[st][j], KAt(st, f), s);
+              q[j] = fma(dp::P[6][j], r.r[f], s);
+            }
+            const double poly = x * (q[0] + x * (q[1] + x * (q[2] + x * q[3])));
+            g_snap[(((size_t)col * opt.n_eval + next_eval) * 5 + f) * N + cell] = fma(h, poly, y[f]);
+          }
+          ++next_eval;
+        }
+        // ---- accept
+#pragma unroll
+        for (int f = 0; f < 5; ++f) {
+          y[f] = fma(h, accY[f], y[f]);
+          KAt(0, f) = r.r[f];           // FSAL
+        }
+        t = t_new;
+        h_abs *= factor;
+        n_acc += 1;
+        if (t >= opt.t_bound) {
+          retire(MARLPDE_STATUS_FINISHED);
+        } else if (opt.max_steps > 0 && attempts_here >= opt.max_steps) {
+          retire(MARLPDE_STATUS_STEP_BUDGET);
+        } else {
+          begin_step();
+          if (!begin_attempt()) retire(MARLPDE_STATUS_STEP_TOO_SMALL);
+        }
+      } else {
+        // NaN error norms land here too: fmax drops the NaN, like Python's max(0.2, nan)
+        h_abs *= fmax(dp::MIN_FACTOR, dp::SAFETY * exp(-0.2 * log(err_norm)));
+        rejected = true;
+        n_rej += 1;
+        if (!begin_attempt()) retire(MARLPDE_STATUS_STEP_TOO_SMALL);
+      }
+    }
+  }
+}
+
+cudaError_t launch_rk45(double* d_y, const marlpde_column_params* d_params, marlpde_column_state* d_state,
+                        int n_columns, int n_cells, const marlpde_rk45_options& opt, const double* d_t_eval,
+                        double* d_snap, int32_t* d_queue, int sm_count, int smem_budget, cudaStream_t stream) {
+  const int C = rk45_columns_per_cta(n_cells, smem_budget);
+  if (C <= 0) return cudaErrorInvalidValue;
+  const SmemLayout L = smem_layout(C, n_cells);
+  cudaError_t e = cudaFuncSetAttribute(rk45_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)L.total);
+  if (e != cudaSuccess) return e;
+  int grid = (n_columns + C - 1) / C;
+  if (grid > sm_count) grid = sm_count;
+  if (grid < 1) grid = 1;
+  rk45_persistent_kernel<<<grid, L.T, L.total, stream>>>(d_y, d_params, d_state, n_columns, n_cells, C, opt,
+                                                         d_t_eval, d_snap, d_queue);
+  return cudaGetLastError();
+}
+
+}  // namespace marlpde

@@ -1,0 +1,189 @@
+"""Batched entry points over the C ABI: one RHS call, or a whole adaptive RK45 integration,
+for many sediment columns at once.
+
+Two flavours per operation, chosen by the type of the state argument:
+  * numpy arrays  -> host-pointer ABI calls (`marlpde_rhs_batch`, `marlpde_rk45_integrate`):
+                     the library copies H2D, runs the kernels, copies D2H.  This is the path the
+                     reference-facing drop-in (`marlpde.integrate_equations`) and `bench.py`'s
+                     `e2e` number use.
+  * torch CUDA tensors -> device-pointer ABI calls (`*_dev`) on torch's current stream, with no
+                     allocation or synchronisation inside the library (sweeps that keep their
+                     columns resident in HBM, multi-GPU shards).
+PyTorch is only plumbing here (device memory, streams); all arithmetic is in csrc/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import PARAMS_DTYPE, STATE_DTYPE, NEVENTS
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _as_params(params) -> np.ndarray:
+    p = np.ascontiguousarray(params)
+    if p.dtype != PARAMS_DTYPE:
+        raise TypeError("params must come from marlpde_b200.derive_column_params")
+    return p.reshape(-1)
+
+
+def _check_y(y, n_columns):
+    if y.ndim != 3 or y.shape[0] != n_columns or y.shape[1] != 5:
+        raise ValueError(f"state must have shape (n_columns={n_columns}, 5, n_cells); got {tuple(y.shape)}")
+
+
+def params_to_device(params, device):
+    """Upload a params record array once (returns a uint8 CUDA tensor to pass back in)."""
+    import torch
+    p = _as_params(params)
+    return torch.from_numpy(p.view(np.uint8).copy()).to(device)
+
+
+def rhs_batch(y, params, out=None, device: int = 0):
+    """dy/dt for every column: y[B,5,N] -> out[B,5,N] (replaces fun_numba/pde_rhs per column,
+    marlpde/LHeureux_model.py:290-522)."""
+    lib = _cabi.lib()
+    if _is_torch(y):
+        import torch
+        if not y.is_cuda or y.dtype != torch.float64 or not y.is_contiguous():
+            raise ValueError("device path needs a contiguous float64 CUDA tensor")
+        d_params = params if _is_torch(params) else params_to_device(params, y.device)
+        B = d_params.numel() // PARAMS_DTYPE.itemsize
+        _check_y(y, B)
+        if out is None:
+            out = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _cabi.check(lib.marlpde_rhs_batch_dev(y.data_ptr(), d_params.data_ptr(), B, y.shape[2],
+                                                  out.data_ptr(), stream))
+        return out
+    p = _as_params(params)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    _check_y(y, p.shape[0])
+    if out is None:
+        out = np.empty_like(y)
+    _cabi.check(lib.marlpde_rhs_batch(_cabi.ptr(y), _cabi.ptr(p), p.shape[0], y.shape[2], _cabi.ptr(out), device))
+    return out
+
+
+@dataclass
+class RK45Result:
+    """Per-column results, the batched analogue of solve_ivp's OdeResult."""
+    y: object                    # [B,5,N] state at the time reached
+    t: np.ndarray                # [B] time reached
+    h_abs: np.ndarray            # [B] next step size the controller would use
+    status: np.ndarray           # [B] 0 finished, -1 step too small, 1 step budget exhausted (resumable)
+    n_accepted: np.ndarray
+    n_rejected: np.ndarray
+    nfev: np.ndarray
+    t_eval: np.ndarray           # [n_eval]
+    snapshots: object            # [B,n_eval,5,N] dense-output samples (rows < next_eval are valid)
+    next_eval: np.ndarray        # [B]
+    event_counts: np.ndarray = None   # [B,7]
+    event_times: np.ndarray = None    # [B,7,capacity]
+    state: np.ndarray = field(default=None, repr=False)  # raw marlpde_column_state records (for resuming)
+
+    @property
+    def n_attempts(self):
+        return self.n_accepted + self.n_rejected
+
+    def solutions(self, column: int) -> np.ndarray:
+        """(5, N, n_t) like `sol.y.reshape(5, N, -1)` in Evolve_scenario.py:168."""
+        snap = self.snapshots[column]
+        snap = snap.cpu().numpy() if _is_torch(snap) else np.asarray(snap)
+        return np.ascontiguousarray(np.transpose(snap[: int(self.next_eval[column])], (1, 2, 0)))
+
+
+def make_state(n_columns: int, t0=0.0, first_step=1e-6) -> np.ndarray:
+    st = np.zeros(n_columns, dtype=STATE_DTYPE)
+    st["t"] = t0
+    st["h_abs"] = first_step
+    return st
+
+
+def integrate_rk45_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e-3, atol=1e-3,
+                         t_eval=None, max_step=np.inf, max_steps: int = 0, events: bool = False,
+                         event_capacity: int = 0, state: np.ndarray | None = None,
+                         device: int = 0, inplace: bool = False) -> RK45Result:
+    """Adaptive Dormand-Prince RK45 for every column, SciPy `solve_ivp(method="RK45")` semantics
+    per column (call site marlpde/Evolve_scenario.py:104-109).
+
+    `first_step` follows SciPy's rule (validate_first_step): it is used verbatim and must be
+    positive and not exceed the interval.  `max_steps` > 0 bounds the step attempts per column in
+    this call; columns that hit it come back with status 1 and can be resumed by passing the
+    returned `.state` and `.y` back in.
+    """
+    lib = _cabi.lib()
+    t0, t_bound = float(t_span[0]), float(t_span[1])
+    if not t_bound > t0:
+        raise ValueError("only forward integration (t_span[1] > t_span[0]) is supported")
+    if state is None:
+        fs = np.asarray(first_step, dtype=np.float64)
+        if np.any(fs <= 0):
+            raise ValueError("`first_step` must be positive.")
+        if np.any(fs > abs(t_bound - t0)):
+            raise ValueError("`first_step` exceeds bounds.")
+    t_eval_arr = np.zeros(0) if t_eval is None else np.ascontiguousarray(t_eval, dtype=np.float64)
+    if t_eval_arr.ndim != 1:
+        raise ValueError("`t_eval` must be 1-dimensional.")
+    if t_eval_arr.size:
+        if np.any(t_eval_arr < t0) or np.any(t_eval_arr > t_bound):
+            raise ValueError("Values in `t_eval` are not within `t_span`.")
+        if np.any(np.diff(t_eval_arr) <= 0):
+            raise ValueError("Values in `t_eval` are not properly sorted.")
+    n_eval = int(t_eval_arr.size)
+    cap = int(event_capacity) if events else 0
+    opts = _cabi.RK45Options(t_bound=t_bound, rtol=float(rtol), atol=float(atol), max_step=float(max_step),
+                             max_steps=int(max_steps), n_eval=n_eval, event_capacity=cap,
+                             flags=_cabi.FLAG_EVENTS if events else 0, reserved=0)
+
+    if _is_torch(y0):
+        import torch
+        if not y0.is_cuda or y0.dtype != torch.float64 or not y0.is_contiguous():
+            raise ValueError("device path needs a contiguous float64 CUDA tensor")
+        dev = y0.device
+        d_params = params if _is_torch(params) else params_to_device(params, dev)
+        B = d_params.numel() // PARAMS_DTYPE.itemsize
+        _check_y(y0, B)
+        N = y0.shape[2]
+        st = make_state(B, t0, first_step) if state is None else np.ascontiguousarray(state, dtype=STATE_DTYPE)
+        y = y0 if inplace else y0.clone()
+        with torch.cuda.device(dev):
+            d_state = torch.from_numpy(st.view(np.uint8).copy()).to(dev)
+            d_te = torch.from_numpy(t_eval_arr.copy()).to(dev) if n_eval else None
+            d_snap = torch.empty((B, n_eval, 5, N), dtype=torch.float64, device=dev)
+            d_queue = torch.zeros(1, dtype=torch.int32, device=dev)
+            d_ec = torch.zeros((B, NEVENTS), dtype=torch.int32, device=dev)
+            d_et = torch.full((B, NEVENTS, max(cap, 1)), float("nan"), dtype=torch.float64, device=dev)
+            stream = torch.cuda.current_stream().cuda_stream
+            _cabi.check(lib.marlpde_rk45_integrate_dev(
+                y.data_ptr(), d_params.data_ptr(), d_state.data_ptr(), B, N, C.byref(opts),
+                d_te.data_ptr() if n_eval else None, d_snap.data_ptr(), d_ec.data_ptr(), d_et.data_ptr(),
+                d_queue.data_ptr(), stream))
+            st_out = d_state.cpu().numpy().view(STATE_DTYPE).reshape(B)   # synchronises the stream
+            ec, et = d_ec.cpu().numpy(), d_et.cpu().numpy()[:, :, :cap]
+        snaps = d_snap
+    else:
+        p = _as_params(params)
+        B = p.shape[0]
+        y = np.array(y0, dtype=np.float64, order="C", copy=not inplace)
+        _check_y(y, B)
+        N = y.shape[2]
+        st_out = make_state(B, t0, first_step) if state is None else np.array(state, dtype=STATE_DTYPE, copy=True)
+        snaps = np.full((B, n_eval, 5, N), np.nan)
+        ec = np.zeros((B, NEVENTS), dtype=np.int32)
+        et = np.full((B, NEVENTS, cap), np.nan)
+        _cabi.check(lib.marlpde_rk45_integrate(
+            _cabi.ptr(y), _cabi.ptr(p), _cabi.ptr(st_out), B, N, C.byref(opts),
+            _cabi.ptr(t_eval_arr) if n_eval else None, _cabi.ptr(snaps) if n_eval else None,
+            _cabi.ptr(ec), _cabi.ptr(et) if cap else None, device))
+    return RK45Result(y=y, t=st_out["t"].copy(), h_abs=st_out["h_abs"].copy(), status=st_out["status"].copy(),
+                      n_accepted=st_out["n_accepted"].copy(), n_rejected=st_out["n_rejected"].copy(),
+                      nfev=st_out["nfev"].copy(), t_eval=t_eval_arr, snapshots=snaps,
+                      next_eval=st_out["next_eval"].copy(), event_counts=ec, event_times=et, state=st_out)

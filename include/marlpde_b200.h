@@ -111,6 +111,10 @@ typedef struct marlpde_device_info {
 } marlpde_device_info;
 
 int marlpde_abi_version(void);
+/* sizeof() of the ABI structs as compiled into the library, for binding self-checks:
+ * which = 0 marlpde_column_params, 1 marlpde_rk45_options, 2 marlpde_column_state,
+ * 3 marlpde_device_info; anything else returns -1. */
+int marlpde_struct_size(int which);
 const char* marlpde_last_error(void);
 int marlpde_device_count(void);
 int marlpde_get_device_info(int device, marlpde_device_info* info);
@@ -146,6 +150,10 @@ int marlpde_rk45_integrate(double* y, const marlpde_column_params* params,
                            const marlpde_rk45_options* opts, const double* t_eval,
                            double* snapshots, int32_t* event_counts, double* event_times,
                            int device);
+
+/* ---- measurement helper: fp64 FMA peak (TFLOP/s, best of `repeats`) of `device`, the roofline
+ * denominator of the fp64-pipe-bound RK45 kernel (no reference counterpart). */
+int marlpde_probe_fp64_peak(int device, int iters, int repeats, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,16 @@ extern "C" {
 
 int marlpde_abi_version(void) { return MARLPDE_ABI_VERSION; }
 
+int marlpde_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(marlpde_column_params);
+    case 1: return (int)sizeof(marlpde_rk45_options);
+    case 2: return (int)sizeof(marlpde_column_state);
+    case 3: return (int)sizeof(marlpde_device_info);
+    default: return -1;
+  }
+}
+
 const char* marlpde_last_error(void) { return g_err; }
 
 int marlpde_device_count(void) {

@@ -12,8 +12,9 @@
 //     double-buffered stage-input tile live in shared memory (64 kB per column at N=200);
 //     HBM is touched only to load y0 and to store snapshots / the final state;
 //   * every column runs its own adaptive controller (own t, h, accept/reject); the error
-//     norm is a warp-shuffle reduction segmented by slot plus one shared-memory hop, summed
-//     in a fixed order so that all threads of a column take bit-identical decisions;
+//     norm is a warp-shuffle butterfly over aligned cell groups plus one shared-memory hop, summed
+//     in a fixed, slot-independent order: all threads of a column take bit-identical decisions
+//     and a column's trajectory does not depend on what else shares the CTA;
 //   * one block barrier per RHS evaluation (the stage tile is double buffered) and one for
 //     the norm: 7 barriers per step attempt;
 //   * finished slots claim the next column from a global atomic queue, so columns with
@@ -52,7 +53,7 @@ constexpr double SAFETY = 0.9, MIN_FACTOR = 0.2, MAX_FACTOR = 10.0;
 }  // namespace dp
 
 // ---- shared memory carve-up -------------------------------------------------------------
-// K[6][5][T] | tile[2][5][T] | red[nwarps][2] | consts[C] | slot_col[C] | svc flag
+// K[6][5][T] | tile[2][5][T] | grp[T] | consts[C] | slot_col[C] | svc flag
 struct SmemLayout {
   int T;        // C * N, padded to a multiple of 32
   int nwarps;
@@ -68,7 +69,7 @@ __host__ __device__ inline SmemLayout smem_layout(int C, int N) {
   size_t o = 0;
   L.off_K = o;      o += sizeof(double) * 6 * 5 * (size_t)L.T;
   L.off_tile = o;   o += sizeof(double) * 2 * 5 * (size_t)L.T;
-  L.off_red = o;    o += sizeof(double) * 2 * (size_t)L.nwarps;
+  L.off_red = o;    o += sizeof(double) * (size_t)L.T;   // group sums of the error norm (<= T/G used)
   L.off_consts = o; o += ((sizeof(ColumnConsts) + 15) / 16 * 16) * (size_t)C;
   L.off_slot = o;   o += sizeof(int) * (size_t)(C + 4);
   L.total = (o + 15) / 16 * 16;
@@ -86,7 +87,7 @@ size_t rk45_smem_bytes(int C, int n_cells) { return smem_layout(C, n_cells).tota
 
 __global__ void __launch_bounds__(kRk45MaxThreads, 1)
 rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __restrict__ g_params,
-                       marlpde_column_state* __restrict__ g_state, int n_columns, int N, int C,
+                       marlpde_column_state* __restrict__ g_state, int n_columns, int N, int C, int logG,
                        marlpde_rk45_options opt, const double* __restrict__ g_t_eval,
                        double* __restrict__ g_snap, int32_t* __restrict__ g_queue) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -94,25 +95,25 @@ rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __
   const int T = L.T;
   double* const sK = reinterpret_cast<double*>(smem_raw + L.off_K);        // [6][5][T]
   double* const sTile = reinterpret_cast<double*>(smem_raw + L.off_tile);  // [2][5][T]
-  double* const sRed = reinterpret_cast<double*>(smem_raw + L.off_red);    // [nwarps][2]
+  double* const sGrp = reinterpret_cast<double*>(smem_raw + L.off_red);    // [T / G]
   const size_t consts_stride = (sizeof(ColumnConsts) + 15) / 16 * 16;
   int* const sSlotCol = reinterpret_cast<int*>(smem_raw + L.off_slot);     // [C]
   int* const sSvc = sSlotCol + C;
 
   const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
   const bool active = tid < C * N;
   const int slot = active ? tid / N : C;          // C = "no slot" for the padding lanes
   const int cell = active ? tid - slot * N : 0;
   const int base = slot * N;                       // first tile index of my column
   const ColumnConsts& kc = *reinterpret_cast<const ColumnConsts*>(
       smem_raw + L.off_consts + consts_stride * (active ? slot : 0));
-  // warp-segmented reduction bookkeeping
-  const int slotLo = (warp * 32 < C * N) ? (warp * 32) / N : C;
-  const int slotHi = (warp * 32 + 31 < C * N) ? (warp * 32 + 31) / N : C;
-  const bool straddle = slotLo != slotHi;
-  const int firstWarp = base >> 5;
-  const int lastWarp = (base + N - 1) >> 5;
+  // Error-norm reduction tree, identical for every slot so that a column's trajectory does not
+  // depend on where it is scheduled: cells are summed in aligned groups of G = 2^k lanes
+  // (G = largest power of two <= 32 dividing N, hence dividing every slot base) by an xor
+  // butterfly, then the N/G group sums are added in cell order from shared memory.
+  const int G = 1 << logG;
+  const int nGroups = N >> logG;
+  const int grpBase = base >> logG;
 
   // per-thread column state
   int col = -1;                 // column index being integrated by my slot, -1 = idle
@@ -320,29 +321,26 @@ rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __
         part = fma(q, q, part);
       }
     }
-    // ---- segmented warp reduction of sum((err/scale)^2) per slot
+    // ---- sum((err/scale)^2) over the column: butterfly inside aligned groups of G cells ...
     {
-      double a = (slot == slotLo) ? part : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      double b = 0.0;
-      if (straddle) {
-        b = (slot == slotHi) ? part : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
-      }
-      if (lane == 0) {
-        sRed[warp * 2 + 0] = a;
-        sRed[warp * 2 + 1] = b;
-      }
+      double a = part;
+      for (int o = G >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (live && (cell & (G - 1)) == 0) sGrp[tid >> logG] = a;
     }
     __syncthreads();
     if (live) {
-      double sum = 0.0;
-      for (int w = firstWarp; w <= lastWarp; ++w) {
-        const int lo = (w * 32) / N;
-        sum += sRed[w * 2 + (lo == slot ? 0 : 1)];
+      // ... then the group sums in cell order (4 interleaved partial sums, fixed association)
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      const double* gp = sGrp + grpBase;
+      int gi = 0;
+      for (; gi + 4 <= nGroups; gi += 4) {
+        s0 += gp[gi];
+        s1 += gp[gi + 1];
+        s2 += gp[gi + 2];
+        s3 += gp[gi + 3];
       }
+      for (; gi < nGroups; ++gi) s0 += gp[gi];
+      const double sum = (s0 + s1) + (s2 + s3);
       const double err_norm = sqrt(sum / (double)(5 * N));
       nfev += 6;
       attempts_here += 1;
@@ -403,6 +401,8 @@ cudaError_t launch_rk45(double* d_y, const marlpde_column_params* d_params, marl
                         double* d_snap, int32_t* d_queue, int sm_count, int smem_budget, cudaStream_t stream) {
   const int C = rk45_columns_per_cta(n_cells, smem_budget);
   if (C <= 0) return cudaErrorInvalidValue;
+  int logG = 0;
+  while (logG < 5 && (n_cells % (2 << logG)) == 0) ++logG;
   const SmemLayout L = smem_layout(C, n_cells);
   cudaError_t e = cudaFuncSetAttribute(rk45_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)L.total);
@@ -410,7 +410,7 @@ cudaError_t launch_rk45(double* d_y, const marlpde_column_params* d_params, marl
   int grid = (n_columns + C - 1) / C;
   if (grid > sm_count) grid = sm_count;
   if (grid < 1) grid = 1;
-  rk45_persistent_kernel<<<grid, L.T, L.total, stream>>>(d_y, d_params, d_state, n_columns, n_cells, C, opt,
+  rk45_persistent_kernel<<<grid, L.T, L.total, stream>>>(d_y, d_params, d_state, n_columns, n_cells, C, logG, opt,
                                                          d_t_eval, d_snap, d_queue);
   return cudaGetLastError();
 }

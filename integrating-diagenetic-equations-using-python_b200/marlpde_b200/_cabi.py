@@ -64,6 +64,7 @@ assert STATE_DTYPE.itemsize == C.sizeof(ColumnState)
 _P = C.c_void_p
 SYMBOLS = {
     "marlpde_abi_version": (C.c_int, []),
+    "marlpde_struct_size": (C.c_int, [C.c_int]),
     "marlpde_last_error": (C.c_char_p, []),
     "marlpde_device_count": (C.c_int, []),
     "marlpde_get_device_info": (C.c_int, [C.c_int, C.POINTER(DeviceInfo)]),
@@ -73,6 +74,7 @@ SYMBOLS = {
     "marlpde_rhs_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int]),
     "marlpde_rk45_integrate_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(RK45Options),
                                              _P, _P, _P, _P, _P, _P]),
+    "marlpde_probe_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "marlpde_rk45_integrate": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(RK45Options),
                                          _P, _P, _P, _P, C.c_int]),
 }
@@ -100,6 +102,9 @@ def lib() -> C.CDLL:
             fn.argtypes = args
         if handle.marlpde_abi_version() != 1:
             raise MarlpdeError("ABI version mismatch between _cabi.py and libmarlpde_b200.so")
+        for which, struct in enumerate((ColumnParams, RK45Options, ColumnState, DeviceInfo)):
+            if handle.marlpde_struct_size(which) != C.sizeof(struct):
+                raise MarlpdeError(f"struct layout mismatch for {struct.__name__}")
         _lib = handle
     return _lib
 

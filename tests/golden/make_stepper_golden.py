@@ -60,6 +60,14 @@ def main():
     with ProcessPoolExecutor(max_workers=min(8, os.cpu_count())) as ex:
         for res in ex.map(run, jobs):
             out.update(res)
+    # CPU-vs-CPU round-off sensitivity of the Matlab case: first_step * (1 + 1e-9).  Its cCO3 boundary
+    # layer (top ~15 cells) moves by up to 1.3e-2 and nfev by 354: the noise floor any second
+    # implementation of the same stepper (the GPU one) is compared against.
+    import lheureux_oracle as o
+    pde = o.default_scenario() | CASES["matlab"][0]
+    sol = o.integrate(pde, method="RK45", first_step=1e-6 * (1 + 1e-9), events=False)
+    out["matlab/RK45/t1/tol0.001/y_end_first_step_times_1p000000001"] = sol.y[:, -1].reshape(5, -1)
+    out["matlab/RK45/t1/tol0.001/nfev_first_step_times_1p000000001"] = np.array(sol.nfev)
     out["__cases__"] = np.array(json.dumps({k: {"overrides": v[0], "first_step": v[1]} for k, v in CASES.items()}))
     np.savez_compressed(os.path.join(HERE, "stepper_reference.npz"), **out)
 

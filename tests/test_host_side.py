@@ -1,0 +1,135 @@
+"""Host logic: per-column constants, sweep lattice, HDF5 writer/reader, C-ABI surface (no compute)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import lheureux_oracle as oracle
+import marlpde_b200 as mb
+from marlpde_b200 import _cabi, hdf5lite
+from conftest import ROOT
+
+np.seterr(all="ignore")
+
+
+def test_column_params_equal_oracle_and_reference(rhs_golden):
+    g, meta = rhs_golden
+    for name, pde in meta.items():
+        P = mb.derive_column_params(pde)
+        assert P.shape == (1,)
+        po = oracle.kernel_params(pde)
+        for k in ("presum", "rhorat", "Da", "lambda_", "dCa", "dCO3", "delta", "KRat", "nu1", "nu2", "m1", "m2",
+                  "n1", "n2", "dPhi_fixed", "dx", "delta_x", "Peclet_min", "Peclet_max"):
+            assert P[k][0] == po[oracle.P_IDX[k]], (name, k)
+        assert P["inv_dx2"][0] == po[oracle.P_IDX["dx_m2"]]
+        assert (P["mask_lo"][0], P["mask_hi"][0]) == (po[oracle.P_IDX["mask_lo"]], po[oracle.P_IDX["mask_hi"]])
+        assert np.array_equal(P["bc_top"][0], po[:5])
+        assert bool(P["FV_switch"][0]) == bool(pde["FV_switch"])
+        ref = g[f"{name}/derived"]        # the reference's own __init__ values
+        assert np.array_equal([P[k][0] for k in ("presum", "rhorat", "Da", "lambda_", "dCa", "dCO3", "delta",
+                                                 "KRat", "nu1", "nu2", "dPhi_fixed", "delta_x")], ref[:12])
+
+
+def test_sweep_lattice_is_vectorised_map_scenario():
+    base = oracle.default_scenario()
+    pde = mb.sweep_lattice(base, 4, 3, 2)
+    P = mb.derive_column_params(pde)
+    y0 = mb.initial_state(pde)
+    assert P.shape == (24,) and y0.shape == (24, 5, 200)
+    # column c = (i*3 + j)*2 + k ; spot-check one column against the scalar derivation
+    i, j, k = 2, 1, 1
+    c = (i * 3 + j) * 2 + k
+    raw = {kk: base[kk] for kk in base}
+    raw.update(sedimentationrate=0.09 + 0.02 * i / 3, b=(4 + 2 * j / 2) / 1e4, DCO3=245 + 55 * k / 1)
+    raw["Xstar"] = raw["D0Ca"] / raw["sedimentationrate"]
+    raw["Tstar"] = raw["Xstar"] / raw["sedimentationrate"]
+    one = mb.derive_column_params(raw)
+    for name in P.dtype.names:
+        assert np.array_equal(P[name][c], one[name][0]), name
+    assert np.all(P["mask_hi"] > P["mask_lo"])
+
+
+def test_params_validation():
+    pde = oracle.default_scenario()
+    bad = dict(pde)
+    del bad["KC"]
+    with pytest.raises(KeyError):
+        mb.derive_column_params(bad)
+    with pytest.raises(ValueError):
+        mb.derive_column_params(pde | {"m1": 0.0})
+
+
+def test_hdf5_roundtrip_layout_of_the_reference_driver(tmp_path):
+    """Same dataset names/shapes/attrs as Evolve_scenario.py:170-178."""
+    p = tmp_path / "LMAHeureuxPorosityDiff.hdf5"
+    sol = np.arange(5 * 7 * 3, dtype=float).reshape(5, 7, 3)
+    attrs = {"method": "RK45", "rtol": 1e-3, "N": 200, "dense_output": False, "t_span": (0, 1),
+             "t_eval": np.linspace(0, 1, 3), "cCa0": np.float64(0.499), "first_step": 1e-6}
+    with hdf5lite.File(p, "w") as f:
+        f.create_dataset("solutions", data=sol)
+        f.create_dataset("times", data=np.linspace(0, 1, 3))
+        for k in range(7):
+            f.create_dataset(f"event_{k}", data=np.array([]) if k != 6 else np.array([0.25, 0.5]))
+        f.attrs.update(attrs)
+    raw = p.read_bytes()
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n" and raw[8] == 0            # superblock v0
+    assert int.from_bytes(raw[40:48], "little") == len(raw)            # end-of-file address
+    with hdf5lite.File(p, "r") as f:
+        assert sorted(f.keys()) == sorted(["solutions", "times"] + [f"event_{k}" for k in range(7)])
+        assert np.array_equal(f["solutions"][:, :, -1], sol[:, :, -1])
+        assert f.get("solutions").shape == (5, 7, 3)
+        assert f["event_0"].shape == (0,) and np.array_equal(f["event_6"][:], [0.25, 0.5])
+        assert f.attrs["method"] == "RK45" and f.attrs["N"] == 200 and f.attrs["dense_output"] == False  # noqa: E712
+        assert np.array_equal(f.attrs["t_span"], [0, 1]) and f.attrs["first_step"] == 1e-6
+        assert f.get("nope") is None
+        with pytest.raises(OSError):
+            f.attrs.update({"x": 1})
+
+
+def test_cabi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "marlpde_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(marlpde_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    L = _cabi.lib()
+    assert L.marlpde_abi_version() == 1
+    assert L.marlpde_struct_size(0) == _cabi.PARAMS_DTYPE.itemsize == 224
+    assert L.marlpde_struct_size(2) == _cabi.STATE_DTYPE.itemsize == 48
+    assert L.marlpde_struct_size(9) == -1
+    assert L.marlpde_rk45_max_cells() == 640
+    assert L.marlpde_rk45_columns_per_cta(200) == 3
+    assert L.marlpde_rk45_columns_per_cta(640) == 1
+    assert L.marlpde_rk45_columns_per_cta(641) == 0 and L.marlpde_rk45_columns_per_cta(16) == 0
+
+
+def test_no_device_fails_loudly():
+    """The product has no CPU fallback: on a box without a GPU compute calls must raise."""
+    if _cabi.lib().marlpde_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    pde = oracle.default_scenario()
+    with pytest.raises(_cabi.MarlpdeError, match="no CUDA device"):
+        mb.rhs_batch(mb.initial_state(pde), mb.derive_column_params(pde))
+    with pytest.raises(_cabi.MarlpdeError, match="no CUDA device"):
+        mb.integrate_rk45_batch(mb.initial_state(pde), mb.derive_column_params(pde), t_span=(0, 1e-4))
+
+
+def test_argument_validation_before_any_device_work():
+    pde = oracle.default_scenario()
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    with pytest.raises(ValueError, match="first_step"):
+        mb.integrate_rk45_batch(y0, P, first_step=0.0)
+    with pytest.raises(ValueError, match="exceeds bounds"):
+        mb.integrate_rk45_batch(y0, P, first_step=2.0)
+    with pytest.raises(ValueError, match="not within"):
+        mb.integrate_rk45_batch(y0, P, t_eval=[0.0, 2.0])
+    with pytest.raises(ValueError, match="sorted"):
+        mb.integrate_rk45_batch(y0, P, t_eval=[0.5, 0.25])
+    with pytest.raises(ValueError):
+        mb.rhs_batch(y0[:, :4], P)
+    opts = _cabi.RK45Options(t_bound=1.0, rtol=1e-3, atol=1e-3, max_step=float("inf"))
+    rc = _cabi.lib().marlpde_rk45_integrate(None, None, None, 1, 1000, ctypes.byref(opts), None, None, None, None, 0)
+    assert rc == -4 and b"n_cells" in _cabi.lib().marlpde_last_error()

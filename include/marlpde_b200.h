@@ -154,6 +154,9 @@ int marlpde_rk45_integrate(double* y, const marlpde_column_params* params,
 /* ---- measurement helper: fp64 FMA peak (TFLOP/s, best of `repeats`) of `device`, the roofline
  * denominator of the fp64-pipe-bound RK45 kernel (no reference counterpart). */
 int marlpde_probe_fp64_peak(int device, int iters, int repeats, double* tflops);
+/* test helper: element-wise evaluation of the kernels' own fp64 maths (csrc/fp64_math.cuh) on HOST
+ * arrays: op 0 log, 1 exp, 2 expm1, 3 reciprocal, 4 (1+x)/x, 5 Fiadeiro-Veronis coth(x)-1/x. */
+int marlpde_probe_math(int op, const double* x, int n, double* out, int device);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,130 @@
+// fp64_math.cuh — table-driven fp64 log / exp / expm1 and Newton reciprocals for sm_100a.
+//
+// Why not libdevice: the RHS needs 3 log, 3-4 exp, 1-3 coth and ~6 divisions per cell per
+// evaluation; CUDA's generic implementations cost 31 / 18 / 45 / 13 fp64-pipe instructions each
+// and materialise every polynomial coefficient with two UMOVs (ncu, profiles/): the kernel was
+// issue-bound and its 200 KB of SASS thrashed the instruction cache.  These versions use
+// 128- and 64-entry tables (staged in shared memory by the caller) and short polynomials whose
+// coefficients sit in constant memory:  log 12, exp 10, expm1 13, reciprocal 4 fp64 instructions.
+// Accuracy (tests/test_gpu_math.py): log  |err| <= 2e-16 * max(1, |log x|)   (absolute, not ulp:
+// it feeds 1-2ln(Phi), m*log(x) and the step controller, never a result near zero),
+// exp <= 3e-16 relative, expm1 <= 4e-16 relative for |x| >= 1e-2, rcp/div <= 2.3e-16 relative.
+// Arguments outside the fast range (zero, negative, denormal, inf, NaN, |x| >= 690 for exp)
+// branch to libdevice, so IEEE special values are preserved.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+
+namespace marlpde {
+namespace fm {
+
+#include "fp64_tables.inc"
+
+// polynomial coefficients (constant bank -> uniform registers, two per LDCU.128)
+__constant__ double kLog1pC[6] = {-0.5, 1.0 / 3.0, -0.25, 0.2, -1.0 / 6.0, 1.0 / 7.0};
+__constant__ double kExpC[5] = {0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0};
+
+struct Tables {            // shared-memory copies (random-index reads would serialise in the constant cache)
+  const double2* logtab;   // [128] {ic, L}
+  const double2* exptab;   // [64]  {Thi, Tlo}
+};
+constexpr int kTableBytes = (128 + 64) * 16;
+
+// cooperative copy constant -> shared; call with all threads of the CTA, then __syncthreads()
+__device__ __forceinline__ Tables stage_tables(void* smem, int tid, int nthreads) {
+  double2* lt = reinterpret_cast<double2*>(smem);
+  double2* et = lt + 128;
+  for (int i = tid; i < 128; i += nthreads) lt[i] = make_double2(kLogTab[i][0], kLogTab[i][1]);
+  for (int i = tid; i < 64; i += nthreads) et[i] = make_double2(kExpTab[i][0], kExpTab[i][1]);
+  return Tables{lt, et};
+}
+
+// Out-of-range arguments are rare: one shared, never-inlined copy of each libdevice fallback
+// keeps the hot code small (the instruction cache matters more than these calls).
+static __device__ __noinline__ double slow_log(double x) { return ::log(x); }
+static __device__ __noinline__ double slow_exp(double x) { return ::exp(x); }
+static __device__ __noinline__ double slow_expm1(double x) { return ::expm1(x); }
+
+// 1/x: MUFU.RCP64H seed (~2^-22) + two Newton steps. x must be a finite normal non-zero number;
+// 0, inf, NaN give NaN/inf garbage that stays non-finite.
+__device__ __forceinline__ double rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
+// a/b with one residual correction (<= 1 ulp for normal operands)
+__device__ __forceinline__ double div(double a, double b) {
+  const double r = rcp(b);
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);
+}
+
+__device__ __forceinline__ double log(const Tables& tb, double x) {
+  const int hi = __double2hiint(x);
+  // fast range: positive normal finite  <=>  0x00100000 <= hi < 0x7ff00000
+  if (__builtin_expect((unsigned)(hi - 0x00100000) >= 0x7fe00000u, 0)) return slow_log(x);
+  const int e = (hi >> 20) - 1023;
+  const int j = (hi >> 13) & 127;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+  const double2 t = tb.logtab[j];
+  const double r = fma(m, t.x, -1.0);                    // |r| <= 2^-8, exact up to 2^-61
+  double p = fma(kLog1pC[5], r, kLog1pC[4]);
+  p = fma(p, r, kLog1pC[3]);
+  p = fma(p, r, kLog1pC[2]);
+  p = fma(p, r, kLog1pC[1]);
+  p = fma(p, r, kLog1pC[0]);
+  const double l1p = fma(r * r, p, r);                   // log1p(r)
+  const double ed = (double)e;
+  return fma(ed, kLn2Hi, t.y) + fma(ed, kLn2Lo, l1p);
+}
+
+// shared core of exp/expm1: x = (64 k + j) ln2/64 + r ; returns p = expm1(r), sets scale 2^k T_j.
+// Degree 5 leaves r^6/720 <= 3.5e-17 relative to exp(r) ~ 1; expm1 needs it relative to r, so it
+// takes the r^6 term as well (kExtraTerm).
+template <bool kExtraTerm>
+__device__ __forceinline__ double exp_core(const Tables& tb, double x, double2& T, int& k) {
+  const double magic = 6755399441055744.0;              // 1.5 * 2^52: round-to-nearest-int trick
+  const double tn = fma(x, k64_Ln2, magic);
+  const int n = __double2loint(tn);
+  const double nf = tn - magic;
+  double r = fma(nf, -kLn2_64Hi, x);
+  r = fma(nf, -kLn2_64Lo, r);                            // |r| <= ln2/128
+  T = tb.exptab[n & 63];
+  k = n >> 6;
+  double p = kExtraTerm ? fma(kExpC[4], r, kExpC[3]) : kExpC[3];
+  p = fma(p, r, kExpC[2]);
+  p = fma(p, r, kExpC[1]);
+  p = fma(p, r, kExpC[0]);
+  return fma(r * r, p, r);
+}
+
+__device__ __forceinline__ double scale2(double v, int k) {  // v * 2^k for results that stay normal
+  return __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
+}
+
+__device__ __forceinline__ double exp(const Tables& tb, double x) {
+  if (__builtin_expect(!(fabs(x) < 690.0), 0)) return slow_exp(x);
+  double2 T;
+  int k;
+  const double p = exp_core<false>(tb, x, T, k);
+  return scale2(fma(T.x, p, T.x), k);
+}
+
+__device__ __forceinline__ double expm1(const Tables& tb, double x) {
+  if (__builtin_expect(!(fabs(x) < 600.0), 0)) return slow_expm1(x);
+  double2 T;
+  int k;
+  const double p = exp_core<true>(tb, x, T, k);
+  const double sc = __hiloint2double((k + 1023) << 20, 0);   // 2^k, |k| <= 866 here
+  const double s = T.x * sc;                               // exact
+  const double sl = T.y * sc;                              // exact (Tlo may be 0)
+  return fma(s, p, s - 1.0) + fma(sl, p, sl);
+}
+
+}  // namespace fm
+}  // namespace marlpde

@@ -14,7 +14,9 @@
 //     so one exp(e*log(.)) replaces two pow() calls, and it is skipped altogether where the
 //     dissolution mask zeroes it;
 //   * coth(Pe)-1/Pe is evaluated from one expm1 as (Pe(em+2)-em)/(Pe em): one division;
-//   * 1/Phi, 1/(1-Phi), 1/den are formed once and reused (the reference divides 27 times).
+//   * 1/Phi, 1/den are formed once and reused (the reference divides 27 times);
+//   * log/exp/expm1/reciprocals are the table-driven versions of fp64_math.cuh (about a third of
+//     libdevice's fp64-pipe instructions, coefficients in constant memory instead of UMOV pairs).
 // Rounding differs from the CPU path at the 1e-16 level (FMA contraction, reciprocal reuse);
 // the parity gate is |delta| <= 1e-12 * term-magnitude (tests/test_rhs_parity.py).
 #pragma once
@@ -23,6 +25,7 @@
 #include <cstdint>
 
 #include "../../include/marlpde_b200.h"
+#include "fp64_math.cuh"
 
 namespace marlpde {
 
@@ -70,20 +73,20 @@ __host__ __device__ inline void make_consts(const marlpde_column_params& p, int 
   c.n_cells = n_cells;
 }
 
-// x^e for x >= 0 (the clamps of LHeureux_model.py:480-484 guarantee it), 0^e = 0 for e > 0.
-__device__ __forceinline__ double pow_nonneg(double x, double e) {
-  double r = exp(e * log(x));      // log(0) = -inf -> exp(-inf) = 0 ; NaN propagates
-  return (x == 0.0 && e == 0.0) ? 1.0 : r;
+// x^e for x >= 0 (the clamps of LHeureux_model.py:480-484 guarantee it) and e > 0 (validated on
+// the host): exp(e log x); log(0) = -inf -> exp(-inf) = 0 ; NaN propagates.
+__device__ __forceinline__ double pow_nonneg(const fm::Tables& tb, double x, double e) {
+  return fm::exp(tb, e * fm::log(tb, x));
 }
 
 // Fiadeiro-Veronis weight, LHeureux_model.py:437-442 (calculate_sigma :147-160).
-__device__ __forceinline__ double fv_sigma(double Pe, double W, double Pe_min, double Pe_max) {
+__device__ __forceinline__ double fv_sigma(const fm::Tables& tb, double Pe, double W, double Pe_min, double Pe_max) {
   const double a = fabs(Pe);
   if (a < Pe_min) return 0.0;
   if (a > Pe_max) return (W > 0.0) ? 1.0 : ((W < 0.0) ? -1.0 : W);  // np.sign (keeps NaN / 0)
   if (!(a <= Pe_max)) return Pe;                                   // NaN Peclet -> NaN weight
-  const double em = expm1(2.0 * Pe);                                 // coth = 1 + 2/em
-  return (Pe * (em + 2.0) - em) / (Pe * em);
+  const double em = fm::expm1(tb, 2.0 * Pe);                         // coth = 1 + 2/em
+  return fm::div(fma(Pe, em + 2.0, -em), Pe * em);
 }
 
 struct CellRates {
@@ -93,19 +96,19 @@ struct CellRates {
 
 // c = centre values, m = cell i-1 (or top ghost), p = cell i+1 (or bottom ghost), field order
 // CA, CC, cCa, cCO3, Phi.  `in_mask` = not_too_deep*not_too_shallow != 0 for this cell.
-__device__ __forceinline__ void cell_rhs(const ColumnConsts& k, const double c[5], const double m[5],
-                                         const double p[5], bool in_mask, CellRates& out) {
+__device__ __forceinline__ void cell_rhs(const ColumnConsts& k, const fm::Tables& tb, const double c[5],
+                                         const double m[5], const double p[5], bool in_mask, CellRates& out) {
   const double CA = c[0], CC = c[1], cCa = c[2], cCO3 = c[3], Phi = c[4];
 
   // ---- porosity-dependent velocities (:414-431)
-  const double rPhi = 1.0 / Phi;
-  const double F = 1.0 - exp(10.0 - 10.0 * rPhi);
+  const double rPhi = fm::rcp(Phi);
+  const double F = 1.0 - fm::exp(tb, fma(-10.0, rPhi, 10.0));
   const double omP = 1.0 - Phi;
   const double Phi2 = Phi * Phi;
-  const double U = k.presum + k.rhorat * (Phi2 * Phi) * F / omP;
-  const double W = k.presum - k.rhorat * Phi2 * F;
-  const double den = 1.0 - 2.0 * log(Phi);
-  const double rden = 1.0 / den;
+  const double U = fma(k.rhorat * (Phi2 * Phi), fm::div(F, omP), k.presum);
+  const double W = fma(-k.rhorat * Phi2, F, k.presum);
+  const double den = fma(-2.0, fm::log(tb, Phi), 1.0);
+  const double rden = fm::rcp(den);
 
   // ---- solids: first-order upwind by the sign of U (:418-423)
   const bool back = U > 0.0;
@@ -116,9 +119,9 @@ __device__ __forceinline__ void cell_rhs(const ColumnConsts& k, const double c[5
   double sCa = 0.0, sCO3 = 0.0, sPhi = 0.0;
   if (k.FV_switch) {
     const double Wden = W * den;
-    sCa = fv_sigma(Wden * k.kPeCa, W, k.Pe_min, k.Pe_max);
-    sCO3 = fv_sigma(Wden * k.kPeCO3, W, k.Pe_min, k.Pe_max);
-    sPhi = fv_sigma(W * k.kPePhi, W, k.Pe_min, k.Pe_max);
+    sCa = fv_sigma(tb, Wden * k.kPeCa, W, k.Pe_min, k.Pe_max);
+    sCO3 = fv_sigma(tb, Wden * k.kPeCO3, W, k.Pe_min, k.Pe_max);
+    sPhi = fv_sigma(tb, W * k.kPePhi, W, k.Pe_min, k.Pe_max);
   }
   // g = 0.5((1-s) gf + (1+s) gb) = 0.5 (gf + gb) - 0.5 s (gf - gb)   (:464-469)
   const double hdx = 0.5 * k.inv_dx;
@@ -140,15 +143,15 @@ __device__ __forceinline__ void cell_rhs(const ColumnConsts& k, const double c[5
   const double three = two * k.KRat;
   double coA;
   if (three < 1.0) {
-    coA = in_mask ? CA * pow_nonneg(1.0 - three, k.m2) : CA * 0.0;
+    coA = in_mask ? CA * pow_nonneg(tb, 1.0 - three, k.m2) : CA * 0.0;
   } else {
-    coA = -CA * k.nu1 * pow_nonneg(three - 1.0, k.m1);      // also carries NaN
+    coA = -CA * k.nu1 * pow_nonneg(tb, three - 1.0, k.m1);      // also carries NaN
   }
   double coC;
   if (two < 1.0) {
-    coC = -CC * k.nu2 * pow_nonneg(1.0 - two, k.n2);
+    coC = -CC * k.nu2 * pow_nonneg(tb, 1.0 - two, k.n2);
   } else {
-    coC = CC * pow_nonneg(two - 1.0, k.n1);
+    coC = CC * pow_nonneg(tb, two - 1.0, k.n1);
   }
   const double h3 = coA - k.lambda_ * coC;
   const double dWdx = -k.rhorat * gPhi * (2.0 * Phi * F + 10.0 * (F - 1.0));

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/marlpde_b200.h"
+#include "lheureux_device.cuh"
 
 namespace {
 
@@ -21,6 +22,27 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, 
   }
   const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
   if (s == 12345.678) out[0] = s;   // keeps the chains alive without a store on the hot path
+}
+
+
+// element-wise evaluation of the table-driven device maths (accuracy tests only)
+__global__ void math_probe_kernel(int op, const double* x, int n, double* out) {
+  __shared__ __align__(16) unsigned char tab_raw[marlpde::fm::kTableBytes];
+  const marlpde::fm::Tables tb = marlpde::fm::stage_tables(tab_raw, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = x[i];
+  double r;
+  switch (op) {
+    case 0: r = marlpde::fm::log(tb, v); break;
+    case 1: r = marlpde::fm::exp(tb, v); break;
+    case 2: r = marlpde::fm::expm1(tb, v); break;
+    case 3: r = marlpde::fm::rcp(v); break;
+    case 4: r = marlpde::fm::div(1.0 + v, v); break;
+    default: r = marlpde::fv_sigma(tb, v, v, 1e-2, 1e2); break;
+  }
+  out[i] = r;
 }
 
 }  // namespace
@@ -57,4 +79,21 @@ extern "C" int marlpde_probe_fp64_peak(int device, int iters, int repeats, doubl
   cudaFree(d);
   *tflops = best;
   return cudaGetLastError() == cudaSuccess ? MARLPDE_OK : MARLPDE_ECUDA;
+}
+
+extern "C" int marlpde_probe_math(int op, const double* x, int n, double* out, int device) {
+  if (!x || !out || n < 0 || op < 0 || op > 5) return MARLPDE_EINVAL;
+  int nd = 0;
+  if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) return MARLPDE_ENODEVICE;
+  if (device < 0 || device >= nd || cudaSetDevice(device) != cudaSuccess) return MARLPDE_EINVAL;
+  if (n == 0) return MARLPDE_OK;
+  double *dx = nullptr, *dout = nullptr;
+  if (cudaMalloc(&dx, sizeof(double) * n) != cudaSuccess) return MARLPDE_ECUDA;
+  if (cudaMalloc(&dout, sizeof(double) * n) != cudaSuccess) { cudaFree(dx); return MARLPDE_ECUDA; }
+  cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice);
+  math_probe_kernel<<<(n + 255) / 256, 256>>>(op, dx, n, dout);
+  cudaError_t e = cudaMemcpy(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  cudaFree(dx);
+  cudaFree(dout);
+  return e == cudaSuccess ? MARLPDE_OK : MARLPDE_ECUDA;
 }

@@ -20,6 +20,8 @@ rhs_batch_kernel(const double* __restrict__ g_y, const marlpde_column_params* __
                  int n_cells, int tiles_per_col, double* __restrict__ g_out) {
   __shared__ ColumnConsts kc;
   __shared__ double tile[5][kCellsPerCta + 2];
+  __shared__ __align__(16) unsigned char tab_raw[fm::kTableBytes];
+  const fm::Tables tb = fm::stage_tables(tab_raw, threadIdx.x, kCellsPerCta);
   const int col = blockIdx.x / tiles_per_col;   // 1-D grid: 65 536+ columns exceed gridDim.y
   const int cell0 = (blockIdx.x - col * tiles_per_col) * kCellsPerCta;
   const int cell = cell0 + threadIdx.x;
@@ -37,7 +39,7 @@ rhs_batch_kernel(const double* __restrict__ g_y, const marlpde_column_params* __
   double c[5], m[5], p[5];
   load_triple(kc, cell, [&](int f, int i) { return tile[f][i - cell0 + 1]; }, c, m, p);
   CellRates r;
-  cell_rhs(kc, c, m, p, cell >= kc.mask_lo && cell < kc.mask_hi, r);
+  cell_rhs(kc, tb, c, m, p, cell >= kc.mask_lo && cell < kc.mask_hi, r);
   double* ocol = g_out + (size_t)col * 5 * n_cells;
 #pragma unroll
   for (int f = 0; f < 5; ++f) ocol[(size_t)f * n_cells + cell] = r.r[f];

@@ -53,37 +53,60 @@ constexpr double SAFETY = 0.9, MIN_FACTOR = 0.2, MAX_FACTOR = 10.0;
 }  // namespace dp
 
 // ---- shared memory carve-up -------------------------------------------------------------
-// K[6][5][T] | tile[2][5][T] | grp[T] | consts[C] | slot_col[C] | svc flag
-struct SmemLayout {
-  int T;        // C * N, padded to a multiple of 32
-  int nwarps;
-  int C;
-  size_t off_K, off_tile, off_red, off_consts, off_slot, total;
+// K[6][5][T] | tile[2][5][T] | y[5][T] | grp[T>>logG] | consts[C] | ctl[C] | log/exp tables | slot_col[C] | svc flag
+struct SlotCtl {          // per-slot counters, touched by the slot's leader thread only
+  long long n_acc, n_rej, nfev;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int C, int N) {
+struct SmemLayout {
+  int T;        // C * N, padded to a multiple of 32
+  int C;
+  size_t off_K, off_tile, off_y, off_grp, off_consts, off_ctl, off_tab, off_slot, total;
+};
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) / 16 * 16; }
+
+__host__ __device__ inline SmemLayout smem_layout(int C, int N, int logG) {
   SmemLayout L;
   L.C = C;
   L.T = ((C * N + 31) / 32) * 32;
-  L.nwarps = L.T / 32;
   size_t o = 0;
   L.off_K = o;      o += sizeof(double) * 6 * 5 * (size_t)L.T;
   L.off_tile = o;   o += sizeof(double) * 2 * 5 * (size_t)L.T;
-  L.off_red = o;    o += sizeof(double) * (size_t)L.T;   // group sums of the error norm (<= T/G used)
-  L.off_consts = o; o += ((sizeof(ColumnConsts) + 15) / 16 * 16) * (size_t)C;
+  L.off_y = o;      o += sizeof(double) * 5 * (size_t)L.T;
+  L.off_grp = o;    o += align16(sizeof(double) * (size_t)((L.T >> logG) + 1));
+  L.off_consts = o; o += align16(sizeof(ColumnConsts)) * (size_t)C;
+  L.off_ctl = o;    o += align16(sizeof(SlotCtl)) * (size_t)C;
+  L.off_tab = o;    o += (size_t)fm::kTableBytes;
   L.off_slot = o;   o += sizeof(int) * (size_t)(C + 4);
-  L.total = (o + 15) / 16 * 16;
+  L.total = align16(o);
   return L;
+}
+
+static int group_log2(int n_cells) {
+  int logG = 0;
+  while (logG < 5 && (n_cells % (2 << logG)) == 0) ++logG;
+  return logG;
 }
 
 int rk45_columns_per_cta(int n_cells, int smem_budget) {
   if (n_cells < 32 || n_cells > kRk45MaxThreads) return 0;
   int C = kRk45MaxThreads / n_cells;
-  while (C > 0 && smem_layout(C, n_cells).total > (size_t)smem_budget) --C;
+  while (C > 0 && smem_layout(C, n_cells, group_log2(n_cells)).total > (size_t)smem_budget) --C;
   return C;
 }
 
-size_t rk45_smem_bytes(int C, int n_cells) { return smem_layout(C, n_cells).total; }
+size_t rk45_smem_bytes(int C, int n_cells) { return smem_layout(C, n_cells, group_log2(n_cells)).total; }
+
+// Stage table: after K_{i+1} has been evaluated (i = 1..5) the next stage input is
+// y + h * sum_{j=0..i} kStage[i-1][j] * K_{j+1}; row 4 holds b (the 5th-order weights, FSAL).
+__constant__ double kStage[5][6] = {
+    {dp::a31, dp::a32, 0, 0, 0, 0},
+    {dp::a41, dp::a42, dp::a43, 0, 0, 0},
+    {dp::a51, dp::a52, dp::a53, dp::a54, 0, 0},
+    {dp::a61, dp::a62, dp::a63, dp::a64, dp::a65, 0},
+    {dp::b1, 0.0, dp::b3, dp::b4, dp::b5, dp::b6}};
+__constant__ double kErr[7] = {dp::e1, 0.0, dp::e3, dp::e4, dp::e5, dp::e6, dp::e7};
 
 __global__ void __launch_bounds__(kRk45MaxThreads, 1)
 rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __restrict__ g_params,
@@ -91,22 +114,25 @@ rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __
                        marlpde_rk45_options opt, const double* __restrict__ g_t_eval,
                        double* __restrict__ g_snap, int32_t* __restrict__ g_queue) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SmemLayout L = smem_layout(C, N);
+  const SmemLayout L = smem_layout(C, N, logG);
   const int T = L.T;
   double* const sK = reinterpret_cast<double*>(smem_raw + L.off_K);        // [6][5][T]
   double* const sTile = reinterpret_cast<double*>(smem_raw + L.off_tile);  // [2][5][T]
-  double* const sGrp = reinterpret_cast<double*>(smem_raw + L.off_red);    // [T / G]
-  const size_t consts_stride = (sizeof(ColumnConsts) + 15) / 16 * 16;
+  double* const sY = reinterpret_cast<double*>(smem_raw + L.off_y);        // [5][T]
+  double* const sGrp = reinterpret_cast<double*>(smem_raw + L.off_grp);    // [T >> logG]
   int* const sSlotCol = reinterpret_cast<int*>(smem_raw + L.off_slot);     // [C]
   int* const sSvc = sSlotCol + C;
 
   const int tid = threadIdx.x;
+  const fm::Tables tb = fm::stage_tables(smem_raw + L.off_tab, tid, blockDim.x);
   const bool active = tid < C * N;
   const int slot = active ? tid / N : C;          // C = "no slot" for the padding lanes
   const int cell = active ? tid - slot * N : 0;
   const int base = slot * N;                       // first tile index of my column
   const ColumnConsts& kc = *reinterpret_cast<const ColumnConsts*>(
-      smem_raw + L.off_consts + consts_stride * (active ? slot : 0));
+      smem_raw + L.off_consts + align16(sizeof(ColumnConsts)) * (active ? slot : 0));
+  SlotCtl& ctl = *reinterpret_cast<SlotCtl*>(smem_raw + L.off_ctl + align16(sizeof(SlotCtl)) * (active ? slot : 0));
+  const bool leader = active && cell == 0;
   // Error-norm reduction tree, identical for every slot so that a column's trajectory does not
   // depend on where it is scheduled: cells are summed in aligned groups of G = 2^k lanes
   // (G = largest power of two <= 32 dividing N, hence dividing every slot base) by an xor
@@ -115,35 +141,35 @@ rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __
   const int nGroups = N >> logG;
   const int grpBase = base >> logG;
 
-  // per-thread column state
+  // per-thread column state (everything else lives in shared memory)
   int col = -1;                 // column index being integrated by my slot, -1 = idle
   bool exhausted = false;       // the work queue ran dry
-  double y[5] = {0, 0, 0, 0, 0};
-  double t = 0.0, h_abs = 0.0, h = 0.0, t_new = 0.0, min_step = 0.0;
   bool rejected = false;
+  double t = 0.0, h_abs = 0.0, h = 0.0, t_new = 0.0;
   int next_eval = 0;
-  long long n_acc = 0, n_rej = 0, nfev = 0, attempts_here = 0;
+  int attempts = 0;             // step attempts made for this column in this launch
 
   auto tileAt = [&](int b, int f, int i) -> double& { return sTile[(b * 5 + f) * T + i]; };
   auto KAt = [&](int s, int f) -> double& { return sK[(s * 5 + f) * T + tid]; };
+  auto yAt = [&](int f) -> double& { return sY[f * T + tid]; };
 
-  // RHS of my cell from stage tile `b`
+  // RHS of my cell from stage tile `b` (one code instance, see the stage loop)
   auto eval_rhs = [&](int b, CellRates& out) {
     double c[5], m[5], p[5];
     load_triple(kc, cell, [&](int f, int i) { return tileAt(b, f, base + i); }, c, m, p);
-    cell_rhs(kc, c, m, p, cell >= kc.mask_lo && cell < kc.mask_hi, out);
+    cell_rhs(kc, tb, c, m, p, cell >= kc.mask_lo && cell < kc.mask_hi, out);
   };
 
-  // scipy _step_impl preamble for a new step + first attempt set-up. Returns false when the
-  // step size underflows (TOO_SMALL_STEP).
+  // scipy _step_impl: min_step = 10 * |nextafter(t, inf) - t| ; clamp h_abs at the start of a step
+  auto min_step_at = [&](double tt) { return 10.0 * fabs(nextafter(tt, (double)INFINITY) - tt); };
   auto begin_step = [&]() {
-    min_step = 10.0 * fabs(nextafter(t, (double)INFINITY) - t);
+    const double ms = min_step_at(t);
     if (h_abs > opt.max_step) h_abs = opt.max_step;
-    else if (h_abs < min_step) h_abs = min_step;
+    else if (h_abs < ms) h_abs = ms;
     rejected = false;
   };
-  auto begin_attempt = [&]() -> bool {
-    if (h_abs < min_step) return false;
+  auto begin_attempt = [&]() -> bool {   // false: TOO_SMALL_STEP
+    if (h_abs < min_step_at(t)) return false;
     h = h_abs;
     t_new = t + h;
     if (t_new - opt.t_bound > 0.0) t_new = opt.t_bound;
@@ -153,14 +179,14 @@ rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __
   };
   auto retire = [&](int status) {  // store the column's end point and free the slot
 #pragma unroll
-    for (int f = 0; f < 5; ++f) g_y[((size_t)col * 5 + f) * N + cell] = y[f];
-    if (cell == 0) {
+    for (int f = 0; f < 5; ++f) g_y[((size_t)col * 5 + f) * N + cell] = yAt(f);
+    if (leader) {
       marlpde_column_state st;
       st.t = t;
       st.h_abs = h_abs;
-      st.n_accepted = n_acc;
-      st.n_rejected = n_rej;
-      st.nfev = nfev;
+      st.n_accepted = ctl.n_acc;
+      st.n_rejected = ctl.n_rej;
+      st.nfev = ctl.nfev;
       st.status = status;
       st.next_eval = next_eval;
       g_state[col] = st;
@@ -169,159 +195,112 @@ rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __
   };
   auto write_stage2 = [&]() {
 #pragma unroll
-    for (int f = 0; f < 5; ++f) tileAt(1, f, tid) = fma(h * dp::a21, KAt(0, f), y[f]);
+    for (int f = 0; f < 5; ++f) tileAt(1, f, tid) = fma(h * dp::a21, KAt(0, f), yAt(f));
   };
 
   if (tid == 0) *sSvc = 0;
   __syncthreads();
 
+  bool fresh = false;           // column just loaded: K1 = f(y) still to be evaluated (stage i = 0)
   for (;;) {
     // ================= stage 2 input + slot service =======================================
     if (col >= 0) write_stage2();
-    if (active && cell == 0 && col < 0 && !exhausted) *sSvc = 1;
-    const int nlive = __syncthreads_count(col >= 0);
+    if (leader && col < 0 && !exhausted) *sSvc = 1;
+    int nlive = __syncthreads_count(col >= 0);
+    int i0 = 1;
     if (*sSvc) {
       // -- claim columns for idle slots
-      if (active && cell == 0 && col < 0 && !exhausted) {
+      if (leader && col < 0 && !exhausted) {
         const int c = atomicAdd(g_queue, 1);
         sSlotCol[slot] = c < n_columns ? c : -1;
       }
       __syncthreads();
       if (tid == 0) *sSvc = 0;
-      bool fresh = false;
       if (active && col < 0 && !exhausted) {
         col = sSlotCol[slot];
         if (col < 0) {
           exhausted = true;
         } else {
-          fresh = true;
-          if (cell == 0) {
+          const marlpde_column_state st = g_state[col];
+          if (leader) {
             ColumnConsts tmp;
             make_consts(g_params[col], N, tmp);
             *const_cast<ColumnConsts*>(&kc) = tmp;
+            ctl.n_acc = st.n_accepted;
+            ctl.n_rej = st.n_rejected;
+            ctl.nfev = st.nfev;
           }
-          const marlpde_column_state st = g_state[col];
+          attempts = 0;
           t = st.t;
           h_abs = st.h_abs;
-          n_acc = st.n_accepted;
-          n_rej = st.n_rejected;
-          nfev = st.nfev;
           next_eval = st.next_eval;
-          attempts_here = 0;
 #pragma unroll
           for (int f = 0; f < 5; ++f) {
-            y[f] = g_y[((size_t)col * 5 + f) * N + cell];
-            tileAt(0, f, tid) = y[f];
+            const double v = g_y[((size_t)col * 5 + f) * N + cell];
+            yAt(f) = v;
+            tileAt(0, f, tid) = v;
+          }
+          if (t >= opt.t_bound) {            // nothing to integrate
+            retire(MARLPDE_STATUS_FINISHED);
+          } else {
+            begin_step();
+            if (begin_attempt()) fresh = true;
+            else retire(MARLPDE_STATUS_STEP_TOO_SMALL);
           }
         }
       }
-      __syncthreads();
-      if (fresh) {
-        if (t >= opt.t_bound) {            // nothing to integrate
-          retire(MARLPDE_STATUS_FINISHED);
-        } else {
-          CellRates r;
-          eval_rhs(0, r);
-#pragma unroll
-          for (int f = 0; f < 5; ++f) KAt(0, f) = r.r[f];
-          nfev += 1;
-          begin_step();
-          if (begin_attempt()) write_stage2();
-          else retire(MARLPDE_STATUS_STEP_TOO_SMALL);
-        }
-      }
-      __syncthreads();
-      continue;  // re-evaluate liveness / further idle slots at the top
+      nlive = __syncthreads_count(col >= 0);   // also publishes consts, y and tile 0 of the new columns
+      if (nlive == 0) continue;                // everything claimed retired at once: look again
+      i0 = 0;
     }
     if (nlive == 0) break;
 
-    // ================= stages 2..6 ========================================================
+    // ================= stages: i = 1..6 evaluates K_{i+1} from tile (i & 1) =================
+    // (i = 0, only after a slot service: K1 = f(y) of freshly loaded columns from tile 0.)
+    // ONE code instance of the RHS serves every stage: the kernel stays inside the instruction
+    // cache and K1 of a resumed column is bit-identical to the FSAL K7 it replaces.
     const bool live = col >= 0;
-    double accY[5], accE[5];
     CellRates r;
-    if (live) {
-      // K2 = f(tile 1)
-      eval_rhs(1, r);
+#pragma unroll 1
+    for (int i = i0; i <= 6; ++i) {
+      if (i > i0) __syncthreads();
+      if (live && (i > 0 || fresh)) {
+        eval_rhs(i & 1, r);
+        if (i == 0) {
 #pragma unroll
-      for (int f = 0; f < 5; ++f) {
-        const double k1 = KAt(0, f), k2 = r.r[f];
-        KAt(1, f) = k2;
-        accY[f] = dp::b1 * k1;
-        accE[f] = dp::e1 * k1;
-        tileAt(0, f, tid) = fma(h, fma(dp::a32, k2, dp::a31 * k1), y[f]);
+          for (int f = 0; f < 5; ++f) KAt(0, f) = r.r[f];
+          if (leader) ctl.nfev += 1;
+          write_stage2();
+          fresh = false;
+        } else if (i < 6) {
+          // store K_{i+1}; next stage input (row 4 = y_new) into the other tile
+          const double* row = kStage[i - 1];
+#pragma unroll
+          for (int f = 0; f < 5; ++f) {
+            const double k = r.r[f];
+            KAt(i, f) = k;
+            double acc = row[i] * k;
+            for (int j = i - 1; j >= 0; --j) acc = fma(row[j], KAt(j, f), acc);
+            tileAt((i + 1) & 1, f, tid) = fma(h, acc, yAt(f));
+          }
+        }
       }
     }
-    __syncthreads();
-    if (live) {
-      // K3 = f(tile 0)
-      eval_rhs(0, r);
-#pragma unroll
-      for (int f = 0; f < 5; ++f) {
-        const double k3 = r.r[f];
-        KAt(2, f) = k3;
-        accY[f] = fma(dp::b3, k3, accY[f]);
-        accE[f] = fma(dp::e3, k3, accE[f]);
-        const double s = fma(dp::a43, k3, fma(dp::a42, KAt(1, f), dp::a41 * KAt(0, f)));
-        tileAt(1, f, tid) = fma(h, s, y[f]);
-      }
-    }
-    __syncthreads();
-    if (live) {
-      // K4 = f(tile 1)
-      eval_rhs(1, r);
-#pragma unroll
-      for (int f = 0; f < 5; ++f) {
-        const double k4 = r.r[f];
-        KAt(3, f) = k4;
-        accY[f] = fma(dp::b4, k4, accY[f]);
-        accE[f] = fma(dp::e4, k4, accE[f]);
-        const double s = fma(dp::a54, k4, fma(dp::a53, KAt(2, f), fma(dp::a52, KAt(1, f), dp::a51 * KAt(0, f))));
-        tileAt(0, f, tid) = fma(h, s, y[f]);
-      }
-    }
-    __syncthreads();
-    if (live) {
-      // K5 = f(tile 0)
-      eval_rhs(0, r);
-#pragma unroll
-      for (int f = 0; f < 5; ++f) {
-        const double k5 = r.r[f];
-        KAt(4, f) = k5;
-        accY[f] = fma(dp::b5, k5, accY[f]);
-        accE[f] = fma(dp::e5, k5, accE[f]);
-        const double s = fma(dp::a65, k5, fma(dp::a64, KAt(3, f), fma(dp::a63, KAt(2, f),
-                         fma(dp::a62, KAt(1, f), dp::a61 * KAt(0, f)))));
-        tileAt(1, f, tid) = fma(h, s, y[f]);
-      }
-    }
-    __syncthreads();
-    if (live) {
-      // K6 = f(tile 1);  y_new = y + h * sum b_j K_j
-      eval_rhs(1, r);
-#pragma unroll
-      for (int f = 0; f < 5; ++f) {
-        const double k6 = r.r[f];
-        KAt(5, f) = k6;
-        accY[f] = fma(dp::b6, k6, accY[f]);
-        accE[f] = fma(dp::e6, k6, accE[f]);
-        tileAt(0, f, tid) = fma(h, accY[f], y[f]);
-      }
-    }
-    __syncthreads();
+    // ---- K7 = f(y_new) is in r; error estimate and its norm
     double part = 0.0;
     if (live) {
-      // K7 = f(y_new) ; error estimate
-      eval_rhs(0, r);
 #pragma unroll
       for (int f = 0; f < 5; ++f) {
-        const double ynew = fma(h, accY[f], y[f]);
-        const double err = h * fma(dp::e7, r.r[f], accE[f]);
-        const double scale = fma(fmax(fabs(y[f]), fabs(ynew)), opt.rtol, opt.atol);
-        const double q = err / scale;
+        double e = kErr[6] * r.r[f];
+#pragma unroll
+        for (int j = 5; j >= 0; --j)
+          if (j != 1) e = fma(kErr[j], KAt(j, f), e);
+        const double ynew = tileAt(0, f, tid);
+        const double scale = fma(fmax(fabs(yAt(f)), fabs(ynew)), opt.rtol, opt.atol);
+        const double q = (h * e) * fm::rcp(scale);
         part = fma(q, q, part);
       }
     }
-    // ---- sum((err/scale)^2) over the column: butterfly inside aligned groups of G cells ...
     {
       double a = part;
       for (int o = G >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -329,7 +308,7 @@ rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __
     }
     __syncthreads();
     if (live) {
-      // ... then the group sums in cell order (4 interleaved partial sums, fixed association)
+      // group sums in cell order (4 interleaved partial sums, fixed association)
       double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       const double* gp = sGrp + grpBase;
       int gi = 0;
@@ -342,18 +321,18 @@ rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __
       for (; gi < nGroups; ++gi) s0 += gp[gi];
       const double sum = (s0 + s1) + (s2 + s3);
       const double err_norm = sqrt(sum / (double)(5 * N));
-      nfev += 6;
-      attempts_here += 1;
+      if (leader) ctl.nfev += 6;
+      attempts += 1;
       if (err_norm < 1.0) {
         double factor = dp::MAX_FACTOR;
-        if (err_norm != 0.0) factor = fmin(dp::MAX_FACTOR, dp::SAFETY * exp(-0.2 * log(err_norm)));
+        if (err_norm != 0.0) factor = fmin(dp::MAX_FACTOR, dp::SAFETY * fm::exp(tb, -0.2 * fm::log(tb, err_norm)));
         if (rejected) factor = fmin(1.0, factor);
         // ---- dense output for t_eval points in (t, t_new] (ivp.py: searchsorted side='right')
         while (next_eval < opt.n_eval) {
           const double te = g_t_eval[next_eval];
           if (!(te <= t_new)) break;
           const double x = (te - t) / h;
-#pragma unroll
+#pragma unroll 1
           for (int f = 0; f < 5; ++f) {
             double q[4];
 #pragma unroll
@@ -364,22 +343,22 @@ rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __
               q[j] = fma(dp::P[6][j], r.r[f], s);
             }
             const double poly = x * (q[0] + x * (q[1] + x * (q[2] + x * q[3])));
-            g_snap[(((size_t)col * opt.n_eval + next_eval) * 5 + f) * N + cell] = fma(h, poly, y[f]);
+            g_snap[(((size_t)col * opt.n_eval + next_eval) * 5 + f) * N + cell] = fma(h, poly, yAt(f));
           }
           ++next_eval;
         }
         // ---- accept
 #pragma unroll
         for (int f = 0; f < 5; ++f) {
-          y[f] = fma(h, accY[f], y[f]);
+          yAt(f) = tileAt(0, f, tid);
           KAt(0, f) = r.r[f];           // FSAL
         }
         t = t_new;
         h_abs *= factor;
-        n_acc += 1;
+        if (leader) ctl.n_acc += 1;
         if (t >= opt.t_bound) {
           retire(MARLPDE_STATUS_FINISHED);
-        } else if (opt.max_steps > 0 && attempts_here >= opt.max_steps) {
+        } else if (opt.max_steps > 0 && (long long)attempts >= opt.max_steps) {
           retire(MARLPDE_STATUS_STEP_BUDGET);
         } else {
           begin_step();
@@ -387,9 +366,9 @@ rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __
         }
       } else {
         // NaN error norms land here too: fmax drops the NaN, like Python's max(0.2, nan)
-        h_abs *= fmax(dp::MIN_FACTOR, dp::SAFETY * exp(-0.2 * log(err_norm)));
+        h_abs *= fmax(dp::MIN_FACTOR, dp::SAFETY * fm::exp(tb, -0.2 * fm::log(tb, err_norm)));
         rejected = true;
-        n_rej += 1;
+        if (leader) ctl.n_rej += 1;
         if (!begin_attempt()) retire(MARLPDE_STATUS_STEP_TOO_SMALL);
       }
     }
@@ -401,9 +380,8 @@ cudaError_t launch_rk45(double* d_y, const marlpde_column_params* d_params, marl
                         double* d_snap, int32_t* d_queue, int sm_count, int smem_budget, cudaStream_t stream) {
   const int C = rk45_columns_per_cta(n_cells, smem_budget);
   if (C <= 0) return cudaErrorInvalidValue;
-  int logG = 0;
-  while (logG < 5 && (n_cells % (2 << logG)) == 0) ++logG;
-  const SmemLayout L = smem_layout(C, n_cells);
+  const int logG = group_log2(n_cells);
+  const SmemLayout L = smem_layout(C, n_cells, logG);
   cudaError_t e = cudaFuncSetAttribute(rk45_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)L.total);
   if (e != cudaSuccess) return e;

@@ -9,9 +9,10 @@
 
 namespace marlpde {
 
-// Upper bound on threads per CTA of the on-chip RK45 kernel: 640 threads x 96 registers
-// fit the 64K-register file of one SM with one resident CTA.
-constexpr int kRk45MaxThreads = 640;
+// Upper bound on threads per CTA of the on-chip RK45 kernel: 608 threads (3 columns of 200
+// cells, 19 warps) x 96 registers (registers are granted per warp in units of 512, so 104 would
+// not fit) fill the 64K-register file of one SM with one resident CTA.
+constexpr int kRk45MaxThreads = 608;
 
 int rk45_columns_per_cta(int n_cells, int smem_budget);
 size_t rk45_smem_bytes(int columns_per_cta, int n_cells);

@@ -91,7 +91,7 @@ def test_step_budget_and_resume_is_bit_identical():
 
 def test_ragged_shapes_and_many_columns():
     """N not a multiple of 32, one and two columns per CTA, more columns than resident slots."""
-    for n_cells, ncol in ((33, 5), (100, 9), (257, 3), (640, 2)):
+    for n_cells, ncol in ((33, 5), (100, 9), (257, 3), (608, 2)):
         pde = oracle.default_scenario() | {"N": n_cells, "Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}
         P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
         t_end = 2e-4 * (200 / n_cells) ** 2 if n_cells > 200 else 2e-4

@@ -190,8 +190,9 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     pde = mb.sweep_lattice(scenario_base(args.base), *lat)
     P_all = mb.derive_column_params(pde)
     y_all = mb.initial_state(pde)
-    per = P_all.shape[0] // world
-    sl = slice(rank * per, (rank + 1) * per)                      # contiguous column block per rank
+    from marlpde_b200 import sweep
+    a, b = sweep.partition(P_all.shape[0], world)[rank]
+    sl = slice(a, b)                                              # contiguous column block per rank
     P, y0 = P_all[sl], y_all[sl]
     B, N = y0.shape[0], y0.shape[2]
 
@@ -202,8 +203,12 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     d_queue = torch.zeros(1, dtype=torch.int32, device=dev)
     d_ec = torch.zeros((B, 7), dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # the 7 event monitors run inside the timed region, as in the reference's solve_ivp call
+    # (Evolve_scenario.py:107-109 passes events=[...]); roots are located and stored (first EVCAP per monitor)
+    EVCAP = 16
+    d_et = torch.full((B, 7, EVCAP), float("nan"), dtype=torch.float64, device=dev)
     opts = _cabi.RK45Options(t_bound=1.0, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=args.attempts,
-                             n_eval=0, event_capacity=0, flags=0, reserved=0)
+                             n_eval=0, event_capacity=EVCAP, flags=_cabi.FLAG_EVENTS, reserved=0)
     stream = torch.cuda.current_stream()
 
     def attempts_done():
@@ -213,7 +218,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     def one_step():
         d_queue.zero_()
         _cabi.check(lib.marlpde_rk45_integrate_dev(d_y.data_ptr(), d_params.data_ptr(), d_state.data_ptr(), B, N,
-                                                   C.byref(opts), None, None, d_ec.data_ptr(), None,
+                                                   C.byref(opts), None, None, d_ec.data_ptr(), d_et.data_ptr(),
                                                    d_queue.data_ptr(), stream.cuda_stream))
 
     def barrier():
@@ -248,12 +253,13 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     h_state = torch.from_numpy(st.view(np.uint8).copy()).pin_memory()
     h_params = torch.from_numpy(P.view(np.uint8).copy()).pin_memory()
     h_ec = torch.zeros((B, 7), dtype=torch.int32).pin_memory()
-    hy, hs, hp, hec = h_y.numpy(), h_state.numpy(), h_params.numpy(), h_ec.numpy()
+    h_et = torch.full((B, 7, EVCAP), float("nan"), dtype=torch.float64).pin_memory()
+    hy, hs, hp, hec, het = h_y.numpy(), h_state.numpy(), h_params.numpy(), h_ec.numpy(), h_et.numpy()
     e2e_steps = max(2, min(args.steps, 5))
 
     def e2e_step():
         _cabi.check(lib.marlpde_rk45_integrate(hy.ctypes.data, hp.ctypes.data, hs.ctypes.data, B, N, C.byref(opts),
-                                               None, None, hec.ctypes.data, None, local_rank))
+                                               None, None, hec.ctypes.data, het.ctypes.data, local_rank))
     e2e_step()                                                       # warm-up (allocations, first touch)
     barrier()
     b0 = int(hs.view(_cabi.STATE_DTYPE)["n_accepted"].sum() + hs.view(_cabi.STATE_DTYPE)["n_rejected"].sum())
@@ -263,8 +269,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     barrier()
     e2e_s = time.perf_counter() - t0
     b1 = int(hs.view(_cabi.STATE_DTYPE)["n_accepted"].sum() + hs.view(_cabi.STATE_DTYPE)["n_rejected"].sum())
-    h2d = hy.nbytes + hp.nbytes + hs.nbytes + hec.nbytes
-    d2h = hy.nbytes + hs.nbytes + hec.nbytes
+    h2d = hy.nbytes + hp.nbytes + hs.nbytes + hec.nbytes + het.nbytes
+    d2h = hy.nbytes + hs.nbytes + hec.nbytes + het.nbytes
 
     # ---- aggregate over ranks: max time, sum of work; one all-gather of end states (the only collective)
     att = torch.tensor([a1 - a0, b1 - b0], dtype=torch.float64, device=dev)
@@ -327,13 +333,14 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         d_y2 = torch.from_numpy(y0).to(dev)
         d_state2 = torch.from_numpy(batch.make_state(B, 0.0, 1e-6).view(np.uint8).copy()).to(dev)
         o2 = _cabi.RK45Options(t_bound=1.0, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=0, n_eval=0,
-                               event_capacity=0, flags=0, reserved=0)
+                               event_capacity=EVCAP, flags=_cabi.FLAG_EVENTS, reserved=0)
         d_queue.zero_()
+        d_ec.zero_()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(stream)
         _cabi.check(lib.marlpde_rk45_integrate_dev(d_y2.data_ptr(), d_params.data_ptr(), d_state2.data_ptr(), B, N,
-                                                   C.byref(o2), None, None, d_ec.data_ptr(), None, d_queue.data_ptr(),
-                                                   stream.cuda_stream))
+                                                   C.byref(o2), None, None, d_ec.data_ptr(), d_et.data_ptr(),
+                                                   d_queue.data_ptr(), stream.cuda_stream))
         f1.record(stream)
         torch.cuda.synchronize()
         st2 = d_state2.cpu().numpy().view(_cabi.STATE_DTYPE)
@@ -341,6 +348,9 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         tot = int(st2["n_accepted"].sum() + st2["n_rejected"].sum())
         line["time_to_Tstar"] = {"seconds": secs, "columns": B, "step_attempts": tot, "column_steps_per_s": tot / secs,
                                  "finished": int((st2["status"] == 0).sum()),
+                                 "status_histogram": {str(int(k)): int(v) for k, v in
+                                                      zip(*np.unique(st2["status"], return_counts=True))},
+                                 "events_located_per_monitor": d_ec.cpu().numpy().sum(axis=0).tolist(),
                                  "steps_per_column_min_max": [int((st2["n_accepted"] + st2["n_rejected"]).min()),
                                                               int((st2["n_accepted"] + st2["n_rejected"]).max())]}
 

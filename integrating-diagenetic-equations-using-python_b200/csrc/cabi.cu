@@ -108,7 +108,7 @@ int marlpde_get_device_info(int device, marlpde_device_info* info) {
   return MARLPDE_OK;
 }
 
-int marlpde_rk45_max_cells(void) { return marlpde::kRk45MaxThreads; }
+int marlpde_rk45_max_cells(void) { return marlpde::rk45_max_cells(); }
 
 int marlpde_rk45_columns_per_cta(int n_cells) {
   // 227 KB is the sm_100 opt-in limit per CTA; the launcher re-checks against the real device.
@@ -149,9 +149,9 @@ int marlpde_rhs_batch(const double* y, const marlpde_column_params* params, int 
 static int check_rk45_args(int n_columns, int n_cells, const marlpde_rk45_options* opts) {
   if (!opts) return fail(MARLPDE_EINVAL, "opts is NULL");
   if (n_columns < 0) return fail(MARLPDE_EINVAL, "n_columns < 0");
-  if (n_cells < 32 || n_cells > marlpde::kRk45MaxThreads)
+  if (n_cells < 32 || n_cells > marlpde::rk45_max_cells())
     return fail(MARLPDE_EUNSUPPORTED, "on-chip RK45 kernel supports 32 <= n_cells <= %d (got %d)",
-                marlpde::kRk45MaxThreads, n_cells);
+                marlpde::rk45_max_cells(), n_cells);
   if (!(opts->rtol > 0.0) || !(opts->atol >= 0.0)) return fail(MARLPDE_EINVAL, "need rtol > 0, atol >= 0");
   if (!(opts->max_step > 0.0)) return fail(MARLPDE_EINVAL, "max_step must be positive (use +inf for none)");
   if (opts->n_eval < 0 || opts->event_capacity < 0) return fail(MARLPDE_EINVAL, "negative n_eval/event_capacity");
@@ -167,15 +167,18 @@ int marlpde_rk45_integrate_dev(double* d_y, const marlpde_column_params* d_param
   if (n_columns == 0) return MARLPDE_OK;
   if (!d_y || !d_params || !d_state || !d_queue) return fail(MARLPDE_EINVAL, "NULL device pointer");
   if (opts->n_eval > 0 && (!d_t_eval || !d_snapshots)) return fail(MARLPDE_EINVAL, "n_eval > 0 needs t_eval and snapshots");
-  (void)d_event_counts;
-  (void)d_event_times;
+  marlpde_rk45_options o = *opts;
+  if (o.flags & MARLPDE_FLAG_EVENTS) {
+    if (!d_event_counts) return fail(MARLPDE_EINVAL, "MARLPDE_FLAG_EVENTS needs event_counts");
+    if (o.event_capacity > 0 && !d_event_times) return fail(MARLPDE_EINVAL, "event_capacity > 0 needs event_times");
+  }
   DevProps props;
   rc = current_props(props);
   if (rc) return rc;
   if (marlpde::rk45_columns_per_cta(n_cells, props.smem_optin) <= 0)
     return fail(MARLPDE_EUNSUPPORTED, "n_cells=%d does not fit %d bytes of shared memory", n_cells, props.smem_optin);
-  cudaError_t e = marlpde::launch_rk45(d_y, d_params, d_state, n_columns, n_cells, *opts, d_t_eval, d_snapshots,
-                                       d_queue, props.sm_count, props.smem_optin, (cudaStream_t)stream);
+  cudaError_t e = marlpde::launch_rk45(d_y, d_params, d_state, n_columns, n_cells, o, d_t_eval, d_snapshots,
+                                       d_event_counts, d_event_times, d_queue, props.sm_count, props.smem_optin, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "rk45 launch");
   return MARLPDE_OK;
 }

@@ -126,5 +126,57 @@ __device__ __forceinline__ double expm1(const Tables& tb, double x) {
   return fma(s, p, s - 1.0) + fma(sl, p, sl);
 }
 
+
+// ---- branch-free variants for the two-cells-per-thread RHS ------------------------------------
+// Same arithmetic as log/exp above, but an argument outside the fast range only raises `bad`
+// (the caller re-evaluates the whole cell on the generic path once, at the end) instead of
+// branching per call: the RHS stays one basic block per phase, which is what lets ptxas
+// interleave the independent dependency chains of the two cells a thread owns.
+// 1/x: MUFU.RCP64H seed + one cubic step r(1 + e + e^2): |rel err| <= e^3 + 1 ulp.
+__device__ __forceinline__ double rcp3(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double e = fma(-x, r, 1.0);
+  const double t = fma(e, e, e);
+  return fma(r, t, r);
+}
+
+__device__ __forceinline__ double log_nb(const Tables& tb, double x, bool& bad) {
+  const int hi = __double2hiint(x);
+  bad |= (unsigned)(hi - 0x00100000) >= 0x7fe00000u;
+  const int e = (hi >> 20) - 1023;
+  const int j = (hi >> 13) & 127;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+  const double2 t = tb.logtab[j];
+  const double r = fma(m, t.x, -1.0);
+  double p = fma(kLog1pC[5], r, kLog1pC[4]);
+  p = fma(p, r, kLog1pC[3]);
+  p = fma(p, r, kLog1pC[2]);
+  p = fma(p, r, kLog1pC[1]);
+  p = fma(p, r, kLog1pC[0]);
+  const double l1p = fma(r * r, p, r);
+  const double ed = (double)e;
+  return fma(ed, kLn2Hi, t.y) + fma(ed, kLn2Lo, l1p);
+}
+
+__device__ __forceinline__ double exp_nb(const Tables& tb, double x, bool& bad) {
+  bad |= !(fabs(x) < 690.0);
+  double2 T;
+  int k;
+  const double p = exp_core<false>(tb, x, T, k);
+  return scale2(fma(T.x, p, T.x), k);
+}
+
+// expm1 for arguments the caller guarantees to be in (-600, 600) on every lane whose result is used
+__device__ __forceinline__ double expm1_nb(const Tables& tb, double x) {
+  double2 T;
+  int k;
+  const double p = exp_core<true>(tb, x, T, k);
+  const double sc = __hiloint2double((k + 1023) << 20, 0);
+  const double s = T.x * sc;
+  const double sl = T.y * sc;
+  return fma(s, p, s - 1.0) + fma(sl, p, sl);
+}
+
 }  // namespace fm
 }  // namespace marlpde

@@ -196,4 +196,209 @@ __device__ __forceinline__ void load_triple(const ColumnConsts& k, int cell, Loa
   }
 }
 
+
+// =================================================================================================
+// Two depth cells per thread (cells 2k and 2k+1 of one column) — the form both kernels use.
+//
+// c[f][q]  centre values of the two cells; mlo[f] = value of cell 2k-1 (or the top ghost),
+// phi[f] = value of cell 2k+2 (or the bottom ghost).  Same formulas as cell_rhs, arranged so that
+//   * every phase is straight-line code over q = 0, 1: the two cells' dependency chains are
+//     independent, ptxas interleaves them (the fp64 pipe has ~8 cycles of latency to hide and
+//     only ~3 resident warps per scheduler fit the register file);
+//   * the rarely needed blocks (real power behind the dissolution mask, coth for a mid-range
+//     Peclet number) are skipped by WARP-UNIFORM votes, so they cost nothing where no lane needs
+//     them and never split a warp;
+//   * log/exp arguments outside the table-driven range only raise a flag; the caller then
+//     re-evaluates that cell once with cell_rhs (generic path, IEEE special values preserved).
+// Must be called by all 32 lanes of a warp (full-mask votes).  Returns the per-cell flags.
+// Gradients: with a = p - c, b = c - m:  gf + gb = (a + b)/dx, gf - gb = (a - b)/dx, so
+//   g = ((a + b) - sigma (a - b)) / (2 dx)   and   laplace = (a - b) dx^-2.
+// =================================================================================================
+struct PairFlags {
+  bool bad[2];
+};
+
+__device__ __forceinline__ void fv_sigma_pair(const fm::Tables& tb, bool fv_on, const double (&Pe)[2],
+                                              const double (&W)[2], double Pe_min, double Pe_max,
+                                              double (&s)[2]) {
+  bool mid[2];
+  double a[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    a[q] = fabs(Pe[q]);
+    mid[q] = fv_on && (a[q] >= Pe_min) && (a[q] <= Pe_max);
+  }
+  double sm[2] = {0.0, 0.0};
+  if (__any_sync(0xffffffffu, mid[0] || mid[1])) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const double em = fm::expm1_nb(tb, 2.0 * Pe[q]);             // coth = 1 + 2/em
+      sm[q] = fma(Pe[q], em + 2.0, -em) * fm::rcp3(Pe[q] * em);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const double sgn = (W[q] > 0.0) ? 1.0 : ((W[q] < 0.0) ? -1.0 : W[q]);   // np.sign (keeps NaN / 0)
+    s[q] = (!fv_on || a[q] < Pe_min) ? 0.0 : ((a[q] > Pe_max) ? sgn : (mid[q] ? sm[q] : Pe[q]));
+  }
+}
+
+__device__ __forceinline__ PairFlags rhs_pair(const ColumnConsts& k, const fm::Tables& tb, const double (&c)[5][2],
+                                              const double (&mlo)[5], const double (&phi)[5],
+                                              const bool (&in_mask)[2], double (&out)[5][2], double (&Uo)[2],
+                                              double (&Wo)[2]) {
+  PairFlags fl;
+  fl.bad[0] = fl.bad[1] = false;
+
+  // ---- porosity-dependent velocities (:414-431)
+  double rPhi[2], F[2], omP[2], U[2], W[2], den[2], rden[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const double Phi = c[4][q];
+    rPhi[q] = fm::rcp3(Phi);
+    F[q] = 1.0 - fm::exp_nb(tb, fma(-10.0, rPhi[q], 10.0), fl.bad[q]);
+    omP[q] = 1.0 - Phi;
+    const double Phi2 = Phi * Phi;
+    U[q] = fma(k.rhorat * (Phi2 * Phi), F[q] * fm::rcp3(omP[q]), k.presum);
+    W[q] = fma(-k.rhorat * Phi2, F[q], k.presum);
+    den[q] = fma(-2.0, fm::log_nb(tb, Phi, fl.bad[q]), 1.0);
+    rden[q] = fm::rcp3(den[q]);
+    Uo[q] = U[q];
+    Wo[q] = W[q];
+  }
+
+  // ---- first differences: a = (next - centre), b = (centre - previous) per field and cell
+  double a[5][2], b[5][2];
+#pragma unroll
+  for (int f = 0; f < 5; ++f) {
+    b[f][0] = c[f][0] - mlo[f];
+    a[f][0] = c[f][1] - c[f][0];
+    b[f][1] = a[f][0];
+    a[f][1] = phi[f] - c[f][1];
+  }
+
+  // ---- Fiadeiro-Veronis weights (:433-462)
+  // (FV_switch is a per-column value and warps straddle columns: it must not guard the votes inside
+  //  fv_sigma_pair, so it is folded into the lane predicates instead of branching here.)
+  double sCa[2], sCO3[2], sPhi[2];
+  {
+    const bool fv_on = k.FV_switch != 0;
+    double PeCa[2], PeCO3[2], PePhi[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const double Wden = W[q] * den[q];
+      PeCa[q] = Wden * k.kPeCa;
+      PeCO3[q] = Wden * k.kPeCO3;
+      PePhi[q] = W[q] * k.kPePhi;
+    }
+    fv_sigma_pair(tb, fv_on, PeCa, W, k.Pe_min, k.Pe_max, sCa);
+    fv_sigma_pair(tb, fv_on, PeCO3, W, k.Pe_min, k.Pe_max, sCO3);
+    fv_sigma_pair(tb, fv_on, PePhi, W, k.Pe_min, k.Pe_max, sPhi);
+  }
+
+  // ---- saturation products and the real powers of the rate laws (:479-491)
+  bool ltA[2], ltC[2], needA[2];
+  double xA[2], xC[2], eA[2], eC[2], pA[2] = {0.0, 0.0}, pC[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const double two = c[2][q] * c[3][q];
+    const double three = two * k.KRat;
+    ltA[q] = three < 1.0;
+    ltC[q] = two < 1.0;
+    xA[q] = fabs(1.0 - three);
+    xC[q] = fabs(1.0 - two);
+    eA[q] = ltA[q] ? k.m2 : k.m1;
+    eC[q] = ltC[q] ? k.n2 : k.n1;
+    needA[q] = !(ltA[q] && !in_mask[q]);
+  }
+  if (__any_sync(0xffffffffu, needA[0] || needA[1])) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      bool bq = false;
+      pA[q] = fm::exp_nb(tb, eA[q] * fm::log_nb(tb, xA[q], bq), bq);
+      fl.bad[q] |= bq && needA[q];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) pC[q] = fm::exp_nb(tb, eC[q] * fm::log_nb(tb, xC[q], fl.bad[q]), fl.bad[q]);
+
+  // ---- rates (:464-477, :493-520)
+  const double hdx = 0.5 * k.inv_dx;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const double CA = c[0][q], CC = c[1][q], cCa = c[2][q], cCO3 = c[3][q], Phi = c[4][q];
+    const bool back = U[q] > 0.0;
+    const double gCA = (back ? b[0][q] : a[0][q]) * k.inv_dx;
+    const double gCC = (back ? b[1][q] : a[1][q]) * k.inv_dx;
+    const double d2Ca = a[2][q] - b[2][q], d2CO3 = a[3][q] - b[3][q], d2Phi = a[4][q] - b[4][q];
+    const double gCa = fma(-sCa[q], d2Ca, a[2][q] + b[2][q]) * hdx;
+    const double gCO3 = fma(-sCO3[q], d2CO3, a[3][q] + b[3][q]) * hdx;
+    const double gPhi = fma(-sPhi[q], d2Phi, a[4][q] + b[4][q]) * hdx;
+    const double lapCa = d2Ca * k.inv_dx2, lapCO3 = d2CO3 * k.inv_dx2, lapPhi = d2Phi * k.inv_dx2;
+
+    const double h1 = Phi * rden[q];
+    const double h2 = gPhi * (2.0 + den[q]) * (rden[q] * rden[q]);
+    const double HCa = k.dCa * fma(h2, gCa, h1 * lapCa);
+    const double HCO3 = k.dCO3 * fma(h2, gCO3, h1 * lapCO3);
+
+    const double coA = ltA[q] ? (in_mask[q] ? CA * pA[q] : CA * 0.0) : -CA * k.nu1 * pA[q];
+    const double coC = ltC[q] ? -CC * k.nu2 * pC[q] : CC * pC[q];
+    const double h3 = fma(-k.lambda_, coC, coA);
+    const double dWdx = -k.rhorat * gPhi * fma(2.0 * Phi, F[q], 10.0 * (F[q] - 1.0));
+    const double react = k.Da * omP[q] * h3;
+
+    out[0][q] = -U[q] * gCA - k.Da * fma(1.0 - CA, coA, k.lambda_ * CA * coC);
+    out[1][q] = fma(k.Da, fma(k.lambda_ * (1.0 - CC), coC, CC * coA), -U[q] * gCC);
+    out[2][q] = fma(fma(react, k.delta - cCa, HCa), rPhi[q], -W[q] * gCa);
+    out[3][q] = fma(fma(react, k.delta - cCO3, HCO3), rPhi[q], -W[q] * gCO3);
+    out[4][q] = fma(k.dPhi, lapPhi, react) - fma(dWdx, Phi, W[q] * gPhi);
+  }
+  return fl;
+}
+
+// Generic-path re-evaluation of ONE cell of a pair (q = 0 or 1) after rhs_pair raised its flag:
+// never inlined — it is rare and the hot loop must stay small.
+static __device__ __noinline__ void rhs_pair_slow_cell(const ColumnConsts* k, const fm::Tables* tb, const double* c5,
+                                                       const double* m5, const double* p5, int in_mask,
+                                                       double* out7) {
+  CellRates r;
+  cell_rhs(*k, *tb, c5, m5, p5, in_mask != 0, r);
+#pragma unroll
+  for (int f = 0; f < 5; ++f) out7[f] = r.r[f];
+  out7[5] = r.U;
+  out7[6] = r.W;
+}
+
+__device__ __forceinline__ void rhs_pair_fixup(const ColumnConsts& k, const fm::Tables& tb, const PairFlags& fl,
+                                               const double (&c)[5][2], const double (&mlo)[5],
+                                               const double (&phi)[5], const bool (&in_mask)[2],
+                                               double (&out)[5][2], double (&Uo)[2], double (&Wo)[2]) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (!fl.bad[q]) continue;
+    double cc[5], mm[5], pp[5], o[7];
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      cc[f] = c[f][q];
+      mm[f] = q == 0 ? mlo[f] : c[f][0];
+      pp[f] = q == 0 ? c[f][1] : phi[f];
+    }
+    rhs_pair_slow_cell(&k, &tb, cc, mm, pp, in_mask[q] ? 1 : 0, o);
+#pragma unroll
+    for (int f = 0; f < 5; ++f) out[f][q] = o[f];
+    Uo[q] = o[5];
+    Wo[q] = o[6];
+  }
+}
+
+// Ghost values for the pair that touches a column end (LHeureux_model.py:26-30, py-pde rules):
+//   top, all fields: value v -> 2 v - a_0 ;  bottom CA, CC: curvature 0 -> 2 a_{N-1} - a_{N-2} ;
+//   bottom cCa, cCO3, Phi: derivative 0 -> a_{N-1}.
+__device__ __forceinline__ double top_ghost(const ColumnConsts& k, int f, double a0) {
+  return fma(2.0, k.bc_top[f], -a0);
+}
+__device__ __forceinline__ double bottom_ghost(int f, double a_last, double a_prev) {
+  return f < 2 ? fma(2.0, a_last, -a_prev) : a_last;
+}
+
 }  // namespace marlpde

@@ -2,10 +2,12 @@
 //
 // Replaces one call of LMAHeureuxPorosityDiff.fun_numba -> pde_rhs per column
 // (marlpde/LHeureux_model.py:290-359, :361-522): y[column][field][cell] -> dy/dt, same layout.
-// One thread per depth cell; a CTA covers kCellsPerCta consecutive cells of one column, stages
-// its 5 x (cells + 2 halo) inputs in shared memory with coalesced loads, and every thread then
-// reads its (i-1, i, i+1) triple from the tile.  Memory traffic is 40 B in + 40 B out per cell
-// against ~350 fp64 instructions, so the kernel is fp64-pipe bound, not HBM bound.
+// One thread per PAIR of adjacent depth cells (the same rhs_pair code the persistent RK45 kernel
+// runs, so the single-call parity tests exercise the integrator's arithmetic); a CTA covers
+// 2 * kPairsPerCta consecutive cells of one column.  Each thread reads its own two cells and one
+// neighbour on either side straight from global memory (the neighbours are L1 hits: they are the
+// adjacent threads' own cells).  40 B in + 40 B out per cell against ~200 fp64 instructions:
+// fp64-pipe bound, not HBM bound.
 #include <cuda_runtime.h>
 
 #include "lheureux_device.cuh"
@@ -13,45 +15,62 @@
 
 namespace marlpde {
 
-constexpr int kCellsPerCta = 256;
+constexpr int kPairsPerCta = 128;
 
-__global__ void __launch_bounds__(kCellsPerCta)
+__global__ void __launch_bounds__(kPairsPerCta)
 rhs_batch_kernel(const double* __restrict__ g_y, const marlpde_column_params* __restrict__ g_params,
                  int n_cells, int tiles_per_col, double* __restrict__ g_out) {
   __shared__ ColumnConsts kc;
-  __shared__ double tile[5][kCellsPerCta + 2];
   __shared__ __align__(16) unsigned char tab_raw[fm::kTableBytes];
-  const fm::Tables tb = fm::stage_tables(tab_raw, threadIdx.x, kCellsPerCta);
+  const fm::Tables tb = fm::stage_tables(tab_raw, threadIdx.x, kPairsPerCta);
   const int col = blockIdx.x / tiles_per_col;   // 1-D grid: 65 536+ columns exceed gridDim.y
-  const int cell0 = (blockIdx.x - col * tiles_per_col) * kCellsPerCta;
-  const int cell = cell0 + threadIdx.x;
+  const int pair = (blockIdx.x - col * tiles_per_col) * kPairsPerCta + threadIdx.x;
+  const int cell0 = 2 * pair;
   const double* ycol = g_y + (size_t)col * 5 * n_cells;
   if (threadIdx.x == 0) make_consts(g_params[col], n_cells, kc);
-  // tile index j <-> cell (cell0 - 1 + j), clamped into the column; ghosts are rebuilt below
-  for (int j = threadIdx.x; j < kCellsPerCta + 2; j += kCellsPerCta) {
-    int i = cell0 - 1 + j;
-    i = i < 0 ? 0 : (i > n_cells - 1 ? n_cells - 1 : i);
-#pragma unroll
-    for (int f = 0; f < 5; ++f) tile[f][j] = ycol[(size_t)f * n_cells + i];
-  }
   __syncthreads();
-  if (cell >= n_cells) return;
-  double c[5], m[5], p[5];
-  load_triple(kc, cell, [&](int f, int i) { return tile[f][i - cell0 + 1]; }, c, m, p);
-  CellRates r;
-  cell_rhs(kc, tb, c, m, p, cell >= kc.mask_lo && cell < kc.mask_hi, r);
+
+  const bool valid0 = cell0 < n_cells;          // lanes past the column end run on benign values:
+  const bool valid1 = cell0 + 1 < n_cells;      // rhs_pair votes need all 32 lanes of the warp
+  double c[5][2], mlo[5], phi[5];
+#pragma unroll
+  for (int f = 0; f < 5; ++f) {
+    const double* yf = ycol + (size_t)f * n_cells;
+    c[f][0] = valid0 ? yf[cell0] : 0.5;
+    c[f][1] = valid1 ? yf[cell0 + 1] : 0.5;
+    mlo[f] = (valid0 && cell0 > 0) ? yf[cell0 - 1] : top_ghost(kc, f, c[f][0]);
+    if (cell0 + 2 < n_cells) {
+      phi[f] = yf[cell0 + 2];
+    } else if (valid1) {                         // cell0 + 1 is the last cell of the column
+      phi[f] = bottom_ghost(f, c[f][1], c[f][0]);
+    } else {                                     // cell0 is the last cell: its ghost sits in slot 1
+      c[f][1] = bottom_ghost(f, c[f][0], mlo[f]);
+      phi[f] = c[f][1];
+    }
+  }
+  const bool in_mask[2] = {cell0 >= kc.mask_lo && cell0 < kc.mask_hi,
+                           cell0 + 1 >= kc.mask_lo && cell0 + 1 < kc.mask_hi};
+  double r[5][2], U[2], W[2];
+  PairFlags fl = rhs_pair(kc, tb, c, mlo, phi, in_mask, r, U, W);
+  fl.bad[0] = fl.bad[0] && valid0;
+  fl.bad[1] = fl.bad[1] && valid1;
+  if (fl.bad[0] || fl.bad[1]) rhs_pair_fixup(kc, tb, fl, c, mlo, phi, in_mask, r, U, W);
   double* ocol = g_out + (size_t)col * 5 * n_cells;
 #pragma unroll
-  for (int f = 0; f < 5; ++f) ocol[(size_t)f * n_cells + cell] = r.r[f];
+  for (int f = 0; f < 5; ++f) {
+    if (valid0) ocol[(size_t)f * n_cells + cell0] = r[f][0];
+    if (valid1) ocol[(size_t)f * n_cells + cell0 + 1] = r[f][1];
+  }
 }
 
 cudaError_t launch_rhs_batch(const double* d_y, const marlpde_column_params* d_params, int n_columns,
                              int n_cells, double* d_out, cudaStream_t stream) {
   if (n_columns == 0) return cudaSuccess;
-  const int tiles = (n_cells + kCellsPerCta - 1) / kCellsPerCta;
+  const int pairs = (n_cells + 1) / 2;
+  const int tiles = (pairs + kPairsPerCta - 1) / kPairsPerCta;
   const long long blocks = (long long)tiles * n_columns;
   if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
-  rhs_batch_kernel<<<(unsigned)blocks, kCellsPerCta, 0, stream>>>(d_y, d_params, n_cells, tiles, d_out);
+  rhs_batch_kernel<<<(unsigned)blocks, kPairsPerCta, 0, stream>>>(d_y, d_params, n_cells, tiles, d_out);
   return cudaGetLastError();
 }
 

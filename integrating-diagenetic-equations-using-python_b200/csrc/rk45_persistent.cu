@@ -5,23 +5,30 @@
 // `RungeKutta._step_impl`, `rk_step`, `RkDenseOutput`; ivp.py main loop for t_eval sampling).
 //
 // Design (B200-first):
-//   * persistent CTAs, one per SM; each CTA integrates C columns side by side ("slots"),
-//     thread <-> (slot, depth cell), so N=200 gives 600 of 608 lanes busy;
-//   * the whole integration of a column happens on-chip: state y and the running
-//     y_new / error accumulators live in registers, stage derivatives K1..K6 and a
-//     double-buffered stage-input tile live in shared memory (64 kB per column at N=200);
+//   * persistent CTAs, one per SM; each CTA integrates C columns side by side ("slots");
+//     a thread owns TWO adjacent depth cells of one column (cells 2k, 2k+1): N=200 gives
+//     4 columns x 100 threads = 400 of 416 lanes busy.  Two cells per thread double the
+//     instruction-level parallelism (the register file only holds ~3 warps per scheduler) and
+//     halve every per-instruction overhead (addresses, constants, control) per cell;
+//   * the whole integration of a column happens on-chip.  In REGISTERS: the state y, K1 (which
+//     is last step's K7 — FSAL costs nothing), the current stage input and the current stage
+//     derivative of the thread's two cells.  In SHARED memory: K2..K5 as double2 per thread
+//     (K6 re-uses K2's slot once K2 is dead) and a double-buffered halo-exchange tile through
+//     which a thread sees cell 2k-1 and cell 2k+2.  48 kB per column at N=200.  All shared
+//     arrays use the compile-time stride TP, so every address is `tid*8|16 + immediate`.
 //     HBM is touched only to load y0 and to store snapshots / the final state;
 //   * every column runs its own adaptive controller (own t, h, accept/reject); the error
-//     norm is a warp-shuffle butterfly over aligned cell groups plus one shared-memory hop, summed
-//     in a fixed, slot-independent order: all threads of a column take bit-identical decisions
-//     and a column's trajectory does not depend on what else shares the CTA;
-//   * one block barrier per RHS evaluation (the stage tile is double buffered) and one for
+//     norm is a warp-shuffle butterfly over aligned thread groups plus one shared-memory hop,
+//     summed in a fixed, slot-independent order: all threads of a column take bit-identical
+//     decisions and a column's trajectory does not depend on what else shares the CTA;
+//   * one block barrier per RHS evaluation (the halo tile is double buffered) and one for
 //     the norm: 7 barriers per step attempt;
 //   * finished slots claim the next column from a global atomic queue, so columns with
 //     different step counts do not leave SMs idle.
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "lheureux_device.cuh"
 #include "rk45_persistent.cuh"
@@ -53,118 +60,315 @@ constexpr double SAFETY = 0.9, MIN_FACTOR = 0.2, MAX_FACTOR = 10.0;
 }  // namespace dp
 
 // ---- shared memory carve-up -------------------------------------------------------------
-// K[6][5][T] | tile[2][5][T] | y[5][T] | grp[T>>logG] | consts[C] | ctl[C] | log/exp tables | slot_col[C] | svc flag
+// K[4][5][TP] double2 | tileE[2][5][TP] | tileO[2][5][TP] | grp[TP] | log/exp tables |
+// consts[C] | ctl[C] | slot_col[C] | svc flag
 struct SlotCtl {          // per-slot counters, touched by the slot's leader thread only
   long long n_acc, n_rej, nfev;
 };
 
-struct SmemLayout {
-  int T;        // C * N, padded to a multiple of 32
-  int C;
-  size_t off_K, off_tile, off_y, off_grp, off_consts, off_ctl, off_tab, off_slot, total;
-};
-
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) / 16 * 16; }
 
-__host__ __device__ inline SmemLayout smem_layout(int C, int N, int logG) {
-  SmemLayout L;
-  L.C = C;
-  L.T = ((C * N + 31) / 32) * 32;
-  size_t o = 0;
-  L.off_K = o;      o += sizeof(double) * 6 * 5 * (size_t)L.T;
-  L.off_tile = o;   o += sizeof(double) * 2 * 5 * (size_t)L.T;
-  L.off_y = o;      o += sizeof(double) * 5 * (size_t)L.T;
-  L.off_grp = o;    o += align16(sizeof(double) * (size_t)((L.T >> logG) + 1));
-  L.off_consts = o; o += align16(sizeof(ColumnConsts)) * (size_t)C;
-  L.off_ctl = o;    o += align16(sizeof(SlotCtl)) * (size_t)C;
-  L.off_tab = o;    o += (size_t)fm::kTableBytes;
-  L.off_slot = o;   o += sizeof(int) * (size_t)(C + 4);
-  L.total = align16(o);
-  return L;
-}
+template <int TP, bool YS>
+struct Smem {
+  static constexpr size_t off_K = 0;
+  static constexpr size_t off_Y = off_K + sizeof(double2) * 4 * 5 * TP;        // [5][TP] double2, YS builds only
+  static constexpr size_t off_tE = off_Y + (YS ? sizeof(double2) * 5 * TP : 0);
+  static constexpr size_t off_tO = off_tE + sizeof(double) * 2 * 5 * TP;
+  static constexpr size_t off_grp = off_tO + sizeof(double) * 2 * 5 * TP;
+  static constexpr size_t off_tab = off_grp + sizeof(double) * TP;
+  static constexpr size_t off_var = off_tab + fm::kTableBytes;          // per-slot arrays start here
+  static constexpr size_t slot_bytes = (sizeof(ColumnConsts) + 15) / 16 * 16 + (sizeof(SlotCtl) + 15) / 16 * 16 + 32;
+  __host__ __device__ static size_t total(int C) { return off_var + slot_bytes * (size_t)C + 16; }
+};
 
-static int group_log2(int n_cells) {
+static int group_log2(int threads_per_column) {
   int logG = 0;
-  while (logG < 5 && (n_cells % (2 << logG)) == 0) ++logG;
+  while (logG < 5 && (threads_per_column % (2 << logG)) == 0) ++logG;
   return logG;
 }
 
-int rk45_columns_per_cta(int n_cells, int smem_budget) {
-  if (n_cells < 32 || n_cells > kRk45MaxThreads) return 0;
-  int C = kRk45MaxThreads / n_cells;
-  while (C > 0 && smem_layout(C, n_cells, group_log2(n_cells)).total > (size_t)smem_budget) --C;
+template <int TP, bool YS>
+static int columns_per_cta_t(int n_cells, int smem_budget) {
+  const int Hc = (n_cells + 1) / 2;
+  if (n_cells < 32 || Hc > TP) return 0;
+  int C = TP / Hc;
+  while (C > 0 && Smem<TP, YS>::total(C) > (size_t)smem_budget) --C;
   return C;
 }
 
-size_t rk45_smem_bytes(int C, int n_cells) { return smem_layout(C, n_cells, group_log2(n_cells)).total; }
+// Builds of the kernel (register file: 16K registers per SM sub-partition, so the register cap
+// follows from the warps per sub-partition, not from the thread count alone):
+//   <320,false> 10 warps, <= 168 registers, y in registers      (any n_cells <= 640; N=200: 3 columns)
+//   <400,true>  13 warps, <= 128 registers, y in shared memory  (n_cells <= 800;     N=200: 4 columns)
+// MARLPDE_RK45_BUILD=320|400 overrides the default choice (tuning / tests).
+static int rk45_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = std::getenv("MARLPDE_RK45_BUILD");
+    const int want = s ? std::atoi(s) : 0;
+    v = (want == 400) ? 400 : 320;
+  }
+  return v;
+}
 
-// Stage table: after K_{i+1} has been evaluated (i = 1..5) the next stage input is
-// y + h * sum_{j=0..i} kStage[i-1][j] * K_{j+1}; row 4 holds b (the 5th-order weights, FSAL).
-__constant__ double kStage[5][6] = {
-    {dp::a31, dp::a32, 0, 0, 0, 0},
-    {dp::a41, dp::a42, dp::a43, 0, 0, 0},
-    {dp::a51, dp::a52, dp::a53, dp::a54, 0, 0},
-    {dp::a61, dp::a62, dp::a63, dp::a64, dp::a65, 0},
-    {dp::b1, 0.0, dp::b3, dp::b4, dp::b5, dp::b6}};
-__constant__ double kErr[7] = {dp::e1, 0.0, dp::e3, dp::e4, dp::e5, dp::e6, dp::e7};
+int rk45_columns_per_cta(int n_cells, int smem_budget) {
+  return rk45_variant() == 320 ? columns_per_cta_t<320, false>(n_cells, smem_budget)
+                               : columns_per_cta_t<400, true>(n_cells, smem_budget);
+}
 
-__global__ void __launch_bounds__(kRk45MaxThreads, 1)
-rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __restrict__ g_params,
-                       marlpde_column_state* __restrict__ g_state, int n_columns, int N, int C, int logG,
-                       marlpde_rk45_options opt, const double* __restrict__ g_t_eval,
-                       double* __restrict__ g_snap, int32_t* __restrict__ g_queue) {
+int rk45_max_cells() { return rk45_variant() == 320 ? 640 : 800; }
+
+
+// ---- event monitors (LHeureux_model.py:524-593, all non-terminal, direction 0) -----------------
+// k: 0 min(y)  1 min(CA)  2 min(CC)  3 max(CA+CC)-1  4 max(Phi)-1  5 min(U)  6 max(W).
+// solve_ivp only needs the SIGN of each monitor after every accepted step (ivp.py
+// find_active_events); signs of a min/max follow from per-cell predicates, so detection is an
+// OR-reduction of 21 bits per thread (3 per monitor: beyond the threshold / on it / NaN) that
+// rides on the error-norm barrier — no fp64 reduction unless a sign change has to be located.
+constexpr unsigned kMaxTypeMask = (1u << 3) | (1u << 4) | (1u << 6);   // monitors that are a max
+
+__device__ __forceinline__ unsigned event_bits(const double (&v)[5][2], const double (&U)[2],
+                                               const double (&W)[2], bool has1) {
+  unsigned b = 0;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (q == 1 && !has1) break;
+    bool lt = false, eq = false, nn = false;
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      lt |= v[f][q] < 0.0;
+      eq |= v[f][q] == 0.0;
+      nn |= v[f][q] != v[f][q];
+    }
+    const double CA = v[0][q], CC = v[1][q], s = CA + CC, Phi = v[4][q];
+    b |= (lt ? 1u : 0u) | (eq ? 2u : 0u) | (nn ? 4u : 0u);
+    b |= (CA < 0.0 ? 1u : 0u) << 3 | (CA == 0.0 ? 1u : 0u) << 4 | (CA != CA ? 1u : 0u) << 5;
+    b |= (CC < 0.0 ? 1u : 0u) << 6 | (CC == 0.0 ? 1u : 0u) << 7 | (CC != CC ? 1u : 0u) << 8;
+    b |= (s > 1.0 ? 1u : 0u) << 9 | (s == 1.0 ? 1u : 0u) << 10 | (s != s ? 1u : 0u) << 11;
+    b |= (Phi > 1.0 ? 1u : 0u) << 12 | (Phi == 1.0 ? 1u : 0u) << 13 | (Phi != Phi ? 1u : 0u) << 14;
+    b |= (U[q] < 0.0 ? 1u : 0u) << 15 | (U[q] == 0.0 ? 1u : 0u) << 16 | (U[q] != U[q] ? 1u : 0u) << 17;
+    b |= (W[q] > 0.0 ? 1u : 0u) << 18 | (W[q] == 0.0 ? 1u : 0u) << 19 | (W[q] != W[q] ? 1u : 0u) << 20;
+  }
+  return b;
+}
+
+// 21 predicate bits -> 7 sign classes, 2 bits each: 0 negative, 1 zero, 2 positive, 3 NaN
+__device__ __forceinline__ unsigned event_classes(unsigned bits) {
+  unsigned cls = 0;
+#pragma unroll
+  for (int k = 0; k < MARLPDE_NEVENTS; ++k) {
+    const unsigned b3 = (bits >> (3 * k)) & 7u;
+    const bool maxtype = (kMaxTypeMask >> k) & 1u;
+    unsigned c;
+    if (b3 & 4u) c = 3u;
+    else if (b3 & 1u) c = maxtype ? 2u : 0u;
+    else if (b3 & 2u) c = 1u;
+    else c = maxtype ? 0u : 2u;
+    cls |= c << (2 * k);
+  }
+  return cls;
+}
+
+// ivp.py find_active_events with direction 0: (g <= 0 & g_new >= 0) | (g >= 0 & g_new <= 0)
+__device__ __forceinline__ unsigned active_events(unsigned cls_old, unsigned cls_new) {
+  unsigned act = 0;
+#pragma unroll
+  for (int k = 0; k < MARLPDE_NEVENTS; ++k) {
+    const unsigned a = (cls_old >> (2 * k)) & 3u, b = (cls_new >> (2 * k)) & 3u;
+    const bool a_le = a <= 1u, a_ge = a == 1u || a == 2u, b_le = b <= 1u, b_ge = b == 1u || b == 2u;
+    if ((a_le && b_ge) || (a_ge && b_le)) act |= 1u << k;
+  }
+  return act;
+}
+
+// scipy.optimize.brentq (Zeros/brentq.c) as a resumable state machine: every function value needs
+// a block-wide reduction, so the caller feeds values one at a time.  Transliteration of
+// oracle/lheureux_oracle.py::brentq_restated, which tests pin bit-for-bit to the installed SciPy;
+// explicit round-to-nearest intrinsics keep nvcc from contracting a*b+c (brentq.c is not).
+struct BrentState {
+  double xpre, xcur, xblk, fpre, fcur, fblk, spre, scur;
+  int stage, iter;
+  __device__ __forceinline__ void init(double xa, double xb) {
+    xpre = xa;
+    xcur = xb;
+    xblk = fblk = spre = scur = 0.0;
+    fpre = fcur = 0.0;
+    stage = 0;
+    iter = 0;
+  }
+  // feed f(xeval); returns true when finished (root set), else xeval = next abscissa
+  __device__ bool feed(double g, double& xeval, double& root) {
+    const double tol = 4.0 * 2.220446049250313e-16;
+    if (stage == 0) {
+      fpre = g;
+      if (fpre == 0.0) { root = xpre; return true; }
+      stage = 1;
+      xeval = xcur;
+      return false;
+    }
+    fcur = g;
+    if (stage == 1) {
+      if (fcur == 0.0) { root = xcur; return true; }
+      if (signbit(fpre) == signbit(fcur)) {      // SciPy raises ValueError here; keep the closer end
+        root = fabs(fpre) < fabs(fcur) ? xpre : xcur;
+        return true;
+      }
+      stage = 2;
+    }
+    if (iter >= 100) { root = xcur; return true; }
+    ++iter;
+    if (fpre != 0.0 && fcur != 0.0 && signbit(fpre) != signbit(fcur)) {
+      xblk = xpre;
+      fblk = fpre;
+      spre = scur = __dsub_rn(xcur, xpre);
+    }
+    if (fabs(fblk) < fabs(fcur)) {
+      xpre = xcur; xcur = xblk; xblk = xpre;
+      fpre = fcur; fcur = fblk; fblk = fpre;
+    }
+    const double delta = __dmul_rn(__dadd_rn(tol, __dmul_rn(tol, fabs(xcur))), 0.5);
+    const double sbis = __dmul_rn(__dsub_rn(xblk, xcur), 0.5);
+    if (fcur == 0.0 || fabs(sbis) < delta) { root = xcur; return true; }
+    if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
+      double stry;
+      if (xpre == xblk) {
+        stry = __ddiv_rn(__dmul_rn(-fcur, __dsub_rn(xcur, xpre)), __dsub_rn(fcur, fpre));
+      } else {
+        const double dpre = __ddiv_rn(__dsub_rn(fpre, fcur), __dsub_rn(xpre, xcur));
+        const double dblk = __ddiv_rn(__dsub_rn(fblk, fcur), __dsub_rn(xblk, xcur));
+        stry = __ddiv_rn(__dmul_rn(-fcur, __dsub_rn(__dmul_rn(fblk, dblk), __dmul_rn(fpre, dpre))),
+                         __dmul_rn(__dmul_rn(dblk, dpre), __dsub_rn(fblk, fpre)));
+      }
+      if (__dmul_rn(2.0, fabs(stry)) < fmin(fabs(spre), __dsub_rn(__dmul_rn(3.0, fabs(sbis)), delta))) {
+        spre = scur;
+        scur = stry;
+      } else {
+        spre = sbis;
+        scur = sbis;
+      }
+    } else {
+      spre = sbis;
+      scur = sbis;
+    }
+    xpre = xcur;
+    fpre = fcur;
+    if (fabs(scur) > delta) xcur = __dadd_rn(xcur, scur);
+    else xcur = __dadd_rn(xcur, sbis > 0.0 ? delta : -delta);
+    xeval = xcur;
+    return false;
+  }
+};
+
+struct Rk45Args {
+  double* g_y;
+  const marlpde_column_params* g_params;
+  marlpde_column_state* g_state;
+  const double* g_t_eval;
+  double* g_snap;
+  int32_t* g_queue;
+  int32_t* g_ev_counts;      // [n_columns][7]
+  double* g_ev_times;        // [n_columns][7][event_capacity]
+  int n_columns, N, C, logG;
+  marlpde_rk45_options opt;
+};
+
+template <int TP, bool YS>
+__global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel(const Rk45Args A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SmemLayout L = smem_layout(C, N, logG);
-  const int T = L.T;
-  double* const sK = reinterpret_cast<double*>(smem_raw + L.off_K);        // [6][5][T]
-  double* const sTile = reinterpret_cast<double*>(smem_raw + L.off_tile);  // [2][5][T]
-  double* const sY = reinterpret_cast<double*>(smem_raw + L.off_y);        // [5][T]
-  double* const sGrp = reinterpret_cast<double*>(smem_raw + L.off_grp);    // [T >> logG]
-  int* const sSlotCol = reinterpret_cast<int*>(smem_raw + L.off_slot);     // [C]
-  int* const sSvc = sSlotCol + C;
-
+  using L = Smem<TP, YS>;
   const int tid = threadIdx.x;
-  const fm::Tables tb = fm::stage_tables(smem_raw + L.off_tab, tid, blockDim.x);
-  const bool active = tid < C * N;
-  const int slot = active ? tid / N : C;          // C = "no slot" for the padding lanes
-  const int cell = active ? tid - slot * N : 0;
-  const int base = slot * N;                       // first tile index of my column
-  const ColumnConsts& kc = *reinterpret_cast<const ColumnConsts*>(
-      smem_raw + L.off_consts + align16(sizeof(ColumnConsts)) * (active ? slot : 0));
-  SlotCtl& ctl = *reinterpret_cast<SlotCtl*>(smem_raw + L.off_ctl + align16(sizeof(SlotCtl)) * (active ? slot : 0));
-  const bool leader = active && cell == 0;
-  // Error-norm reduction tree, identical for every slot so that a column's trajectory does not
-  // depend on where it is scheduled: cells are summed in aligned groups of G = 2^k lanes
-  // (G = largest power of two <= 32 dividing N, hence dividing every slot base) by an xor
-  // butterfly, then the N/G group sums are added in cell order from shared memory.
-  const int G = 1 << logG;
-  const int nGroups = N >> logG;
-  const int grpBase = base >> logG;
+  const int N = A.N, C = A.C;
+  const int Hc = (N + 1) >> 1;                     // threads per column
+  double2* const sK = reinterpret_cast<double2*>(smem_raw + L::off_K) + tid;         // [4][5][TP]
+  double2* const sY = reinterpret_cast<double2*>(smem_raw + L::off_Y) + tid;         // [5][TP] (YS builds)
+  double* const sE = reinterpret_cast<double*>(smem_raw + L::off_tE);               // [2][5][TP] even cells
+  double* const sO = reinterpret_cast<double*>(smem_raw + L::off_tO);               // [2][5][TP] odd cells
+  double* const sGrp = reinterpret_cast<double*>(smem_raw + L::off_grp);            // [TP >> logG]
+  unsigned char* const var = smem_raw + L::off_var;
+  const size_t consts_sz = align16(sizeof(ColumnConsts)), ctl_sz = align16(sizeof(SlotCtl));
+  int* const sSlotCol = reinterpret_cast<int*>(var + (consts_sz + ctl_sz) * C);     // [C]
+  unsigned* const sEv = reinterpret_cast<unsigned*>(sSlotCol + C);                  // [2][C] bits of y_new
+  unsigned* const sEv0 = sEv + 2 * C;                                               // [C] bits of a fresh y
+  int* const sSvc = reinterpret_cast<int*>(sEv0 + C);
 
-  // per-thread column state (everything else lives in shared memory)
+  const fm::Tables tb = fm::stage_tables(smem_raw + L::off_tab, tid, blockDim.x);
+  const bool active = tid < C * Hc;
+  const int slot = active ? tid / Hc : 0;
+  const int pr = active ? tid - slot * Hc : 0;     // pair index inside the column
+  const int cell0 = 2 * pr;
+  const bool has1 = cell0 + 1 < N;                 // false only for the last thread of an odd-N column
+  const bool first = pr == 0, last = pr == Hc - 1;
+  const ColumnConsts& kc = *reinterpret_cast<const ColumnConsts*>(var + consts_sz * slot);
+  SlotCtl& ctl = *reinterpret_cast<SlotCtl*>(var + consts_sz * C + ctl_sz * slot);
+  const bool leader = active && first;
+  // halo reads: cell 2k-1 is the odd cell of thread tid-1, cell 2k+2 the even cell of thread tid+1
+  const double* const haloM = sO + (first ? tid : tid - 1);
+  const double* const haloP = sE + (last ? tid : tid + 1);
+  double* const myE = sE + tid;
+  double* const myO = sO + tid;
+  // Error-norm reduction tree, identical for every slot so that a column's trajectory does not
+  // depend on where it is scheduled: threads are summed in aligned groups of G = 2^k lanes
+  // (G = largest power of two <= 32 dividing Hc, hence dividing every slot base) by an xor
+  // butterfly, then the Hc/G group sums are added in order from shared memory.
+  const int logG = A.logG;
+  const int G = 1 << logG;
+  const int nGroups = Hc >> logG;
+  const double* const grpRow = sGrp + ((slot * Hc) >> logG);
+  const double inv_n = 1.0 / (double)(5 * N);
+  // event monitors: lanes of my slot inside my warp (slots are not warp aligned)
+  const bool ev_on = (A.opt.flags & MARLPDE_FLAG_EVENTS) != 0;
+  const unsigned peers = __match_any_sync(0xffffffffu, active ? slot : -1);
+  const bool peer_lead = (tid & 31) == (__ffs(peers) - 1);
+  const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((tid & 31) & ~(G - 1));
+  unsigned ev_prev = 0, ev_new_s = 0, ev_todo = 0;   // sign classes at y / at the parked y_new; monitors to locate
+  bool need_prev = false, parked = false;
+  double factor_s = 1.0;
+  unsigned it = 0;                                    // loop counter (parity selects the sEv buffer)
+
+  // per-thread column state
   int col = -1;                 // column index being integrated by my slot, -1 = idle
-  bool exhausted = false;       // the work queue ran dry
+  bool exhausted = !active;     // the work queue ran dry (padding lanes never claim)
   bool rejected = false;
   double t = 0.0, h_abs = 0.0, h = 0.0, t_new = 0.0;
   int next_eval = 0;
   int attempts = 0;             // step attempts made for this column in this launch
+  bool in_mask[2] = {false, false};
+  double y[5][2], k1[5][2], c[5][2], r[5][2];
+#pragma unroll
+  for (int f = 0; f < 5; ++f)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      y[f][q] = 0.5;
+      k1[f][q] = 0.0;
+      c[f][q] = 0.5;
+      r[f][q] = 0.0;
+    }
 
-  auto tileAt = [&](int b, int f, int i) -> double& { return sTile[(b * 5 + f) * T + i]; };
-  auto KAt = [&](int s, int f) -> double& { return sK[(s * 5 + f) * T + tid]; };
-  auto yAt = [&](int f) -> double& { return sY[f * T + tid]; };
-
-  // RHS of my cell from stage tile `b` (one code instance, see the stage loop)
-  auto eval_rhs = [&](int b, CellRates& out) {
-    double c[5], m[5], p[5];
-    load_triple(kc, cell, [&](int f, int i) { return tileAt(b, f, base + i); }, c, m, p);
-    cell_rhs(kc, tb, c, m, p, cell >= kc.mask_lo && cell < kc.mask_hi, out);
+  auto tile_store = [&](int b) {
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      myE[(b * 5 + f) * TP] = c[f][0];
+      myO[(b * 5 + f) * TP] = c[f][1];
+    }
+  };
+  auto Kst = [&](int s, int f, double v0, double v1) { sK[(s * 5 + f) * TP] = make_double2(v0, v1); };
+  auto Kld = [&](int s, int f) -> double2 { return sK[(s * 5 + f) * TP]; };
+  // the state y of the thread's two cells: registers, or (YS builds) one double2 per field in shared memory
+  auto Yld = [&](int f) -> double2 { return YS ? sY[f * TP] : make_double2(y[f][0], y[f][1]); };
+  auto Yst = [&](int f, double v0, double v1) {
+    if (YS) {
+      sY[f * TP] = make_double2(v0, v1);
+    } else {
+      y[f][0] = v0;
+      y[f][1] = v1;
+    }
   };
 
   // scipy _step_impl: min_step = 10 * |nextafter(t, inf) - t| ; clamp h_abs at the start of a step
   auto min_step_at = [&](double tt) { return 10.0 * fabs(nextafter(tt, (double)INFINITY) - tt); };
   auto begin_step = [&]() {
     const double ms = min_step_at(t);
-    if (h_abs > opt.max_step) h_abs = opt.max_step;
+    if (h_abs > A.opt.max_step) h_abs = A.opt.max_step;
     else if (h_abs < ms) h_abs = ms;
     rejected = false;
   };
@@ -172,14 +376,19 @@ rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __
     if (h_abs < min_step_at(t)) return false;
     h = h_abs;
     t_new = t + h;
-    if (t_new - opt.t_bound > 0.0) t_new = opt.t_bound;
+    if (t_new - A.opt.t_bound > 0.0) t_new = A.opt.t_bound;
     h = t_new - t;
     h_abs = fabs(h);
     return true;
   };
   auto retire = [&](int status) {  // store the column's end point and free the slot
+    double* gy = A.g_y + (size_t)col * 5 * N + cell0;
 #pragma unroll
-    for (int f = 0; f < 5; ++f) g_y[((size_t)col * 5 + f) * N + cell] = yAt(f);
+    for (int f = 0; f < 5; ++f) {
+      const double2 yv = Yld(f);
+      gy[(size_t)f * N] = yv.x;
+      if (has1) gy[(size_t)f * N + 1] = yv.y;
+    }
     if (leader) {
       marlpde_column_state st;
       st.t = t;
@@ -189,30 +398,127 @@ rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __
       st.nfev = ctl.nfev;
       st.status = status;
       st.next_eval = next_eval;
-      g_state[col] = st;
+      A.g_state[col] = st;
     }
     col = -1;
-  };
-  auto write_stage2 = [&]() {
 #pragma unroll
-    for (int f = 0; f < 5; ++f) tileAt(1, f, tid) = fma(h * dp::a21, KAt(0, f), yAt(f));
+    for (int f = 0; f < 5; ++f) c[f][0] = c[f][1] = 0.5;   // idle lanes evaluate the RHS on benign values
+  };
+  auto stage2_input = [&]() {
+    const double ha = h * dp::a21;
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      const double2 yv = Yld(f);
+      c[f][0] = fma(ha, k1[f][0], yv.x);
+      c[f][1] = fma(ha, k1[f][1], yv.y);
+    }
+    tile_store(1);
+  };
+  // quartic dense output of the step just computed (scipy RkDenseOutput): y(t + x h) for my two cells;
+  // needs K1 (k1), K3..K5 and K6 (shared memory) and K7 (= r), i.e. must run before the commit
+  auto interp_all = [&](double x, double (&out)[5][2]) {
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      const double2 K3 = Kld(1, f), K4 = Kld(2, f), K5 = Kld(3, f), K6 = Kld(0, f), yv = Yld(f);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const double v3 = q ? K3.y : K3.x, v4 = q ? K4.y : K4.x, v5 = q ? K5.y : K5.x, v6 = q ? K6.y : K6.x;
+        double qq[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          double sacc = dp::P[0][j] * k1[f][q];
+          sacc = fma(dp::P[2][j], v3, sacc);
+          sacc = fma(dp::P[3][j], v4, sacc);
+          sacc = fma(dp::P[4][j], v5, sacc);
+          sacc = fma(dp::P[5][j], v6, sacc);
+          qq[j] = fma(dp::P[6][j], r[f][q], sacc);
+        }
+        const double poly = x * (qq[0] + x * (qq[1] + x * (qq[2] + x * qq[3])));
+        out[f][q] = fma(h, poly, q ? yv.y : yv.x);
+      }
+    }
+  };
+  // an accepted step becomes the column's state: t_eval samples, y <- y_new, K1 <- K7 (FSAL)
+  auto commit = [&](double factor) {
+    // dense output for t_eval points in (t, t_new] (ivp.py: searchsorted side='right')
+    while (next_eval < A.opt.n_eval) {
+      const double te = A.g_t_eval[next_eval];
+      if (!(te <= t_new)) break;
+      double ys[5][2];
+      interp_all((te - t) / h, ys);
+      double* gs = A.g_snap + ((size_t)col * A.opt.n_eval + next_eval) * 5 * N + cell0;
+#pragma unroll
+      for (int f = 0; f < 5; ++f) {
+        gs[(size_t)f * N] = ys[f][0];
+        if (has1) gs[(size_t)f * N + 1] = ys[f][1];
+      }
+      ++next_eval;
+    }
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      Yst(f, c[f][0], c[f][1]);
+      k1[f][0] = r[f][0];
+      k1[f][1] = r[f][1];
+    }
+    t = t_new;
+    h_abs *= factor;
+    if (leader) ctl.n_acc += 1;
+    if (t >= A.opt.t_bound) {
+      retire(MARLPDE_STATUS_FINISHED);
+    } else if (A.opt.max_steps > 0 && (long long)attempts >= A.opt.max_steps) {
+      retire(MARLPDE_STATUS_STEP_BUDGET);
+    } else {
+      begin_step();
+      if (!begin_attempt()) retire(MARLPDE_STATUS_STEP_TOO_SMALL);
+    }
+  };
+  // value of monitor k on my two cells at y(t + x h), in "min form" (a max is the min of the negation)
+  auto event_partial = [&](int k, double x) -> double {
+    double ys[5][2];
+    interp_all(x, ys);
+    double v[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const double Phi = ys[4][q];
+      double UW = 0.0;
+      if (k >= 5) {   // same arithmetic as rhs_pair, so detection and location agree
+        const double F = 1.0 - fm::exp(tb, fma(-10.0, fm::rcp3(Phi), 10.0));
+        const double Phi2 = Phi * Phi;
+        UW = k == 5 ? fma(kc.rhorat * (Phi2 * Phi), F * fm::rcp3(1.0 - Phi), kc.presum)
+                    : -fma(-kc.rhorat * Phi2, F, kc.presum);
+      }
+      switch (k) {
+        case 0: v[q] = fmin(fmin(fmin(ys[0][q], ys[1][q]), fmin(ys[2][q], ys[3][q])), ys[4][q]); break;
+        case 1: v[q] = ys[0][q]; break;
+        case 2: v[q] = ys[1][q]; break;
+        case 3: v[q] = -(ys[0][q] + ys[1][q]); break;
+        case 4: v[q] = -Phi; break;
+        default: v[q] = UW; break;
+      }
+    }
+    return has1 ? fmin(v[0], v[1]) : v[0];
   };
 
-  if (tid == 0) *sSvc = 0;
+  // per-slot constants, counters and flags start as zeros: slots that never receive a column still
+  // run the (ignored) RHS evaluations of their lanes, on benign values
+  for (int i = tid; i < (int)((L::slot_bytes * (size_t)C + 16) / 4); i += blockDim.x)
+    reinterpret_cast<int*>(var)[i] = 0;
   __syncthreads();
 
   bool fresh = false;           // column just loaded: K1 = f(y) still to be evaluated (stage i = 0)
   for (;;) {
     // ================= stage 2 input + slot service =======================================
-    if (col >= 0) write_stage2();
-    if (leader && col < 0 && !exhausted) *sSvc = 1;
+    ++it;
+    if (col >= 0 && !parked) stage2_input();
+    if (leader && col < 0 && !exhausted) atomicOr(sSvc, 1);
     int nlive = __syncthreads_count(col >= 0);
     int i0 = 1;
-    if (*sSvc) {
+    const int svc = *sSvc;
+    if (svc) {
       // -- claim columns for idle slots
       if (leader && col < 0 && !exhausted) {
-        const int c = atomicAdd(g_queue, 1);
-        sSlotCol[slot] = c < n_columns ? c : -1;
+        const int cc = atomicAdd(A.g_queue, 1);
+        sSlotCol[slot] = cc < A.n_columns ? cc : -1;
       }
       __syncthreads();
       if (tid == 0) *sSvc = 0;
@@ -221,26 +527,33 @@ rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __
         if (col < 0) {
           exhausted = true;
         } else {
-          const marlpde_column_state st = g_state[col];
+          const marlpde_column_state st = A.g_state[col];
           if (leader) {
             ColumnConsts tmp;
-            make_consts(g_params[col], N, tmp);
+            make_consts(A.g_params[col], N, tmp);
             *const_cast<ColumnConsts*>(&kc) = tmp;
             ctl.n_acc = st.n_accepted;
             ctl.n_rej = st.n_rejected;
             ctl.nfev = st.nfev;
+            sEv0[slot] = 0u;
           }
+          need_prev = true;
+          const int mlo_ = A.g_params[col].mask_lo, mhi_ = A.g_params[col].mask_hi;
+          in_mask[0] = cell0 >= mlo_ && cell0 < mhi_;
+          in_mask[1] = cell0 + 1 >= mlo_ && cell0 + 1 < mhi_;
           attempts = 0;
           t = st.t;
           h_abs = st.h_abs;
           next_eval = st.next_eval;
+          const double* gy = A.g_y + (size_t)col * 5 * N + cell0;
 #pragma unroll
           for (int f = 0; f < 5; ++f) {
-            const double v = g_y[((size_t)col * 5 + f) * N + cell];
-            yAt(f) = v;
-            tileAt(0, f, tid) = v;
+            c[f][0] = gy[(size_t)f * N];
+            c[f][1] = has1 ? gy[(size_t)f * N + 1] : 0.0;
+            Yst(f, c[f][0], c[f][1]);
           }
-          if (t >= opt.t_bound) {            // nothing to integrate
+          tile_store(0);
+          if (t >= A.opt.t_bound) {            // nothing to integrate
             retire(MARLPDE_STATUS_FINISHED);
           } else {
             begin_step();
@@ -249,120 +562,245 @@ rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __
           }
         }
       }
-      nlive = __syncthreads_count(col >= 0);   // also publishes consts, y and tile 0 of the new columns
+      if (svc & 2) {
+        // -- locate the events of parked steps (ivp.py handle_events -> brentq on the dense output),
+        //    then commit them.  Every function value is a reduction over the column: one barrier each.
+        //    Scratch: rows 0/1 of halo tile 0 (dead here), indexed inside the slot's own thread range.
+        BrentState bs;
+        int k = 0, buf = 0;
+        double xeval = t;
+        bool working = parked && ev_todo != 0u;
+        if (working) {
+          k = __ffs(ev_todo) - 1;
+          ev_todo &= ev_todo - 1u;
+          bs.init(t, t_new);
+        }
+        for (;;) {
+          double* const scr = sE + buf * TP + slot * Hc;
+          if (working) {
+            double v = event_partial(k, (xeval - t) / h);
+            for (int o = G >> 1; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(gmask, v, o));
+            if ((pr & (G - 1)) == 0) scr[pr >> logG] = v;
+          }
+          if (!__syncthreads_or(working)) break;
+          if (working) {
+            double m = scr[0];
+            for (int gi = 1; gi < nGroups; ++gi) m = fmin(m, scr[gi]);
+            const double g = (k == 3 || k == 4) ? (-m) - 1.0 : (k == 6 ? -m : m);
+            double root = 0.0;
+            if (bs.feed(g, xeval, root)) {
+              if (leader) {
+                int32_t* cnt = A.g_ev_counts + (size_t)col * MARLPDE_NEVENTS + k;
+                const int n = *cnt;
+                if (n < A.opt.event_capacity)
+                  A.g_ev_times[((size_t)col * MARLPDE_NEVENTS + k) * A.opt.event_capacity + n] = root;
+                *cnt = n + 1;
+              }
+              if (ev_todo != 0u) {
+                k = __ffs(ev_todo) - 1;
+                ev_todo &= ev_todo - 1u;
+                bs.init(t, t_new);
+                xeval = t;
+              } else {
+                working = false;
+              }
+            }
+          }
+          buf ^= 1;
+        }
+        if (parked) {
+          parked = false;
+          ev_prev = ev_new_s;
+          commit(factor_s);
+          if (col >= 0) stage2_input();
+        }
+      }
+      nlive = __syncthreads_count(col >= 0);   // also publishes consts and tile 0 of the new columns
       if (nlive == 0) continue;                // everything claimed retired at once: look again
       i0 = 0;
     }
     if (nlive == 0) break;
 
-    // ================= stages: i = 1..6 evaluates K_{i+1} from tile (i & 1) =================
+    // ================= stages: i = 1..6 evaluates K_{i+1} from halo tile (i & 1) ============
     // (i = 0, only after a slot service: K1 = f(y) of freshly loaded columns from tile 0.)
     // ONE code instance of the RHS serves every stage: the kernel stays inside the instruction
-    // cache and K1 of a resumed column is bit-identical to the FSAL K7 it replaces.
+    // cache and K1 of a resumed column is bit-identical to the FSAL K7 it replaces.  Every lane
+    // evaluates (votes inside need whole warps); only live slots consume the result.
     const bool live = col >= 0;
-    CellRates r;
+    double U[2], W[2];
 #pragma unroll 1
     for (int i = i0; i <= 6; ++i) {
       if (i > i0) __syncthreads();
-      if (live && (i > 0 || fresh)) {
-        eval_rhs(i & 1, r);
-        if (i == 0) {
-#pragma unroll
-          for (int f = 0; f < 5; ++f) KAt(0, f) = r.r[f];
-          if (leader) ctl.nfev += 1;
-          write_stage2();
-          fresh = false;
-        } else if (i < 6) {
-          // store K_{i+1}; next stage input (row 4 = y_new) into the other tile
-          const double* row = kStage[i - 1];
-#pragma unroll
-          for (int f = 0; f < 5; ++f) {
-            const double k = r.r[f];
-            KAt(i, f) = k;
-            double acc = row[i] * k;
-            for (int j = i - 1; j >= 0; --j) acc = fma(row[j], KAt(j, f), acc);
-            tileAt((i + 1) & 1, f, tid) = fma(h, acc, yAt(f));
-          }
-        }
-      }
-    }
-    // ---- K7 = f(y_new) is in r; error estimate and its norm
-    double part = 0.0;
-    if (live) {
+      const int tb_ = (i & 1) * 5 * TP;
+      double mlo[5], phi[5];
 #pragma unroll
       for (int f = 0; f < 5; ++f) {
-        double e = kErr[6] * r.r[f];
-#pragma unroll
-        for (int j = 5; j >= 0; --j)
-          if (j != 1) e = fma(kErr[j], KAt(j, f), e);
-        const double ynew = tileAt(0, f, tid);
-        const double scale = fma(fmax(fabs(yAt(f)), fabs(ynew)), opt.rtol, opt.atol);
-        const double q = (h * e) * fm::rcp(scale);
-        part = fma(q, q, part);
+        const double hm = haloM[tb_ + f * TP], hp = haloP[tb_ + f * TP];
+        mlo[f] = first ? top_ghost(kc, f, c[f][0]) : hm;
+        if (!last) {
+          phi[f] = hp;
+        } else if (has1) {
+          phi[f] = bottom_ghost(f, c[f][1], c[f][0]);
+        } else {                               // odd N: the ghost of cell N-1 sits in the pair's slot 1
+          c[f][1] = bottom_ghost(f, c[f][0], mlo[f]);
+          phi[f] = c[f][1];
+        }
       }
+      PairFlags fl = rhs_pair(kc, tb, c, mlo, phi, in_mask, r, U, W);
+      fl.bad[0] = fl.bad[0] && live;
+      fl.bad[1] = fl.bad[1] && live && has1;
+      if (fl.bad[0] || fl.bad[1]) rhs_pair_fixup(kc, tb, fl, c, mlo, phi, in_mask, r, U, W);
+      if (!has1) {
+#pragma unroll
+        for (int f = 0; f < 5; ++f) r[f][1] = 0.0;
+      }
+      if (!live) continue;
+      switch (i) {
+        case 0:
+          if (fresh) {
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {
+              k1[f][0] = r[f][0];
+              k1[f][1] = r[f][1];
+            }
+            if (leader) ctl.nfev += 1;
+            if (ev_on) {     // signs of the monitors at the start point (ivp.py: g = event(t0, y0))
+              const unsigned bv = __reduce_or_sync(peers, event_bits(c, U, W, has1));
+              if (peer_lead && bv) atomicOr(&sEv0[slot], bv);
+            }
+            stage2_input();
+            fresh = false;
+          }
+          break;
+        case 1:   // r = K2
+#pragma unroll
+          for (int f = 0; f < 5; ++f) {
+            Kst(0, f, r[f][0], r[f][1]);
+            const double2 yv = Yld(f);
+            c[f][0] = fma(h, fma(dp::a31, k1[f][0], dp::a32 * r[f][0]), yv.x);
+            c[f][1] = fma(h, fma(dp::a31, k1[f][1], dp::a32 * r[f][1]), yv.y);
+          }
+          tile_store(0);
+          break;
+        case 2:   // r = K3
+#pragma unroll
+          for (int f = 0; f < 5; ++f) {
+            Kst(1, f, r[f][0], r[f][1]);
+            const double2 K2 = Kld(0, f), yv = Yld(f);
+            c[f][0] = fma(h, fma(dp::a41, k1[f][0], fma(dp::a42, K2.x, dp::a43 * r[f][0])), yv.x);
+            c[f][1] = fma(h, fma(dp::a41, k1[f][1], fma(dp::a42, K2.y, dp::a43 * r[f][1])), yv.y);
+          }
+          tile_store(1);
+          break;
+        case 3:   // r = K4
+#pragma unroll
+          for (int f = 0; f < 5; ++f) {
+            Kst(2, f, r[f][0], r[f][1]);
+            const double2 K2 = Kld(0, f), K3 = Kld(1, f), yv = Yld(f);
+            c[f][0] = fma(h, fma(dp::a51, k1[f][0], fma(dp::a52, K2.x, fma(dp::a53, K3.x, dp::a54 * r[f][0]))),
+                          yv.x);
+            c[f][1] = fma(h, fma(dp::a51, k1[f][1], fma(dp::a52, K2.y, fma(dp::a53, K3.y, dp::a54 * r[f][1]))),
+                          yv.y);
+          }
+          tile_store(0);
+          break;
+        case 4:   // r = K5
+#pragma unroll
+          for (int f = 0; f < 5; ++f) {
+            Kst(3, f, r[f][0], r[f][1]);
+            const double2 K2 = Kld(0, f), K3 = Kld(1, f), K4 = Kld(2, f), yv = Yld(f);
+            c[f][0] = fma(h, fma(dp::a61, k1[f][0],
+                                 fma(dp::a62, K2.x, fma(dp::a63, K3.x, fma(dp::a64, K4.x, dp::a65 * r[f][0])))),
+                          yv.x);
+            c[f][1] = fma(h, fma(dp::a61, k1[f][1],
+                                 fma(dp::a62, K2.y, fma(dp::a63, K3.y, fma(dp::a64, K4.y, dp::a65 * r[f][1])))),
+                          yv.y);
+          }
+          tile_store(1);
+          break;
+        case 5:   // r = K6 (stored over the dead K2): c becomes y_new
+#pragma unroll
+          for (int f = 0; f < 5; ++f) {
+            const double2 K3 = Kld(1, f), K4 = Kld(2, f), K5 = Kld(3, f), yv = Yld(f);
+            Kst(0, f, r[f][0], r[f][1]);
+            c[f][0] = fma(h, fma(dp::b1, k1[f][0], fma(dp::b3, K3.x, fma(dp::b4, K4.x, fma(dp::b5, K5.x, dp::b6 * r[f][0])))),
+                          yv.x);
+            c[f][1] = fma(h, fma(dp::b1, k1[f][1], fma(dp::b3, K3.y, fma(dp::b4, K4.y, fma(dp::b5, K5.y, dp::b6 * r[f][1])))),
+                          yv.y);
+          }
+          tile_store(0);
+          break;
+        default:  // i == 6: r = K7 = f(y_new); monitor signs at y_new ride on the norm barrier
+          if (ev_on) {
+            const unsigned bv = __reduce_or_sync(peers, event_bits(c, U, W, has1));
+            if (peer_lead && bv) atomicOr(&sEv[(it & 1u) * C + slot], bv);
+          }
+          break;
+      }
+    }
+    // ---- K7 = f(y_new) is in r, y_new in c; error estimate and its norm
+    double part = 0.0;
+    if (live) {
+      double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+      for (int f = 0; f < 5; ++f) {
+        const double2 K3 = Kld(1, f), K4 = Kld(2, f), K5 = Kld(3, f), K6 = Kld(0, f), yv = Yld(f);
+        const double e0 = fma(dp::e1, k1[f][0], fma(dp::e3, K3.x, fma(dp::e4, K4.x, fma(dp::e5, K5.x, fma(dp::e6, K6.x, dp::e7 * r[f][0])))));
+        const double e1_ = fma(dp::e1, k1[f][1], fma(dp::e3, K3.y, fma(dp::e4, K4.y, fma(dp::e5, K5.y, fma(dp::e6, K6.y, dp::e7 * r[f][1])))));
+        const double s0 = fma(fmax(fabs(yv.x), fabs(c[f][0])), A.opt.rtol, A.opt.atol);
+        const double s1 = fma(fmax(fabs(yv.y), fabs(c[f][1])), A.opt.rtol, A.opt.atol);
+        const double q0 = (h * e0) * fm::rcp3(s0);
+        const double q1 = (h * e1_) * fm::rcp3(s1);
+        p0 = fma(q0, q0, p0);
+        p1 = fma(q1, q1, p1);
+      }
+      part = has1 ? p0 + p1 : p0;
     }
     {
       double a = part;
       for (int o = G >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (live && (cell & (G - 1)) == 0) sGrp[tid >> logG] = a;
+      if (live && (pr & (G - 1)) == 0) sGrp[tid >> logG] = a;
     }
     __syncthreads();
     if (live) {
-      // group sums in cell order (4 interleaved partial sums, fixed association)
+      // group sums in order (4 interleaved partial sums, fixed association)
       double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      const double* gp = sGrp + grpBase;
       int gi = 0;
       for (; gi + 4 <= nGroups; gi += 4) {
-        s0 += gp[gi];
-        s1 += gp[gi + 1];
-        s2 += gp[gi + 2];
-        s3 += gp[gi + 3];
+        s0 += grpRow[gi];
+        s1 += grpRow[gi + 1];
+        s2 += grpRow[gi + 2];
+        s3 += grpRow[gi + 3];
       }
-      for (; gi < nGroups; ++gi) s0 += gp[gi];
+      for (; gi < nGroups; ++gi) s0 += grpRow[gi];
       const double sum = (s0 + s1) + (s2 + s3);
-      const double err_norm = sqrt(sum / (double)(5 * N));
+      const double err_norm = sqrt(sum * inv_n);
       if (leader) ctl.nfev += 6;
       attempts += 1;
+      unsigned ev_bits_new = 0u;
+      if (ev_on) {
+        if (need_prev) {
+          ev_prev = event_classes(sEv0[slot]);
+          need_prev = false;
+        }
+        ev_bits_new = sEv[(it & 1u) * C + slot];
+        if (leader) sEv[((it + 1u) & 1u) * C + slot] = 0u;   // next attempt's buffer (last read 7 barriers ago)
+      }
       if (err_norm < 1.0) {
         double factor = dp::MAX_FACTOR;
         if (err_norm != 0.0) factor = fmin(dp::MAX_FACTOR, dp::SAFETY * fm::exp(tb, -0.2 * fm::log(tb, err_norm)));
         if (rejected) factor = fmin(1.0, factor);
-        // ---- dense output for t_eval points in (t, t_new] (ivp.py: searchsorted side='right')
-        while (next_eval < opt.n_eval) {
-          const double te = g_t_eval[next_eval];
-          if (!(te <= t_new)) break;
-          const double x = (te - t) / h;
-#pragma unroll 1
-          for (int f = 0; f < 5; ++f) {
-            double q[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              double s = dp::P[0][j] * KAt(0, f);
-#pragma unroll
-              for (int st = 2; st < 6; ++st) s = fma(dp::P[st][j], KAt(st, f), s);
-              q[j] = fma(dp::P[6][j], r.r[f], s);
-            }
-            const double poly = x * (q[0] + x * (q[1] + x * (q[2] + x * q[3])));
-            g_snap[(((size_t)col * opt.n_eval + next_eval) * 5 + f) * N + cell] = fma(h, poly, yAt(f));
-          }
-          ++next_eval;
-        }
-        // ---- accept
-#pragma unroll
-        for (int f = 0; f < 5; ++f) {
-          yAt(f) = tileAt(0, f, tid);
-          KAt(0, f) = r.r[f];           // FSAL
-        }
-        t = t_new;
-        h_abs *= factor;
-        if (leader) ctl.n_acc += 1;
-        if (t >= opt.t_bound) {
-          retire(MARLPDE_STATUS_FINISHED);
-        } else if (opt.max_steps > 0 && (long long)attempts >= opt.max_steps) {
-          retire(MARLPDE_STATUS_STEP_BUDGET);
+        const unsigned ev_new = event_classes(ev_bits_new);
+        const unsigned act = ev_on ? active_events(ev_prev, ev_new) : 0u;
+        if (act) {           // park the step: its events are located in the slot-service phase, then it commits
+          parked = true;
+          ev_todo = act;
+          ev_new_s = ev_new;
+          factor_s = factor;
+          if (leader) atomicOr(sSvc, 2);
         } else {
-          begin_step();
-          if (!begin_attempt()) retire(MARLPDE_STATUS_STEP_TOO_SMALL);
+          ev_prev = ev_new;
+          commit(factor);
         }
       } else {
         // NaN error norms land here too: fmax drops the NaN, like Python's max(0.2, nan)
@@ -375,22 +813,44 @@ rk45_persistent_kernel(double* __restrict__ g_y, const marlpde_column_params* __
   }
 }
 
-cudaError_t launch_rk45(double* d_y, const marlpde_column_params* d_params, marlpde_column_state* d_state,
-                        int n_columns, int n_cells, const marlpde_rk45_options& opt, const double* d_t_eval,
-                        double* d_snap, int32_t* d_queue, int sm_count, int smem_budget, cudaStream_t stream) {
-  const int C = rk45_columns_per_cta(n_cells, smem_budget);
-  if (C <= 0) return cudaErrorInvalidValue;
-  const int logG = group_log2(n_cells);
-  const SmemLayout L = smem_layout(C, n_cells, logG);
-  cudaError_t e = cudaFuncSetAttribute(rk45_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)L.total);
+template <int TP, bool YS>
+static cudaError_t launch_t(const Rk45Args& a, int sm_count, int smem_budget, cudaStream_t stream) {
+  Rk45Args args = a;
+  args.C = columns_per_cta_t<TP, YS>(a.N, smem_budget);
+  if (args.C <= 0) return cudaErrorInvalidValue;
+  const int Hc = (a.N + 1) / 2;
+  args.logG = group_log2(Hc);
+  const size_t smem = Smem<TP, YS>::total(args.C);
+  cudaError_t e = cudaFuncSetAttribute(rk45_persistent_kernel<TP, YS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  int grid = (n_columns + C - 1) / C;
+  int grid = (a.n_columns + args.C - 1) / args.C;
   if (grid > sm_count) grid = sm_count;
   if (grid < 1) grid = 1;
-  rk45_persistent_kernel<<<grid, L.T, L.total, stream>>>(d_y, d_params, d_state, n_columns, n_cells, C, logG, opt,
-                                                         d_t_eval, d_snap, d_queue);
+  const int threads = ((args.C * Hc + 31) / 32) * 32;
+  rk45_persistent_kernel<TP, YS><<<grid, threads, smem, stream>>>(args);
   return cudaGetLastError();
+}
+
+cudaError_t launch_rk45(double* d_y, const marlpde_column_params* d_params, marlpde_column_state* d_state,
+                        int n_columns, int n_cells, const marlpde_rk45_options& opt, const double* d_t_eval,
+                        double* d_snap, int32_t* d_ev_counts, double* d_ev_times, int32_t* d_queue, int sm_count,
+                        int smem_budget, cudaStream_t stream) {
+  Rk45Args a;
+  a.g_y = d_y;
+  a.g_params = d_params;
+  a.g_state = d_state;
+  a.g_t_eval = d_t_eval;
+  a.g_snap = d_snap;
+  a.g_queue = d_queue;
+  a.g_ev_counts = d_ev_counts;
+  a.g_ev_times = d_ev_times;
+  a.n_columns = n_columns;
+  a.N = n_cells;
+  a.C = 0;
+  a.logG = 0;
+  a.opt = opt;
+  return rk45_variant() == 320 ? launch_t<320, false>(a, sm_count, smem_budget, stream)
+                               : launch_t<400, true>(a, sm_count, smem_budget, stream);
 }
 
 }  // namespace marlpde

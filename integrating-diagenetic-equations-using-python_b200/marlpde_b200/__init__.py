@@ -5,6 +5,7 @@ Layers (bottom up):
   _cabi                            ctypes binding of that ABI
   params                           per-column constants (mirror of LMAHeureuxPorosityDiff.__init__)
   batch                            batched RHS / RK45 entry points on host or device buffers
+  sweep                            column sharding over GPUs + the one all-gather of results
   pde_standin, hdf5lite            the sliver of py-pde / h5py the reference driver touches
 The reference-facing drop-in (`Map_Scenario`, `Solver`, `Tracker`, `LMAHeureuxPorosityDiff`,
 `integrate_equations`) lives in the sibling package `marlpde`.
@@ -12,3 +13,4 @@ The reference-facing drop-in (`Map_Scenario`, `Solver`, `Tracker`, `LMAHeureuxPo
 from . import _cabi  # noqa: F401
 from .params import derive_column_params, initial_state, sweep_lattice  # noqa: F401
 from .batch import rhs_batch, integrate_rk45_batch, RK45Result  # noqa: F401
+from . import sweep  # noqa: F401

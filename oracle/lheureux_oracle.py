@@ -356,11 +356,12 @@ def event_fns(p: np.ndarray, N: int):
 
 
 def integrate(pde: dict, method: str = "RK45", first_step: float = 1e-6, rtol: float = 1e-3,
-              atol: float = 1e-3, t_span=(0.0, 1.0), t_eval=None, events: bool = True, **opts):
-    """What Evolve_scenario.py:104-109 does: SciPy solve_ivp on the restated RHS."""
+              atol: float = 1e-3, t_span=(0.0, 1.0), t_eval=None, events: bool = True, y0=None, **opts):
+    """What Evolve_scenario.py:104-109 does: SciPy solve_ivp on the restated RHS
+    (`y0` overrides the uniform initial state of Evolve_scenario.py:76-86, for tests)."""
     from scipy.integrate import solve_ivp
     p = kernel_params(pde)
-    y0 = initial_state(pde)
+    y0 = initial_state(pde) if y0 is None else np.ascontiguousarray(y0, dtype=np.float64).ravel()
     N = int(pde["N"])
     if t_eval is None:
         t_eval = np.linspace(t_span[0], t_span[1], 2)
@@ -378,3 +379,57 @@ def jacobian_sparsity(N: int = 200):
     raw = lil_matrix(dia_matrix((np.ones((len(offsets), n)), offsets), shape=(n, n)))
     raw[:2 * N, 4 * N:] = 0
     return csr_matrix(raw)
+
+
+def brentq_restated(f, xa, xb, xtol=4 * np.finfo(float).eps, rtol=4 * np.finfo(float).eps, maxiter=100):
+    """Restatement of `scipy.optimize.brentq` (scipy/optimize/Zeros/brentq.c, Brent's method with
+    inverse quadratic extrapolation), the root finder `solve_ivp` uses to locate events
+    (scipy/integrate/_ivp/ivp.py `solve_event_equation`, xtol = rtol = 4 eps).  The CUDA kernel's
+    event location (csrc/rk45_persistent.cu `BrentState`) is a transliteration of THIS function;
+    tests/test_oracle_golden.py pins it bit-for-bit (root, iterations, function calls) to the
+    installed SciPy.  Returns (root, iterations, funcalls)."""
+    xpre, xcur = float(xa), float(xb)
+    xblk = fblk = spre = scur = 0.0
+    fpre = f(xpre)
+    fcur = f(xcur)
+    funcalls = 2
+    if fpre == 0:
+        return xpre, 0, funcalls
+    if fcur == 0:
+        return xcur, 0, funcalls
+    if math.copysign(1.0, fpre) == math.copysign(1.0, fcur):
+        raise ValueError("f(a) and f(b) must have different signs")
+    it = 0
+    for _ in range(maxiter):
+        it += 1
+        if fpre != 0 and fcur != 0 and math.copysign(1.0, fpre) != math.copysign(1.0, fcur):
+            xblk, fblk = xpre, fpre
+            spre = scur = xcur - xpre
+        if abs(fblk) < abs(fcur):
+            xpre, xcur, xblk = xcur, xblk, xcur
+            fpre, fcur, fblk = fcur, fblk, fcur
+        delta = (xtol + rtol * abs(xcur)) / 2
+        sbis = (xblk - xcur) / 2
+        if fcur == 0 or abs(sbis) < delta:
+            return xcur, it, funcalls
+        if abs(spre) > delta and abs(fcur) < abs(fpre):
+            if xpre == xblk:
+                stry = -fcur * (xcur - xpre) / (fcur - fpre)                 # secant
+            else:
+                dpre = (fpre - fcur) / (xpre - xcur)                         # inverse quadratic
+                dblk = (fblk - fcur) / (xblk - xcur)
+                stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre))
+            if 2 * abs(stry) < min(abs(spre), 3 * abs(sbis) - delta):
+                spre, scur = scur, stry
+            else:
+                spre = scur = sbis
+        else:
+            spre = scur = sbis
+        xpre, fpre = xcur, fcur
+        if abs(scur) > delta:
+            xcur += scur
+        else:
+            xcur += delta if sbis > 0 else -delta
+        fcur = f(xcur)
+        funcalls += 1
+    return xcur, it, funcalls

@@ -171,3 +171,75 @@ def test_full_Tstar_against_scipy_rk45_and_reference_fixtures(stepper_golden, fi
         x, _ = oracle.grid_coords(pde)
         interp = np.stack([np.interp(x * pde["Xstar"], np.linspace(0, 500, 201), m[f, :, 0]) for f in range(5)])
         assert_allclose(got[:, 2:], interp[:, 2:], atol=0.05)
+
+
+# ---- event monitors (LHeureux_model.py:524-593; ivp.py find_active_events / brentq) -----------------
+def _event_lists(res, column):
+    cap = res.event_times.shape[2]
+    return [np.sort(res.event_times[column, k, :min(int(res.event_counts[column, k]), cap)]) for k in range(7)]
+
+
+def test_events_default_scenario_match_scipy():
+    """Default Map_Scenario to t = 0.03: porosity crosses 1 once (event 4) and max W changes sign
+    seven times (event 6).  Same counts as SciPy, root times to 1e-7 (the two trajectories agree to
+    ~1e-9, the roots are located to 4 eps on either side)."""
+    pde = oracle.default_scenario()
+    sol = oracle.integrate(pde, method="RK45", t_span=(0, 0.03), t_eval=[0, 0.03], events=True)
+    res = mb.integrate_rk45_batch(mb.initial_state(pde), mb.derive_column_params(pde), t_span=(0, 0.03),
+                                  first_step=1e-6, t_eval=[0, 0.03], events=True, event_capacity=32)
+    assert res.status[0] == 0 and abs(int(res.nfev[0]) - sol.nfev) <= 60
+    assert [len(e) for e in sol.t_events] == list(res.event_counts[0]) == [0, 0, 0, 0, 1, 0, 7]
+    for got, want in zip(_event_lists(res, 0), sol.t_events):
+        assert_allclose(got, want, rtol=0, atol=1e-7)
+    assert_allclose(res.solutions(0)[:, :, -1], sol.y[:, -1].reshape(5, 200), rtol=0, atol=1e-7)
+    # monitoring must not change the trajectory
+    plain = mb.integrate_rk45_batch(mb.initial_state(pde), mb.derive_column_params(pde), t_span=(0, 0.03),
+                                    first_step=1e-6, t_eval=[0, 0.03])
+    assert np.array_equal(plain.y, res.y) and np.array_equal(plain.nfev, res.nfev)
+
+
+def test_events_synthetic_state_six_monitors_and_capacity():
+    """A state that starts outside the physical bounds (CA<0, CC<0, CA+CC>1, Phi>1 in single cells)
+    re-enters them within t = 4e-3: monitors 0-4 and 6 fire; columns sharing a CTA keep their own
+    event lists; a small capacity truncates the stored times but not the counts."""
+    pde = oracle.default_scenario() | {"Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}
+    y0 = mb.initial_state(pde)
+    y0[0, 0, 50] = -2e-3
+    y0[0, 1, 60] = -1e-3
+    y0[0, 0, 100] = 0.705
+    y0[0, 4, 150] = 1.0005
+    sol = oracle.integrate(pde, method="RK45", t_span=(0, 4e-3), t_eval=[0, 4e-3], events=True, y0=y0[0])
+    want_counts = [len(e) for e in sol.t_events]
+    assert want_counts == [1, 1, 1, 1, 2, 0, 2]
+    P = mb.derive_column_params(pde)
+    Y = np.concatenate([y0, mb.initial_state(pde), y0, y0])          # columns 0, 2, 3 perturbed, 1 plain
+    res = mb.integrate_rk45_batch(Y, np.repeat(P, 4), t_span=(0, 4e-3), first_step=1e-6, t_eval=[0, 4e-3],
+                                  events=True, event_capacity=8)
+    assert np.all(res.status == 0)
+    for c in (0, 2, 3):
+        assert list(res.event_counts[c]) == want_counts
+        for got, want in zip(_event_lists(res, c), sol.t_events):
+            assert_allclose(got, want, rtol=0, atol=1e-9)
+    assert np.all(res.event_counts[1] == 0)
+    assert np.array_equal(res.y[0], res.y[2]) and np.array_equal(res.event_times[0], res.event_times[3], equal_nan=True)
+    small = mb.integrate_rk45_batch(y0, P, t_span=(0, 4e-3), first_step=1e-6, events=True, event_capacity=1)
+    assert list(small.event_counts[0]) == want_counts and small.event_times.shape == (1, 7, 1)
+    assert small.event_times[0, 4, 0] == res.event_times[0, 4, 0]
+
+
+def test_events_survive_resume():
+    """Stopping on a step budget and resuming gives the same event lists as one uninterrupted run."""
+    pde = oracle.default_scenario()
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    whole = mb.integrate_rk45_batch(y0, P, t_span=(0, 0.029), first_step=1e-6, events=True, event_capacity=16)
+    part = mb.integrate_rk45_batch(y0, P, t_span=(0, 0.029), first_step=1e-6, events=True, event_capacity=16,
+                                   max_steps=7000)
+    times = [list(e) for e in _event_lists(part, 0)]
+    while part.status[0] == 1:
+        part = mb.integrate_rk45_batch(part.y, P, t_span=(0, 0.029), events=True, event_capacity=16,
+                                       max_steps=7000, state=part.state)
+        for k, e in enumerate(_event_lists(part, 0)):
+            times[k] += list(e)
+    assert part.status[0] == 0 and np.array_equal(part.y, whole.y)
+    for k in range(7):
+        assert np.array_equal(np.asarray(times[k]), _event_lists(whole, 0)[k])

@@ -100,10 +100,10 @@ def test_cabi_exports_every_declared_symbol():
     assert L.marlpde_struct_size(0) == _cabi.PARAMS_DTYPE.itemsize == 224
     assert L.marlpde_struct_size(2) == _cabi.STATE_DTYPE.itemsize == 48
     assert L.marlpde_struct_size(9) == -1
-    assert L.marlpde_rk45_max_cells() == 608
+    assert L.marlpde_rk45_max_cells() == 640
     assert L.marlpde_rk45_columns_per_cta(200) == 3
-    assert L.marlpde_rk45_columns_per_cta(608) == 1
-    assert L.marlpde_rk45_columns_per_cta(609) == 0 and L.marlpde_rk45_columns_per_cta(16) == 0
+    assert L.marlpde_rk45_columns_per_cta(640) == 1 and L.marlpde_rk45_columns_per_cta(639) == 1
+    assert L.marlpde_rk45_columns_per_cta(641) == 0 and L.marlpde_rk45_columns_per_cta(16) == 0
 
 
 def test_no_device_fails_loudly():

@@ -128,3 +128,27 @@ def test_live_scipy_rk45_reproduces_committed_short_golden(stepper_golden):
     sol = oracle.integrate(pde, method="RK45", first_step=fs, t_span=(0, 0.002), t_eval=g[key + "/t"])
     assert sol.nfev == g[key + "/counts"][0]
     assert_allclose(sol.y, g[key + "/y"], rtol=0, atol=1e-12)
+
+
+def test_brentq_restatement_is_bit_identical_to_scipy():
+    """The event locator restated in the oracle (and transliterated in the kernel) against the
+    installed scipy.optimize.brentq: same root, iteration count and function calls."""
+    import math
+    from scipy.optimize import brentq
+    rng = np.random.default_rng(0)
+    eps4 = 4 * np.finfo(float).eps
+    checked = 0
+    for trial in range(1200):
+        a, b = sorted(rng.uniform(-2, 2, 2))
+        r0 = rng.uniform(a, b)
+        f = [lambda x: (x - r0) * (1 + 0.3 * np.sin(5 * x)), lambda x: math.expm1(3 * (x - r0)),
+             lambda x: (x - r0) ** 3 + 1e-3 * (x - r0), lambda x: min(x - r0, 0.3 * (x - r0))][trial % 4]
+        if f(a) * f(b) > 0:
+            continue
+        root, res = brentq(f, a, b, xtol=eps4, rtol=eps4, full_output=True)
+        assert oracle.brentq_restated(f, a, b) == (root, res.iterations, res.function_calls)
+        checked += 1
+    assert checked > 1000
+    assert oracle.brentq_restated(lambda x: x, 0.0, 1.0)[0] == 0.0          # f(a) == 0 returns a
+    with pytest.raises(ValueError):
+        oracle.brentq_restated(lambda x: x * x + 1, -1.0, 1.0)

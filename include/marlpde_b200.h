@@ -12,6 +12,8 @@
  *   LMAHeureuxPorosityDiff.fun (NumPy backend, :162-288)  marlpde_rhs_batch[_dev] (same maths)
  *   scipy.integrate.solve_ivp(method="RK45", ...)         marlpde_rk45_integrate[_dev]
  *     call site marlpde/Evolve_scenario.py:104-109
+ *   scipy.integrate.solve_ivp(method="Radau", jac_sparsity=jacobian_sparsity())   marlpde_radau_integrate[_dev]
+ *     the reference's default Solver (marlpde/parameters.py:150-199, :213)
  *   7 event monitors (LHeureux_model.py:524-593)          event outputs of marlpde_rk45_integrate*
  *   derived constants of __init__ (:31-72, :130-133)      marlpde_column_params (filled by the host
  *                                                          mirror, one struct per sediment column)
@@ -77,7 +79,7 @@ typedef struct marlpde_column_params {
   int32_t reserved;
 } marlpde_column_params;
 
-/* Options of one batched Dormand-Prince RK45 integration (scipy RK45 semantics). */
+/* Options of one batched integration (scipy RK45 / Radau semantics; both steppers take this struct). */
 typedef struct marlpde_rk45_options {
   double t_bound;      /* end time (t_span[1]); direction is forward only              */
   double rtol, atol;   /* scale = atol + rtol*max(|y|,|y_new|)                         */
@@ -150,6 +152,44 @@ int marlpde_rk45_integrate(double* y, const marlpde_column_params* params,
                            const marlpde_rk45_options* opts, const double* t_eval,
                            double* snapshots, int32_t* event_counts, double* event_times,
                            int device);
+
+/* ---- the same RK45 for depth grids that do not fit on chip (n_cells up to millions): stage vectors
+ * stream through HBM/L2, one kernel launch per Runge-Kutta stage (csrc/rk45_streaming.cu).
+ *  Arguments as for marlpde_rk45_integrate_dev (events are not monitored on this path), plus
+ *  d_workspace  marlpde_rk45_stream_workspace_bytes(n_columns, n_cells) bytes of device scratch.
+ *  opts->max_steps must be > 0: the call enqueues exactly that many step attempts per column and
+ *  returns without synchronising; columns that reach t_bound earlier idle, the others come back with
+ *  MARLPDE_STATUS_STEP_BUDGET and are resumed by calling again with the returned state.
+ *  The host-pointer marlpde_rk45_integrate picks this path by itself when n_cells exceeds
+ *  marlpde_rk45_max_cells() and repeats calls until every column has finished (or max_steps is used up).
+ */
+size_t marlpde_rk45_stream_workspace_bytes(int n_columns, int n_cells);
+int marlpde_rk45_stream_integrate_dev(double* d_y, const marlpde_column_params* d_params,
+                                      marlpde_column_state* d_state, int n_columns, int n_cells,
+                                      const marlpde_rk45_options* opts, const double* d_t_eval,
+                                      double* d_snapshots, void* d_workspace, size_t workspace_bytes,
+                                      void* stream);
+
+/* ---- batched implicit integrator: 3-stage Radau IIA with a block-tridiagonal simplified Newton solve
+ * (replaces solve_ivp(method="Radau", jac_sparsity=...) per column; scipy/integrate/_ivp/radau.py) ------
+ *  Arguments as for marlpde_rk45_integrate_dev (same options struct; flags are ignored), plus
+ *  d_stats    [n_columns][4] int64, accumulated: Jacobian evaluations (njev), LU factorisations (nlu),
+ *             Newton iterations, Newton failures
+ *  d_workspace  marlpde_radau_workspace_bytes(n_columns, n_cells) bytes of device scratch (Jacobian
+ *             blocks, factors and stage vectors of every column; need not be initialised)
+ *  Any n_cells >= 3 is accepted (nothing has to fit on chip).  A column that stops on the step budget
+ *  resumes "cold": (t, h_abs, y) are kept, the Jacobian and the Newton start guess are rebuilt.
+ */
+size_t marlpde_radau_workspace_bytes(int n_columns, int n_cells);
+int marlpde_radau_integrate_dev(double* d_y, const marlpde_column_params* d_params,
+                                marlpde_column_state* d_state, int n_columns, int n_cells,
+                                const marlpde_rk45_options* opts, const double* d_t_eval,
+                                double* d_snapshots, int64_t* d_stats, void* d_workspace,
+                                size_t workspace_bytes, int32_t* d_queue, void* stream);
+int marlpde_radau_integrate(double* y, const marlpde_column_params* params,
+                            marlpde_column_state* state, int n_columns, int n_cells,
+                            const marlpde_rk45_options* opts, const double* t_eval,
+                            double* snapshots, int64_t* stats, int device);
 
 /* ---- measurement helper: fp64 FMA peak (TFLOP/s, best of `repeats`) of `device`, the roofline
  * denominator of the fp64-pipe-bound RK45 kernel (no reference counterpart). */

@@ -9,7 +9,9 @@
 #include <vector>
 
 #include "../../include/marlpde_b200.h"
+#include "radau_batch.cuh"
 #include "rk45_persistent.cuh"
+#include "rk45_streaming.cuh"
 
 namespace {
 
@@ -183,9 +185,65 @@ int marlpde_rk45_integrate_dev(double* d_y, const marlpde_column_params* d_param
   return MARLPDE_OK;
 }
 
+static int check_stream_args(int n_columns, int n_cells, const marlpde_rk45_options* opts);
+
+// Host-pointer driver of the streaming path: repeats fixed-size batches of step attempts until every
+// column has left the STEP_BUDGET state (or the caller's max_steps budget is used up).
+static int rk45_integrate_streaming(double* y, const marlpde_column_params* params, marlpde_column_state* state,
+                                    int n_columns, int n_cells, const marlpde_rk45_options* opts,
+                                    const double* t_eval, double* snapshots, int device) {
+  int rc = check_stream_args(n_columns, n_cells, opts);
+  if (rc) return rc;
+  if (n_columns == 0) return MARLPDE_OK;
+  if (!y || !params || !state) return fail(MARLPDE_EINVAL, "NULL pointer");
+  if (opts->n_eval > 0 && (!t_eval || !snapshots)) return fail(MARLPDE_EINVAL, "n_eval > 0 needs t_eval and snapshots");
+  rc = select_device(device);
+  if (rc) return rc;
+  const size_t nb_y = sizeof(double) * 5 * (size_t)n_cells * n_columns;
+  const size_t nb_snap = nb_y * (size_t)opts->n_eval;
+  const size_t nb_state = sizeof(marlpde_column_state) * (size_t)n_columns;
+  const size_t nb_work = marlpde::rk45_stream_workspace_bytes(n_columns, n_cells);
+  DevBuf dy, dp, ds, dte, dsnap, dw;
+  CU(dy.alloc(nb_y));
+  CU(dp.alloc(sizeof(marlpde_column_params) * (size_t)n_columns));
+  CU(ds.alloc(nb_state));
+  CU(dte.alloc(sizeof(double) * (size_t)opts->n_eval));
+  CU(dsnap.alloc(nb_snap));
+  CU(dw.alloc(nb_work));
+  CU(cudaMemcpy(dy.p, y, nb_y, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dp.p, params, sizeof(marlpde_column_params) * (size_t)n_columns, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ds.p, state, nb_state, cudaMemcpyHostToDevice));
+  if (opts->n_eval) CU(cudaMemcpy(dte.p, t_eval, sizeof(double) * (size_t)opts->n_eval, cudaMemcpyHostToDevice));
+  if (snapshots && nb_snap) CU(cudaMemcpy(dsnap.p, snapshots, nb_snap, cudaMemcpyHostToDevice));
+  const long long budget = opts->max_steps > 0 ? opts->max_steps : -1;   // -1: until done
+  long long used = 0;
+  std::vector<marlpde_column_state> hs((size_t)n_columns);
+  for (;;) {
+    marlpde_rk45_options o = *opts;
+    long long batch = 512;
+    if (budget > 0 && budget - used < batch) batch = budget - used;
+    o.max_steps = batch;
+    rc = marlpde_rk45_stream_integrate_dev(dy.as<double>(), dp.as<marlpde_column_params>(),
+                                           ds.as<marlpde_column_state>(), n_columns, n_cells, &o, dte.as<double>(),
+                                           dsnap.as<double>(), dw.p, nb_work, nullptr);
+    if (rc) return rc;
+    CU(cudaMemcpy(hs.data(), ds.p, nb_state, cudaMemcpyDeviceToHost));   // synchronises
+    used += batch;
+    bool pending = false;
+    for (int c = 0; c < n_columns; ++c) pending = pending || hs[(size_t)c].status == MARLPDE_STATUS_STEP_BUDGET;
+    if (!pending || (budget > 0 && used >= budget)) break;
+  }
+  CU(cudaMemcpy(y, dy.p, nb_y, cudaMemcpyDeviceToHost));
+  std::memcpy(state, hs.data(), nb_state);
+  if (snapshots && nb_snap) CU(cudaMemcpy(snapshots, dsnap.p, nb_snap, cudaMemcpyDeviceToHost));
+  return MARLPDE_OK;
+}
+
 int marlpde_rk45_integrate(double* y, const marlpde_column_params* params, marlpde_column_state* state,
                            int n_columns, int n_cells, const marlpde_rk45_options* opts, const double* t_eval,
                            double* snapshots, int32_t* event_counts, double* event_times, int device) {
+  if (opts && (n_cells > marlpde::rk45_max_cells() || (n_cells >= 2 && n_cells < 32)))
+    return rk45_integrate_streaming(y, params, state, n_columns, n_cells, opts, t_eval, snapshots, device);
   int rc = check_rk45_args(n_columns, n_cells, opts);
   if (rc) return rc;
   if (n_columns == 0) return MARLPDE_OK;
@@ -225,6 +283,123 @@ int marlpde_rk45_integrate(double* y, const marlpde_column_params* params, marlp
   if (snapshots && nb_snap) CU(cudaMemcpy(snapshots, dsnap.p, nb_snap, cudaMemcpyDeviceToHost));
   if (event_counts) CU(cudaMemcpy(event_counts, dec.p, nb_ec, cudaMemcpyDeviceToHost));
   if (event_times && nb_et) CU(cudaMemcpy(event_times, det.p, nb_et, cudaMemcpyDeviceToHost));
+  return MARLPDE_OK;
+}
+
+size_t marlpde_rk45_stream_workspace_bytes(int n_columns, int n_cells) {
+  if (n_columns <= 0 || n_cells <= 0) return 0;
+  return marlpde::rk45_stream_workspace_bytes(n_columns, n_cells);
+}
+
+static int check_stream_args(int n_columns, int n_cells, const marlpde_rk45_options* opts) {
+  if (!opts) return fail(MARLPDE_EINVAL, "opts is NULL");
+  if (n_columns < 0) return fail(MARLPDE_EINVAL, "n_columns < 0");
+  if (n_cells < 2) return fail(MARLPDE_EINVAL, "need n_cells >= 2");
+  if (!(opts->rtol > 0.0) || !(opts->atol >= 0.0)) return fail(MARLPDE_EINVAL, "need rtol > 0, atol >= 0");
+  if (!(opts->max_step > 0.0)) return fail(MARLPDE_EINVAL, "max_step must be positive (use +inf for none)");
+  if (opts->n_eval < 0) return fail(MARLPDE_EINVAL, "negative n_eval");
+  if (opts->flags & MARLPDE_FLAG_EVENTS)
+    return fail(MARLPDE_EUNSUPPORTED, "the streaming RK45 path does not monitor events");
+  return MARLPDE_OK;
+}
+
+int marlpde_rk45_stream_integrate_dev(double* d_y, const marlpde_column_params* d_params,
+                                      marlpde_column_state* d_state, int n_columns, int n_cells,
+                                      const marlpde_rk45_options* opts, const double* d_t_eval, double* d_snapshots,
+                                      void* d_workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_stream_args(n_columns, n_cells, opts);
+  if (rc) return rc;
+  if (n_columns == 0) return MARLPDE_OK;
+  if (opts->max_steps <= 0) return fail(MARLPDE_EINVAL, "the streaming path needs max_steps > 0 per call");
+  if (opts->max_steps > 1000000) return fail(MARLPDE_EINVAL, "max_steps per call is limited to 1e6 on the streaming path");
+  if (!d_y || !d_params || !d_state || !d_workspace) return fail(MARLPDE_EINVAL, "NULL device pointer");
+  if (opts->n_eval > 0 && (!d_t_eval || !d_snapshots)) return fail(MARLPDE_EINVAL, "n_eval > 0 needs t_eval and snapshots");
+  if (workspace_bytes < marlpde::rk45_stream_workspace_bytes(n_columns, n_cells))
+    return fail(MARLPDE_EINVAL, "workspace too small: %zu < %zu bytes", workspace_bytes,
+                marlpde::rk45_stream_workspace_bytes(n_columns, n_cells));
+  cudaError_t e = marlpde::launch_rk45_stream(d_y, d_params, d_state, n_columns, n_cells, *opts, d_t_eval,
+                                              d_snapshots, d_workspace, opts->max_steps, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "rk45 stream launch");
+  return MARLPDE_OK;
+}
+
+size_t marlpde_radau_workspace_bytes(int n_columns, int n_cells) {
+  if (n_columns <= 0 || n_cells <= 0) return 0;
+  return marlpde::radau_workspace_bytes(n_columns, n_cells);
+}
+
+static int check_radau_args(int n_columns, int n_cells, const marlpde_rk45_options* opts) {
+  if (!opts) return fail(MARLPDE_EINVAL, "opts is NULL");
+  if (n_columns < 0) return fail(MARLPDE_EINVAL, "n_columns < 0");
+  if (n_cells < 3) return fail(MARLPDE_EINVAL, "the implicit integrator needs n_cells >= 3 (got %d)", n_cells);
+  if (!(opts->rtol > 0.0) || !(opts->atol >= 0.0)) return fail(MARLPDE_EINVAL, "need rtol > 0, atol >= 0");
+  if (!(opts->max_step > 0.0)) return fail(MARLPDE_EINVAL, "max_step must be positive (use +inf for none)");
+  if (opts->n_eval < 0) return fail(MARLPDE_EINVAL, "negative n_eval");
+  return MARLPDE_OK;
+}
+
+int marlpde_radau_integrate_dev(double* d_y, const marlpde_column_params* d_params, marlpde_column_state* d_state,
+                                int n_columns, int n_cells, const marlpde_rk45_options* opts,
+                                const double* d_t_eval, double* d_snapshots, int64_t* d_stats, void* d_workspace,
+                                size_t workspace_bytes, int32_t* d_queue, void* stream) {
+  int rc = check_radau_args(n_columns, n_cells, opts);
+  if (rc) return rc;
+  if (n_columns == 0) return MARLPDE_OK;
+  if (!d_y || !d_params || !d_state || !d_queue || !d_stats || !d_workspace)
+    return fail(MARLPDE_EINVAL, "NULL device pointer");
+  if (opts->n_eval > 0 && (!d_t_eval || !d_snapshots)) return fail(MARLPDE_EINVAL, "n_eval > 0 needs t_eval and snapshots");
+  if (workspace_bytes < marlpde::radau_workspace_bytes(n_columns, n_cells))
+    return fail(MARLPDE_EINVAL, "workspace too small: %zu < %zu bytes", workspace_bytes,
+                marlpde::radau_workspace_bytes(n_columns, n_cells));
+  DevProps props;
+  rc = current_props(props);
+  if (rc) return rc;
+  cudaError_t e = marlpde::launch_radau(d_y, d_params, d_state, n_columns, n_cells, *opts, d_t_eval, d_snapshots,
+                                        d_stats, static_cast<double*>(d_workspace), d_queue, props.sm_count,
+                                        (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "radau launch");
+  return MARLPDE_OK;
+}
+
+int marlpde_radau_integrate(double* y, const marlpde_column_params* params, marlpde_column_state* state,
+                            int n_columns, int n_cells, const marlpde_rk45_options* opts, const double* t_eval,
+                            double* snapshots, int64_t* stats, int device) {
+  int rc = check_radau_args(n_columns, n_cells, opts);
+  if (rc) return rc;
+  if (n_columns == 0) return MARLPDE_OK;
+  if (!y || !params || !state || !stats) return fail(MARLPDE_EINVAL, "NULL pointer");
+  if (opts->n_eval > 0 && (!t_eval || !snapshots)) return fail(MARLPDE_EINVAL, "n_eval > 0 needs t_eval and snapshots");
+  rc = select_device(device);
+  if (rc) return rc;
+  const size_t nb_y = sizeof(double) * 5 * (size_t)n_cells * n_columns;
+  const size_t nb_snap = nb_y * (size_t)opts->n_eval;
+  const size_t nb_stats = sizeof(int64_t) * 4 * (size_t)n_columns;
+  const size_t nb_work = marlpde::radau_workspace_bytes(n_columns, n_cells);
+  DevBuf dy, dp, ds, dte, dsnap, dq, dst, dw;
+  CU(dy.alloc(nb_y));
+  CU(dp.alloc(sizeof(marlpde_column_params) * (size_t)n_columns));
+  CU(ds.alloc(sizeof(marlpde_column_state) * (size_t)n_columns));
+  CU(dte.alloc(sizeof(double) * (size_t)opts->n_eval));
+  CU(dsnap.alloc(nb_snap));
+  CU(dq.alloc(sizeof(int32_t)));
+  CU(dst.alloc(nb_stats));
+  CU(dw.alloc(nb_work));
+  CU(cudaMemcpy(dy.p, y, nb_y, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dp.p, params, sizeof(marlpde_column_params) * (size_t)n_columns, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ds.p, state, sizeof(marlpde_column_state) * (size_t)n_columns, cudaMemcpyHostToDevice));
+  if (opts->n_eval) CU(cudaMemcpy(dte.p, t_eval, sizeof(double) * (size_t)opts->n_eval, cudaMemcpyHostToDevice));
+  if (snapshots && nb_snap) CU(cudaMemcpy(dsnap.p, snapshots, nb_snap, cudaMemcpyHostToDevice));
+  CU(cudaMemset(dq.p, 0, sizeof(int32_t)));
+  CU(cudaMemcpy(dst.p, stats, nb_stats, cudaMemcpyHostToDevice));
+  rc = marlpde_radau_integrate_dev(dy.as<double>(), dp.as<marlpde_column_params>(), ds.as<marlpde_column_state>(),
+                                   n_columns, n_cells, opts, dte.as<double>(), dsnap.as<double>(),
+                                   dst.as<int64_t>(), dw.p, nb_work, dq.as<int32_t>(), nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(y, dy.p, nb_y, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(state, ds.p, sizeof(marlpde_column_state) * (size_t)n_columns, cudaMemcpyDeviceToHost));
+  if (snapshots && nb_snap) CU(cudaMemcpy(snapshots, dsnap.p, nb_snap, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(stats, dst.p, nb_stats, cudaMemcpyDeviceToHost));
   return MARLPDE_OK;
 }
 

@@ -30,34 +30,12 @@
 #include <cstdint>
 #include <cstdlib>
 
+#include "dopri.cuh"
 #include "lheureux_device.cuh"
 #include "rk45_persistent.cuh"
 
 namespace marlpde {
 
-namespace dp {  // Dormand-Prince coefficients, as scipy RK45.{A,B,E,P}
-constexpr double a21 = 1.0 / 5.0;
-constexpr double a31 = 3.0 / 40.0, a32 = 9.0 / 40.0;
-constexpr double a41 = 44.0 / 45.0, a42 = -56.0 / 15.0, a43 = 32.0 / 9.0;
-constexpr double a51 = 19372.0 / 6561.0, a52 = -25360.0 / 2187.0, a53 = 64448.0 / 6561.0,
-                 a54 = -212.0 / 729.0;
-constexpr double a61 = 9017.0 / 3168.0, a62 = -355.0 / 33.0, a63 = 46732.0 / 5247.0,
-                 a64 = 49.0 / 176.0, a65 = -5103.0 / 18656.0;
-constexpr double b1 = 35.0 / 384.0, b3 = 500.0 / 1113.0, b4 = 125.0 / 192.0,
-                 b5 = -2187.0 / 6784.0, b6 = 11.0 / 84.0;
-constexpr double e1 = -71.0 / 57600.0, e3 = 71.0 / 16695.0, e4 = -71.0 / 1920.0,
-                 e5 = 17253.0 / 339200.0, e6 = -22.0 / 525.0, e7 = 1.0 / 40.0;
-// dense output P[s][j], s = stage 1..7 (row 2 is zero), j = 0..3
-__constant__ double P[7][4] = {
-    {1.0, -8048581381.0 / 2820520608.0, 8663915743.0 / 2820520608.0, -12715105075.0 / 11282082432.0},
-    {0.0, 0.0, 0.0, 0.0},
-    {0.0, 131558114200.0 / 32700410799.0, -68118460800.0 / 10900136933.0, 87487479700.0 / 32700410799.0},
-    {0.0, -1754552775.0 / 470086768.0, 14199869525.0 / 1410260304.0, -10690763975.0 / 1880347072.0},
-    {0.0, 127303824393.0 / 49829197408.0, -318862633887.0 / 49829197408.0, 701980252875.0 / 199316789632.0},
-    {0.0, -282668133.0 / 205662961.0, 2019193451.0 / 616988883.0, -1453857185.0 / 822651844.0},
-    {0.0, 40617522.0 / 29380423.0, -110615467.0 / 29380423.0, 69997945.0 / 29380423.0}};
-constexpr double SAFETY = 0.9, MIN_FACTOR = 0.2, MAX_FACTOR = 10.0;
-}  // namespace dp
 
 // ---- shared memory carve-up -------------------------------------------------------------
 // K[4][5][TP] double2 | tileE[2][5][TP] | tileO[2][5][TP] | grp[TP] | log/exp tables |
@@ -71,8 +49,8 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) / 16 * 16;
 template <int TP, bool YS>
 struct Smem {
   static constexpr size_t off_K = 0;
-  static constexpr size_t off_Y = off_K + sizeof(double2) * 4 * 5 * TP;        // [5][TP] double2, YS builds only
-  static constexpr size_t off_tE = off_Y + (YS ? sizeof(double2) * 5 * TP : 0);
+  static constexpr size_t off_Y = off_K + sizeof(double2) * 4 * 5 * TP;        // y, K1: [2][5][TP] double2, YS builds only
+  static constexpr size_t off_tE = off_Y + (YS ? sizeof(double2) * 2 * 5 * TP : 0);
   static constexpr size_t off_tO = off_tE + sizeof(double) * 2 * 5 * TP;
   static constexpr size_t off_grp = off_tO + sizeof(double) * 2 * 5 * TP;
   static constexpr size_t off_tab = off_grp + sizeof(double) * TP;
@@ -98,25 +76,25 @@ static int columns_per_cta_t(int n_cells, int smem_budget) {
 
 // Builds of the kernel (register file: 16K registers per SM sub-partition, so the register cap
 // follows from the warps per sub-partition, not from the thread count alone):
-//   <320,false> 10 warps, <= 168 registers, y in registers      (any n_cells <= 640; N=200: 3 columns)
-//   <400,true>  13 warps, <= 128 registers, y in shared memory  (n_cells <= 800;     N=200: 4 columns)
-// MARLPDE_RK45_BUILD=320|400 overrides the default choice (tuning / tests).
+//   <320,false> 10 warps, <= 168 registers, y and K1 in registers      (n_cells <= 640; N=200: 3 columns)
+//   <320,true>  10 warps, <= 168 registers, y and K1 in shared memory  (same shapes; fewer register spills)
+// MARLPDE_RK45_BUILD=320|321 overrides the default choice (tuning / tests).
 static int rk45_variant() {
   static int v = -1;
   if (v < 0) {
     const char* s = std::getenv("MARLPDE_RK45_BUILD");
     const int want = s ? std::atoi(s) : 0;
-    v = (want == 400) ? 400 : 320;
+    v = (want == 321) ? 321 : 320;
   }
   return v;
 }
 
 int rk45_columns_per_cta(int n_cells, int smem_budget) {
-  return rk45_variant() == 320 ? columns_per_cta_t<320, false>(n_cells, smem_budget)
-                               : columns_per_cta_t<400, true>(n_cells, smem_budget);
+  return rk45_variant() == 321 ? columns_per_cta_t<320, true>(n_cells, smem_budget)
+                               : columns_per_cta_t<320, false>(n_cells, smem_budget);
 }
 
-int rk45_max_cells() { return rk45_variant() == 320 ? 640 : 800; }
+int rk45_max_cells() { return 640; }
 
 
 // ---- event monitors (LHeureux_model.py:524-593, all non-terminal, direction 0) -----------------
@@ -280,7 +258,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
   const int N = A.N, C = A.C;
   const int Hc = (N + 1) >> 1;                     // threads per column
   double2* const sK = reinterpret_cast<double2*>(smem_raw + L::off_K) + tid;         // [4][5][TP]
-  double2* const sY = reinterpret_cast<double2*>(smem_raw + L::off_Y) + tid;         // [5][TP] (YS builds)
+  double2* const sY = reinterpret_cast<double2*>(smem_raw + L::off_Y) + tid;         // y [5][TP], K1 [5][TP] (YS builds)
   double* const sE = reinterpret_cast<double*>(smem_raw + L::off_tE);               // [2][5][TP] even cells
   double* const sO = reinterpret_cast<double*>(smem_raw + L::off_tO);               // [2][5][TP] odd cells
   double* const sGrp = reinterpret_cast<double*>(smem_raw + L::off_grp);            // [TP >> logG]
@@ -355,6 +333,15 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
   auto Kld = [&](int s, int f) -> double2 { return sK[(s * 5 + f) * TP]; };
   // the state y of the thread's two cells: registers, or (YS builds) one double2 per field in shared memory
   auto Yld = [&](int f) -> double2 { return YS ? sY[f * TP] : make_double2(y[f][0], y[f][1]); };
+  auto K1ld = [&](int f) -> double2 { return YS ? sY[(5 + f) * TP] : make_double2(k1[f][0], k1[f][1]); };
+  auto K1st = [&](int f, double v0, double v1) {
+    if (YS) {
+      sY[(5 + f) * TP] = make_double2(v0, v1);
+    } else {
+      k1[f][0] = v0;
+      k1[f][1] = v1;
+    }
+  };
   auto Yst = [&](int f, double v0, double v1) {
     if (YS) {
       sY[f * TP] = make_double2(v0, v1);
@@ -408,9 +395,9 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
     const double ha = h * dp::a21;
 #pragma unroll
     for (int f = 0; f < 5; ++f) {
-      const double2 yv = Yld(f);
-      c[f][0] = fma(ha, k1[f][0], yv.x);
-      c[f][1] = fma(ha, k1[f][1], yv.y);
+      const double2 yv = Yld(f), kv = K1ld(f);
+      c[f][0] = fma(ha, kv.x, yv.x);
+      c[f][1] = fma(ha, kv.y, yv.y);
     }
     tile_store(1);
   };
@@ -419,14 +406,15 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
   auto interp_all = [&](double x, double (&out)[5][2]) {
 #pragma unroll
     for (int f = 0; f < 5; ++f) {
-      const double2 K3 = Kld(1, f), K4 = Kld(2, f), K5 = Kld(3, f), K6 = Kld(0, f), yv = Yld(f);
+      const double2 K3 = Kld(1, f), K4 = Kld(2, f), K5 = Kld(3, f), K6 = Kld(0, f), yv = Yld(f), kv = K1ld(f);
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const double v3 = q ? K3.y : K3.x, v4 = q ? K4.y : K4.x, v5 = q ? K5.y : K5.x, v6 = q ? K6.y : K6.x;
+        const double v1 = q ? kv.y : kv.x;
         double qq[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          double sacc = dp::P[0][j] * k1[f][q];
+          double sacc = dp::P[0][j] * v1;
           sacc = fma(dp::P[2][j], v3, sacc);
           sacc = fma(dp::P[3][j], v4, sacc);
           sacc = fma(dp::P[4][j], v5, sacc);
@@ -457,8 +445,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
 #pragma unroll
     for (int f = 0; f < 5; ++f) {
       Yst(f, c[f][0], c[f][1]);
-      k1[f][0] = r[f][0];
-      k1[f][1] = r[f][1];
+      K1st(f, r[f][0], r[f][1]);
     }
     t = t_new;
     h_abs *= factor;
@@ -660,8 +647,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
           if (fresh) {
 #pragma unroll
             for (int f = 0; f < 5; ++f) {
-              k1[f][0] = r[f][0];
-              k1[f][1] = r[f][1];
+              K1st(f, r[f][0], r[f][1]);
             }
             if (leader) ctl.nfev += 1;
             if (ev_on) {     // signs of the monitors at the start point (ivp.py: g = event(t0, y0))
@@ -676,9 +662,9 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
 #pragma unroll
           for (int f = 0; f < 5; ++f) {
             Kst(0, f, r[f][0], r[f][1]);
-            const double2 yv = Yld(f);
-            c[f][0] = fma(h, fma(dp::a31, k1[f][0], dp::a32 * r[f][0]), yv.x);
-            c[f][1] = fma(h, fma(dp::a31, k1[f][1], dp::a32 * r[f][1]), yv.y);
+            const double2 yv = Yld(f), kv = K1ld(f);
+            c[f][0] = fma(h, fma(dp::a31, kv.x, dp::a32 * r[f][0]), yv.x);
+            c[f][1] = fma(h, fma(dp::a31, kv.y, dp::a32 * r[f][1]), yv.y);
           }
           tile_store(0);
           break;
@@ -686,9 +672,9 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
 #pragma unroll
           for (int f = 0; f < 5; ++f) {
             Kst(1, f, r[f][0], r[f][1]);
-            const double2 K2 = Kld(0, f), yv = Yld(f);
-            c[f][0] = fma(h, fma(dp::a41, k1[f][0], fma(dp::a42, K2.x, dp::a43 * r[f][0])), yv.x);
-            c[f][1] = fma(h, fma(dp::a41, k1[f][1], fma(dp::a42, K2.y, dp::a43 * r[f][1])), yv.y);
+            const double2 K2 = Kld(0, f), yv = Yld(f), kv = K1ld(f);
+            c[f][0] = fma(h, fma(dp::a41, kv.x, fma(dp::a42, K2.x, dp::a43 * r[f][0])), yv.x);
+            c[f][1] = fma(h, fma(dp::a41, kv.y, fma(dp::a42, K2.y, dp::a43 * r[f][1])), yv.y);
           }
           tile_store(1);
           break;
@@ -696,10 +682,10 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
 #pragma unroll
           for (int f = 0; f < 5; ++f) {
             Kst(2, f, r[f][0], r[f][1]);
-            const double2 K2 = Kld(0, f), K3 = Kld(1, f), yv = Yld(f);
-            c[f][0] = fma(h, fma(dp::a51, k1[f][0], fma(dp::a52, K2.x, fma(dp::a53, K3.x, dp::a54 * r[f][0]))),
+            const double2 K2 = Kld(0, f), K3 = Kld(1, f), yv = Yld(f), kv = K1ld(f);
+            c[f][0] = fma(h, fma(dp::a51, kv.x, fma(dp::a52, K2.x, fma(dp::a53, K3.x, dp::a54 * r[f][0]))),
                           yv.x);
-            c[f][1] = fma(h, fma(dp::a51, k1[f][1], fma(dp::a52, K2.y, fma(dp::a53, K3.y, dp::a54 * r[f][1]))),
+            c[f][1] = fma(h, fma(dp::a51, kv.y, fma(dp::a52, K2.y, fma(dp::a53, K3.y, dp::a54 * r[f][1]))),
                           yv.y);
           }
           tile_store(0);
@@ -708,11 +694,11 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
 #pragma unroll
           for (int f = 0; f < 5; ++f) {
             Kst(3, f, r[f][0], r[f][1]);
-            const double2 K2 = Kld(0, f), K3 = Kld(1, f), K4 = Kld(2, f), yv = Yld(f);
-            c[f][0] = fma(h, fma(dp::a61, k1[f][0],
+            const double2 K2 = Kld(0, f), K3 = Kld(1, f), K4 = Kld(2, f), yv = Yld(f), kv = K1ld(f);
+            c[f][0] = fma(h, fma(dp::a61, kv.x,
                                  fma(dp::a62, K2.x, fma(dp::a63, K3.x, fma(dp::a64, K4.x, dp::a65 * r[f][0])))),
                           yv.x);
-            c[f][1] = fma(h, fma(dp::a61, k1[f][1],
+            c[f][1] = fma(h, fma(dp::a61, kv.y,
                                  fma(dp::a62, K2.y, fma(dp::a63, K3.y, fma(dp::a64, K4.y, dp::a65 * r[f][1])))),
                           yv.y);
           }
@@ -721,11 +707,11 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
         case 5:   // r = K6 (stored over the dead K2): c becomes y_new
 #pragma unroll
           for (int f = 0; f < 5; ++f) {
-            const double2 K3 = Kld(1, f), K4 = Kld(2, f), K5 = Kld(3, f), yv = Yld(f);
+            const double2 K3 = Kld(1, f), K4 = Kld(2, f), K5 = Kld(3, f), yv = Yld(f), kv = K1ld(f);
             Kst(0, f, r[f][0], r[f][1]);
-            c[f][0] = fma(h, fma(dp::b1, k1[f][0], fma(dp::b3, K3.x, fma(dp::b4, K4.x, fma(dp::b5, K5.x, dp::b6 * r[f][0])))),
+            c[f][0] = fma(h, fma(dp::b1, kv.x, fma(dp::b3, K3.x, fma(dp::b4, K4.x, fma(dp::b5, K5.x, dp::b6 * r[f][0])))),
                           yv.x);
-            c[f][1] = fma(h, fma(dp::b1, k1[f][1], fma(dp::b3, K3.y, fma(dp::b4, K4.y, fma(dp::b5, K5.y, dp::b6 * r[f][1])))),
+            c[f][1] = fma(h, fma(dp::b1, kv.y, fma(dp::b3, K3.y, fma(dp::b4, K4.y, fma(dp::b5, K5.y, dp::b6 * r[f][1])))),
                           yv.y);
           }
           tile_store(0);
@@ -744,9 +730,9 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
       double p0 = 0.0, p1 = 0.0;
 #pragma unroll
       for (int f = 0; f < 5; ++f) {
-        const double2 K3 = Kld(1, f), K4 = Kld(2, f), K5 = Kld(3, f), K6 = Kld(0, f), yv = Yld(f);
-        const double e0 = fma(dp::e1, k1[f][0], fma(dp::e3, K3.x, fma(dp::e4, K4.x, fma(dp::e5, K5.x, fma(dp::e6, K6.x, dp::e7 * r[f][0])))));
-        const double e1_ = fma(dp::e1, k1[f][1], fma(dp::e3, K3.y, fma(dp::e4, K4.y, fma(dp::e5, K5.y, fma(dp::e6, K6.y, dp::e7 * r[f][1])))));
+        const double2 K3 = Kld(1, f), K4 = Kld(2, f), K5 = Kld(3, f), K6 = Kld(0, f), yv = Yld(f), kv = K1ld(f);
+        const double e0 = fma(dp::e1, kv.x, fma(dp::e3, K3.x, fma(dp::e4, K4.x, fma(dp::e5, K5.x, fma(dp::e6, K6.x, dp::e7 * r[f][0])))));
+        const double e1_ = fma(dp::e1, kv.y, fma(dp::e3, K3.y, fma(dp::e4, K4.y, fma(dp::e5, K5.y, fma(dp::e6, K6.y, dp::e7 * r[f][1])))));
         const double s0 = fma(fmax(fabs(yv.x), fabs(c[f][0])), A.opt.rtol, A.opt.atol);
         const double s1 = fma(fmax(fabs(yv.y), fabs(c[f][1])), A.opt.rtol, A.opt.atol);
         const double q0 = (h * e0) * fm::rcp3(s0);
@@ -849,8 +835,8 @@ cudaError_t launch_rk45(double* d_y, const marlpde_column_params* d_params, marl
   a.C = 0;
   a.logG = 0;
   a.opt = opt;
-  return rk45_variant() == 320 ? launch_t<320, false>(a, sm_count, smem_budget, stream)
-                               : launch_t<400, true>(a, sm_count, smem_budget, stream);
+  return rk45_variant() == 321 ? launch_t<320, true>(a, sm_count, smem_budget, stream)
+                               : launch_t<320, false>(a, sm_count, smem_budget, stream);
 }
 
 }  // namespace marlpde

@@ -1,0 +1,460 @@
+// rk45_streaming.cu — adaptive Dormand-Prince 5(4) for depth grids too large for shared memory
+// (BASELINE.json configs[3]: N = 2 000 ... 20 000 cells, 1-64 columns).
+//
+// Same stepper as rk45_persistent.cu (scipy RK45 semantics per column: rk.py `_step_impl`, `rk_step`,
+// `RkDenseOutput`; call site marlpde/Evolve_scenario.py:104-109) and the same rhs_pair arithmetic, but
+// the stage vectors stream through HBM/L2 instead of living on chip:
+//   * state, stage derivatives K1..K7 and two alternating stage-input vectors are [column][field][cell]
+//     arrays in a caller-provided workspace; a thread owns two adjacent cells, a CTA 256 cells of one
+//     column, the grid covers every column: 1.28 M cells in flight for 64 columns of 20 000 cells;
+//   * one launch per Runge-Kutta stage.  A stage kernel reads its input vector (own cells as 16-byte
+//     loads, the two halo cells from the neighbours' cache lines), evaluates the RHS, writes K_s and
+//     the next stage's input for its own cells.  The kernel boundary is the only synchronisation a
+//     stage needs (halos), so columns never wait for each other inside a kernel;
+//   * per-column control (error norm from per-CTA partial sums added in fixed order, accept/reject,
+//     step-size factor, t_eval dense output, FSAL by swapping two slot indices instead of copying K7)
+//     is folded into the `prepare` kernel that also forms the stage-2 input of the next attempt.
+//     Control blocks are double buffered, so every CTA of a column derives the same decision from
+//     the same inputs while the column's first CTA publishes the updated block;
+//   * algorithmic HBM traffic: 42 vector passes of 40 bytes per cell and attempt = 1 680 B per cell
+//     (DESIGN.md §4.4); the L2 keeps working sets up to ~100 MB on chip.
+// A call enqueues a fixed number of step attempts (no host round trip, no synchronisation); columns
+// that reach t_bound earlier idle, columns that do not come back resumable with status STEP_BUDGET.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "dopri.cuh"
+#include "lheureux_device.cuh"
+#include "rk45_streaming.cuh"
+
+namespace marlpde {
+namespace st {
+
+constexpr int kThreads = 128;                 // pairs per CTA
+constexpr int kCellsPerCta = 2 * kThreads;
+
+struct Ctl {                                   // per-column control block (double buffered)
+  double t, h_abs, h, t_new;
+  long long n_acc, n_rej, nfev, attempts;
+  int status;                                  // MARLPDE_STATUS_* once inactive
+  int active;                                  // 1: attempt in flight / to be started
+  int rejected;                                // a rejection happened within the current step
+  int next_eval;
+  int k1, k7;                                  // physical slots of K1 and K7 (0 or 6)
+  int fresh;                                   // 1: K1 has just been evaluated, no attempt finished yet
+  int pad;
+};
+
+struct Args {
+  double* y;                 // [B][5][N] state (updated in place on accepted steps)
+  const marlpde_column_params* params;
+  marlpde_column_state* state;
+  const double* t_eval;
+  double* snap;
+  double* K;                 // [7][B][5][N]
+  double* tile;              // [2][B][5][N]
+  double* partials;          // [B][tiles]
+  Ctl* ctl;                  // [2][B]
+  int B, N, tiles;
+  marlpde_rk45_options opt;
+};
+
+__host__ __device__ inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+struct Layout {
+  size_t off_K, off_tile, off_part, off_ctl, total;
+};
+__host__ inline Layout layout(int B, int N) {
+  const size_t vec = sizeof(double) * 5 * (size_t)N * B;
+  const int tiles = (N + kCellsPerCta - 1) / kCellsPerCta;
+  Layout L;
+  size_t o = 0;
+  L.off_K = o;     o += align256(7 * vec);
+  L.off_tile = o;  o += align256(2 * vec);
+  L.off_part = o;  o += align256(sizeof(double) * (size_t)tiles * B);
+  L.off_ctl = o;   o += align256(sizeof(Ctl) * 2 * (size_t)B);
+  L.total = o;
+  return L;
+}
+
+__device__ __forceinline__ double min_step_at(double t) { return 10.0 * fabs(nextafter(t, (double)INFINITY) - t); }
+
+// rk.py _step_impl prologue: clamp h_abs at the start of a step; then the attempt's (h, t_new)
+__device__ __forceinline__ void begin_step(Ctl& c, const marlpde_rk45_options& opt) {
+  const double ms = min_step_at(c.t);
+  if (c.h_abs > opt.max_step) c.h_abs = opt.max_step;
+  else if (c.h_abs < ms) c.h_abs = ms;
+  c.rejected = 0;
+}
+__device__ __forceinline__ bool begin_attempt(Ctl& c, const marlpde_rk45_options& opt) {
+  if (c.h_abs < min_step_at(c.t)) return false;
+  double h = c.h_abs;
+  c.t_new = c.t + h;
+  if (c.t_new - opt.t_bound > 0.0) c.t_new = opt.t_bound;
+  h = c.t_new - c.t;
+  c.h = h;
+  c.h_abs = fabs(h);
+  return true;
+}
+
+// ---- control blocks from the caller's per-column state (one thread per column)
+__global__ void init_kernel(const Args A) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= A.B) return;
+  const marlpde_column_state s = A.state[col];
+  Ctl c;
+  c.t = s.t;
+  c.h_abs = s.h_abs;
+  c.h = 0.0;
+  c.t_new = s.t;
+  c.n_acc = s.n_accepted;
+  c.n_rej = s.n_rejected;
+  c.nfev = s.nfev;
+  c.attempts = 0;
+  c.status = MARLPDE_STATUS_STEP_BUDGET;
+  c.active = 1;
+  c.rejected = 0;
+  c.next_eval = s.next_eval;
+  c.k1 = 0;
+  c.k7 = 6;
+  c.fresh = 1;
+  c.pad = 0;
+  if (s.t >= A.opt.t_bound) {
+    c.active = 0;
+    c.status = MARLPDE_STATUS_FINISHED;
+  }
+  A.ctl[col] = c;            // buffer 0: read by the first stage-0 launch and the first prepare
+  A.ctl[A.B + col] = c;
+}
+
+__global__ void finish_kernel(const Args A, int parity) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= A.B) return;
+  const Ctl c = A.ctl[(size_t)parity * A.B + col];
+  marlpde_column_state s;
+  s.t = c.t;
+  s.h_abs = c.h_abs;
+  s.n_accepted = c.n_acc;
+  s.n_rejected = c.n_rej;
+  s.nfev = c.nfev;
+  s.status = c.active ? MARLPDE_STATUS_STEP_BUDGET : c.status;
+  s.next_eval = c.next_eval;
+  A.state[col] = s;
+}
+
+struct Cells {               // what a thread knows about its two cells
+  int col, pair, cell0;
+  bool v0, v1;
+  size_t base;               // offset of (col, field 0, cell0) inside a [B][5][N] vector
+};
+
+__device__ __forceinline__ Cells my_cells(const Args& A) {
+  Cells m;
+  m.col = blockIdx.x / A.tiles;
+  m.pair = (blockIdx.x - m.col * A.tiles) * kThreads + threadIdx.x;
+  m.cell0 = 2 * m.pair;
+  m.v0 = m.cell0 < A.N;
+  m.v1 = m.cell0 + 1 < A.N;
+  m.base = (size_t)m.col * 5 * A.N + m.cell0;
+  return m;
+}
+
+// two adjacent cells of field f from a [B][5][N] vector (N may be odd: no 16-byte loads)
+__device__ __forceinline__ void ld2(const double* v, const Cells& m, int f, int N, double& a, double& b) {
+  const double* p = v + m.base + (size_t)f * N;
+  a = m.v0 ? p[0] : 0.0;
+  b = m.v1 ? p[1] : 0.0;
+}
+__device__ __forceinline__ void st2(double* v, const Cells& m, int f, int N, double a, double b) {
+  double* p = v + m.base + (size_t)f * N;
+  if (m.v0) p[0] = a;
+  if (m.v1) p[1] = b;
+}
+
+// ---- prepare: close the previous attempt of every column (error norm -> accept/reject -> new h,
+// dense output, y <- y_new, FSAL slot swap) and form the stage-2 input of the next attempt.
+// Reads control buffer `pin`, writes `pin ^ 1`.
+__global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin) {
+  __shared__ __align__(16) unsigned char tab_raw[fm::kTableBytes];
+  const fm::Tables tb = fm::stage_tables(tab_raw, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const Cells m = my_cells(A);
+  const int N = A.N;
+  const size_t vec = (size_t)A.B * 5 * N;
+  Ctl c = A.ctl[(size_t)pin * A.B + m.col];
+  const bool publisher = blockIdx.x == m.col * A.tiles && threadIdx.x == 0;
+  if (!c.active) {
+    if (publisher) A.ctl[(size_t)(pin ^ 1) * A.B + m.col] = c;
+    return;
+  }
+  double* const tile0 = A.tile;
+  double* const tile1 = A.tile + vec;
+  const double* K1 = A.K + (size_t)c.k1 * vec;
+  if (!c.fresh) {
+    // ---- error norm of the attempt that just ran: per-CTA partial sums, fixed order
+    double sum = 0.0;
+    const double* part = A.partials + (size_t)m.col * A.tiles;
+    for (int i = 0; i < A.tiles; ++i) sum += part[i];
+    const double err_norm = sqrt(sum / (double)(5 * N));
+    c.nfev += 6;
+    c.attempts += 1;
+    if (err_norm < 1.0) {
+      double factor = dp::MAX_FACTOR;
+      if (err_norm != 0.0) factor = fmin(dp::MAX_FACTOR, dp::SAFETY * fm::exp(tb, -0.2 * fm::log(tb, err_norm)));
+      if (c.rejected) factor = fmin(1.0, factor);
+      const double* K7 = A.K + (size_t)c.k7 * vec;
+      // dense output for t_eval points in (t, t_new]
+      int ne = c.next_eval;
+      while (ne < A.opt.n_eval) {
+        const double te = A.t_eval[ne];
+        if (!(te <= c.t_new)) break;
+        const double x = (te - c.t) / c.h;
+#pragma unroll 1
+        for (int f = 0; f < 5; ++f) {
+          double k[6][2], yv[2];
+          ld2(K1, m, f, N, k[0][0], k[0][1]);
+          ld2(A.K + 2 * vec, m, f, N, k[1][0], k[1][1]);
+          ld2(A.K + 3 * vec, m, f, N, k[2][0], k[2][1]);
+          ld2(A.K + 4 * vec, m, f, N, k[3][0], k[3][1]);
+          ld2(A.K + 5 * vec, m, f, N, k[4][0], k[4][1]);
+          ld2(K7, m, f, N, k[5][0], k[5][1]);
+          ld2(A.y, m, f, N, yv[0], yv[1]);
+          double out[2];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            double qq[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              double s = dp::P[0][j] * k[0][q];
+              s = fma(dp::P[2][j], k[1][q], s);
+              s = fma(dp::P[3][j], k[2][q], s);
+              s = fma(dp::P[4][j], k[3][q], s);
+              s = fma(dp::P[5][j], k[4][q], s);
+              qq[j] = fma(dp::P[6][j], k[5][q], s);
+            }
+            out[q] = fma(c.h, x * (qq[0] + x * (qq[1] + x * (qq[2] + x * qq[3]))), yv[q]);
+          }
+          double* sp = A.snap + ((size_t)m.col * A.opt.n_eval + ne) * 5 * N + (size_t)f * N + m.cell0;
+          if (m.v0) sp[0] = out[0];
+          if (m.v1) sp[1] = out[1];
+        }
+        ++ne;
+      }
+      c.next_eval = ne;
+      // accept: y <- y_new (stage-6 input, tile 0), K1 <-> K7
+#pragma unroll
+      for (int f = 0; f < 5; ++f) {
+        double a, b;
+        ld2(tile0, m, f, N, a, b);
+        st2(A.y, m, f, N, a, b);
+      }
+      const int tmp = c.k1;
+      c.k1 = c.k7;
+      c.k7 = tmp;
+      K1 = A.K + (size_t)c.k1 * vec;
+      c.t = c.t_new;
+      c.h_abs *= factor;
+      c.n_acc += 1;
+      if (c.t >= A.opt.t_bound) {
+        c.active = 0;
+        c.status = MARLPDE_STATUS_FINISHED;
+      } else {
+        begin_step(c, A.opt);
+        if (!begin_attempt(c, A.opt)) {
+          c.active = 0;
+          c.status = MARLPDE_STATUS_STEP_TOO_SMALL;
+        }
+      }
+    } else {
+      c.h_abs *= fmax(dp::MIN_FACTOR, dp::SAFETY * fm::exp(tb, -0.2 * fm::log(tb, err_norm)));
+      c.rejected = 1;
+      c.n_rej += 1;
+      if (!begin_attempt(c, A.opt)) {
+        c.active = 0;
+        c.status = MARLPDE_STATUS_STEP_TOO_SMALL;
+      }
+    }
+  } else {
+    c.fresh = 0;
+    c.nfev += 1;
+    begin_step(c, A.opt);
+    if (!begin_attempt(c, A.opt)) {
+      c.active = 0;
+      c.status = MARLPDE_STATUS_STEP_TOO_SMALL;
+    }
+  }
+  if (c.active) {
+    // stage-2 input: y + h a21 K1 (for an accepted step y was just rewritten by this very thread)
+    const double ha = c.h * dp::a21;
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      double y0, y1, k0, k1v;
+      ld2(A.y, m, f, N, y0, y1);
+      ld2(K1, m, f, N, k0, k1v);
+      st2(tile1, m, f, N, fma(ha, k0, y0), fma(ha, k1v, y1));
+    }
+  }
+  if (publisher) A.ctl[(size_t)(pin ^ 1) * A.B + m.col] = c;
+}
+
+// ---- one Runge-Kutta stage: i = 0 evaluates K1 = f(y) (fresh columns), i = 1..6 evaluates K_{i+1}
+// from stage-input vector (i & 1), stores it and writes the next stage input; i = 6 writes the
+// CTA's contribution to the error norm instead.
+__global__ void __launch_bounds__(kThreads) stage_kernel(const Args A, int i, int cbuf) {
+  __shared__ ColumnConsts kc;
+  __shared__ __align__(16) unsigned char tab_raw[fm::kTableBytes];
+  __shared__ double red[kThreads / 32];
+  const Cells m = my_cells(A);
+  const Ctl c = A.ctl[(size_t)cbuf * A.B + m.col];
+  if (!c.active || (i == 0 && !c.fresh)) return;          // uniform per CTA
+  const fm::Tables tb = fm::stage_tables(tab_raw, threadIdx.x, blockDim.x);
+  const int N = A.N;
+  if (threadIdx.x == 0) make_consts(A.params[m.col], N, kc);
+  __syncthreads();
+  const size_t vec = (size_t)A.B * 5 * N;
+  const double* in = i == 0 ? A.y : A.tile + (size_t)(i & 1) * vec;
+  double* const nxt = A.tile + (size_t)((i + 1) & 1) * vec;
+
+  double cc[5][2], mlo[5], phi[5];
+#pragma unroll
+  for (int f = 0; f < 5; ++f) {
+    const double* p = in + m.base + (size_t)f * N;
+    cc[f][0] = m.v0 ? p[0] : 0.5;
+    cc[f][1] = m.v1 ? p[1] : 0.5;
+    mlo[f] = (m.v0 && m.cell0 > 0) ? p[-1] : top_ghost(kc, f, cc[f][0]);
+    if (m.cell0 + 2 < N) {
+      phi[f] = p[2];
+    } else if (m.v1) {
+      phi[f] = bottom_ghost(f, cc[f][1], cc[f][0]);
+    } else {
+      cc[f][1] = bottom_ghost(f, cc[f][0], mlo[f]);
+      phi[f] = cc[f][1];
+    }
+  }
+  const bool in_mask[2] = {m.cell0 >= kc.mask_lo && m.cell0 < kc.mask_hi,
+                           m.cell0 + 1 >= kc.mask_lo && m.cell0 + 1 < kc.mask_hi};
+  double r[5][2], U[2], W[2];
+  PairFlags fl = rhs_pair(kc, tb, cc, mlo, phi, in_mask, r, U, W);
+  fl.bad[0] = fl.bad[0] && m.v0;
+  fl.bad[1] = fl.bad[1] && m.v1;
+  if (fl.bad[0] || fl.bad[1]) rhs_pair_fixup(kc, tb, fl, cc, mlo, phi, in_mask, r, U, W);
+
+  const double h = c.h;
+  auto Kslot = [&](int logical) -> double* {   // logical stage 1..7 -> physical slot
+    const int s = logical == 1 ? c.k1 : (logical == 7 ? c.k7 : logical - 1);
+    return A.K + (size_t)s * vec;
+  };
+  double part = 0.0;
+#pragma unroll 1
+  for (int f = 0; f < 5; ++f) {
+    const double r0 = r[f][0], r1 = r[f][1];
+    if (i == 0) {
+      st2(Kslot(1), m, f, N, r0, r1);
+      continue;
+    }
+    st2(Kslot(i + 1), m, f, N, r0, r1);
+    double y0, y1, a0 = 0.0, a1 = 0.0, k0, k1v;
+    ld2(A.y, m, f, N, y0, y1);
+    ld2(Kslot(1), m, f, N, k0, k1v);
+    if (i == 1) {
+      a0 = fma(dp::a31, k0, dp::a32 * r0);
+      a1 = fma(dp::a31, k1v, dp::a32 * r1);
+    } else if (i == 2) {
+      double p0, p1;
+      ld2(Kslot(2), m, f, N, p0, p1);
+      a0 = fma(dp::a41, k0, fma(dp::a42, p0, dp::a43 * r0));
+      a1 = fma(dp::a41, k1v, fma(dp::a42, p1, dp::a43 * r1));
+    } else if (i == 3) {
+      double p0, p1, q0, q1;
+      ld2(Kslot(2), m, f, N, p0, p1);
+      ld2(Kslot(3), m, f, N, q0, q1);
+      a0 = fma(dp::a51, k0, fma(dp::a52, p0, fma(dp::a53, q0, dp::a54 * r0)));
+      a1 = fma(dp::a51, k1v, fma(dp::a52, p1, fma(dp::a53, q1, dp::a54 * r1)));
+    } else if (i == 4) {
+      double p0, p1, q0, q1, s0, s1;
+      ld2(Kslot(2), m, f, N, p0, p1);
+      ld2(Kslot(3), m, f, N, q0, q1);
+      ld2(Kslot(4), m, f, N, s0, s1);
+      a0 = fma(dp::a61, k0, fma(dp::a62, p0, fma(dp::a63, q0, fma(dp::a64, s0, dp::a65 * r0))));
+      a1 = fma(dp::a61, k1v, fma(dp::a62, p1, fma(dp::a63, q1, fma(dp::a64, s1, dp::a65 * r1))));
+    } else {
+      double q0, q1, s0, s1, u0, u1;
+      ld2(Kslot(3), m, f, N, q0, q1);
+      ld2(Kslot(4), m, f, N, s0, s1);
+      ld2(Kslot(5), m, f, N, u0, u1);
+      if (i == 5) {
+        a0 = fma(dp::b1, k0, fma(dp::b3, q0, fma(dp::b4, s0, fma(dp::b5, u0, dp::b6 * r0))));
+        a1 = fma(dp::b1, k1v, fma(dp::b3, q1, fma(dp::b4, s1, fma(dp::b5, u1, dp::b6 * r1))));
+      } else {  // i == 6: r = K7; error estimate of both cells
+        double v0, v1;
+        ld2(Kslot(6), m, f, N, v0, v1);
+        const double e0 = fma(dp::e1, k0, fma(dp::e3, q0, fma(dp::e4, s0, fma(dp::e5, u0, fma(dp::e6, v0, dp::e7 * r0)))));
+        const double e1 = fma(dp::e1, k1v, fma(dp::e3, q1, fma(dp::e4, s1, fma(dp::e5, u1, fma(dp::e6, v1, dp::e7 * r1)))));
+        const double s0c = fma(fmax(fabs(y0), fabs(cc[f][0])), A.opt.rtol, A.opt.atol);
+        const double s1c = fma(fmax(fabs(y1), fabs(cc[f][1])), A.opt.rtol, A.opt.atol);
+        const double z0 = (h * e0) * fm::rcp3(s0c), z1 = (h * e1) * fm::rcp3(s1c);
+        if (m.v0) part = fma(z0, z0, part);
+        if (m.v1) part = fma(z1, z1, part);
+        continue;
+      }
+    }
+    st2(nxt, m, f, N, fma(h, a0, y0), fma(h, a1, y1));
+  }
+  if (i == 6) {
+    // CTA-wide sum in a fixed order: xor butterfly per warp, then the warp sums in warp order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < kThreads / 32; ++w) s += red[w];
+      A.partials[(size_t)m.col * A.tiles + (blockIdx.x - m.col * A.tiles)] = s;
+    }
+  }
+}
+
+}  // namespace st
+
+size_t rk45_stream_workspace_bytes(int n_columns, int n_cells) { return st::layout(n_columns, n_cells).total; }
+
+cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_params, marlpde_column_state* d_state,
+                               int n_columns, int n_cells, const marlpde_rk45_options& opt, const double* d_t_eval,
+                               double* d_snap, void* d_work, long long attempts, cudaStream_t stream) {
+  const st::Layout L = st::layout(n_columns, n_cells);
+  unsigned char* w = static_cast<unsigned char*>(d_work);
+  st::Args a;
+  a.y = d_y;
+  a.params = d_params;
+  a.state = d_state;
+  a.t_eval = d_t_eval;
+  a.snap = d_snap;
+  a.K = reinterpret_cast<double*>(w + L.off_K);
+  a.tile = reinterpret_cast<double*>(w + L.off_tile);
+  a.partials = reinterpret_cast<double*>(w + L.off_part);
+  a.ctl = reinterpret_cast<st::Ctl*>(w + L.off_ctl);
+  a.B = n_columns;
+  a.N = n_cells;
+  a.tiles = (n_cells + st::kCellsPerCta - 1) / st::kCellsPerCta;
+  a.opt = opt;
+  const long long blocks = (long long)a.tiles * n_columns;
+  if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+  const unsigned grid = (unsigned)blocks;
+  const unsigned cgrid = (unsigned)((n_columns + 127) / 128);
+  st::init_kernel<<<cgrid, 128, 0, stream>>>(a);
+  st::stage_kernel<<<grid, st::kThreads, 0, stream>>>(a, 0, 0);            // K1 = f(y)
+  int pin = 0;
+  // attempts + 1 prepares: the last one only closes the last attempt (its stage-2 input is unused)
+  for (long long j = 0; j < attempts; ++j) {
+    st::prepare_kernel<<<grid, st::kThreads, 0, stream>>>(a, pin);
+    for (int i = 1; i <= 6; ++i) st::stage_kernel<<<grid, st::kThreads, 0, stream>>>(a, i, pin ^ 1);
+    pin ^= 1;
+  }
+  st::prepare_kernel<<<grid, st::kThreads, 0, stream>>>(a, pin);
+  pin ^= 1;
+  st::finish_kernel<<<cgrid, 128, 0, stream>>>(a, pin);
+  return cudaGetLastError();
+}
+
+}  // namespace marlpde

@@ -74,6 +74,14 @@ SYMBOLS = {
     "marlpde_rhs_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int]),
     "marlpde_rk45_integrate_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(RK45Options),
                                              _P, _P, _P, _P, _P, _P]),
+    "marlpde_rk45_stream_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "marlpde_rk45_stream_integrate_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(RK45Options),
+                                                    _P, _P, _P, C.c_size_t, _P]),
+    "marlpde_radau_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "marlpde_radau_integrate_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(RK45Options),
+                                              _P, _P, _P, _P, C.c_size_t, _P, _P]),
+    "marlpde_radau_integrate": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(RK45Options),
+                                          _P, _P, _P, C.c_int]),
     "marlpde_probe_math": (C.c_int, [C.c_int, _P, C.c_int, _P, C.c_int]),
     "marlpde_probe_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "marlpde_rk45_integrate": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(RK45Options),

@@ -154,6 +154,8 @@ def integrate_rk45_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e
         N = y0.shape[2]
         st = make_state(B, t0, first_step) if state is None else np.ascontiguousarray(state, dtype=STATE_DTYPE)
         y = y0 if inplace else y0.clone()
+        if B and (N > lib.marlpde_rk45_max_cells() or N < 32):
+            return _stream_rk45_device(lib, y, d_params, st, opts, t_eval_arr, B, N, dev, cap)
         with torch.cuda.device(dev):
             d_state = torch.from_numpy(st.view(np.uint8).copy()).to(dev)
             d_te = torch.from_numpy(t_eval_arr.copy()).to(dev) if n_eval else None
@@ -187,3 +189,136 @@ def integrate_rk45_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e
                       n_accepted=st_out["n_accepted"].copy(), n_rejected=st_out["n_rejected"].copy(),
                       nfev=st_out["nfev"].copy(), t_eval=t_eval_arr, snapshots=snaps,
                       next_eval=st_out["next_eval"].copy(), event_counts=ec, event_times=et, state=st_out)
+
+
+def _stream_rk45_device(lib, y, d_params, st, opts, t_eval_arr, B, N, dev, cap, batch: int = 512):
+    """Depth grids that do not fit on chip: repeat fixed-size batches of step attempts of the streaming
+    kernels (csrc/rk45_streaming.cu) on torch's current stream until every column has finished or
+    `max_steps` is used up.  The per-batch status read-back is the only host round trip."""
+    import torch
+    n_eval = int(t_eval_arr.size)
+    budget = int(opts.max_steps)
+    with torch.cuda.device(dev):
+        d_state = torch.from_numpy(st.view(np.uint8).copy()).to(dev)
+        d_te = torch.from_numpy(t_eval_arr.copy()).to(dev) if n_eval else None
+        d_snap = torch.empty((B, n_eval, 5, N), dtype=torch.float64, device=dev)
+        nb = int(lib.marlpde_rk45_stream_workspace_bytes(B, N))
+        d_work = torch.empty(nb // 8 + 1, dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        used = 0
+        while True:
+            o = _cabi.RK45Options(t_bound=opts.t_bound, rtol=opts.rtol, atol=opts.atol, max_step=opts.max_step,
+                                  max_steps=min(batch, budget - used) if budget > 0 else batch, n_eval=n_eval,
+                                  event_capacity=opts.event_capacity, flags=opts.flags, reserved=0)
+            _cabi.check(lib.marlpde_rk45_stream_integrate_dev(
+                y.data_ptr(), d_params.data_ptr(), d_state.data_ptr(), B, N, C.byref(o),
+                d_te.data_ptr() if n_eval else None, d_snap.data_ptr(), d_work.data_ptr(), nb, stream))
+            used += int(o.max_steps)
+            st_out = d_state.cpu().numpy().view(STATE_DTYPE).reshape(B)
+            if not np.any(st_out["status"] == 1) or (budget > 0 and used >= budget):
+                break
+    ec = np.zeros((B, NEVENTS), dtype=np.int32)
+    et = np.full((B, NEVENTS, cap), np.nan)
+    return RK45Result(y=y, t=st_out["t"].copy(), h_abs=st_out["h_abs"].copy(), status=st_out["status"].copy(),
+                      n_accepted=st_out["n_accepted"].copy(), n_rejected=st_out["n_rejected"].copy(),
+                      nfev=st_out["nfev"].copy(), t_eval=t_eval_arr, snapshots=d_snap,
+                      next_eval=st_out["next_eval"].copy(), event_counts=ec, event_times=et, state=st_out)
+
+
+@dataclass
+class RadauResult:
+    """Per-column results of the implicit integrator (batched analogue of solve_ivp's OdeResult)."""
+    y: object                    # [B,5,N] state at the time reached
+    t: np.ndarray                # [B]
+    h_abs: np.ndarray            # [B] next step size
+    status: np.ndarray           # [B] 0 finished, -1 step too small, 1 step budget exhausted
+    n_accepted: np.ndarray       # accepted steps
+    n_rejected: np.ndarray       # steps rejected by the error test
+    nfev: np.ndarray
+    njev: np.ndarray             # finite-difference Jacobians (15 RHS evaluations each, counted in nfev)
+    nlu: np.ndarray              # block-tridiagonal factorisations (real and complex counted separately)
+    newton_iterations: np.ndarray
+    newton_failures: np.ndarray
+    t_eval: np.ndarray
+    snapshots: object            # [B,n_eval,5,N]
+    next_eval: np.ndarray
+    state: np.ndarray = field(default=None, repr=False)
+
+    def solutions(self, column: int) -> np.ndarray:
+        snap = self.snapshots[column]
+        snap = snap.cpu().numpy() if _is_torch(snap) else np.asarray(snap)
+        return np.ascontiguousarray(np.transpose(snap[: int(self.next_eval[column])], (1, 2, 0)))
+
+
+def integrate_radau_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e-3, atol=1e-3, t_eval=None,
+                          max_step=np.inf, max_steps: int = 0, state: np.ndarray | None = None, device: int = 0,
+                          inplace: bool = False) -> RadauResult:
+    """Implicit integration of every column: 3-stage Radau IIA with SciPy's step-size, Newton and
+    Jacobian-reuse rules (`solve_ivp(method="Radau", jac_sparsity=jacobian_sparsity())`, the
+    reference's default Solver, parameters.py:201-221) and a block-tridiagonal linear solver."""
+    lib = _cabi.lib()
+    t0, t_bound = float(t_span[0]), float(t_span[1])
+    if not t_bound > t0:
+        raise ValueError("only forward integration (t_span[1] > t_span[0]) is supported")
+    if state is None:
+        fs = np.asarray(first_step, dtype=np.float64)
+        if np.any(fs <= 0):
+            raise ValueError("`first_step` must be positive.")
+        if np.any(fs > abs(t_bound - t0)):
+            raise ValueError("`first_step` exceeds bounds.")
+    t_eval_arr = np.zeros(0) if t_eval is None else np.ascontiguousarray(t_eval, dtype=np.float64)
+    if t_eval_arr.ndim != 1:
+        raise ValueError("`t_eval` must be 1-dimensional.")
+    if t_eval_arr.size:
+        if np.any(t_eval_arr < t0) or np.any(t_eval_arr > t_bound):
+            raise ValueError("Values in `t_eval` are not within `t_span`.")
+        if np.any(np.diff(t_eval_arr) <= 0):
+            raise ValueError("Values in `t_eval` are not properly sorted.")
+    n_eval = int(t_eval_arr.size)
+    opts = _cabi.RK45Options(t_bound=t_bound, rtol=float(rtol), atol=float(atol), max_step=float(max_step),
+                             max_steps=int(max_steps), n_eval=n_eval, event_capacity=0, flags=0, reserved=0)
+    if _is_torch(y0):
+        import torch
+        if not y0.is_cuda or y0.dtype != torch.float64 or not y0.is_contiguous():
+            raise ValueError("device path needs a contiguous float64 CUDA tensor")
+        dev = y0.device
+        d_params = params if _is_torch(params) else params_to_device(params, dev)
+        B = d_params.numel() // PARAMS_DTYPE.itemsize
+        _check_y(y0, B)
+        N = y0.shape[2]
+        st = make_state(B, t0, first_step) if state is None else np.ascontiguousarray(state, dtype=STATE_DTYPE)
+        y = y0 if inplace else y0.clone()
+        with torch.cuda.device(dev):
+            d_state = torch.from_numpy(st.view(np.uint8).copy()).to(dev)
+            d_te = torch.from_numpy(t_eval_arr.copy()).to(dev) if n_eval else None
+            d_snap = torch.empty((B, n_eval, 5, N), dtype=torch.float64, device=dev)
+            d_queue = torch.zeros(1, dtype=torch.int32, device=dev)
+            d_stats = torch.zeros((B, 4), dtype=torch.int64, device=dev)
+            nb = int(lib.marlpde_radau_workspace_bytes(B, N))
+            d_work = torch.empty(max(nb, 8) // 8, dtype=torch.float64, device=dev)
+            stream = torch.cuda.current_stream().cuda_stream
+            _cabi.check(lib.marlpde_radau_integrate_dev(
+                y.data_ptr(), d_params.data_ptr(), d_state.data_ptr(), B, N, C.byref(opts),
+                d_te.data_ptr() if n_eval else None, d_snap.data_ptr(), d_stats.data_ptr(), d_work.data_ptr(),
+                nb, d_queue.data_ptr(), stream))
+            st_out = d_state.cpu().numpy().view(STATE_DTYPE).reshape(B)
+            stats = d_stats.cpu().numpy()
+        snaps = d_snap
+    else:
+        p = _as_params(params)
+        B = p.shape[0]
+        y = np.array(y0, dtype=np.float64, order="C", copy=not inplace)
+        _check_y(y, B)
+        N = y.shape[2]
+        st_out = make_state(B, t0, first_step) if state is None else np.array(state, dtype=STATE_DTYPE, copy=True)
+        snaps = np.full((B, n_eval, 5, N), np.nan)
+        stats = np.zeros((B, 4), dtype=np.int64)
+        _cabi.check(lib.marlpde_radau_integrate(
+            _cabi.ptr(y), _cabi.ptr(p), _cabi.ptr(st_out), B, N, C.byref(opts),
+            _cabi.ptr(t_eval_arr) if n_eval else None, _cabi.ptr(snaps) if n_eval else None, _cabi.ptr(stats),
+            device))
+    return RadauResult(y=y, t=st_out["t"].copy(), h_abs=st_out["h_abs"].copy(), status=st_out["status"].copy(),
+                       n_accepted=st_out["n_accepted"].copy(), n_rejected=st_out["n_rejected"].copy(),
+                       nfev=st_out["nfev"].copy(), njev=stats[:, 0].copy(), nlu=stats[:, 1].copy(),
+                       newton_iterations=stats[:, 2].copy(), newton_failures=stats[:, 3].copy(),
+                       t_eval=t_eval_arr, snapshots=snaps, next_eval=st_out["next_eval"].copy(), state=st_out)

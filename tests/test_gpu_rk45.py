@@ -113,8 +113,8 @@ def test_unsupported_and_degenerate_inputs():
     from marlpde_b200._cabi import MarlpdeError
     pde = oracle.default_scenario()
     P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
-    with pytest.raises(MarlpdeError, match="n_cells"):
-        mb.integrate_rk45_batch(np.zeros((1, 5, 700)), P)
+    with pytest.raises(MarlpdeError, match="events"):          # large grids stream through HBM, without event monitors
+        mb.integrate_rk45_batch(np.full((1, 5, 700), 0.5), P, events=True, event_capacity=4)
     res = mb.integrate_rk45_batch(y0[:0], P[:0])
     assert res.y.shape == (0, 5, 200)
     # a state that is already non-finite collapses the step size like SciPy: status -1, never hangs

@@ -90,7 +90,7 @@ def test_hdf5_roundtrip_layout_of_the_reference_driver(tmp_path):
 
 def test_cabi_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "marlpde_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|const char\*)\s+(marlpde_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:int|size_t|const char\*)\s+(marlpde_[a-z0-9_]+)\s*\(", header, flags=re.M))
     assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
     lib = ctypes.CDLL(_cabi.LIB_PATH)
     for name in declared:
@@ -131,5 +131,15 @@ def test_argument_validation_before_any_device_work():
     with pytest.raises(ValueError):
         mb.rhs_batch(y0[:, :4], P)
     opts = _cabi.RK45Options(t_bound=1.0, rtol=1e-3, atol=1e-3, max_step=float("inf"))
-    rc = _cabi.lib().marlpde_rk45_integrate(None, None, None, 1, 1000, ctypes.byref(opts), None, None, None, None, 0)
+    # the on-chip kernel's device entry point refuses grids that do not fit shared memory ...
+    rc = _cabi.lib().marlpde_rk45_integrate_dev(None, None, None, 1, 1000, ctypes.byref(opts), None, None, None, None,
+                                                None, None)
     assert rc == -4 and b"n_cells" in _cabi.lib().marlpde_last_error()
+    # ... the host entry point routes them to the streaming path, which validates its own arguments
+    rc = _cabi.lib().marlpde_rk45_integrate(None, None, None, 1, 1000, ctypes.byref(opts), None, None, None, None, 0)
+    assert rc == -1 and b"NULL" in _cabi.lib().marlpde_last_error()
+    opts.flags = _cabi.FLAG_EVENTS
+    rc = _cabi.lib().marlpde_rk45_integrate(None, None, None, 1, 1000, ctypes.byref(opts), None, None, None, None, 0)
+    assert rc == -4 and b"events" in _cabi.lib().marlpde_last_error()
+    assert _cabi.lib().marlpde_rk45_stream_workspace_bytes(64, 20000) > 9 * 64 * 5 * 20000 * 8
+    assert _cabi.lib().marlpde_radau_workspace_bytes(1, 200) == 8 * 200 * (80 + 76 + 100)

@@ -351,8 +351,71 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                                  "status_histogram": {str(int(k)): int(v) for k, v in
                                                       zip(*np.unique(st2["status"], return_counts=True))},
                                  "events_located_per_monitor": d_ec.cpu().numpy().sum(axis=0).tolist(),
+                                 "unfinished_columns": [[int(c), int(st2["status"][c]), float(st2["t"][c]),
+                                                         float(st2["h_abs"][c])]
+                                                        for c in np.nonzero(st2["status"] != 0)[0][:32]],
                                  "steps_per_column_min_max": [int((st2["n_accepted"] + st2["n_rejected"]).min()),
                                                               int((st2["n_accepted"] + st2["n_rejected"]).max())]}
+
+    if args.full:
+        # ---- implicit path (BASELINE.json configs[4]): the same sweep to T* with the batched Radau IIA kernel
+        implicit = {}
+        for base_name in ("scenario_A", "default"):
+            sw = mb.sweep_lattice(scenario_base(base_name), *lat)
+            Pi, yi = mb.derive_column_params(sw)[sl], mb.initial_state(sw)[sl]
+            d_yi = torch.from_numpy(yi).to(dev)
+            d_pi = batch.params_to_device(Pi, dev)
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(stream)
+            rr = mb.integrate_radau_batch(d_yi, d_pi, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e-3, atol=1e-3,
+                                          events=True, event_capacity=EVCAP, inplace=True)
+            r1.record(stream)
+            torch.cuda.synchronize()
+            secs = r0.elapsed_time(r1) * 1e-3
+            implicit[base_name] = {
+                "seconds": secs, "columns": int(B), "finished": int((rr.status == 0).sum()),
+                "steps_per_column_min_max": [int(rr.n_accepted.min()), int(rr.n_accepted.max())],
+                "radau_steps": int(rr.n_accepted.sum()), "rejected": int(rr.n_rejected.sum()),
+                "newton_iterations": int(rr.newton_iterations.sum()), "lu_factorisations": int(rr.nlu.sum()),
+                "jacobians": int(rr.njev.sum()), "nfev": int(rr.nfev.sum()),
+                "radau_steps_per_s": float(rr.n_accepted.sum() + rr.n_rejected.sum()) / secs}
+            del d_yi, rr
+        line["implicit_time_to_Tstar"] = implicit
+        # ---- large depth grids (BASELINE.json configs[3]): streaming RK45, HBM roofline
+        large = {}
+        for nL, bL, attL in ((20000, 64, 96), (2000, 64, 256), (20000, 1, 256)):
+            pL = scenario_base("scenario_A") | {"N": nL}
+            PL = np.repeat(mb.derive_column_params(pL), bL)
+            yL = torch.from_numpy(np.repeat(mb.initial_state(pL), bL, 0)).to(dev)
+            dPL = batch.params_to_device(PL, dev)
+            stL = batch.make_state(bL, 0.0, 1e-6 * (200 / nL) ** 2)
+            d_stL = torch.from_numpy(stL.view(np.uint8).copy()).to(dev)
+            nb = int(lib.marlpde_rk45_stream_workspace_bytes(bL, nL))
+            d_wL = torch.empty(nb // 8 + 1, dtype=torch.float64, device=dev)
+            oL = _cabi.RK45Options(t_bound=1.0, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=attL, n_eval=0,
+                                   event_capacity=0, flags=0, reserved=0)
+
+            def run_large():
+                _cabi.check(lib.marlpde_rk45_stream_integrate_dev(yL.data_ptr(), dPL.data_ptr(), d_stL.data_ptr(), bL, nL,
+                                                                  C.byref(oL), None, None, d_wL.data_ptr(), nb,
+                                                                  stream.cuda_stream))
+            run_large()                                            # warm-up (also moves past the first steps)
+            torch.cuda.synchronize()
+            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0.record(stream)
+            run_large()
+            l1.record(stream)
+            torch.cuda.synchronize()
+            secs = l0.elapsed_time(l1) * 1e-3
+            alg_bytes = 1680.0 * nL * bL * attL                    # 42 vector passes x 40 B per cell and attempt
+            large[f"N{nL}_B{bL}"] = {"n_cells": nL, "columns": bL, "attempts_per_column": attL, "seconds": secs,
+                                     "column_steps_per_s": bL * attL / secs, "cell_steps_per_s": bL * attL * nL / secs,
+                                     "algorithmic_GBps": alg_bytes / secs / 1e9,
+                                     "frac_of_hbm_peak": alg_bytes / secs / 1e9 / 6550.4,
+                                     "working_set_MB": nb / 1e6, "launches": 7 * attL + 4}
+            del yL, d_wL
+        line["large_n_streaming"] = large
 
     if world == 1 and not args.no_cpu_baseline:
         import multiprocessing as mp

@@ -55,6 +55,10 @@ extern "C" {
 #define MARLPDE_STATUS_STEP_TOO_SMALL (-1) /* "Required step size is less than spacing between numbers." */
 #define MARLPDE_STATUS_NONFINITE (-2)   /* state became non-finite and the step size collapsed */
 #define MARLPDE_STATUS_STEP_BUDGET 1    /* max_steps attempts used up; (t, h_abs, y) are resumable */
+#define MARLPDE_STATUS_STEP_BUDGET_MIDSTEP 2 /* streaming path only: the budget ended inside a step whose last
+                                          attempt was rejected; resumable like 1 (pass the state back unchanged:
+                                          the next attempt then keeps SciPy's "no growth after a rejection" rule,
+                                          so a run cut into batches is bit-identical to an uninterrupted one) */
 
 /*
  * Per-column constants: exactly the scalars the reference passes into pde_rhs
@@ -172,7 +176,9 @@ int marlpde_rk45_stream_integrate_dev(double* d_y, const marlpde_column_params* 
 
 /* ---- batched implicit integrator: 3-stage Radau IIA with a block-tridiagonal simplified Newton solve
  * (replaces solve_ivp(method="Radau", jac_sparsity=...) per column; scipy/integrate/_ivp/radau.py) ------
- *  Arguments as for marlpde_rk45_integrate_dev (same options struct; flags are ignored), plus
+ *  Arguments as for marlpde_rk45_integrate_dev (same options struct, same event outputs: with
+ *  MARLPDE_FLAG_EVENTS the 7 monitors are evaluated after every accepted step and sign changes are
+ *  located with Brent's method on the cubic Radau dense output), plus
  *  d_stats    [n_columns][4] int64, accumulated: Jacobian evaluations (njev), LU factorisations (nlu),
  *             Newton iterations, Newton failures
  *  d_workspace  marlpde_radau_workspace_bytes(n_columns, n_cells) bytes of device scratch (Jacobian
@@ -184,12 +190,14 @@ size_t marlpde_radau_workspace_bytes(int n_columns, int n_cells);
 int marlpde_radau_integrate_dev(double* d_y, const marlpde_column_params* d_params,
                                 marlpde_column_state* d_state, int n_columns, int n_cells,
                                 const marlpde_rk45_options* opts, const double* d_t_eval,
-                                double* d_snapshots, int64_t* d_stats, void* d_workspace,
-                                size_t workspace_bytes, int32_t* d_queue, void* stream);
+                                double* d_snapshots, int32_t* d_event_counts, double* d_event_times,
+                                int64_t* d_stats, void* d_workspace, size_t workspace_bytes,
+                                int32_t* d_queue, void* stream);
 int marlpde_radau_integrate(double* y, const marlpde_column_params* params,
                             marlpde_column_state* state, int n_columns, int n_cells,
                             const marlpde_rk45_options* opts, const double* t_eval,
-                            double* snapshots, int64_t* stats, int device);
+                            double* snapshots, int32_t* event_counts, double* event_times,
+                            int64_t* stats, int device);
 
 /* ---- measurement helper: fp64 FMA peak (TFLOP/s, best of `repeats`) of `device`, the roofline
  * denominator of the fp64-pipe-bound RK45 kernel (no reference counterpart). */

@@ -230,7 +230,9 @@ static int rk45_integrate_streaming(double* y, const marlpde_column_params* para
     CU(cudaMemcpy(hs.data(), ds.p, nb_state, cudaMemcpyDeviceToHost));   // synchronises
     used += batch;
     bool pending = false;
-    for (int c = 0; c < n_columns; ++c) pending = pending || hs[(size_t)c].status == MARLPDE_STATUS_STEP_BUDGET;
+    for (int c = 0; c < n_columns; ++c)
+      pending = pending || hs[(size_t)c].status == MARLPDE_STATUS_STEP_BUDGET ||
+                hs[(size_t)c].status == MARLPDE_STATUS_STEP_BUDGET_MIDSTEP;
     if (!pending || (budget > 0 && used >= budget)) break;
   }
   CU(cudaMemcpy(y, dy.p, nb_y, cudaMemcpyDeviceToHost));
@@ -340,14 +342,19 @@ static int check_radau_args(int n_columns, int n_cells, const marlpde_rk45_optio
 
 int marlpde_radau_integrate_dev(double* d_y, const marlpde_column_params* d_params, marlpde_column_state* d_state,
                                 int n_columns, int n_cells, const marlpde_rk45_options* opts,
-                                const double* d_t_eval, double* d_snapshots, int64_t* d_stats, void* d_workspace,
-                                size_t workspace_bytes, int32_t* d_queue, void* stream) {
+                                const double* d_t_eval, double* d_snapshots, int32_t* d_event_counts,
+                                double* d_event_times, int64_t* d_stats, void* d_workspace, size_t workspace_bytes,
+                                int32_t* d_queue, void* stream) {
   int rc = check_radau_args(n_columns, n_cells, opts);
   if (rc) return rc;
   if (n_columns == 0) return MARLPDE_OK;
   if (!d_y || !d_params || !d_state || !d_queue || !d_stats || !d_workspace)
     return fail(MARLPDE_EINVAL, "NULL device pointer");
   if (opts->n_eval > 0 && (!d_t_eval || !d_snapshots)) return fail(MARLPDE_EINVAL, "n_eval > 0 needs t_eval and snapshots");
+  if (opts->flags & MARLPDE_FLAG_EVENTS) {
+    if (!d_event_counts) return fail(MARLPDE_EINVAL, "MARLPDE_FLAG_EVENTS needs event_counts");
+    if (opts->event_capacity > 0 && !d_event_times) return fail(MARLPDE_EINVAL, "event_capacity > 0 needs event_times");
+  }
   if (workspace_bytes < marlpde::radau_workspace_bytes(n_columns, n_cells))
     return fail(MARLPDE_EINVAL, "workspace too small: %zu < %zu bytes", workspace_bytes,
                 marlpde::radau_workspace_bytes(n_columns, n_cells));
@@ -355,7 +362,8 @@ int marlpde_radau_integrate_dev(double* d_y, const marlpde_column_params* d_para
   rc = current_props(props);
   if (rc) return rc;
   cudaError_t e = marlpde::launch_radau(d_y, d_params, d_state, n_columns, n_cells, *opts, d_t_eval, d_snapshots,
-                                        d_stats, static_cast<double*>(d_workspace), d_queue, props.sm_count,
+                                        d_stats, d_event_counts, d_event_times, static_cast<double*>(d_workspace),
+                                        d_queue, props.sm_count,
                                         (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "radau launch");
   return MARLPDE_OK;
@@ -363,7 +371,8 @@ int marlpde_radau_integrate_dev(double* d_y, const marlpde_column_params* d_para
 
 int marlpde_radau_integrate(double* y, const marlpde_column_params* params, marlpde_column_state* state,
                             int n_columns, int n_cells, const marlpde_rk45_options* opts, const double* t_eval,
-                            double* snapshots, int64_t* stats, int device) {
+                            double* snapshots, int32_t* event_counts, double* event_times, int64_t* stats,
+                            int device) {
   int rc = check_radau_args(n_columns, n_cells, opts);
   if (rc) return rc;
   if (n_columns == 0) return MARLPDE_OK;
@@ -375,7 +384,14 @@ int marlpde_radau_integrate(double* y, const marlpde_column_params* params, marl
   const size_t nb_snap = nb_y * (size_t)opts->n_eval;
   const size_t nb_stats = sizeof(int64_t) * 4 * (size_t)n_columns;
   const size_t nb_work = marlpde::radau_workspace_bytes(n_columns, n_cells);
-  DevBuf dy, dp, ds, dte, dsnap, dq, dst, dw;
+  const size_t nb_ec = sizeof(int32_t) * MARLPDE_NEVENTS * (size_t)n_columns;
+  const size_t nb_et = sizeof(double) * MARLPDE_NEVENTS * (size_t)(opts->event_capacity > 0 ? opts->event_capacity : 0) * n_columns;
+  DevBuf dy, dp, ds, dte, dsnap, dq, dst, dw, dec, det;
+  CU(dec.alloc(nb_ec));
+  CU(det.alloc(nb_et));
+  if (event_counts) CU(cudaMemcpy(dec.p, event_counts, nb_ec, cudaMemcpyHostToDevice));
+  else CU(cudaMemset(dec.p, 0, nb_ec));
+  if (event_times && nb_et) CU(cudaMemcpy(det.p, event_times, nb_et, cudaMemcpyHostToDevice));
   CU(dy.alloc(nb_y));
   CU(dp.alloc(sizeof(marlpde_column_params) * (size_t)n_columns));
   CU(ds.alloc(sizeof(marlpde_column_state) * (size_t)n_columns));
@@ -393,13 +409,16 @@ int marlpde_radau_integrate(double* y, const marlpde_column_params* params, marl
   CU(cudaMemcpy(dst.p, stats, nb_stats, cudaMemcpyHostToDevice));
   rc = marlpde_radau_integrate_dev(dy.as<double>(), dp.as<marlpde_column_params>(), ds.as<marlpde_column_state>(),
                                    n_columns, n_cells, opts, dte.as<double>(), dsnap.as<double>(),
-                                   dst.as<int64_t>(), dw.p, nb_work, dq.as<int32_t>(), nullptr);
+                                   dec.as<int32_t>(), det.as<double>(), dst.as<int64_t>(), dw.p, nb_work,
+                                   dq.as<int32_t>(), nullptr);
   if (rc) return rc;
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(y, dy.p, nb_y, cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(state, ds.p, sizeof(marlpde_column_state) * (size_t)n_columns, cudaMemcpyDeviceToHost));
   if (snapshots && nb_snap) CU(cudaMemcpy(snapshots, dsnap.p, nb_snap, cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(stats, dst.p, nb_stats, cudaMemcpyDeviceToHost));
+  if (event_counts) CU(cudaMemcpy(event_counts, dec.p, nb_ec, cudaMemcpyDeviceToHost));
+  if (event_times && nb_et) CU(cudaMemcpy(event_times, det.p, nb_et, cudaMemcpyDeviceToHost));
   return MARLPDE_OK;
 }
 

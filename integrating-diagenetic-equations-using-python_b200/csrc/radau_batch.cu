@@ -28,6 +28,7 @@
 
 #include <cstdint>
 
+#include "brent.cuh"
 #include "lheureux_device.cuh"
 #include "radau_batch.cuh"
 
@@ -53,6 +54,12 @@ constexpr double kEps = 2.220446049250313e-16;
 constexpr double kSqrtEps = 1.4901161193847656e-08;
 
 constexpr int kWarpsPerCta = 4;
+// resident CTAs per SM the kernel is compiled for: 4 x 4 warps = 16 columns in flight per SM at 128
+// registers per thread (measured r01b, 4096 columns: 4 -> 3.07 s, 6 -> 3.12 s, 8 -> 3.42 s: more
+// residency only adds spills, the sweeps are bound by memory latency, see the cp.async ring below)
+#ifndef MARLPDE_RADAU_MINBLOCKS
+#define MARLPDE_RADAU_MINBLOCKS 4
+#endif
 
 // ---- complex helpers (double2 = re, im) -------------------------------------------------------
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -68,6 +75,18 @@ __device__ __forceinline__ double2 cinv(double2 a) {
   const double d = 1.0 / fma(a.x, a.x, a.y * a.y);
   return make_double2(a.x * d, -a.y * d);
 }
+
+// ---- asynchronous global -> shared copies (LDGSTS): the block-Thomas sweeps are sequential in the cell
+// index, so the matrices of the next kDepth cells are kept in flight while the current cell is processed
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+constexpr int kDepth = 3;          // cells in flight ahead of the one being processed
+constexpr int kSlots = kDepth + 1;
 
 // per-column workspace, in doubles (n = 5 N): see radau_workspace_doubles()
 struct Work {
@@ -86,8 +105,8 @@ struct __align__(16) WarpScratch {          // shared memory per warp
   double2 sinv_prev[2][25];   // S_{i-1}^{-1} of both systems (row major)
   double2 vec[2][2][8];       // two broadcast buffers x two systems x 5 entries (padded)
   double2 mult[2][8];         // Gauss-Jordan multipliers of the pivot column, + pivot row index in [5].x
-  double jst[2][80];          // factorise: staged Jacobian blocks [L|D|U] of cell i / i+1
-  double mst[2][128];         // solve: staged {J block, S^-1 sys 0, S^-1 sys 1} of cell i / i+1 (16-byte aligned)
+  double jst[kSlots][80];     // factorise: staged Jacobian blocks [L|D|U] of cells i .. i+kDepth (ring)
+  double mst[kSlots][128];    // solve: staged {J block, S^-1 sys 0, S^-1 sys 1} of cells i .. i+kDepth (16-byte aligned)
 };
 
 struct Args {
@@ -97,6 +116,8 @@ struct Args {
   const double* g_t_eval;
   double* g_snap;
   int64_t* g_stats;     // [n_columns][4]: njev, nlu, newton iterations, newton failures
+  int32_t* g_ev_counts; // [n_columns][7]              (MARLPDE_FLAG_EVENTS)
+  double* g_ev_times;   // [n_columns][7][event_capacity]
   double* g_work;
   int32_t* g_queue;
   int n_columns, N;
@@ -216,22 +237,26 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
   const int c5 = apart ? cc : cc - 5;
   const double2 M = s == 0 ? make_double2(kMuReal / h, 0.0) : make_double2(kMuCRe / h, kMuCIm / h);
   double2* const out = Sinv + (size_t)s * N * 25;
-  // stage cell 0
-  for (int e = lane; e < 75; e += 32) ws.jst[0][e] = J[e];
-  __syncwarp();
+  // ring of kSlots staged cells: cells 0 .. kDepth-1 are requested up front, cell i+kDepth at iteration i
+  auto request = [&](int cell) {
+    if (cell < N) {
+      const double* Jn = J + (size_t)cell * 75;
+      double* dst = ws.jst[cell % kSlots];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (lane + 32 * k < 75) cp_async8(dst + lane + 32 * k, Jn + lane + 32 * k);
+    }
+    cp_async_commit();                                       // (empty groups keep the group count uniform)
+  };
+  for (int c0 = 0; c0 < kDepth; ++c0) request(c0);
   double2 xcol[5];                                          // column c5 of X_{i-1} = S_{i-1}^{-1} U_{i-1}
 #pragma unroll
   for (int r = 0; r < 5; ++r) xcol[r] = make_double2(0.0, 0.0);
   for (int i = 0; i < N; ++i) {
-    const double* Ji = ws.jst[i & 1];
-    // prefetch the blocks of cell i+1 (registers now, shared memory at the end of this iteration)
-    double pre[3] = {0.0, 0.0, 0.0};
-    if (i + 1 < N) {
-      const double* Jn = J + (size_t)(i + 1) * 75;
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        if (lane + 32 * k < 75) pre[k] = Jn[lane + 32 * k];
-    }
+    request(i + kDepth);                  // slot (i + kDepth) % kSlots was released at the end of iteration i-1
+    cp_async_wait<kDepth>();              // all but the kDepth newest groups have landed: cell i is in shared memory
+    __syncwarp();
+    const double* Ji = ws.jst[i % kSlots];
     double2 col[5];
     if (apart) {
       // column c5 of S = M I - D_i - L_i X_{i-1} e_c   (X_{-1} = 0)
@@ -309,15 +334,9 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
         xcol[r] = acc;
       }
     }
-    // hand the prefetched blocks of cell i+1 over
-    if (i + 1 < N) {
-      double* Jst = ws.jst[(i + 1) & 1];
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        if (lane + 32 * k < 75) Jst[lane + 32 * k] = pre[k];
-    }
-    __syncwarp();
+    __syncwarp();                         // everyone is done with slot i % kSlots before it is requested again
   }
+  cp_async_wait<0>();
 }
 
 // Solve (M I - J) x = b for both systems by the block-Thomas sweeps.  lane = 8 s + r (r < 5):
@@ -337,32 +356,33 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
   const double* S1 = reinterpret_cast<const double*>(Sinv + (size_t)N * 25);
   // element e of the staged record of cell i: [0,25) J block (L forward / U backward), [26,76) S^{-1}
   // of system 0, [76,126) S^{-1} of system 1 (offsets keep the double2 reads 16-byte aligned)
-  auto fetch = [&](int i, int blk, double (&pre)[4]) {
-    const double* Jb = J + (size_t)i * 75 + blk;
-    const double* s0 = S0 + (size_t)i * 50;
-    const double* s1 = S1 + (size_t)i * 50;
+  auto request = [&](int i, int blk, int slot, bool ok) {
+    if (ok) {
+      const double* Jb = J + (size_t)i * 75 + blk;
+      const double* s0 = S0 + (size_t)i * 50;
+      const double* s1 = S1 + (size_t)i * 50;
+      double* dst = ws.mst[slot];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int e = lane + 32 * k;
-      pre[k] = e < 25 ? Jb[e] : (e < 26 ? 0.0 : (e < 76 ? s0[e - 26] : (e < 126 ? s1[e - 76] : 0.0)));
+      for (int k = 0; k < 4; ++k) {
+        const int e = lane + 32 * k;
+        if (e < 25) cp_async8(dst + e, Jb + e);
+        else if (e >= 26 && e < 76) cp_async8(dst + e, s0 + (e - 26));
+        else if (e >= 76 && e < 126) cp_async8(dst + e, s1 + (e - 76));
+      }
     }
-  };
-  auto hand_over = [&](int slot, const double (&pre)[4]) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) ws.mst[slot][lane + 32 * k] = pre[k];
+    cp_async_commit();
   };
   int buf = 0;
-  double pre[4];
-  fetch(0, 0, pre);
-  hand_over(0, pre);
-  __syncwarp();
+  for (int c0 = 0; c0 < kDepth; ++c0) request(c0, 0, c0 % kSlots, c0 < N);
   // ---- forward: g_i = b_i + L_i p_{i-1},  p_i = S_i^{-1} g_i  (p overwrites b)
   double2 p = make_double2(0.0, 0.0);
   double2 bnext = valid ? make_double2(bre[r * N], bim ? bim[r * N] : 0.0) : make_double2(0.0, 0.0);
   for (int i = 0; i < N; ++i) {
-    const double* M = ws.mst[i & 1];
+    request(i + kDepth, 0, (i + kDepth) % kSlots, i + kDepth < N);
+    cp_async_wait<kDepth>();
+    __syncwarp();
+    const double* M = ws.mst[i % kSlots];
     const bool more = i + 1 < N;
-    if (more) fetch(i + 1, 0, pre);
     double2 g = bnext;
     if (valid && more) bnext = make_double2(bre[r * N + i + 1], bim ? bim[r * N + i + 1] : 0.0);
     if (valid) ws.vec[buf][s][r] = p;
@@ -384,21 +404,20 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
       if (bim) bim[r * N + i] = p.y;
     }
     buf ^= 1;
-    if (more) hand_over((i + 1) & 1, pre);
     __syncwarp();
   }
+  cp_async_wait<0>();
   if (N < 2) return;
-  // ---- backward: x_{N-1} = p_{N-1},  x_i = p_i + S_i^{-1} (U_i x_{i+1})
-  fetch(N - 2, 50, pre);
-  hand_over(0, pre);
-  __syncwarp();
+  // ---- backward: x_{N-1} = p_{N-1},  x_i = p_i + S_i^{-1} (U_i x_{i+1});  step j handles cell N-2-j
+  for (int c0 = 0; c0 < kDepth; ++c0) request(N - 2 - c0, 50, c0 % kSlots, N - 2 - c0 >= 0);
   double2 x = p;
   bnext = valid ? make_double2(bre[r * N + N - 2], bim ? bim[r * N + N - 2] : 0.0) : make_double2(0.0, 0.0);
-  int slot = 0;
-  for (int i = N - 2; i >= 0; --i) {
-    const double* M = ws.mst[slot];
+  for (int i = N - 2, j = 0; i >= 0; --i, ++j) {
+    request(i - kDepth, 50, (j + kDepth) % kSlots, i - kDepth >= 0);
+    cp_async_wait<kDepth>();
+    __syncwarp();
+    const double* M = ws.mst[j % kSlots];
     const bool more = i > 0;
-    if (more) fetch(i - 1, 50, pre);
     const double2 pi = bnext;
     if (valid && more) bnext = make_double2(bre[r * N + i - 1], bim ? bim[r * N + i - 1] : 0.0);
     if (valid) ws.vec[buf][s][r] = x;
@@ -421,10 +440,58 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
       if (bim) bim[r * N + i] = x.y;
     }
     buf ^= 1;
-    if (more) hand_over(slot ^ 1, pre);
-    slot ^= 1;
     __syncwarp();
   }
+  cp_async_wait<0>();
+}
+
+// The seven event monitors (LHeureux_model.py:524-593) of the state val(f, i), by one warp:
+// g = {min y, min CA, min CC, max(CA+CC)-1, max Phi - 1, min U(Phi), max W(Phi)}.  NaNs propagate like
+// np.amin / np.amax.  U and W use the arithmetic of rhs_pair.
+template <class Val>
+__device__ __forceinline__ void monitors(const ColumnConsts& kc, const fm::Tables& tb, int N, int lane, Val&& val,
+                                         double (&g)[7]) {
+  const double inf = (double)INFINITY;
+  double m[7] = {inf, inf, inf, -inf, -inf, inf, -inf};
+  bool nan5 = false, nanS = false, nanPhi = false, nanCA = false, nanCC = false;
+  for (int i = lane; i < N; i += 32) {
+    const double CA = val(0, i), CC = val(1, i), cCa = val(2, i), cCO3 = val(3, i), Phi = val(4, i);
+    nanCA |= CA != CA;
+    nanCC |= CC != CC;
+    nanPhi |= Phi != Phi;
+    nan5 |= (cCa != cCa) || (cCO3 != cCO3);
+    const double F = 1.0 - fm::exp(tb, fma(-10.0, fm::rcp3(Phi), 10.0));
+    const double Phi2 = Phi * Phi;
+    const double U = fma(kc.rhorat * (Phi2 * Phi), F * fm::rcp3(1.0 - Phi), kc.presum);
+    const double W = fma(-kc.rhorat * Phi2, F, kc.presum);
+    m[0] = fmin(m[0], fmin(fmin(fmin(CA, CC), fmin(cCa, cCO3)), Phi));
+    m[1] = fmin(m[1], CA);
+    m[2] = fmin(m[2], CC);
+    m[3] = fmax(m[3], CA + CC);
+    m[4] = fmax(m[4], Phi);
+    m[5] = fmin(m[5], U);
+    m[6] = fmax(m[6], W);
+    nanS |= (U != U) || (W != W);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const double other = __shfl_xor_sync(0xffffffffu, m[k], o);
+      m[k] = (k == 3 || k == 4 || k == 6) ? fmax(m[k], other) : fmin(m[k], other);
+    }
+  }
+  const unsigned bCA = __ballot_sync(0xffffffffu, nanCA), bCC = __ballot_sync(0xffffffffu, nanCC),
+                 bPhi = __ballot_sync(0xffffffffu, nanPhi), b5 = __ballot_sync(0xffffffffu, nan5),
+                 bS = __ballot_sync(0xffffffffu, nanS);
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  g[0] = (bCA | bCC | bPhi | b5) ? qnan : m[0];
+  g[1] = bCA ? qnan : m[1];
+  g[2] = bCC ? qnan : m[2];
+  g[3] = (bCA | bCC) ? qnan : m[3] - 1.0;
+  g[4] = bPhi ? qnan : m[4] - 1.0;
+  g[5] = (bPhi | bS) ? qnan : m[5];
+  g[6] = (bPhi | bS) ? qnan : m[6];
 }
 
 __device__ __forceinline__ double predict_factor(double h_abs, double h_abs_old, double err, double err_old) {
@@ -434,7 +501,7 @@ __device__ __forceinline__ double predict_factor(double h_abs, double h_abs_old,
   return fmin(1.0, mult) * pow(err, -0.25);     // err == 0 -> inf, as numpy with divide='ignore'
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) radau_kernel(const Args A) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) radau_kernel(const Args A) {
   __shared__ __align__(16) unsigned char tab_raw[fm::kTableBytes];
   __shared__ WarpScratch scratch[kWarpsPerCta];
   const fm::Tables tb = fm::stage_tables(tab_raw, threadIdx.x, blockDim.x);
@@ -487,6 +554,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) radau_kernel(const Args 
       njev += 1;
       nfev += 15;
     }
+    const bool ev_on = (A.opt.flags & MARLPDE_FLAG_EVENTS) != 0;
+    double g_old[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (ev_on && t < A.opt.t_bound)                        // ivp.py: g = [event(t0, y0) for event in events]
+      monitors(kc, tb, N, lane, [&](int f, int i) { return y[f * N + i]; }, g_old);
     bool current_jac = true, lu_valid = false, have_sol = false;
     double h_abs_old = -1.0, err_old = -1.0;     // "None"
     double t_old = t, h_old = 0.0;
@@ -691,6 +762,42 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) radau_kernel(const Args 
       have_sol = true;
       n_acc += 1;
       steps_done += 1;
+      // ---- events (ivp.py main loop: after every accepted step, before the t_eval samples)
+      if (ev_on) {
+        double g_new[7];
+        monitors(kc, tb, N, lane, [&](int f, int i) { return y[f * N + i]; }, g_new);
+#pragma unroll 1
+        for (int k = 0; k < 7; ++k) {
+          if (!event_active(g_old[k], g_new[k])) continue;
+          // brentq on the dense output between t_old and t (solve_event_equation, xtol = rtol = 4 eps)
+          BrentState bs;
+          bs.init(t_old, t);
+          double xeval = t_old, root = t;
+          for (;;) {
+            const double xx = (xeval - t_old) / h_old;
+            double gv[7];
+            monitors(kc, tb, N, lane,
+                     [&](int f, int i) {
+                       const int idx = f * N + i;
+                       return w.yold[idx] + xx * (w.Q[idx] + xx * (w.Q[n + idx] + xx * w.Q[2 * n + idx]));
+                     },
+                     gv);
+            double gk = gv[0];
+#pragma unroll
+            for (int kk = 1; kk < 7; ++kk) gk = (k == kk) ? gv[kk] : gk;
+            if (bs.feed(gk, xeval, root)) break;
+          }
+          if (lane == 0) {
+            int32_t* cnt = A.g_ev_counts + (size_t)col * MARLPDE_NEVENTS + k;
+            const int have = *cnt;
+            if (have < A.opt.event_capacity)
+              A.g_ev_times[((size_t)col * MARLPDE_NEVENTS + k) * A.opt.event_capacity + have] = root;
+            *cnt = have + 1;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 7; ++k) g_old[k] = g_new[k];
+      }
       // ---- t_eval samples in (t_old, t] (t_eval[0] == t0 belongs to the first step): y_old + Q p(x)
       while (next_eval < A.opt.n_eval) {
         const double te = A.g_t_eval[next_eval];
@@ -729,8 +836,8 @@ size_t radau_workspace_bytes(int n_columns, int n_cells) {
 
 cudaError_t launch_radau(double* d_y, const marlpde_column_params* d_params, marlpde_column_state* d_state,
                          int n_columns, int n_cells, const marlpde_rk45_options& opt, const double* d_t_eval,
-                         double* d_snap, int64_t* d_stats, double* d_work, int32_t* d_queue, int sm_count,
-                         cudaStream_t stream) {
+                         double* d_snap, int64_t* d_stats, int32_t* d_ev_counts, double* d_ev_times, double* d_work,
+                         int32_t* d_queue, int sm_count, cudaStream_t stream) {
   rd::Args a;
   a.g_y = d_y;
   a.g_params = d_params;
@@ -738,13 +845,15 @@ cudaError_t launch_radau(double* d_y, const marlpde_column_params* d_params, mar
   a.g_t_eval = d_t_eval;
   a.g_snap = d_snap;
   a.g_stats = d_stats;
+  a.g_ev_counts = d_ev_counts;
+  a.g_ev_times = d_ev_times;
   a.g_work = d_work;
   a.g_queue = d_queue;
   a.n_columns = n_columns;
   a.N = n_cells;
   a.opt = opt;
   int ctas = (n_columns + rd::kWarpsPerCta - 1) / rd::kWarpsPerCta;
-  const int max_ctas = sm_count * 8;
+  const int max_ctas = sm_count * MARLPDE_RADAU_MINBLOCKS;
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas < 1) ctas = 1;
   rd::radau_kernel<<<ctas, rd::kWarpsPerCta * 32, 0, stream>>>(a);

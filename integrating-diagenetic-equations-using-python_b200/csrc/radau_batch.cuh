@@ -13,7 +13,7 @@ size_t radau_workspace_bytes(int n_columns, int n_cells);
 
 cudaError_t launch_radau(double* d_y, const marlpde_column_params* d_params, marlpde_column_state* d_state,
                          int n_columns, int n_cells, const marlpde_rk45_options& opt, const double* d_t_eval,
-                         double* d_snap, int64_t* d_stats, double* d_work, int32_t* d_queue, int sm_count,
-                         cudaStream_t stream);
+                         double* d_snap, int64_t* d_stats, int32_t* d_ev_counts, double* d_ev_times, double* d_work,
+                         int32_t* d_queue, int sm_count, cudaStream_t stream);
 
 }  // namespace marlpde

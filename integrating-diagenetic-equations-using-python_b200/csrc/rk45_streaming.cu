@@ -43,7 +43,7 @@ struct Ctl {                                   // per-column control block (doub
   int next_eval;
   int k1, k7;                                  // physical slots of K1 and K7 (0 or 6)
   int fresh;                                   // 1: K1 has just been evaluated, no attempt finished yet
-  int pad;
+  int midstep;                                 // resumed inside a step (after a rejected attempt)
 };
 
 struct Args {
@@ -119,7 +119,8 @@ __global__ void init_kernel(const Args A) {
   c.k1 = 0;
   c.k7 = 6;
   c.fresh = 1;
-  c.pad = 0;
+  c.midstep = s.status == MARLPDE_STATUS_STEP_BUDGET_MIDSTEP ? 1 : 0;
+  c.rejected = c.midstep;
   if (s.t >= A.opt.t_bound) {
     c.active = 0;
     c.status = MARLPDE_STATUS_FINISHED;
@@ -138,7 +139,7 @@ __global__ void finish_kernel(const Args A, int parity) {
   s.n_accepted = c.n_acc;
   s.n_rejected = c.n_rej;
   s.nfev = c.nfev;
-  s.status = c.active ? MARLPDE_STATUS_STEP_BUDGET : c.status;
+  s.status = c.active ? (c.rejected ? MARLPDE_STATUS_STEP_BUDGET_MIDSTEP : MARLPDE_STATUS_STEP_BUDGET) : c.status;
   s.next_eval = c.next_eval;
   A.state[col] = s;
 }
@@ -277,8 +278,9 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin
     }
   } else {
     c.fresh = 0;
-    c.nfev += 1;
-    begin_step(c, A.opt);
+    if (c.nfev == 0) c.nfev = 1;               // K1 of a resumed column replaces the FSAL value: not counted again
+    if (!c.midstep) begin_step(c, A.opt);      // a mid-step resume continues the step it was in
+    c.midstep = 0;
     if (!begin_attempt(c, A.opt)) {
       c.active = 0;
       c.status = MARLPDE_STATUS_STEP_TOO_SMALL;
@@ -298,10 +300,26 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin
   if (publisher) A.ctl[(size_t)(pin ^ 1) * A.B + m.col] = c;
 }
 
+// Stage algebra as data: after K_{i+1} = r has been evaluated, the next stage input is
+//   y + h (sum_j kCoef[i][j-1] K_j + kNew[i] r)          (i = 1..5; i = 5 gives y_new)
+// and for i = 6 the same sum is the error estimate h (sum_j e_j K_j + e_7 r).
+__constant__ double kCoef[7][6] = {{0, 0, 0, 0, 0, 0},
+                                   {dp::a31, 0, 0, 0, 0, 0},
+                                   {dp::a41, dp::a42, 0, 0, 0, 0},
+                                   {dp::a51, dp::a52, dp::a53, 0, 0, 0},
+                                   {dp::a61, dp::a62, dp::a63, dp::a64, 0, 0},
+                                   {dp::b1, 0, dp::b3, dp::b4, dp::b5, 0},
+                                   {dp::e1, 0, dp::e3, dp::e4, dp::e5, dp::e6}};
+__constant__ double kNew[7] = {0, dp::a32, dp::a43, dp::a54, dp::a65, dp::b6, dp::e7};
+
 // ---- one Runge-Kutta stage: i = 0 evaluates K1 = f(y) (fresh columns), i = 1..6 evaluates K_{i+1}
 // from stage-input vector (i & 1), stores it and writes the next stage input; i = 6 writes the
 // CTA's contribution to the error norm instead.
-__global__ void __launch_bounds__(kThreads) stage_kernel(const Args A, int i, int cbuf) {
+// Memory-level parallelism: EVERYTHING the stage reads — its input cells and halos, y and the
+// earlier K's — is requested before the RHS is evaluated (the K's are reduced to one partial sum
+// per cell on arrival), so ~80 independent loads per thread are in flight while the fp64 work of
+// the RHS runs; after the RHS only two fused multiply-adds and the stores remain.
+__global__ void __launch_bounds__(kThreads, 3) stage_kernel(const Args A, int i, int cbuf) {
   __shared__ ColumnConsts kc;
   __shared__ __align__(16) unsigned char tab_raw[fm::kTableBytes];
   __shared__ double red[kThreads / 32];
@@ -311,20 +329,63 @@ __global__ void __launch_bounds__(kThreads) stage_kernel(const Args A, int i, in
   const fm::Tables tb = fm::stage_tables(tab_raw, threadIdx.x, blockDim.x);
   const int N = A.N;
   if (threadIdx.x == 0) make_consts(A.params[m.col], N, kc);
-  __syncthreads();
   const size_t vec = (size_t)A.B * 5 * N;
   const double* in = i == 0 ? A.y : A.tile + (size_t)(i & 1) * vec;
   double* const nxt = A.tile + (size_t)((i + 1) & 1) * vec;
+  const double h = c.h;
+  auto Kslot = [&](int logical) -> double* {   // logical stage 1..7 -> physical slot
+    const int s = logical == 1 ? c.k1 : (logical == 7 ? c.k7 : logical - 1);
+    return A.K + (size_t)s * vec;
+  };
 
-  double cc[5][2], mlo[5], phi[5];
+  // ---- all loads of this stage: input cells + raw halo values, y, earlier K's (as partial sums)
+  double cc[5][2], hm[5], hp[5], acc[5][2], pre[5][2];
 #pragma unroll
   for (int f = 0; f < 5; ++f) {
     const double* p = in + m.base + (size_t)f * N;
     cc[f][0] = m.v0 ? p[0] : 0.5;
     cc[f][1] = m.v1 ? p[1] : 0.5;
-    mlo[f] = (m.v0 && m.cell0 > 0) ? p[-1] : top_ghost(kc, f, cc[f][0]);
+    hm[f] = (m.v0 && m.cell0 > 0) ? p[-1] : 0.0;
+    hp[f] = (m.cell0 + 2 < N) ? p[2] : 0.0;
+    acc[f][0] = acc[f][1] = 0.0;
+    pre[f][0] = pre[f][1] = 0.0;
+  }
+  if (i > 0) {
+#pragma unroll
+    for (int j = 1; j <= 6; ++j) {
+      const double cj = kCoef[i][j - 1];
+      if (cj != 0.0) {                                      // uniform: the stage index is a launch argument
+        const double* Kj = Kslot(j);
+#pragma unroll
+        for (int f = 0; f < 5; ++f) {
+          double a0, a1;
+          ld2(Kj, m, f, N, a0, a1);
+          acc[f][0] = fma(cj, a0, acc[f][0]);
+          acc[f][1] = fma(cj, a1, acc[f][1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      double y0, y1;
+      ld2(A.y, m, f, N, y0, y1);
+      if (i < 6) {
+        pre[f][0] = fma(h, acc[f][0], y0);
+        pre[f][1] = fma(h, acc[f][1], y1);
+      } else {   // error weights h / scale, scale = atol + rtol max(|y|, |y_new|)  (cc = y_new)
+        pre[f][0] = h * fm::rcp3(fma(fmax(fabs(y0), fabs(cc[f][0])), A.opt.rtol, A.opt.atol));
+        pre[f][1] = h * fm::rcp3(fma(fmax(fabs(y1), fabs(cc[f][1])), A.opt.rtol, A.opt.atol));
+      }
+    }
+  }
+  __syncthreads();                                          // kc and the tables are staged
+
+  double mlo[5], phi[5];
+#pragma unroll
+  for (int f = 0; f < 5; ++f) {
+    mlo[f] = (m.v0 && m.cell0 > 0) ? hm[f] : top_ghost(kc, f, cc[f][0]);
     if (m.cell0 + 2 < N) {
-      phi[f] = p[2];
+      phi[f] = hp[f];
     } else if (m.v1) {
       phi[f] = bottom_ghost(f, cc[f][1], cc[f][0]);
     } else {
@@ -340,68 +401,30 @@ __global__ void __launch_bounds__(kThreads) stage_kernel(const Args A, int i, in
   fl.bad[1] = fl.bad[1] && m.v1;
   if (fl.bad[0] || fl.bad[1]) rhs_pair_fixup(kc, tb, fl, cc, mlo, phi, in_mask, r, U, W);
 
-  const double h = c.h;
-  auto Kslot = [&](int logical) -> double* {   // logical stage 1..7 -> physical slot
-    const int s = logical == 1 ? c.k1 : (logical == 7 ? c.k7 : logical - 1);
-    return A.K + (size_t)s * vec;
-  };
+  // ---- epilogue: K_{i+1} and the next stage input (or the error contribution)
   double part = 0.0;
-#pragma unroll 1
-  for (int f = 0; f < 5; ++f) {
-    const double r0 = r[f][0], r1 = r[f][1];
-    if (i == 0) {
-      st2(Kslot(1), m, f, N, r0, r1);
-      continue;
+  if (i == 0) {
+    double* K1 = Kslot(1);
+#pragma unroll
+    for (int f = 0; f < 5; ++f) st2(K1, m, f, N, r[f][0], r[f][1]);
+  } else if (i < 6) {
+    double* Kn = Kslot(i + 1);
+    const double hn = h * kNew[i];
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      st2(Kn, m, f, N, r[f][0], r[f][1]);
+      st2(nxt, m, f, N, fma(hn, r[f][0], pre[f][0]), fma(hn, r[f][1], pre[f][1]));
     }
-    st2(Kslot(i + 1), m, f, N, r0, r1);
-    double y0, y1, a0 = 0.0, a1 = 0.0, k0, k1v;
-    ld2(A.y, m, f, N, y0, y1);
-    ld2(Kslot(1), m, f, N, k0, k1v);
-    if (i == 1) {
-      a0 = fma(dp::a31, k0, dp::a32 * r0);
-      a1 = fma(dp::a31, k1v, dp::a32 * r1);
-    } else if (i == 2) {
-      double p0, p1;
-      ld2(Kslot(2), m, f, N, p0, p1);
-      a0 = fma(dp::a41, k0, fma(dp::a42, p0, dp::a43 * r0));
-      a1 = fma(dp::a41, k1v, fma(dp::a42, p1, dp::a43 * r1));
-    } else if (i == 3) {
-      double p0, p1, q0, q1;
-      ld2(Kslot(2), m, f, N, p0, p1);
-      ld2(Kslot(3), m, f, N, q0, q1);
-      a0 = fma(dp::a51, k0, fma(dp::a52, p0, fma(dp::a53, q0, dp::a54 * r0)));
-      a1 = fma(dp::a51, k1v, fma(dp::a52, p1, fma(dp::a53, q1, dp::a54 * r1)));
-    } else if (i == 4) {
-      double p0, p1, q0, q1, s0, s1;
-      ld2(Kslot(2), m, f, N, p0, p1);
-      ld2(Kslot(3), m, f, N, q0, q1);
-      ld2(Kslot(4), m, f, N, s0, s1);
-      a0 = fma(dp::a61, k0, fma(dp::a62, p0, fma(dp::a63, q0, fma(dp::a64, s0, dp::a65 * r0))));
-      a1 = fma(dp::a61, k1v, fma(dp::a62, p1, fma(dp::a63, q1, fma(dp::a64, s1, dp::a65 * r1))));
-    } else {
-      double q0, q1, s0, s1, u0, u1;
-      ld2(Kslot(3), m, f, N, q0, q1);
-      ld2(Kslot(4), m, f, N, s0, s1);
-      ld2(Kslot(5), m, f, N, u0, u1);
-      if (i == 5) {
-        a0 = fma(dp::b1, k0, fma(dp::b3, q0, fma(dp::b4, s0, fma(dp::b5, u0, dp::b6 * r0))));
-        a1 = fma(dp::b1, k1v, fma(dp::b3, q1, fma(dp::b4, s1, fma(dp::b5, u1, dp::b6 * r1))));
-      } else {  // i == 6: r = K7; error estimate of both cells
-        double v0, v1;
-        ld2(Kslot(6), m, f, N, v0, v1);
-        const double e0 = fma(dp::e1, k0, fma(dp::e3, q0, fma(dp::e4, s0, fma(dp::e5, u0, fma(dp::e6, v0, dp::e7 * r0)))));
-        const double e1 = fma(dp::e1, k1v, fma(dp::e3, q1, fma(dp::e4, s1, fma(dp::e5, u1, fma(dp::e6, v1, dp::e7 * r1)))));
-        const double s0c = fma(fmax(fabs(y0), fabs(cc[f][0])), A.opt.rtol, A.opt.atol);
-        const double s1c = fma(fmax(fabs(y1), fabs(cc[f][1])), A.opt.rtol, A.opt.atol);
-        const double z0 = (h * e0) * fm::rcp3(s0c), z1 = (h * e1) * fm::rcp3(s1c);
-        if (m.v0) part = fma(z0, z0, part);
-        if (m.v1) part = fma(z1, z1, part);
-        continue;
-      }
+  } else {
+    double* K7 = Kslot(7);
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      st2(K7, m, f, N, r[f][0], r[f][1]);
+      const double z0 = fma(kNew[6], r[f][0], acc[f][0]) * pre[f][0];
+      const double z1 = fma(kNew[6], r[f][1], acc[f][1]) * pre[f][1];
+      if (m.v0) part = fma(z0, z0, part);
+      if (m.v1) part = fma(z1, z1, part);
     }
-    st2(nxt, m, f, N, fma(h, a0, y0), fma(h, a1, y1));
-  }
-  if (i == 6) {
     // CTA-wide sum in a fixed order: xor butterfly per warp, then the warp sums in warp order
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);

@@ -8,9 +8,12 @@ and the same HDF5 output (`solutions` (5, N, n_t), `times`, `event_0..6`, parame
 attributes) under ../Results/<timestamp>/, but the time stepping runs on the B200:
 
   method == "RK45"   the persistent sm_100a kernel integrates the column on-chip
-                     (csrc/rk45_persistent.cu), SciPy RK45 semantics incl. t_eval dense output;
-  other methods      SciPy's solve_ivp drives `eq.fun_numba`, whose RHS is the CUDA kernel
-                     (one column per call) — same arguments upstream passes (:104-109).
+                     (csrc/rk45_persistent.cu), SciPy RK45 semantics incl. t_eval dense output and events;
+  method == "Radau"  (the reference's default, parameters.py:213) the batched implicit kernel
+                     (csrc/radau_batch.cu): SciPy Radau semantics, block-tridiagonal Newton solve;
+  other methods      (LSODA, BDF, ...) SciPy's solve_ivp drives `eq.fun_numba`, whose RHS is the CUDA
+                     kernel (one column per call) — same arguments upstream passes (:104-109).
+                     MARLPDE_SCIPY_STEPPER=1 forces this route for RK45/Radau as well.
 
 `integrate_equations_batch` is the sweep entry point: many parameter sets in one launch.
 """
@@ -80,6 +83,33 @@ def _gpu_rk45(eq, y0, solver_parms, t_eval, n_cells):
                            message=_MESSAGES.get(status, "unknown status"), t_reached=float(res.t[0]))
 
 
+def _gpu_radau(eq, y0, solver_parms, t_eval, n_cells):
+    """One column through the batched implicit integrator (csrc/radau_batch.cu): SciPy Radau semantics,
+    block-tridiagonal Newton solve.  `jac_sparsity` is accepted and ignored — the 5x5 block-tridiagonal
+    structure is intrinsic to the kernel (it is the exact structure the reference's pattern approximates)."""
+    known = {"first_step", "atol", "rtol", "t_span", "method", "dense_output", "max_step", "jac_sparsity"}
+    extra = set(solver_parms) - known
+    if extra:
+        raise TypeError(f"options not supported by the GPU Radau path: {sorted(extra)}")
+    if solver_parms.get("dense_output"):
+        raise NotImplementedError("dense_output=True (a callable OdeSolution) is not available on the GPU path; "
+                                  "use t_eval")
+    te = np.asarray(t_eval, dtype=np.float64) if t_eval is not None else np.array(solver_parms["t_span"], float)
+    res = _mb.integrate_radau_batch(y0.reshape(1, 5, n_cells), eq.column_params, t_span=solver_parms["t_span"],
+                                    first_step=solver_parms.get("first_step", 1e-6),
+                                    rtol=solver_parms.get("rtol", 1e-3), atol=solver_parms.get("atol", 1e-6),
+                                    max_step=solver_parms.get("max_step", np.inf), t_eval=te,
+                                    events=True, event_capacity=4096)
+    k = int(res.next_eval[0])
+    status = int(res.status[0])
+    t_events = [np.sort(res.event_times[0, e, :min(int(res.event_counts[0, e]), res.event_times.shape[2])])
+                for e in range(7)]
+    return SimpleNamespace(t=te[:k], y=res.solutions(0).reshape(5 * n_cells, k), t_events=t_events,
+                           nfev=int(res.nfev[0]), njev=int(res.njev[0]), nlu=int(res.nlu[0]), status=status,
+                           success=status >= 0, message=_MESSAGES.get(status, "unknown status"),
+                           t_reached=float(res.t[0]))
+
+
 def _store(store_folder, stored_parms, field_solutions, times, t_events):
     os.makedirs(store_folder)
     stored_results = store_folder + "LMAHeureuxPorosityDiff.hdf5"
@@ -106,9 +136,13 @@ def integrate_equations(solver_parms, tracker_parms, pde_parms):
 
     start_computing = time.time()
     progress = 0
-    if solver_parms["method"] == "RK45":
+    scipy_stepper = os.environ.get("MARLPDE_SCIPY_STEPPER", "0") == "1"    # SciPy steps, the GPU only evaluates the RHS
+    if solver_parms["method"] == "RK45" and not scipy_stepper:
         gpu_parms = {k: v for k, v in solver_parms.items() if k not in ("jac_sparsity", "lband", "uband")}
         sol = _gpu_rk45(eq, y0, gpu_parms, tracker_parms["t_eval"], n_cells)
+        progress = (sol.t_reached - t0) / (end_time - t0)
+    elif solver_parms["method"] == "Radau" and not scipy_stepper:
+        sol = _gpu_radau(eq, y0, solver_parms, tracker_parms["t_eval"], n_cells)
         progress = (sol.t_reached - t0) / (end_time - t0)
     else:
         from scipy.integrate import solve_ivp
@@ -161,15 +195,17 @@ def integrate_equations_batch(solver_parms, tracker_parms, pde_parms, store_fold
         pde_parms = {k: (np.array([p[k] for p in pde_parms]) if k != "N" else pde_parms[0]["N"]) for k in keys}
     solver_parms = dict(solver_parms)
     solver_parms.pop("backend", None)
-    if solver_parms.get("method", "RK45") != "RK45":
-        raise NotImplementedError("the batched on-device integrator implements method='RK45'")
+    method = solver_parms.get("method", "RK45")
+    if method not in ("RK45", "Radau"):
+        raise NotImplementedError("the batched on-device integrators implement method='RK45' and method='Radau'")
     params = _mb.derive_column_params(pde_parms)
     y0 = _mb.initial_state(pde_parms)
-    res = _mb.integrate_rk45_batch(y0, params, t_span=solver_parms.get("t_span", (0, 1)),
-                                   first_step=solver_parms.get("first_step", 1e-6),
-                                   rtol=solver_parms.get("rtol", 1e-3), atol=solver_parms.get("atol", 1e-3),
-                                   max_step=solver_parms.get("max_step", np.inf), t_eval=tracker_parms["t_eval"],
-                                   events=True, event_capacity=64, device=device)
+    integrate = _mb.integrate_rk45_batch if method == "RK45" else _mb.integrate_radau_batch
+    res = integrate(y0, params, t_span=solver_parms.get("t_span", (0, 1)),
+                    first_step=solver_parms.get("first_step", 1e-6),
+                    rtol=solver_parms.get("rtol", 1e-3), atol=solver_parms.get("atol", 1e-3),
+                    max_step=solver_parms.get("max_step", np.inf), t_eval=tracker_parms["t_eval"],
+                    events=True, event_capacity=64, device=device)
     if store_folder is not None:
         os.makedirs(store_folder, exist_ok=True)
         with hdf5lite.File(os.path.join(store_folder, "LMAHeureuxPorosityDiff_sweep.hdf5"), "w") as stored:

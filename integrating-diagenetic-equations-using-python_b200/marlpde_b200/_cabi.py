@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmarlpde_b200.so")
+LIB_PATH = os.environ.get("MARLPDE_B200_LIB") or os.path.join(_HERE, "libmarlpde_b200.so")
 
 NFIELDS = 5
 NEVENTS = 7
@@ -79,9 +79,9 @@ SYMBOLS = {
                                                     _P, _P, _P, C.c_size_t, _P]),
     "marlpde_radau_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "marlpde_radau_integrate_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(RK45Options),
-                                              _P, _P, _P, _P, C.c_size_t, _P, _P]),
+                                              _P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P]),
     "marlpde_radau_integrate": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(RK45Options),
-                                          _P, _P, _P, C.c_int]),
+                                          _P, _P, _P, _P, _P, C.c_int]),
     "marlpde_probe_math": (C.c_int, [C.c_int, _P, C.c_int, _P, C.c_int]),
     "marlpde_probe_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "marlpde_rk45_integrate": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(RK45Options),

@@ -78,7 +78,8 @@ class RK45Result:
     y: object                    # [B,5,N] state at the time reached
     t: np.ndarray                # [B] time reached
     h_abs: np.ndarray            # [B] next step size the controller would use
-    status: np.ndarray           # [B] 0 finished, -1 step too small, 1 step budget exhausted (resumable)
+    status: np.ndarray           # [B] 0 finished, -1 step too small, 1 (2: mid-step, streaming path) step budget
+                                 #     exhausted, resumable
     n_accepted: np.ndarray
     n_rejected: np.ndarray
     nfev: np.ndarray
@@ -215,8 +216,9 @@ def _stream_rk45_device(lib, y, d_params, st, opts, t_eval_arr, B, N, dev, cap, 
                 d_te.data_ptr() if n_eval else None, d_snap.data_ptr(), d_work.data_ptr(), nb, stream))
             used += int(o.max_steps)
             st_out = d_state.cpu().numpy().view(STATE_DTYPE).reshape(B)
-            if not np.any(st_out["status"] == 1) or (budget > 0 and used >= budget):
+            if not np.any(st_out["status"] >= 1) or (budget > 0 and used >= budget):
                 break
+            d_state = torch.from_numpy(st_out.view(np.uint8).copy()).to(dev)
     ec = np.zeros((B, NEVENTS), dtype=np.int32)
     et = np.full((B, NEVENTS, cap), np.nan)
     return RK45Result(y=y, t=st_out["t"].copy(), h_abs=st_out["h_abs"].copy(), status=st_out["status"].copy(),
@@ -242,6 +244,8 @@ class RadauResult:
     t_eval: np.ndarray
     snapshots: object            # [B,n_eval,5,N]
     next_eval: np.ndarray
+    event_counts: np.ndarray = None   # [B,7]
+    event_times: np.ndarray = None    # [B,7,capacity]
     state: np.ndarray = field(default=None, repr=False)
 
     def solutions(self, column: int) -> np.ndarray:
@@ -251,8 +255,8 @@ class RadauResult:
 
 
 def integrate_radau_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e-3, atol=1e-3, t_eval=None,
-                          max_step=np.inf, max_steps: int = 0, state: np.ndarray | None = None, device: int = 0,
-                          inplace: bool = False) -> RadauResult:
+                          max_step=np.inf, max_steps: int = 0, events: bool = False, event_capacity: int = 0,
+                          state: np.ndarray | None = None, device: int = 0, inplace: bool = False) -> RadauResult:
     """Implicit integration of every column: 3-stage Radau IIA with SciPy's step-size, Newton and
     Jacobian-reuse rules (`solve_ivp(method="Radau", jac_sparsity=jacobian_sparsity())`, the
     reference's default Solver, parameters.py:201-221) and a block-tridiagonal linear solver."""
@@ -275,8 +279,10 @@ def integrate_radau_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1
         if np.any(np.diff(t_eval_arr) <= 0):
             raise ValueError("Values in `t_eval` are not properly sorted.")
     n_eval = int(t_eval_arr.size)
+    cap = int(event_capacity) if events else 0
     opts = _cabi.RK45Options(t_bound=t_bound, rtol=float(rtol), atol=float(atol), max_step=float(max_step),
-                             max_steps=int(max_steps), n_eval=n_eval, event_capacity=0, flags=0, reserved=0)
+                             max_steps=int(max_steps), n_eval=n_eval, event_capacity=cap,
+                             flags=_cabi.FLAG_EVENTS if events else 0, reserved=0)
     if _is_torch(y0):
         import torch
         if not y0.is_cuda or y0.dtype != torch.float64 or not y0.is_contiguous():
@@ -294,15 +300,18 @@ def integrate_radau_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1
             d_snap = torch.empty((B, n_eval, 5, N), dtype=torch.float64, device=dev)
             d_queue = torch.zeros(1, dtype=torch.int32, device=dev)
             d_stats = torch.zeros((B, 4), dtype=torch.int64, device=dev)
+            d_ec = torch.zeros((B, NEVENTS), dtype=torch.int32, device=dev)
+            d_et = torch.full((B, NEVENTS, max(cap, 1)), float("nan"), dtype=torch.float64, device=dev)
             nb = int(lib.marlpde_radau_workspace_bytes(B, N))
             d_work = torch.empty(max(nb, 8) // 8, dtype=torch.float64, device=dev)
             stream = torch.cuda.current_stream().cuda_stream
             _cabi.check(lib.marlpde_radau_integrate_dev(
                 y.data_ptr(), d_params.data_ptr(), d_state.data_ptr(), B, N, C.byref(opts),
-                d_te.data_ptr() if n_eval else None, d_snap.data_ptr(), d_stats.data_ptr(), d_work.data_ptr(),
-                nb, d_queue.data_ptr(), stream))
+                d_te.data_ptr() if n_eval else None, d_snap.data_ptr(), d_ec.data_ptr(), d_et.data_ptr(),
+                d_stats.data_ptr(), d_work.data_ptr(), nb, d_queue.data_ptr(), stream))
             st_out = d_state.cpu().numpy().view(STATE_DTYPE).reshape(B)
             stats = d_stats.cpu().numpy()
+            ec, et = d_ec.cpu().numpy(), d_et.cpu().numpy()[:, :, :cap]
         snaps = d_snap
     else:
         p = _as_params(params)
@@ -313,12 +322,15 @@ def integrate_radau_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1
         st_out = make_state(B, t0, first_step) if state is None else np.array(state, dtype=STATE_DTYPE, copy=True)
         snaps = np.full((B, n_eval, 5, N), np.nan)
         stats = np.zeros((B, 4), dtype=np.int64)
+        ec = np.zeros((B, NEVENTS), dtype=np.int32)
+        et = np.full((B, NEVENTS, cap), np.nan)
         _cabi.check(lib.marlpde_radau_integrate(
             _cabi.ptr(y), _cabi.ptr(p), _cabi.ptr(st_out), B, N, C.byref(opts),
-            _cabi.ptr(t_eval_arr) if n_eval else None, _cabi.ptr(snaps) if n_eval else None, _cabi.ptr(stats),
-            device))
+            _cabi.ptr(t_eval_arr) if n_eval else None, _cabi.ptr(snaps) if n_eval else None, _cabi.ptr(ec),
+            _cabi.ptr(et) if cap else None, _cabi.ptr(stats), device))
     return RadauResult(y=y, t=st_out["t"].copy(), h_abs=st_out["h_abs"].copy(), status=st_out["status"].copy(),
                        n_accepted=st_out["n_accepted"].copy(), n_rejected=st_out["n_rejected"].copy(),
                        nfev=st_out["nfev"].copy(), njev=stats[:, 0].copy(), nlu=stats[:, 1].copy(),
                        newton_iterations=stats[:, 2].copy(), newton_failures=stats[:, 3].copy(),
-                       t_eval=t_eval_arr, snapshots=snaps, next_eval=st_out["next_eval"].copy(), state=st_out)
+                       t_eval=t_eval_arr, snapshots=snaps, next_eval=st_out["next_eval"].copy(), event_counts=ec,
+                       event_times=et, state=st_out)

@@ -28,3 +28,8 @@ for base_name, base in (("scenario_A", pde | {"Phi0": 0.6, "PhiIni": 0.5, "PhiNR
     torch.cuda.synchronize(); dt = time.time() - t0
     print(base_name, "64 columns to T*:", f"{dt:.2f}s", "status", np.unique(rr.status, return_counts=True), "steps", rr.n_accepted.min(), rr.n_accepted.max(),
           "nlu", rr.nlu.min(), rr.nlu.max(), "newton", rr.newton_iterations.max())
+# event times, scenario A to T*
+pa = pde | {"Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}
+ra = mb.integrate_radau_batch(mb.initial_state(pa), mb.derive_column_params(pa), t_span=(0, 1), first_step=1e-6, events=True, event_capacity=8)
+sa = oracle.integrate(pa, method="Radau", t_span=(0, 1), t_eval=[0, 1], events=True, jac_sparsity=sp)
+print("gpu events", ra.event_counts[0], ra.event_times[0, 0], ra.event_times[0, 1]); print("scipy events", [list(e) for e in sa.t_events])

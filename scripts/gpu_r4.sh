@@ -1,0 +1,8 @@
+#!/bin/bash
+set -u
+OUT=gpurun_out/${1:-r4}
+mkdir -p $OUT
+PT="python -m pytest -q -m gpu -p no:cacheprovider --timeout=300 --timeout-method=thread"
+( time timeout 1500 $PT tests ) > $OUT/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> $OUT/pytest_gpu.log
+echo done

@@ -98,3 +98,26 @@ def test_grid_sizes_budget_and_device_path():
     dev = mb.integrate_radau_batch(torch.from_numpy(y0).cuda(), P, t_span=(0, 1), first_step=1e-6)
     assert np.array_equal(dev.y.cpu().numpy(), whole.y)
     assert mb.integrate_radau_batch(y0[:0], P[:0]).y.shape == (0, 5, 200)
+
+
+def test_radau_events_match_scipy():
+    """Event monitors on the implicit path: same monitors, same sign-change rule, Brent on the cubic dense
+    output.  Default Map_Scenario: the porosity crosses 1 near t = 0.027 (event 4) and max W changes sign
+    right after (event 6) — crossings of the solution, not of round-off, so their first occurrence must
+    agree with SciPy Radau to the accuracy of two rtol = 1e-3 trajectories.  (Scenario A's events 0/1 are not
+    used here: CA decays to 1e-17 and the sign of min(CA) is noise — SciPy reports 0.2488 at rtol 1e-3 and
+    0.2939 at 1e-8.)"""
+    pde = oracle.default_scenario()
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    res = mb.integrate_radau_batch(y0, P, t_span=(0, 0.05), first_step=5e-7, t_eval=[0, 0.05], events=True,
+                                   event_capacity=64)
+    sol = oracle.integrate(pde, method="Radau", t_span=(0, 0.05), t_eval=[0, 0.05], events=True, first_step=5e-7,
+                           jac_sparsity=oracle.jacobian_sparsity(200))
+    got = [np.sort(res.event_times[0, k, :min(int(res.event_counts[0, k]), 64)]) for k in range(7)]
+    for k in (0, 1, 2, 3, 5):
+        assert res.event_counts[0, k] == 0 == len(sol.t_events[k])
+    assert len(sol.t_events[4]) >= 1 and len(got[4]) >= 1 and abs(got[4][0] - sol.t_events[4][0]) <= 5e-4
+    assert len(sol.t_events[6]) >= 1 and len(got[6]) >= 1 and abs(got[6][0] - sol.t_events[6][0]) <= 1e-3
+    assert np.all(np.diff(got[6]) > 0) and np.all((got[6] > 0) & (got[6] <= 0.05))
+    plain = mb.integrate_radau_batch(y0, P, t_span=(0, 0.05), first_step=5e-7)
+    assert np.array_equal(plain.y, res.y)                              # monitoring does not change the trajectory

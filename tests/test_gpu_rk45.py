@@ -243,3 +243,42 @@ def test_events_survive_resume():
     assert part.status[0] == 0 and np.array_equal(part.y, whole.y)
     for k in range(7):
         assert np.array_equal(np.asarray(times[k]), _event_lists(whole, 0)[k])
+
+
+# ---- depth grids that do not fit on chip: the streaming path (csrc/rk45_streaming.cu) ---------------
+@pytest.mark.parametrize("n_cells,ncol", [(2000, 3), (5000, 1), (641, 2), (16, 2)])
+def test_streaming_path_matches_scipy(n_cells, ncol):
+    """BASELINE.json configs[3]: fixed budget of ~2000 steps, t_end and
+    first_step scaled with (200/N)^2 (the explicit step is stability bound), state at t_end against SciPy
+    RK45 on the oracle.  Same stepper semantics as the on-chip kernel: nfev within two attempts."""
+    pde = oracle.default_scenario() | {"N": n_cells, "Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}
+    scale = min(1.0, (200 / n_cells) ** 2)
+    t_end, fs = 600 * 2.6e-6 * scale, 1e-6 * scale
+    te = [0.0, 0.4 * t_end, t_end]
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    res = mb.integrate_rk45_batch(np.repeat(y0, ncol, 0), np.repeat(P, ncol), t_span=(0, t_end), first_step=fs, t_eval=te)
+    sol = oracle.integrate(pde, method="RK45", t_span=(0, t_end), t_eval=te, events=False, first_step=fs)
+    assert np.all(res.status == 0) and np.all(res.t == t_end) and np.all(res.next_eval == 3)
+    assert np.all(np.abs(res.nfev - sol.nfev) <= 12), (res.nfev, sol.nfev)
+    want = sol.y.reshape(5, n_cells, -1)
+    for c in range(ncol):
+        assert_allclose(res.solutions(c), want, rtol=0, atol=1e-9)
+        assert_allclose(res.y[c], want[:, :, -1], rtol=0, atol=1e-9)
+    assert np.array_equal(res.y[0], res.y[-1])
+
+
+def test_streaming_path_resume_device_tensors_and_budget():
+    import torch
+    n_cells = 1000
+    pde = oracle.default_scenario() | {"N": n_cells, "Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    t_end, fs = 700 * 2.6e-6 / 25, 1e-6 / 25
+    whole = mb.integrate_rk45_batch(y0, P, t_span=(0, t_end), first_step=fs, t_eval=[0, t_end])
+    assert whole.status[0] == 0
+    part = mb.integrate_rk45_batch(y0, P, t_span=(0, t_end), first_step=fs, max_steps=300)
+    assert part.status[0] in (1, 2) and part.n_attempts[0] == 300 and 0 < part.t[0] < t_end
+    rest = mb.integrate_rk45_batch(part.y, P, t_span=(0, t_end), state=part.state)
+    assert rest.status[0] == 0 and rest.n_attempts[0] == whole.n_attempts[0]
+    assert_allclose(rest.y, whole.y, rtol=0, atol=1e-12)             # K1 is re-evaluated on resume: same bits expected
+    dev = mb.integrate_rk45_batch(torch.from_numpy(y0).cuda(), P, t_span=(0, t_end), first_step=fs, t_eval=[0, t_end])
+    assert np.array_equal(dev.y.cpu().numpy(), whole.y) and np.array_equal(dev.snapshots.cpu().numpy(), whole.snapshots)

@@ -162,7 +162,7 @@ def run_reference_arm(args, rank: int, world: int):
 def workload_config(args, world: int) -> dict:
     lat = lattice_for(world)
     per_gpu = 4096 if world == 1 else 8192
-    return {"workload": (f"{per_gpu * world}-column Map_Scenario sweep ({lat[0]}x{lat[1]}x{lat[2]} lattice over "
+    return {"workload": (f"{per_gpu * world}-column Map_Scenario sweep ({'every %d-th column of the ' % (8 // world) if 1 < world < 8 else ''}{lat[0]}x{lat[1]}x{lat[2]} lattice over "
                          f"sedimentationrate, b, D0co3; {args.base} base), N=200, RK45 rtol=atol=1e-3, "
                          f"first_step=1e-6; {args.attempts} step attempts per column per bench step, resumed"),
             "columns": per_gpu * world, "columns_per_gpu": per_gpu, "n_cells": 200,
@@ -188,6 +188,13 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
 
     lat = lattice_for(world)
     pde = mb.sweep_lattice(scenario_base(args.base), *lat)
+    if world > 1:
+        # weak scaling: 8192 columns per GPU, taken as every (8/world)-th column of the 65,536-column lattice
+        # so that every world size covers the full parameter ranges (world = 8: the whole lattice)
+        n_all = lat[0] * lat[1] * lat[2]
+        stride = max(1, n_all // (8192 * world))
+        sel = np.arange(0, n_all, stride)[: 8192 * world]
+        pde = {k: (np.asarray(v)[sel] if (k != "N" and np.ndim(v) == 1) else v) for k, v in pde.items()}
     P_all = mb.derive_column_params(pde)
     y_all = mb.initial_state(pde)
     from marlpde_b200 import sweep
@@ -357,7 +364,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                                  "steps_per_column_min_max": [int((st2["n_accepted"] + st2["n_rejected"]).min()),
                                                               int((st2["n_accepted"] + st2["n_rejected"]).max())]}
 
-    if args.full:
+    if args.full and world == 1:
         # ---- implicit path (BASELINE.json configs[4]): the same sweep to T* with the batched Radau IIA kernel
         implicit = {}
         for base_name in ("scenario_A", "default"):

@@ -131,6 +131,7 @@ template <class Load, class Sink>
 __device__ __forceinline__ void rhs_column(const ColumnConsts& kc, const fm::Tables& tb, int N, int lane, Load&& ld,
                                            Sink&& sink) {
   const int Hc = (N + 1) >> 1;
+#pragma unroll 1
   for (int base = 0; base < Hc; base += 32) {
     const int p = base + lane;
     const int cell0 = 2 * p;
@@ -168,13 +169,37 @@ __device__ __forceinline__ void rhs_column(const ColumnConsts& kc, const fm::Tab
   }
 }
 
-// out = rhs(yy + add) (add may be NULL), field-major [5][N]
+// finite-difference step of num_jac (scipy/integrate/_ivp/common.py): h = (y + factor*y_scale) - y,
+// y_scale = sign(f) * max(threshold, |y|), factor = sqrt(eps) (not adapted here), threshold = atol
+__device__ __forceinline__ double fd_step(double y, double f, double atol) {
+  const double ys = (f >= 0.0 ? 1.0 : -1.0) * fmax(atol, fabs(y));
+  return (y + kSqrtEps * ys) - y;
+}
+
+// THE one instance of the RHS in this kernel (instruction-cache footprint matters: 16 warps per SM sit
+// in different phases of their columns).  Two uses:
+//   fld < 0 : out = rhs(yy + add)                      (add may be NULL), field-major [5][N]
+//   fld >= 0: finite-difference Jacobian colour (c3, fld): yy is the state with field fld of every cell
+//             i = c3 (mod 3) perturbed by fd_step; cell i' reads off d f(i') / d y(fld, j) for the one
+//             perturbed cell j in {i'-1, i', i'+1} and stores it as column fld of its L, D or U block
+//             in `out` (= J); y0/f0 are the unperturbed state and its RHS
 __device__ __noinline__ void rhs_eval(const ColumnConsts* kc, const fm::Tables* tb, int N, int lane, const double* yy,
-                                      const double* add, double* out) {
-  auto ld = [&](int f, int i) -> double { return add ? yy[f * N + i] + add[f * N + i] : yy[f * N + i]; };
+                                      const double* add, double* out, int fld, int c3, const double* y0,
+                                      const double* f0, double atol) {
+  auto ld = [&](int ff, int i) -> double { return add ? yy[ff * N + i] + add[ff * N + i] : yy[ff * N + i]; };
   auto sink = [&](int i, const double (&r5)[5]) {
+    if (fld < 0) {
 #pragma unroll
-    for (int f = 0; f < 5; ++f) out[f * N + i] = r5[f];
+      for (int f = 0; f < 5; ++f) out[f * N + i] = r5[f];
+      return;
+    }
+    const int d = ((c3 - (i % 3)) + 3) % 3;           // 0: j = i, 1: j = i+1, 2: j = i-1
+    const int j = i + (d == 2 ? -1 : d);
+    if (j < 0 || j >= N) return;
+    const double inv = 1.0 / fd_step(y0[fld * N + j], f0[fld * N + j], atol);
+    double* blk = out + (size_t)i * 75 + (d == 0 ? 25 : (d == 1 ? 50 : 0));
+#pragma unroll
+    for (int r = 0; r < 5; ++r) blk[r * 5 + fld] = (r5[r] - f0[r * N + i]) * inv;
   };
   rhs_column(*kc, *tb, N, lane, ld, sink);
   __syncwarp();
@@ -186,40 +211,31 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// finite-difference step of num_jac (scipy/integrate/_ivp/common.py): h = (y + factor*y_scale) - y,
-// y_scale = sign(f) * max(threshold, |y|), factor = sqrt(eps) (not adapted here), threshold = atol
-__device__ __forceinline__ double fd_step(double y, double f, double atol) {
-  const double ys = (f >= 0.0 ? 1.0 : -1.0) * fmax(atol, fabs(y));
-  return (y + kSqrtEps * ys) - y;
-}
-
-// J = d rhs / d y by 15 finite-difference evaluations: colour (c3, fld) perturbs field fld in every
-// cell i = c3 (mod 3); cell i' then reads off d f(i') / d y(fld, j) for the one perturbed cell j in
-// {i'-1, i', i'+1} and stores it as column fld of its L, D or U block.
+// J = d rhs / d y by 15 finite-difference evaluations (3 cell classes x 5 fields); `pert` is scratch [5N]
 __device__ __noinline__ void fd_jacobian(const ColumnConsts& kc, const fm::Tables& tb, int N, int lane, const double* y,
-                            const double* f, double atol, double* J) {
+                                         const double* f, double atol, double* J, double* pert) {
+  const int n = 5 * N;
+#pragma unroll 1
   for (int i = lane; i < 75 * N; i += 32) J[i] = 0.0;     // L_0 and U_{N-1} stay zero
+#pragma unroll 1
+  for (int idx = lane; idx < n; idx += 32) pert[idx] = y[idx];
   __syncwarp();
+#pragma unroll 1
   for (int c3 = 0; c3 < 3; ++c3) {
+#pragma unroll 1
     for (int fld = 0; fld < 5; ++fld) {
-      auto ld = [&](int ff, int i) -> double {
-        const double v = y[ff * N + i];
-        return (ff == fld && (i % 3) == c3) ? v + fd_step(v, f[ff * N + i], atol) : v;
-      };
-      auto sink = [&](int i, const double (&r5)[5]) {
-        const int d = ((c3 - (i % 3)) + 3) % 3;           // 0: j = i, 1: j = i+1, 2: j = i-1
-        const int j = i + (d == 2 ? -1 : d);
-        if (j < 0 || j >= N) return;
-        const double hstep = fd_step(y[fld * N + j], f[fld * N + j], atol);
-        const double inv = 1.0 / hstep;
-        double* blk = J + (size_t)i * 75 + (d == 0 ? 25 : (d == 1 ? 50 : 0));
-#pragma unroll
-        for (int r = 0; r < 5; ++r) blk[r * 5 + fld] = (r5[r] - f[r * N + i]) * inv;
-      };
-      rhs_column(kc, tb, N, lane, ld, sink);
+#pragma unroll 1
+      for (int i = c3 + 3 * lane; i < N; i += 96) {
+        const double v = y[fld * N + i];
+        pert[fld * N + i] = v + fd_step(v, f[fld * N + i], atol);
+      }
+      __syncwarp();
+      rhs_eval(&kc, &tb, N, lane, pert, nullptr, J, fld, c3, y, f, atol);
+#pragma unroll 1
+      for (int i = c3 + 3 * lane; i < N; i += 96) pert[fld * N + i] = y[fld * N + i];
+      __syncwarp();
     }
   }
-  __syncwarp();
 }
 
 // Block-Thomas factorisation of (M I - J) for both systems at once.
@@ -252,6 +268,7 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
   double2 xcol[5];                                          // column c5 of X_{i-1} = S_{i-1}^{-1} U_{i-1}
 #pragma unroll
   for (int r = 0; r < 5; ++r) xcol[r] = make_double2(0.0, 0.0);
+#pragma unroll 1
   for (int i = 0; i < N; ++i) {
     request(i + kDepth);                  // slot (i + kDepth) % kSlots was released at the end of iteration i-1
     cp_async_wait<kDepth>();              // all but the kDepth newest groups have landed: cell i is in shared memory
@@ -273,9 +290,8 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
     }
     // ---- Gauss-Jordan on [S | I] with partial pivoting; rows are never swapped physically:
     //      perm[k] = row that served as pivot of column k
-    unsigned used = 0;
-    int perm[5];
-#pragma unroll
+    unsigned used = 0, perm = 0;                             // perm: 4 bits per pivot column
+#pragma unroll 1
     for (int k = 0; k < 5; ++k) {
       if (valid && apart && c5 == k) {                     // the lane holding column k of S picks the pivot
         int p = 0;
@@ -298,7 +314,7 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
       }
       __syncwarp();
       const int p = (int)ws.mult[s][5].x;
-      perm[k] = p;
+      perm |= (unsigned)p << (4 * k);
       used |= 1u << p;
       if (valid) {
         double2 piv = col[0];
@@ -312,13 +328,14 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
       }
       __syncwarp();
     }
-    // ---- identity-part lanes now hold column c5 of Pi S^{-1}: S^{-1}[k][c5] = col[perm[k]]
+    // ---- identity-part lanes now hold column c5 of Pi S^{-1}: S^{-1}[k][c5] = col[perm_k]
     if (valid && !apart) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
+        const int pk = (perm >> (4 * k)) & 15;
         double2 v = col[0];
 #pragma unroll
-        for (int r = 1; r < 5; ++r) v = (perm[k] == r) ? col[r] : v;
+        for (int r = 1; r < 5; ++r) v = (pk == r) ? col[r] : v;
         ws.sinv_prev[s][k * 5 + c5] = v;
         out[(size_t)i * 25 + k * 5 + c5] = v;
       }
@@ -377,6 +394,7 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
   // ---- forward: g_i = b_i + L_i p_{i-1},  p_i = S_i^{-1} g_i  (p overwrites b)
   double2 p = make_double2(0.0, 0.0);
   double2 bnext = valid ? make_double2(bre[r * N], bim ? bim[r * N] : 0.0) : make_double2(0.0, 0.0);
+#pragma unroll 1
   for (int i = 0; i < N; ++i) {
     request(i + kDepth, 0, (i + kDepth) % kSlots, i + kDepth < N);
     cp_async_wait<kDepth>();
@@ -412,6 +430,7 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
   for (int c0 = 0; c0 < kDepth; ++c0) request(N - 2 - c0, 50, c0 % kSlots, N - 2 - c0 >= 0);
   double2 x = p;
   bnext = valid ? make_double2(bre[r * N + N - 2], bim ? bim[r * N + N - 2] : 0.0) : make_double2(0.0, 0.0);
+#pragma unroll 1
   for (int i = N - 2, j = 0; i >= 0; --i, ++j) {
     request(i - kDepth, 50, (j + kDepth) % kSlots, i - kDepth >= 0);
     cp_async_wait<kDepth>();
@@ -448,12 +467,18 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
 // The seven event monitors (LHeureux_model.py:524-593) of the state val(f, i), by one warp:
 // g = {min y, min CA, min CC, max(CA+CC)-1, max Phi - 1, min U(Phi), max W(Phi)}.  NaNs propagate like
 // np.amin / np.amax.  U and W use the arithmetic of rhs_pair.
-template <class Val>
-__device__ __forceinline__ void monitors(const ColumnConsts& kc, const fm::Tables& tb, int N, int lane, Val&& val,
-                                         double (&g)[7]) {
+// State = y0[idx] (q == NULL) or the dense output y0[idx] + x (q0 + x (q1 + x q2)) with q = Q [3][n].
+__device__ __noinline__ void monitors(const ColumnConsts& kc, const fm::Tables& tb, int N, int lane, const double* y0,
+                                      const double* q, double x, double* g) {
+  const int n = 5 * N;
+  auto val = [&](int f, int i) -> double {
+    const int idx = f * N + i;
+    return q ? y0[idx] + x * (q[idx] + x * (q[n + idx] + x * q[2 * n + idx])) : y0[idx];
+  };
   const double inf = (double)INFINITY;
   double m[7] = {inf, inf, inf, -inf, -inf, inf, -inf};
   bool nan5 = false, nanS = false, nanPhi = false, nanCA = false, nanCC = false;
+#pragma unroll 1
   for (int i = lane; i < N; i += 32) {
     const double CA = val(0, i), CC = val(1, i), cCa = val(2, i), cCO3 = val(3, i), Phi = val(4, i);
     nanCA |= CA != CA;
@@ -497,8 +522,8 @@ __device__ __forceinline__ void monitors(const ColumnConsts& kc, const fm::Table
 __device__ __forceinline__ double predict_factor(double h_abs, double h_abs_old, double err, double err_old) {
   // radau.py predict_factor; "None" is encoded as a negative value
   double mult = 1.0;
-  if (!(err_old < 0.0 || h_abs_old < 0.0 || err == 0.0)) mult = h_abs / h_abs_old * pow(err_old / err, 0.25);
-  return fmin(1.0, mult) * pow(err, -0.25);     // err == 0 -> inf, as numpy with divide='ignore'
+  if (!(err_old < 0.0 || h_abs_old < 0.0 || err == 0.0)) mult = h_abs / h_abs_old * sqrt(sqrt(err_old / err));
+  return fmin(1.0, mult) / sqrt(sqrt(err));      // x**0.25 as two square roots; err == 0 -> inf, as numpy
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) radau_kernel(const Args A) {
@@ -544,20 +569,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
     long long steps_done = 0;
 
     auto eval_to = [&](const double* yy, const double* add, double* out) {   // out = rhs(yy + add)
-      rhs_eval(&kc, &tb, N, lane, yy, add, out);
+      rhs_eval(&kc, &tb, N, lane, yy, add, out, -1, 0, nullptr, nullptr, 0.0);
     };
 
     if (t < A.opt.t_bound) {
       eval_to(y, nullptr, w.f);
       nfev += 1;
-      fd_jacobian(kc, tb, N, lane, y, w.f, atol, w.J);
+      fd_jacobian(kc, tb, N, lane, y, w.f, atol, w.J, w.B);
       njev += 1;
       nfev += 15;
     }
     const bool ev_on = (A.opt.flags & MARLPDE_FLAG_EVENTS) != 0;
     double g_old[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (ev_on && t < A.opt.t_bound)                        // ivp.py: g = [event(t0, y0) for event in events]
-      monitors(kc, tb, N, lane, [&](int f, int i) { return y[f * N + i]; }, g_old);
+      monitors(kc, tb, N, lane, y, nullptr, 0.0, g_old);
     bool current_jac = true, lu_valid = false, have_sol = false;
     double h_abs_old = -1.0, err_old = -1.0;     // "None"
     double t_old = t, h_old = 0.0;
@@ -568,7 +593,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
         break;
       }
       // ------------------------------------------------------------------ radau.py _step_impl
-      const double min_step = 10.0 * fabs(nextafter(t, (double)INFINITY) - t);
+      // 10 * |nextafter(t, inf) - t| for t >= 0 (forward integration from t0 >= 0 is validated on the host)
+      const double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);
       double h_abs = h_attr, hao = h_abs_old, eo = err_old;
       if (h_attr > A.opt.max_step) {
         h_abs = A.opt.max_step;
@@ -601,7 +627,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
             lu_valid = true;
           }
           // ---- Z0 from the previous step's dense output (radau.py: Z0 = sol(t + h C).T - y), W = TI Z0
-          for (int idx = lane; idx < n; idx += 32) {
+          _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
             double z[3] = {0.0, 0.0, 0.0};
             if (have_sol) {
               const double q0 = w.Q[idx], q1 = w.Q[n + idx], q2 = w.Q[2 * n + idx];
@@ -631,7 +657,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
             eval_to(y, w.Z + 2 * n, w.B + 2 * n);
             nfev += 3;
             bool finite = true;
-            for (int idx = lane; idx < n; idx += 32) {
+            _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
               const double F0 = w.B[idx], F1 = w.B[n + idx], F2 = w.B[2 * n + idx];
               finite = finite && isfinite(F0) && isfinite(F1) && isfinite(F2);
               const double W0 = w.W[idx], W1 = w.W[n + idx], W2 = w.W[2 * n + idx];
@@ -644,16 +670,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
             if (!__all_sync(0xffffffffu, finite)) break;
             solve(ws, N, lane, w.J, w.Sinv, w.B, w.B + n, w.B + 2 * n, true);
             double ss = 0.0;
-            for (int idx = lane; idx < n; idx += 32) {
+            _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
               const double sc = fma(fabs(y[idx]), rtol, atol);
               const double a0 = w.B[idx] / sc, a1 = w.B[n + idx] / sc, a2 = w.B[2 * n + idx] / sc;
               ss += a0 * a0 + a1 * a1 + a2 * a2;
             }
             const double dW_norm = sqrt(warp_sum(ss) / (double)(3 * n));
             if (dW_norm_old >= 0.0) rate = dW_norm / dW_norm_old;
-            if (rate >= 0.0 && (rate >= 1.0 || pow(rate, (double)(kNewtonMaxIter - k)) / (1.0 - rate) * dW_norm > newton_tol))
-              break;
-            for (int idx = lane; idx < n; idx += 32) {
+            double rate_pow = rate;                     // rate ** (NEWTON_MAXITER - k)
+            for (int e = 1; e < kNewtonMaxIter - k; ++e) rate_pow *= rate;
+            if (rate >= 0.0 && (rate >= 1.0 || rate_pow / (1.0 - rate) * dW_norm > newton_tol)) break;
+            _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
               const double W0 = w.W[idx] + w.B[idx], W1 = w.W[n + idx] + w.B[n + idx],
                            W2 = w.W[2 * n + idx] + w.B[2 * n + idx];
               w.W[idx] = W0;
@@ -674,7 +701,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
           if (converged) break;
           n_newton_fail += 1;
           if (current_jac) break;
-          fd_jacobian(kc, tb, N, lane, y, w.f, atol, w.J);
+          fd_jacobian(kc, tb, N, lane, y, w.f, atol, w.J, w.B);
           njev += 1;
           nfev += 15;
           current_jac = true;
@@ -686,7 +713,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
           continue;
         }
         // ---- error estimate: error = LU_real.solve(f + Z^T E / h)
-        for (int idx = lane; idx < n; idx += 32) {
+        _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
           const double ze = (w.Z[idx] * kE[0] + w.Z[n + idx] * kE[1] + w.Z[2 * n + idx] * kE[2]) / h;
           w.tmp[idx] = ze;
           w.err[idx] = w.f[idx] + ze;
@@ -695,7 +722,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
         solve(ws, N, lane, w.J, w.Sinv, w.err, nullptr, nullptr, false);
         auto err_norm_of = [&]() {
           double ss = 0.0;
-          for (int idx = lane; idx < n; idx += 32) {
+          _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
             const double yn = y[idx] + w.Z[2 * n + idx];
             const double sc = fma(fmax(fabs(y[idx]), fabs(yn)), rtol, atol);
             const double a = w.err[idx] / sc;
@@ -709,7 +736,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
           // error = LU_real.solve(fun(t, y + error) + ZE)
           eval_to(y, w.err, w.B);
           nfev += 1;
-          for (int idx = lane; idx < n; idx += 32) w.err[idx] = w.B[idx] + w.tmp[idx];
+          _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) w.err[idx] = w.B[idx] + w.tmp[idx];
           __syncwarp();
           solve(ws, N, lane, w.J, w.Sinv, w.err, nullptr, nullptr, false);
           error_norm = err_norm_of();
@@ -734,7 +761,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
       if (!recompute_jac && factor < 1.2) factor = 1.0;
       else lu_valid = false;
       // y_old <- y, y <- y + Z[2], Q = Z^T P (dense output of this step)
-      for (int idx = lane; idx < n; idx += 32) {
+      _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
         const double z0 = w.Z[idx], z1 = w.Z[n + idx], z2 = w.Z[2 * n + idx];
         const double yo = y[idx];
         w.yold[idx] = yo;
@@ -746,7 +773,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
       eval_to(y, nullptr, w.f);
       nfev += 1;
       if (recompute_jac) {
-        fd_jacobian(kc, tb, N, lane, y, w.f, atol, w.J);
+        fd_jacobian(kc, tb, N, lane, y, w.f, atol, w.J, w.B);
         njev += 1;
         nfev += 15;
         current_jac = true;
@@ -765,7 +792,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
       // ---- events (ivp.py main loop: after every accepted step, before the t_eval samples)
       if (ev_on) {
         double g_new[7];
-        monitors(kc, tb, N, lane, [&](int f, int i) { return y[f * N + i]; }, g_new);
+        monitors(kc, tb, N, lane, y, nullptr, 0.0, g_new);
 #pragma unroll 1
         for (int k = 0; k < 7; ++k) {
           if (!event_active(g_old[k], g_new[k])) continue;
@@ -776,12 +803,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
           for (;;) {
             const double xx = (xeval - t_old) / h_old;
             double gv[7];
-            monitors(kc, tb, N, lane,
-                     [&](int f, int i) {
-                       const int idx = f * N + i;
-                       return w.yold[idx] + xx * (w.Q[idx] + xx * (w.Q[n + idx] + xx * w.Q[2 * n + idx]));
-                     },
-                     gv);
+            monitors(kc, tb, N, lane, w.yold, w.Q, xx, gv);
             double gk = gv[0];
 #pragma unroll
             for (int kk = 1; kk < 7; ++kk) gk = (k == kk) ? gv[kk] : gk;
@@ -804,7 +826,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
         if (!(te <= t)) break;
         const double xx = (te - t_old) / h_old;
         double* snap = A.g_snap + ((size_t)col * A.opt.n_eval + next_eval) * n;
-        for (int idx = lane; idx < n; idx += 32)
+        _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32)
           snap[idx] = w.yold[idx] + xx * (w.Q[idx] + xx * (w.Q[n + idx] + xx * w.Q[2 * n + idx]));
         ++next_eval;
       }

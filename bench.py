@@ -415,12 +415,20 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             l1.record(stream)
             torch.cuda.synchronize()
             secs = l0.elapsed_time(l1) * 1e-3
-            alg_bytes = 1680.0 * nL * bL * attL                    # 42 vector passes x 40 B per cell and attempt
+            tiles_mode = os.environ.get("MARLPDE_RK45_STREAM", "tiles")[0] != "s"
+            # algorithmic HBM bytes per cell and attempt: overlapped tiles read y, K1 and write y_new, K7, the
+            # commit copies y_new -> y (6 vector passes x 40 B); one launch per stage moves 42 passes
+            per_cell = 240.0 if tiles_mode else 1680.0
+            alg_bytes = per_cell * nL * bL * attL
+            flops = FLOP_PER_COLUMN_STEP_PER_CELL * float(nL) * bL * attL
             large[f"N{nL}_B{bL}"] = {"n_cells": nL, "columns": bL, "attempts_per_column": attL, "seconds": secs,
+                                     "mode": "overlapped tiles (1 launch per attempt)" if tiles_mode else "1 launch per stage",
                                      "column_steps_per_s": bL * attL / secs, "cell_steps_per_s": bL * attL * nL / secs,
                                      "algorithmic_GBps": alg_bytes / secs / 1e9,
                                      "frac_of_hbm_peak": alg_bytes / secs / 1e9 / 6550.4,
-                                     "working_set_MB": nb / 1e6, "launches": 7 * attL + 4}
+                                     "algorithmic_TFLOPs": flops / secs / 1e12,
+                                     "frac_of_fp64_peak": flops / secs / 1e12 / peak.value if peak.value else None,
+                                     "working_set_MB": nb / 1e6, "launches": (2 if tiles_mode else 7) * attL + 4}
             del yL, d_wL
         line["large_n_streaming"] = large
 

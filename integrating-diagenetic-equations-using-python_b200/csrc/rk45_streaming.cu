@@ -20,9 +20,14 @@
 //     (DESIGN.md §4.4); the L2 keeps working sets up to ~100 MB on chip.
 // A call enqueues a fixed number of step attempts (no host round trip, no synchronisation); columns
 // that reach t_bound earlier idle, columns that do not come back resumable with status STEP_BUDGET.
+//
+// Default since r01c: the six stage launches of an attempt are replaced by ONE launch of
+// tile_attempt_kernel (overlapped 640-cell windows integrated on chip, see below); the per-stage
+// kernels remain as the HBM-streaming variant (MARLPDE_RK45_STREAM=stages) and for K1 = f(y).
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "dopri.cuh"
 #include "lheureux_device.cuh"
@@ -57,6 +62,7 @@ struct Args {
   double* partials;          // [B][tiles]
   Ctl* ctl;                  // [2][B]
   int B, N, tiles;
+  int tiles2;                // overlapped-tile path: attempt tiles per column (0: one launch per stage)
   marlpde_rk45_options opt;
 };
 
@@ -195,8 +201,9 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin
   if (!c.fresh) {
     // ---- error norm of the attempt that just ran: per-CTA partial sums, fixed order
     double sum = 0.0;
-    const double* part = A.partials + (size_t)m.col * A.tiles;
-    for (int i = 0; i < A.tiles; ++i) sum += part[i];
+    const int n_part = A.tiles2 > 0 ? A.tiles2 : A.tiles;
+    const double* part = A.partials + (size_t)m.col * n_part;
+    for (int i = 0; i < n_part; ++i) sum += part[i];
     const double err_norm = sqrt(sum / (double)(5 * N));
     c.nfev += 6;
     c.attempts += 1;
@@ -286,7 +293,7 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin
       c.status = MARLPDE_STATUS_STEP_TOO_SMALL;
     }
   }
-  if (c.active) {
+  if (c.active && A.tiles2 == 0) {
     // stage-2 input: y + h a21 K1 (for an accepted step y was just rewritten by this very thread)
     const double ha = c.h * dp::a21;
 #pragma unroll
@@ -438,6 +445,236 @@ __global__ void __launch_bounds__(kThreads, 3) stage_kernel(const Args A, int i,
   }
 }
 
+
+// =================================================================================================
+// Overlapped tiles: ONE launch per step attempt.  A 320-thread CTA integrates a 640-cell window of a
+// long column through all six stages and the FSAL evaluation ON CHIP, exactly like a slot of the
+// persistent kernel (y, K1, stage input and stage derivative in registers, K2..K5 and the halo
+// exchange tile in shared memory).  Neighbouring windows overlap by 2 x 6 cells: a stage evaluation
+// invalidates one more cell at each window edge (its neighbour lies outside the window), so after
+// K2..K7 the inner 628 cells are exact and only those are written back.  HBM traffic per attempt drops
+// from 42 to 4 vector passes (read y, K1; write y_new, K7), at 1.9 % redundant arithmetic.
+// =================================================================================================
+constexpr int kTileThreads = 320;
+constexpr int kTileCells = 2 * kTileThreads;
+constexpr int kTileHalo = 6;
+constexpr int kTileValid = kTileCells - 2 * kTileHalo;
+
+struct TileSmem {
+  static constexpr size_t off_K = 0;                                                   // double2 [4][5][320]
+  static constexpr size_t off_E = off_K + sizeof(double2) * 4 * 5 * kTileThreads;      // double [2][5][320]
+  static constexpr size_t off_O = off_E + sizeof(double) * 2 * 5 * kTileThreads;
+  static constexpr size_t off_tab = off_O + sizeof(double) * 2 * 5 * kTileThreads;
+  static constexpr size_t off_kc = off_tab + fm::kTableBytes;
+  static constexpr size_t off_red = off_kc + (sizeof(ColumnConsts) + 15) / 16 * 16;
+  static constexpr size_t total = off_red + 16 * sizeof(double);
+};
+
+__global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Args A, int cbuf) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int TP = kTileThreads;
+  const int tid = threadIdx.x;
+  const int col = blockIdx.x / A.tiles2;
+  const int tile = blockIdx.x - col * A.tiles2;
+  const Ctl c0 = A.ctl[(size_t)cbuf * A.B + col];
+  if (!c0.active) return;                                   // uniform per CTA
+  double2* const sK = reinterpret_cast<double2*>(smem_raw + TileSmem::off_K) + tid;
+  double* const sE = reinterpret_cast<double*>(smem_raw + TileSmem::off_E);
+  double* const sO = reinterpret_cast<double*>(smem_raw + TileSmem::off_O);
+  ColumnConsts& kc = *reinterpret_cast<ColumnConsts*>(smem_raw + TileSmem::off_kc);
+  double* const red = reinterpret_cast<double*>(smem_raw + TileSmem::off_red);
+  const fm::Tables tb = fm::stage_tables(smem_raw + TileSmem::off_tab, tid, blockDim.x);
+  const int N = A.N;
+  if (tid == 0) make_consts(A.params[col], N, kc);
+  const size_t vec = (size_t)A.B * 5 * N;
+  const double h = c0.h;
+
+  const int e0 = 2 * tid;                                   // position inside the window
+  const int g0 = tile * kTileValid - kTileHalo + e0;        // global cell of my first cell (always even)
+  const bool in0 = g0 >= 0 && g0 < N, in1 = g0 + 1 >= 0 && g0 + 1 < N;
+  const bool top = g0 == 0;                                 // my first cell is the column's first cell
+  const bool bot1 = g0 + 1 == N - 1;                        // my second cell is the column's last cell
+  const bool bot0 = g0 == N - 1;                            // odd N: my first cell is the last one
+  const bool out0 = in0 && e0 >= kTileHalo && e0 < kTileCells - kTileHalo;      // cells this window owns
+  const bool out1 = in1 && e0 + 1 >= kTileHalo && e0 + 1 < kTileCells - kTileHalo;
+  const size_t base = (size_t)col * 5 * N + (size_t)(g0 < 0 ? 0 : g0);
+  const double* const haloM = sO + (tid == 0 ? tid : tid - 1);
+  const double* const haloP = sE + (tid == TP - 1 ? tid : tid + 1);
+  double* const myE = sE + tid;
+  double* const myO = sO + tid;
+  auto Kslot = [&](int logical) -> double* {
+    const int s = logical == 1 ? c0.k1 : (logical == 7 ? c0.k7 : logical - 1);
+    return A.K + (size_t)s * vec;
+  };
+  auto Kst = [&](int s, int f, double v0, double v1) { sK[(s * 5 + f) * TP] = make_double2(v0, v1); };
+  auto Kld = [&](int s, int f) -> double2 { return sK[(s * 5 + f) * TP]; };
+
+  double y[5][2], k1[5][2], c[5][2], r[5][2];
+  {
+    const double* K1g = Kslot(1);
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      const double* yp = A.y + base + (size_t)f * N;
+      const double* kp = K1g + base + (size_t)f * N;
+      y[f][0] = in0 ? yp[0] : 0.5;
+      y[f][1] = in1 ? yp[g0 < 0 ? g0 + 1 : 1] : 0.5;     // (g0 = -2k < 0 never has an in-range partner; kept safe)
+      k1[f][0] = in0 ? kp[0] : 0.0;
+      k1[f][1] = in1 ? kp[g0 < 0 ? g0 + 1 : 1] : 0.0;
+    }
+  }
+  const bool in_mask[2] = {in0 && g0 >= A.params[col].mask_lo && g0 < A.params[col].mask_hi,
+                           in1 && g0 + 1 >= A.params[col].mask_lo && g0 + 1 < A.params[col].mask_hi};
+  auto tile_store = [&](int b) {
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      myE[(b * 5 + f) * TP] = c[f][0];
+      myO[(b * 5 + f) * TP] = c[f][1];
+    }
+  };
+  {
+    const double ha = h * dp::a21;
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      c[f][0] = fma(ha, k1[f][0], y[f][0]);
+      c[f][1] = fma(ha, k1[f][1], y[f][1]);
+    }
+    tile_store(1);
+  }
+  __syncthreads();
+
+  double U[2], W[2];
+#pragma unroll 1
+  for (int i = 1; i <= 6; ++i) {
+    if (i > 1) __syncthreads();
+    const int tb_ = (i & 1) * 5 * TP;
+    double mlo[5], phi[5];
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      const double hm = haloM[tb_ + f * TP], hp = haloP[tb_ + f * TP];
+      mlo[f] = top ? top_ghost(kc, f, c[f][0]) : (tid == 0 ? c[f][0] : hm);
+      if (bot1) {
+        phi[f] = bottom_ghost(f, c[f][1], c[f][0]);
+      } else if (bot0) {
+        c[f][1] = bottom_ghost(f, c[f][0], mlo[f]);
+        phi[f] = c[f][1];
+      } else {
+        phi[f] = tid == TP - 1 ? c[f][1] : hp;
+      }
+    }
+    PairFlags fl = rhs_pair(kc, tb, c, mlo, phi, in_mask, r, U, W);
+    // cells a stage can still compute correctly: i window cells are lost at either edge by stage i
+    fl.bad[0] = fl.bad[0] && in0 && e0 >= i && e0 < kTileCells - i;
+    fl.bad[1] = fl.bad[1] && in1 && e0 + 1 >= i && e0 + 1 < kTileCells - i;
+    if (fl.bad[0] || fl.bad[1]) rhs_pair_fixup(kc, tb, fl, c, mlo, phi, in_mask, r, U, W);
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {                            // cells outside the column stay inert
+      if (!in0) r[f][0] = 0.0;
+      if (!in1) r[f][1] = 0.0;
+    }
+    switch (i) {
+      case 1:
+#pragma unroll
+        for (int f = 0; f < 5; ++f) {
+          Kst(0, f, r[f][0], r[f][1]);
+          c[f][0] = fma(h, fma(dp::a31, k1[f][0], dp::a32 * r[f][0]), y[f][0]);
+          c[f][1] = fma(h, fma(dp::a31, k1[f][1], dp::a32 * r[f][1]), y[f][1]);
+        }
+        tile_store(0);
+        break;
+      case 2:
+#pragma unroll
+        for (int f = 0; f < 5; ++f) {
+          Kst(1, f, r[f][0], r[f][1]);
+          const double2 K2 = Kld(0, f);
+          c[f][0] = fma(h, fma(dp::a41, k1[f][0], fma(dp::a42, K2.x, dp::a43 * r[f][0])), y[f][0]);
+          c[f][1] = fma(h, fma(dp::a41, k1[f][1], fma(dp::a42, K2.y, dp::a43 * r[f][1])), y[f][1]);
+        }
+        tile_store(1);
+        break;
+      case 3:
+#pragma unroll
+        for (int f = 0; f < 5; ++f) {
+          Kst(2, f, r[f][0], r[f][1]);
+          const double2 K2 = Kld(0, f), K3 = Kld(1, f);
+          c[f][0] = fma(h, fma(dp::a51, k1[f][0], fma(dp::a52, K2.x, fma(dp::a53, K3.x, dp::a54 * r[f][0]))), y[f][0]);
+          c[f][1] = fma(h, fma(dp::a51, k1[f][1], fma(dp::a52, K2.y, fma(dp::a53, K3.y, dp::a54 * r[f][1]))), y[f][1]);
+        }
+        tile_store(0);
+        break;
+      case 4:
+#pragma unroll
+        for (int f = 0; f < 5; ++f) {
+          Kst(3, f, r[f][0], r[f][1]);
+          const double2 K2 = Kld(0, f), K3 = Kld(1, f), K4 = Kld(2, f);
+          c[f][0] = fma(h, fma(dp::a61, k1[f][0], fma(dp::a62, K2.x, fma(dp::a63, K3.x, fma(dp::a64, K4.x, dp::a65 * r[f][0])))), y[f][0]);
+          c[f][1] = fma(h, fma(dp::a61, k1[f][1], fma(dp::a62, K2.y, fma(dp::a63, K3.y, fma(dp::a64, K4.y, dp::a65 * r[f][1])))), y[f][1]);
+        }
+        tile_store(1);
+        break;
+      case 5:
+#pragma unroll
+        for (int f = 0; f < 5; ++f) {
+          const double2 K3 = Kld(1, f), K4 = Kld(2, f), K5 = Kld(3, f);
+          Kst(0, f, r[f][0], r[f][1]);                       // K6 over the dead K2
+          c[f][0] = fma(h, fma(dp::b1, k1[f][0], fma(dp::b3, K3.x, fma(dp::b4, K4.x, fma(dp::b5, K5.x, dp::b6 * r[f][0])))), y[f][0]);
+          c[f][1] = fma(h, fma(dp::b1, k1[f][1], fma(dp::b3, K3.y, fma(dp::b4, K4.y, fma(dp::b5, K5.y, dp::b6 * r[f][1])))), y[f][1]);
+        }
+        tile_store(0);
+        break;
+      default:
+        break;
+    }
+  }
+  // ---- r = K7 = f(y_new), c = y_new: error contribution of the cells this window owns, write-back
+  const bool sample = c0.next_eval < A.opt.n_eval && A.t_eval[c0.next_eval] <= c0.t_new;   // dense output pending
+  double part = 0.0;
+  double* const ynew = A.tile;                               // vector 0 of the stage-input pair
+  double* const K7g = Kslot(7);
+#pragma unroll
+  for (int f = 0; f < 5; ++f) {
+    const double2 K3 = Kld(1, f), K4 = Kld(2, f), K5 = Kld(3, f), K6 = Kld(0, f);
+    const double e0v = fma(dp::e1, k1[f][0], fma(dp::e3, K3.x, fma(dp::e4, K4.x, fma(dp::e5, K5.x, fma(dp::e6, K6.x, dp::e7 * r[f][0])))));
+    const double e1v = fma(dp::e1, k1[f][1], fma(dp::e3, K3.y, fma(dp::e4, K4.y, fma(dp::e5, K5.y, fma(dp::e6, K6.y, dp::e7 * r[f][1])))));
+    const double s0 = fma(fmax(fabs(y[f][0]), fabs(c[f][0])), A.opt.rtol, A.opt.atol);
+    const double s1 = fma(fmax(fabs(y[f][1]), fabs(c[f][1])), A.opt.rtol, A.opt.atol);
+    const double z0 = (h * e0v) * fm::rcp3(s0), z1 = (h * e1v) * fm::rcp3(s1);
+    if (out0) part = fma(z0, z0, part);
+    if (out1) part = fma(z1, z1, part);
+    const size_t o = base + (size_t)f * N;
+    if (out0) {
+      ynew[o] = c[f][0];
+      K7g[o] = r[f][0];
+    }
+    if (out1) {
+      ynew[o + 1] = c[f][1];
+      K7g[o + 1] = r[f][1];
+    }
+    if (sample) {                                            // K3..K6 are only needed by the dense output
+      if (out0) {
+        A.K[2 * vec + o] = K3.x;
+        A.K[3 * vec + o] = K4.x;
+        A.K[4 * vec + o] = K5.x;
+        A.K[5 * vec + o] = K6.x;
+      }
+      if (out1) {
+        A.K[2 * vec + o + 1] = K3.y;
+        A.K[3 * vec + o + 1] = K4.y;
+        A.K[4 * vec + o + 1] = K5.y;
+        A.K[5 * vec + o + 1] = K6.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((tid & 31) == 0) red[tid >> 5] = part;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kTileThreads / 32; ++w) s += red[w];
+    A.partials[(size_t)col * A.tiles2 + tile] = s;
+  }
+}
+
 }  // namespace st
 
 size_t rk45_stream_workspace_bytes(int n_columns, int n_cells) { return st::layout(n_columns, n_cells).total; }
@@ -461,17 +698,33 @@ cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_param
   a.N = n_cells;
   a.tiles = (n_cells + st::kCellsPerCta - 1) / st::kCellsPerCta;
   a.opt = opt;
+  a.tiles2 = 0;
   const long long blocks = (long long)a.tiles * n_columns;
   if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
   const unsigned grid = (unsigned)blocks;
   const unsigned cgrid = (unsigned)((n_columns + 127) / 128);
+  // MARLPDE_RK45_STREAM=stages selects one launch per stage (HBM-streaming) instead of overlapped tiles
+  const char* mode_env = std::getenv("MARLPDE_RK45_STREAM");
+  const int use_tiles = (mode_env && mode_env[0] == 's') ? 0 : 1;
+  unsigned tgrid = 0;
+  if (use_tiles) {
+    a.tiles2 = (n_cells + st::kTileValid - 1) / st::kTileValid;
+    tgrid = (unsigned)((long long)a.tiles2 * n_columns);
+    cudaError_t e = cudaFuncSetAttribute(st::tile_attempt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)st::TileSmem::total);
+    if (e != cudaSuccess) return e;
+  }
   st::init_kernel<<<cgrid, 128, 0, stream>>>(a);
   st::stage_kernel<<<grid, st::kThreads, 0, stream>>>(a, 0, 0);            // K1 = f(y)
   int pin = 0;
-  // attempts + 1 prepares: the last one only closes the last attempt (its stage-2 input is unused)
+  // attempts + 1 prepares: the last one only closes the last attempt
   for (long long j = 0; j < attempts; ++j) {
     st::prepare_kernel<<<grid, st::kThreads, 0, stream>>>(a, pin);
-    for (int i = 1; i <= 6; ++i) st::stage_kernel<<<grid, st::kThreads, 0, stream>>>(a, i, pin ^ 1);
+    if (use_tiles) {
+      st::tile_attempt_kernel<<<tgrid, st::kTileThreads, st::TileSmem::total, stream>>>(a, pin ^ 1);
+    } else {
+      for (int i = 1; i <= 6; ++i) st::stage_kernel<<<grid, st::kThreads, 0, stream>>>(a, i, pin ^ 1);
+    }
     pin ^= 1;
   }
   st::prepare_kernel<<<grid, st::kThreads, 0, stream>>>(a, pin);

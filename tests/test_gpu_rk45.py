@@ -246,11 +246,13 @@ def test_events_survive_resume():
 
 
 # ---- depth grids that do not fit on chip: the streaming path (csrc/rk45_streaming.cu) ---------------
-@pytest.mark.parametrize("n_cells,ncol", [(2000, 3), (5000, 1), (641, 2), (16, 2)])
-def test_streaming_path_matches_scipy(n_cells, ncol):
+@pytest.mark.parametrize("mode", ["tiles", "stages"])
+@pytest.mark.parametrize("n_cells,ncol", [(2000, 3), (5000, 1), (641, 2), (16, 2), (1257, 2)])
+def test_streaming_path_matches_scipy(n_cells, ncol, mode, monkeypatch):
     """BASELINE.json configs[3]: fixed budget of ~2000 steps, t_end and
     first_step scaled with (200/N)^2 (the explicit step is stability bound), state at t_end against SciPy
     RK45 on the oracle.  Same stepper semantics as the on-chip kernel: nfev within two attempts."""
+    monkeypatch.setenv("MARLPDE_RK45_STREAM", mode)          # overlapped on-chip tiles (default) / one launch per stage
     pde = oracle.default_scenario() | {"N": n_cells, "Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}
     scale = min(1.0, (200 / n_cells) ** 2)
     t_end, fs = 600 * 2.6e-6 * scale, 1e-6 * scale

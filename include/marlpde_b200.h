@@ -125,6 +125,10 @@ const char* marlpde_last_error(void);
 int marlpde_device_count(void);
 int marlpde_get_device_info(int device, marlpde_device_info* info);
 
+/* The host-pointer entry points keep their device scratch buffers in a small per-process pool between
+ * calls (cudaMalloc/cudaFree are slow); this returns them to the driver. Returns the number of blocks freed. */
+int marlpde_release_cached_memory(void);
+
 /* Largest n_cells the on-chip (shared-memory resident) RK45 kernel accepts, and the
  * number of columns one CTA integrates side by side for a given n_cells. */
 int marlpde_rk45_max_cells(void);

@@ -3,9 +3,12 @@
 // only enqueue work on the caller's stream.  There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "../../include/marlpde_b200.h"
@@ -50,11 +53,76 @@ int current_props(DevProps& p) {
   return MARLPDE_OK;
 }
 
-// RAII device buffer for the host-pointer entry points
+// MARLPDE_TRACE=1: wall-clock phases of the host-pointer entry points on stderr (the reference prints
+// the wall time around solve_ivp, Evolve_scenario.py:90, :110, :148-149)
+struct PhaseTrace {
+  bool on;
+  const char* what;
+  std::chrono::steady_clock::time_point t0;
+  explicit PhaseTrace(const char* w) : on(std::getenv("MARLPDE_TRACE") != nullptr), what(w), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* phase) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[marlpde trace] %s: %-10s %8.2f ms\n", what, phase,
+                 std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
+// Device scratch of the host-pointer entry points.  cudaMalloc / cudaFree cost 3-130 ms per call on the
+// bench box (measured with MARLPDE_TRACE, r01c) — as much as 20 % of a 3000-attempt step — so freed
+// blocks are kept in a small per-process pool and handed out again (best fit, at most 2x the request);
+// marlpde_release_cached_memory() returns them to the driver.
+struct CachedBlock {
+  void* p;
+  size_t bytes;
+  int device;
+};
+std::mutex g_pool_mutex;
+std::vector<CachedBlock> g_pool;
+
 struct DevBuf {
   void* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+  size_t bytes = 0;
+  int device = 0;
+  ~DevBuf() {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (g_pool.size() < 64) g_pool.push_back({p, bytes, device});
+    else cudaFree(p);
+  }
+  cudaError_t alloc(size_t n) {
+    if (n == 0) n = 1;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return e;
+    {
+      std::lock_guard<std::mutex> lock(g_pool_mutex);
+      int best = -1;
+      for (int i = 0; i < (int)g_pool.size(); ++i)
+        if (g_pool[i].device == device && g_pool[i].bytes >= n && g_pool[i].bytes <= 2 * n + 4096 &&
+            (best < 0 || g_pool[i].bytes < g_pool[best].bytes))
+          best = i;
+      if (best >= 0) {
+        p = g_pool[best].p;
+        bytes = g_pool[best].bytes;
+        g_pool.erase(g_pool.begin() + best);
+        return cudaSuccess;
+      }
+    }
+    bytes = n;
+    e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) {                       // out of memory: drop the pool and retry once
+      {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        for (auto& b : g_pool) cudaFree(b.p);
+        g_pool.clear();
+      }
+      cudaGetLastError();
+      e = cudaMalloc(&p, n);
+    }
+    if (e != cudaSuccess) p = nullptr;
+    return e;
+  }
   template <typename T> T* as() { return static_cast<T*>(p); }
 };
 
@@ -108,6 +176,21 @@ int marlpde_get_device_info(int device, marlpde_device_info* info) {
   info->max_smem_per_block = (int32_t)p.sharedMemPerBlockOptin;
   info->total_mem = (int64_t)p.totalGlobalMem;
   return MARLPDE_OK;
+}
+
+int marlpde_release_cached_memory(void) {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  int n = 0;
+  for (auto& b : g_pool) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != b.device) cudaSetDevice(b.device);
+    cudaFree(b.p);
+    if (cur != b.device) cudaSetDevice(cur);
+    ++n;
+  }
+  g_pool.clear();
+  return n;
 }
 
 int marlpde_rk45_max_cells(void) { return marlpde::rk45_max_cells(); }
@@ -257,6 +340,7 @@ int marlpde_rk45_integrate(double* y, const marlpde_column_params* params, marlp
   const size_t nb_snap = nb_y * (size_t)opts->n_eval;
   const size_t nb_ec = sizeof(int32_t) * MARLPDE_NEVENTS * (size_t)n_columns;
   const size_t nb_et = sizeof(double) * MARLPDE_NEVENTS * (size_t)opts->event_capacity * n_columns;
+  PhaseTrace trace("rk45_integrate");
   DevBuf dy, dp, ds, dte, dsnap, dq, dec, det;
   CU(dy.alloc(nb_y));
   CU(dp.alloc(sizeof(marlpde_column_params) * (size_t)n_columns));
@@ -266,6 +350,7 @@ int marlpde_rk45_integrate(double* y, const marlpde_column_params* params, marlp
   CU(dq.alloc(sizeof(int32_t)));
   CU(dec.alloc(nb_ec));
   CU(det.alloc(nb_et));
+  trace.mark("alloc");
   CU(cudaMemcpy(dy.p, y, nb_y, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(dp.p, params, sizeof(marlpde_column_params) * (size_t)n_columns, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(ds.p, state, sizeof(marlpde_column_state) * (size_t)n_columns, cudaMemcpyHostToDevice));
@@ -279,12 +364,15 @@ int marlpde_rk45_integrate(double* y, const marlpde_column_params* params, marlp
                                   n_columns, n_cells, opts, dte.as<double>(), dsnap.as<double>(),
                                   dec.as<int32_t>(), det.as<double>(), dq.as<int32_t>(), nullptr);
   if (rc) return rc;
+  trace.mark("h2d+launch");
   CU(cudaDeviceSynchronize());
+  trace.mark("kernel");
   CU(cudaMemcpy(y, dy.p, nb_y, cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(state, ds.p, sizeof(marlpde_column_state) * (size_t)n_columns, cudaMemcpyDeviceToHost));
   if (snapshots && nb_snap) CU(cudaMemcpy(snapshots, dsnap.p, nb_snap, cudaMemcpyDeviceToHost));
   if (event_counts) CU(cudaMemcpy(event_counts, dec.p, nb_ec, cudaMemcpyDeviceToHost));
   if (event_times && nb_et) CU(cudaMemcpy(event_times, det.p, nb_et, cudaMemcpyDeviceToHost));
+  trace.mark("d2h");
   return MARLPDE_OK;
 }
 

@@ -68,6 +68,7 @@ SYMBOLS = {
     "marlpde_last_error": (C.c_char_p, []),
     "marlpde_device_count": (C.c_int, []),
     "marlpde_get_device_info": (C.c_int, [C.c_int, C.POINTER(DeviceInfo)]),
+    "marlpde_release_cached_memory": (C.c_int, []),
     "marlpde_rk45_max_cells": (C.c_int, []),
     "marlpde_rk45_columns_per_cta": (C.c_int, [C.c_int]),
     "marlpde_rhs_batch_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),

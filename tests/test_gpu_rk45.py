@@ -284,3 +284,19 @@ def test_streaming_path_resume_device_tensors_and_budget():
     assert_allclose(rest.y, whole.y, rtol=0, atol=1e-12)             # K1 is re-evaluated on resume: same bits expected
     dev = mb.integrate_rk45_batch(torch.from_numpy(y0).cuda(), P, t_span=(0, t_end), first_step=fs, t_eval=[0, t_end])
     assert np.array_equal(dev.y.cpu().numpy(), whole.y) and np.array_equal(dev.snapshots.cpu().numpy(), whole.snapshots)
+
+
+def test_host_path_scratch_pool_is_reused_and_released():
+    """The host-pointer entry points keep their device scratch between calls (cudaMalloc/cudaFree cost up to
+    130 ms per call on the bench box); results do not depend on it and the pool can be handed back."""
+    from marlpde_b200 import _cabi
+    pde = oracle.default_scenario()
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    _cabi.lib().marlpde_release_cached_memory()
+    a = mb.integrate_rk45_batch(y0, P, t_span=(0, 1e-4), first_step=1e-6)
+    b = mb.integrate_rk45_batch(y0, P, t_span=(0, 1e-4), first_step=1e-6)        # served from the pool
+    assert np.array_equal(a.y, b.y) and np.array_equal(a.nfev, b.nfev)
+    assert _cabi.lib().marlpde_release_cached_memory() >= 4
+    assert _cabi.lib().marlpde_release_cached_memory() == 0
+    c = mb.integrate_rk45_batch(y0, P, t_span=(0, 1e-4), first_step=1e-6)
+    assert np.array_equal(a.y, c.y)

@@ -82,10 +82,6 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
@@ -96,13 +92,12 @@ constexpr int kSlots = kDepth + 1;
 struct Work {
   double *yold, *f, *Z, *W, *B, *Q, *err, *tmp;   // n, n, 3n, 3n, 3n, 3n, n, n
   double* J;                                       // [N][3][5][5]  (L, D, U blocks of the Jacobian)
-  double* F;                                       // [N+1][200] forward records  {Y_i, S_{i-1}^-1} x 2 systems (complex)
-  double* Bk;                                      // [N][100]   backward records {X_i} x 2 systems (complex)
+  double2* Sinv;                                   // [2][N][5][5]  inverse Schur complements, both systems
 };
 
 __host__ __device__ inline size_t work_doubles(int N) {
   const size_t n = 5 * (size_t)N;
-  return 16 * n + 76 * (size_t)N + 200 * ((size_t)N + 1) + 100 * (size_t)N;   // 76: keeps the records 16-byte aligned
+  return 16 * n + 76 * (size_t)N + 2 * 2 * 25 * (size_t)N;   // 76: keeps the double2 array 16-byte aligned
 }
 
 struct __align__(16) WarpScratch {          // shared memory per warp
@@ -111,7 +106,7 @@ struct __align__(16) WarpScratch {          // shared memory per warp
   double2 vec[2][2][8];       // two broadcast buffers x two systems x 5 entries (padded)
   double2 mult[2][8];         // Gauss-Jordan multipliers of the pivot column, + pivot row index in [5].x
   double jst[kSlots][80];     // factorise: staged Jacobian blocks [L|D|U] of cells i .. i+kDepth (ring)
-  double mst[kSlots][200];    // solve: staged forward / backward records of cells i .. i+kDepth (16-byte aligned)
+  double mst[kSlots][128];    // solve: staged {J block, S^-1 sys 0, S^-1 sys 1} of cells i .. i+kDepth (16-byte aligned)
 };
 
 struct Args {
@@ -251,12 +246,13 @@ __device__ __noinline__ void fd_jacobian(const ColumnConsts& kc, const fm::Table
 // eliminated, and hand them over through a double-buffered shared-memory stage.  The product
 // X_i = S_i^{-1} U_i needed by the next cell is formed while U_i is still staged and stays in
 // registers (lane (s, c) keeps column c).
-__device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double h, const double* J, double* F, double* Bk) {
+__device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double h, const double* J, double2* Sinv) {
   const int s = lane >> 4, cc = lane & 15;
   const bool valid = cc < 10;
   const bool apart = cc < 5;
   const int c5 = apart ? cc : cc - 5;
   const double2 M = s == 0 ? make_double2(kMuReal / h, 0.0) : make_double2(kMuCRe / h, kMuCIm / h);
+  double2* const out = Sinv + (size_t)s * N * 25;
   // ring of kSlots staged cells: cells 0 .. kDepth-1 are requested up front, cell i+kDepth at iteration i
   auto request = [&](int cell) {
     if (cell < N) {
@@ -279,20 +275,6 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
     __syncwarp();
     const double* Ji = ws.jst[i % kSlots];
     double2 col[5];
-    if (valid && apart) {
-      // forward record of cell i: column c5 of Y_i = L_i S_{i-1}^{-1} (zero for i = 0)
-      double2* Yi = reinterpret_cast<double2*>(F + (size_t)i * 200 + 100 * s);
-#pragma unroll
-      for (int r = 0; r < 5; ++r) {
-        double2 acc = make_double2(0.0, 0.0);
-        if (i > 0) {
-#pragma unroll
-          for (int m = 0; m < 5; ++m) acc = crfma(Ji[r * 5 + m], ws.sinv_prev[s][m * 5 + c5], acc);
-        }
-        Yi[r * 5 + c5] = acc;
-      }
-    }
-    __syncwarp();                                            // sinv_prev is rewritten below
     if (apart) {
       // column c5 of S = M I - D_i - L_i X_{i-1} e_c   (X_{-1} = 0)
 #pragma unroll
@@ -355,7 +337,7 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
 #pragma unroll
         for (int r = 1; r < 5; ++r) v = (pk == r) ? col[r] : v;
         ws.sinv_prev[s][k * 5 + c5] = v;
-        reinterpret_cast<double2*>(F + (size_t)(i + 1) * 200 + 100 * s + 50)[k * 5 + c5] = v;   // S_i^{-1} rides in record i+1
+        out[(size_t)i * 25 + k * 5 + c5] = v;
       }
     }
     __syncwarp();
@@ -368,11 +350,6 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
         for (int m = 0; m < 5; ++m) acc = crfma(Ji[50 + m * 5 + c5], ws.sinv_prev[s][r * 5 + m], acc);
         xcol[r] = acc;
       }
-      if (valid) {                                           // backward record of cell i
-        double2* Xi = reinterpret_cast<double2*>(Bk + (size_t)i * 100 + 50 * s);
-#pragma unroll
-        for (int r = 0; r < 5; ++r) Xi[r * 5 + c5] = xcol[r];
-      }
     }
     __syncwarp();                         // everyone is done with slot i % kSlots before it is requested again
   }
@@ -383,77 +360,100 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
 // system s, row r.  b0: real right-hand side of system 0; (b1, b2): real and imaginary part of the
 // right-hand side of system 1; all field-major [5][N], overwritten with the solution.
 // `both` = false solves system 0 only (error estimate).
-// With Y_i = L_i S_{i-1}^{-1} and X_i = S_i^{-1} U_i from the factorisation each sweep has ONE dependent
-// 5x5 mat-vec per cell:
-//   forward   g_i = b_i + Y_i g_{i-1}   (and, off the recurrence, p_{i-1} = S_{i-1}^{-1} g_{i-1}, stored over b)
-//   backward  x_i = p_i + X_i x_{i+1}
-// Forward record i = {Y_i, S_{i-1}^{-1}} per system (200 doubles, i = 0..N), backward record i = {X_i}
-// (100 doubles); the records of the next kDepth cells are kept in flight by cp.async.
-__device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const double* F, const double* Bk, double* b0,
+// As in factorise(), the matrices of the NEXT cell (one real 5x5 block of J and S^{-1} of both
+// systems, 125 doubles) are fetched by all 32 lanes while the current cell is processed and handed
+// over through shared memory; the right-hand side entry of the next cell is prefetched as well.
+__device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const double* J, const double2* Sinv, double* b0,
                                    double* b1, double* b2, bool both) {
   const int s = (lane >> 3) & 1, r = lane & 7;
   const bool valid = lane < 16 && r < 5 && (s == 0 || both);
   double* const bre = s == 0 ? b0 : b1;
   double* const bim = s == 0 ? nullptr : b2;
-  auto request = [&](const double* rec, int n16, int slot, bool ok) {
+  const double* S0 = reinterpret_cast<const double*>(Sinv);
+  const double* S1 = reinterpret_cast<const double*>(Sinv + (size_t)N * 25);
+  // element e of the staged record of cell i: [0,25) J block (L forward / U backward), [26,76) S^{-1}
+  // of system 0, [76,126) S^{-1} of system 1 (offsets keep the double2 reads 16-byte aligned)
+  auto request = [&](int i, int blk, int slot, bool ok) {
     if (ok) {
+      const double* Jb = J + (size_t)i * 75 + blk;
+      const double* s0 = S0 + (size_t)i * 50;
+      const double* s1 = S1 + (size_t)i * 50;
       double* dst = ws.mst[slot];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int e = lane + 32 * k;
-        if (e < n16) cp_async16(dst + 2 * e, rec + 2 * e);
+        if (e < 25) cp_async8(dst + e, Jb + e);
+        else if (e >= 26 && e < 76) cp_async8(dst + e, s0 + (e - 26));
+        else if (e >= 76 && e < 126) cp_async8(dst + e, s1 + (e - 76));
       }
     }
     cp_async_commit();
   };
   int buf = 0;
-  // ---- forward, steps i = 0..N: step i forms g_i (i < N) and p_{i-1} (i > 0) from the broadcast g_{i-1}
-  for (int c0 = 0; c0 < kDepth; ++c0) request(F + (size_t)c0 * 200, 100, c0 % kSlots, c0 <= N);
-  double2 g = make_double2(0.0, 0.0);
+  for (int c0 = 0; c0 < kDepth; ++c0) request(c0, 0, c0 % kSlots, c0 < N);
+  // ---- forward: g_i = b_i + L_i p_{i-1},  p_i = S_i^{-1} g_i  (p overwrites b)
+  double2 p = make_double2(0.0, 0.0);
   double2 bnext = valid ? make_double2(bre[r * N], bim ? bim[r * N] : 0.0) : make_double2(0.0, 0.0);
 #pragma unroll 1
-  for (int i = 0; i <= N; ++i) {
-    request(F + (size_t)(i + kDepth) * 200, 100, (i + kDepth) % kSlots, i + kDepth <= N);
+  for (int i = 0; i < N; ++i) {
+    request(i + kDepth, 0, (i + kDepth) % kSlots, i + kDepth < N);
     cp_async_wait<kDepth>();
-    if (valid) ws.vec[buf][s][r] = g;                      // g_{i-1}
     __syncwarp();
-    const double2* R = reinterpret_cast<const double2*>(ws.mst[i % kSlots] + 100 * s);
-    double2 gi = bnext, pprev = make_double2(0.0, 0.0);
-    if (valid) {
-      if (i + 1 < N) bnext = make_double2(bre[r * N + i + 1], bim ? bim[r * N + i + 1] : 0.0);
+    const double* M = ws.mst[i % kSlots];
+    const bool more = i + 1 < N;
+    double2 g = bnext;
+    if (valid && more) bnext = make_double2(bre[r * N + i + 1], bim ? bim[r * N + i + 1] : 0.0);
+    if (valid) ws.vec[buf][s][r] = p;
+    __syncwarp();
+    if (valid && i > 0) {
 #pragma unroll
-      for (int m = 0; m < 5; ++m) {
-        const double2 v = ws.vec[buf][s][m];
-        gi = cfma(R[r * 5 + m], v, gi);                    // Y_i g_{i-1}
-        pprev = cfma(R[25 + r * 5 + m], v, pprev);         // S_{i-1}^{-1} g_{i-1}
-      }
-      if (i > 0) {
-        bre[r * N + i - 1] = pprev.x;
-        if (bim) bim[r * N + i - 1] = pprev.y;
-      }
-      g = gi;
+      for (int m = 0; m < 5; ++m) g = crfma(M[r * 5 + m], ws.vec[buf][s][m], g);
+    }
+    buf ^= 1;
+    if (valid) ws.vec[buf][s][r] = g;
+    __syncwarp();
+    if (valid) {
+      const double2* Sr = reinterpret_cast<const double2*>(M + 26 + 50 * s) + r * 5;
+      double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int m = 0; m < 5; ++m) acc = cfma(Sr[m], ws.vec[buf][s][m], acc);
+      p = acc;
+      bre[r * N + i] = p.x;
+      if (bim) bim[r * N + i] = p.y;
     }
     buf ^= 1;
     __syncwarp();
   }
   cp_async_wait<0>();
   if (N < 2) return;
-  // ---- backward: x_{N-1} = p_{N-1} (just stored by this lane), x_i = p_i + X_i x_{i+1}; step j handles cell N-2-j
-  double2 x = valid ? make_double2(bre[r * N + N - 1], bim ? bim[r * N + N - 1] : 0.0) : make_double2(0.0, 0.0);
-  for (int c0 = 0; c0 < kDepth; ++c0) request(Bk + (size_t)(N - 2 - c0 < 0 ? 0 : N - 2 - c0) * 100, 50, c0 % kSlots, N - 2 - c0 >= 0);
+  // ---- backward: x_{N-1} = p_{N-1},  x_i = p_i + S_i^{-1} (U_i x_{i+1});  step j handles cell N-2-j
+  for (int c0 = 0; c0 < kDepth; ++c0) request(N - 2 - c0, 50, c0 % kSlots, N - 2 - c0 >= 0);
+  double2 x = p;
   bnext = valid ? make_double2(bre[r * N + N - 2], bim ? bim[r * N + N - 2] : 0.0) : make_double2(0.0, 0.0);
 #pragma unroll 1
   for (int i = N - 2, j = 0; i >= 0; --i, ++j) {
-    request(Bk + (size_t)(i - kDepth < 0 ? 0 : i - kDepth) * 100, 50, (j + kDepth) % kSlots, i - kDepth >= 0);
+    request(i - kDepth, 50, (j + kDepth) % kSlots, i - kDepth >= 0);
     cp_async_wait<kDepth>();
-    if (valid) ws.vec[buf][s][r] = x;                      // x_{i+1}
     __syncwarp();
-    const double2* R = reinterpret_cast<const double2*>(ws.mst[j % kSlots] + 50 * s);
+    const double* M = ws.mst[j % kSlots];
+    const bool more = i > 0;
+    const double2 pi = bnext;
+    if (valid && more) bnext = make_double2(bre[r * N + i - 1], bim ? bim[r * N + i - 1] : 0.0);
+    if (valid) ws.vec[buf][s][r] = x;
+    __syncwarp();
+    double2 u = make_double2(0.0, 0.0);
     if (valid) {
-      double2 acc = bnext;                                 // p_i
-      if (i > 0) bnext = make_double2(bre[r * N + i - 1], bim ? bim[r * N + i - 1] : 0.0);
 #pragma unroll
-      for (int m = 0; m < 5; ++m) acc = cfma(R[r * 5 + m], ws.vec[buf][s][m], acc);
+      for (int m = 0; m < 5; ++m) u = crfma(M[r * 5 + m], ws.vec[buf][s][m], u);
+    }
+    buf ^= 1;
+    if (valid) ws.vec[buf][s][r] = u;
+    __syncwarp();
+    if (valid) {
+      const double2* Sr = reinterpret_cast<const double2*>(M + 26 + 50 * s) + r * 5;
+      double2 acc = pi;
+#pragma unroll
+      for (int m = 0; m < 5; ++m) acc = cfma(Sr[m], ws.vec[buf][s][m], acc);
       x = acc;
       bre[r * N + i] = x.x;
       if (bim) bim[r * N + i] = x.y;
@@ -556,8 +556,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
     w.err = wbase;                wbase += n;
     w.tmp = wbase;                wbase += n;
     w.J = wbase;                  wbase += 76 * (size_t)N;
-    w.F = wbase;                  wbase += 200 * ((size_t)N + 1);
-    w.Bk = wbase;
+    w.Sinv = reinterpret_cast<double2*>(wbase);
     if (lane == 0) make_consts(A.g_params[col], N, ws.kc);
     __syncwarp();
     const ColumnConsts& kc = ws.kc;
@@ -623,7 +622,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
         bool converged = false;
         for (;;) {
           if (!lu_valid) {                 // (radau.py keeps the factors while the step-size factor is 1)
-            factorise(ws, N, lane, h, w.J, w.F, w.Bk);
+            factorise(ws, N, lane, h, w.J, w.Sinv);
             nlu += 2;
             lu_valid = true;
           }
@@ -669,7 +668,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
             }
             __syncwarp();
             if (!__all_sync(0xffffffffu, finite)) break;
-            solve(ws, N, lane, w.F, w.Bk, w.B, w.B + n, w.B + 2 * n, true);
+            solve(ws, N, lane, w.J, w.Sinv, w.B, w.B + n, w.B + 2 * n, true);
             double ss = 0.0;
             _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
               const double sc = fma(fabs(y[idx]), rtol, atol);
@@ -720,7 +719,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
           w.err[idx] = w.f[idx] + ze;
         }
         __syncwarp();
-        solve(ws, N, lane, w.F, w.Bk, w.err, nullptr, nullptr, false);
+        solve(ws, N, lane, w.J, w.Sinv, w.err, nullptr, nullptr, false);
         auto err_norm_of = [&]() {
           double ss = 0.0;
           _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
@@ -739,7 +738,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
           nfev += 1;
           _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) w.err[idx] = w.B[idx] + w.tmp[idx];
           __syncwarp();
-          solve(ws, N, lane, w.F, w.Bk, w.err, nullptr, nullptr, false);
+          solve(ws, N, lane, w.J, w.Sinv, w.err, nullptr, nullptr, false);
           error_norm = err_norm_of();
         }
         if (error_norm > 1.0 || !(error_norm == error_norm)) {

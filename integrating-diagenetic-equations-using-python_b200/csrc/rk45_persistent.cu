@@ -47,13 +47,16 @@ struct SlotCtl {          // per-slot counters, touched by the slot's leader thr
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) / 16 * 16; }
 
-template <int TP, bool YS>
+template <int TP, bool YS, bool HS>
 struct Smem {
   static constexpr size_t off_K = 0;
   static constexpr size_t off_Y = off_K + sizeof(double2) * 4 * 5 * TP;        // y, K1: [2][5][TP] double2, YS builds only
+  // halo exchange: HS = false: two full stage-input vectors [2][5][TP] per parity (even / odd cells);
+  //                HS = true : warp shuffles, only the warp-edge values [2][TP/32][2][5] and a 2 x TP scratch
+  //                            (event location) live in shared memory
   static constexpr size_t off_tE = off_Y + (YS ? sizeof(double2) * 2 * 5 * TP : 0);
-  static constexpr size_t off_tO = off_tE + sizeof(double) * 2 * 5 * TP;
-  static constexpr size_t off_grp = off_tO + sizeof(double) * 2 * 5 * TP;
+  static constexpr size_t off_tO = off_tE + (HS ? sizeof(double) * 2 * TP : sizeof(double) * 2 * 5 * TP);
+  static constexpr size_t off_grp = off_tO + (HS ? sizeof(double) * 2 * (TP / 32 + 1) * 2 * 5 : sizeof(double) * 2 * 5 * TP);
   static constexpr size_t off_tab = off_grp + sizeof(double) * TP;
   static constexpr size_t off_var = off_tab + fm::kTableBytes;          // per-slot arrays start here
   static constexpr size_t slot_bytes = (sizeof(ColumnConsts) + 15) / 16 * 16 + (sizeof(SlotCtl) + 15) / 16 * 16 + 32;
@@ -66,12 +69,12 @@ static int group_log2(int threads_per_column) {
   return logG;
 }
 
-template <int TP, bool YS>
+template <int TP, bool YS, bool HS>
 static int columns_per_cta_t(int n_cells, int smem_budget) {
   const int Hc = (n_cells + 1) / 2;
   if (n_cells < 32 || Hc > TP) return 0;
   int C = TP / Hc;
-  while (C > 0 && Smem<TP, YS>::total(C) > (size_t)smem_budget) --C;
+  while (C > 0 && Smem<TP, YS, HS>::total(C) > (size_t)smem_budget) --C;
   return C;
 }
 
@@ -79,23 +82,28 @@ static int columns_per_cta_t(int n_cells, int smem_budget) {
 // follows from the warps per sub-partition, not from the thread count alone):
 //   <320,false> 10 warps, <= 168 registers, y and K1 in registers      (n_cells <= 640; N=200: 3 columns)
 //   <320,true>  10 warps, <= 168 registers, y and K1 in shared memory  (same shapes; fewer register spills)
-// MARLPDE_RK45_BUILD=320|321 overrides the default choice (tuning / tests).
+//   <416,true,HS> 13 warps, <= 128 registers, y and K1 in shared memory, halo exchange by warp shuffles
+//               instead of a stage-input tile (frees 64 kB: N=200 runs 4 columns per CTA)
+// MARLPDE_RK45_BUILD=320|321|416 overrides the default choice (tuning / tests).
 static int rk45_variant() {
   static int v = -1;
   if (v < 0) {
     const char* s = std::getenv("MARLPDE_RK45_BUILD");
     const int want = s ? std::atoi(s) : 0;
-    v = (want == 321) ? 321 : 320;
+    v = (want == 321 || want == 416) ? want : 320;
   }
   return v;
 }
 
 int rk45_columns_per_cta(int n_cells, int smem_budget) {
-  return rk45_variant() == 321 ? columns_per_cta_t<320, true>(n_cells, smem_budget)
-                               : columns_per_cta_t<320, false>(n_cells, smem_budget);
+  switch (rk45_variant()) {
+    case 321: return columns_per_cta_t<320, true, false>(n_cells, smem_budget);
+    case 416: return columns_per_cta_t<416, true, true>(n_cells, smem_budget);
+    default: return columns_per_cta_t<320, false, false>(n_cells, smem_budget);
+  }
 }
 
-int rk45_max_cells() { return 640; }
+int rk45_max_cells() { return 640; }   // (the 416 build would take 832; the ABI reports the default build)
 
 
 // ---- event monitors (LHeureux_model.py:524-593, all non-terminal, direction 0) -----------------
@@ -173,10 +181,10 @@ struct Rk45Args {
   marlpde_rk45_options opt;
 };
 
-template <int TP, bool YS>
+template <int TP, bool YS, bool HS>
 __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel(const Rk45Args A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  using L = Smem<TP, YS>;
+  using L = Smem<TP, YS, HS>;
   const int tid = threadIdx.x;
   const int N = A.N, C = A.C;
   const int Hc = (N + 1) >> 1;                     // threads per column
@@ -207,6 +215,10 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
   const double* const haloP = sE + (last ? tid : tid + 1);
   double* const myE = sE + tid;
   double* const myO = sO + tid;
+  // HS builds: sO holds the warp-edge values [2 parities][warp][2 sides][5]; side 0 = lane 0's even cell,
+  // side 1 = lane 31's odd cell
+  const int lane_id = tid & 31, warp_id = tid >> 5;
+  constexpr int kEdgeStride = (TP / 32 + 1) * 2 * 5;
   // Error-norm reduction tree, identical for every slot so that a column's trajectory does not
   // depend on where it is scheduled: threads are summed in aligned groups of G = 2^k lanes
   // (G = largest power of two <= 32 dividing Hc, hence dividing every slot base) by an xor
@@ -246,10 +258,31 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
     }
 
   auto tile_store = [&](int b) {
+    if (HS) {                                       // only the two edge lanes of a warp publish through shared memory
+      if (lane_id == 0 || lane_id == 31) {
+        double* e = sO + b * kEdgeStride + (warp_id * 2 + (lane_id == 31 ? 1 : 0)) * 5;
+#pragma unroll
+        for (int f = 0; f < 5; ++f) e[f] = lane_id == 31 ? c[f][1] : c[f][0];
+      }
+      return;
+    }
 #pragma unroll
     for (int f = 0; f < 5; ++f) {
       myE[(b * 5 + f) * TP] = c[f][0];
       myO[(b * 5 + f) * TP] = c[f][1];
+    }
+  };
+  // raw halo values of my pair for stage parity b: (odd cell of thread tid-1, even cell of thread tid+1)
+  auto halo_load = [&](int b, int f, double& hm, double& hp) {
+    if (HS) {
+      hm = __shfl_up_sync(0xffffffffu, c[f][1], 1);
+      hp = __shfl_down_sync(0xffffffffu, c[f][0], 1);
+      const double* e = sO + b * kEdgeStride;
+      if (lane_id == 0 && warp_id > 0) hm = e[((warp_id - 1) * 2 + 1) * 5 + f];
+      if (lane_id == 31) hp = e[((warp_id + 1) * 2) * 5 + f];
+    } else {
+      hm = haloM[(b * 5 + f) * TP];
+      hp = haloP[(b * 5 + f) * TP];
     }
   };
   auto Kst = [&](int s, int f, double v0, double v1) { sK[(s * 5 + f) * TP] = make_double2(v0, v1); };
@@ -486,7 +519,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
           bs.init(t, t_new);
         }
         for (;;) {
-          double* const scr = sE + buf * TP + slot * Hc;
+          double* const scr = sE + buf * TP + slot * Hc;   // (HS builds: sE is exactly this 2 x TP scratch)
           if (working) {
             double v = event_partial(k, (xeval - t) / h);
             for (int o = G >> 1; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(gmask, v, o));
@@ -541,11 +574,11 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
 #pragma unroll 1
     for (int i = i0; i <= 6; ++i) {
       if (i > i0) __syncthreads();
-      const int tb_ = (i & 1) * 5 * TP;
       double mlo[5], phi[5];
 #pragma unroll
       for (int f = 0; f < 5; ++f) {
-        const double hm = haloM[tb_ + f * TP], hp = haloP[tb_ + f * TP];
+        double hm, hp;
+        halo_load(i & 1, f, hm, hp);
         mlo[f] = first ? top_ghost(kc, f, c[f][0]) : hm;
         if (!last) {
           phi[f] = hp;
@@ -722,21 +755,21 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
   }
 }
 
-template <int TP, bool YS>
+template <int TP, bool YS, bool HS>
 static cudaError_t launch_t(const Rk45Args& a, int sm_count, int smem_budget, cudaStream_t stream) {
   Rk45Args args = a;
-  args.C = columns_per_cta_t<TP, YS>(a.N, smem_budget);
+  args.C = columns_per_cta_t<TP, YS, HS>(a.N, smem_budget);
   if (args.C <= 0) return cudaErrorInvalidValue;
   const int Hc = (a.N + 1) / 2;
   args.logG = group_log2(Hc);
-  const size_t smem = Smem<TP, YS>::total(args.C);
-  cudaError_t e = cudaFuncSetAttribute(rk45_persistent_kernel<TP, YS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = Smem<TP, YS, HS>::total(args.C);
+  cudaError_t e = cudaFuncSetAttribute(rk45_persistent_kernel<TP, YS, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int grid = (a.n_columns + args.C - 1) / args.C;
   if (grid > sm_count) grid = sm_count;
   if (grid < 1) grid = 1;
   const int threads = ((args.C * Hc + 31) / 32) * 32;
-  rk45_persistent_kernel<TP, YS><<<grid, threads, smem, stream>>>(args);
+  rk45_persistent_kernel<TP, YS, HS><<<grid, threads, smem, stream>>>(args);
   return cudaGetLastError();
 }
 
@@ -758,8 +791,11 @@ cudaError_t launch_rk45(double* d_y, const marlpde_column_params* d_params, marl
   a.C = 0;
   a.logG = 0;
   a.opt = opt;
-  return rk45_variant() == 321 ? launch_t<320, true>(a, sm_count, smem_budget, stream)
-                               : launch_t<320, false>(a, sm_count, smem_budget, stream);
+  switch (rk45_variant()) {
+    case 321: return launch_t<320, true, false>(a, sm_count, smem_budget, stream);
+    case 416: return launch_t<416, true, true>(a, sm_count, smem_budget, stream);
+    default: return launch_t<320, false, false>(a, sm_count, smem_budget, stream);
+  }
 }
 
 }  // namespace marlpde

@@ -90,14 +90,14 @@ constexpr int kSlots = kDepth + 1;
 
 // per-column workspace, in doubles (n = 5 N): see radau_workspace_doubles()
 struct Work {
-  double *yold, *f, *Z, *W, *B, *Q, *err, *tmp;   // n, n, 3n, 3n, 3n, 3n, n, n
+  double *y, *yold, *f, *Z, *W, *B, *Q, *err, *tmp;   // n, n, n, 3n, 3n, 3n, 3n, n, n  — all CELL-major [cell][field]
   double* J;                                       // [N][3][5][5]  (L, D, U blocks of the Jacobian)
   double2* Sinv;                                   // [2][N][5][5]  inverse Schur complements, both systems
 };
 
 __host__ __device__ inline size_t work_doubles(int N) {
   const size_t n = 5 * (size_t)N;
-  return 16 * n + 76 * (size_t)N + 2 * 2 * 25 * (size_t)N;   // 76: keeps the double2 array 16-byte aligned
+  return 18 * n + 76 * (size_t)N + 2 * 2 * 25 * (size_t)N;   // 76: keeps the double2 array 16-byte aligned
 }
 
 struct __align__(16) WarpScratch {          // shared memory per warp
@@ -186,20 +186,20 @@ __device__ __forceinline__ double fd_step(double y, double f, double atol) {
 __device__ __noinline__ void rhs_eval(const ColumnConsts* kc, const fm::Tables* tb, int N, int lane, const double* yy,
                                       const double* add, double* out, int fld, int c3, const double* y0,
                                       const double* f0, double atol) {
-  auto ld = [&](int ff, int i) -> double { return add ? yy[ff * N + i] + add[ff * N + i] : yy[ff * N + i]; };
+  auto ld = [&](int ff, int i) -> double { return add ? yy[i * 5 + ff] + add[i * 5 + ff] : yy[i * 5 + ff]; };
   auto sink = [&](int i, const double (&r5)[5]) {
     if (fld < 0) {
 #pragma unroll
-      for (int f = 0; f < 5; ++f) out[f * N + i] = r5[f];
+      for (int f = 0; f < 5; ++f) out[i * 5 + f] = r5[f];
       return;
     }
     const int d = ((c3 - (i % 3)) + 3) % 3;           // 0: j = i, 1: j = i+1, 2: j = i-1
     const int j = i + (d == 2 ? -1 : d);
     if (j < 0 || j >= N) return;
-    const double inv = 1.0 / fd_step(y0[fld * N + j], f0[fld * N + j], atol);
+    const double inv = 1.0 / fd_step(y0[j * 5 + fld], f0[j * 5 + fld], atol);
     double* blk = out + (size_t)i * 75 + (d == 0 ? 25 : (d == 1 ? 50 : 0));
 #pragma unroll
-    for (int r = 0; r < 5; ++r) blk[r * 5 + fld] = (r5[r] - f0[r * N + i]) * inv;
+    for (int r = 0; r < 5; ++r) blk[r * 5 + fld] = (r5[r] - f0[i * 5 + r]) * inv;
   };
   rhs_column(*kc, *tb, N, lane, ld, sink);
   __syncwarp();
@@ -226,13 +226,13 @@ __device__ __noinline__ void fd_jacobian(const ColumnConsts& kc, const fm::Table
     for (int fld = 0; fld < 5; ++fld) {
 #pragma unroll 1
       for (int i = c3 + 3 * lane; i < N; i += 96) {
-        const double v = y[fld * N + i];
-        pert[fld * N + i] = v + fd_step(v, f[fld * N + i], atol);
+        const double v = y[i * 5 + fld];
+        pert[i * 5 + fld] = v + fd_step(v, f[i * 5 + fld], atol);
       }
       __syncwarp();
       rhs_eval(&kc, &tb, N, lane, pert, nullptr, J, fld, c3, y, f, atol);
 #pragma unroll 1
-      for (int i = c3 + 3 * lane; i < N; i += 96) pert[fld * N + i] = y[fld * N + i];
+      for (int i = c3 + 3 * lane; i < N; i += 96) pert[i * 5 + fld] = y[i * 5 + fld];
       __syncwarp();
     }
   }
@@ -393,7 +393,7 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
   for (int c0 = 0; c0 < kDepth; ++c0) request(c0, 0, c0 % kSlots, c0 < N);
   // ---- forward: g_i = b_i + L_i p_{i-1},  p_i = S_i^{-1} g_i  (p overwrites b)
   double2 p = make_double2(0.0, 0.0);
-  double2 bnext = valid ? make_double2(bre[r * N], bim ? bim[r * N] : 0.0) : make_double2(0.0, 0.0);
+  double2 bnext = valid ? make_double2(bre[r], bim ? bim[r] : 0.0) : make_double2(0.0, 0.0);
 #pragma unroll 1
   for (int i = 0; i < N; ++i) {
     request(i + kDepth, 0, (i + kDepth) % kSlots, i + kDepth < N);
@@ -402,7 +402,7 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
     const double* M = ws.mst[i % kSlots];
     const bool more = i + 1 < N;
     double2 g = bnext;
-    if (valid && more) bnext = make_double2(bre[r * N + i + 1], bim ? bim[r * N + i + 1] : 0.0);
+    if (valid && more) bnext = make_double2(bre[(i + 1) * 5 + r], bim ? bim[(i + 1) * 5 + r] : 0.0);
     if (valid) ws.vec[buf][s][r] = p;
     __syncwarp();
     if (valid && i > 0) {
@@ -418,8 +418,8 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
 #pragma unroll
       for (int m = 0; m < 5; ++m) acc = cfma(Sr[m], ws.vec[buf][s][m], acc);
       p = acc;
-      bre[r * N + i] = p.x;
-      if (bim) bim[r * N + i] = p.y;
+      bre[i * 5 + r] = p.x;
+      if (bim) bim[i * 5 + r] = p.y;
     }
     buf ^= 1;
     __syncwarp();
@@ -429,7 +429,7 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
   // ---- backward: x_{N-1} = p_{N-1},  x_i = p_i + S_i^{-1} (U_i x_{i+1});  step j handles cell N-2-j
   for (int c0 = 0; c0 < kDepth; ++c0) request(N - 2 - c0, 50, c0 % kSlots, N - 2 - c0 >= 0);
   double2 x = p;
-  bnext = valid ? make_double2(bre[r * N + N - 2], bim ? bim[r * N + N - 2] : 0.0) : make_double2(0.0, 0.0);
+  bnext = valid ? make_double2(bre[(N - 2) * 5 + r], bim ? bim[(N - 2) * 5 + r] : 0.0) : make_double2(0.0, 0.0);
 #pragma unroll 1
   for (int i = N - 2, j = 0; i >= 0; --i, ++j) {
     request(i - kDepth, 50, (j + kDepth) % kSlots, i - kDepth >= 0);
@@ -438,7 +438,7 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
     const double* M = ws.mst[j % kSlots];
     const bool more = i > 0;
     const double2 pi = bnext;
-    if (valid && more) bnext = make_double2(bre[r * N + i - 1], bim ? bim[r * N + i - 1] : 0.0);
+    if (valid && more) bnext = make_double2(bre[(i - 1) * 5 + r], bim ? bim[(i - 1) * 5 + r] : 0.0);
     if (valid) ws.vec[buf][s][r] = x;
     __syncwarp();
     double2 u = make_double2(0.0, 0.0);
@@ -455,8 +455,8 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
 #pragma unroll
       for (int m = 0; m < 5; ++m) acc = cfma(Sr[m], ws.vec[buf][s][m], acc);
       x = acc;
-      bre[r * N + i] = x.x;
-      if (bim) bim[r * N + i] = x.y;
+      bre[i * 5 + r] = x.x;
+      if (bim) bim[i * 5 + r] = x.y;
     }
     buf ^= 1;
     __syncwarp();
@@ -472,7 +472,7 @@ __device__ __noinline__ void monitors(const ColumnConsts& kc, const fm::Tables& 
                                       const double* q, double x, double* g) {
   const int n = 5 * N;
   auto val = [&](int f, int i) -> double {
-    const int idx = f * N + i;
+    const int idx = i * 5 + f;
     return q ? y0[idx] + x * (q[idx] + x * (q[n + idx] + x * q[2 * n + idx])) : y0[idx];
   };
   const double inf = (double)INFINITY;
@@ -544,9 +544,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
     if (col >= A.n_columns) break;
 
     // ---- column set-up
-    double* const y = A.g_y + (size_t)col * n;
+    // Inside the kernel every per-column vector is CELL-major ([cell][field]): the block-Thomas sweeps read
+    // the five entries of a cell from one 40-byte run instead of five sectors, the RHS reads a thread's two
+    // cells as one 80-byte run, element-wise loops are unit stride.  The caller's y / snapshots stay
+    // field-major (the reference's layout); they are transposed on the way in and out.
+    double* const gy = A.g_y + (size_t)col * n;
     double* wbase = A.g_work + (size_t)col * work_doubles(N);
     Work w;
+    w.y = wbase;                  wbase += 2 * n;          // (+ n of padding keeps the offsets below 16-byte aligned)
+    double* const y = w.y;
     w.yold = wbase;               wbase += n;
     w.f = wbase;                  wbase += n;
     w.Z = wbase;                  wbase += 3 * n;
@@ -558,6 +564,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
     w.J = wbase;                  wbase += 76 * (size_t)N;
     w.Sinv = reinterpret_cast<double2*>(wbase);
     if (lane == 0) make_consts(A.g_params[col], N, ws.kc);
+#pragma unroll 1
+    for (int idx = lane; idx < n; idx += 32) y[idx] = gy[(idx % 5) * N + idx / 5];
     __syncwarp();
     const ColumnConsts& kc = ws.kc;
     marlpde_column_state st = A.g_state[col];
@@ -827,10 +835,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
         const double xx = (te - t_old) / h_old;
         double* snap = A.g_snap + ((size_t)col * A.opt.n_eval + next_eval) * n;
         _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32)
-          snap[idx] = w.yold[idx] + xx * (w.Q[idx] + xx * (w.Q[n + idx] + xx * w.Q[2 * n + idx]));
+          snap[(idx % 5) * N + idx / 5] = w.yold[idx] + xx * (w.Q[idx] + xx * (w.Q[n + idx] + xx * w.Q[2 * n + idx]));
         ++next_eval;
       }
     }
+#pragma unroll 1
+    for (int idx = lane; idx < n; idx += 32) gy[(idx % 5) * N + idx / 5] = y[idx];
     if (lane == 0) {
       st.t = t;
       st.h_abs = h_attr;

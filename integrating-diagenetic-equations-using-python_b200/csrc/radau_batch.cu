@@ -91,7 +91,7 @@ constexpr int kSlots = kDepth + 1;
 // per-column workspace, in doubles (n = 5 N): see radau_workspace_doubles()
 struct Work {
   double *y, *yold, *f, *Z, *W, *B, *Q, *err, *tmp;   // n, n, n, 3n, 3n, 3n, 3n, n, n  — all CELL-major [cell][field]
-  double* J;                                       // [N][3][5][5]  (L, D, U blocks of the Jacobian)
+  double* J;                                       // [N][3][5][5]  (L, D, U blocks of the Jacobian, each column-major)
   double2* Sinv;                                   // [2][N][5][5]  inverse Schur complements, both systems
 };
 
@@ -199,7 +199,7 @@ __device__ __noinline__ void rhs_eval(const ColumnConsts* kc, const fm::Tables* 
     const double inv = 1.0 / fd_step(y0[j * 5 + fld], f0[j * 5 + fld], atol);
     double* blk = out + (size_t)i * 75 + (d == 0 ? 25 : (d == 1 ? 50 : 0));
 #pragma unroll
-    for (int r = 0; r < 5; ++r) blk[r * 5 + fld] = (r5[r] - f0[i * 5 + r]) * inv;
+    for (int r = 0; r < 5; ++r) blk[fld * 5 + r] = (r5[r] - f0[i * 5 + r]) * inv;   // blocks are COLUMN-major: one 40-byte run
   };
   rhs_column(*kc, *tb, N, lane, ld, sink);
   __syncwarp();
@@ -215,8 +215,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __noinline__ void fd_jacobian(const ColumnConsts& kc, const fm::Tables& tb, int N, int lane, const double* y,
                                          const double* f, double atol, double* J, double* pert) {
   const int n = 5 * N;
-#pragma unroll 1
-  for (int i = lane; i < 75 * N; i += 32) J[i] = 0.0;     // L_0 and U_{N-1} stay zero
+  // every block column is written by exactly one colour, except L_0 and U_{N-1} (no neighbour): those are zero
+  if (lane < 25) {
+    J[lane] = 0.0;
+    J[(size_t)(N - 1) * 75 + 50 + lane] = 0.0;
+  }
 #pragma unroll 1
   for (int idx = lane; idx < n; idx += 32) pert[idx] = y[idx];
   __syncwarp();
@@ -279,9 +282,9 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
       // column c5 of S = M I - D_i - L_i X_{i-1} e_c   (X_{-1} = 0)
 #pragma unroll
       for (int r = 0; r < 5; ++r) {
-        double2 acc = make_double2((r == c5 ? M.x : 0.0) - Ji[25 + r * 5 + c5], r == c5 ? M.y : 0.0);
+        double2 acc = make_double2((r == c5 ? M.x : 0.0) - Ji[25 + c5 * 5 + r], r == c5 ? M.y : 0.0);
 #pragma unroll
-        for (int m = 0; m < 5; ++m) acc = crfma(-Ji[r * 5 + m], xcol[m], acc);
+        for (int m = 0; m < 5; ++m) acc = crfma(-Ji[m * 5 + r], xcol[m], acc);
         col[r] = acc;
       }
     } else {
@@ -347,7 +350,7 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
       for (int r = 0; r < 5; ++r) {
         double2 acc = make_double2(0.0, 0.0);
 #pragma unroll
-        for (int m = 0; m < 5; ++m) acc = crfma(Ji[50 + m * 5 + c5], ws.sinv_prev[s][r * 5 + m], acc);
+        for (int m = 0; m < 5; ++m) acc = crfma(Ji[50 + c5 * 5 + m], ws.sinv_prev[s][r * 5 + m], acc);
         xcol[r] = acc;
       }
     }
@@ -407,7 +410,7 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
     __syncwarp();
     if (valid && i > 0) {
 #pragma unroll
-      for (int m = 0; m < 5; ++m) g = crfma(M[r * 5 + m], ws.vec[buf][s][m], g);
+      for (int m = 0; m < 5; ++m) g = crfma(M[m * 5 + r], ws.vec[buf][s][m], g);
     }
     buf ^= 1;
     if (valid) ws.vec[buf][s][r] = g;
@@ -444,7 +447,7 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
     double2 u = make_double2(0.0, 0.0);
     if (valid) {
 #pragma unroll
-      for (int m = 0; m < 5; ++m) u = crfma(M[r * 5 + m], ws.vec[buf][s][m], u);
+      for (int m = 0; m < 5; ++m) u = crfma(M[m * 5 + r], ws.vec[buf][s][m], u);
     }
     buf ^= 1;
     if (valid) ws.vec[buf][s][r] = u;

@@ -85,6 +85,21 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+// Tuning switches, all measured on 4096 columns (r01c, baseline 2.48 s to t = 0.05) and left OFF: with 16 columns
+// per SM in flight the kernel is bound by DRAM traffic (1.6-1.8 TB/s of 1-kB runs), so more loads in flight lose:
+//   RADAU_BATCH4 (four strides of loads per trip of the element-wise passes) 2.68 s,
+//   RADAU_PF_RHS (L1 prefetch of the next 32 cell pairs of an RHS evaluation) 2.55 s,
+//   RADAU_PF_SOLVE (L1 prefetch of the right-hand side 8 cells ahead in the sweeps) 2.57 s.
+#ifndef RADAU_PF_RHS
+#define RADAU_PF_RHS 0
+#endif
+#ifndef RADAU_PF_SOLVE
+#define RADAU_PF_SOLVE 0
+#endif
+#ifndef RADAU_BATCH4
+#define RADAU_BATCH4 0
+#endif
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 constexpr int kDepth = 3;          // cells in flight ahead of the one being processed
 constexpr int kSlots = kDepth + 1;
 
@@ -124,17 +139,31 @@ struct Args {
   marlpde_rk45_options opt;
 };
 
-// One RHS evaluation of the whole column by one warp.  ld(f, i) returns the state value of field f
-// in cell i; sink(i, r5) receives the five rates of cell i.  All 32 lanes run every iteration
-// (rhs_pair votes), lanes without a pair work on benign values.
-template <class Load, class Sink>
-__device__ __forceinline__ void rhs_column(const ColumnConsts& kc, const fm::Tables& tb, int N, int lane, Load&& ld,
-                                           Sink&& sink) {
+// One RHS evaluation of the whole column by one warp: state = yy (+ add, may be NULL), both cell-major
+// [cell][field]; sink(i, r5) receives the five rates of cell i.  All 32 lanes run every iteration
+// (rhs_pair votes), lanes without a pair work on benign values.  The 160-byte runs the NEXT 32 pairs
+// will read can be prefetched into L1 while the current ones are evaluated (RADAU_PF_RHS; off, see the switches).
+template <class Sink>
+__device__ __forceinline__ void rhs_column(const ColumnConsts& kc, const fm::Tables& tb, int N, int lane,
+                                           const double* yy, const double* add, Sink&& sink) {
   const int Hc = (N + 1) >> 1;
+  auto ld = [&](int ff, int i) -> double { return add ? yy[i * 5 + ff] + add[i * 5 + ff] : yy[i * 5 + ff]; };
 #pragma unroll 1
   for (int base = 0; base < Hc; base += 32) {
     const int p = base + lane;
     const int cell0 = 2 * p;
+    if (RADAU_PF_RHS && base + 32 < Hc) {
+      const int cn = 2 * (p + 32) - 1;                      // first cell the next iteration touches
+      if (cn < N) {
+        const size_t o = (size_t)cn * 5, o2 = o + 16 < (size_t)5 * N ? o + 16 : o;   // stay inside the vector
+        prefetch_l1(yy + o);
+        prefetch_l1(yy + o2);
+        if (add) {
+          prefetch_l1(add + o);
+          prefetch_l1(add + o2);
+        }
+      }
+    }
     const bool v0 = cell0 < N, v1 = cell0 + 1 < N;
     double c[5][2], mlo[5], phi[5];
 #pragma unroll
@@ -186,7 +215,6 @@ __device__ __forceinline__ double fd_step(double y, double f, double atol) {
 __device__ __noinline__ void rhs_eval(const ColumnConsts* kc, const fm::Tables* tb, int N, int lane, const double* yy,
                                       const double* add, double* out, int fld, int c3, const double* y0,
                                       const double* f0, double atol) {
-  auto ld = [&](int ff, int i) -> double { return add ? yy[i * 5 + ff] + add[i * 5 + ff] : yy[i * 5 + ff]; };
   auto sink = [&](int i, const double (&r5)[5]) {
     if (fld < 0) {
 #pragma unroll
@@ -201,7 +229,7 @@ __device__ __noinline__ void rhs_eval(const ColumnConsts* kc, const fm::Tables* 
 #pragma unroll
     for (int r = 0; r < 5; ++r) blk[fld * 5 + r] = (r5[r] - f0[i * 5 + r]) * inv;   // blocks are COLUMN-major: one 40-byte run
   };
-  rhs_column(*kc, *tb, N, lane, ld, sink);
+  rhs_column(*kc, *tb, N, lane, yy, add, sink);
   __syncwarp();
 }
 
@@ -404,6 +432,10 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
     __syncwarp();
     const double* M = ws.mst[i % kSlots];
     const bool more = i + 1 < N;
+    if (RADAU_PF_SOLVE && valid && r == 0 && i + 8 < N) {
+      prefetch_l1(bre + (i + 8) * 5);
+      if (bim) prefetch_l1(bim + (i + 8) * 5);
+    }
     double2 g = bnext;
     if (valid && more) bnext = make_double2(bre[(i + 1) * 5 + r], bim ? bim[(i + 1) * 5 + r] : 0.0);
     if (valid) ws.vec[buf][s][r] = p;
@@ -440,6 +472,10 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
     __syncwarp();
     const double* M = ws.mst[j % kSlots];
     const bool more = i > 0;
+    if (RADAU_PF_SOLVE && valid && r == 0 && i >= 8) {
+      prefetch_l1(bre + (i - 8) * 5);
+      if (bim) prefetch_l1(bim + (i - 8) * 5);
+    }
     const double2 pi = bnext;
     if (valid && more) bnext = make_double2(bre[(i - 1) * 5 + r], bim ? bim[(i - 1) * 5 + r] : 0.0);
     if (valid) ws.vec[buf][s][r] = x;
@@ -668,39 +704,74 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
             eval_to(y, w.Z + 2 * n, w.B + 2 * n);
             nfev += 3;
             bool finite = true;
-            _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
-              const double F0 = w.B[idx], F1 = w.B[n + idx], F2 = w.B[2 * n + idx];
-              finite = finite && isfinite(F0) && isfinite(F1) && isfinite(F2);
-              const double W0 = w.W[idx], W1 = w.W[n + idx], W2 = w.W[2 * n + idx];
-              // f_real = F^T TI_REAL - M_real W0 ; f_complex = F^T TI_COMPLEX - M_complex (W1 + i W2)
-              w.B[idx] = kTI[0][0] * F0 + kTI[0][1] * F1 + kTI[0][2] * F2 - Mr * W0;
-              w.B[n + idx] = kTI[1][0] * F0 + kTI[1][1] * F1 + kTI[1][2] * F2 - (Mcr * W1 - Mci * W2);
-              w.B[2 * n + idx] = kTI[2][0] * F0 + kTI[2][1] * F1 + kTI[2][2] * F2 - (Mcr * W2 + Mci * W1);
+            // (element-wise passes; RADAU_BATCH4 issues 4 strides of loads per trip)
+#pragma unroll 1
+            for (int base = lane; base < n; base += (RADAU_BATCH4 ? 128 : 32)) {
+              double F0[4], F1[4], F2[4], W0[4], W1[4], W2[4];
+#pragma unroll
+              for (int u = 0; u < (RADAU_BATCH4 ? 4 : 1); ++u) {
+                const int idx = base + 32 * u;
+                const bool ok = idx < n;
+                F0[u] = ok ? w.B[idx] : 0.0;
+                F1[u] = ok ? w.B[n + idx] : 0.0;
+                F2[u] = ok ? w.B[2 * n + idx] : 0.0;
+                W0[u] = ok ? w.W[idx] : 0.0;
+                W1[u] = ok ? w.W[n + idx] : 0.0;
+                W2[u] = ok ? w.W[2 * n + idx] : 0.0;
+              }
+#pragma unroll
+              for (int u = 0; u < (RADAU_BATCH4 ? 4 : 1); ++u) {
+                const int idx = base + 32 * u;
+                if (idx >= n) continue;
+                finite = finite && isfinite(F0[u]) && isfinite(F1[u]) && isfinite(F2[u]);
+                // f_real = F^T TI_REAL - M_real W0 ; f_complex = F^T TI_COMPLEX - M_complex (W1 + i W2)
+                w.B[idx] = kTI[0][0] * F0[u] + kTI[0][1] * F1[u] + kTI[0][2] * F2[u] - Mr * W0[u];
+                w.B[n + idx] = kTI[1][0] * F0[u] + kTI[1][1] * F1[u] + kTI[1][2] * F2[u] - (Mcr * W1[u] - Mci * W2[u]);
+                w.B[2 * n + idx] = kTI[2][0] * F0[u] + kTI[2][1] * F1[u] + kTI[2][2] * F2[u] - (Mcr * W2[u] + Mci * W1[u]);
+              }
             }
             __syncwarp();
             if (!__all_sync(0xffffffffu, finite)) break;
             solve(ws, N, lane, w.J, w.Sinv, w.B, w.B + n, w.B + 2 * n, true);
+            // norm(dW / scale) and, in the same pass, W += dW, Z = T W.  (radau.py leaves W and Z untouched when
+            // the rate test below breaks; they are dead then — every continuation re-initialises them from Z0.)
             double ss = 0.0;
-            _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
-              const double sc = fma(fabs(y[idx]), rtol, atol);
-              const double a0 = w.B[idx] / sc, a1 = w.B[n + idx] / sc, a2 = w.B[2 * n + idx] / sc;
-              ss += a0 * a0 + a1 * a1 + a2 * a2;
+#pragma unroll 1
+            for (int base = lane; base < n; base += (RADAU_BATCH4 ? 128 : 32)) {
+              double d0[4], d1[4], d2[4], yy4[4], W0[4], W1[4], W2[4];
+#pragma unroll
+              for (int u = 0; u < (RADAU_BATCH4 ? 4 : 1); ++u) {
+                const int idx = base + 32 * u;
+                const bool ok = idx < n;
+                d0[u] = ok ? w.B[idx] : 0.0;
+                d1[u] = ok ? w.B[n + idx] : 0.0;
+                d2[u] = ok ? w.B[2 * n + idx] : 0.0;
+                yy4[u] = ok ? y[idx] : 0.0;
+                W0[u] = ok ? w.W[idx] : 0.0;
+                W1[u] = ok ? w.W[n + idx] : 0.0;
+                W2[u] = ok ? w.W[2 * n + idx] : 0.0;
+              }
+#pragma unroll
+              for (int u = 0; u < (RADAU_BATCH4 ? 4 : 1); ++u) {
+                const int idx = base + 32 * u;
+                if (idx >= n) continue;
+                const double sc = fma(fabs(yy4[u]), rtol, atol);
+                const double a0 = d0[u] / sc, a1 = d1[u] / sc, a2 = d2[u] / sc;
+                ss += a0 * a0 + a1 * a1 + a2 * a2;
+                const double V0 = W0[u] + d0[u], V1 = W1[u] + d1[u], V2 = W2[u] + d2[u];
+                w.W[idx] = V0;
+                w.W[n + idx] = V1;
+                w.W[2 * n + idx] = V2;
+#pragma unroll
+                for (int sgi = 0; sgi < 3; ++sgi) w.Z[sgi * n + idx] = kT[sgi][0] * V0 + kT[sgi][1] * V1 + kT[sgi][2] * V2;
+              }
             }
+            __syncwarp();
             const double dW_norm = sqrt(warp_sum(ss) / (double)(3 * n));
             if (dW_norm_old >= 0.0) rate = dW_norm / dW_norm_old;
             double rate_pow = rate;                     // rate ** (NEWTON_MAXITER - k)
             for (int e = 1; e < kNewtonMaxIter - k; ++e) rate_pow *= rate;
             if (rate >= 0.0 && (rate >= 1.0 || rate_pow / (1.0 - rate) * dW_norm > newton_tol)) break;
-            _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
-              const double W0 = w.W[idx] + w.B[idx], W1 = w.W[n + idx] + w.B[n + idx],
-                           W2 = w.W[2 * n + idx] + w.B[2 * n + idx];
-              w.W[idx] = W0;
-              w.W[n + idx] = W1;
-              w.W[2 * n + idx] = W2;
-#pragma unroll
-              for (int sgi = 0; sgi < 3; ++sgi) w.Z[sgi * n + idx] = kT[sgi][0] * W0 + kT[sgi][1] * W1 + kT[sgi][2] * W2;
-            }
-            __syncwarp();
             if (dW_norm == 0.0 || (rate >= 0.0 && rate / (1.0 - rate) * dW_norm < newton_tol)) {
               converged = true;
               break;

@@ -107,12 +107,14 @@ constexpr int kSlots = kDepth + 1;
 struct Work {
   double *y, *yold, *f, *Z, *W, *B, *Q, *err, *tmp;   // n, n, n, 3n, 3n, 3n, 3n, n, n  — all CELL-major [cell][field]
   double* J;                                       // [N][3][5][5]  (L, D, U blocks of the Jacobian, each column-major)
-  double2* Sinv;                                   // [2][N][5][5]  inverse Schur complements, both systems
+  float2* Sinv;                                    // [2][N][5][5]  inverse Schur complements, both systems, FP32:
+                                                   // they only precondition the simplified Newton iteration (the
+                                                   // residual is fp64), and the sweeps are bound by their bytes
 };
 
 __host__ __device__ inline size_t work_doubles(int N) {
   const size_t n = 5 * (size_t)N;
-  return 18 * n + 76 * (size_t)N + 2 * 2 * 25 * (size_t)N;   // 76: keeps the double2 array 16-byte aligned
+  return 18 * n + 76 * (size_t)N + 2 * 25 * (size_t)N;   // 76: keeps the double2 array 16-byte aligned
 }
 
 struct __align__(16) WarpScratch {          // shared memory per warp
@@ -121,7 +123,7 @@ struct __align__(16) WarpScratch {          // shared memory per warp
   double2 vec[2][2][8];       // two broadcast buffers x two systems x 5 entries (padded)
   double2 mult[2][8];         // Gauss-Jordan multipliers of the pivot column, + pivot row index in [5].x
   double jst[kSlots][80];     // factorise: staged Jacobian blocks [L|D|U] of cells i .. i+kDepth (ring)
-  double mst[kSlots][128];    // solve: staged {J block, S^-1 sys 0, S^-1 sys 1} of cells i .. i+kDepth (16-byte aligned)
+  double mst[kSlots][80];     // solve: staged {J block fp64, S^-1 sys 0, S^-1 sys 1 as float2} of cells i .. i+kDepth
 };
 
 struct Args {
@@ -277,13 +279,13 @@ __device__ __noinline__ void fd_jacobian(const ColumnConsts& kc, const fm::Table
 // eliminated, and hand them over through a double-buffered shared-memory stage.  The product
 // X_i = S_i^{-1} U_i needed by the next cell is formed while U_i is still staged and stays in
 // registers (lane (s, c) keeps column c).
-__device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double h, const double* J, double2* Sinv) {
+__device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double h, const double* J, float2* Sinv) {
   const int s = lane >> 4, cc = lane & 15;
   const bool valid = cc < 10;
   const bool apart = cc < 5;
   const int c5 = apart ? cc : cc - 5;
   const double2 M = s == 0 ? make_double2(kMuReal / h, 0.0) : make_double2(kMuCRe / h, kMuCIm / h);
-  double2* const out = Sinv + (size_t)s * N * 25;
+  float2* const out = Sinv + (size_t)s * N * 25;
   // ring of kSlots staged cells: cells 0 .. kDepth-1 are requested up front, cell i+kDepth at iteration i
   auto request = [&](int cell) {
     if (cell < N) {
@@ -368,7 +370,7 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
 #pragma unroll
         for (int r = 1; r < 5; ++r) v = (pk == r) ? col[r] : v;
         ws.sinv_prev[s][k * 5 + c5] = v;
-        out[(size_t)i * 25 + k * 5 + c5] = v;
+        out[(size_t)i * 25 + k * 5 + c5] = make_float2((float)v.x, (float)v.y);
       }
     }
     __syncwarp();
@@ -394,28 +396,28 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
 // As in factorise(), the matrices of the NEXT cell (one real 5x5 block of J and S^{-1} of both
 // systems, 125 doubles) are fetched by all 32 lanes while the current cell is processed and handed
 // over through shared memory; the right-hand side entry of the next cell is prefetched as well.
-__device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const double* J, const double2* Sinv, double* b0,
+__device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const double* J, const float2* Sinv, double* b0,
                                    double* b1, double* b2, bool both) {
   const int s = (lane >> 3) & 1, r = lane & 7;
   const bool valid = lane < 16 && r < 5 && (s == 0 || both);
   double* const bre = s == 0 ? b0 : b1;
   double* const bim = s == 0 ? nullptr : b2;
-  const double* S0 = reinterpret_cast<const double*>(Sinv);
+  const double* S0 = reinterpret_cast<const double*>(Sinv);                       // 25 float2 = 25 eight-byte words
   const double* S1 = reinterpret_cast<const double*>(Sinv + (size_t)N * 25);
-  // element e of the staged record of cell i: [0,25) J block (L forward / U backward), [26,76) S^{-1}
-  // of system 0, [76,126) S^{-1} of system 1 (offsets keep the double2 reads 16-byte aligned)
+  // eight-byte word e of the staged record of cell i: [0,25) J block (L forward / U backward, fp64),
+  // [25,50) S^{-1} of system 0, [50,75) S^{-1} of system 1 (float2 each)
   auto request = [&](int i, int blk, int slot, bool ok) {
     if (ok) {
       const double* Jb = J + (size_t)i * 75 + blk;
-      const double* s0 = S0 + (size_t)i * 50;
-      const double* s1 = S1 + (size_t)i * 50;
+      const double* s0 = S0 + (size_t)i * 25;
+      const double* s1 = S1 + (size_t)i * 25;
       double* dst = ws.mst[slot];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 3; ++k) {
         const int e = lane + 32 * k;
         if (e < 25) cp_async8(dst + e, Jb + e);
-        else if (e >= 26 && e < 76) cp_async8(dst + e, s0 + (e - 26));
-        else if (e >= 76 && e < 126) cp_async8(dst + e, s1 + (e - 76));
+        else if (e < 50) cp_async8(dst + e, s0 + (e - 25));
+        else if (e < 75) cp_async8(dst + e, s1 + (e - 50));
       }
     }
     cp_async_commit();
@@ -448,10 +450,10 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
     if (valid) ws.vec[buf][s][r] = g;
     __syncwarp();
     if (valid) {
-      const double2* Sr = reinterpret_cast<const double2*>(M + 26 + 50 * s) + r * 5;
+      const float2* Sr = reinterpret_cast<const float2*>(M + 25 + 25 * s) + r * 5;
       double2 acc = make_double2(0.0, 0.0);
 #pragma unroll
-      for (int m = 0; m < 5; ++m) acc = cfma(Sr[m], ws.vec[buf][s][m], acc);
+      for (int m = 0; m < 5; ++m) acc = cfma(make_double2((double)Sr[m].x, (double)Sr[m].y), ws.vec[buf][s][m], acc);
       p = acc;
       bre[i * 5 + r] = p.x;
       if (bim) bim[i * 5 + r] = p.y;
@@ -489,10 +491,10 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
     if (valid) ws.vec[buf][s][r] = u;
     __syncwarp();
     if (valid) {
-      const double2* Sr = reinterpret_cast<const double2*>(M + 26 + 50 * s) + r * 5;
+      const float2* Sr = reinterpret_cast<const float2*>(M + 25 + 25 * s) + r * 5;
       double2 acc = pi;
 #pragma unroll
-      for (int m = 0; m < 5; ++m) acc = cfma(Sr[m], ws.vec[buf][s][m], acc);
+      for (int m = 0; m < 5; ++m) acc = cfma(make_double2((double)Sr[m].x, (double)Sr[m].y), ws.vec[buf][s][m], acc);
       x = acc;
       bre[i * 5 + r] = x.x;
       if (bim) bim[i * 5 + r] = x.y;
@@ -601,7 +603,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
     w.err = wbase;                wbase += n;
     w.tmp = wbase;                wbase += n;
     w.J = wbase;                  wbase += 76 * (size_t)N;
-    w.Sinv = reinterpret_cast<double2*>(wbase);
+    w.Sinv = reinterpret_cast<float2*>(wbase);
     if (lane == 0) make_consts(A.g_params[col], N, ws.kc);
 #pragma unroll 1
     for (int idx = lane; idx < n; idx += 32) y[idx] = gy[(idx % 5) * N + idx / 5];

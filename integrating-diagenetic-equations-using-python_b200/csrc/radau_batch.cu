@@ -107,14 +107,16 @@ constexpr int kSlots = kDepth + 1;
 struct Work {
   double *y, *yold, *f, *Z, *W, *B, *Q, *err, *tmp;   // n, n, n, 3n, 3n, 3n, 3n, n, n  — all CELL-major [cell][field]
   double* J;                                       // [N][3][5][5]  (L, D, U blocks of the Jacobian, each column-major)
-  float2* Sinv;                                    // [2][N][5][5]  inverse Schur complements, both systems, FP32:
-                                                   // they only precondition the simplified Newton iteration (the
-                                                   // residual is fp64), and the sweeps are bound by their bytes
+  float* Rec;                                      // [N][128] what the sweeps read, FP32, one 512-byte record per cell:
+                                                   // [0,25) L_i | [26,51) S_i^-1 of the real system (real) | [52,102)
+                                                   // S_i^-1 of the complex system (float2) | [102,127) U_i, blocks column-
+                                                   // major.  They only precondition the simplified Newton iteration (the
+                                                   // residual is fp64) and the sweeps are bound by their bytes.
 };
 
 __host__ __device__ inline size_t work_doubles(int N) {
   const size_t n = 5 * (size_t)N;
-  return 18 * n + 76 * (size_t)N + 2 * 25 * (size_t)N;   // 76: keeps the double2 array 16-byte aligned
+  return 18 * n + 76 * (size_t)N + 64 * (size_t)N;   // 76: keeps the double2 array 16-byte aligned
 }
 
 struct __align__(16) WarpScratch {          // shared memory per warp
@@ -123,7 +125,7 @@ struct __align__(16) WarpScratch {          // shared memory per warp
   double2 vec[2][2][8];       // two broadcast buffers x two systems x 5 entries (padded)
   double2 mult[2][8];         // Gauss-Jordan multipliers of the pivot column, + pivot row index in [5].x
   double jst[kSlots][80];     // factorise: staged Jacobian blocks [L|D|U] of cells i .. i+kDepth (ring)
-  double mst[kSlots][80];     // solve: staged {J block fp64, S^-1 sys 0, S^-1 sys 1 as float2} of cells i .. i+kDepth
+  double mst[kSlots][52];     // solve: 51 eight-byte words of a cell's fp32 record, cells i .. i+kDepth
 };
 
 struct Args {
@@ -279,13 +281,12 @@ __device__ __noinline__ void fd_jacobian(const ColumnConsts& kc, const fm::Table
 // eliminated, and hand them over through a double-buffered shared-memory stage.  The product
 // X_i = S_i^{-1} U_i needed by the next cell is formed while U_i is still staged and stays in
 // registers (lane (s, c) keeps column c).
-__device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double h, const double* J, float2* Sinv) {
+__device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double h, const double* J, float* Rec) {
   const int s = lane >> 4, cc = lane & 15;
   const bool valid = cc < 10;
   const bool apart = cc < 5;
   const int c5 = apart ? cc : cc - 5;
   const double2 M = s == 0 ? make_double2(kMuReal / h, 0.0) : make_double2(kMuCRe / h, kMuCIm / h);
-  float2* const out = Sinv + (size_t)s * N * 25;
   // ring of kSlots staged cells: cells 0 .. kDepth-1 are requested up front, cell i+kDepth at iteration i
   auto request = [&](int cell) {
     if (cell < N) {
@@ -307,6 +308,11 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
     cp_async_wait<kDepth>();              // all but the kDepth newest groups have landed: cell i is in shared memory
     __syncwarp();
     const double* Ji = ws.jst[i % kSlots];
+    if (lane < 25) {                                         // fp32 copies of L_i and U_i for the sweeps
+      float* rec = Rec + (size_t)i * 128;
+      rec[lane] = (float)Ji[lane];
+      rec[102 + lane] = (float)Ji[50 + lane];
+    }
     double2 col[5];
     if (apart) {
       // column c5 of S = M I - D_i - L_i X_{i-1} e_c   (X_{-1} = 0)
@@ -370,7 +376,9 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
 #pragma unroll
         for (int r = 1; r < 5; ++r) v = (pk == r) ? col[r] : v;
         ws.sinv_prev[s][k * 5 + c5] = v;
-        out[(size_t)i * 25 + k * 5 + c5] = make_float2((float)v.x, (float)v.y);
+        float* rec = Rec + (size_t)i * 128;
+        if (s == 0) rec[26 + k * 5 + c5] = (float)v.x;
+        else reinterpret_cast<float2*>(rec + 52)[k * 5 + c5] = make_float2((float)v.x, (float)v.y);
       }
     }
     __syncwarp();
@@ -396,34 +404,26 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
 // As in factorise(), the matrices of the NEXT cell (one real 5x5 block of J and S^{-1} of both
 // systems, 125 doubles) are fetched by all 32 lanes while the current cell is processed and handed
 // over through shared memory; the right-hand side entry of the next cell is prefetched as well.
-__device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const double* J, const float2* Sinv, double* b0,
+__device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const float* Rec, double* b0,
                                    double* b1, double* b2, bool both) {
   const int s = (lane >> 3) & 1, r = lane & 7;
   const bool valid = lane < 16 && r < 5 && (s == 0 || both);
   double* const bre = s == 0 ? b0 : b1;
   double* const bim = s == 0 ? nullptr : b2;
-  const double* S0 = reinterpret_cast<const double*>(Sinv);                       // 25 float2 = 25 eight-byte words
-  const double* S1 = reinterpret_cast<const double*>(Sinv + (size_t)N * 25);
-  // eight-byte word e of the staged record of cell i: [0,25) J block (L forward / U backward, fp64),
-  // [25,50) S^{-1} of system 0, [50,75) S^{-1} of system 1 (float2 each)
-  auto request = [&](int i, int blk, int slot, bool ok) {
+  // a sweep reads 51 eight-byte words of a cell's record: forward words [0,51) = {L, S0, S1}, backward words
+  // [13,64) = {S0, S1, U} (both runs contiguous, 8-byte aligned)
+  auto request = [&](int i, int first_word, int slot, bool ok) {
     if (ok) {
-      const double* Jb = J + (size_t)i * 75 + blk;
-      const double* s0 = S0 + (size_t)i * 25;
-      const double* s1 = S1 + (size_t)i * 25;
+      const double* src = reinterpret_cast<const double*>(Rec + (size_t)i * 128) + first_word;
       double* dst = ws.mst[slot];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int e = lane + 32 * k;
-        if (e < 25) cp_async8(dst + e, Jb + e);
-        else if (e < 50) cp_async8(dst + e, s0 + (e - 25));
-        else if (e < 75) cp_async8(dst + e, s1 + (e - 50));
-      }
+      cp_async8(dst + lane, src + lane);
+      if (lane + 32 < 51) cp_async8(dst + lane + 32, src + lane + 32);
     }
     cp_async_commit();
   };
   int buf = 0;
   for (int c0 = 0; c0 < kDepth; ++c0) request(c0, 0, c0 % kSlots, c0 < N);
+  // forward record in shared memory (floats): L [0,25), S0 [26,51), S1 float2 from float 52
   // ---- forward: g_i = b_i + L_i p_{i-1},  p_i = S_i^{-1} g_i  (p overwrites b)
   double2 p = make_double2(0.0, 0.0);
   double2 bnext = valid ? make_double2(bre[r], bim ? bim[r] : 0.0) : make_double2(0.0, 0.0);
@@ -432,7 +432,7 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
     request(i + kDepth, 0, (i + kDepth) % kSlots, i + kDepth < N);
     cp_async_wait<kDepth>();
     __syncwarp();
-    const double* M = ws.mst[i % kSlots];
+    const float* M = reinterpret_cast<const float*>(ws.mst[i % kSlots]);
     const bool more = i + 1 < N;
     if (RADAU_PF_SOLVE && valid && r == 0 && i + 8 < N) {
       prefetch_l1(bre + (i + 8) * 5);
@@ -444,16 +444,20 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
     __syncwarp();
     if (valid && i > 0) {
 #pragma unroll
-      for (int m = 0; m < 5; ++m) g = crfma(M[m * 5 + r], ws.vec[buf][s][m], g);
+      for (int m = 0; m < 5; ++m) g = crfma((double)M[m * 5 + r], ws.vec[buf][s][m], g);
     }
     buf ^= 1;
     if (valid) ws.vec[buf][s][r] = g;
     __syncwarp();
     if (valid) {
-      const float2* Sr = reinterpret_cast<const float2*>(M + 25 + 25 * s) + r * 5;
+      const float* S0r = M + 26 + r * 5;
+      const float2* S1r = reinterpret_cast<const float2*>(M + 52) + r * 5;
       double2 acc = make_double2(0.0, 0.0);
 #pragma unroll
-      for (int m = 0; m < 5; ++m) acc = cfma(make_double2((double)Sr[m].x, (double)Sr[m].y), ws.vec[buf][s][m], acc);
+      for (int m = 0; m < 5; ++m) {
+        const double2 sv = s == 0 ? make_double2((double)S0r[m], 0.0) : make_double2((double)S1r[m].x, (double)S1r[m].y);
+        acc = cfma(sv, ws.vec[buf][s][m], acc);
+      }
       p = acc;
       bre[i * 5 + r] = p.x;
       if (bim) bim[i * 5 + r] = p.y;
@@ -464,15 +468,16 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
   cp_async_wait<0>();
   if (N < 2) return;
   // ---- backward: x_{N-1} = p_{N-1},  x_i = p_i + S_i^{-1} (U_i x_{i+1});  step j handles cell N-2-j
-  for (int c0 = 0; c0 < kDepth; ++c0) request(N - 2 - c0, 50, c0 % kSlots, N - 2 - c0 >= 0);
+  // backward record in shared memory (floats): S0 [0,25), S1 float2 from float 26, U [76,101)
+  for (int c0 = 0; c0 < kDepth; ++c0) request(N - 2 - c0 < 0 ? 0 : N - 2 - c0, 13, c0 % kSlots, N - 2 - c0 >= 0);
   double2 x = p;
   bnext = valid ? make_double2(bre[(N - 2) * 5 + r], bim ? bim[(N - 2) * 5 + r] : 0.0) : make_double2(0.0, 0.0);
 #pragma unroll 1
   for (int i = N - 2, j = 0; i >= 0; --i, ++j) {
-    request(i - kDepth, 50, (j + kDepth) % kSlots, i - kDepth >= 0);
+    request(i - kDepth < 0 ? 0 : i - kDepth, 13, (j + kDepth) % kSlots, i - kDepth >= 0);
     cp_async_wait<kDepth>();
     __syncwarp();
-    const double* M = ws.mst[j % kSlots];
+    const float* M = reinterpret_cast<const float*>(ws.mst[j % kSlots]);
     const bool more = i > 0;
     if (RADAU_PF_SOLVE && valid && r == 0 && i >= 8) {
       prefetch_l1(bre + (i - 8) * 5);
@@ -485,16 +490,20 @@ __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const doubl
     double2 u = make_double2(0.0, 0.0);
     if (valid) {
 #pragma unroll
-      for (int m = 0; m < 5; ++m) u = crfma(M[m * 5 + r], ws.vec[buf][s][m], u);
+      for (int m = 0; m < 5; ++m) u = crfma((double)M[76 + m * 5 + r], ws.vec[buf][s][m], u);
     }
     buf ^= 1;
     if (valid) ws.vec[buf][s][r] = u;
     __syncwarp();
     if (valid) {
-      const float2* Sr = reinterpret_cast<const float2*>(M + 25 + 25 * s) + r * 5;
+      const float* S0r = M + r * 5;
+      const float2* S1r = reinterpret_cast<const float2*>(M + 26) + r * 5;
       double2 acc = pi;
 #pragma unroll
-      for (int m = 0; m < 5; ++m) acc = cfma(make_double2((double)Sr[m].x, (double)Sr[m].y), ws.vec[buf][s][m], acc);
+      for (int m = 0; m < 5; ++m) {
+        const double2 sv = s == 0 ? make_double2((double)S0r[m], 0.0) : make_double2((double)S1r[m].x, (double)S1r[m].y);
+        acc = cfma(sv, ws.vec[buf][s][m], acc);
+      }
       x = acc;
       bre[i * 5 + r] = x.x;
       if (bim) bim[i * 5 + r] = x.y;
@@ -603,7 +612,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
     w.err = wbase;                wbase += n;
     w.tmp = wbase;                wbase += n;
     w.J = wbase;                  wbase += 76 * (size_t)N;
-    w.Sinv = reinterpret_cast<float2*>(wbase);
+    w.Rec = reinterpret_cast<float*>(wbase);
     if (lane == 0) make_consts(A.g_params[col], N, ws.kc);
 #pragma unroll 1
     for (int idx = lane; idx < n; idx += 32) y[idx] = gy[(idx % 5) * N + idx / 5];
@@ -671,7 +680,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
         bool converged = false;
         for (;;) {
           if (!lu_valid) {                 // (radau.py keeps the factors while the step-size factor is 1)
-            factorise(ws, N, lane, h, w.J, w.Sinv);
+            factorise(ws, N, lane, h, w.J, w.Rec);
             nlu += 2;
             lu_valid = true;
           }
@@ -734,7 +743,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
             }
             __syncwarp();
             if (!__all_sync(0xffffffffu, finite)) break;
-            solve(ws, N, lane, w.J, w.Sinv, w.B, w.B + n, w.B + 2 * n, true);
+            solve(ws, N, lane, w.Rec, w.B, w.B + n, w.B + 2 * n, true);
             // norm(dW / scale) and, in the same pass, W += dW, Z = T W.  (radau.py leaves W and Z untouched when
             // the rate test below breaks; they are dead then — every continuation re-initialises them from Z0.)
             double ss = 0.0;
@@ -803,7 +812,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
           w.err[idx] = w.f[idx] + ze;
         }
         __syncwarp();
-        solve(ws, N, lane, w.J, w.Sinv, w.err, nullptr, nullptr, false);
+        solve(ws, N, lane, w.Rec, w.err, nullptr, nullptr, false);
         auto err_norm_of = [&]() {
           double ss = 0.0;
           _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
@@ -822,7 +831,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
           nfev += 1;
           _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) w.err[idx] = w.B[idx] + w.tmp[idx];
           __syncwarp();
-          solve(ws, N, lane, w.J, w.Sinv, w.err, nullptr, nullptr, false);
+          solve(ws, N, lane, w.Rec, w.err, nullptr, nullptr, false);
           error_norm = err_norm_of();
         }
         if (error_norm > 1.0 || !(error_norm == error_norm)) {

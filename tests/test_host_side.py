@@ -142,4 +142,4 @@ def test_argument_validation_before_any_device_work():
     rc = _cabi.lib().marlpde_rk45_integrate(None, None, None, 1, 1000, ctypes.byref(opts), None, None, None, None, 0)
     assert rc == -4 and b"events" in _cabi.lib().marlpde_last_error()
     assert _cabi.lib().marlpde_rk45_stream_workspace_bytes(64, 20000) > 9 * 64 * 5 * 20000 * 8
-    assert _cabi.lib().marlpde_radau_workspace_bytes(1, 200) == 8 * 200 * (90 + 76 + 50)
+    assert _cabi.lib().marlpde_radau_workspace_bytes(1, 200) == 8 * 200 * (90 + 76 + 64)

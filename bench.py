@@ -416,9 +416,9 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             torch.cuda.synchronize()
             secs = l0.elapsed_time(l1) * 1e-3
             tiles_mode = os.environ.get("MARLPDE_RK45_STREAM", "tiles")[0] != "s"
-            # algorithmic HBM bytes per cell and attempt: overlapped tiles read y, K1 and write y_new, K7, the
-            # commit copies y_new -> y (6 vector passes x 40 B); one launch per stage moves 42 passes
-            per_cell = 240.0 if tiles_mode else 1680.0
+            # algorithmic HBM bytes per cell and attempt: overlapped tiles read y, K1 and write y_new, K7
+            # (4 vector passes x 40 B; y ping-pongs between two buffers); one launch per stage moves 42 passes
+            per_cell = 160.0 if tiles_mode else 1680.0
             alg_bytes = per_cell * nL * bL * attL
             flops = FLOP_PER_COLUMN_STEP_PER_CELL * float(nL) * bL * attL
             large[f"N{nL}_B{bL}"] = {"n_cells": nL, "columns": bL, "attempts_per_column": attL, "seconds": secs,

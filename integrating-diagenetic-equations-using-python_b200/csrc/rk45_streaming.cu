@@ -49,6 +49,8 @@ struct Ctl {                                   // per-column control block (doub
   int k1, k7;                                  // physical slots of K1 and K7 (0 or 6)
   int fresh;                                   // 1: K1 has just been evaluated, no attempt finished yet
   int midstep;                                 // resumed inside a step (after a rejected attempt)
+  int ysl;                                     // tile path: which buffer holds y (0: caller's y, 1: workspace vector 0)
+  int pad;
 };
 
 struct Args {
@@ -127,6 +129,8 @@ __global__ void init_kernel(const Args A) {
   c.fresh = 1;
   c.midstep = s.status == MARLPDE_STATUS_STEP_BUDGET_MIDSTEP ? 1 : 0;
   c.rejected = c.midstep;
+  c.ysl = 0;
+  c.pad = 0;
   if (s.t >= A.opt.t_bound) {
     c.active = 0;
     c.status = MARLPDE_STATUS_FINISHED;
@@ -167,6 +171,10 @@ __device__ __forceinline__ Cells my_cells(const Args& A) {
   return m;
 }
 
+// tile path: y ping-pongs between the caller's array and workspace vector 0 (an accepted step flips the index
+// instead of copying y_new over y); the per-stage path keeps y in the caller's array
+__device__ __forceinline__ double* ybuf(const Args& A, int sl) { return sl ? A.tile : A.y; }
+
 // two adjacent cells of field f from a [B][5][N] vector (N may be odd: no 16-byte loads)
 __device__ __forceinline__ void ld2(const double* v, const Cells& m, int f, int N, double& a, double& b) {
   const double* p = v + m.base + (size_t)f * N;
@@ -177,6 +185,18 @@ __device__ __forceinline__ void st2(double* v, const Cells& m, int f, int N, dou
   double* p = v + m.base + (size_t)f * N;
   if (m.v0) p[0] = a;
   if (m.v1) p[1] = b;
+}
+
+// tile path, end of a call: columns whose y lives in the workspace buffer are copied back to the caller's array
+__global__ void __launch_bounds__(kThreads) copyback_kernel(const Args A, int parity) {
+  const Cells m = my_cells(A);
+  if (A.ctl[(size_t)parity * A.B + m.col].ysl == 0) return;
+#pragma unroll
+  for (int f = 0; f < 5; ++f) {
+    double a, b;
+    ld2(A.tile, m, f, A.N, a, b);
+    st2(A.y, m, f, A.N, a, b);
+  }
 }
 
 // ---- prepare: close the previous attempt of every column (error norm -> accept/reject -> new h,
@@ -227,7 +247,7 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin
           ld2(A.K + 4 * vec, m, f, N, k[3][0], k[3][1]);
           ld2(A.K + 5 * vec, m, f, N, k[4][0], k[4][1]);
           ld2(K7, m, f, N, k[5][0], k[5][1]);
-          ld2(A.y, m, f, N, yv[0], yv[1]);
+          ld2(ybuf(A, c.ysl), m, f, N, yv[0], yv[1]);
           double out[2];
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
@@ -250,12 +270,17 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin
         ++ne;
       }
       c.next_eval = ne;
-      // accept: y <- y_new (stage-6 input, tile 0), K1 <-> K7
+      // accept: y <- y_new, K1 <-> K7.  Tile path: y_new was written to the other y buffer, flip the index;
+      // per-stage path: y_new is the stage-6 input (tile 0), copy it over y
+      if (A.tiles2 > 0) {
+        c.ysl ^= 1;
+      } else {
 #pragma unroll
-      for (int f = 0; f < 5; ++f) {
-        double a, b;
-        ld2(tile0, m, f, N, a, b);
-        st2(A.y, m, f, N, a, b);
+        for (int f = 0; f < 5; ++f) {
+          double a, b;
+          ld2(tile0, m, f, N, a, b);
+          st2(A.y, m, f, N, a, b);
+        }
       }
       const int tmp = c.k1;
       c.k1 = c.k7;
@@ -514,7 +539,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
     const double* K1g = Kslot(1);
 #pragma unroll
     for (int f = 0; f < 5; ++f) {
-      const double* yp = A.y + base + (size_t)f * N;
+      const double* yp = ybuf(A, c0.ysl) + base + (size_t)f * N;
       const double* kp = K1g + base + (size_t)f * N;
       y[f][0] = in0 ? yp[0] : 0.5;
       y[f][1] = in1 ? yp[g0 < 0 ? g0 + 1 : 1] : 0.5;     // (g0 = -2k < 0 never has an in-range partner; kept safe)
@@ -628,7 +653,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
   // ---- r = K7 = f(y_new), c = y_new: error contribution of the cells this window owns, write-back
   const bool sample = c0.next_eval < A.opt.n_eval && A.t_eval[c0.next_eval] <= c0.t_new;   // dense output pending
   double part = 0.0;
-  double* const ynew = A.tile;                               // vector 0 of the stage-input pair
+  double* const ynew = ybuf(A, c0.ysl ^ 1);                  // the y buffer that is not in use
   double* const K7g = Kslot(7);
 #pragma unroll
   for (int f = 0; f < 5; ++f) {
@@ -729,6 +754,7 @@ cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_param
   }
   st::prepare_kernel<<<grid, st::kThreads, 0, stream>>>(a, pin);
   pin ^= 1;
+  if (use_tiles) st::copyback_kernel<<<grid, st::kThreads, 0, stream>>>(a, pin);
   st::finish_kernel<<<cgrid, 128, 0, stream>>>(a, pin);
   return cudaGetLastError();
 }

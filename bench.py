@@ -162,7 +162,7 @@ def run_reference_arm(args, rank: int, world: int):
 def workload_config(args, world: int) -> dict:
     lat = lattice_for(world)
     per_gpu = 4096 if world == 1 else 8192
-    return {"workload": (f"{per_gpu * world}-column Map_Scenario sweep ({'every %d-th column of the ' % (8 // world) if 1 < world < 8 else ''}{lat[0]}x{lat[1]}x{lat[2]} lattice over "
+    return {"workload": (f"{per_gpu * world}-column Map_Scenario sweep ({'one column in every %d of the ' % (8 // world) if 1 < world < 8 else ''}{lat[0]}x{lat[1]}x{lat[2]} lattice over "
                          f"sedimentationrate, b, D0co3; {args.base} base), N=200, RK45 rtol=atol=1e-3, "
                          f"first_step=1e-6; {args.attempts} step attempts per column per bench step, resumed"),
             "columns": per_gpu * world, "columns_per_gpu": per_gpu, "n_cells": 200,

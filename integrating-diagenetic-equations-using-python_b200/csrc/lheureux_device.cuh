@@ -243,57 +243,60 @@ __device__ __forceinline__ void fv_sigma_pair(const fm::Tables& tb, bool fv_on, 
   }
 }
 
-__device__ __forceinline__ PairFlags rhs_pair(const ColumnConsts& k, const fm::Tables& tb, const double (&c)[5][2],
-                                              const double (&mlo)[5], const double (&phi)[5],
-                                              const bool (&in_mask)[2], double (&out)[5][2], double (&Uo)[2],
-                                              double (&Wo)[2]) {
+// Everything of the RHS that needs only the thread's OWN two cells (no neighbour): porosity functions,
+// velocities, Fiadeiro-Veronis weights, reaction terms — about two thirds of the arithmetic.  The
+// integrators evaluate this part while the block barrier that publishes the neighbours' values is
+// still pending (split arrive / wait), then finish with the stencil part below.
+struct OwnTerms {
+  double U[2], W[2], rPhi[2];
+  double sCa[2], sCO3[2], sPhi[2];
+  double h1[2];      // Phi / den
+  double h2c[2];     // (2 + den) / den^2            (h2 = h2c * grad Phi)
+  double dWc[2];     // -rhorat (2 Phi F + 10 (F - 1))   (dW/dx = dWc * grad Phi)
+  double react[2];   // Da (1 - Phi) (coA - lambda coC)
+  double rA[2];      // Da ((1 - CA) coA + lambda CA coC)
+  double rC[2];      // Da (lambda (1 - CC) coC + CC coA)
+};
+
+__device__ __forceinline__ PairFlags rhs_pair_own(const ColumnConsts& k, const fm::Tables& tb, const double (&c)[5][2],
+                                                  const bool (&in_mask)[2], OwnTerms& o) {
   PairFlags fl;
   fl.bad[0] = fl.bad[1] = false;
 
   // ---- porosity-dependent velocities (:414-431)
-  double rPhi[2], F[2], omP[2], U[2], W[2], den[2], rden[2];
+  double F[2], omP[2], den[2];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     const double Phi = c[4][q];
-    rPhi[q] = fm::rcp3(Phi);
-    F[q] = 1.0 - fm::exp_nb(tb, fma(-10.0, rPhi[q], 10.0), fl.bad[q]);
+    o.rPhi[q] = fm::rcp3(Phi);
+    F[q] = 1.0 - fm::exp_nb(tb, fma(-10.0, o.rPhi[q], 10.0), fl.bad[q]);
     omP[q] = 1.0 - Phi;
     const double Phi2 = Phi * Phi;
-    U[q] = fma(k.rhorat * (Phi2 * Phi), F[q] * fm::rcp3(omP[q]), k.presum);
-    W[q] = fma(-k.rhorat * Phi2, F[q], k.presum);
+    o.U[q] = fma(k.rhorat * (Phi2 * Phi), F[q] * fm::rcp3(omP[q]), k.presum);
+    o.W[q] = fma(-k.rhorat * Phi2, F[q], k.presum);
     den[q] = fma(-2.0, fm::log_nb(tb, Phi, fl.bad[q]), 1.0);
-    rden[q] = fm::rcp3(den[q]);
-    Uo[q] = U[q];
-    Wo[q] = W[q];
-  }
-
-  // ---- first differences: a = (next - centre), b = (centre - previous) per field and cell
-  double a[5][2], b[5][2];
-#pragma unroll
-  for (int f = 0; f < 5; ++f) {
-    b[f][0] = c[f][0] - mlo[f];
-    a[f][0] = c[f][1] - c[f][0];
-    b[f][1] = a[f][0];
-    a[f][1] = phi[f] - c[f][1];
+    const double rden = fm::rcp3(den[q]);
+    o.h1[q] = Phi * rden;
+    o.h2c[q] = (2.0 + den[q]) * (rden * rden);
+    o.dWc[q] = -k.rhorat * fma(2.0 * Phi, F[q], 10.0 * (F[q] - 1.0));
   }
 
   // ---- Fiadeiro-Veronis weights (:433-462)
   // (FV_switch is a per-column value and warps straddle columns: it must not guard the votes inside
   //  fv_sigma_pair, so it is folded into the lane predicates instead of branching here.)
-  double sCa[2], sCO3[2], sPhi[2];
   {
     const bool fv_on = k.FV_switch != 0;
     double PeCa[2], PeCO3[2], PePhi[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      const double Wden = W[q] * den[q];
+      const double Wden = o.W[q] * den[q];
       PeCa[q] = Wden * k.kPeCa;
       PeCO3[q] = Wden * k.kPeCO3;
-      PePhi[q] = W[q] * k.kPePhi;
+      PePhi[q] = o.W[q] * k.kPePhi;
     }
-    fv_sigma_pair(tb, fv_on, PeCa, W, k.Pe_min, k.Pe_max, sCa);
-    fv_sigma_pair(tb, fv_on, PeCO3, W, k.Pe_min, k.Pe_max, sCO3);
-    fv_sigma_pair(tb, fv_on, PePhi, W, k.Pe_min, k.Pe_max, sPhi);
+    fv_sigma_pair(tb, fv_on, PeCa, o.W, k.Pe_min, k.Pe_max, o.sCa);
+    fv_sigma_pair(tb, fv_on, PeCO3, o.W, k.Pe_min, k.Pe_max, o.sCO3);
+    fv_sigma_pair(tb, fv_on, PePhi, o.W, k.Pe_min, k.Pe_max, o.sPhi);
   }
 
   // ---- saturation products and the real powers of the rate laws (:479-491)
@@ -322,37 +325,68 @@ __device__ __forceinline__ PairFlags rhs_pair(const ColumnConsts& k, const fm::T
 #pragma unroll
   for (int q = 0; q < 2; ++q) pC[q] = fm::exp_nb(tb, eC[q] * fm::log_nb(tb, xC[q], fl.bad[q]), fl.bad[q]);
 
-  // ---- rates (:464-477, :493-520)
-  const double hdx = 0.5 * k.inv_dx;
+  // ---- reaction terms (:486-493, the Da(...) parts of :498-520)
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
-    const double CA = c[0][q], CC = c[1][q], cCa = c[2][q], cCO3 = c[3][q], Phi = c[4][q];
-    const bool back = U[q] > 0.0;
-    const double gCA = (back ? b[0][q] : a[0][q]) * k.inv_dx;
-    const double gCC = (back ? b[1][q] : a[1][q]) * k.inv_dx;
-    const double d2Ca = a[2][q] - b[2][q], d2CO3 = a[3][q] - b[3][q], d2Phi = a[4][q] - b[4][q];
-    const double gCa = fma(-sCa[q], d2Ca, a[2][q] + b[2][q]) * hdx;
-    const double gCO3 = fma(-sCO3[q], d2CO3, a[3][q] + b[3][q]) * hdx;
-    const double gPhi = fma(-sPhi[q], d2Phi, a[4][q] + b[4][q]) * hdx;
-    const double lapCa = d2Ca * k.inv_dx2, lapCO3 = d2CO3 * k.inv_dx2, lapPhi = d2Phi * k.inv_dx2;
-
-    const double h1 = Phi * rden[q];
-    const double h2 = gPhi * (2.0 + den[q]) * (rden[q] * rden[q]);
-    const double HCa = k.dCa * fma(h2, gCa, h1 * lapCa);
-    const double HCO3 = k.dCO3 * fma(h2, gCO3, h1 * lapCO3);
-
+    const double CA = c[0][q], CC = c[1][q];
     const double coA = ltA[q] ? (in_mask[q] ? CA * pA[q] : CA * 0.0) : -CA * k.nu1 * pA[q];
     const double coC = ltC[q] ? -CC * k.nu2 * pC[q] : CC * pC[q];
     const double h3 = fma(-k.lambda_, coC, coA);
-    const double dWdx = -k.rhorat * gPhi * fma(2.0 * Phi, F[q], 10.0 * (F[q] - 1.0));
-    const double react = k.Da * omP[q] * h3;
-
-    out[0][q] = -U[q] * gCA - k.Da * fma(1.0 - CA, coA, k.lambda_ * CA * coC);
-    out[1][q] = fma(k.Da, fma(k.lambda_ * (1.0 - CC), coC, CC * coA), -U[q] * gCC);
-    out[2][q] = fma(fma(react, k.delta - cCa, HCa), rPhi[q], -W[q] * gCa);
-    out[3][q] = fma(fma(react, k.delta - cCO3, HCO3), rPhi[q], -W[q] * gCO3);
-    out[4][q] = fma(k.dPhi, lapPhi, react) - fma(dWdx, Phi, W[q] * gPhi);
+    o.react[q] = k.Da * omP[q] * h3;
+    o.rA[q] = k.Da * fma(1.0 - CA, coA, k.lambda_ * CA * coC);
+    o.rC[q] = k.Da * fma(k.lambda_ * (1.0 - CC), coC, CC * coA);
   }
+  return fl;
+}
+
+// The stencil part: first differences of the five fields, upwinded / Fiadeiro-Veronis weighted gradients,
+// Laplacians and the five rates (:418-423, :464-477, :495-520).
+__device__ __forceinline__ void rhs_pair_finish(const ColumnConsts& k, const double (&c)[5][2], const double (&mlo)[5],
+                                                const double (&phi)[5], const OwnTerms& o, double (&out)[5][2]) {
+  // a = (next - centre), b = (centre - previous) per field and cell
+  double a[5][2], b[5][2];
+#pragma unroll
+  for (int f = 0; f < 5; ++f) {
+    b[f][0] = c[f][0] - mlo[f];
+    a[f][0] = c[f][1] - c[f][0];
+    b[f][1] = a[f][0];
+    a[f][1] = phi[f] - c[f][1];
+  }
+  const double hdx = 0.5 * k.inv_dx;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const double cCa = c[2][q], cCO3 = c[3][q], Phi = c[4][q];
+    const bool back = o.U[q] > 0.0;
+    const double gCA = (back ? b[0][q] : a[0][q]) * k.inv_dx;
+    const double gCC = (back ? b[1][q] : a[1][q]) * k.inv_dx;
+    const double d2Ca = a[2][q] - b[2][q], d2CO3 = a[3][q] - b[3][q], d2Phi = a[4][q] - b[4][q];
+    const double gCa = fma(-o.sCa[q], d2Ca, a[2][q] + b[2][q]) * hdx;
+    const double gCO3 = fma(-o.sCO3[q], d2CO3, a[3][q] + b[3][q]) * hdx;
+    const double gPhi = fma(-o.sPhi[q], d2Phi, a[4][q] + b[4][q]) * hdx;
+    const double lapCa = d2Ca * k.inv_dx2, lapCO3 = d2CO3 * k.inv_dx2, lapPhi = d2Phi * k.inv_dx2;
+    const double h2 = gPhi * o.h2c[q];
+    const double HCa = k.dCa * fma(h2, gCa, o.h1[q] * lapCa);
+    const double HCO3 = k.dCO3 * fma(h2, gCO3, o.h1[q] * lapCO3);
+    const double dWdx = o.dWc[q] * gPhi;
+    out[0][q] = -o.U[q] * gCA - o.rA[q];
+    out[1][q] = fma(-o.U[q], gCC, o.rC[q]);
+    out[2][q] = fma(fma(o.react[q], k.delta - cCa, HCa), o.rPhi[q], -o.W[q] * gCa);
+    out[3][q] = fma(fma(o.react[q], k.delta - cCO3, HCO3), o.rPhi[q], -o.W[q] * gCO3);
+    out[4][q] = fma(k.dPhi, lapPhi, o.react[q]) - fma(dWdx, Phi, o.W[q] * gPhi);
+  }
+}
+
+__device__ __forceinline__ PairFlags rhs_pair(const ColumnConsts& k, const fm::Tables& tb, const double (&c)[5][2],
+                                              const double (&mlo)[5], const double (&phi)[5],
+                                              const bool (&in_mask)[2], double (&out)[5][2], double (&Uo)[2],
+                                              double (&Wo)[2]) {
+  OwnTerms o;
+  const PairFlags fl = rhs_pair_own(k, tb, c, in_mask, o);
+  rhs_pair_finish(k, c, mlo, phi, o, out);
+  Uo[0] = o.U[0];
+  Uo[1] = o.U[1];
+  Wo[0] = o.W[0];
+  Wo[1] = o.W[1];
   return fl;
 }
 

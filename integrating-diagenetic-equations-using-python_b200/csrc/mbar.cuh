@@ -1,0 +1,32 @@
+// mbar.cuh — split block barrier (arrive now, wait later) on a shared-memory mbarrier object.
+// __syncthreads() makes every warp idle until the slowest one has published its values; with
+// arrive / wait a thread signals "my values are published", keeps computing what does not need the
+// neighbours, and only then waits — the barrier latency hides behind useful fp64 work.
+#pragma once
+#include <cstdint>
+
+namespace marlpde {
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// release semantics at CTA scope: shared-memory writes made before the arrive are visible after the wait
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+}  // namespace marlpde

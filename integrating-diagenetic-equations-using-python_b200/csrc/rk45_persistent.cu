@@ -33,6 +33,7 @@
 #include "brent.cuh"
 #include "dopri.cuh"
 #include "lheureux_device.cuh"
+#include "mbar.cuh"
 #include "rk45_persistent.cuh"
 
 namespace marlpde {
@@ -60,7 +61,7 @@ struct Smem {
   static constexpr size_t off_tab = off_grp + sizeof(double) * TP;
   static constexpr size_t off_var = off_tab + fm::kTableBytes;          // per-slot arrays start here
   static constexpr size_t slot_bytes = (sizeof(ColumnConsts) + 15) / 16 * 16 + (sizeof(SlotCtl) + 15) / 16 * 16 + 32;
-  __host__ __device__ static size_t total(int C) { return off_var + slot_bytes * (size_t)C + 16; }
+  __host__ __device__ static size_t total(int C) { return off_var + slot_bytes * (size_t)C + 32; }   // + svc flag, mbarrier
 };
 
 static int group_log2(int threads_per_column) {
@@ -199,6 +200,8 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
   unsigned* const sEv = reinterpret_cast<unsigned*>(sSlotCol + C);                  // [2][C] bits of y_new
   unsigned* const sEv0 = sEv + 2 * C;                                               // [C] bits of a fresh y
   int* const sSvc = reinterpret_cast<int*>(sEv0 + C);
+  // split barrier of the stage loop (16-byte aligned slot at the very end of the carve-up)
+  uint64_t* const sBar = reinterpret_cast<uint64_t*>(var + ((L::slot_bytes * (size_t)C + 15) / 16) * 16 + 16);
 
   const fm::Tables tb = fm::stage_tables(smem_raw + L::off_tab, tid, blockDim.x);
   const bool active = tid < C * Hc;
@@ -446,6 +449,8 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
   // run the (ignored) RHS evaluations of their lanes, on benign values
   for (int i = tid; i < (int)((L::slot_bytes * (size_t)C + 16) / 4); i += blockDim.x)
     reinterpret_cast<int*>(var)[i] = 0;
+  if (tid == 0) mbar_init(sBar, blockDim.x);
+  unsigned bar_parity = 0;
   __syncthreads();
 
   bool fresh = false;           // column just loaded: K1 = f(y) still to be evaluated (stage i = 0)
@@ -573,7 +578,14 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
     double U[2], W[2];
 #pragma unroll 1
     for (int i = i0; i <= 6; ++i) {
-      if (i > i0) __syncthreads();
+      // the part of the RHS that needs no neighbour runs while the barrier that publishes the neighbours'
+      // stage inputs (arrived at below, at the end of the previous trip) is still pending
+      OwnTerms own;
+      PairFlags fl = rhs_pair_own(kc, tb, c, in_mask, own);
+      if (i > i0) {
+        mbar_wait(sBar, bar_parity);
+        bar_parity ^= 1u;
+      }
       double mlo[5], phi[5];
 #pragma unroll
       for (int f = 0; f < 5; ++f) {
@@ -589,7 +601,11 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
           phi[f] = c[f][1];
         }
       }
-      PairFlags fl = rhs_pair(kc, tb, c, mlo, phi, in_mask, r, U, W);
+      rhs_pair_finish(kc, c, mlo, phi, own, r);
+      U[0] = own.U[0];
+      U[1] = own.U[1];
+      W[0] = own.W[0];
+      W[1] = own.W[1];
       fl.bad[0] = fl.bad[0] && live;
       fl.bad[1] = fl.bad[1] && live && has1;
       if (fl.bad[0] || fl.bad[1]) rhs_pair_fixup(kc, tb, fl, c, mlo, phi, in_mask, r, U, W);
@@ -597,8 +613,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
 #pragma unroll
         for (int f = 0; f < 5; ++f) r[f][1] = 0.0;
       }
-      if (!live) continue;
-      switch (i) {
+      if (live) switch (i) {
         case 0:
           if (fresh) {
 #pragma unroll
@@ -679,6 +694,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
           }
           break;
       }
+      if (i < 6) mbar_arrive(sBar);        // my stage input for trip i+1 is published (every thread arrives, live or not)
     }
     // ---- K7 = f(y_new) is in r, y_new in c; error estimate and its norm
     double part = 0.0;

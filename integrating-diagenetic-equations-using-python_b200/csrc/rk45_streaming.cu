@@ -31,6 +31,7 @@
 
 #include "dopri.cuh"
 #include "lheureux_device.cuh"
+#include "mbar.cuh"
 #include "rk45_streaming.cuh"
 
 namespace marlpde {
@@ -492,7 +493,8 @@ struct TileSmem {
   static constexpr size_t off_tab = off_O + sizeof(double) * 2 * 5 * kTileThreads;
   static constexpr size_t off_kc = off_tab + fm::kTableBytes;
   static constexpr size_t off_red = off_kc + (sizeof(ColumnConsts) + 15) / 16 * 16;
-  static constexpr size_t total = off_red + 16 * sizeof(double);
+  static constexpr size_t off_bar = off_red + 16 * sizeof(double);
+  static constexpr size_t total = off_bar + 16;
 };
 
 __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Args A, int cbuf) {
@@ -508,6 +510,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
   double* const sO = reinterpret_cast<double*>(smem_raw + TileSmem::off_O);
   ColumnConsts& kc = *reinterpret_cast<ColumnConsts*>(smem_raw + TileSmem::off_kc);
   double* const red = reinterpret_cast<double*>(smem_raw + TileSmem::off_red);
+  uint64_t* const sBar = reinterpret_cast<uint64_t*>(smem_raw + TileSmem::off_bar);   // split barrier of the stage loop
+  if (tid == 0) mbar_init(sBar, blockDim.x);
+  unsigned bar_parity = 0;
   const fm::Tables tb = fm::stage_tables(smem_raw + TileSmem::off_tab, tid, blockDim.x);
   const int N = A.N;
   if (tid == 0) make_consts(A.params[col], N, kc);
@@ -570,7 +575,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
   double U[2], W[2];
 #pragma unroll 1
   for (int i = 1; i <= 6; ++i) {
-    if (i > 1) __syncthreads();
+    // the neighbour-free part of the RHS overlaps the pending barrier (see rk45_persistent.cu)
+    OwnTerms own;
+    PairFlags fl = rhs_pair_own(kc, tb, c, in_mask, own);
+    if (i > 1) {
+      mbar_wait(sBar, bar_parity);
+      bar_parity ^= 1u;
+    }
     const int tb_ = (i & 1) * 5 * TP;
     double mlo[5], phi[5];
 #pragma unroll
@@ -586,7 +597,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
         phi[f] = tid == TP - 1 ? c[f][1] : hp;
       }
     }
-    PairFlags fl = rhs_pair(kc, tb, c, mlo, phi, in_mask, r, U, W);
+    rhs_pair_finish(kc, c, mlo, phi, own, r);
+    U[0] = own.U[0];
+    U[1] = own.U[1];
+    W[0] = own.W[0];
+    W[1] = own.W[1];
     // cells a stage can still compute correctly: i window cells are lost at either edge by stage i
     fl.bad[0] = fl.bad[0] && in0 && e0 >= i && e0 < kTileCells - i;
     fl.bad[1] = fl.bad[1] && in1 && e0 + 1 >= i && e0 + 1 < kTileCells - i;
@@ -649,6 +664,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
       default:
         break;
     }
+    if (i < 6) mbar_arrive(sBar);
   }
   // ---- r = K7 = f(y_new), c = y_new: error contribution of the cells this window owns, write-back
   const bool sample = c0.next_eval < A.opt.n_eval && A.t_eval[c0.next_eval] <= c0.t_new;   // dense output pending

@@ -339,7 +339,11 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         # time-to-T*: the whole sweep from t=0 to T* (BASELINE.json: "time-to-T* per 4096 columns")
         d_y2 = torch.from_numpy(y0).to(dev)
         d_state2 = torch.from_numpy(batch.make_state(B, 0.0, 1e-6).view(np.uint8).copy()).to(dev)
-        o2 = _cabi.RK45Options(t_bound=1.0, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=0, n_eval=0,
+        # Columns that reach T* need 0.50-1.18 M attempts on this lattice.  A few columns run into a singularity
+        # of the model near t = 0.5-0.7 and end with status -1 (step below 10 ulp, as SciPy does); how many
+        # attempts they burn there is chaotic (0.7-6.8 M seen for the same column in two builds that differ by
+        # FMA contraction only) and a lone column advances at ~50 k attempts/s, so the cap bounds the tail.
+        o2 = _cabi.RK45Options(t_bound=1.0, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=args.step_cap, n_eval=0,
                                event_capacity=EVCAP, flags=_cabi.FLAG_EVENTS, reserved=0)
         d_queue.zero_()
         d_ec.zero_()
@@ -354,6 +358,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         secs = f0.elapsed_time(f1) * 1e-3
         tot = int(st2["n_accepted"].sum() + st2["n_rejected"].sum())
         line["time_to_Tstar"] = {"seconds": secs, "columns": B, "step_attempts": tot, "column_steps_per_s": tot / secs,
+                                 "step_cap_per_column": args.step_cap,
                                  "finished": int((st2["status"] == 0).sum()),
                                  "status_histogram": {str(int(k)): int(v) for k, v in
                                                       zip(*np.unique(st2["status"], return_counts=True))},
@@ -457,6 +462,9 @@ def main():
     ap.add_argument("--base", default="default", choices=["default", "scenario_A"])
     ap.add_argument("--attempts", type=int, default=3000, help="RK45 step attempts per column per bench step")
     ap.add_argument("--full", action="store_true", help="also time the whole sweep from t=0 to T*")
+    ap.add_argument("--step-cap", type=int, default=2_000_000,
+                    help="--full: step-attempt cap per column of the sweep to T* (SURVEY.md 8d, config 2: 'give every "
+                         "column a step cap + status'); 0 = none")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-t-end", type=float, default=0.03, help="CPU sample: integrate to this fraction of T*")
     args = ap.parse_args()

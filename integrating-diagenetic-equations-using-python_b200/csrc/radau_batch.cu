@@ -121,9 +121,15 @@ __host__ __device__ inline size_t work_doubles(int N) {
 
 struct __align__(16) WarpScratch {          // shared memory per warp
   ColumnConsts kc;
-  double2 sinv_prev[2][25];   // S_{i-1}^{-1} of both systems (row major)
-  double2 vec[2][2][8];       // two broadcast buffers x two systems x 5 entries (padded)
-  double2 mult[2][8];         // Gauss-Jordan multipliers of the pivot column, + pivot row index in [5].x
+  double2 vec[2][2][8];       // solve: two broadcast buffers x two systems x 5 entries (padded)
+  // factorise (lane = 5 r + c holds entry (r, c) of [S | I] of both systems):
+  double2 g0[2][32];          //   double-buffered exchange stage, real system: (S entry, I entry)
+  double2 g1a[2][32];         //   complex system, S entries
+  double2 g1b[2][32];         //   complex system, I entries
+  double2 sinv1[26];          //   S_i^{-1} of the complex system (row major)
+  double2 x1[26];             //   X_{i-1} = S_{i-1}^{-1} U_{i-1}, complex system (row major)
+  double sinv0[26];           //   S_i^{-1} of the real system
+  double x0[26];              //   X_{i-1}, real system
   double jst[kSlots][80];     // factorise: staged Jacobian blocks [L|D|U] of cells i .. i+kDepth (ring)
   double mst[kSlots][52];     // solve: 51 eight-byte words of a cell's fp32 record, cells i .. i+kDepth
 };
@@ -274,19 +280,30 @@ __device__ __noinline__ void fd_jacobian(const ColumnConsts& kc, const fm::Table
 }
 
 // Block-Thomas factorisation of (M I - J) for both systems at once.
-//   lane = 16 s + cc, s = system (0: M = mu_real/h, 1: M = mu_complex/h), cc = column of [S | I]
-//   (cc 0-4: column cc of S; cc 5-9: column cc-5 of the identity / of the inverse).
+//   lane = 5 r + c (25 lanes): ONE entry (r, c) of [S | I] of both systems per lane — the real system
+//   (M = mu_real/h) in real arithmetic, the complex one (M = mu_complex/h) in double2.
+// Per cell: S = M I - D_i - L_i X_{i-1}; Gauss-Jordan on [S | I] with partial pivoting (rows are never
+// swapped: a lane remembers at which step its row was the pivot row); X_i = S^{-1} U_i for the next cell.
+// Each elimination step exchanges the pivot row and the pivot column through a double-buffered shared
+// stage (one __syncwarp per step) and finds the pivot with one warp REDUX per system on a packed
+// (magnitude, row) key.  ~3x fewer instructions per cell than the column-per-lane version of r01d, whose
+// pivot search and multipliers ran on 2 of 32 lanes (ncu r01e: 1480 warp instructions per cell, 36 % of the
+// kernel's samples).
 // The recurrence is sequential in the cell index, so memory latency is taken off its critical path:
-// all 32 lanes fetch the Jacobian blocks of cell i+1 (75 doubles, coalesced) while cell i is being
-// eliminated, and hand them over through a double-buffered shared-memory stage.  The product
-// X_i = S_i^{-1} U_i needed by the next cell is formed while U_i is still staged and stays in
-// registers (lane (s, c) keeps column c).
+// all 32 lanes fetch the Jacobian blocks of cell i+kDepth (75 doubles, coalesced) while cell i is being
+// eliminated, and hand them over through a ring of shared-memory stages.
+__device__ __forceinline__ unsigned pivot_key(double mag, int r, bool candidate) {
+  // float magnitude in the high bits (non-negative floats order like their bit patterns), 7 - r in the low
+  // three: the warp maximum is the largest magnitude, the smallest row among (float-)equal ones
+  return candidate ? ((__float_as_uint((float)mag) & ~7u) | (unsigned)(7 - r)) : 0u;
+}
+
 __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double h, const double* J, float* Rec) {
-  const int s = lane >> 4, cc = lane & 15;
-  const bool valid = cc < 10;
-  const bool apart = cc < 5;
-  const int c5 = apart ? cc : cc - 5;
-  const double2 M = s == 0 ? make_double2(kMuReal / h, 0.0) : make_double2(kMuCRe / h, kMuCIm / h);
+  const int l = lane < 25 ? lane : 0;     // lanes 25-31 shadow lane 0 (same values to the same shared words)
+  const int r = l / 5, c = l - 5 * r;
+  const bool diag = r == c;
+  const double M0 = kMuReal / h;
+  const double2 M1 = make_double2(kMuCRe / h, kMuCIm / h);
   // ring of kSlots staged cells: cells 0 .. kDepth-1 are requested up front, cell i+kDepth at iteration i
   auto request = [&](int cell) {
     if (cell < N) {
@@ -299,99 +316,93 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
     cp_async_commit();                                       // (empty groups keep the group count uniform)
   };
   for (int c0 = 0; c0 < kDepth; ++c0) request(c0);
-  double2 xcol[5];                                          // column c5 of X_{i-1} = S_{i-1}^{-1} U_{i-1}
-#pragma unroll
-  for (int r = 0; r < 5; ++r) xcol[r] = make_double2(0.0, 0.0);
+  ws.x0[l] = 0.0;                                            // X_{-1} = 0
+  ws.x1[l] = make_double2(0.0, 0.0);
 #pragma unroll 1
   for (int i = 0; i < N; ++i) {
     request(i + kDepth);                  // slot (i + kDepth) % kSlots was released at the end of iteration i-1
     cp_async_wait<kDepth>();              // all but the kDepth newest groups have landed: cell i is in shared memory
     __syncwarp();
     const double* Ji = ws.jst[i % kSlots];
+    float* const rec = Rec + (size_t)i * 128;
     if (lane < 25) {                                         // fp32 copies of L_i and U_i for the sweeps
-      float* rec = Rec + (size_t)i * 128;
       rec[lane] = (float)Ji[lane];
       rec[102 + lane] = (float)Ji[50 + lane];
     }
-    double2 col[5];
-    if (apart) {
-      // column c5 of S = M I - D_i - L_i X_{i-1} e_c   (X_{-1} = 0)
+    // entry (r, c) of S = M I - D_i - L_i X_{i-1}  and of the identity
+    double A0 = (diag ? M0 : 0.0) - Ji[25 + c * 5 + r];
+    double2 A1 = make_double2((diag ? M1.x : 0.0) - Ji[25 + c * 5 + r], diag ? M1.y : 0.0);
 #pragma unroll
-      for (int r = 0; r < 5; ++r) {
-        double2 acc = make_double2((r == c5 ? M.x : 0.0) - Ji[25 + c5 * 5 + r], r == c5 ? M.y : 0.0);
-#pragma unroll
-        for (int m = 0; m < 5; ++m) acc = crfma(-Ji[m * 5 + r], xcol[m], acc);
-        col[r] = acc;
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < 5; ++r) col[r] = make_double2(r == c5 ? 1.0 : 0.0, 0.0);
+    for (int m = 0; m < 5; ++m) {
+      const double nl = -Ji[m * 5 + r];
+      A0 = fma(nl, ws.x0[m * 5 + c], A0);
+      A1 = crfma(nl, ws.x1[m * 5 + c], A1);
     }
-    // ---- Gauss-Jordan on [S | I] with partial pivoting; rows are never swapped physically:
-    //      perm[k] = row that served as pivot of column k
-    unsigned used = 0, perm = 0;                             // perm: 4 bits per pivot column
+    double B0 = diag ? 1.0 : 0.0;
+    double2 B1 = make_double2(diag ? 1.0 : 0.0, 0.0);
+    bool used0 = false, used1 = false;
+    int step0 = 0, step1 = 0;                                // elimination step at which my row was the pivot row
 #pragma unroll 1
     for (int k = 0; k < 5; ++k) {
-      if (valid && apart && c5 == k) {                     // the lane holding column k of S picks the pivot
-        int p = 0;
-        double best = -1.0;
-#pragma unroll
-        for (int r = 0; r < 5; ++r) {
-          const double mag = fma(col[r].x, col[r].x, col[r].y * col[r].y);
-          if (!((used >> r) & 1u) && mag > best) {
-            best = mag;
-            p = r;
-          }
-        }
-        double2 piv = col[0];
-#pragma unroll
-        for (int r = 1; r < 5; ++r) piv = (p == r) ? col[r] : piv;
-        const double2 inv = cinv(piv);
-#pragma unroll
-        for (int r = 0; r < 5; ++r) ws.mult[s][r] = (r == p) ? inv : cmul(col[r], inv);
-        ws.mult[s][5] = make_double2((double)p, 0.0);
-      }
+      const int buf = k & 1;
+      ws.g0[buf][l] = make_double2(A0, B0);
+      ws.g1a[buf][l] = A1;
+      ws.g1b[buf][l] = B1;
+      const int p0 = 7 - (int)(__reduce_max_sync(0xffffffffu, pivot_key(fabs(A0), r, c == k && !used0)) & 7u);
+      const int p1 =
+          7 - (int)(__reduce_max_sync(0xffffffffu, pivot_key(fabs(A1.x) + fabs(A1.y), r, c == k && !used1)) & 7u);
       __syncwarp();
-      const int p = (int)ws.mult[s][5].x;
-      perm |= (unsigned)p << (4 * k);
-      used |= 1u << p;
-      if (valid) {
-        double2 piv = col[0];
-#pragma unroll
-        for (int r = 1; r < 5; ++r) piv = (p == r) ? col[r] : piv;
-#pragma unroll
-        for (int r = 0; r < 5; ++r) {
-          const double2 m = ws.mult[s][r];
-          col[r] = (r == p) ? cmul(piv, m) : cfma(make_double2(-m.x, -m.y), piv, col[r]);
+      {   // real system
+        const double2 prow = ws.g0[buf][5 * p0 + c];         // (S, I) entries of the pivot row in my column
+        const double ark = ws.g0[buf][5 * r + k].x;          // my row's entry in the pivot column
+        const double piv = ws.g0[buf][5 * p0 + k].x;
+        const double inv = piv * fm::rcp3(piv * piv);
+        const bool mine = r == p0;
+        const double m = mine ? inv : ark * inv;
+        A0 = mine ? prow.x * m : fma(-m, prow.x, A0);
+        B0 = mine ? prow.y * m : fma(-m, prow.y, B0);
+        if (mine) {
+          used0 = true;
+          step0 = k;
         }
       }
-      __syncwarp();
+      {   // complex system
+        const double2 pa = ws.g1a[buf][5 * p1 + c], pb = ws.g1b[buf][5 * p1 + c];
+        const double2 ark = ws.g1a[buf][5 * r + k];
+        const double2 inv = cinv(ws.g1a[buf][5 * p1 + k]);
+        const bool mine = r == p1;
+        const double2 m = mine ? inv : cmul(ark, inv);
+        const double2 nm = make_double2(-m.x, -m.y);
+        const double2 a_s = cmul(pa, m), a_e = cfma(nm, pa, A1);
+        const double2 b_s = cmul(pb, m), b_e = cfma(nm, pb, B1);
+        A1 = mine ? a_s : a_e;
+        B1 = mine ? b_s : b_e;
+        if (mine) {
+          used1 = true;
+          step1 = k;
+        }
+      }
+      // (the stage written at step k is rewritten at step k+2, behind the __syncwarp of step k+1)
     }
-    // ---- identity-part lanes now hold column c5 of Pi S^{-1}: S^{-1}[k][c5] = col[perm_k]
-    if (valid && !apart) {
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const int pk = (perm >> (4 * k)) & 15;
-        double2 v = col[0];
-#pragma unroll
-        for (int r = 1; r < 5; ++r) v = (pk == r) ? col[r] : v;
-        ws.sinv_prev[s][k * 5 + c5] = v;
-        float* rec = Rec + (size_t)i * 128;
-        if (s == 0) rec[26 + k * 5 + c5] = (float)v.x;
-        else reinterpret_cast<float2*>(rec + 52)[k * 5 + c5] = make_float2((float)v.x, (float)v.y);
-      }
+    // ---- the identity part now holds S^{-1}: row step_s of it sits in the lanes of row r
+    ws.sinv0[step0 * 5 + c] = B0;
+    ws.sinv1[step1 * 5 + c] = B1;
+    if (lane < 25) {
+      rec[26 + step0 * 5 + c] = (float)B0;
+      reinterpret_cast<float2*>(rec + 52)[step1 * 5 + c] = make_float2((float)B1.x, (float)B1.y);
     }
     __syncwarp();
-    // ---- X_i e_c = S_i^{-1} (U_i e_c) for the next cell, while U_i is staged
-    if (apart) {
+    // ---- X_i = S_i^{-1} U_i for the next cell, while U_i is staged
+    double X0 = 0.0;
+    double2 X1 = make_double2(0.0, 0.0);
 #pragma unroll
-      for (int r = 0; r < 5; ++r) {
-        double2 acc = make_double2(0.0, 0.0);
-#pragma unroll
-        for (int m = 0; m < 5; ++m) acc = crfma(Ji[50 + c5 * 5 + m], ws.sinv_prev[s][r * 5 + m], acc);
-        xcol[r] = acc;
-      }
+    for (int m = 0; m < 5; ++m) {
+      const double u = Ji[50 + c * 5 + m];
+      X0 = fma(u, ws.sinv0[r * 5 + m], X0);
+      X1 = crfma(u, ws.sinv1[r * 5 + m], X1);
     }
+    ws.x0[l] = X0;
+    ws.x1[l] = X1;
     __syncwarp();                         // everyone is done with slot i % kSlots before it is requested again
   }
   cp_async_wait<0>();

@@ -216,28 +216,12 @@ __device__ __forceinline__ double fd_step(double y, double f, double atol) {
 }
 
 // THE one instance of the RHS in this kernel (instruction-cache footprint matters: 16 warps per SM sit
-// in different phases of their columns).  Two uses:
-//   fld < 0 : out = rhs(yy + add)                      (add may be NULL), field-major [5][N]
-//   fld >= 0: finite-difference Jacobian colour (c3, fld): yy is the state with field fld of every cell
-//             i = c3 (mod 3) perturbed by fd_step; cell i' reads off d f(i') / d y(fld, j) for the one
-//             perturbed cell j in {i'-1, i', i'+1} and stores it as column fld of its L, D or U block
-//             in `out` (= J); y0/f0 are the unperturbed state and its RHS
+// in different phases of their columns): out = rhs(yy + add) (add may be NULL), all cell-major [N][5].
 __device__ __noinline__ void rhs_eval(const ColumnConsts* kc, const fm::Tables* tb, int N, int lane, const double* yy,
-                                      const double* add, double* out, int fld, int c3, const double* y0,
-                                      const double* f0, double atol) {
+                                      const double* add, double* out) {
   auto sink = [&](int i, const double (&r5)[5]) {
-    if (fld < 0) {
 #pragma unroll
-      for (int f = 0; f < 5; ++f) out[i * 5 + f] = r5[f];
-      return;
-    }
-    const int d = ((c3 - (i % 3)) + 3) % 3;           // 0: j = i, 1: j = i+1, 2: j = i-1
-    const int j = i + (d == 2 ? -1 : d);
-    if (j < 0 || j >= N) return;
-    const double inv = 1.0 / fd_step(y0[j * 5 + fld], f0[j * 5 + fld], atol);
-    double* blk = out + (size_t)i * 75 + (d == 0 ? 25 : (d == 1 ? 50 : 0));
-#pragma unroll
-    for (int r = 0; r < 5; ++r) blk[fld * 5 + r] = (r5[r] - f0[i * 5 + r]) * inv;   // blocks are COLUMN-major: one 40-byte run
+    for (int f = 0; f < 5; ++f) out[i * 5 + f] = r5[f];
   };
   rhs_column(*kc, *tb, N, lane, yy, add, sink);
   __syncwarp();
@@ -249,33 +233,132 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// J = d rhs / d y by 15 finite-difference evaluations (3 cell classes x 5 fields); `pert` is scratch [5N]
-__device__ __noinline__ void fd_jacobian(const ColumnConsts& kc, const fm::Tables& tb, int N, int lane, const double* y,
-                                         const double* f, double atol, double* J, double* pert) {
-  const int n = 5 * N;
-  // every block column is written by exactly one colour, except L_0 and U_{N-1} (no neighbour): those are zero
-  if (lane < 25) {
-    J[lane] = 0.0;
-    J[(size_t)(N - 1) * 75 + 50 + lane] = 0.0;
+// Column `fld` of all three Jacobian blocks of every cell, after ONE evaluation Fp = rhs(pert) with field
+// fld of EVERY cell perturbed (pert = y0 + d, d_j = fd_step):
+//   * L_i e_fld and U_i e_fld analytically.  Given a cell's own values the RHS is linear in each neighbour value
+//     (the stencils of rhs_pair_finish; the coefficients U, W, sigma, h1, h2c, dWc depend on the cell's own Phi
+//     only), so these are exact.  Structure: (CA,CA), (CC,CC) on the upwind side, (cCa,cCa),
+//     (cCO3,cCO3), (Phi,Phi), (cCa,Phi), (cCO3,Phi) on both sides.  The bottom ghost of CA and CC is
+//     2 a_{N-1} - a_{N-2}: the last cell's dependence on it folds into its L block.
+//   * D_i e_fld = (Fp_i - f0_i - d_{i-1} L_i e_fld - d_{i+1} U_i e_fld) / d_i: with the coefficients taken at the
+//     cell's PERTURBED own values this is exactly the one-cell difference quotient num_jac forms.
+// So the Jacobian costs 5 RHS evaluations + 5 of these cheap passes instead of the 15 colours a block-
+// tridiagonal pattern needs (the reference's 27-diagonal pattern: 21).  One cell per lane, generic (IEEE) math
+// as in cell_rhs: no restriction on the state.  The formulas are checked against central differences of the
+// oracle RHS in tests/test_host_side.py::test_offdiagonal_jacobian_block_formulas.
+__device__ __noinline__ void jac_columns(const ColumnConsts* kp, const fm::Tables* tbp, int N, int lane, int fld,
+                                         const double* pert, const double* Fp, const double* y0, const double* f0,
+                                         double atol, double* J) {
+  const ColumnConsts& k = *kp;
+  const fm::Tables& tb = *tbp;
+  const double hdx = 0.5 * k.inv_dx;
+#pragma unroll 1
+  for (int i = lane; i < N; i += 32) {
+    const bool first = i == 0, last = i == N - 1;
+    const double Phi = pert[i * 5 + 4];
+    // ---- the cell's own coefficients (LHeureux_model.py:414-462, arithmetic of cell_rhs)
+    const double rPhi = fm::rcp(Phi);
+    const double F = 1.0 - fm::exp(tb, fma(-10.0, rPhi, 10.0));
+    const double Phi2 = Phi * Phi;
+    const double U = fma(k.rhorat * (Phi2 * Phi), fm::div(F, 1.0 - Phi), k.presum);
+    const double W = fma(-k.rhorat * Phi2, F, k.presum);
+    const double den = fma(-2.0, fm::log(tb, Phi), 1.0);
+    const double rden = fm::rcp(den);
+    double Lc[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, Uc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    // weighted gradient of field f (2, 3 or 4) at this cell: 0.5 ((1 - s) forward + (1 + s) backward)
+    auto grad = [&](int f, double sg) {
+      const double ce = pert[i * 5 + f];
+      const double pv = first ? fma(2.0, k.bc_top[f], -ce) : pert[(i - 1) * 5 + f];
+      const double nx = last ? ce : pert[(i + 1) * 5 + f];
+      return ((1.0 - sg) * (nx - ce) + (1.0 + sg) * (ce - pv)) * hdx;
+    };
+    auto sigma = [&](double Pe) { return k.FV_switch ? fv_sigma(tb, Pe, W, k.Pe_min, k.Pe_max) : 0.0; };
+    if (fld < 2) {
+      const bool back = U > 0.0;
+      double lv = back ? U * k.inv_dx : 0.0;
+      const double uv = back ? 0.0 : -U * k.inv_dx;
+      if (last) lv -= uv;                                   // bottom ghost 2 a_{N-1} - a_{N-2}
+      Lc[0] = fld == 0 ? lv : 0.0;
+      Lc[1] = fld == 1 ? lv : 0.0;
+      Uc[0] = fld == 0 ? uv : 0.0;
+      Uc[1] = fld == 1 ? uv : 0.0;
+    } else {
+      const double sPhi = sigma(W * k.kPePhi);
+      const double h2c = (2.0 + den) * (rden * rden);
+      if (fld < 4) {
+        const double sg = sigma(W * den * (fld == 2 ? k.kPeCa : k.kPeCO3)), d = fld == 2 ? k.dCa : k.dCO3;
+        const double h1 = Phi * rden, h2 = grad(4, sPhi) * h2c;
+        const double dgp = -(1.0 + sg) * hdx, dgn = (1.0 - sg) * hdx;
+        const double lv = rPhi * d * fma(h2, dgp, h1 * k.inv_dx2) - W * dgp;
+        const double uv = rPhi * d * fma(h2, dgn, h1 * k.inv_dx2) - W * dgn;
+        Lc[2] = fld == 2 ? lv : 0.0;
+        Lc[3] = fld == 3 ? lv : 0.0;
+        Uc[2] = fld == 2 ? uv : 0.0;
+        Uc[3] = fld == 3 ? uv : 0.0;
+      } else {
+        const double dgp = -(1.0 + sPhi) * hdx, dgn = (1.0 - sPhi) * hdx;
+        const double Wden = W * den;
+        const double t2 = rPhi * k.dCa * grad(2, sigma(Wden * k.kPeCa)) * h2c;
+        const double t3 = rPhi * k.dCO3 * grad(3, sigma(Wden * k.kPeCO3)) * h2c;
+        const double dWc = -k.rhorat * fma(2.0 * Phi, F, 10.0 * (F - 1.0));
+        const double t4 = fma(dWc, Phi, W);
+        Lc[2] = t2 * dgp;
+        Uc[2] = t2 * dgn;
+        Lc[3] = t3 * dgp;
+        Uc[3] = t3 * dgn;
+        Lc[4] = fma(k.dPhi, k.inv_dx2, -t4 * dgp);
+        Uc[4] = fma(k.dPhi, k.inv_dx2, -t4 * dgn);
+      }
+    }
+    const double di = fd_step(y0[i * 5 + fld], f0[i * 5 + fld], atol);
+    double dp = 0.0, dn = 0.0;
+    if (first) {
+#pragma unroll
+      for (int r = 0; r < 5; ++r) Lc[r] = 0.0;
+    } else {
+      dp = fd_step(y0[(i - 1) * 5 + fld], f0[(i - 1) * 5 + fld], atol);
+    }
+    if (last) {
+#pragma unroll
+      for (int r = 0; r < 5; ++r) Uc[r] = 0.0;
+    } else {
+      dn = fd_step(y0[(i + 1) * 5 + fld], f0[(i + 1) * 5 + fld], atol);
+    }
+    const double inv = 1.0 / di;
+    double* blk = J + (size_t)i * 75 + fld * 5;             // blocks [L|D|U] are COLUMN-major: 40-byte runs
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      blk[r] = Lc[r];
+      blk[25 + r] = fma(-dn, Uc[r], fma(-dp, Lc[r], Fp[i * 5 + r] - f0[i * 5 + r])) * inv;
+      blk[50 + r] = Uc[r];
+    }
   }
+  __syncwarp();
+}
+
+// J = d rhs / d y: per field one RHS evaluation with that field perturbed in every cell, then jac_columns.
+// `scratch` holds 2 x 5N doubles (perturbed state, its RHS).
+__device__ __noinline__ void fd_jacobian(const ColumnConsts& kc, const fm::Tables& tb, int N, int lane, const double* y,
+                                         const double* f, double atol, double* J, double* scratch) {
+  const int n = 5 * N;
+  double* const pert = scratch;
+  double* const Fp = scratch + n;
 #pragma unroll 1
   for (int idx = lane; idx < n; idx += 32) pert[idx] = y[idx];
   __syncwarp();
 #pragma unroll 1
-  for (int c3 = 0; c3 < 3; ++c3) {
+  for (int fld = 0; fld < 5; ++fld) {
 #pragma unroll 1
-    for (int fld = 0; fld < 5; ++fld) {
-#pragma unroll 1
-      for (int i = c3 + 3 * lane; i < N; i += 96) {
-        const double v = y[i * 5 + fld];
-        pert[i * 5 + fld] = v + fd_step(v, f[i * 5 + fld], atol);
-      }
-      __syncwarp();
-      rhs_eval(&kc, &tb, N, lane, pert, nullptr, J, fld, c3, y, f, atol);
-#pragma unroll 1
-      for (int i = c3 + 3 * lane; i < N; i += 96) pert[i * 5 + fld] = y[i * 5 + fld];
-      __syncwarp();
+    for (int i = lane; i < N; i += 32) {
+      const double v = y[i * 5 + fld];
+      pert[i * 5 + fld] = v + fd_step(v, f[i * 5 + fld], atol);
     }
+    __syncwarp();
+    rhs_eval(&kc, &tb, N, lane, pert, nullptr, Fp);
+    jac_columns(&kc, &tb, N, lane, fld, pert, Fp, y, f, atol, J);
+#pragma unroll 1
+    for (int i = lane; i < N; i += 32) pert[i * 5 + fld] = y[i * 5 + fld];
+    __syncwarp();
   }
 }
 
@@ -638,7 +721,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
     long long steps_done = 0;
 
     auto eval_to = [&](const double* yy, const double* add, double* out) {   // out = rhs(yy + add)
-      rhs_eval(&kc, &tb, N, lane, yy, add, out, -1, 0, nullptr, nullptr, 0.0);
+      rhs_eval(&kc, &tb, N, lane, yy, add, out);
     };
 
     if (t < A.opt.t_bound) {
@@ -646,7 +729,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
       nfev += 1;
       fd_jacobian(kc, tb, N, lane, y, w.f, atol, w.J, w.B);
       njev += 1;
-      nfev += 15;
+      nfev += 5;   // Jacobian: one evaluation per field (fd_jacobian)
     }
     const bool ev_on = (A.opt.flags & MARLPDE_FLAG_EVENTS) != 0;
     double g_old[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -807,7 +890,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
           if (current_jac) break;
           fd_jacobian(kc, tb, N, lane, y, w.f, atol, w.J, w.B);
           njev += 1;
-          nfev += 15;
+          nfev += 5;   // Jacobian: one evaluation per field (fd_jacobian)
           current_jac = true;
           lu_valid = false;
         }
@@ -879,7 +962,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
       if (recompute_jac) {
         fd_jacobian(kc, tb, N, lane, y, w.f, atol, w.J, w.B);
         njev += 1;
-        nfev += 15;
+        nfev += 5;   // Jacobian: one evaluation per field (fd_jacobian)
         current_jac = true;
       } else {
         current_jac = false;

@@ -237,7 +237,7 @@ class RadauResult:
     n_accepted: np.ndarray       # accepted steps
     n_rejected: np.ndarray       # steps rejected by the error test
     nfev: np.ndarray
-    njev: np.ndarray             # finite-difference Jacobians (15 RHS evaluations each, counted in nfev)
+    njev: np.ndarray             # Jacobians (analytic off-diagonal blocks + 5 RHS evaluations each, counted in nfev)
     nlu: np.ndarray              # block-tridiagonal factorisations (real and complex counted separately)
     newton_iterations: np.ndarray
     newton_failures: np.ndarray

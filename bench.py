@@ -335,7 +335,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     if gather_ms is not None:
         line["allgather_end_states_ms"] = gather_ms
 
-    if args.full:
+    if args.full and not args.skip_rk45_tstar:
         # time-to-T*: the whole sweep from t=0 to T* (BASELINE.json: "time-to-T* per 4096 columns")
         d_y2 = torch.from_numpy(y0).to(dev)
         d_state2 = torch.from_numpy(batch.make_state(B, 0.0, 1e-6).view(np.uint8).copy()).to(dev)
@@ -465,6 +465,8 @@ def main():
     ap.add_argument("--step-cap", type=int, default=2_000_000,
                     help="--full: step-attempt cap per column of the sweep to T* (SURVEY.md 8d, config 2: 'give every "
                          "column a step cap + status'); 0 = none")
+    ap.add_argument("--skip-rk45-tstar", action="store_true",
+                    help="--full without the ~170 s explicit sweep to T* (implicit sweep and large-N lines only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-t-end", type=float, default=0.03, help="CPU sample: integrate to this fraction of T*")
     args = ap.parse_args()

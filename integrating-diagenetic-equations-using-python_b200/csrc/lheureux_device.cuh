@@ -218,6 +218,43 @@ struct PairFlags {
   bool bad[2];
 };
 
+// How rhs_pair_own lays out its transcendental chains in basic blocks (the values are identical, only the
+// instruction schedule differs; `kSched` template parameter of rhs_pair_own / rhs_pair):
+//   kSchedSplit   one block per function behind its own warp vote (3 x coth, aragonite power, calcite power);
+//   kSchedMerged  coth of the porosity Peclet number + calcite power unconditional in ONE block (4 chains in
+//                 flight), coth of the two solute Peclet numbers behind one vote, aragonite power behind one;
+//   kSchedAll     as kSchedMerged with the aragonite power unconditional too (6 chains, no vote);
+//   kSchedTwoArm  two instances of the merged block, with (6 chains) and without (4 chains) the aragonite
+//                 power, chosen by one vote.
+// Measured on B200 (r01g, 4096 columns): on-chip RK45 18.7 / 19.5 / 19.9 / 20.4 M column-steps/s; Radau to t = 0.05
+// 1.61 / 1.58 / 1.55 / 1.60 s; overlapped tiles (N = 20 000 x 64) 224 / 220 / 211 / 218 k column-steps/s.  Each
+// kernel instantiates the one that suits it.  -DMARLPDE_RHS_MERGE=n forces one schedule everywhere (A/B builds).
+constexpr int kSchedSplit = 0, kSchedMerged = 1, kSchedAll = 2, kSchedTwoArm = 3;
+__host__ __device__ constexpr int rhs_schedule(int preferred) {
+#ifdef MARLPDE_RHS_MERGE
+  return MARLPDE_RHS_MERGE;
+#else
+  return preferred;
+#endif
+}
+
+// The three pieces of fv_sigma_pair for one value (same arithmetic, so the weights are bit-identical however the
+// pieces are scheduled): range test, coth(Pe) - 1/Pe from one expm1, selection (np.sign keeps NaN / 0).
+__device__ __forceinline__ bool fv_mid(bool fv_on, double Pe, double Pe_min, double Pe_max) {
+  const double a = fabs(Pe);
+  return fv_on && (a >= Pe_min) && (a <= Pe_max);
+}
+__device__ __forceinline__ double fv_langevin(const fm::Tables& tb, double Pe) {
+  const double em = fm::expm1_nb(tb, 2.0 * Pe);                    // coth = 1 + 2/em
+  return fma(Pe, em + 2.0, -em) * fm::rcp3(Pe * em);
+}
+__device__ __forceinline__ double fv_select(bool fv_on, double Pe, double W, double Pe_min, double Pe_max, bool mid,
+                                            double sm) {
+  const double a = fabs(Pe);
+  const double sgn = (W > 0.0) ? 1.0 : ((W < 0.0) ? -1.0 : W);
+  return (!fv_on || a < Pe_min) ? 0.0 : ((a > Pe_max) ? sgn : (mid ? sm : Pe));
+}
+
 __device__ __forceinline__ void fv_sigma_pair(const fm::Tables& tb, bool fv_on, const double (&Pe)[2],
                                               const double (&W)[2], double Pe_min, double Pe_max,
                                               double (&s)[2]) {
@@ -258,6 +295,7 @@ struct OwnTerms {
   double rC[2];      // Da (lambda (1 - CC) coC + CC coA)
 };
 
+template <int kSched>
 __device__ __forceinline__ PairFlags rhs_pair_own(const ColumnConsts& k, const fm::Tables& tb, const double (&c)[5][2],
                                                   const bool (&in_mask)[2], OwnTerms& o) {
   PairFlags fl;
@@ -281,25 +319,11 @@ __device__ __forceinline__ PairFlags rhs_pair_own(const ColumnConsts& k, const f
     o.dWc[q] = -k.rhorat * fma(2.0 * Phi, F[q], 10.0 * (F[q] - 1.0));
   }
 
-  // ---- Fiadeiro-Veronis weights (:433-462)
-  // (FV_switch is a per-column value and warps straddle columns: it must not guard the votes inside
-  //  fv_sigma_pair, so it is folded into the lane predicates instead of branching here.)
-  {
-    const bool fv_on = k.FV_switch != 0;
-    double PeCa[2], PeCO3[2], PePhi[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const double Wden = o.W[q] * den[q];
-      PeCa[q] = Wden * k.kPeCa;
-      PeCO3[q] = Wden * k.kPeCO3;
-      PePhi[q] = o.W[q] * k.kPePhi;
-    }
-    fv_sigma_pair(tb, fv_on, PeCa, o.W, k.Pe_min, k.Pe_max, o.sCa);
-    fv_sigma_pair(tb, fv_on, PeCO3, o.W, k.Pe_min, k.Pe_max, o.sCO3);
-    fv_sigma_pair(tb, fv_on, PePhi, o.W, k.Pe_min, k.Pe_max, o.sPhi);
-  }
-
-  // ---- saturation products and the real powers of the rate laws (:479-491)
+  // ---- Fiadeiro-Veronis weights (:433-462) and the real powers of the rate laws (:479-491)
+  // (FV_switch is a per-column value and warps straddle columns: it must not guard the votes, so it is
+  //  folded into the lane predicates instead of branching here.)
+  // Every transcendental below is a long dependent chain (expm1 + reciprocal, log + exp: ~300 cycles for ~70
+  // instructions when a basic block holds only the two cells' chains); kSched decides which chains share a block.
   bool ltA[2], ltC[2], needA[2];
   double xA[2], xC[2], eA[2], eC[2], pA[2] = {0.0, 0.0}, pC[2];
 #pragma unroll
@@ -314,16 +338,83 @@ __device__ __forceinline__ PairFlags rhs_pair_own(const ColumnConsts& k, const f
     eC[q] = ltC[q] ? k.n2 : k.n1;
     needA[q] = !(ltA[q] && !in_mask[q]);
   }
-  if (__any_sync(0xffffffffu, needA[0] || needA[1])) {
+  auto powA = [&]() {
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       bool bq = false;
       pA[q] = fm::exp_nb(tb, eA[q] * fm::log_nb(tb, xA[q], bq), bq);
       fl.bad[q] |= bq && needA[q];
     }
-  }
+  };
+  auto powC = [&]() {
 #pragma unroll
-  for (int q = 0; q < 2; ++q) pC[q] = fm::exp_nb(tb, eC[q] * fm::log_nb(tb, xC[q], fl.bad[q]), fl.bad[q]);
+    for (int q = 0; q < 2; ++q) pC[q] = fm::exp_nb(tb, eC[q] * fm::log_nb(tb, xC[q], fl.bad[q]), fl.bad[q]);
+  };
+  {
+    const bool fv_on = k.FV_switch != 0;
+    double PeCa[2], PeCO3[2], PePhi[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const double Wden = o.W[q] * den[q];
+      PeCa[q] = Wden * k.kPeCa;
+      PeCO3[q] = Wden * k.kPeCO3;
+      PePhi[q] = o.W[q] * k.kPePhi;
+    }
+    if constexpr (kSched == kSchedSplit) {
+      fv_sigma_pair(tb, fv_on, PeCa, o.W, k.Pe_min, k.Pe_max, o.sCa);
+      fv_sigma_pair(tb, fv_on, PeCO3, o.W, k.Pe_min, k.Pe_max, o.sCO3);
+      fv_sigma_pair(tb, fv_on, PePhi, o.W, k.Pe_min, k.Pe_max, o.sPhi);
+      if (__any_sync(0xffffffffu, needA[0] || needA[1])) powA();
+      powC();
+    } else {
+      bool midCa[2], midCO3[2], midPhi[2];
+      double smCa[2] = {0.0, 0.0}, smCO3[2] = {0.0, 0.0}, smPhi[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        midCa[q] = fv_mid(fv_on, PeCa[q], k.Pe_min, k.Pe_max);
+        midCO3[q] = fv_mid(fv_on, PeCO3[q], k.Pe_min, k.Pe_max);
+        midPhi[q] = fv_mid(fv_on, PePhi[q], k.Pe_min, k.Pe_max);
+      }
+      if (__any_sync(0xffffffffu, midCa[0] || midCa[1] || midCO3[0] || midCO3[1])) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          smCa[q] = fv_langevin(tb, PeCa[q]);
+          smCO3[q] = fv_langevin(tb, PeCO3[q]);
+        }
+      }
+      // coth of the porosity Peclet number: unconditional (the value is only selected where the number is
+      // mid-range; expm1_nb on any other argument yields a discarded number, its table index is masked)
+      auto langPhi = [&]() {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) smPhi[q] = fv_langevin(tb, PePhi[q]);
+      };
+      if constexpr (kSched == kSchedTwoArm) {
+        // The two arms are written in different orders on purpose: identical leading / trailing code would be
+        // hoisted / sunk out of them and the aragonite chains would sit alone in their block again.
+        if (__any_sync(0xffffffffu, needA[0] || needA[1])) {
+          langPhi();
+          powC();
+          powA();
+        } else {
+          powC();
+          langPhi();
+        }
+      } else {
+        langPhi();
+        if constexpr (kSched == kSchedAll) powA();
+        powC();
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        o.sCa[q] = fv_select(fv_on, PeCa[q], o.W[q], k.Pe_min, k.Pe_max, midCa[q], smCa[q]);
+        o.sCO3[q] = fv_select(fv_on, PeCO3[q], o.W[q], k.Pe_min, k.Pe_max, midCO3[q], smCO3[q]);
+        o.sPhi[q] = fv_select(fv_on, PePhi[q], o.W[q], k.Pe_min, k.Pe_max, midPhi[q], smPhi[q]);
+      }
+      if constexpr (kSched == kSchedMerged) {
+        if (__any_sync(0xffffffffu, needA[0] || needA[1])) powA();
+      }
+    }
+  }
 
   // ---- reaction terms (:486-493, the Da(...) parts of :498-520)
 #pragma unroll
@@ -376,12 +467,13 @@ __device__ __forceinline__ void rhs_pair_finish(const ColumnConsts& k, const dou
   }
 }
 
+template <int kSched>
 __device__ __forceinline__ PairFlags rhs_pair(const ColumnConsts& k, const fm::Tables& tb, const double (&c)[5][2],
                                               const double (&mlo)[5], const double (&phi)[5],
                                               const bool (&in_mask)[2], double (&out)[5][2], double (&Uo)[2],
                                               double (&Wo)[2]) {
   OwnTerms o;
-  const PairFlags fl = rhs_pair_own(k, tb, c, in_mask, o);
+  const PairFlags fl = rhs_pair_own<kSched>(k, tb, c, in_mask, o);
   rhs_pair_finish(k, c, mlo, phi, o, out);
   Uo[0] = o.U[0];
   Uo[1] = o.U[1];

@@ -56,7 +56,9 @@ constexpr double kSqrtEps = 1.4901161193847656e-08;
 constexpr int kWarpsPerCta = 4;
 // resident CTAs per SM the kernel is compiled for: 4 x 4 warps = 16 columns in flight per SM at 128
 // registers per thread (measured r01b, 4096 columns: 4 -> 3.07 s, 6 -> 3.12 s, 8 -> 3.42 s: more
-// residency only adds spills, the sweeps are bound by memory latency, see the cp.async ring below)
+// residency only adds spills, the sweeps are bound by memory latency, see the cp.async ring below;
+// r01g, to t = 0.05: 3 CTAs (168 registers) 1.52-1.56 s, 4 CTAs 1.55-1.61 s, 5 CTAs (96 registers) 1.69 s;
+// ring depth MARLPDE_RADAU_DEPTH 2 / 3 / 4: 1.57 / 1.55 / 1.62 s)
 #ifndef MARLPDE_RADAU_MINBLOCKS
 #define MARLPDE_RADAU_MINBLOCKS 4
 #endif
@@ -100,7 +102,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #define RADAU_BATCH4 0
 #endif
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-constexpr int kDepth = 3;          // cells in flight ahead of the one being processed
+#ifndef MARLPDE_RADAU_DEPTH
+#define MARLPDE_RADAU_DEPTH 3
+#endif
+constexpr int kDepth = MARLPDE_RADAU_DEPTH;   // cells in flight ahead of the one being processed
 constexpr int kSlots = kDepth + 1;
 
 // per-column workspace, in doubles (n = 5 N): see radau_workspace_doubles()
@@ -193,7 +198,7 @@ __device__ __forceinline__ void rhs_column(const ColumnConsts& kc, const fm::Tab
     const bool in_mask[2] = {cell0 >= kc.mask_lo && cell0 < kc.mask_hi,
                              cell0 + 1 >= kc.mask_lo && cell0 + 1 < kc.mask_hi};
     double r[5][2], U[2], Wv[2];
-    PairFlags fl = rhs_pair(kc, tb, c, mlo, phi, in_mask, r, U, Wv);
+    PairFlags fl = rhs_pair<rhs_schedule(kSchedAll)>(kc, tb, c, mlo, phi, in_mask, r, U, Wv);
     fl.bad[0] = fl.bad[0] && v0;
     fl.bad[1] = fl.bad[1] && v1;
     if (fl.bad[0] || fl.bad[1]) rhs_pair_fixup(kc, tb, fl, c, mlo, phi, in_mask, r, U, Wv);

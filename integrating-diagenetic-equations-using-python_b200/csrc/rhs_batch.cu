@@ -3,12 +3,15 @@
 // Replaces one call of LMAHeureuxPorosityDiff.fun_numba -> pde_rhs per column
 // (marlpde/LHeureux_model.py:290-359, :361-522): y[column][field][cell] -> dy/dt, same layout.
 // One thread per PAIR of adjacent depth cells (the same rhs_pair code the persistent RK45 kernel
-// runs, so the single-call parity tests exercise the integrator's arithmetic); a CTA covers
+// runs, so the single-call parity tests exercise the integrators' arithmetic — every instruction schedule of
+// rhs_pair_own that an integrator instantiates can be selected with MARLPDE_RHS_SCHEDULE=0..3); a CTA covers
 // 2 * kPairsPerCta consecutive cells of one column.  Each thread reads its own two cells and one
 // neighbour on either side straight from global memory (the neighbours are L1 hits: they are the
 // adjacent threads' own cells).  40 B in + 40 B out per cell against ~200 fp64 instructions:
 // fp64-pipe bound, not HBM bound.
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 
 #include "lheureux_device.cuh"
 #include "rk45_persistent.cuh"
@@ -17,6 +20,7 @@ namespace marlpde {
 
 constexpr int kPairsPerCta = 128;
 
+template <int kSched>
 __global__ void __launch_bounds__(kPairsPerCta)
 rhs_batch_kernel(const double* __restrict__ g_y, const marlpde_column_params* __restrict__ g_params,
                  int n_cells, int tiles_per_col, double* __restrict__ g_out) {
@@ -51,7 +55,7 @@ rhs_batch_kernel(const double* __restrict__ g_y, const marlpde_column_params* __
   const bool in_mask[2] = {cell0 >= kc.mask_lo && cell0 < kc.mask_hi,
                            cell0 + 1 >= kc.mask_lo && cell0 + 1 < kc.mask_hi};
   double r[5][2], U[2], W[2];
-  PairFlags fl = rhs_pair(kc, tb, c, mlo, phi, in_mask, r, U, W);
+  PairFlags fl = rhs_pair<kSched>(kc, tb, c, mlo, phi, in_mask, r, U, W);
   fl.bad[0] = fl.bad[0] && valid0;
   fl.bad[1] = fl.bad[1] && valid1;
   if (fl.bad[0] || fl.bad[1]) rhs_pair_fixup(kc, tb, fl, c, mlo, phi, in_mask, r, U, W);
@@ -70,7 +74,16 @@ cudaError_t launch_rhs_batch(const double* d_y, const marlpde_column_params* d_p
   const int tiles = (pairs + kPairsPerCta - 1) / kPairsPerCta;
   const long long blocks = (long long)tiles * n_columns;
   if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
-  rhs_batch_kernel<<<(unsigned)blocks, kPairsPerCta, 0, stream>>>(d_y, d_params, n_cells, tiles, d_out);
+  // default: the schedule of the on-chip RK45 kernel; MARLPDE_RHS_SCHEDULE (read per call) selects another one
+  const char* env = std::getenv("MARLPDE_RHS_SCHEDULE");
+  const int sched = rhs_schedule(env && env[0] >= '0' && env[0] <= '3' && !env[1] ? env[0] - '0' : kSchedTwoArm);
+  const unsigned g = (unsigned)blocks;
+  switch (sched) {
+    case kSchedSplit: rhs_batch_kernel<kSchedSplit><<<g, kPairsPerCta, 0, stream>>>(d_y, d_params, n_cells, tiles, d_out); break;
+    case kSchedMerged: rhs_batch_kernel<kSchedMerged><<<g, kPairsPerCta, 0, stream>>>(d_y, d_params, n_cells, tiles, d_out); break;
+    case kSchedAll: rhs_batch_kernel<kSchedAll><<<g, kPairsPerCta, 0, stream>>>(d_y, d_params, n_cells, tiles, d_out); break;
+    default: rhs_batch_kernel<kSchedTwoArm><<<g, kPairsPerCta, 0, stream>>>(d_y, d_params, n_cells, tiles, d_out); break;
+  }
   return cudaGetLastError();
 }
 

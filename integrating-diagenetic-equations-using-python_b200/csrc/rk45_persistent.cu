@@ -179,6 +179,7 @@ struct Rk45Args {
   int32_t* g_ev_counts;      // [n_columns][7]
   double* g_ev_times;        // [n_columns][7][event_capacity]
   int n_columns, N, C, logG;
+  unsigned long long warp_perm;   // logical warp of physical warp w = (warp_perm >> 4 w) & 15 (see rk45_warp_perm)
   marlpde_rk45_options opt;
 };
 
@@ -186,7 +187,9 @@ template <int TP, bool YS, bool HS>
 __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel(const Rk45Args A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using L = Smem<TP, YS, HS>;
-  const int tid = threadIdx.x;
+  // logical thread index: physical warps may be dealt out to the column ranges in any order (warp_perm), which
+  // decides WHICH scheduler (physical warp & 3) runs the warps that carry the extra aragonite-power block
+  const int tid = (int)((A.warp_perm >> (4 * (threadIdx.x >> 5))) & 15ull) * 32 + (threadIdx.x & 31);
   const int N = A.N, C = A.C;
   const int Hc = (N + 1) >> 1;                     // threads per column
   double2* const sK = reinterpret_cast<double2*>(smem_raw + L::off_K) + tid;         // [4][5][TP]
@@ -581,7 +584,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
       // the part of the RHS that needs no neighbour runs while the barrier that publishes the neighbours'
       // stage inputs (arrived at below, at the end of the previous trip) is still pending
       OwnTerms own;
-      PairFlags fl = rhs_pair_own(kc, tb, c, in_mask, own);
+      PairFlags fl = rhs_pair_own<rhs_schedule(kSchedTwoArm)>(kc, tb, c, in_mask, own);
       if (i > i0) {
         mbar_wait(sBar, bar_parity);
         bar_parity ^= 1u;
@@ -771,6 +774,30 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
   }
 }
 
+// Warp order.  Ten warps over four schedulers is 3-3-2-2, and the warps whose lanes lie in the dissolution zone
+// evaluate one more real power per RHS: MARLPDE_RK45_WARP_PERM="l0,l1,..." (logical warp of physical warp 0, 1, ...)
+// lets those land on the schedulers that hold two warps.  Default: identity.  Results do not depend on it.
+static unsigned long long rk45_warp_perm(int n_warps) {
+  unsigned long long id = 0;
+  for (int w = 0; w < 16; ++w) id |= (unsigned long long)w << (4 * w);
+  const char* s = std::getenv("MARLPDE_RK45_WARP_PERM");
+  if (!s || n_warps > 16) return id;
+  unsigned long long p = 0;
+  unsigned seen = 0;
+  int w = 0;
+  while (*s && w < n_warps) {
+    char* end;
+    const long v = std::strtol(s, &end, 10);
+    if (end == s || v < 0 || v >= n_warps || (seen >> v & 1u)) return id;
+    seen |= 1u << v;
+    p |= (unsigned long long)v << (4 * w++);
+    s = *end == ',' ? end + 1 : end;
+  }
+  if (w != n_warps) return id;          // not a permutation of all warps: ignore
+  for (; w < 16; ++w) p |= (unsigned long long)w << (4 * w);
+  return p;
+}
+
 template <int TP, bool YS, bool HS>
 static cudaError_t launch_t(const Rk45Args& a, int sm_count, int smem_budget, cudaStream_t stream) {
   Rk45Args args = a;
@@ -785,6 +812,7 @@ static cudaError_t launch_t(const Rk45Args& a, int sm_count, int smem_budget, cu
   if (grid > sm_count) grid = sm_count;
   if (grid < 1) grid = 1;
   const int threads = ((args.C * Hc + 31) / 32) * 32;
+  args.warp_perm = rk45_warp_perm(threads / 32);
   rk45_persistent_kernel<TP, YS, HS><<<grid, threads, smem, stream>>>(args);
   return cudaGetLastError();
 }
@@ -806,6 +834,7 @@ cudaError_t launch_rk45(double* d_y, const marlpde_column_params* d_params, marl
   a.N = n_cells;
   a.C = 0;
   a.logG = 0;
+  a.warp_perm = 0;
   a.opt = opt;
   switch (rk45_variant()) {
     case 321: return launch_t<320, true, false>(a, sm_count, smem_budget, stream);

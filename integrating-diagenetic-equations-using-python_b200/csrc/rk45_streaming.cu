@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(kThreads, 3) stage_kernel(const Args A, int i,
   const bool in_mask[2] = {m.cell0 >= kc.mask_lo && m.cell0 < kc.mask_hi,
                            m.cell0 + 1 >= kc.mask_lo && m.cell0 + 1 < kc.mask_hi};
   double r[5][2], U[2], W[2];
-  PairFlags fl = rhs_pair(kc, tb, cc, mlo, phi, in_mask, r, U, W);
+  PairFlags fl = rhs_pair<rhs_schedule(kSchedSplit)>(kc, tb, cc, mlo, phi, in_mask, r, U, W);
   fl.bad[0] = fl.bad[0] && m.v0;
   fl.bad[1] = fl.bad[1] && m.v1;
   if (fl.bad[0] || fl.bad[1]) rhs_pair_fixup(kc, tb, fl, cc, mlo, phi, in_mask, r, U, W);
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
   for (int i = 1; i <= 6; ++i) {
     // the neighbour-free part of the RHS overlaps the pending barrier (see rk45_persistent.cu)
     OwnTerms own;
-    PairFlags fl = rhs_pair_own(kc, tb, c, in_mask, own);
+    PairFlags fl = rhs_pair_own<rhs_schedule(kSchedSplit)>(kc, tb, c, in_mask, own);
     if (i > 1) {
       mbar_wait(sBar, bar_parity);
       bar_parity ^= 1u;

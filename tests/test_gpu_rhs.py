@@ -95,3 +95,35 @@ def test_rhs_nonfinite_inputs_follow_ieee():
     assert not np.all(np.isfinite(out[0, :, 50]))
     assert np.all(np.isfinite(out[0, :, :49])) and np.all(np.isfinite(out[0, :, 52:]))
     assert np.all(np.isfinite(out[1]))
+
+
+@pytest.mark.parametrize("sched", [0, 1, 2, 3])
+def test_rhs_every_instruction_schedule(rhs_golden, sched, monkeypatch):
+    """rhs_pair_own exists in four instruction schedules (csrc/lheureux_device.cuh: kSchedSplit, kSchedMerged,
+    kSchedAll, kSchedTwoArm); each integrator kernel instantiates the one that is fastest for it.  All of them
+    must meet the single-call gate on the reference's golden states (default case: dissolution zone, evolved
+    fixture snapshots, noise), on a case with FV_switch = 0, and on IEEE special values."""
+    monkeypatch.setenv("MARLPDE_RHS_SCHEDULE", str(sched))
+    g, meta = rhs_golden
+    for name in ("default", "fv_off", "lattice_corner"):
+        pde = meta[name]
+        P = mb.derive_column_params(pde)
+        po = oracle.kernel_params(pde)
+        states = list(rhs_states(g, name))
+        Y = np.stack([s[1].reshape(5, -1) for s in states])
+        out = mb.rhs_batch(Y, np.repeat(P, len(states)))
+        for (sname, y, r_numba, _r_numpy, _ev), got in zip(states, out):
+            got = got.ravel()
+            assert np.array_equal(np.isnan(got), np.isnan(r_numba)), (name, sname)
+            assert _scaled_err(got, r_numba, y, po) <= TOL, (name, sname)
+    pde = oracle.default_scenario()
+    P = mb.derive_column_params(pde)
+    y = np.repeat(mb.initial_state(pde), 2, axis=0)
+    y[0, 4, 50] = 1.0
+    out = mb.rhs_batch(y, np.repeat(P, 2))
+    assert not np.all(np.isfinite(out[0, :, 50])) and np.all(np.isfinite(out[1]))
+    monkeypatch.delenv("MARLPDE_RHS_SCHEDULE")
+    ref = mb.rhs_batch(y, np.repeat(P, 2))                       # default schedule (the RK45 kernel's)
+    monkeypatch.setenv("MARLPDE_RHS_SCHEDULE", str(sched))
+    assert np.array_equal(np.isfinite(out), np.isfinite(ref))
+    assert np.allclose(out[1], ref[1], rtol=1e-12, atol=0.0)

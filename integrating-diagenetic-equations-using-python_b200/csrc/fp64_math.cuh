@@ -16,6 +16,10 @@
 #include <cmath>
 #include <cstdint>
 
+#ifndef MARLPDE_EXP_INTCHECK
+#define MARLPDE_EXP_INTCHECK 0
+#endif
+
 namespace marlpde {
 namespace fm {
 
@@ -160,7 +164,12 @@ __device__ __forceinline__ double log_nb(const Tables& tb, double x, bool& bad) 
 }
 
 __device__ __forceinline__ double exp_nb(const Tables& tb, double x, bool& bad) {
+#if MARLPDE_EXP_INTCHECK
+  // !(|x| < 690) on the high word: 690.0 = 0x4085900000000000 has a zero low word, NaN / inf compare above it
+  bad |= (unsigned)(__double2hiint(x) & 0x7fffffff) >= 0x40859000u;
+#else
   bad |= !(fabs(x) < 690.0);
+#endif
   double2 T;
   int k;
   const double p = exp_core<false>(tb, x, T, k);

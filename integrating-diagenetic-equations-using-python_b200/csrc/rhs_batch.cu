@@ -4,7 +4,7 @@
 // (marlpde/LHeureux_model.py:290-359, :361-522): y[column][field][cell] -> dy/dt, same layout.
 // One thread per PAIR of adjacent depth cells (the same rhs_pair code the persistent RK45 kernel
 // runs, so the single-call parity tests exercise the integrators' arithmetic — every instruction schedule of
-// rhs_pair_own that an integrator instantiates can be selected with MARLPDE_RHS_SCHEDULE=0..3); a CTA covers
+// rhs_pair_own that an integrator instantiates can be selected with MARLPDE_RHS_SCHEDULE=0..4); a CTA covers
 // 2 * kPairsPerCta consecutive cells of one column.  Each thread reads its own two cells and one
 // neighbour on either side straight from global memory (the neighbours are L1 hits: they are the
 // adjacent threads' own cells).  40 B in + 40 B out per cell against ~200 fp64 instructions:
@@ -76,13 +76,14 @@ cudaError_t launch_rhs_batch(const double* d_y, const marlpde_column_params* d_p
   if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
   // default: the schedule of the on-chip RK45 kernel; MARLPDE_RHS_SCHEDULE (read per call) selects another one
   const char* env = std::getenv("MARLPDE_RHS_SCHEDULE");
-  const int sched = rhs_schedule(env && env[0] >= '0' && env[0] <= '3' && !env[1] ? env[0] - '0' : kSchedTwoArm);
+  const int sched = rhs_schedule(env && env[0] >= '0' && env[0] <= '4' && !env[1] ? env[0] - '0' : kSchedLean);
   const unsigned g = (unsigned)blocks;
   switch (sched) {
     case kSchedSplit: rhs_batch_kernel<kSchedSplit><<<g, kPairsPerCta, 0, stream>>>(d_y, d_params, n_cells, tiles, d_out); break;
     case kSchedMerged: rhs_batch_kernel<kSchedMerged><<<g, kPairsPerCta, 0, stream>>>(d_y, d_params, n_cells, tiles, d_out); break;
+    default: rhs_batch_kernel<kSchedLean><<<g, kPairsPerCta, 0, stream>>>(d_y, d_params, n_cells, tiles, d_out); break;
     case kSchedAll: rhs_batch_kernel<kSchedAll><<<g, kPairsPerCta, 0, stream>>>(d_y, d_params, n_cells, tiles, d_out); break;
-    default: rhs_batch_kernel<kSchedTwoArm><<<g, kPairsPerCta, 0, stream>>>(d_y, d_params, n_cells, tiles, d_out); break;
+    case kSchedTwoArm: rhs_batch_kernel<kSchedTwoArm><<<g, kPairsPerCta, 0, stream>>>(d_y, d_params, n_cells, tiles, d_out); break;
   }
   return cudaGetLastError();
 }

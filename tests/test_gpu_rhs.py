@@ -97,10 +97,10 @@ def test_rhs_nonfinite_inputs_follow_ieee():
     assert np.all(np.isfinite(out[1]))
 
 
-@pytest.mark.parametrize("sched", [0, 1, 2, 3])
+@pytest.mark.parametrize("sched", [0, 1, 2, 3, 4])
 def test_rhs_every_instruction_schedule(rhs_golden, sched, monkeypatch):
-    """rhs_pair_own exists in four instruction schedules (csrc/lheureux_device.cuh: kSchedSplit, kSchedMerged,
-    kSchedAll, kSchedTwoArm); each integrator kernel instantiates the one that is fastest for it.  All of them
+    """rhs_pair_own exists in five instruction schedules (csrc/lheureux_device.cuh: kSchedSplit, kSchedMerged,
+    kSchedAll, kSchedTwoArm, kSchedLean); each integrator kernel instantiates the one that is fastest for it.  All of them
     must meet the single-call gate on the reference's golden states (default case: dissolution zone, evolved
     fixture snapshots, noise), on a case with FV_switch = 0, and on IEEE special values."""
     monkeypatch.setenv("MARLPDE_RHS_SCHEDULE", str(sched))

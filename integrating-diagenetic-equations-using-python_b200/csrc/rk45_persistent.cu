@@ -114,6 +114,7 @@ int rk45_max_cells() { return 640; }   // (the 416 build would take 832; the ABI
 // OR-reduction of 21 bits per thread (3 per monitor: beyond the threshold / on it / NaN) that
 // rides on the error-norm barrier — no fp64 reduction unless a sign change has to be located.
 constexpr unsigned kMaxTypeMask = (1u << 3) | (1u << 4) | (1u << 6);   // monitors that are a max
+constexpr unsigned kEqBitsMask = 0x92492u;                              // the "on the threshold" bit of every monitor
 
 __device__ __forceinline__ unsigned event_bits(const double (&v)[5][2], const double (&U)[2],
                                                const double (&W)[2], bool has1) {
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
   const unsigned peers = __match_any_sync(0xffffffffu, active ? slot : -1);
   const bool peer_lead = (tid & 31) == (__ffs(peers) - 1);
   const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((tid & 31) & ~(G - 1));
-  unsigned ev_prev = 0, ev_new_s = 0, ev_todo = 0;   // sign classes at y / at the parked y_new; monitors to locate
+  unsigned ev_prev = 0, ev_new_s = 0, ev_todo = 0;   // predicate bits at y / at the parked y_new; monitors to locate
   bool need_prev = false, parked = false;
   double factor_s = 1.0;
   unsigned it = 0;                                    // loop counter (parity selects the sEv buffer)
@@ -782,7 +783,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
       unsigned ev_bits_new = 0u;
       if (ev_on) {
         if (need_prev) {
-          ev_prev = event_classes(sEv0[slot]);
+          ev_prev = sEv0[slot];
           need_prev = false;
         }
         ev_bits_new = sEv[(it & 1u) * C + slot];
@@ -792,8 +793,12 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
         double factor = dp::MAX_FACTOR;
         if (err_norm != 0.0) factor = fmin(dp::MAX_FACTOR, dp::SAFETY * fm::exp(tb, -0.2 * fm::log(tb, err_norm)));
         if (rejected) factor = fmin(1.0, factor);
-        const unsigned ev_new = event_classes(ev_bits_new);
-        const unsigned act = ev_on ? active_events(ev_prev, ev_new) : 0u;
+        // Same predicate bits as at the step's start and no monitor exactly on its threshold: the sign classes
+        // are equal and none is "zero", so find_active_events reports nothing — skip the 7-monitor classification.
+        const unsigned ev_new = ev_bits_new;
+        unsigned act = 0u;
+        if (ev_on && (ev_new != ev_prev || (ev_new & kEqBitsMask) != 0u))
+          act = active_events(event_classes(ev_prev), event_classes(ev_new));
         if (act) {           // park the step: its events are located in the slot-service phase, then it commits
           parked = true;
           ev_todo = act;

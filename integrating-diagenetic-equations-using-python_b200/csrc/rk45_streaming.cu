@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
   for (int i = 1; i <= 6; ++i) {
     // the neighbour-free part of the RHS overlaps the pending barrier (see rk45_persistent.cu)
     OwnTerms own;
-    PairFlags fl = rhs_pair_own<rhs_schedule(kSchedSplit)>(kc, tb, c, in_mask, own);
+    PairFlags fl = rhs_pair_own<rhs_schedule(kSchedLean)>(kc, tb, c, in_mask, own);
     if (i > 1) {
       mbar_wait(sBar, bar_parity);
       bar_parity ^= 1u;

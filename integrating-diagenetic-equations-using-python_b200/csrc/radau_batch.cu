@@ -126,7 +126,7 @@ __host__ __device__ inline size_t work_doubles(int N) {
 
 struct __align__(16) WarpScratch {          // shared memory per warp
   ColumnConsts kc;
-  double2 vec[2][2][8];       // solve: two broadcast buffers x two systems x 5 entries (padded)
+  double2 vec[2][2][2][8];    // solve: two broadcast buffers x two chains x two systems x 5 entries (padded)
   // factorise (lane = 5 r + c holds entry (r, c) of [S | I] of both systems):
   double2 g0[2][32];          //   double-buffered exchange stage, real system: (S entry, I entry)
   double2 g1a[2][32];         //   complex system, S entries
@@ -135,8 +135,12 @@ struct __align__(16) WarpScratch {          // shared memory per warp
   double2 x1[26];             //   X_{i-1} = S_{i-1}^{-1} U_{i-1}, complex system (row major)
   double sinv0[26];           //   S_i^{-1} of the real system
   double x0[26];              //   X_{i-1}, real system
-  double jst[kSlots][80];     // factorise: staged Jacobian blocks [L|D|U] of cells i .. i+kDepth (ring)
-  double mst[kSlots][52];     // solve: 51 eight-byte words of a cell's fp32 record, cells i .. i+kDepth
+  double2 xs1[26];            //   X of the last cell of the top chain, kept for the meeting cell (complex system)
+  double xs0[26];             //   same, real system
+  union {                     // factorise and solve never overlap (each drains its cp.async groups before it returns)
+    double jst[kSlots][80];      // factorise: staged Jacobian blocks [L|D|U] of the next cells of the schedule (ring)
+    double mst[2][kSlots][52];   // solve: per chain, 51 eight-byte words of a cell's fp32 record (ring)
+  };
 };
 
 struct Args {
@@ -386,17 +390,25 @@ __device__ __forceinline__ unsigned pivot_key(double mag, int r, bool candidate)
   return candidate ? ((__float_as_uint((float)mag) & ~7u) | (unsigned)(7 - r)) : 0u;
 }
 
+// TWO-ENDED ("twisted") elimination: cells 0 .. mid-1 are eliminated top-down (S_i = M I - D_i - L_i X_{i-1},
+// X_i = S_i^{-1} U_i), cells N-1 .. mid+1 bottom-up with the roles of L and U swapped (T_i = M I - D_i - U_i Y_{i+1},
+// Y_i = T_i^{-1} L_i), and the two chains meet in cell mid = N/2: S_mid = M I - D_mid - L_mid X_{mid-1} - U_mid Y_{mid+1}.
+// Same flops as the one-directional sweep; what it buys is that the SOLVES run both chains side by side in the two
+// halves of the warp (half as many sequential steps, see solve()).  One loop over a schedule of N steps — top chain,
+// bottom chain, meeting cell — keeps a single instance of the elimination code.
 __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double h, const double* J, float* Rec) {
   const int l = lane < 25 ? lane : 0;     // lanes 25-31 shadow lane 0 (same values to the same shared words)
   const int r = l / 5, c = l - 5 * r;
   const bool diag = r == c;
   const double M0 = kMuReal / h;
   const double2 M1 = make_double2(kMuCRe / h, kMuCIm / h);
-  // ring of kSlots staged cells: cells 0 .. kDepth-1 are requested up front, cell i+kDepth at iteration i
-  auto request = [&](int cell) {
-    if (cell < N) {
-      const double* Jn = J + (size_t)cell * 75;
-      double* dst = ws.jst[cell % kSlots];
+  const int mid = N / 2;
+  auto cell_of = [&](int j) { return j < mid ? j : (j < N - 1 ? N - 1 - (j - mid) : mid); };
+  // ring of kSlots staged cells: steps 0 .. kDepth-1 are requested up front, step j+kDepth at iteration j
+  auto request = [&](int j) {
+    if (j < N) {
+      const double* Jn = J + (size_t)cell_of(j) * 75;
+      double* dst = ws.jst[j % kSlots];
 #pragma unroll
       for (int k = 0; k < 3; ++k)
         if (lane + 32 * k < 75) cp_async8(dst + lane + 32 * k, Jn + lane + 32 * k);
@@ -407,24 +419,46 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
   ws.x0[l] = 0.0;                                            // X_{-1} = 0
   ws.x1[l] = make_double2(0.0, 0.0);
 #pragma unroll 1
-  for (int i = 0; i < N; ++i) {
-    request(i + kDepth);                  // slot (i + kDepth) % kSlots was released at the end of iteration i-1
-    cp_async_wait<kDepth>();              // all but the kDepth newest groups have landed: cell i is in shared memory
+  for (int j = 0; j < N; ++j) {
+    request(j + kDepth);                  // slot (j + kDepth) % kSlots was released at the end of iteration j-1
+    cp_async_wait<kDepth>();              // all but the kDepth newest groups have landed: step j is in shared memory
+    const int i = cell_of(j);
+    const bool middle = j == N - 1, bottom = !middle && j >= mid;
+    if (j == mid) {                       // the top chain is complete: keep its X for the meeting cell, restart from 0
+      ws.xs0[l] = ws.x0[l];
+      ws.xs1[l] = ws.x1[l];
+      ws.x0[l] = 0.0;
+      ws.x1[l] = make_double2(0.0, 0.0);
+    }
     __syncwarp();
-    const double* Ji = ws.jst[i % kSlots];
+    const double* Ji = ws.jst[j % kSlots];
     float* const rec = Rec + (size_t)i * 128;
     if (lane < 25) {                                         // fp32 copies of L_i and U_i for the sweeps
       rec[lane] = (float)Ji[lane];
       rec[102 + lane] = (float)Ji[50 + lane];
     }
-    // entry (r, c) of S = M I - D_i - L_i X_{i-1}  and of the identity
+    const int offP = bottom ? 50 : 0;     // block that couples to the PREVIOUS cell of the chain (L top-down, U bottom-up)
+    const int offN = bottom ? 0 : 50;     // block that couples to the NEXT cell of the chain
+    // entry (r, c) of S = M I - D_i - P_i X_prev (- U_i Y_{i+1} in the meeting cell)  and of the identity
     double A0 = (diag ? M0 : 0.0) - Ji[25 + c * 5 + r];
     double2 A1 = make_double2((diag ? M1.x : 0.0) - Ji[25 + c * 5 + r], diag ? M1.y : 0.0);
+    {
+      const double* xp0 = middle ? ws.xs0 : ws.x0;
+      const double2* xp1 = middle ? ws.xs1 : ws.x1;
 #pragma unroll
-    for (int m = 0; m < 5; ++m) {
-      const double nl = -Ji[m * 5 + r];
-      A0 = fma(nl, ws.x0[m * 5 + c], A0);
-      A1 = crfma(nl, ws.x1[m * 5 + c], A1);
+      for (int m = 0; m < 5; ++m) {
+        const double nl = -Ji[offP + m * 5 + r];
+        A0 = fma(nl, xp0[m * 5 + c], A0);
+        A1 = crfma(nl, xp1[m * 5 + c], A1);
+      }
+    }
+    if (middle) {
+#pragma unroll
+      for (int m = 0; m < 5; ++m) {
+        const double nu = -Ji[50 + m * 5 + r];
+        A0 = fma(nu, ws.x0[m * 5 + c], A0);
+        A1 = crfma(nu, ws.x1[m * 5 + c], A1);
+      }
     }
     double B0 = diag ? 1.0 : 0.0;
     double2 B1 = make_double2(diag ? 1.0 : 0.0, 0.0);
@@ -480,137 +514,141 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
       reinterpret_cast<float2*>(rec + 52)[step1 * 5 + c] = make_float2((float)B1.x, (float)B1.y);
     }
     __syncwarp();
-    // ---- X_i = S_i^{-1} U_i for the next cell, while U_i is staged
+    // ---- X_i = S_i^{-1} N_i for the next cell of the chain, while N_i is staged
     double X0 = 0.0;
     double2 X1 = make_double2(0.0, 0.0);
 #pragma unroll
     for (int m = 0; m < 5; ++m) {
-      const double u = Ji[50 + c * 5 + m];
+      const double u = Ji[offN + c * 5 + m];
       X0 = fma(u, ws.sinv0[r * 5 + m], X0);
       X1 = crfma(u, ws.sinv1[r * 5 + m], X1);
     }
     ws.x0[l] = X0;
     ws.x1[l] = X1;
-    __syncwarp();                         // everyone is done with slot i % kSlots before it is requested again
+    __syncwarp();                         // everyone is done with slot j % kSlots before it is requested again
   }
   cp_async_wait<0>();
+  __syncwarp();
 }
 
-// Solve (M I - J) x = b for both systems by the block-Thomas sweeps.  lane = 8 s + r (r < 5):
-// system s, row r.  b0: real right-hand side of system 0; (b1, b2): real and imaginary part of the
-// right-hand side of system 1; all field-major [5][N], overwritten with the solution.
-// `both` = false solves system 0 only (error estimate).
-// As in factorise(), the matrices of the NEXT cell (one real 5x5 block of J and S^{-1} of both
-// systems, 125 doubles) are fetched by all 32 lanes while the current cell is processed and handed
-// over through shared memory; the right-hand side entry of the next cell is prefetched as well.
+// Solve (M I - J) x = b for both systems with the two-ended factors of factorise().  lane = 16 ch + 8 s + r (r < 5):
+// chain ch (0: cells 0 .. mid-1 top-down, 1: cells N-1 .. mid+1 bottom-up), system s, row r.  b0: real right-hand
+// side of system 0; (b1, b2): real and imaginary part of the right-hand side of system 1; all CELL-major [N][5],
+// overwritten with the solution.  `both` = false solves system 0 only (error estimate).
+//   inward :  top    p_i = S_i^{-1} (b_i + L_i p_{i-1}),   bottom q_i = T_i^{-1} (b_i + U_i q_{i+1})      (lock-step)
+//   meeting:  x_mid  = S_mid^{-1} (b_mid + L_mid p_{mid-1} + U_mid q_{mid+1})
+//   outward:  top    x_i = p_i + S_i^{-1} (U_i x_{i+1}),    bottom x_i = q_i + T_i^{-1} (L_i x_{i-1})     (lock-step)
+// Both chains of both systems run side by side in one warp, so a solve takes N/2 sequential steps per direction
+// instead of N.  As in factorise(), the records of the next kDepth cells of each chain are in flight (cp.async)
+// while the current cell is processed; a sweep reads 51 eight-byte words of a cell's record: words [0,51) =
+// {L, S0, S1} (top inward, bottom outward) or words [13,64) = {S0, S1, U} (bottom inward, top outward).
 __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const float* Rec, double* b0,
                                    double* b1, double* b2, bool both) {
-  const int s = (lane >> 3) & 1, r = lane & 7;
-  const bool valid = lane < 16 && r < 5 && (s == 0 || both);
+  const int ch = lane >> 4, s = (lane >> 3) & 1, r = lane & 7, l16 = lane & 15;
+  const bool valid = r < 5 && (s == 0 || both);
   double* const bre = s == 0 ? b0 : b1;
   double* const bim = s == 0 ? nullptr : b2;
-  // a sweep reads 51 eight-byte words of a cell's record: forward words [0,51) = {L, S0, S1}, backward words
-  // [13,64) = {S0, S1, U} (both runs contiguous, 8-byte aligned)
-  auto request = [&](int i, int first_word, int slot, bool ok) {
-    if (ok) {
-      const double* src = reinterpret_cast<const double*>(Rec + (size_t)i * 128) + first_word;
-      double* dst = ws.mst[slot];
-      cp_async8(dst + lane, src + lane);
-      if (lane + 32 < 51) cp_async8(dst + lane + 32, src + lane + 32);
+  const int mid = N / 2;
+  const int nch = ch == 0 ? mid : N - 1 - mid;               // cells of my chain
+  const int nmax = mid;                                      // (the top chain is never the shorter one)
+  auto ldb = [&](int i) { return make_double2(bre[i * 5 + r], bim ? bim[i * 5 + r] : 0.0); };
+  auto stb = [&](int i, double2 v) {
+    bre[i * 5 + r] = v.x;
+    if (bim) bim[i * 5 + r] = v.y;
+  };
+  // 5x5 block (fp32, row stride / column stride given) times the 5-vector published in vec[buf][chv][s][.]
+  auto s_times = [&](const float* S0, const float* S1, int buf, int chv, double2 acc) {
+    const float* S0r = S0 + r * 5;
+    const float2* S1r = reinterpret_cast<const float2*>(S1) + r * 5;
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+      const double2 sv = s == 0 ? make_double2((double)S0r[m], 0.0) : make_double2((double)S1r[m].x, (double)S1r[m].y);
+      acc = cfma(sv, ws.vec[buf][chv][s][m], acc);
     }
-    cp_async_commit();
+    return acc;
   };
   int buf = 0;
-  for (int c0 = 0; c0 < kDepth; ++c0) request(c0, 0, c0 % kSlots, c0 < N);
-  // forward record in shared memory (floats): L [0,25), S0 [26,51), S1 float2 from float 52
-  // ---- forward: g_i = b_i + L_i p_{i-1},  p_i = S_i^{-1} g_i  (p overwrites b)
-  double2 p = make_double2(0.0, 0.0);
-  double2 bnext = valid ? make_double2(bre[r], bim ? bim[r] : 0.0) : make_double2(0.0, 0.0);
-#pragma unroll 1
-  for (int i = 0; i < N; ++i) {
-    request(i + kDepth, 0, (i + kDepth) % kSlots, i + kDepth < N);
-    cp_async_wait<kDepth>();
-    __syncwarp();
-    const float* M = reinterpret_cast<const float*>(ws.mst[i % kSlots]);
-    const bool more = i + 1 < N;
-    if (RADAU_PF_SOLVE && valid && r == 0 && i + 8 < N) {
-      prefetch_l1(bre + (i + 8) * 5);
-      if (bim) prefetch_l1(bim + (i + 8) * 5);
-    }
-    double2 g = bnext;
-    if (valid && more) bnext = make_double2(bre[(i + 1) * 5 + r], bim ? bim[(i + 1) * 5 + r] : 0.0);
-    if (valid) ws.vec[buf][s][r] = p;
-    __syncwarp();
-    if (valid && i > 0) {
+  double2 v = make_double2(0.0, 0.0);     // inward: p / q of the chain's previous cell; outward: x of it
+
+  // one lock-step pass over both chains; `outward` = false: cells 0.. and N-1.. towards the meeting cell
+  auto sweep = [&](const bool outward) {
+    auto cell = [&](int j) { return outward ? (ch == 0 ? mid - 1 - j : mid + 1 + j) : (ch == 0 ? j : N - 1 - j); };
+    const bool low_window = (ch == 0) != outward;            // words [0,51): {L, S0, S1}; else [13,64): {S0, S1, U}
+    const int oC = low_window ? 0 : 76, oS0 = low_window ? 26 : 0, oS1 = low_window ? 52 : 26;   // float offsets
+    auto request = [&](int j) {
+      if (j < nch) {
+        const double* src = reinterpret_cast<const double*>(Rec + (size_t)cell(j) * 128) + (low_window ? 0 : 13);
+        double* dst = ws.mst[ch][j % kSlots];
 #pragma unroll
-      for (int m = 0; m < 5; ++m) g = crfma((double)M[m * 5 + r], ws.vec[buf][s][m], g);
+        for (int k = 0; k < 4; ++k)
+          if (l16 + 16 * k < 51) cp_async8(dst + l16 + 16 * k, src + l16 + 16 * k);
+      }
+      cp_async_commit();                                     // (empty groups keep the group count uniform)
+    };
+    for (int c0 = 0; c0 < kDepth; ++c0) request(c0);
+    double2 bnext = (valid && nch > 0) ? ldb(cell(0)) : make_double2(0.0, 0.0);
+#pragma unroll 1
+    for (int j = 0; j < nmax; ++j) {
+      request(j + kDepth);
+      cp_async_wait<kDepth>();
+      __syncwarp();
+      const float* M = reinterpret_cast<const float*>(ws.mst[ch][j % kSlots]);
+      const bool act = valid && j < nch;
+      const double2 bi = bnext;
+      if (valid && j + 1 < nch) bnext = ldb(cell(j + 1));
+      if (valid) ws.vec[buf][ch][s][r] = v;
+      __syncwarp();
+      // coupling block times the previous cell's vector: inward it joins the right-hand side, outward it is what
+      // S^{-1} is applied to
+      double2 g = outward ? make_double2(0.0, 0.0) : bi;
+      if (act && (outward || j > 0)) {
+#pragma unroll
+        for (int m = 0; m < 5; ++m) g = crfma((double)M[oC + m * 5 + r], ws.vec[buf][ch][s][m], g);
+      }
+      buf ^= 1;
+      if (valid) ws.vec[buf][ch][s][r] = g;
+      __syncwarp();
+      if (act) {
+        v = s_times(M + oS0, M + oS1, buf, ch, outward ? bi : make_double2(0.0, 0.0));
+        stb(cell(j), v);
+      }
+      buf ^= 1;
+      __syncwarp();
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+  };
+
+  sweep(false);
+  // ---- meeting cell: g = b_mid + L_mid p_{mid-1} + U_mid q_{mid+1}, x_mid = S_mid^{-1} g.  Its record is read
+  // straight from global memory (once per solve); both halves of the warp compute the same x_mid.
+  {
+    const float* Rm = Rec + (size_t)mid * 128;
+    if (valid) ws.vec[buf][ch][s][r] = v;                    // p_{mid-1} (chain 0), q_{mid+1} (chain 1)
+    __syncwarp();
+    double2 g = make_double2(0.0, 0.0);
+    if (valid) {
+      g = ldb(mid);
+      if (mid > 0) {
+#pragma unroll
+        for (int m = 0; m < 5; ++m) g = crfma((double)Rm[m * 5 + r], ws.vec[buf][0][s][m], g);
+      }
+      if (N - 1 - mid > 0) {
+#pragma unroll
+        for (int m = 0; m < 5; ++m) g = crfma((double)Rm[102 + m * 5 + r], ws.vec[buf][1][s][m], g);
+      }
     }
     buf ^= 1;
-    if (valid) ws.vec[buf][s][r] = g;
+    if (valid && ch == 0) ws.vec[buf][0][s][r] = g;
     __syncwarp();
     if (valid) {
-      const float* S0r = M + 26 + r * 5;
-      const float2* S1r = reinterpret_cast<const float2*>(M + 52) + r * 5;
-      double2 acc = make_double2(0.0, 0.0);
-#pragma unroll
-      for (int m = 0; m < 5; ++m) {
-        const double2 sv = s == 0 ? make_double2((double)S0r[m], 0.0) : make_double2((double)S1r[m].x, (double)S1r[m].y);
-        acc = cfma(sv, ws.vec[buf][s][m], acc);
-      }
-      p = acc;
-      bre[i * 5 + r] = p.x;
-      if (bim) bim[i * 5 + r] = p.y;
+      v = s_times(Rm + 26, Rm + 52, buf, 0, make_double2(0.0, 0.0));
+      if (ch == 0) stb(mid, v);
     }
     buf ^= 1;
     __syncwarp();
   }
-  cp_async_wait<0>();
-  if (N < 2) return;
-  // ---- backward: x_{N-1} = p_{N-1},  x_i = p_i + S_i^{-1} (U_i x_{i+1});  step j handles cell N-2-j
-  // backward record in shared memory (floats): S0 [0,25), S1 float2 from float 26, U [76,101)
-  for (int c0 = 0; c0 < kDepth; ++c0) request(N - 2 - c0 < 0 ? 0 : N - 2 - c0, 13, c0 % kSlots, N - 2 - c0 >= 0);
-  double2 x = p;
-  bnext = valid ? make_double2(bre[(N - 2) * 5 + r], bim ? bim[(N - 2) * 5 + r] : 0.0) : make_double2(0.0, 0.0);
-#pragma unroll 1
-  for (int i = N - 2, j = 0; i >= 0; --i, ++j) {
-    request(i - kDepth < 0 ? 0 : i - kDepth, 13, (j + kDepth) % kSlots, i - kDepth >= 0);
-    cp_async_wait<kDepth>();
-    __syncwarp();
-    const float* M = reinterpret_cast<const float*>(ws.mst[j % kSlots]);
-    const bool more = i > 0;
-    if (RADAU_PF_SOLVE && valid && r == 0 && i >= 8) {
-      prefetch_l1(bre + (i - 8) * 5);
-      if (bim) prefetch_l1(bim + (i - 8) * 5);
-    }
-    const double2 pi = bnext;
-    if (valid && more) bnext = make_double2(bre[(i - 1) * 5 + r], bim ? bim[(i - 1) * 5 + r] : 0.0);
-    if (valid) ws.vec[buf][s][r] = x;
-    __syncwarp();
-    double2 u = make_double2(0.0, 0.0);
-    if (valid) {
-#pragma unroll
-      for (int m = 0; m < 5; ++m) u = crfma((double)M[76 + m * 5 + r], ws.vec[buf][s][m], u);
-    }
-    buf ^= 1;
-    if (valid) ws.vec[buf][s][r] = u;
-    __syncwarp();
-    if (valid) {
-      const float* S0r = M + r * 5;
-      const float2* S1r = reinterpret_cast<const float2*>(M + 26) + r * 5;
-      double2 acc = pi;
-#pragma unroll
-      for (int m = 0; m < 5; ++m) {
-        const double2 sv = s == 0 ? make_double2((double)S0r[m], 0.0) : make_double2((double)S1r[m].x, (double)S1r[m].y);
-        acc = cfma(sv, ws.vec[buf][s][m], acc);
-      }
-      x = acc;
-      bre[i * 5 + r] = x.x;
-      if (bim) bim[i * 5 + r] = x.y;
-    }
-    buf ^= 1;
-    __syncwarp();
-  }
-  cp_async_wait<0>();
+  sweep(true);
 }
 
 // The seven event monitors (LHeureux_model.py:524-593) of the state val(f, i), by one warp:

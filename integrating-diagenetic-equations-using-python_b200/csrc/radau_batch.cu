@@ -54,13 +54,12 @@ constexpr double kEps = 2.220446049250313e-16;
 constexpr double kSqrtEps = 1.4901161193847656e-08;
 
 constexpr int kWarpsPerCta = 4;
-// resident CTAs per SM the kernel is compiled for: 4 x 4 warps = 16 columns in flight per SM at 128
-// registers per thread (measured r01b, 4096 columns: 4 -> 3.07 s, 6 -> 3.12 s, 8 -> 3.42 s: more
-// residency only adds spills, the sweeps are bound by memory latency, see the cp.async ring below;
-// r01g, to t = 0.05: 3 CTAs (168 registers) 1.52-1.56 s, 4 CTAs 1.55-1.61 s, 5 CTAs (96 registers) 1.69 s;
-// ring depth MARLPDE_RADAU_DEPTH 2 / 3 / 4: 1.57 / 1.55 / 1.62 s)
+// resident CTAs per SM the kernel is compiled for: 3 x 4 warps = 12 columns in flight per SM at 168 registers per
+// thread.  Measured on 4096 columns to t = 0.05: r01b 4 -> 3.07 s, 6 -> 3.12 s, 8 -> 3.42 s (more residency only adds
+// spills); r01g 3 / 4 / 5 CTAs 1.52-1.56 / 1.55-1.61 / 1.69 s; r01h (two-ended sweeps) 2 / 3 / 4 CTAs 1.556 / 1.490 /
+// 1.531 s.  Ring depth MARLPDE_RADAU_DEPTH 2 / 3 / 4: 1.57 / 1.55 / 1.62 s.
 #ifndef MARLPDE_RADAU_MINBLOCKS
-#define MARLPDE_RADAU_MINBLOCKS 4
+#define MARLPDE_RADAU_MINBLOCKS 3
 #endif
 
 // ---- complex helpers (double2 = re, im) -------------------------------------------------------

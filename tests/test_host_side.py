@@ -215,3 +215,50 @@ def test_offdiagonal_jacobian_block_formulas(fixtures_reference, name, over, sna
             assert np.abs(J[np.ix_(rows, [f * N + i - 1 for f in range(5)])] - L).max() <= 1e-8 * scale
         if i < N - 1:
             assert np.abs(J[np.ix_(rows, [f * N + i + 1 for f in range(5)])] - Ub).max() <= 1e-8 * scale
+
+
+@pytest.mark.parametrize("n_cells", [1, 2, 3, 4, 5, 37, 200])
+def test_two_ended_block_thomas_against_dense_solve(n_cells):
+    """The linear algebra of the Radau kernel (csrc/radau_batch.cu factorise / solve: cells 0 .. N/2-1 eliminated
+    top-down, N-1 .. N/2+1 bottom-up, meeting cell N/2; both chains of a solve in lock-step), restated in numpy
+    (oracle/twisted_block_thomas.py), against a dense solve — for the real and the complex shift of scipy's Radau
+    on the block-tridiagonal finite-difference Jacobian of the oracle RHS, and on random blocks for the tiny grids."""
+    import twisted_block_thomas as tw
+    rng = np.random.default_rng(n_cells)
+    if n_cells >= 37:
+        pde = oracle.default_scenario() | {"N": n_cells, "Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}
+        po = oracle.kernel_params(pde)
+        y = (mb.initial_state(pde)[0] * (1 + 0.05 * rng.uniform(-1, 1, (5, n_cells)))).ravel()
+        n = 5 * n_cells
+        f0 = oracle.rhs(y, po, np.empty(n)).copy()
+        Jf = np.empty((n, n))
+        for j in range(n):
+            d = 1e-7 * max(1e-3, abs(y[j]))
+            yp = y.copy()
+            yp[j] += d
+            Jf[:, j] = (oracle.rhs(yp, po, np.empty(n)) - f0) / d
+        perm = np.arange(n).reshape(5, n_cells).T.ravel()           # field-major -> cell-major
+        Jc = Jf[np.ix_(perm, perm)]
+        blk = lambda i, k: Jc[5 * i:5 * i + 5, 5 * k:5 * k + 5]
+        D = np.stack([blk(i, i) for i in range(n_cells)])
+        L = np.stack([blk(i, i - 1) if i > 0 else np.zeros((5, 5)) for i in range(n_cells)])
+        U = np.stack([blk(i, i + 1) if i < n_cells - 1 else np.zeros((5, 5)) for i in range(n_cells)])
+        # the Jacobian IS block tridiagonal in cell-major order (SURVEY.md 8a)
+        T = np.zeros_like(Jc)
+        for i in range(n_cells):
+            for k in (i - 1, i, i + 1):
+                if 0 <= k < n_cells:
+                    T[5 * i:5 * i + 5, 5 * k:5 * k + 5] = blk(i, k)
+        assert np.max(np.abs(Jc - T)) <= 1e-6 * np.max(np.abs(Jc))
+        h = 1e-4
+    else:
+        D = rng.normal(size=(n_cells, 5, 5))
+        L = 0.3 * rng.normal(size=(n_cells, 5, 5))
+        U = 0.3 * rng.normal(size=(n_cells, 5, 5))
+        h = 0.05
+    for M in (3.637834252744496 / h, complex(2.6810828736277523, -3.050430199247411) / h):   # radau.py MU_REAL, MU_COMPLEX
+        rhs = rng.normal(size=5 * n_cells)
+        x = tw.solve(L, U, tw.factor(L, D, U, M), rhs)
+        ref = np.linalg.solve(tw.dense(L, D, U, M), rhs)
+        assert np.max(np.abs(x - ref)) <= 1e-11 * np.max(np.abs(ref))
+

@@ -29,6 +29,39 @@ namespace fm {
 __constant__ double kLog1pC[6] = {-0.5, 1.0 / 3.0, -0.25, 0.2, -1.0 / 6.0, 1.0 / 7.0};
 __constant__ double kExpC[5] = {0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0};
 
+// MARLPDE_FP64_IMM=1 (experimental, OFF: not yet measured on a GPU): every constant that tolerates it is replaced by a
+// double whose low 32 bits are zero, which sm_100a encodes as an instruction immediate (Blackwell has no constant-
+// bank operands: each other constant costs an LDC and a register pair per basic block — 37 LDC per RHS of a cell pair).
+// Exactly representable: -1/2, -1/4, 1/2.  Rounded to 21 significant bits: the r^5, r^6 terms of log1p and the r^5, r^6
+// terms of exp (error <= 1e-19), 64/ln2 (only picks the reduction integer), and the HIGH parts of the ln2 and ln2/64
+// splits (the low parts absorb the difference; n * hi stays exact).  1/3, 1/7, 1/6, 1/24 and the low parts stay full
+// doubles.  Accuracy with an exact-FMA model of these routines against mpmath (20 000 samples, same ranges as
+// tests/test_gpu_math.py): log 2.18e-16 (2.16e-16 with full constants), exp 2.19e-16 (2.14e-16), expm1 2.58e-16 (2.60e-16).
+// Results differ from the default build in the last bits, so the whole GPU parity suite must be re-run before enabling.
+#ifndef MARLPDE_FP64_IMM
+#define MARLPDE_FP64_IMM 0
+#endif
+#if MARLPDE_FP64_IMM
+constexpr double kImmLn2Hi = 0x1.62e42p-1, kImmLn2_64Hi = 0x1.62e42p-7, kImm64_Ln2 = 0x1.71547p+6;
+__constant__ double kImmLn2Lo = 0x1.fdf473de6af28p-22, kImmLn2_64Lo = 0x1.fdf473de6af28p-28;
+constexpr double kImmLog3 = 0x1.9999ap-3, kImmLog4 = -0x1.55555p-3, kImmExp3 = 0x1.11111p-7, kImmExp4 = 0x1.6c16cp-10;
+#define FM_LN2HI kImmLn2Hi
+#define FM_LN2LO kImmLn2Lo
+#define FM_L64HI kImmLn2_64Hi
+#define FM_L64LO kImmLn2_64Lo
+#define FM_K64 kImm64_Ln2
+#define FM_LOG(i) ((i) == 0 ? -0.5 : (i) == 2 ? -0.25 : (i) == 3 ? kImmLog3 : (i) == 4 ? kImmLog4 : kLog1pC[i])
+#define FM_EXP(i) ((i) == 0 ? 0.5 : (i) == 3 ? kImmExp3 : (i) == 4 ? kImmExp4 : kExpC[i])
+#else
+#define FM_LN2HI kLn2Hi
+#define FM_LN2LO kLn2Lo
+#define FM_L64HI kLn2_64Hi
+#define FM_L64LO kLn2_64Lo
+#define FM_K64 k64_Ln2
+#define FM_LOG(i) kLog1pC[i]
+#define FM_EXP(i) kExpC[i]
+#endif
+
 struct Tables {            // shared-memory copies (random-index reads would serialise in the constant cache)
   const double2* logtab;   // [128] {ic, L}
   const double2* exptab;   // [64]  {Thi, Tlo}
@@ -77,14 +110,14 @@ __device__ __forceinline__ double log(const Tables& tb, double x) {
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
   const double2 t = tb.logtab[j];
   const double r = fma(m, t.x, -1.0);                    // |r| <= 2^-8, exact up to 2^-61
-  double p = fma(kLog1pC[5], r, kLog1pC[4]);
-  p = fma(p, r, kLog1pC[3]);
-  p = fma(p, r, kLog1pC[2]);
-  p = fma(p, r, kLog1pC[1]);
-  p = fma(p, r, kLog1pC[0]);
+  double p = fma(FM_LOG(5), r, FM_LOG(4));
+  p = fma(p, r, FM_LOG(3));
+  p = fma(p, r, FM_LOG(2));
+  p = fma(p, r, FM_LOG(1));
+  p = fma(p, r, FM_LOG(0));
   const double l1p = fma(r * r, p, r);                   // log1p(r)
   const double ed = (double)e;
-  return fma(ed, kLn2Hi, t.y) + fma(ed, kLn2Lo, l1p);
+  return fma(ed, FM_LN2HI, t.y) + fma(ed, FM_LN2LO, l1p);
 }
 
 // shared core of exp/expm1: x = (64 k + j) ln2/64 + r ; returns p = expm1(r), sets scale 2^k T_j.
@@ -93,17 +126,17 @@ __device__ __forceinline__ double log(const Tables& tb, double x) {
 template <bool kExtraTerm>
 __device__ __forceinline__ double exp_core(const Tables& tb, double x, double2& T, int& k) {
   const double magic = 6755399441055744.0;              // 1.5 * 2^52: round-to-nearest-int trick
-  const double tn = fma(x, k64_Ln2, magic);
+  const double tn = fma(x, FM_K64, magic);
   const int n = __double2loint(tn);
   const double nf = tn - magic;
-  double r = fma(nf, -kLn2_64Hi, x);
-  r = fma(nf, -kLn2_64Lo, r);                            // |r| <= ln2/128
+  double r = fma(nf, -FM_L64HI, x);
+  r = fma(nf, -FM_L64LO, r);                             // |r| <= ln2/128
   T = tb.exptab[n & 63];
   k = n >> 6;
-  double p = kExtraTerm ? fma(kExpC[4], r, kExpC[3]) : kExpC[3];
-  p = fma(p, r, kExpC[2]);
-  p = fma(p, r, kExpC[1]);
-  p = fma(p, r, kExpC[0]);
+  double p = kExtraTerm ? fma(FM_EXP(4), r, FM_EXP(3)) : FM_EXP(3);
+  p = fma(p, r, FM_EXP(2));
+  p = fma(p, r, FM_EXP(1));
+  p = fma(p, r, FM_EXP(0));
   return fma(r * r, p, r);
 }
 
@@ -153,14 +186,14 @@ __device__ __forceinline__ double log_nb(const Tables& tb, double x, bool& bad) 
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
   const double2 t = tb.logtab[j];
   const double r = fma(m, t.x, -1.0);
-  double p = fma(kLog1pC[5], r, kLog1pC[4]);
-  p = fma(p, r, kLog1pC[3]);
-  p = fma(p, r, kLog1pC[2]);
-  p = fma(p, r, kLog1pC[1]);
-  p = fma(p, r, kLog1pC[0]);
+  double p = fma(FM_LOG(5), r, FM_LOG(4));
+  p = fma(p, r, FM_LOG(3));
+  p = fma(p, r, FM_LOG(2));
+  p = fma(p, r, FM_LOG(1));
+  p = fma(p, r, FM_LOG(0));
   const double l1p = fma(r * r, p, r);
   const double ed = (double)e;
-  return fma(ed, kLn2Hi, t.y) + fma(ed, kLn2Lo, l1p);
+  return fma(ed, FM_LN2HI, t.y) + fma(ed, FM_LN2LO, l1p);
 }
 
 __device__ __forceinline__ double exp_nb(const Tables& tb, double x, bool& bad) {

@@ -1,0 +1,7 @@
+#!/bin/bash
+# Variant libraries for scripts/gpu_ab_next.sh (build_ab/ is git-ignored but travels to the GPU box).
+set -eu
+cd "$(dirname "$0")/../integrating-diagenetic-equations-using-python_b200"
+NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared -cudart static --threads 0"
+mkdir -p ../build_ab
+$NV -DMARLPDE_FP64_IMM=1 -o ../build_ab/lib_imm.so csrc/*.cu

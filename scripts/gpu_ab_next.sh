@@ -1,0 +1,17 @@
+#!/bin/bash
+# A/B candidates prepared at the end of round 1 (not yet measured on a GPU).  Build the variant libraries first:
+#   bash scripts/build_ab_next.sh
+# then:  gpurun --timeout 400 -- bash scripts/gpu_ab_next.sh <tag>
+set -u
+OUT=gpurun_out/${1:-ab_next}; mkdir -p $OUT
+B=$PWD/build_ab
+rk() { MARLPDE_B200_LIB=$1 MARLPDE_PROFILE_EVENTS=1 timeout 120 python scripts/profile_rk45.py 300 5 > $OUT/rk45_$2.log 2>&1; echo "rk45 $2: $(tail -2 $OUT/rk45_$2.log | tr '\n' ' ')"; }
+IN=$PWD/integrating-diagenetic-equations-using-python_b200/marlpde_b200/libmarlpde_b200.so
+rk $IN intree
+rk $B/lib_imm.so imm          # -DMARLPDE_FP64_IMM=1: constants with a zero low word as instruction immediates (results change in the last bits)
+rk $IN intree_again
+MARLPDE_B200_LIB=$B/lib_imm.so timeout 120 python scripts/profile_radau.py 16 0.05 > $OUT/radau_imm.log 2>&1; echo "radau imm: $(head -1 $OUT/radau_imm.log)"
+timeout 120 python scripts/profile_radau.py 16 0.05 > $OUT/radau_intree.log 2>&1; echo "radau in-tree: $(head -1 $OUT/radau_intree.log)"
+MARLPDE_B200_LIB=$B/lib_imm.so timeout 600 python -m pytest -q -m gpu -p no:cacheprovider --timeout=300 --timeout-method=thread tests > $OUT/pytest_imm.log 2>&1
+echo "pytest imm: $(tail -1 $OUT/pytest_imm.log)"
+echo done

@@ -262,3 +262,27 @@ def test_two_ended_block_thomas_against_dense_solve(n_cells):
         ref = np.linalg.solve(tw.dense(L, D, U, M), rhs)
         assert np.max(np.abs(x - ref)) <= 1e-11 * np.max(np.abs(ref))
 
+
+@pytest.mark.parametrize("imm", [False, True])
+def test_table_driven_fp64_maths_model_against_mpmath(imm):
+    """Tables (csrc/fp64_tables.inc), constants and algorithms of csrc/fp64_math.cuh, evaluated by an exact-FMA CPU
+    model (oracle/fp64_math_model.py), against mpmath — same ranges and bounds as tests/test_gpu_math.py — for the
+    default constants and for the experimental immediate-constant variant (MARLPDE_FP64_IMM=1)."""
+    mp = pytest.importorskip("mpmath")
+    import fp64_math_model as fm
+    mp.mp.prec = 120
+    c = fm.Constants(imm)
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([rng.uniform(1e-3, 3.0, 300), 10.0 ** rng.uniform(-300, 300, 100), 1 + rng.uniform(-1e-3, 1e-3, 100),
+                         [1.0, 0.5, 2.0, np.nextafter(1, 0), np.nextafter(1, 2), 0.8, 0.6]])
+    err = max(abs(mp.mpf(fm.log(c, float(x))) - mp.log(mp.mpf(float(x)))) / max(1, abs(mp.log(mp.mpf(float(x))))) for x in xs)
+    assert err <= 2.5e-16
+    xe = np.concatenate([rng.uniform(-40, 40, 300), rng.uniform(-689, 689, 100), rng.uniform(-1, 1, 100), [0.0]])
+    err = max(abs(mp.mpf(fm.exp(c, float(x))) / mp.exp(mp.mpf(float(x))) - 1) for x in xe)
+    assert err <= 4e-16
+    xm = np.concatenate([rng.uniform(-200, 200, 200), rng.uniform(-1, 1, 200), rng.uniform(-0.03, 0.03, 200)])
+    xm = xm[np.abs(xm) >= 1e-3]
+    err = max(abs(mp.mpf(fm.expm1(c, float(x))) / mp.expm1(mp.mpf(float(x))) - 1) for x in xm)
+    assert err <= 6e-16
+    assert fm.exp(c, 0.0) == 1.0 and fm.log(c, 1.0) == 0.0
+

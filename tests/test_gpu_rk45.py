@@ -69,6 +69,22 @@ def test_columns_are_independent_and_deterministic():
     assert np.array_equal(rev.y[::-1], full.y)
 
 
+def test_warp_order_does_not_change_results(monkeypatch):
+    """The kernel deals its physical warps out to the column ranges in an order chosen for scheduler balance
+    (rk45_persistent.cu: sPerm).  Which warp integrates which cells must not matter: the automatic order, the
+    identity and an arbitrary permutation give bit-identical trajectories, counters and event times."""
+    pde = mb.sweep_lattice(oracle.default_scenario(), 2, 2, 2)
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    kw = dict(t_span=(0, 5e-4), first_step=5e-7, t_eval=[2.5e-4, 5e-4], events=True, event_capacity=16)
+    auto = mb.integrate_rk45_batch(y0, P, **kw)
+    for order in ("identity", "9,8,7,6,5,4,3,2,1,0", "0,1,4,3,2,5,6,7,8,9"):
+        monkeypatch.setenv("MARLPDE_RK45_WARP_PERM", order)
+        res = mb.integrate_rk45_batch(y0, P, **kw)
+        assert np.array_equal(res.y, auto.y) and np.array_equal(res.snapshots, auto.snapshots), order
+        assert np.array_equal(res.nfev, auto.nfev) and np.array_equal(res.event_counts, auto.event_counts), order
+        assert np.array_equal(res.event_times, auto.event_times, equal_nan=True), order
+
+
 def test_step_budget_and_resume_is_bit_identical():
     pde = oracle.default_scenario() | {"Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}
     P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)

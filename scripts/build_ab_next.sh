@@ -4,4 +4,6 @@ set -eu
 cd "$(dirname "$0")/../integrating-diagenetic-equations-using-python_b200"
 NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared -cudart static --threads 0"
 mkdir -p ../build_ab
-$NV -DMARLPDE_FP64_IMM=1 -o ../build_ab/lib_imm.so csrc/*.cu
+$NV -DMARLPDE_FP64_IMM=1 -o ../build_ab/lib_imm.so csrc/*.cu &
+$NV -DMARLPDE_RADAU_FUSE_F=1 -o ../build_ab/lib_fuse.so csrc/*.cu &
+wait

@@ -12,6 +12,12 @@ rk $B/lib_imm.so imm          # -DMARLPDE_FP64_IMM=1: constants with a zero low 
 rk $IN intree_again
 MARLPDE_B200_LIB=$B/lib_imm.so timeout 120 python scripts/profile_radau.py 16 0.05 > $OUT/radau_imm.log 2>&1; echo "radau imm: $(head -1 $OUT/radau_imm.log)"
 timeout 120 python scripts/profile_radau.py 16 0.05 > $OUT/radau_intree.log 2>&1; echo "radau in-tree: $(head -1 $OUT/radau_intree.log)"
+# -DMARLPDE_RADAU_FUSE_F=1: the three stage evaluations of a Newton iteration fused with B = TI F - M W (6 x 5N fewer doubles through DRAM)
+MARLPDE_B200_LIB=$B/lib_fuse.so timeout 120 python scripts/profile_radau.py 16 0.05 > $OUT/radau_fuse.log 2>&1; echo "radau fuse: $(head -1 $OUT/radau_fuse.log)"
+MARLPDE_B200_LIB=$B/lib_fuse.so timeout 120 python scripts/profile_radau.py 4 0.05 > $OUT/radau_fuse_64.log 2>&1; echo "radau fuse, 64 columns: $(head -1 $OUT/radau_fuse_64.log)"
+timeout 120 python scripts/profile_radau.py 4 0.05 > $OUT/radau_intree_64.log 2>&1; echo "radau in-tree, 64 columns: $(head -1 $OUT/radau_intree_64.log)"
+MARLPDE_B200_LIB=$B/lib_fuse.so timeout 400 python -m pytest -q -m gpu -p no:cacheprovider --timeout=300 --timeout-method=thread tests/test_gpu_radau.py tests/test_gpu_dropin.py > $OUT/pytest_fuse.log 2>&1
+echo "pytest fuse: $(tail -1 $OUT/pytest_fuse.log)"
 MARLPDE_B200_LIB=$B/lib_imm.so timeout 600 python -m pytest -q -m gpu -p no:cacheprovider --timeout=300 --timeout-method=thread tests > $OUT/pytest_imm.log 2>&1
 echo "pytest imm: $(tail -1 $OUT/pytest_imm.log)"
 echo done

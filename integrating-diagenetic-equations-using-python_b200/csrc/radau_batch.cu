@@ -8,22 +8,21 @@
 // Gustafsson step-size prediction, same Jacobian/LU reuse policy.
 //
 // What is B200-native about it:
-//   * one WARP per sediment column, many columns per SM, columns claimed from a global queue; all
+//   * one WARP per sediment column, 12 columns per SM in flight, columns claimed from a global queue; all
 //     control flow of a column is warp-uniform, so there is no block barrier anywhere;
 //   * the Jacobian is what it is for this PDE: block-TRIDIAGONAL in cell-major order with dense 5x5
 //     blocks (the reference hands SciPy a 27-diagonal field-major pattern, parameters.py:150-199,
-//     and SciPy then runs a general sparse LU).  It is formed by finite differences with 15 colours
-//     (3 cell classes x 5 fields; the reference's pattern needs 21) from the same rhs_pair code as
-//     the explicit kernel, and kept in HBM as [cell][L|D|U][5][5];
+//     and SciPy then runs a general sparse LU).  Off-diagonal blocks are analytic, the diagonal blocks come
+//     from 5 finite-difference evaluations (jac_columns) of the same rhs_pair code as the explicit kernel; it
+//     is kept in HBM as [cell][L|D|U][5][5];
 //   * the two linear systems of a Radau step, (mu_real/h I - J) and (mu_complex/h I - J), are
-//     factorised TOGETHER by one block-Thomas sweep: lanes 0-9 carry the real system, lanes 16-25
-//     the complex one (both in complex arithmetic, the real one with zero imaginary part), one lane
-//     per column of [S | I]; Gauss-Jordan with partial pivoting inside the 5x5 block, pivot search
-//     local to one lane, multipliers broadcast through shared memory.  What is stored per cell is
-//     S_i^{-1} (S_i = Schur complement), so a solve is two 5x5 mat-vecs per cell and direction;
-//   * both triangular sweeps of a Newton iteration again run side by side in one warp.
-// Everything is fp64; state vectors live in a per-column HBM workspace (L2 resident while a
-// column is being worked on).
+//     factorised TOGETHER by one two-ended block-Thomas pass (top-down and bottom-up chains meeting in the
+//     middle cell): one entry of [S | I] of both systems per lane, Gauss-Jordan with partial pivoting inside
+//     the 5x5 block, pivot search by warp REDUX.  What is stored per cell is S_i^{-1} (fp32: it only
+//     preconditions the simplified Newton iteration), so a solve is two 5x5 mat-vecs per cell and direction;
+//   * in a solve the two chains of both systems run side by side in one warp: N/2 sequential steps per sweep.
+// State vectors are fp64 and live in a per-column HBM workspace; when all 12 x 148 columns are in flight the
+// kernel is bound by the DRAM traffic of those vectors and of the fp32 records.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -223,7 +222,7 @@ __device__ __forceinline__ double fd_step(double y, double f, double atol) {
   return (y + kSqrtEps * ys) - y;
 }
 
-// THE one instance of the RHS in this kernel (instruction-cache footprint matters: 16 warps per SM sit
+// THE one instance of the RHS in this kernel (instruction-cache footprint matters: 12 warps per SM sit
 // in different phases of their columns): out = rhs(yy + add) (add may be NULL), all cell-major [N][5].
 #if MARLPDE_RADAU_FUSE_F
 __device__ __noinline__ bool rhs_eval_fused(const ColumnConsts* kcp, const fm::Tables* tbp, int N, int lane, const double* yy,

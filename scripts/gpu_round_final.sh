@@ -17,6 +17,8 @@ timeout 200 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_r
 PROF="python scripts/profile_rk45.py 300 3"
 MARLPDE_PROFILE_EVENTS=1 timeout 100 $PROF > $OUT/profile_plain.log 2>&1 &&
 MARLPDE_PROFILE_EVENTS=1 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches.csv $PROF > $OUT/ncu_launches.log 2>&1
+# launch list of the bench command itself (the contract's "same command"): one rk45_persistent_kernel per step
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_launches_bench.log 2>&1
 MARLPDE_PROFILE_EVENTS=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:rk45_persistent -s 1 -c 1 -o $OUT/rk45_full $PROF > $OUT/ncu_full.log 2>&1
 timeout 600 python bench.py --steps 3 --warmup 3 --full --no-cpu-baseline > $OUT/bench_full.json 2>> $OUT/bench.err
 echo "bench full exit $?" >> $OUT/bench.err

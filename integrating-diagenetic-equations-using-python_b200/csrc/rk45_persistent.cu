@@ -35,6 +35,7 @@
 #include "lheureux_device.cuh"
 #include "mbar.cuh"
 #include "rk45_persistent.cuh"
+#include "rk45_quad.cuh"
 
 namespace marlpde {
 
@@ -85,18 +86,22 @@ static int columns_per_cta_t(int n_cells, int smem_budget) {
 //   <320,true>  10 warps, <= 168 registers, y and K1 in shared memory  (same shapes; fewer register spills)
 //   <416,true,HS> 13 warps, <= 128 registers, y and K1 in shared memory, halo exchange by warp shuffles
 //               instead of a stage-input tile (frees 64 kB: N=200 runs 4 columns per CTA)
-// MARLPDE_RK45_BUILD=320|321|416 overrides the default choice (tuning / tests).
+//   450         EXPERIMENTAL, rk45_quad.cu: four cells per thread, 8 warps, N=200 runs 5 columns per CTA (grids it
+//               does not take fall back to the default build)
+// MARLPDE_RK45_BUILD=320|321|416|450 overrides the default choice (tuning / tests).
 static int rk45_variant() {
   static int v = -1;
   if (v < 0) {
     const char* s = std::getenv("MARLPDE_RK45_BUILD");
     const int want = s ? std::atoi(s) : 0;
-    v = (want == 321 || want == 416) ? want : 320;
+    v = (want == 321 || want == 416 || want == 450) ? want : 320;
   }
   return v;
 }
 
 int rk45_columns_per_cta(int n_cells, int smem_budget) {
+  if (rk45_variant() == 450 && rk45_quad_columns_per_cta(n_cells, smem_budget) > 0)
+    return rk45_quad_columns_per_cta(n_cells, smem_budget);
   switch (rk45_variant()) {
     case 321: return columns_per_cta_t<320, true, false>(n_cells, smem_budget);
     case 416: return columns_per_cta_t<416, true, true>(n_cells, smem_budget);
@@ -884,6 +889,9 @@ cudaError_t launch_rk45(double* d_y, const marlpde_column_params* d_params, marl
   a.logG = 0;
   a.warp_perm = 0;
   a.opt = opt;
+  if (rk45_variant() == 450 && rk45_quad_columns_per_cta(n_cells, smem_budget) > 0)
+    return launch_rk45_quad(d_y, d_params, d_state, n_columns, n_cells, opt, d_t_eval, d_snap, d_ev_counts, d_ev_times,
+                            d_queue, sm_count, smem_budget, stream);
   switch (rk45_variant()) {
     case 321: return launch_t<320, true, false>(a, sm_count, smem_budget, stream);
     case 416: return launch_t<416, true, true>(a, sm_count, smem_budget, stream);

@@ -87,7 +87,11 @@ static __device__ __noinline__ double slow_expm1(double x) { return ::expm1(x); 
 // 0, inf, NaN give NaN/inf garbage that stays non-finite.
 __device__ __forceinline__ double rcp(double x) {
   double r;
+#ifdef MARLPDE_HOST_EMU   // tests/emu/: a ~2^-22 seed from the high word, like MUFU.RCP64H
+  r = __hiloint2double(__double2hiint(1.0 / __hiloint2double(__double2hiint(x), 0)), 0);
+#else
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#endif
   double e = fma(-x, r, 1.0);
   r = fma(r, e, r);
   e = fma(-x, r, 1.0);
@@ -172,7 +176,11 @@ __device__ __forceinline__ double expm1(const Tables& tb, double x) {
 // 1/x: MUFU.RCP64H seed + one cubic step r(1 + e + e^2): |rel err| <= e^3 + 1 ulp.
 __device__ __forceinline__ double rcp3(double x) {
   double r;
+#ifdef MARLPDE_HOST_EMU   // tests/emu/: a ~2^-22 seed from the high word, like MUFU.RCP64H
+  r = __hiloint2double(__double2hiint(1.0 / __hiloint2double(__double2hiint(x), 0)), 0);
+#else
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#endif
   const double e = fma(-x, r, 1.0);
   const double t = fma(e, e, e);
   return fma(r, t, r);

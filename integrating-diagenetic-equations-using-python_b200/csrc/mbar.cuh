@@ -5,8 +5,18 @@
 #pragma once
 #include <cstdint>
 
+// the kernel's dynamic shared memory (the host emulator of tests/emu/ substitutes its own buffer)
+#ifndef MARLPDE_DYN_SMEM
+#define MARLPDE_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
 namespace marlpde {
 
+#ifdef MARLPDE_HOST_EMU   // tests/emu/: kernel control logic on the host, test infrastructure only
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) { ::simt::mbar_init(bar, count); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { ::simt::mbar_arrive(bar); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) { ::simt::mbar_wait(bar, parity); }
+#else
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -28,5 +38,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         : "memory");
   } while (!done);
 }
+#endif
 
 }  // namespace marlpde

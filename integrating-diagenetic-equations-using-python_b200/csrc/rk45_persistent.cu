@@ -191,7 +191,7 @@ struct Rk45Args {
 
 template <int TP, bool YS, bool HS>
 __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel(const Rk45Args A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MARLPDE_DYN_SMEM(smem_raw);
   using L = Smem<TP, YS, HS>;
   // Logical thread index.  Physical warps can be dealt out to the column ranges in any order; the order decides WHICH
   // scheduler (physical warp & 3) runs the warps whose lanes lie in the dissolution zone and therefore evaluate one
@@ -851,6 +851,7 @@ static unsigned long long rk45_warp_perm(int n_warps) {
   return p;
 }
 
+#ifndef MARLPDE_HOST_EMU
 template <int TP, bool YS, bool HS>
 static cudaError_t launch_t(const Rk45Args& a, int sm_count, int smem_budget, cudaStream_t stream) {
   Rk45Args args = a;
@@ -898,5 +899,7 @@ cudaError_t launch_rk45(double* d_y, const marlpde_column_params* d_params, marl
     default: return launch_t<320, false, false>(a, sm_count, smem_budget, stream);
   }
 }
+
+#endif
 
 }  // namespace marlpde

@@ -141,7 +141,7 @@ struct Args {
 };
 
 __global__ void __launch_bounds__(TP, 1) rk45_quad_kernel(const Args A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MARLPDE_DYN_SMEM(smem_raw);
   using L = Smem;
   const int tid = threadIdx.x;
   const int N = A.N, C = A.C;
@@ -745,6 +745,7 @@ __global__ void __launch_bounds__(TP, 1) rk45_quad_kernel(const Args A) {
 
 int rk45_quad_columns_per_cta(int n_cells, int smem_budget) { return quad::columns_per_cta(n_cells, smem_budget); }
 
+#ifndef MARLPDE_HOST_EMU
 cudaError_t launch_rk45_quad(double* d_y, const marlpde_column_params* d_params, marlpde_column_state* d_state,
                              int n_columns, int n_cells, const marlpde_rk45_options& opt, const double* d_t_eval,
                              double* d_snap, int32_t* d_ev_counts, double* d_ev_times, int32_t* d_queue, int sm_count,
@@ -773,5 +774,6 @@ cudaError_t launch_rk45_quad(double* d_y, const marlpde_column_params* d_params,
   quad::rk45_quad_kernel<<<grid, quad::TP, smem, stream>>>(a);
   return cudaGetLastError();
 }
+#endif
 
 }  // namespace marlpde

@@ -1,0 +1,139 @@
+"""Kernel control logic on the host: the on-chip RK45 kernels (csrc/rk45_persistent.cu — the default build, validated on
+B200 — and csrc/rk45_quad.cu — the experimental 4-cells-per-thread build that has not been on a GPU yet) are compiled
+for the host with g++ and run one thread block at a time by a small SIMT emulator (tests/emu/: one fiber per CUDA thread,
+rendezvous at every barrier / warp collective / mbarrier wait; a missing barrier or a collective that not all named
+lanes reach is reported instead of hanging).
+
+This is test infrastructure, not a CPU path of the product: it checks indexing, halo exchange, barriers, slot service,
+dense output and event location of a kernel BEFORE it is first launched on a GPU; arithmetic parity on the device stays
+the job of the `-m gpu` tests.  Calibration: the default kernel under emulation reproduces SciPy RK45 exactly as it does
+on the GPU (identical nfev, differences at the 1e-14 level)."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import lheureux_oracle as oracle
+import marlpde_b200 as mb
+from marlpde_b200 import _cabi, batch
+from conftest import ROOT
+
+EMU = os.path.join(ROOT, "tests", "emu")
+np.seterr(all="ignore")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    out = os.path.join(EMU, "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libemu_rk45.so")
+    srcs = [os.path.join(EMU, f) for f in ("emu_rk45.cc", "simt_emu.cc")]
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", "-I", EMU, "-o", so] + srcs,
+                   check=True, capture_output=True)
+    lib = C.CDLL(so)
+    lib.emu_rk45.restype = C.c_int
+
+    def run(variant, P, y, t_end, t_eval=(), events=False, first_step=1e-6, max_steps=0, state=None, capacity=16):
+        y = np.ascontiguousarray(y, dtype=np.float64).copy()
+        P = np.ascontiguousarray(P)
+        B, _, N = y.shape
+        st = batch.make_state(B, 0.0, first_step) if state is None else state.copy()
+        te = np.asarray(t_eval, dtype=np.float64)
+        snap = np.full((B, max(1, te.size), 5, N), np.nan)
+        ec = np.zeros((B, 7), np.int32)
+        et = np.full((B, 7, capacity), np.nan)
+        o = _cabi.RK45Options(t_bound=t_end, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=max_steps,
+                              n_eval=te.size, event_capacity=capacity, flags=_cabi.FLAG_EVENTS if events else 0, reserved=0)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = lib.emu_rk45(variant, p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), p(ec), p(et))
+        assert rc == 0, f"emulated kernel {variant}: rc {rc} (deadlock or mismatched collective, see stderr)"
+        return dict(y=y, state=st, snapshots=snap, event_counts=ec, event_times=et)
+    return run
+
+
+SCEN_A = {"Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}
+
+
+def test_default_kernel_under_emulation_reproduces_scipy(emu):
+    """Calibration of the emulator with the kernel that is validated on the GPU."""
+    pde = oracle.default_scenario() | SCEN_A
+    sol = oracle.integrate(pde, method="RK45", t_span=(0, 2e-4), t_eval=[2e-4], events=False, first_step=1e-6)
+    res = emu(320, mb.derive_column_params(pde), mb.initial_state(pde), 2e-4)
+    assert res["state"]["status"][0] == 0 and res["state"]["nfev"][0] == sol.nfev
+    assert np.max(np.abs(res["y"][0] - sol.y.reshape(5, 200, -1)[:, :, -1])) <= 1e-12
+
+
+def test_quad_kernel_lattice_dense_output_and_slot_reuse(emu):
+    """Eight columns with different parameters through five slots (queue refills), rejected steps, t_eval samples: the
+    4-cells-per-thread build against the default build and against SciPy."""
+    pde = mb.sweep_lattice(oracle.default_scenario(), 2, 2, 2)
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    te = [1e-4, 2.5e-4, 4e-4]
+    ref = emu(320, P, y0, 4e-4, t_eval=te, events=True, first_step=5e-7)
+    got = emu(450, P, y0, 4e-4, t_eval=te, events=True, first_step=5e-7)
+    for k in ("nfev", "n_accepted", "n_rejected", "status", "next_eval"):
+        assert np.array_equal(got["state"][k], ref["state"][k]), k
+    assert got["state"]["n_rejected"].min() > 0
+    assert np.max(np.abs(got["y"] - ref["y"])) <= 1e-12 and np.max(np.abs(got["snapshots"] - ref["snapshots"])) <= 1e-12
+    for c in (0, 5):
+        one = {k: (float(v[c]) if np.ndim(v) else v) for k, v in pde.items()}
+        sol = oracle.integrate(one, method="RK45", t_span=(0, 4e-4), t_eval=te, events=False, first_step=5e-7)
+        want = sol.y.reshape(5, 200, -1)
+        assert got["state"]["nfev"][c] == sol.nfev
+        assert np.max(np.abs(got["snapshots"][c] - np.moveaxis(want, 2, 0))) <= 1e-12
+
+
+def test_quad_kernel_events_and_column_independence(emu):
+    """Parked steps, Brent location on the dense output, per-column event lists (the GPU test
+    test_events_synthetic_state_six_monitors_and_capacity, on the emulated experimental kernel)."""
+    pde = oracle.default_scenario() | SCEN_A
+    y0 = mb.initial_state(pde)
+    y0[0, 0, 50] = -2e-3
+    y0[0, 1, 60] = -1e-3
+    y0[0, 0, 100] = 0.705
+    y0[0, 4, 150] = 1.0005
+    t_end = 2.5e-3
+    sol = oracle.integrate(pde, method="RK45", t_span=(0, t_end), t_eval=[0, t_end], events=True, y0=y0[0])
+    want = [len(e) for e in sol.t_events]
+    assert sum(want) >= 5
+    P = mb.derive_column_params(pde)
+    Y = np.concatenate([y0, mb.initial_state(pde), y0])
+    res = emu(450, np.repeat(P, 3), Y, t_end, t_eval=[0, t_end], events=True, capacity=8)
+    assert np.all(res["state"]["status"] == 0) and res["state"]["nfev"][0] == sol.nfev
+    for c in (0, 2):
+        assert list(res["event_counts"][c]) == want
+        for k in range(7):
+            got = np.sort(res["event_times"][c, k, :want[k]])
+            assert np.allclose(got, sol.t_events[k], rtol=0, atol=1e-12)
+    assert np.all(res["event_counts"][1] == 0)
+    assert np.array_equal(res["y"][0], res["y"][2])
+    assert np.max(np.abs(res["y"][0] - sol.y.reshape(5, 200, -1)[:, :, -1])) <= 1e-10
+
+
+def test_quad_kernel_resume_is_bit_identical_and_other_grids(emu):
+    pde = oracle.default_scenario() | SCEN_A
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    te = np.linspace(0, 6e-4, 4)
+    whole = emu(450, P, y0, 6e-4, t_eval=te)
+    part = emu(450, P, y0, 6e-4, t_eval=te, max_steps=60)
+    hops = 1
+    while part["state"]["status"][0] == 1:
+        nxt = emu(450, P, part["y"], 6e-4, t_eval=te, max_steps=60, state=part["state"])
+        keep = np.isnan(nxt["snapshots"])
+        nxt["snapshots"][keep] = part["snapshots"][keep]
+        part = nxt
+        hops += 1
+    assert hops >= 3 and np.array_equal(part["y"], whole["y"]) and np.array_equal(part["snapshots"], whole["snapshots"])
+    for n_cells in (32, 64, 400):
+        p2 = pde | {"N": n_cells}
+        h0 = 1e-6 * min(1.0, (200 / n_cells) ** 2)
+        t_end = 2e-4 * min(1.0, (200 / n_cells) ** 2)
+        sol = oracle.integrate(p2, method="RK45", t_span=(0, t_end), t_eval=[t_end], events=False, first_step=h0)
+        res = emu(450, np.repeat(mb.derive_column_params(p2), 3), np.repeat(mb.initial_state(p2), 3, 0), t_end, first_step=h0)
+        assert np.all(res["state"]["nfev"] == sol.nfev), n_cells
+        assert np.max(np.abs(res["y"][1] - sol.y.reshape(5, n_cells, -1)[:, :, -1])) <= 1e-12, n_cells

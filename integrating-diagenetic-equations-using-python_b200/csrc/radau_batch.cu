@@ -78,6 +78,14 @@ __device__ __forceinline__ double2 cinv(double2 a) {   // pivots are finite and 
 
 // ---- asynchronous global -> shared copies (LDGSTS): the block-Thomas sweeps are sequential in the cell
 // index, so the matrices of the next kDepth cells are kept in flight while the current cell is processed
+#ifdef MARLPDE_HOST_EMU   // tests/emu/: kernel control logic on the host (test infrastructure only): copy at once
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  *reinterpret_cast<double*>(smem) = *reinterpret_cast<const double*>(gmem);
+}
+__device__ __forceinline__ void cp_async_commit() {}
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() {}
+#else
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
@@ -85,6 +93,7 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+#endif
 // Tuning switches, all measured on 4096 columns (r01c, baseline 2.48 s to t = 0.05) and left OFF: with 16 columns
 // per SM in flight the kernel is bound by DRAM traffic (1.6-1.8 TB/s of 1-kB runs), so more loads in flight lose:
 //   RADAU_BATCH4 (four strides of loads per trip of the element-wise passes) 2.68 s,
@@ -99,7 +108,11 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #ifndef RADAU_BATCH4
 #define RADAU_BATCH4 0
 #endif
+#ifdef MARLPDE_HOST_EMU
+__device__ __forceinline__ void prefetch_l1(const void*) {}
+#else
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#endif
 #ifndef MARLPDE_RADAU_DEPTH
 #define MARLPDE_RADAU_DEPTH 3
 #endif
@@ -1197,6 +1210,7 @@ size_t radau_workspace_bytes(int n_columns, int n_cells) {
   return sizeof(double) * rd::work_doubles(n_cells) * (size_t)n_columns;
 }
 
+#ifndef MARLPDE_HOST_EMU
 cudaError_t launch_radau(double* d_y, const marlpde_column_params* d_params, marlpde_column_state* d_state,
                          int n_columns, int n_cells, const marlpde_rk45_options& opt, const double* d_t_eval,
                          double* d_snap, int64_t* d_stats, int32_t* d_ev_counts, double* d_ev_times, double* d_work,
@@ -1222,5 +1236,7 @@ cudaError_t launch_radau(double* d_y, const marlpde_column_params* d_params, mar
   rd::radau_kernel<<<ctas, rd::kWarpsPerCta * 32, 0, stream>>>(a);
   return cudaGetLastError();
 }
+
+#endif
 
 }  // namespace marlpde

@@ -18,7 +18,7 @@
 #define __noinline__ __attribute__((noinline))
 #define __constant__
 #define __launch_bounds__(...)
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static            // block-scope shared variables: one CTA is emulated at a time
 #define MARLPDE_DYN_SMEM(name) unsigned char* const name = ::simt::dyn_smem()
 

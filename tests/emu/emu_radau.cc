@@ -1,0 +1,33 @@
+// tests/emu/emu_radau.cc — the batched Radau kernel (csrc/radau_batch.cu), compiled for the host and run by the SIMT
+// emulator: one CTA of four warps works through all columns of the queue.  TEST INFRASTRUCTURE ONLY (simt_emu.h).
+// Built twice by tests/test_emu_kernels.py: as is, and with -DMARLPDE_RADAU_FUSE_F=1.
+#include <cstdint>
+#include <vector>
+
+#include "cuda_runtime.h"
+#include "simt_emu.h"
+
+#include "../../integrating-diagenetic-equations-using-python_b200/csrc/radau_batch.cu"
+
+extern "C" int emu_radau(double* y, const marlpde_column_params* params, marlpde_column_state* state, int n_columns,
+                         int n_cells, const marlpde_rk45_options* opt, const double* t_eval, double* snap,
+                         int64_t* stats, int32_t* ev_counts, double* ev_times) {
+  using namespace marlpde;
+  std::vector<double> work(rd::work_doubles(n_cells) * (size_t)n_columns + 16, 0.0);
+  int32_t queue = 0;
+  rd::Args a;
+  a.g_y = y;
+  a.g_params = params;
+  a.g_state = state;
+  a.g_t_eval = t_eval;
+  a.g_snap = snap;
+  a.g_stats = stats;
+  a.g_ev_counts = ev_counts;
+  a.g_ev_times = ev_times;
+  a.g_work = work.data();
+  a.g_queue = &queue;
+  a.n_columns = n_columns;
+  a.N = n_cells;
+  a.opt = *opt;
+  return simt::run_block(rd::kWarpsPerCta * 32, 0, [&]() { rd::radau_kernel(a); });
+}

@@ -1,4 +1,5 @@
-"""Kernel control logic on the host: the on-chip RK45 kernels (csrc/rk45_persistent.cu — the default build, validated on
+"""Kernel control logic on the host: the batched Radau kernel (csrc/radau_batch.cu, as is and with the experimental
+-DMARLPDE_RADAU_FUSE_F=1) and the on-chip RK45 kernels (csrc/rk45_persistent.cu — the default build, validated on
 B200 — and csrc/rk45_quad.cu — the experimental 4-cells-per-thread build that has not been on a GPU yet) are compiled
 for the host with g++ and run one thread block at a time by a small SIMT emulator (tests/emu/: one fiber per CUDA thread,
 rendezvous at every barrier / warp collective / mbarrier wait; a missing barrier or a collective that not all named
@@ -137,3 +138,67 @@ def test_quad_kernel_resume_is_bit_identical_and_other_grids(emu):
         res = emu(450, np.repeat(mb.derive_column_params(p2), 3), np.repeat(mb.initial_state(p2), 3, 0), t_end, first_step=h0)
         assert np.all(res["state"]["nfev"] == sol.nfev), n_cells
         assert np.max(np.abs(res["y"][1] - sol.y.reshape(5, n_cells, -1)[:, :, -1])) <= 1e-12, n_cells
+
+
+# --------------------------------------------------------------------------------------- Radau kernel
+@pytest.fixture(scope="module")
+def emu_radau():
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    out = os.path.join(EMU, "_build")
+    os.makedirs(out, exist_ok=True)
+    libs = {}
+    for fuse in (0, 1):
+        so = os.path.join(out, f"libemu_radau{fuse}.so")
+        srcs = [os.path.join(EMU, f) for f in ("emu_radau.cc", "simt_emu.cc")]
+        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", f"-DMARLPDE_RADAU_FUSE_F={fuse}",
+                        "-I", EMU, "-o", so] + srcs, check=True, capture_output=True)
+        libs[fuse] = C.CDLL(so)
+        libs[fuse].emu_radau.restype = C.c_int
+
+    def run(fuse, P, y, t_end, t_eval=(), events=False, first_step=1e-6):
+        y = np.ascontiguousarray(y, dtype=np.float64).copy()
+        P = np.ascontiguousarray(P)
+        B, _, N = y.shape
+        st = batch.make_state(B, 0.0, first_step)
+        te = np.asarray(t_eval, dtype=np.float64)
+        snap = np.full((B, max(1, te.size), 5, N), np.nan)
+        ec, et, stats = np.zeros((B, 7), np.int32), np.full((B, 7, 16), np.nan), np.zeros((B, 4), np.int64)
+        o = _cabi.RK45Options(t_bound=t_end, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=0, n_eval=te.size,
+                              event_capacity=16, flags=_cabi.FLAG_EVENTS if events else 0, reserved=0)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = libs[fuse].emu_radau(p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), p(stats), p(ec), p(et))
+        assert rc == 0, f"emulated Radau kernel (fuse={fuse}): rc {rc}"
+        return dict(y=y, state=st, snapshots=snap, stats=stats, event_counts=ec)
+    return run
+
+
+def test_radau_kernel_under_emulation_and_fused_stage_evaluation(emu_radau):
+    """Scenario A to T* (the reference's regression case) and a lattice of five columns through the four warps of one CTA:
+    the Radau kernel under emulation against SciPy Radau with the reference's sparsity, and the experimental fused stage
+    evaluation against the plain one (same step / LU / Newton counts, solutions equal to 1e-3 tolerance units)."""
+    pde = oracle.default_scenario() | SCEN_A
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    te = np.linspace(0, 1, 11)
+    sol = oracle.integrate(pde, method="Radau", t_span=(0, 1), t_eval=te, events=False, first_step=1e-6,
+                           jac_sparsity=oracle.jacobian_sparsity(200))
+    want = np.moveaxis(sol.y.reshape(5, 200, -1), 2, 0)
+    unit = 1e-3 + 1e-3 * np.abs(want)
+    res = {f: emu_radau(f, P, y0, 1.0, t_eval=te) for f in (0, 1)}
+    for f in (0, 1):
+        assert res[f]["state"]["status"][0] == 0 and 25 <= res[f]["state"]["n_accepted"][0] <= 80
+        assert np.max(np.abs(res[f]["snapshots"][0] - want) / unit) <= 2.0      # two Radau codes at rtol = 1e-3
+    assert np.array_equal(res[0]["stats"], res[1]["stats"])
+    for k in ("n_accepted", "n_rejected", "nfev", "status", "next_eval"):
+        assert np.array_equal(res[0]["state"][k], res[1]["state"][k]), k
+    assert np.max(np.abs(res[0]["snapshots"] - res[1]["snapshots"]) / unit) <= 1e-3
+    lat = mb.sweep_lattice(oracle.default_scenario(), 1, 1, 5)
+    Pl, yl = mb.derive_column_params(lat), mb.initial_state(lat)
+    a = emu_radau(0, Pl, yl, 0.006, t_eval=[0.006], events=True, first_step=5e-7)
+    b = emu_radau(1, Pl, yl, 0.006, t_eval=[0.006], events=True, first_step=5e-7)
+    assert np.all(a["state"]["status"] == 0) and np.array_equal(a["stats"][:, :2], b["stats"][:, :2])
+    assert np.max(np.abs(a["y"] - b["y"]) / (1e-3 + 1e-3 * np.abs(a["y"]))) <= 1e-3
+    one = {k: (float(v[4]) if np.ndim(v) else v) for k, v in lat.items()}
+    s4 = oracle.integrate(one, method="Radau", t_span=(0, 0.006), t_eval=[0.006], events=False, first_step=5e-7,
+                          jac_sparsity=oracle.jacobian_sparsity(200)).y.reshape(5, 200)
+    assert np.max(np.abs(a["y"][4] - s4) / (1e-3 + 1e-3 * np.abs(s4))) <= 1.0

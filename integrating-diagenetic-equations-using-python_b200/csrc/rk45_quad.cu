@@ -35,6 +35,9 @@ namespace quad {
 constexpr int TP = 256;   // threads per CTA
 constexpr int Q = 4;      // cells per thread
 constexpr int kWarps = TP / 32;
+#ifndef MARLPDE_QUAD_ORDER
+#define MARLPDE_QUAD_ORDER 0   // 1: own-cell parts of both pairs before the stage-barrier wait (A/B candidate)
+#endif
 
 struct SlotCtl {          // per-slot counters, touched by the slot's leader thread only
   long long n_acc, n_rej, nfev;
@@ -522,6 +525,11 @@ __global__ void __launch_bounds__(TP, 1) rk45_quad_kernel(const Args A) {
       const bool maskA[2] = {in_mask[0], in_mask[1]}, maskB[2] = {in_mask[2], in_mask[3]};
       OwnTerms ownA;
       PairFlags flA = rhs_pair_own<rhs_schedule(kSchedLean)>(kc, tb, cA, maskA, ownA);
+#if MARLPDE_QUAD_ORDER == 1
+      // own-cell parts of BOTH pairs before the wait (more work behind the barrier, 48 more live registers)
+      OwnTerms ownB;
+      PairFlags flB = rhs_pair_own<rhs_schedule(kSchedLean)>(kc, tb, cB, maskB, ownB);
+#endif
       if (i > i0) {
         mbar_wait(sBar, bar_parity);
         bar_parity ^= 1u;
@@ -545,7 +553,15 @@ __global__ void __launch_bounds__(TP, 1) rk45_quad_kernel(const Args A) {
       flA.bad[0] = flA.bad[0] && live;
       flA.bad[1] = flA.bad[1] && live;
       if (flA.bad[0] || flA.bad[1]) rhs_pair_fixup(kc, tb, flA, cA, mloA, phiA, maskA, rA, UA, WA);
+#if MARLPDE_QUAD_ORDER == 1
+      rhs_pair_finish(kc, cB, mloB, phiB, ownB, rB);
+      UB[0] = ownB.U[0];
+      UB[1] = ownB.U[1];
+      WB[0] = ownB.W[0];
+      WB[1] = ownB.W[1];
+#else
       PairFlags flB = rhs_pair<rhs_schedule(kSchedLean)>(kc, tb, cB, mloB, phiB, maskB, rB, UB, WB);
+#endif
       flB.bad[0] = flB.bad[0] && live;
       flB.bad[1] = flB.bad[1] && live;
       if (flB.bad[0] || flB.bad[1]) rhs_pair_fixup(kc, tb, flB, cB, mloB, phiB, maskB, rB, UB, WB);

@@ -6,4 +6,5 @@ NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -
 mkdir -p ../build_ab
 $NV -DMARLPDE_FP64_IMM=1 -o ../build_ab/lib_imm.so csrc/*.cu &
 $NV -DMARLPDE_RADAU_FUSE_F=1 -o ../build_ab/lib_fuse.so csrc/*.cu &
+$NV -DMARLPDE_QUAD_ORDER=1 -o ../build_ab/lib_quad_o1.so csrc/*.cu &
 wait

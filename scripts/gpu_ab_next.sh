@@ -14,6 +14,7 @@ rk $IN intree_again
 # a short timeout: the kernel has never been on a GPU
 MARLPDE_RK45_BUILD=450 timeout 60 python scripts/profile_rk45.py 300 5 > $OUT/rk45_quad.log 2>&1; echo "rk45 quad (no events): $(tail -2 $OUT/rk45_quad.log | tr '\n' ' ')"
 MARLPDE_RK45_BUILD=450 MARLPDE_PROFILE_EVENTS=1 timeout 60 python scripts/profile_rk45.py 300 5 > $OUT/rk45_quad_ev.log 2>&1; echo "rk45 quad: $(tail -2 $OUT/rk45_quad_ev.log | tr '\n' ' ')"
+MARLPDE_B200_LIB=$B/lib_quad_o1.so MARLPDE_RK45_BUILD=450 MARLPDE_PROFILE_EVENTS=1 timeout 60 python scripts/profile_rk45.py 300 5 > $OUT/rk45_quad_o1.log 2>&1; echo "rk45 quad, own parts of both pairs before the wait: $(tail -2 $OUT/rk45_quad_o1.log | tr '\n' ' ')"
 MARLPDE_RK45_BUILD=450 timeout 300 python -m pytest -q -x -m gpu -p no:cacheprovider --timeout=60 --timeout-method=thread tests/test_gpu_rk45.py tests/test_gpu_dropin.py > $OUT/pytest_quad.log 2>&1
 echo "pytest quad: $(tail -3 $OUT/pytest_quad.log | tr '\n' ' ')"
 MARLPDE_B200_LIB=$B/lib_imm.so timeout 120 python scripts/profile_radau.py 16 0.05 > $OUT/radau_imm.log 2>&1; echo "radau imm: $(head -1 $OUT/radau_imm.log)"

@@ -38,6 +38,11 @@ def emu():
                    check=True, capture_output=True)
     lib = C.CDLL(so)
     lib.emu_rk45.restype = C.c_int
+    so_imm = os.path.join(out, "libemu_rk45_imm.so")           # the experimental immediate-constant fp64 maths
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", "-DMARLPDE_FP64_IMM=1", "-I", EMU,
+                    "-o", so_imm] + srcs, check=True, capture_output=True)
+    lib_imm = C.CDLL(so_imm)
+    lib_imm.emu_rk45.restype = C.c_int
 
     def run(variant, P, y, t_end, t_eval=(), events=False, first_step=1e-6, max_steps=0, state=None, capacity=16):
         y = np.ascontiguousarray(y, dtype=np.float64).copy()
@@ -51,7 +56,8 @@ def emu():
         o = _cabi.RK45Options(t_bound=t_end, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=max_steps,
                               n_eval=te.size, event_capacity=capacity, flags=_cabi.FLAG_EVENTS if events else 0, reserved=0)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
-        rc = lib.emu_rk45(variant, p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), p(ec), p(et))
+        rc = (lib_imm if variant >= 1000 else lib).emu_rk45(variant % 1000, p(y), p(P), p(st), B, N, C.byref(o), p(te),
+                                                           p(snap), p(ec), p(et))
         assert rc == 0, f"emulated kernel {variant}: rc {rc} (deadlock or mismatched collective, see stderr)"
         return dict(y=y, state=st, snapshots=snap, event_counts=ec, event_times=et)
     return run
@@ -64,9 +70,10 @@ def test_default_kernel_under_emulation_reproduces_scipy(emu):
     """Calibration of the emulator with the kernel that is validated on the GPU."""
     pde = oracle.default_scenario() | SCEN_A
     sol = oracle.integrate(pde, method="RK45", t_span=(0, 2e-4), t_eval=[2e-4], events=False, first_step=1e-6)
-    res = emu(320, mb.derive_column_params(pde), mb.initial_state(pde), 2e-4)
-    assert res["state"]["status"][0] == 0 and res["state"]["nfev"][0] == sol.nfev
-    assert np.max(np.abs(res["y"][0] - sol.y.reshape(5, 200, -1)[:, :, -1])) <= 1e-12
+    for variant in (320, 1320, 1450):       # default kernel; default and 4-cell kernels with -DMARLPDE_FP64_IMM=1
+        res = emu(variant, mb.derive_column_params(pde), mb.initial_state(pde), 2e-4)
+        assert res["state"]["status"][0] == 0 and res["state"]["nfev"][0] == sol.nfev, variant
+        assert np.max(np.abs(res["y"][0] - sol.y.reshape(5, 200, -1)[:, :, -1])) <= 1e-12, variant
 
 
 def test_quad_kernel_lattice_dense_output_and_slot_reuse(emu):

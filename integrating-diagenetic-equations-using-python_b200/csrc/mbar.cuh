@@ -10,6 +10,14 @@
 #define MARLPDE_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
+// kernel launch (the host emulator runs the blocks of the grid one after the other)
+#ifdef MARLPDE_HOST_EMU
+#define MARLPDE_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  ::simt::run_grid((int)(grid), (int)(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); })
+#else
+#define MARLPDE_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 namespace marlpde {
 
 #ifdef MARLPDE_HOST_EMU   // tests/emu/: kernel control logic on the host, test infrastructure only

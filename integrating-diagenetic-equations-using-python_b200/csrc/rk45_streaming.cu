@@ -498,7 +498,7 @@ struct TileSmem {
 };
 
 __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Args A, int cbuf) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MARLPDE_DYN_SMEM(smem_raw);
   constexpr int TP = kTileThreads;
   const int tid = threadIdx.x;
   const int col = blockIdx.x / A.tiles2;
@@ -755,23 +755,23 @@ cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_param
                                          (int)st::TileSmem::total);
     if (e != cudaSuccess) return e;
   }
-  st::init_kernel<<<cgrid, 128, 0, stream>>>(a);
-  st::stage_kernel<<<grid, st::kThreads, 0, stream>>>(a, 0, 0);            // K1 = f(y)
+  MARLPDE_LAUNCH(st::init_kernel, cgrid, 128, 0, stream, a);
+  MARLPDE_LAUNCH(st::stage_kernel, grid, st::kThreads, 0, stream, a, 0, 0);            // K1 = f(y)
   int pin = 0;
   // attempts + 1 prepares: the last one only closes the last attempt
   for (long long j = 0; j < attempts; ++j) {
-    st::prepare_kernel<<<grid, st::kThreads, 0, stream>>>(a, pin);
+    MARLPDE_LAUNCH(st::prepare_kernel, grid, st::kThreads, 0, stream, a, pin);
     if (use_tiles) {
-      st::tile_attempt_kernel<<<tgrid, st::kTileThreads, st::TileSmem::total, stream>>>(a, pin ^ 1);
+      MARLPDE_LAUNCH(st::tile_attempt_kernel, tgrid, st::kTileThreads, st::TileSmem::total, stream, a, pin ^ 1);
     } else {
-      for (int i = 1; i <= 6; ++i) st::stage_kernel<<<grid, st::kThreads, 0, stream>>>(a, i, pin ^ 1);
+      for (int i = 1; i <= 6; ++i) MARLPDE_LAUNCH(st::stage_kernel, grid, st::kThreads, 0, stream, a, i, pin ^ 1);
     }
     pin ^= 1;
   }
-  st::prepare_kernel<<<grid, st::kThreads, 0, stream>>>(a, pin);
+  MARLPDE_LAUNCH(st::prepare_kernel, grid, st::kThreads, 0, stream, a, pin);
   pin ^= 1;
-  if (use_tiles) st::copyback_kernel<<<grid, st::kThreads, 0, stream>>>(a, pin);
-  st::finish_kernel<<<cgrid, 128, 0, stream>>>(a, pin);
+  if (use_tiles) MARLPDE_LAUNCH(st::copyback_kernel, grid, st::kThreads, 0, stream, a, pin);
+  MARLPDE_LAUNCH(st::finish_kernel, cgrid, 128, 0, stream, a, pin);
   return cudaGetLastError();
 }
 

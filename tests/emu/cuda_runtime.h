@@ -25,6 +25,9 @@
 typedef int cudaError_t;
 typedef void* cudaStream_t;
 enum { cudaSuccess = 0, cudaErrorInvalidValue = 1 };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 
 struct double2 { double x, y; };
 struct float2 { float x, y; };
@@ -32,7 +35,9 @@ struct uint3_ { unsigned x, y, z; };
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 
+#include <functional>
 namespace simt {
+void run_grid(int grid, int n_threads, size_t dyn_smem_bytes, const std::function<void()>& body);
 unsigned char* dyn_smem();
 extern uint3_ g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
 // collectives (simt_emu.cc): every lane named in `mask` must call the same one

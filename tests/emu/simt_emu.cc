@@ -3,6 +3,7 @@
 
 #include <ucontext.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -16,7 +17,7 @@ namespace simt {
 uint3_ g_threadIdx, g_blockIdx, g_blockDim = {1, 1, 1}, g_gridDim = {1, 1, 1};
 
 namespace {
-constexpr size_t kStack = 512 * 1024;
+constexpr size_t kStack = 256 * 1024;
 struct Fiber {
   ucontext_t ctx;
   std::vector<unsigned char> stack;
@@ -171,22 +172,23 @@ void mbar_wait(uint64_t* bar, unsigned parity) {
   while (m.phase == (parity & 1u)) yield();     // the phase with this parity has not completed yet
 }
 
-int run_block(int n_threads, size_t dyn_smem_bytes, const std::function<void()>& body) {
-  fibers.clear();
-  fibers.resize(n_threads);
+int run_block(int n_threads, size_t dyn_smem_bytes, const std::function<void()>& body, int block, int grid) {
+  if ((int)fibers.size() != n_threads) fibers.resize(n_threads);     // stacks are kept between blocks
+  for (Fiber& f : fibers) f.done = false;
   rdv.clear();
   mbars.clear();
   bb = BlockBar();
   failed = false;
   progress = 0;
-  smem.assign(dyn_smem_bytes + 64, 0);
+  if (smem.size() < dyn_smem_bytes + 64) smem.resize(dyn_smem_bytes + 64);
+  std::fill(smem.begin(), smem.end(), 0);
   body_fn = &body;
   g_blockDim = {(unsigned)n_threads, 1, 1};
-  g_blockIdx = {0, 0, 0};
-  g_gridDim = {1, 1, 1};
+  g_blockIdx = {(unsigned)block, 0, 0};
+  g_gridDim = {(unsigned)grid, 1, 1};
   for (int i = 0; i < n_threads; ++i) {
     Fiber& f = fibers[i];
-    f.stack.resize(kStack);
+    if (f.stack.size() != kStack) f.stack.resize(kStack);
     getcontext(&f.ctx);
     f.ctx.uc_stack.ss_sp = f.stack.data();
     f.ctx.uc_stack.ss_size = kStack;
@@ -216,6 +218,14 @@ int run_block(int n_threads, size_t dyn_smem_bytes, const std::function<void()>&
       last_progress = progress;
     }
   }
+}
+
+void run_grid(int grid, int n_threads, size_t dyn_smem_bytes, const std::function<void()>& body) {
+  for (int b = 0; b < grid; ++b)
+    if (run_block(n_threads, dyn_smem_bytes, body, b, grid) != 0) {
+      std::fprintf(stderr, "[simt_emu] block %d of %d failed\n", b, grid);
+      std::abort();
+    }
 }
 
 }  // namespace simt

@@ -209,3 +209,66 @@ def test_radau_kernel_under_emulation_and_fused_stage_evaluation(emu_radau):
     s4 = oracle.integrate(one, method="Radau", t_span=(0, 0.006), t_eval=[0.006], events=False, first_step=5e-7,
                           jac_sparsity=oracle.jacobian_sparsity(200)).y.reshape(5, 200)
     assert np.max(np.abs(a["y"][4] - s4) / (1e-3 + 1e-3 * np.abs(s4))) <= 1.0
+
+
+# ------------------------------------------------------------------- streaming path (large depth grids)
+@pytest.fixture(scope="module")
+def emu_stream():
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    out = os.path.join(EMU, "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libemu_stream.so")
+    srcs = [os.path.join(EMU, f) for f in ("emu_stream.cc", "simt_emu.cc")]
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", "-I", EMU, "-o", so] + srcs,
+                   check=True, capture_output=True)
+    lib = C.CDLL(so)
+    lib.emu_rk45_stream.restype = C.c_int
+
+    def run(P, y, t_end, t_eval, first_step, attempts, state=None):
+        y = np.ascontiguousarray(y, dtype=np.float64).copy()
+        P = np.ascontiguousarray(P)
+        B, _, N = y.shape
+        st = batch.make_state(B, 0.0, first_step) if state is None else state.copy()
+        te = np.asarray(t_eval, dtype=np.float64)
+        snap = np.full((B, max(1, te.size), 5, N), np.nan)
+        o = _cabi.RK45Options(t_bound=t_end, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=attempts,
+                              n_eval=te.size, event_capacity=0, flags=0, reserved=0)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = lib.emu_rk45_stream(p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), C.c_longlong(attempts))
+        assert rc == 0, f"emulated streaming launcher: rc {rc}"
+        return dict(y=y, state=st, snapshots=snap)
+    return run
+
+
+@pytest.mark.parametrize("n_cells,ncol", [(16, 2), (641, 2), (1257, 1)])
+def test_streaming_launcher_under_emulation_reproduces_scipy(emu_stream, n_cells, ncol, monkeypatch):
+    """csrc/rk45_streaming.cu with its own launcher (init / K1 / prepare + tile_attempt or six stage launches / copyback /
+    finish), every launch run block by block: both modes, ragged last tiles, batches of 16 attempts resumed from the
+    column state as the host driver does (csrc/cabi.cu rk45_integrate_streaming) — the GPU test
+    test_streaming_path_matches_scipy at a shorter t_end."""
+    pde = oracle.default_scenario() | SCEN_A | {"N": n_cells}
+    scale = min(1.0, (200 / n_cells) ** 2)
+    t_end, fs = 60 * 2.6e-6 * scale, 1e-6 * scale
+    te = [0.0, 0.4 * t_end, t_end]
+    P, y0 = np.repeat(mb.derive_column_params(pde), ncol), np.repeat(mb.initial_state(pde), ncol, 0)
+    sol = oracle.integrate(pde, method="RK45", t_span=(0, t_end), t_eval=te, events=False, first_step=fs)
+    want = sol.y.reshape(5, n_cells, -1)
+    got = {}
+    for mode in ("tiles", "stages"):
+        monkeypatch.setenv("MARLPDE_RK45_STREAM", mode)
+        r = emu_stream(P, y0, t_end, te, fs, 16)
+        while np.any((r["state"]["status"] == 1) | (r["state"]["status"] == 2)):
+            nxt = emu_stream(P, r["y"], t_end, te, fs, 16, state=r["state"])
+            keep = np.isnan(nxt["snapshots"])
+            nxt["snapshots"][keep] = r["snapshots"][keep]
+            r = nxt
+        assert np.all(r["state"]["status"] == 0) and np.all(r["state"]["t"] == t_end) and np.all(r["state"]["next_eval"] == 3)
+        assert np.all(r["state"]["nfev"] == sol.nfev), (mode, r["state"]["nfev"], sol.nfev)
+        assert np.max(np.abs(r["y"][0] - want[:, :, -1])) <= 1e-12
+        assert np.max(np.abs(r["snapshots"][0] - np.moveaxis(want, 2, 0))) <= 1e-12
+        assert np.array_equal(r["y"][0], r["y"][-1])
+        got[mode] = r
+    for k in ("n_accepted", "n_rejected", "nfev"):
+        assert np.array_equal(got["tiles"]["state"][k], got["stages"]["state"][k]), k
+    assert np.max(np.abs(got["tiles"]["y"] - got["stages"]["y"])) <= 1e-12

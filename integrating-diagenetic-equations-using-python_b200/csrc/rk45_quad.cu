@@ -1,5 +1,5 @@
 // rk45_quad.cu — EXPERIMENTAL build of the on-chip RK45 kernel: four depth cells per thread, eight warps.
-// Selected with MARLPDE_RK45_BUILD=450 (N % 4 == 0, N <= 1024); NOT the default and not yet run on a GPU
+// Selected with MARLPDE_RK45_BUILD=450 (N % 4 == 0, N <= 1024); NOT the default; first GPU contact r01i: counters identical to the default build, +3.6 %
 // (DESIGN.md 10.3).  Same algorithm, same controller, same event handling as rk45_persistent.cu — read that
 // file first; this one only differs in how the work is laid out:
 //

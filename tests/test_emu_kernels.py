@@ -1,6 +1,6 @@
 """Kernel control logic on the host: the batched Radau kernel (csrc/radau_batch.cu, as is and with the experimental
 -DMARLPDE_RADAU_FUSE_F=1) and the on-chip RK45 kernels (csrc/rk45_persistent.cu — the default build, validated on
-B200 — and csrc/rk45_quad.cu — the experimental 4-cells-per-thread build that has not been on a GPU yet) are compiled
+B200 — and csrc/rk45_quad.cu — the experimental 4-cells-per-thread build whose GPU parity suite has not been run yet) are compiled
 for the host with g++ and run one thread block at a time by a small SIMT emulator (tests/emu/: one fiber per CUDA thread,
 rendezvous at every barrier / warp collective / mbarrier wait; a missing barrier or a collective that not all named
 lanes reach is reported instead of hanging).

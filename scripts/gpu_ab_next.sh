@@ -20,6 +20,8 @@ for m in 2 3; do   # other RHS instruction schedules under the 8-warp kernel (25
 done
 MARLPDE_RK45_BUILD=450 timeout 300 python -m pytest -q -x -m gpu -p no:cacheprovider --timeout=60 --timeout-method=thread tests/test_gpu_rk45.py tests/test_gpu_dropin.py > $OUT/pytest_quad.log 2>&1
 echo "pytest quad: $(tail -3 $OUT/pytest_quad.log | tr '\n' ' ')"
+# r01i first contact: build 450 is correct but only +3.6 % (static estimate +25 %): capture it, after the plain runs above exited
+MARLPDE_RK45_BUILD=450 MARLPDE_PROFILE_EVENTS=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:rk45_quad -s 1 -c 1 -o $OUT/rk45_quad_full python scripts/profile_rk45.py 300 3 > $OUT/ncu_quad_full.log 2>&1; echo "ncu quad: rc $?"
 MARLPDE_B200_LIB=$B/lib_imm.so timeout 120 python scripts/profile_radau.py 16 0.05 > $OUT/radau_imm.log 2>&1; echo "radau imm: $(head -1 $OUT/radau_imm.log)"
 timeout 120 python scripts/profile_radau.py 16 0.05 > $OUT/radau_intree.log 2>&1; echo "radau in-tree: $(head -1 $OUT/radau_intree.log)"
 # -DMARLPDE_RADAU_FUSE_F=1: the three stage evaluations of a Newton iteration fused with B = TI F - M W (6 x 5N fewer doubles through DRAM)

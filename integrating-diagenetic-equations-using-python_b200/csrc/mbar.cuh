@@ -10,6 +10,11 @@
 #define MARLPDE_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
+// A/B candidate (off): spread the last columns of a sweep over the SMs (rk45_persistent.cu / rk45_quad.cu slot service)
+#ifndef MARLPDE_TAIL_SPREAD
+#define MARLPDE_TAIL_SPREAD 0
+#endif
+
 // kernel launch (the host emulator runs the blocks of the grid one after the other)
 #ifdef MARLPDE_HOST_EMU
 #define MARLPDE_LAUNCH(kernel, grid, block, smem, stream, ...) \

@@ -515,7 +515,13 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
     if (svc) {
       // -- claim columns for idle slots
       if (leader && col < 0 && !exhausted) {
+#if MARLPDE_TAIL_SPREAD   // slot s only claims while more than s columns per CTA are left: the tail of a sweep (and a
+                          // batch smaller than the machine) is spread one column per SM instead of stacked on a few
+        const int left = A.n_columns - *reinterpret_cast<volatile int32_t*>(A.g_queue);
+        const int cc = (slot > 0 && left <= slot * (int)gridDim.x) ? A.n_columns : atomicAdd(A.g_queue, 1);
+#else
         const int cc = atomicAdd(A.g_queue, 1);
+#endif
         sSlotCol[slot] = cc < A.n_columns ? cc : -1;
       }
       __syncthreads();
@@ -862,7 +868,7 @@ static cudaError_t launch_t(const Rk45Args& a, int sm_count, int smem_budget, cu
   const size_t smem = Smem<TP, YS, HS>::total(args.C);
   cudaError_t e = cudaFuncSetAttribute(rk45_persistent_kernel<TP, YS, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  int grid = (a.n_columns + args.C - 1) / args.C;
+  int grid = MARLPDE_TAIL_SPREAD ? a.n_columns : (a.n_columns + args.C - 1) / args.C;
   if (grid > sm_count) grid = sm_count;
   if (grid < 1) grid = 1;
   const int threads = ((args.C * Hc + 31) / 32) * 32;

@@ -405,7 +405,13 @@ __global__ void __launch_bounds__(TP, 1) rk45_quad_kernel(const Args A) {
     const int svc = *sSvc;
     if (svc) {
       if (leader && col < 0 && !exhausted) {
+#if MARLPDE_TAIL_SPREAD   // slot s only claims while more than s columns per CTA are left: the tail of a sweep (and a
+                          // batch smaller than the machine) is spread one column per SM instead of stacked on a few
+        const int left = A.n_columns - *reinterpret_cast<volatile int32_t*>(A.g_queue);
+        const int cc = (slot > 0 && left <= slot * (int)gridDim.x) ? A.n_columns : atomicAdd(A.g_queue, 1);
+#else
         const int cc = atomicAdd(A.g_queue, 1);
+#endif
         sSlotCol[slot] = cc < A.n_columns ? cc : -1;
       }
       __syncthreads();
@@ -784,7 +790,7 @@ cudaError_t launch_rk45_quad(double* d_y, const marlpde_column_params* d_params,
   const size_t smem = quad::Smem::total(a.C);
   cudaError_t e = cudaFuncSetAttribute(quad::rk45_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  int grid = (n_columns + a.C - 1) / a.C;
+  int grid = MARLPDE_TAIL_SPREAD ? n_columns : (n_columns + a.C - 1) / a.C;
   if (grid > sm_count) grid = sm_count;
   if (grid < 1) grid = 1;
   quad::rk45_quad_kernel<<<grid, quad::TP, smem, stream>>>(a);

@@ -22,6 +22,18 @@ MARLPDE_RK45_BUILD=450 timeout 300 python -m pytest -q -x -m gpu -p no:cacheprov
 echo "pytest quad: $(tail -3 $OUT/pytest_quad.log | tr '\n' ' ')"
 # r01i first contact: build 450 is correct but only +3.6 % (static estimate +25 %): capture it, after the plain runs above exited
 MARLPDE_RK45_BUILD=450 MARLPDE_PROFILE_EVENTS=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:rk45_quad -s 1 -c 1 -o $OUT/rk45_quad_full python scripts/profile_rk45.py 300 3 > $OUT/ncu_quad_full.log 2>&1; echo "ncu quad: rc $?"
+# -DMARLPDE_TAIL_SPREAD=1: slot s of a CTA claims only while more than s * gridDim columns are left, grid = min(SMs, columns): the
+# last (partly filled) round of a sweep and batches smaller than the machine run one column per SM (results are slot independent:
+# bit-identical).  4096 columns x 3000 attempts (the bench step: 9.2 rounds of 444 slots), 64 columns, build 450 too; then parity.
+for lat in 16,16,16 4,4,4; do
+  for l in $IN $B/lib_spread.so; do
+    MARLPDE_PROFILE_LATTICE=$lat MARLPDE_B200_LIB=$l MARLPDE_PROFILE_EVENTS=1 timeout 120 python scripts/profile_rk45.py 3000 3 > $OUT/rk45_spread_tmp.log 2>&1
+    echo "rk45 lattice $lat $(basename $l): $(tail -1 $OUT/rk45_spread_tmp.log)"; cat $OUT/rk45_spread_tmp.log >> $OUT/rk45_spread.log
+  done
+done
+MARLPDE_RK45_BUILD=450 MARLPDE_B200_LIB=$B/lib_spread.so MARLPDE_PROFILE_EVENTS=1 timeout 120 python scripts/profile_rk45.py 3000 3 > $OUT/rk45_quad_spread.log 2>&1; echo "rk45 quad + spread: $(tail -1 $OUT/rk45_quad_spread.log)"
+MARLPDE_B200_LIB=$B/lib_spread.so timeout 400 python -m pytest -q -x -m gpu -p no:cacheprovider --timeout=120 --timeout-method=thread tests/test_gpu_rk45.py tests/test_gpu_dropin.py > $OUT/pytest_spread.log 2>&1
+echo "pytest spread: $(tail -1 $OUT/pytest_spread.log)"
 MARLPDE_B200_LIB=$B/lib_imm.so timeout 120 python scripts/profile_radau.py 16 0.05 > $OUT/radau_imm.log 2>&1; echo "radau imm: $(head -1 $OUT/radau_imm.log)"
 timeout 120 python scripts/profile_radau.py 16 0.05 > $OUT/radau_intree.log 2>&1; echo "radau in-tree: $(head -1 $OUT/radau_intree.log)"
 # -DMARLPDE_RADAU_FUSE_F=1: the three stage evaluations of a Newton iteration fused with B = TI F - M W (6 x 5N fewer doubles through DRAM)

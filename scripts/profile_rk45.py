@@ -13,7 +13,8 @@ launches = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 base = asdict(Map_Scenario())
 if len(sys.argv) > 3 and sys.argv[3] == "scenario_A":
     base |= {"Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}
-pde = mb.sweep_lattice(base, 16, 16, 16)
+lat = [int(v) for v in os.environ.get("MARLPDE_PROFILE_LATTICE", "16,16,16").split(",")]   # e.g. 4,4,4: a batch smaller than the machine
+pde = mb.sweep_lattice(base, *lat)
 P = mb.derive_column_params(pde)
 y = torch.from_numpy(mb.initial_state(pde)).cuda()
 dP = mb.batch.params_to_device(P, y.device)

@@ -16,6 +16,9 @@ extern "C" int emu_rk45(int variant, double* y, const marlpde_column_params* par
   using namespace marlpde;
   int32_t queue = 0;
   const int budget = 227 * 1024;
+  // EMU_GRID blocks, one after the other, on the same column queue (the claim policy sees gridDim.x = EMU_GRID)
+  const char* ge = std::getenv("EMU_GRID");
+  const int grid = ge && std::atoi(ge) > 0 ? std::atoi(ge) : 1;
   if (variant == 450) {
     quad::Args a;
     a.g_y = y;
@@ -32,7 +35,9 @@ extern "C" int emu_rk45(int variant, double* y, const marlpde_column_params* par
     if (a.C <= 0) return -2;
     a.logG = quad::group_log2(n_cells / quad::Q);
     a.opt = *opt;
-    return simt::run_block(quad::TP, quad::Smem::total(a.C), [&]() { quad::rk45_quad_kernel(a); });
+    for (int b = 0; b < grid; ++b)
+      if (int rc = simt::run_block(quad::TP, quad::Smem::total(a.C), [&]() { quad::rk45_quad_kernel(a); }, b, grid)) return rc;
+    return 0;
   }
   Rk45Args a;
   a.g_y = y;
@@ -52,6 +57,9 @@ extern "C" int emu_rk45(int variant, double* y, const marlpde_column_params* par
   a.warp_perm = ~0ull;
   a.opt = *opt;
   const int threads = ((a.C * Hc + 31) / 32) * 32;
-  return simt::run_block(threads, Smem<320, false, false>::total(a.C),
-                         [&]() { rk45_persistent_kernel<320, false, false>(a); });
+  for (int b = 0; b < grid; ++b)
+    if (int rc = simt::run_block(threads, Smem<320, false, false>::total(a.C),
+                                 [&]() { rk45_persistent_kernel<320, false, false>(a); }, b, grid))
+      return rc;
+  return 0;
 }

@@ -43,6 +43,11 @@ def emu():
                     "-o", so_imm] + srcs, check=True, capture_output=True)
     lib_imm = C.CDLL(so_imm)
     lib_imm.emu_rk45.restype = C.c_int
+    so_spread = os.path.join(out, "libemu_rk45_spread.so")     # the experimental claim policy (-DMARLPDE_TAIL_SPREAD=1)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", "-DMARLPDE_TAIL_SPREAD=1", "-I", EMU,
+                    "-o", so_spread] + srcs, check=True, capture_output=True)
+    lib_spread = C.CDLL(so_spread)
+    lib_spread.emu_rk45.restype = C.c_int
 
     def run(variant, P, y, t_end, t_eval=(), events=False, first_step=1e-6, max_steps=0, state=None, capacity=16):
         y = np.ascontiguousarray(y, dtype=np.float64).copy()
@@ -56,8 +61,8 @@ def emu():
         o = _cabi.RK45Options(t_bound=t_end, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=max_steps,
                               n_eval=te.size, event_capacity=capacity, flags=_cabi.FLAG_EVENTS if events else 0, reserved=0)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
-        rc = (lib_imm if variant >= 1000 else lib).emu_rk45(variant % 1000, p(y), p(P), p(st), B, N, C.byref(o), p(te),
-                                                           p(snap), p(ec), p(et))
+        which = lib_spread if variant >= 2000 else lib_imm if variant >= 1000 else lib
+        rc = which.emu_rk45(variant % 1000, p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), p(ec), p(et))
         assert rc == 0, f"emulated kernel {variant}: rc {rc} (deadlock or mismatched collective, see stderr)"
         return dict(y=y, state=st, snapshots=snap, event_counts=ec, event_times=et)
     return run
@@ -145,6 +150,25 @@ def test_quad_kernel_resume_is_bit_identical_and_other_grids(emu):
         res = emu(450, np.repeat(mb.derive_column_params(p2), 3), np.repeat(mb.initial_state(p2), 3, 0), t_end, first_step=h0)
         assert np.all(res["state"]["nfev"] == sol.nfev), n_cells
         assert np.max(np.abs(res["y"][1] - sol.y.reshape(5, n_cells, -1)[:, :, -1])) <= 1e-12, n_cells
+
+
+def test_tail_spread_claim_policy_processes_every_column_with_identical_results(emu, monkeypatch):
+    """-DMARLPDE_TAIL_SPREAD=1 (A/B candidate, off by default): slot s of a CTA only claims while more than s * gridDim
+    columns are left.  Eight columns on a grid of three CTAs that share one queue (run one after the other): slots that
+    decline retire for good, CTAs that find the queue empty leave at once, every column is integrated, and — results being
+    independent of the slot a column runs in — bit-identical to the default policy.  Both on-chip kernels."""
+    pde = mb.sweep_lattice(oracle.default_scenario(), 2, 2, 2)
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    te = [1e-4, 1.5e-4]
+    for variant, grids in ((320, ("3", "8")), (450, ("3",))):
+        monkeypatch.setenv("EMU_GRID", "1")
+        ref = emu(variant, P, y0, 1.5e-4, t_eval=te, events=True, first_step=5e-7)
+        for grid in grids:
+            monkeypatch.setenv("EMU_GRID", grid)
+            got = emu(2000 + variant, P, y0, 1.5e-4, t_eval=te, events=True, first_step=5e-7)
+            assert np.all(got["state"]["status"] == 0) and np.all(got["state"]["t"] == 1.5e-4), (variant, grid)
+            assert np.array_equal(got["state"], ref["state"]) and np.array_equal(got["y"], ref["y"]), (variant, grid)
+            assert np.array_equal(got["snapshots"], ref["snapshots"]) and np.array_equal(got["event_counts"], ref["event_counts"])
 
 
 # --------------------------------------------------------------------------------------- Radau kernel

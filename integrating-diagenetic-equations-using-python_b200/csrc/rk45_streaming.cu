@@ -493,9 +493,11 @@ struct TileSmem {
   static constexpr size_t off_tab = off_O + sizeof(double) * 2 * 5 * kTileThreads;
   static constexpr size_t off_kc = off_tab + fm::kTableBytes;
   static constexpr size_t off_red = off_kc + (sizeof(ColumnConsts) + 15) / 16 * 16;
-  static constexpr size_t off_bar = off_red + 16 * sizeof(double);
-  static constexpr size_t total = off_bar + 16;
+  static constexpr size_t off_bar = off_red + 16 * sizeof(double);                      // two mbarriers
+  static constexpr size_t off_stage = off_bar + 16;                                    // double [2][5][640] (MARLPDE_TILE_TMA)
+  static constexpr size_t total = off_stage + (MARLPDE_TILE_TMA ? sizeof(double) * 2 * 5 * kTileCells : 0);
 };
+static_assert(TileSmem::off_stage % 16 == 0 && TileSmem::total <= 227 * 1024, "tile kernel shared memory");
 
 __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Args A, int cbuf) {
   MARLPDE_DYN_SMEM(smem_raw);
@@ -518,6 +520,30 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
   if (tid == 0) make_consts(A.params[col], N, kc);
   const size_t vec = (size_t)A.B * 5 * N;
   const double h = c0.h;
+#if MARLPDE_TILE_TMA
+  // Window loads and write-back by the TMA unit: ten 1-D bulk copies each way (5 fields x {y, K1} in, {y_new, K7} out) issued
+  // by one thread, in flight while the tables and the column constants are set up.  Every row start and length is a
+  // multiple of 16 bytes when N is even (window starts and the 628-cell stride are even); odd N keeps the plain loads.
+  double* const sStage = reinterpret_cast<double*>(smem_raw + TileSmem::off_stage);
+  uint64_t* const sLoad = sBar + 1;
+  const bool tma = (N & 1) == 0 && ((reinterpret_cast<uintptr_t>(A.y) | reinterpret_cast<uintptr_t>(A.K) |
+                                      reinterpret_cast<uintptr_t>(A.tile)) & 15) == 0;   // (a caller's view may be 8-byte aligned)
+  const int w0 = tile * kTileValid - kTileHalo;              // global cell of window position 0
+  if (tma && tid == 0) {
+    const int lo = w0 < 0 ? 0 : w0, hi = w0 + kTileCells < N ? w0 + kTileCells : N;
+    const unsigned bytes = (unsigned)(hi - lo) * 8u;
+    mbar_init(sLoad, 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(sLoad, 10u * bytes);
+    const size_t row0 = (size_t)col * 5 * N + (size_t)lo;
+    const double* const ysrc = ybuf(A, c0.ysl) + row0;
+    const double* const ksrc = A.K + (size_t)c0.k1 * vec + row0;
+    for (int f = 0; f < 5; ++f) {
+      bulk_g2s(sStage + f * kTileCells + (lo - w0), ysrc + (size_t)f * N, bytes, sLoad);
+      bulk_g2s(sStage + (5 + f) * kTileCells + (lo - w0), ksrc + (size_t)f * N, bytes, sLoad);
+    }
+  }
+#endif
 
   const int e0 = 2 * tid;                                   // position inside the window
   const int g0 = tile * kTileValid - kTileHalo + e0;        // global cell of my first cell (always even)
@@ -540,6 +566,21 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
   auto Kld = [&](int s, int f) -> double2 { return sK[(s * 5 + f) * TP]; };
 
   double y[5][2], k1[5][2], c[5][2], r[5][2];
+#if MARLPDE_TILE_TMA
+  if (tma) {
+    __syncthreads();                                        // the load barrier is initialised
+    mbar_wait(sLoad, 0);                                    // ... and the ten rows have landed
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {                           // (positions outside the column hold stale bytes: not selected)
+      const double2 yv = *reinterpret_cast<const double2*>(sStage + f * kTileCells + e0);
+      const double2 kv = *reinterpret_cast<const double2*>(sStage + (5 + f) * kTileCells + e0);
+      y[f][0] = in0 ? yv.x : 0.5;
+      y[f][1] = in1 ? yv.y : 0.5;
+      k1[f][0] = in0 ? kv.x : 0.0;
+      k1[f][1] = in1 ? kv.y : 0.0;
+    }
+  } else
+#endif
   {
     const double* K1g = Kslot(1);
 #pragma unroll
@@ -682,13 +723,21 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
     if (out0) part = fma(z0, z0, part);
     if (out1) part = fma(z1, z1, part);
     const size_t o = base + (size_t)f * N;
-    if (out0) {
-      ynew[o] = c[f][0];
-      K7g[o] = r[f][0];
-    }
-    if (out1) {
-      ynew[o + 1] = c[f][1];
-      K7g[o + 1] = r[f][1];
+#if MARLPDE_TILE_TMA
+    if (tma) {                                               // staged; one thread stores the owned range below
+      *reinterpret_cast<double2*>(sStage + f * kTileCells + e0) = make_double2(c[f][0], c[f][1]);
+      *reinterpret_cast<double2*>(sStage + (5 + f) * kTileCells + e0) = make_double2(r[f][0], r[f][1]);
+    } else
+#endif
+    {
+      if (out0) {
+        ynew[o] = c[f][0];
+        K7g[o] = r[f][0];
+      }
+      if (out1) {
+        ynew[o + 1] = c[f][1];
+        K7g[o + 1] = r[f][1];
+      }
     }
     if (sample) {                                            // K3..K6 are only needed by the dense output
       if (out0) {
@@ -708,11 +757,26 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
   if ((tid & 31) == 0) red[tid >> 5] = part;
+#if MARLPDE_TILE_TMA
+  if (tma) fence_proxy_async();                              // my staged values, for the bulk stores after the barrier
+#endif
   __syncthreads();
   if (tid == 0) {
     double s = 0.0;
     for (int w = 0; w < kTileThreads / 32; ++w) s += red[w];
     A.partials[(size_t)col * A.tiles2 + tile] = s;
+#if MARLPDE_TILE_TMA
+    if (tma) {                                               // the cells this window owns: window positions [6, 634) inside the column
+      const int olo = w0 + kTileHalo, ohi = olo + kTileValid < N ? olo + kTileValid : N;
+      const unsigned bytes = (unsigned)(ohi - olo) * 8u;
+      const size_t row0 = (size_t)col * 5 * N + (size_t)olo;
+      for (int f = 0; f < 5; ++f) {
+        bulk_s2g(ynew + row0 + (size_t)f * N, sStage + f * kTileCells + kTileHalo, bytes);
+        bulk_s2g(K7g + row0 + (size_t)f * N, sStage + (5 + f) * kTileCells + kTileHalo, bytes);
+      }
+      bulk_commit_wait();
+    }
+#endif
   }
 }
 

@@ -34,6 +34,15 @@ done
 MARLPDE_RK45_BUILD=450 MARLPDE_B200_LIB=$B/lib_spread.so MARLPDE_PROFILE_EVENTS=1 timeout 120 python scripts/profile_rk45.py 3000 3 > $OUT/rk45_quad_spread.log 2>&1; echo "rk45 quad + spread: $(tail -1 $OUT/rk45_quad_spread.log)"
 MARLPDE_B200_LIB=$B/lib_spread.so timeout 400 python -m pytest -q -x -m gpu -p no:cacheprovider --timeout=120 --timeout-method=thread tests/test_gpu_rk45.py tests/test_gpu_dropin.py > $OUT/pytest_spread.log 2>&1
 echo "pytest spread: $(tail -1 $OUT/pytest_spread.log)"
+# -DMARLPDE_TILE_TMA=1: the tile kernel of the large-N path moves its windows with 1-D TMA bulk copies (UBLKCP; never run on a GPU):
+# parity first (streaming tests, under a short timeout), then N = 20 000 x 64 and N = 2 000 x 64 against the in-tree library
+MARLPDE_B200_LIB=$B/lib_tma.so timeout 300 python -m pytest -q -x -m gpu -p no:cacheprovider --timeout=60 --timeout-method=thread tests/test_gpu_rk45.py -k streaming > $OUT/pytest_tma.log 2>&1
+echo "pytest tma: $(tail -1 $OUT/pytest_tma.log)"
+for l in $IN $B/lib_tma.so; do
+  for n in 20000 2000; do
+    MARLPDE_B200_LIB=$l timeout 120 python scripts/profile_stream.py $n 64 > $OUT/stream_tmp.log 2>&1; echo "stream N=$n x 64 $(basename $l): $(tail -1 $OUT/stream_tmp.log)"
+  done
+done
 MARLPDE_B200_LIB=$B/lib_imm.so timeout 120 python scripts/profile_radau.py 16 0.05 > $OUT/radau_imm.log 2>&1; echo "radau imm: $(head -1 $OUT/radau_imm.log)"
 timeout 120 python scripts/profile_radau.py 16 0.05 > $OUT/radau_intree.log 2>&1; echo "radau in-tree: $(head -1 $OUT/radau_intree.log)"
 # -DMARLPDE_RADAU_FUSE_F=1: the three stage evaluations of a Newton iteration fused with B = TI F - M W (6 x 5N fewer doubles through DRAM)

@@ -242,14 +242,17 @@ def emu_stream():
         pytest.skip("g++ not available")
     out = os.path.join(EMU, "_build")
     os.makedirs(out, exist_ok=True)
-    so = os.path.join(out, "libemu_stream.so")
     srcs = [os.path.join(EMU, f) for f in ("emu_stream.cc", "simt_emu.cc")]
-    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", "-I", EMU, "-o", so] + srcs,
-                   check=True, capture_output=True)
-    lib = C.CDLL(so)
-    lib.emu_rk45_stream.restype = C.c_int
+    libs = {}
+    for tma in (0, 1):                     # 1: the tile kernel's windows by 1-D bulk copies (-DMARLPDE_TILE_TMA=1, A/B candidate)
+        so = os.path.join(out, f"libemu_stream{tma}.so")
+        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", f"-DMARLPDE_TILE_TMA={tma}", "-I", EMU,
+                        "-o", so] + srcs, check=True, capture_output=True)
+        libs[tma] = C.CDLL(so)
+        libs[tma].emu_rk45_stream.restype = C.c_int
 
-    def run(P, y, t_end, t_eval, first_step, attempts, state=None):
+    def run(P, y, t_end, t_eval, first_step, attempts, state=None, tma=0):
+        lib = libs[tma]
         y = np.ascontiguousarray(y, dtype=np.float64).copy()
         P = np.ascontiguousarray(P)
         B, _, N = y.shape
@@ -296,3 +299,23 @@ def test_streaming_launcher_under_emulation_reproduces_scipy(emu_stream, n_cells
     for k in ("n_accepted", "n_rejected", "nfev"):
         assert np.array_equal(got["tiles"]["state"][k], got["stages"]["state"][k]), k
     assert np.max(np.abs(got["tiles"]["y"] - got["stages"]["y"])) <= 1e-12
+
+
+@pytest.mark.parametrize("n_cells", [16, 628, 1256, 1884, 1300])
+def test_tile_kernel_bulk_copy_windows_are_bit_identical(emu_stream, n_cells, monkeypatch):
+    """-DMARLPDE_TILE_TMA=1 (A/B candidate, off by default): the tile kernel loads y and K1 of its 640-cell window and stores
+    y_new and K7 of the 628 cells it owns with ten 1-D bulk copies each way (on the host: memcpy at issue).  Window clipping
+    at both column ends, a column that ends exactly on a window boundary, one-window columns and a sampled step: the same
+    bits as the per-thread loads and stores."""
+    monkeypatch.setenv("MARLPDE_RK45_STREAM", "tiles")
+    pde = oracle.default_scenario() | SCEN_A | {"N": n_cells}
+    scale = min(1.0, (200 / n_cells) ** 2)
+    fs = 1e-6 * scale
+    te = [0.0, 4 * fs, 1.0]
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    y0 = y0 * (1 + 0.01 * np.sin(np.arange(n_cells) * 0.37))          # a profile, so that misplaced rows would show
+    a = emu_stream(P, y0, 1.0, te, fs, 12)
+    b = emu_stream(P, y0, 1.0, te, fs, 12, tma=1)
+    assert a["state"]["n_accepted"][0] >= 8 and a["state"]["next_eval"][0] == 2
+    assert np.array_equal(a["state"], b["state"]) and np.array_equal(a["y"], b["y"])
+    assert np.array_equal(a["snapshots"][:, :2], b["snapshots"][:, :2])

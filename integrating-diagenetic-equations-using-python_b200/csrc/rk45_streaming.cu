@@ -28,6 +28,8 @@
 
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
 
 #include "dopri.cuh"
 #include "lheureux_device.cuh"
@@ -784,12 +786,21 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
 
 size_t rk45_stream_workspace_bytes(int n_columns, int n_cells) { return st::layout(n_columns, n_cells).total; }
 
+namespace {
+struct GraphKey {             // everything a captured batch depends on (compared bytewise)
+  st::Args a;
+  long long attempts;
+  int use_tiles, device;
+};
+}  // namespace
+
 cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_params, marlpde_column_state* d_state,
                                int n_columns, int n_cells, const marlpde_rk45_options& opt, const double* d_t_eval,
                                double* d_snap, void* d_work, long long attempts, cudaStream_t stream) {
   const st::Layout L = st::layout(n_columns, n_cells);
   unsigned char* w = static_cast<unsigned char*>(d_work);
   st::Args a;
+  std::memset(&a, 0, sizeof a);               // (padding bytes take part in the graph-cache comparison)
   a.y = d_y;
   a.params = d_params;
   a.state = d_state;
@@ -819,24 +830,67 @@ cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_param
                                          (int)st::TileSmem::total);
     if (e != cudaSuccess) return e;
   }
-  MARLPDE_LAUNCH(st::init_kernel, cgrid, 128, 0, stream, a);
-  MARLPDE_LAUNCH(st::stage_kernel, grid, st::kThreads, 0, stream, a, 0, 0);            // K1 = f(y)
-  int pin = 0;
-  // attempts + 1 prepares: the last one only closes the last attempt
-  for (long long j = 0; j < attempts; ++j) {
-    MARLPDE_LAUNCH(st::prepare_kernel, grid, st::kThreads, 0, stream, a, pin);
-    if (use_tiles) {
-      MARLPDE_LAUNCH(st::tile_attempt_kernel, tgrid, st::kTileThreads, st::TileSmem::total, stream, a, pin ^ 1);
-    } else {
-      for (int i = 1; i <= 6; ++i) MARLPDE_LAUNCH(st::stage_kernel, grid, st::kThreads, 0, stream, a, i, pin ^ 1);
+  auto enqueue = [&](cudaStream_t s_) -> cudaError_t {
+    MARLPDE_LAUNCH(st::init_kernel, cgrid, 128, 0, s_, a);
+    MARLPDE_LAUNCH(st::stage_kernel, grid, st::kThreads, 0, s_, a, 0, 0);            // K1 = f(y)
+    int pin = 0;
+    // attempts + 1 prepares: the last one only closes the last attempt
+    for (long long j = 0; j < attempts; ++j) {
+      MARLPDE_LAUNCH(st::prepare_kernel, grid, st::kThreads, 0, s_, a, pin);
+      if (use_tiles) {
+        MARLPDE_LAUNCH(st::tile_attempt_kernel, tgrid, st::kTileThreads, st::TileSmem::total, s_, a, pin ^ 1);
+      } else {
+        for (int i = 1; i <= 6; ++i) MARLPDE_LAUNCH(st::stage_kernel, grid, st::kThreads, 0, s_, a, i, pin ^ 1);
+      }
+      pin ^= 1;
     }
+    MARLPDE_LAUNCH(st::prepare_kernel, grid, st::kThreads, 0, s_, a, pin);
     pin ^= 1;
+    if (use_tiles) MARLPDE_LAUNCH(st::copyback_kernel, grid, st::kThreads, 0, s_, a, pin);
+    MARLPDE_LAUNCH(st::finish_kernel, cgrid, 128, 0, s_, a, pin);
+    return cudaGetLastError();
+  };
+#ifndef MARLPDE_HOST_EMU
+  // MARLPDE_RK45_STREAM_GRAPH=1 (off by default; not measured yet): the launches of a batch are captured once into a CUDA graph
+  // and replayed — a batch of a few columns is bound by launch latency (two dependent launches per attempt), and the host
+  // driver repeats identical batches (all step state lives in device memory, the kernel arguments do not change).
+  const char* graph_env = std::getenv("MARLPDE_RK45_STREAM_GRAPH");
+  if (graph_env && graph_env[0] == '1' && attempts <= 1024) {
+    static std::mutex mu;
+    static struct { bool valid; GraphKey key; cudaGraphExec_t exec; cudaStream_t cap; } cache = {false, {}, nullptr, nullptr};
+    std::lock_guard<std::mutex> lock(mu);
+    GraphKey key;
+    std::memset(&key, 0, sizeof key);
+    key.a = a;
+    key.attempts = attempts;
+    key.use_tiles = use_tiles;
+    cudaError_t e = cudaGetDevice(&key.device);
+    if (e != cudaSuccess) return e;
+    if (!(cache.valid && std::memcmp(&cache.key, &key, sizeof key) == 0)) {
+      if (cache.exec) cudaGraphExecDestroy(cache.exec);
+      if (cache.cap) cudaStreamDestroy(cache.cap);           // (a stream belongs to the device it was created on)
+      cache.valid = false;
+      cache.exec = nullptr;
+      cache.cap = nullptr;
+      if ((e = cudaStreamCreateWithFlags(&cache.cap, cudaStreamNonBlocking)) != cudaSuccess) return e;
+      if ((e = cudaStreamBeginCapture(cache.cap, cudaStreamCaptureModeThreadLocal)) != cudaSuccess) return e;
+      const cudaError_t el = enqueue(cache.cap);
+      cudaGraph_t graph = nullptr;
+      e = cudaStreamEndCapture(cache.cap, &graph);
+      if (el != cudaSuccess || e != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        return el != cudaSuccess ? el : e;
+      }
+      e = cudaGraphInstantiate(&cache.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) return e;
+      cache.key = key;
+      cache.valid = true;
+    }
+    return cudaGraphLaunch(cache.exec, stream);
   }
-  MARLPDE_LAUNCH(st::prepare_kernel, grid, st::kThreads, 0, stream, a, pin);
-  pin ^= 1;
-  if (use_tiles) MARLPDE_LAUNCH(st::copyback_kernel, grid, st::kThreads, 0, stream, a, pin);
-  MARLPDE_LAUNCH(st::finish_kernel, cgrid, 128, 0, stream, a, pin);
-  return cudaGetLastError();
+#endif
+  return enqueue(stream);
 }
 
 }  // namespace marlpde

@@ -43,6 +43,15 @@ for l in $IN $B/lib_tma.so; do
     MARLPDE_B200_LIB=$l timeout 120 python scripts/profile_stream.py $n 64 > $OUT/stream_tmp.log 2>&1; echo "stream N=$n x 64 $(basename $l): $(tail -1 $OUT/stream_tmp.log)"
   done
 done
+# MARLPDE_RK45_STREAM_GRAPH=1 (runtime switch of the in-tree library): a batch of the streaming path captured once into a CUDA graph and
+# replayed; small batches are launch bound (N = 20 000 x 1: 37 k attempts/s).  Parity (streaming tests), then timing with 256 attempts.
+MARLPDE_RK45_STREAM_GRAPH=1 timeout 300 python -m pytest -q -x -m gpu -p no:cacheprovider --timeout=60 --timeout-method=thread tests/test_gpu_rk45.py -k streaming > $OUT/pytest_graph.log 2>&1
+echo "pytest graph: $(tail -1 $OUT/pytest_graph.log)"
+for g in 0 1; do
+  for nb in "20000 1" "2000 8" "20000 64"; do
+    MARLPDE_RK45_STREAM_GRAPH=$g timeout 120 python scripts/profile_stream.py $nb 256 > $OUT/stream_tmp.log 2>&1; echo "stream $nb graph=$g: $(tail -1 $OUT/stream_tmp.log)"
+  done
+done
 MARLPDE_B200_LIB=$B/lib_imm.so timeout 120 python scripts/profile_radau.py 16 0.05 > $OUT/radau_imm.log 2>&1; echo "radau imm: $(head -1 $OUT/radau_imm.log)"
 timeout 120 python scripts/profile_radau.py 16 0.05 > $OUT/radau_intree.log 2>&1; echo "radau in-tree: $(head -1 $OUT/radau_intree.log)"
 # -DMARLPDE_RADAU_FUSE_F=1: the three stage evaluations of a Newton iteration fused with B = TI F - M W (6 x 5N fewer doubles through DRAM)

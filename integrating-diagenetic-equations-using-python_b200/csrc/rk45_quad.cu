@@ -35,6 +35,9 @@ namespace quad {
 constexpr int TP = 256;   // threads per CTA
 constexpr int Q = 4;      // cells per thread
 constexpr int kWarps = TP / 32;
+#ifndef MARLPDE_QUAD_ROLLED
+#define MARLPDE_QUAD_ROLLED 0  // 1: one RHS instance in a rolled loop over the two pairs (A/B candidate: half the hot code)
+#endif
 #ifndef MARLPDE_QUAD_ORDER
 #define MARLPDE_QUAD_ORDER 0   // 1: own-cell parts of both pairs before the stage-barrier wait (A/B candidate)
 #endif
@@ -519,6 +522,72 @@ __global__ void __launch_bounds__(TP, 1) rk45_quad_kernel(const Args A) {
     double U[Q], W[Q];
 #pragma unroll 1
     for (int i = i0; i <= 6; ++i) {
+#if MARLPDE_QUAD_ROLLED
+      // ONE instance of the RHS in a rolled loop over the thread's two pairs (half the hot code of the two inlined instances;
+      // the pair's inputs and outputs change places in registers between the trips)
+      double cP[5][2], mloP[5], phiP[5], hpS[5], rP[5][2], UP[2], WP[2];
+      bool maskP[2] = {in_mask[0], in_mask[1]};
+#pragma unroll
+      for (int f = 0; f < 5; ++f) {
+        cP[f][0] = c[f][0];
+        cP[f][1] = c[f][1];
+        mloP[f] = phiP[f] = hpS[f] = 0.0;
+      }
+#pragma unroll 1
+      for (int p = 0; p < 2; ++p) {
+        OwnTerms own;
+        PairFlags fl = rhs_pair_own<rhs_schedule(kSchedLean)>(kc, tb, cP, maskP, own);
+        if (p == 0) {                              // the own-cell part of the first pair overlapped the pending barrier
+          if (i > i0) {
+            mbar_wait(sBar, bar_parity);
+            bar_parity ^= 1u;
+          }
+#pragma unroll
+          for (int f = 0; f < 5; ++f) {
+            double hm, hp;
+            halo_load(i & 1, f, hm, hp);
+            mloP[f] = first ? top_ghost(kc, f, c[f][0]) : hm;
+            phiP[f] = c[f][2];
+            hpS[f] = hp;
+          }
+        }
+        rhs_pair_finish(kc, cP, mloP, phiP, own, rP);
+        UP[0] = own.U[0];
+        UP[1] = own.U[1];
+        WP[0] = own.W[0];
+        WP[1] = own.W[1];
+        fl.bad[0] = fl.bad[0] && live;
+        fl.bad[1] = fl.bad[1] && live;
+        if (fl.bad[0] || fl.bad[1]) rhs_pair_fixup(kc, tb, fl, cP, mloP, phiP, maskP, rP, UP, WP);
+        if (p == 0) {
+#pragma unroll
+          for (int f = 0; f < 5; ++f) {
+            r[f][0] = rP[f][0];
+            r[f][1] = rP[f][1];
+            cP[f][0] = c[f][2];
+            cP[f][1] = c[f][3];
+            mloP[f] = c[f][1];
+            phiP[f] = last ? bottom_ghost(f, c[f][3], c[f][2]) : hpS[f];
+          }
+          U[0] = UP[0];
+          U[1] = UP[1];
+          W[0] = WP[0];
+          W[1] = WP[1];
+          maskP[0] = in_mask[2];
+          maskP[1] = in_mask[3];
+        } else {
+#pragma unroll
+          for (int f = 0; f < 5; ++f) {
+            r[f][2] = rP[f][0];
+            r[f][3] = rP[f][1];
+          }
+          U[2] = UP[0];
+          U[3] = UP[1];
+          W[2] = WP[0];
+          W[3] = WP[1];
+        }
+      }
+#else
       // own-cell part of the first pair while the barrier that publishes the warp-edge values is pending
       double cA[5][2], cB[5][2];
 #pragma unroll
@@ -586,6 +655,7 @@ __global__ void __launch_bounds__(TP, 1) rk45_quad_kernel(const Args A) {
       W[1] = WA[1];
       W[2] = WB[0];
       W[3] = WB[1];
+#endif
       if (live) switch (i) {
         case 0:
           if (fresh) {

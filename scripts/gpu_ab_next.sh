@@ -15,6 +15,7 @@ rk $IN intree_again
 MARLPDE_RK45_BUILD=450 timeout 60 python scripts/profile_rk45.py 300 5 > $OUT/rk45_quad.log 2>&1; echo "rk45 quad (no events): $(tail -2 $OUT/rk45_quad.log | tr '\n' ' ')"
 MARLPDE_RK45_BUILD=450 MARLPDE_PROFILE_EVENTS=1 timeout 60 python scripts/profile_rk45.py 300 5 > $OUT/rk45_quad_ev.log 2>&1; echo "rk45 quad: $(tail -2 $OUT/rk45_quad_ev.log | tr '\n' ' ')"
 MARLPDE_B200_LIB=$B/lib_quad_o1.so MARLPDE_RK45_BUILD=450 MARLPDE_PROFILE_EVENTS=1 timeout 60 python scripts/profile_rk45.py 300 5 > $OUT/rk45_quad_o1.log 2>&1; echo "rk45 quad, own parts of both pairs before the wait: $(tail -2 $OUT/rk45_quad_o1.log | tr '\n' ' ')"
+MARLPDE_B200_LIB=$B/lib_quad_rolled.so MARLPDE_RK45_BUILD=450 MARLPDE_PROFILE_EVENTS=1 timeout 60 python scripts/profile_rk45.py 300 5 > $OUT/rk45_quad_rolled.log 2>&1; echo "rk45 quad, one RHS instance in a rolled pair loop (half the hot code, spills): $(tail -2 $OUT/rk45_quad_rolled.log | tr '\n' ' ')"
 for m in 2 3; do   # other RHS instruction schedules under the 8-warp kernel (255 registers change what ptxas can overlap)
   MARLPDE_B200_LIB=$B/lib_m$m.so MARLPDE_RK45_BUILD=450 MARLPDE_PROFILE_EVENTS=1 timeout 60 python scripts/profile_rk45.py 300 5 > $OUT/rk45_quad_m$m.log 2>&1; echo "rk45 quad, RHS schedule $m: $(tail -1 $OUT/rk45_quad_m$m.log)"
 done

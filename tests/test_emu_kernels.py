@@ -48,6 +48,11 @@ def emu():
                     "-o", so_spread] + srcs, check=True, capture_output=True)
     lib_spread = C.CDLL(so_spread)
     lib_spread.emu_rk45.restype = C.c_int
+    so_rolled = os.path.join(out, "libemu_rk45_rolled.so")     # 4-cell kernel with one RHS instance in a rolled loop
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", "-DMARLPDE_QUAD_ROLLED=1", "-I", EMU,
+                    "-o", so_rolled] + srcs, check=True, capture_output=True)
+    lib_rolled = C.CDLL(so_rolled)
+    lib_rolled.emu_rk45.restype = C.c_int
 
     def run(variant, P, y, t_end, t_eval=(), events=False, first_step=1e-6, max_steps=0, state=None, capacity=16):
         y = np.ascontiguousarray(y, dtype=np.float64).copy()
@@ -61,7 +66,7 @@ def emu():
         o = _cabi.RK45Options(t_bound=t_end, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=max_steps,
                               n_eval=te.size, event_capacity=capacity, flags=_cabi.FLAG_EVENTS if events else 0, reserved=0)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
-        which = lib_spread if variant >= 2000 else lib_imm if variant >= 1000 else lib
+        which = lib_rolled if variant >= 3000 else lib_spread if variant >= 2000 else lib_imm if variant >= 1000 else lib
         rc = which.emu_rk45(variant % 1000, p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), p(ec), p(et))
         assert rc == 0, f"emulated kernel {variant}: rc {rc} (deadlock or mismatched collective, see stderr)"
         return dict(y=y, state=st, snapshots=snap, event_counts=ec, event_times=et)
@@ -150,6 +155,18 @@ def test_quad_kernel_resume_is_bit_identical_and_other_grids(emu):
         res = emu(450, np.repeat(mb.derive_column_params(p2), 3), np.repeat(mb.initial_state(p2), 3, 0), t_end, first_step=h0)
         assert np.all(res["state"]["nfev"] == sol.nfev), n_cells
         assert np.max(np.abs(res["y"][1] - sol.y.reshape(5, n_cells, -1)[:, :, -1])) <= 1e-12, n_cells
+
+
+def test_quad_kernel_rolled_pair_loop_is_bit_identical(emu):
+    """-DMARLPDE_QUAD_ROLLED=1 (A/B candidate): one RHS instance serves both pairs of a thread in a rolled loop (inputs and
+    outputs change places between the trips) — same bits as the two inlined instances, events and dense output included."""
+    pde = mb.sweep_lattice(oracle.default_scenario(), 2, 2, 2)
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    a = emu(450, P, y0, 1e-4, t_eval=[5e-5, 1e-4], events=True, first_step=5e-7)
+    b = emu(3450, P, y0, 1e-4, t_eval=[5e-5, 1e-4], events=True, first_step=5e-7)
+    assert np.all(a["state"]["status"] == 0) and a["state"]["n_rejected"].min() > 0
+    assert np.array_equal(a["state"], b["state"]) and np.array_equal(a["y"], b["y"])
+    assert np.array_equal(a["snapshots"], b["snapshots"]) and np.array_equal(a["event_counts"], b["event_counts"])
 
 
 def test_tail_spread_claim_policy_processes_every_column_with_identical_results(emu, monkeypatch):

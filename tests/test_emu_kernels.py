@@ -32,27 +32,20 @@ def emu():
         pytest.skip("g++ not available")
     out = os.path.join(EMU, "_build")
     os.makedirs(out, exist_ok=True)
-    so = os.path.join(out, "libemu_rk45.so")
     srcs = [os.path.join(EMU, f) for f in ("emu_rk45.cc", "simt_emu.cc")]
-    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", "-I", EMU, "-o", so] + srcs,
-                   check=True, capture_output=True)
-    lib = C.CDLL(so)
-    lib.emu_rk45.restype = C.c_int
-    so_imm = os.path.join(out, "libemu_rk45_imm.so")           # the experimental immediate-constant fp64 maths
-    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", "-DMARLPDE_FP64_IMM=1", "-I", EMU,
-                    "-o", so_imm] + srcs, check=True, capture_output=True)
-    lib_imm = C.CDLL(so_imm)
-    lib_imm.emu_rk45.restype = C.c_int
-    so_spread = os.path.join(out, "libemu_rk45_spread.so")     # the experimental claim policy (-DMARLPDE_TAIL_SPREAD=1)
-    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", "-DMARLPDE_TAIL_SPREAD=1", "-I", EMU,
-                    "-o", so_spread] + srcs, check=True, capture_output=True)
-    lib_spread = C.CDLL(so_spread)
-    lib_spread.emu_rk45.restype = C.c_int
-    so_rolled = os.path.join(out, "libemu_rk45_rolled.so")     # 4-cell kernel with one RHS instance in a rolled loop
-    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", "-DMARLPDE_QUAD_ROLLED=1", "-I", EMU,
-                    "-o", so_rolled] + srcs, check=True, capture_output=True)
-    lib_rolled = C.CDLL(so_rolled)
-    lib_rolled.emu_rk45.restype = C.c_int
+    # the default sources, and the experimental compile-time variants: immediate-constant fp64 maths, tail-spreading claim
+    # policy, 4-cell kernel with one RHS instance in a rolled pair loop (compiled side by side)
+    variants = {"": [], "_imm": ["-DMARLPDE_FP64_IMM=1"], "_spread": ["-DMARLPDE_TAIL_SPREAD=1"], "_rolled": ["-DMARLPDE_QUAD_ROLLED=1"]}
+    jobs = {k: subprocess.Popen(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", *flags, "-I", EMU, "-o",
+                                 os.path.join(out, f"libemu_rk45{k}.so")] + srcs, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+            for k, flags in variants.items()}
+    libs = {}
+    for k, job in jobs.items():
+        log = job.communicate()[0]
+        assert job.returncode == 0, log.decode()
+        libs[k] = C.CDLL(os.path.join(out, f"libemu_rk45{k}.so"))
+        libs[k].emu_rk45.restype = C.c_int
+    lib, lib_imm, lib_spread, lib_rolled = libs[""], libs["_imm"], libs["_spread"], libs["_rolled"]
 
     def run(variant, P, y, t_end, t_eval=(), events=False, first_step=1e-6, max_steps=0, state=None, capacity=16):
         y = np.ascontiguousarray(y, dtype=np.float64).copy()

@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B candidates prepared at the end of round 1 (not yet measured on a GPU).  Build the variant libraries first:
 #   bash scripts/build_ab_next.sh
-# then:  gpurun --timeout 400 -- bash scripts/gpu_ab_next.sh <tag>
+# then:  gpurun --timeout 1500 -- bash scripts/gpu_ab_next.sh <tag>      (~15 min of box time; every step has its own timeout)
 set -u
 OUT=gpurun_out/${1:-ab_next}; mkdir -p $OUT
 B=$PWD/build_ab

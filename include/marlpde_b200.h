@@ -92,10 +92,15 @@ typedef struct marlpde_rk45_options {
   int32_t n_eval;      /* number of t_eval points (may be 0)                           */
   int32_t event_capacity; /* slots per (column,event) in event_times (may be 0)       */
   int32_t flags;       /* MARLPDE_FLAG_*                                               */
-  int32_t reserved;
+  int32_t quantum;     /* on-chip RK45 only, with MARLPDE_FLAG_QUEUE_LOCKS and max_steps > 0: step attempts per
+                          work item; 0 = chosen by the library, < 0 = one item per column (no quanta)        */
 } marlpde_rk45_options;
 
 #define MARLPDE_FLAG_EVENTS 1u   /* monitor the 7 events and locate their roots */
+#define MARLPDE_FLAG_QUEUE_LOCKS 2u /* d_queue holds 1 + 2 n_columns zeroed int32 (work counter, one lock word and one
+                                    attempt counter per column): the on-chip RK45 kernel may then cut every column's step budget into
+                                    quanta claimed quantum-major, which shortens the partly filled last round of a
+                                    launch (results are unchanged: a resumed column is bit-identical)          */
 
 /* Per-column integrator state: input (start/resume point) and output (end point). */
 typedef struct marlpde_column_state {
@@ -148,7 +153,8 @@ int marlpde_rhs_batch(const double* y, const marlpde_column_params* params,
  *                                       scipy RkDenseOutput); rows >= state.next_eval are untouched
  *  d_event_counts[n_columns][7]         number of roots found per monitor (accumulated)
  *  d_event_times [n_columns][7][event_capacity]  root times (first event_capacity kept)
- *  d_queue    one int32 work counter, must be 0 on entry (the kernel claims columns from it)
+ *  d_queue    int32 work counter, must be 0 on entry (the kernel claims columns from it); with
+ *             MARLPDE_FLAG_QUEUE_LOCKS: 1 + 2 n_columns int32, all 0 on entry
  */
 int marlpde_rk45_integrate_dev(double* d_y, const marlpde_column_params* d_params,
                                marlpde_column_state* d_state, int n_columns, int n_cells,

@@ -347,7 +347,8 @@ int marlpde_rk45_integrate(double* y, const marlpde_column_params* params, marlp
   CU(ds.alloc(sizeof(marlpde_column_state) * (size_t)n_columns));
   CU(dte.alloc(sizeof(double) * (size_t)opts->n_eval));
   CU(dsnap.alloc(nb_snap));
-  CU(dq.alloc(sizeof(int32_t)));
+  const size_t nb_q = sizeof(int32_t) * (1 + 2 * (size_t)n_columns);   // work counter + lock word and attempt counter per column
+  CU(dq.alloc(nb_q));
   CU(dec.alloc(nb_ec));
   CU(det.alloc(nb_et));
   trace.mark("alloc");
@@ -356,12 +357,14 @@ int marlpde_rk45_integrate(double* y, const marlpde_column_params* params, marlp
   CU(cudaMemcpy(ds.p, state, sizeof(marlpde_column_state) * (size_t)n_columns, cudaMemcpyHostToDevice));
   if (opts->n_eval) CU(cudaMemcpy(dte.p, t_eval, sizeof(double) * (size_t)opts->n_eval, cudaMemcpyHostToDevice));
   if (snapshots && nb_snap) CU(cudaMemcpy(dsnap.p, snapshots, nb_snap, cudaMemcpyHostToDevice));
-  CU(cudaMemset(dq.p, 0, sizeof(int32_t)));
+  CU(cudaMemset(dq.p, 0, nb_q));
   if (event_counts) CU(cudaMemcpy(dec.p, event_counts, nb_ec, cudaMemcpyHostToDevice));
   else CU(cudaMemset(dec.p, 0, nb_ec));
   if (event_times && nb_et) CU(cudaMemcpy(det.p, event_times, nb_et, cudaMemcpyHostToDevice));
+  marlpde_rk45_options o = *opts;
+  o.flags |= MARLPDE_FLAG_QUEUE_LOCKS;
   rc = marlpde_rk45_integrate_dev(dy.as<double>(), dp.as<marlpde_column_params>(), ds.as<marlpde_column_state>(),
-                                  n_columns, n_cells, opts, dte.as<double>(), dsnap.as<double>(),
+                                  n_columns, n_cells, &o, dte.as<double>(), dsnap.as<double>(),
                                   dec.as<int32_t>(), det.as<double>(), dq.as<int32_t>(), nullptr);
   if (rc) return rc;
   trace.mark("h2d+launch");

@@ -27,8 +27,10 @@
 //     different step counts do not leave SMs idle.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 
 #include "brent.cuh"
 #include "dopri.cuh"
@@ -43,8 +45,11 @@ namespace marlpde {
 // ---- shared memory carve-up -------------------------------------------------------------
 // K[4][5][TP] double2 | tileE[2][5][TP] | tileO[2][5][TP] | grp[TP] | log/exp tables |
 // consts[C] | ctl[C] | slot_col[C] | svc flag
-struct SlotCtl {          // per-slot counters, touched by the slot's leader thread only
+struct SlotCtl {          // per-slot counters, written by the slot's leader thread only
   long long n_acc, n_rej, nfev;
+  long long budget;       // the claim ends at the first accepted step with this many attempts (0: unlimited) ...
+  long long used;         // ... counted from here (attempts of earlier claims on the column in this launch);
+                          // both read by the whole slot after the claim barrier
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) / 16 * 16; }
@@ -94,7 +99,7 @@ static int rk45_variant() {
   if (v < 0) {
     const char* s = std::getenv("MARLPDE_RK45_BUILD");
     const int want = s ? std::atoi(s) : 0;
-    v = (want == 321 || want == 416 || want == 450) ? want : 320;
+    v = (want == 128 || want == 129 || want == 321 || want == 416 || want == 450) ? want : 320;
   }
   return v;
 }
@@ -103,10 +108,13 @@ int rk45_columns_per_cta(int n_cells, int smem_budget) {
   if (rk45_variant() == 450 && rk45_quad_columns_per_cta(n_cells, smem_budget) > 0)
     return rk45_quad_columns_per_cta(n_cells, smem_budget);
   switch (rk45_variant()) {
+    case 128: if (n_cells <= 256) return columns_per_cta_t<128, false, false>(n_cells, smem_budget / 3 - 1024); break;
+    case 129: if (n_cells <= 256) return columns_per_cta_t<128, true, false>(n_cells, smem_budget / 3 - 1024); break;
     case 321: return columns_per_cta_t<320, true, false>(n_cells, smem_budget);
     case 416: return columns_per_cta_t<416, true, true>(n_cells, smem_budget);
-    default: return columns_per_cta_t<320, false, false>(n_cells, smem_budget);
+    default: break;
   }
+  return columns_per_cta_t<320, false, false>(n_cells, smem_budget);
 }
 
 int rk45_max_cells() { return 640; }   // (the 416 build would take 832; the ABI reports the default build)
@@ -185,12 +193,14 @@ struct Rk45Args {
   int32_t* g_ev_counts;      // [n_columns][7]
   double* g_ev_times;        // [n_columns][7][event_capacity]
   int n_columns, N, C, logG;
+  int n_quanta;                   // work items per column (1: a claim covers the column's whole step budget)
+  long long quantum;              // step attempts per work item when n_quanta > 1
   unsigned long long warp_perm;   // logical warp of physical warp w = (warp_perm >> 4 w) & 15 (see rk45_warp_perm)
   marlpde_rk45_options opt;
 };
 
 template <int TP, bool YS, bool HS>
-__global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel(const Rk45Args A) {
+__global__ void __launch_bounds__((TP + 31) / 32 * 32, TP <= 128 ? 3 : 1) rk45_persistent_kernel(const Rk45Args A) {
   MARLPDE_DYN_SMEM(smem_raw);
   using L = Smem<TP, YS, HS>;
   // Logical thread index.  Physical warps can be dealt out to the column ranges in any order; the order decides WHICH
@@ -298,6 +308,9 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
   double t = 0.0, h_abs = 0.0, h = 0.0, t_new = 0.0;
   int next_eval = 0;
   int attempts = 0;             // step attempts made for this column in this launch
+  long long budget = 0;         // the current claim ends at the first accepted step with attempts >= budget (0: unlimited)
+  int pending_item = -1;        // leader: work item whose column was busy at the last claim
+  int release_col = -1;         // leader: column to unlock once the slot's stores have passed a block barrier
   bool in_mask[2] = {false, false};
   double y[5][2], k1[5][2], c[5][2], r[5][2];
 #pragma unroll
@@ -395,6 +408,10 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
       st.status = status;
       st.next_eval = next_eval;
       A.g_state[col] = st;
+      if (A.n_quanta > 1) {
+        A.g_queue[1 + A.n_columns + col] = attempts;
+        release_col = col;
+      }
     }
     col = -1;
 #pragma unroll
@@ -461,7 +478,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
     if (leader) ctl.n_acc += 1;
     if (t >= A.opt.t_bound) {
       retire(MARLPDE_STATUS_FINISHED);
-    } else if (A.opt.max_steps > 0 && (long long)attempts >= A.opt.max_steps) {
+    } else if (budget > 0 && (long long)attempts >= budget) {
       retire(MARLPDE_STATUS_STEP_BUDGET);
     } else {
       begin_step();
@@ -510,28 +527,71 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
     if (col >= 0 && !parked) stage2_input();
     if (leader && col < 0 && !exhausted) atomicOr(sSvc, 1);
     int nlive = __syncthreads_count(col >= 0);
+    auto release = [&]() {      // the barrier above ordered the slot's y / state stores before this thread
+      if (release_col >= 0) {
+        __threadfence();
+        atomicExch(A.g_queue + 1 + release_col, 0);
+        release_col = -1;
+      }
+    };
+    release();
     int i0 = 1;
     const int svc = *sSvc;
     if (svc) {
       // -- claim columns for idle slots
       if (leader && col < 0 && !exhausted) {
-#if MARLPDE_TAIL_SPREAD   // slot s only claims while more than s columns per CTA are left: the tail of a sweep (and a
-                          // batch smaller than the machine) is spread one column per SM instead of stacked on a few
-        const int left = A.n_columns - *reinterpret_cast<volatile int32_t*>(A.g_queue);
-        const int cc = (slot > 0 && left <= slot * (int)gridDim.x) ? A.n_columns : atomicAdd(A.g_queue, 1);
-#else
-        const int cc = atomicAdd(A.g_queue, 1);
-#endif
-        sSlotCol[slot] = cc < A.n_columns ? cc : -1;
+        // Work items: item = quantum * n_columns + column (quantum-major), each "advance this column by up to
+        // `quantum` step attempts from its stored state".  With n_quanta == 1 an item is a whole column (the
+        // classic queue).  Items of one column may be claimed by different CTAs at about the same time, so a
+        // column is guarded by a lock word (g_queue[1 + column]); which item runs first does not matter, they
+        // are interchangeable.  A slot that finds its column busy keeps the item and tries again at the next
+        // service (the holder is resident and running, so it will release).
+        int item = pending_item >= 0 ? pending_item : atomicAdd(A.g_queue, 1);
+        pending_item = -1;
+        int cc = -1;
+        if (item < A.n_columns * A.n_quanta) {
+          const int q = item / A.n_columns;
+          cc = item - q * A.n_columns;
+          long long budget = A.opt.max_steps > 0 ? A.opt.max_steps : 0;
+          long long used = 0;
+          if (A.n_quanta > 1) {
+            if (atomicCAS(A.g_queue + 1 + cc, 0, 1) != 0) {
+              pending_item = item;
+              cc = -2;
+            } else {
+              __threadfence();       // acquire: the previous holder's y / state / counter stores are visible from here on
+              // attempts this column has used in this launch so far; the claim runs to the next multiple of the
+              // quantum (an attempt budget ends at the first ACCEPTED step at or beyond it, so claims may overrun and
+              // later items of the column may find nothing left to do)
+              used = __ldcg(A.g_queue + 1 + A.n_columns + cc);
+              const long long target = (used / A.quantum + 1) * A.quantum;
+              budget = target < A.opt.max_steps ? target : A.opt.max_steps;
+            }
+          }
+          ctl.budget = budget;
+          ctl.used = used;
+        }
+        sSlotCol[slot] = cc;
       }
       __syncthreads();
       if (tid == 0) *sSvc = 0;
       if (active && col < 0 && !exhausted) {
         col = sSlotCol[slot];
-        if (col < 0) {
+        if (col == -2) {
+          col = -1;                  // column busy elsewhere: stay idle, the leader retries
+        } else if (col < 0) {
           exhausted = true;
         } else {
-          const marlpde_column_state st = A.g_state[col];
+          budget = ctl.budget;
+          // (L2 loads: another SM may have written this column's state and y a moment ago)
+          marlpde_column_state st;
+          {
+            const double* sp = reinterpret_cast<const double*>(A.g_state + col);
+            double w[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) w[i] = __ldcg(sp + i);
+            memcpy(&st, w, sizeof(st));
+          }
           if (leader) {
             ColumnConsts tmp;
             make_consts(A.g_params[col], N, tmp);
@@ -545,20 +605,22 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
           const int mlo_ = A.g_params[col].mask_lo, mhi_ = A.g_params[col].mask_hi;
           in_mask[0] = cell0 >= mlo_ && cell0 < mhi_;
           in_mask[1] = cell0 + 1 >= mlo_ && cell0 + 1 < mhi_;
-          attempts = 0;
+          attempts = (int)ctl.used;
           t = st.t;
           h_abs = st.h_abs;
           next_eval = st.next_eval;
           const double* gy = A.g_y + (size_t)col * 5 * N + cell0;
 #pragma unroll
           for (int f = 0; f < 5; ++f) {
-            c[f][0] = gy[(size_t)f * N];
-            c[f][1] = has1 ? gy[(size_t)f * N + 1] : 0.0;
+            c[f][0] = __ldcg(gy + (size_t)f * N);
+            c[f][1] = has1 ? __ldcg(gy + (size_t)f * N + 1) : 0.0;
             Yst(f, c[f][0], c[f][1]);
           }
           tile_store(0);
           if (t >= A.opt.t_bound) {            // nothing to integrate
             retire(MARLPDE_STATUS_FINISHED);
+          } else if (budget > 0 && (long long)attempts >= budget) {   // earlier claims used the column's whole budget
+            retire(st.status);
           } else {
             begin_step();
             if (begin_attempt()) fresh = true;
@@ -620,6 +682,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
         }
       }
       nlive = __syncthreads_count(col >= 0);   // also publishes consts and tile 0 of the new columns
+      release();
       if (nlive == 0) continue;                // everything claimed retired at once: look again
       i0 = 0;
     }
@@ -857,6 +920,45 @@ static unsigned long long rk45_warp_perm(int n_warps) {
   return p;
 }
 
+// Work items per column.  A launch whose columns all get the same step budget (a sweep advanced in steps, bench.py)
+// runs ceil(columns / slots) rounds and the last round is only partly filled: 4096 columns on 444 slots are 9.22
+// rounds of work in 10 rounds of time.  Cutting the budget into quanta that are claimed quantum-major makes the
+// partly filled round 1 / n_quanta as long.  Needs the per-column lock and counter words (MARLPDE_FLAG_QUEUE_LOCKS)
+// and a finite budget; opt.quantum > 0 fixes the quantum, < 0 switches it off.  The end point of a column does not
+// depend on the quanta: it is the first accepted step at which the launch's attempts reach max_steps, as without them.
+static void choose_quanta(Rk45Args& a, int slots) {
+  a.n_quanta = 1;
+  a.quantum = 0;
+  if (!(a.opt.flags & MARLPDE_FLAG_QUEUE_LOCKS) || a.opt.max_steps <= 0 || a.opt.quantum < 0) return;
+  const long long budget = a.opt.max_steps;
+  if (a.opt.quantum > 0) {
+    a.quantum = a.opt.quantum;
+    a.n_quanta = (int)((budget + a.quantum - 1) / a.quantum);
+  } else {
+    if (a.n_columns <= slots) return;          // every column has its own slot anyway
+    double best = 1e300;
+    for (int nq = 1; nq <= 32; ++nq) {
+      const long long q = (budget + nq - 1) / nq;
+      if (nq > 1 && q < 64) break;
+      const double items = (double)a.n_columns * nq, rounds = items / slots;
+      const double cost = std::ceil(rounds) / rounds + 0.5 / (double)q;   // idle tail + ~half an attempt per claim
+      if (cost < best - 1e-9) {
+        best = cost;
+        a.n_quanta = nq;
+        a.quantum = q;
+      }
+    }
+  }
+  if ((long long)a.n_columns * a.n_quanta > 0x7fffffffLL) {
+    a.n_quanta = 1;
+    a.quantum = 0;
+  }
+  if (a.n_quanta <= 1) {
+    a.n_quanta = 1;
+    a.quantum = 0;
+  }
+}
+
 #ifndef MARLPDE_HOST_EMU
 template <int TP, bool YS, bool HS>
 static cudaError_t launch_t(const Rk45Args& a, int sm_count, int smem_budget, cudaStream_t stream) {
@@ -869,9 +971,16 @@ static cudaError_t launch_t(const Rk45Args& a, int sm_count, int smem_budget, cu
   cudaError_t e = cudaFuncSetAttribute(rk45_persistent_kernel<TP, YS, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int grid = MARLPDE_TAIL_SPREAD ? a.n_columns : (a.n_columns + args.C - 1) / args.C;
-  if (grid > sm_count) grid = sm_count;
+  int per_sm = 1;
+  if (TP <= 128) {   // small CTAs: as many as fit side by side on an SM (registers: 3 at 168 per thread)
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rk45_persistent_kernel<TP, YS, HS>, ((args.C * Hc + 31) / 32) * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+  }
+  if (grid > sm_count * per_sm) grid = sm_count * per_sm;
   if (grid < 1) grid = 1;
   const int threads = ((args.C * Hc + 31) / 32) * 32;
+  choose_quanta(args, grid * args.C);
   args.warp_perm = rk45_warp_perm(threads / 32);
   rk45_persistent_kernel<TP, YS, HS><<<grid, threads, smem, stream>>>(args);
   return cudaGetLastError();
@@ -894,16 +1003,21 @@ cudaError_t launch_rk45(double* d_y, const marlpde_column_params* d_params, marl
   a.N = n_cells;
   a.C = 0;
   a.logG = 0;
+  a.n_quanta = 1;
+  a.quantum = 0;
   a.warp_perm = 0;
   a.opt = opt;
   if (rk45_variant() == 450 && rk45_quad_columns_per_cta(n_cells, smem_budget) > 0)
     return launch_rk45_quad(d_y, d_params, d_state, n_columns, n_cells, opt, d_t_eval, d_snap, d_ev_counts, d_ev_times,
                             d_queue, sm_count, smem_budget, stream);
   switch (rk45_variant()) {
+    case 128: if (n_cells <= 256) return launch_t<128, false, false>(a, sm_count, smem_budget / 3 - 1024, stream); break;
+    case 129: if (n_cells <= 256) return launch_t<128, true, false>(a, sm_count, smem_budget / 3 - 1024, stream); break;
     case 321: return launch_t<320, true, false>(a, sm_count, smem_budget, stream);
     case 416: return launch_t<416, true, true>(a, sm_count, smem_budget, stream);
-    default: return launch_t<320, false, false>(a, sm_count, smem_budget, stream);
+    default: break;
   }
+  return launch_t<320, false, false>(a, sm_count, smem_budget, stream);
 }
 
 #endif

@@ -177,6 +177,9 @@ def integrate_equations(solver_parms, tracker_parms, pde_parms):
     covered_time = tstar * end_time if sol.status == 0 else progress * tstar * end_time
 
     store_folder = "../Results/" + datetime.now().strftime("%d_%m_%Y_%H_%M_%S" + "/")
+    while os.path.exists(store_folder):        # upstream's names have a one-second resolution (:157-159) and it needs
+        time.sleep(0.1)                        # >= 0.2 s per run; a column takes ~30 ms here, so two runs can collide
+        store_folder = "../Results/" + datetime.now().strftime("%d_%m_%Y_%H_%M_%S" + "/")
     stored_parms = solver_parms | tracker_parms | pde_parms
     stored_parms.pop("jac_sparsity", None)     # not storable as HDF5 metadata
     field_solutions = sol.y.reshape(5, n_cells, sol.y.shape[-1])

@@ -17,6 +17,7 @@ NFIELDS = 5
 NEVENTS = 7
 STATUS_FINISHED, STATUS_STEP_TOO_SMALL, STATUS_NONFINITE, STATUS_STEP_BUDGET = 0, -1, -2, 1
 FLAG_EVENTS = 1
+FLAG_QUEUE_LOCKS = 2
 
 
 class ColumnParams(C.Structure):
@@ -33,7 +34,7 @@ class ColumnParams(C.Structure):
 class RK45Options(C.Structure):
     _fields_ = [("t_bound", C.c_double), ("rtol", C.c_double), ("atol", C.c_double),
                 ("max_step", C.c_double), ("max_steps", C.c_int64), ("n_eval", C.c_int32),
-                ("event_capacity", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32)]
+                ("event_capacity", C.c_int32), ("flags", C.c_int32), ("quantum", C.c_int32)]
 
 
 class ColumnState(C.Structure):

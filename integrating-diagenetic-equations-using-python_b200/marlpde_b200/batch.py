@@ -111,14 +111,15 @@ def make_state(n_columns: int, t0=0.0, first_step=1e-6) -> np.ndarray:
 def integrate_rk45_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e-3, atol=1e-3,
                          t_eval=None, max_step=np.inf, max_steps: int = 0, events: bool = False,
                          event_capacity: int = 0, state: np.ndarray | None = None,
-                         device: int = 0, inplace: bool = False) -> RK45Result:
+                         device: int = 0, inplace: bool = False, quantum: int = 0) -> RK45Result:
     """Adaptive Dormand-Prince RK45 for every column, SciPy `solve_ivp(method="RK45")` semantics
     per column (call site marlpde/Evolve_scenario.py:104-109).
 
     `first_step` follows SciPy's rule (validate_first_step): it is used verbatim and must be
     positive and not exceed the interval.  `max_steps` > 0 bounds the step attempts per column in
     this call; columns that hit it come back with status 1 and can be resumed by passing the
-    returned `.state` and `.y` back in.
+    returned `.state` and `.y` back in.  `quantum` (on-chip kernel, `max_steps` > 0 only): step attempts per work
+    item of the kernel's queue; 0 lets the library choose, a negative value claims whole columns.
     """
     lib = _cabi.lib()
     t0, t_bound = float(t_span[0]), float(t_span[1])
@@ -142,7 +143,7 @@ def integrate_rk45_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e
     cap = int(event_capacity) if events else 0
     opts = _cabi.RK45Options(t_bound=t_bound, rtol=float(rtol), atol=float(atol), max_step=float(max_step),
                              max_steps=int(max_steps), n_eval=n_eval, event_capacity=cap,
-                             flags=_cabi.FLAG_EVENTS if events else 0, reserved=0)
+                             flags=(_cabi.FLAG_EVENTS if events else 0) | _cabi.FLAG_QUEUE_LOCKS, quantum=int(quantum))
 
     if _is_torch(y0):
         import torch
@@ -161,7 +162,7 @@ def integrate_rk45_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e
             d_state = torch.from_numpy(st.view(np.uint8).copy()).to(dev)
             d_te = torch.from_numpy(t_eval_arr.copy()).to(dev) if n_eval else None
             d_snap = torch.empty((B, n_eval, 5, N), dtype=torch.float64, device=dev)
-            d_queue = torch.zeros(1, dtype=torch.int32, device=dev)
+            d_queue = torch.zeros(1 + 2 * B, dtype=torch.int32, device=dev)   # work counter + lock word and attempt counter per column
             d_ec = torch.zeros((B, NEVENTS), dtype=torch.int32, device=dev)
             d_et = torch.full((B, NEVENTS, max(cap, 1)), float("nan"), dtype=torch.float64, device=dev)
             stream = torch.cuda.current_stream().cuda_stream
@@ -210,7 +211,7 @@ def _stream_rk45_device(lib, y, d_params, st, opts, t_eval_arr, B, N, dev, cap, 
         while True:
             o = _cabi.RK45Options(t_bound=opts.t_bound, rtol=opts.rtol, atol=opts.atol, max_step=opts.max_step,
                                   max_steps=min(batch, budget - used) if budget > 0 else batch, n_eval=n_eval,
-                                  event_capacity=opts.event_capacity, flags=opts.flags, reserved=0)
+                                  event_capacity=opts.event_capacity, flags=opts.flags, quantum=0)
             _cabi.check(lib.marlpde_rk45_stream_integrate_dev(
                 y.data_ptr(), d_params.data_ptr(), d_state.data_ptr(), B, N, C.byref(o),
                 d_te.data_ptr() if n_eval else None, d_snap.data_ptr(), d_work.data_ptr(), nb, stream))
@@ -282,7 +283,7 @@ def integrate_radau_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1
     cap = int(event_capacity) if events else 0
     opts = _cabi.RK45Options(t_bound=t_bound, rtol=float(rtol), atol=float(atol), max_step=float(max_step),
                              max_steps=int(max_steps), n_eval=n_eval, event_capacity=cap,
-                             flags=_cabi.FLAG_EVENTS if events else 0, reserved=0)
+                             flags=_cabi.FLAG_EVENTS if events else 0, quantum=0)
     if _is_torch(y0):
         import torch
         if not y0.is_cuda or y0.dtype != torch.float64 or not y0.is_contiguous():

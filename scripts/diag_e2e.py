@@ -14,7 +14,7 @@ hy = torch.from_numpy(y0.copy()).pin_memory().numpy(); hp = torch.from_numpy(P.v
 hs = torch.from_numpy(batch.make_state(B, 0.0, 1e-6).view(np.uint8).copy()).pin_memory().numpy()
 hec = torch.zeros((B, 7), dtype=torch.int32).pin_memory().numpy(); het = torch.full((B, 7, 16), float("nan"), dtype=torch.float64).pin_memory().numpy()
 for steps in (1, 1, 300, 3000, 3000):
-    o = _cabi.RK45Options(t_bound=1.0, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=steps, n_eval=0, event_capacity=16, flags=1, reserved=0)
+    o = _cabi.RK45Options(t_bound=1.0, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=steps, n_eval=0, event_capacity=16, flags=1, quantum=0)
     t0 = time.perf_counter()
     _cabi.check(lib.marlpde_rk45_integrate(hy.ctypes.data, hp.ctypes.data, hs.ctypes.data, B, N, C.byref(o), None, None, hec.ctypes.data, het.ctypes.data, 0))
     print(f"host call, {steps} attempts/column: {1e3*(time.perf_counter()-t0):.1f} ms")

@@ -24,7 +24,8 @@ state, y = r.state, r.y
 ev = bool(int(os.environ.get("MARLPDE_PROFILE_EVENTS", "0")))
 for i in range(launches):
     torch.cuda.synchronize(); t0 = time.time()
-    r = mb.integrate_rk45_batch(y, dP, t_span=(0, 1), max_steps=attempts, state=state, events=ev, event_capacity=16)
+    r = mb.integrate_rk45_batch(y, dP, t_span=(0, 1), max_steps=attempts, state=state, events=ev, event_capacity=16,
+                                quantum=int(os.environ.get("MARLPDE_PROFILE_QUANTUM", "0")))
     torch.cuda.synchronize(); dt = time.time() - t0
     att = int(r.n_attempts.sum() - (state["n_accepted"].sum() + state["n_rejected"].sum()))
     print(f"launch {i}: {att} attempts in {dt*1e3:.1f} ms -> {att/dt:.3e} col-steps/s")

@@ -19,7 +19,7 @@ st = torch.from_numpy(batch.make_state(B, 0.0, 1e-6 * (200 / N) ** 2).view(np.ui
 lib = _cabi.lib()
 nb = int(lib.marlpde_rk45_stream_workspace_bytes(B, N))
 w = torch.empty(nb // 8 + 1, dtype=torch.float64, device="cuda")
-o = _cabi.RK45Options(t_bound=1.0, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=att, n_eval=0, event_capacity=0, flags=0, reserved=0)
+o = _cabi.RK45Options(t_bound=1.0, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=att, n_eval=0, event_capacity=0, flags=0, quantum=0)
 stream = torch.cuda.current_stream().cuda_stream
 for i in range(3):
     torch.cuda.synchronize(); t0 = time.time()

@@ -90,3 +90,7 @@ inline int __syncthreads_or(int p) { return simt::block_barrier(p != 0, 2); }
 template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
 inline int atomicOr(int* p, int v) { int o = *p; *p = o | v; return o; }
+template <class T> inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
+template <class T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
+inline void __threadfence() {}
+template <class T> inline T __ldcg(const T* p) { return *p; }

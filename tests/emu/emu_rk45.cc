@@ -14,7 +14,8 @@ extern "C" int emu_rk45(int variant, double* y, const marlpde_column_params* par
                         int n_columns, int n_cells, const marlpde_rk45_options* opt, const double* t_eval, double* snap,
                         int32_t* ev_counts, double* ev_times) {
   using namespace marlpde;
-  int32_t queue = 0;
+  std::vector<int32_t> queue_words(1 + 2 * (size_t)(n_columns > 0 ? n_columns : 0), 0);   // counter + lock words + attempt counters
+  int32_t& queue = queue_words[0];
   const int budget = 227 * 1024;
   // EMU_GRID blocks, one after the other, on the same column queue (the claim policy sees gridDim.x = EMU_GRID)
   const char* ge = std::getenv("EMU_GRID");
@@ -56,6 +57,11 @@ extern "C" int emu_rk45(int variant, double* y, const marlpde_column_params* par
   a.logG = group_log2(Hc);
   a.warp_perm = ~0ull;
   a.opt = *opt;
+  a.n_quanta = 1;
+  a.quantum = 0;
+  // EMU_SLOTS: pretend the launch has this many resident slots when the library chooses the quanta itself
+  const char* se = std::getenv("EMU_SLOTS");
+  choose_quanta(a, se && std::atoi(se) > 0 ? std::atoi(se) : grid * a.C);
   const int threads = ((a.C * Hc + 31) / 32) * 32;
   for (int b = 0; b < grid; ++b)
     if (int rc = simt::run_block(threads, Smem<320, false, false>::total(a.C),

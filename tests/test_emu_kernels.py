@@ -47,7 +47,8 @@ def emu():
         libs[k].emu_rk45.restype = C.c_int
     lib, lib_imm, lib_spread, lib_rolled = libs[""], libs["_imm"], libs["_spread"], libs["_rolled"]
 
-    def run(variant, P, y, t_end, t_eval=(), events=False, first_step=1e-6, max_steps=0, state=None, capacity=16):
+    def run(variant, P, y, t_end, t_eval=(), events=False, first_step=1e-6, max_steps=0, state=None, capacity=16,
+            quantum=None):
         y = np.ascontiguousarray(y, dtype=np.float64).copy()
         P = np.ascontiguousarray(P)
         B, _, N = y.shape
@@ -57,7 +58,9 @@ def emu():
         ec = np.zeros((B, 7), np.int32)
         et = np.full((B, 7, capacity), np.nan)
         o = _cabi.RK45Options(t_bound=t_end, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=max_steps,
-                              n_eval=te.size, event_capacity=capacity, flags=_cabi.FLAG_EVENTS if events else 0, reserved=0)
+                              n_eval=te.size, event_capacity=capacity,
+                              flags=(_cabi.FLAG_EVENTS if events else 0) | (0 if quantum is None else _cabi.FLAG_QUEUE_LOCKS),
+                              quantum=quantum or 0)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         which = lib_rolled if variant >= 3000 else lib_spread if variant >= 2000 else lib_imm if variant >= 1000 else lib
         rc = which.emu_rk45(variant % 1000, p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), p(ec), p(et))
@@ -77,6 +80,37 @@ def test_default_kernel_under_emulation_reproduces_scipy(emu):
         res = emu(variant, mb.derive_column_params(pde), mb.initial_state(pde), 2e-4)
         assert res["state"]["status"][0] == 0 and res["state"]["nfev"][0] == sol.nfev, variant
         assert np.max(np.abs(res["y"][0] - sol.y.reshape(5, 200, -1)[:, :, -1])) <= 1e-12, variant
+
+
+def test_quantum_major_work_items_are_bit_identical_to_whole_column_claims(emu, monkeypatch):
+    """MARLPDE_FLAG_QUEUE_LOCKS: a column's step budget cut into quanta that are claimed quantum-major (the partly filled last
+    round of a launch becomes 1 / n_quanta as long).  A quantum ends like a step budget and the next one resumes from the
+    stored state, so the result must equal the whole-column claim bit for bit: 8 columns on 3 slots (every slot switches column
+    at every quantum), 2 columns on 3 slots (a slot finds its column locked by another slot and retries), t_eval samples
+    and events across quantum boundaries, a quantum that does not divide the budget, and the library's own choice."""
+    pde = mb.sweep_lattice(oracle.default_scenario() | SCEN_A, 2, 2, 2)
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    te = [1e-4, 2.5e-4]
+    whole = emu(320, P, y0, 1.0, t_eval=te, events=True, max_steps=100)
+    for q in (7, 25, 100, 1000):
+        part = emu(320, P, y0, 1.0, t_eval=te, events=True, max_steps=100, quantum=q)
+        assert np.array_equal(part["y"], whole["y"]), q
+        for k in ("t", "h_abs", "n_accepted", "n_rejected", "status", "next_eval"):
+            assert np.array_equal(part["state"][k], whole["state"][k]), (q, k)
+        # one extra K1 evaluation per resumed quantum, nothing else
+        extra = part["state"]["nfev"] - whole["state"]["nfev"]
+        assert np.all(extra == (100 + q - 1) // q - 1), (q, extra)
+        assert np.array_equal(part["snapshots"], whole["snapshots"], equal_nan=True)
+        assert np.array_equal(part["event_counts"], whole["event_counts"])
+    two = emu(320, P[:2], y0[:2], 1.0, max_steps=60, quantum=9)
+    ref = emu(320, P[:2], y0[:2], 1.0, max_steps=60)
+    assert np.array_equal(two["y"], ref["y"]) and np.array_equal(two["state"]["t"], ref["state"]["t"])
+    monkeypatch.setenv("EMU_SLOTS", "3")           # 8 columns on 3 slots: 2.67 rounds -> the library picks several quanta
+    auto = emu(320, P, y0, 1.0, max_steps=640, quantum=0)
+    ref = emu(320, P, y0, 1.0, max_steps=640)
+    assert np.array_equal(auto["y"], ref["y"])
+    assert np.all(auto["state"]["nfev"] > ref["state"]["nfev"])    # it did cut the budget
+    assert np.array_equal(auto["state"]["n_accepted"], ref["state"]["n_accepted"])
 
 
 def test_quad_kernel_lattice_dense_output_and_slot_reuse(emu):
@@ -206,7 +240,7 @@ def emu_radau():
         snap = np.full((B, max(1, te.size), 5, N), np.nan)
         ec, et, stats = np.zeros((B, 7), np.int32), np.full((B, 7, 16), np.nan), np.zeros((B, 4), np.int64)
         o = _cabi.RK45Options(t_bound=t_end, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=0, n_eval=te.size,
-                              event_capacity=16, flags=_cabi.FLAG_EVENTS if events else 0, reserved=0)
+                              event_capacity=16, flags=_cabi.FLAG_EVENTS if events else 0, quantum=0)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         rc = libs[fuse].emu_radau(p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), p(stats), p(ec), p(et))
         assert rc == 0, f"emulated Radau kernel (fuse={fuse}): rc {rc}"
@@ -270,7 +304,7 @@ def emu_stream():
         te = np.asarray(t_eval, dtype=np.float64)
         snap = np.full((B, max(1, te.size), 5, N), np.nan)
         o = _cabi.RK45Options(t_bound=t_end, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=attempts,
-                              n_eval=te.size, event_capacity=0, flags=0, reserved=0)
+                              n_eval=te.size, event_capacity=0, flags=0, quantum=0)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         rc = lib.emu_rk45_stream(p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), C.c_longlong(attempts))
         assert rc == 0, f"emulated streaming launcher: rc {rc}"

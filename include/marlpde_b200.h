@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MARLPDE_ABI_VERSION 1
+#define MARLPDE_ABI_VERSION 2
 #define MARLPDE_NFIELDS 5
 #define MARLPDE_NEVENTS 7
 
@@ -80,8 +80,16 @@ typedef struct marlpde_column_params {
   double dPhi_fixed, Peclet_min, Peclet_max;
   int32_t FV_switch;
   int32_t mask_lo, mask_hi;
-  int32_t reserved;
+  int32_t model_flags; /* MARLPDE_MODEL_*: model variants the reference toggles by editing its source        */
+  double auxcon;      /* beta / (D0Ca b g rhow (PhiNR - PhiInfty)) (:65-66); read only with MARLPDE_MODEL_VAR_DPHI */
 } marlpde_column_params;
+
+/* model_flags bit 0: time-varying porosity diffusion coefficient dPhi = auxcon F Phi^3 / (1 - Phi) per cell — the line
+ * the reference keeps commented out at LHeureux_model.py:222-223 and :430-431 — instead of dPhi_fixed.  It enters the
+ * porosity Peclet number (:239, :452) and dPhi * laplace(Phi) (:285, :519).  Integrations of batches that contain such
+ * columns must also set MARLPDE_FLAG_VAR_DPHI in marlpde_rk45_options.flags (it selects the kernel build; without it
+ * the per-column flag is ignored).  marlpde_rhs_batch* looks at the per-column flag by itself. */
+#define MARLPDE_MODEL_VAR_DPHI 1
 
 /* Options of one batched integration (scipy RK45 / Radau semantics; both steppers take this struct). */
 typedef struct marlpde_rk45_options {
@@ -101,6 +109,7 @@ typedef struct marlpde_rk45_options {
                                     attempt counter per column): the on-chip RK45 kernel may then cut every column's step budget into
                                     quanta claimed quantum-major, which shortens the partly filled last round of a
                                     launch (results are unchanged: a resumed column is bit-identical)          */
+#define MARLPDE_FLAG_VAR_DPHI 4u /* some columns of the batch carry MARLPDE_MODEL_VAR_DPHI (see marlpde_column_params) */
 
 /* Per-column integrator state: input (start/resume point) and output (end point). */
 typedef struct marlpde_column_state {

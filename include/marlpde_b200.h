@@ -139,8 +139,9 @@ const char* marlpde_last_error(void);
 int marlpde_device_count(void);
 int marlpde_get_device_info(int device, marlpde_device_info* info);
 
-/* The host-pointer entry points keep their device scratch buffers in a small per-process pool between
- * calls (cudaMalloc/cudaFree are slow); this returns them to the driver. Returns the number of blocks freed. */
+/* The host-pointer entry points take their device scratch from one stream-ordered memory pool per device that keeps at
+ * most 256 MB cached between calls (cudaMalloc/cudaFree are slow); this trims the pools to zero. Returns the number of
+ * pools trimmed. */
 int marlpde_release_cached_memory(void);
 
 /* Largest n_cells the on-chip (shared-memory resident) RK45 kernel accepts, and the
@@ -175,10 +176,21 @@ int marlpde_rk45_integrate(double* y, const marlpde_column_params* params,
                            const marlpde_rk45_options* opts, const double* t_eval,
                            double* snapshots, int32_t* event_counts, double* event_times,
                            int device);
+/* Stream-ordered variant of the host-pointer call, for sweep drivers that overlap the copies of one batch with the
+ * kernel of another: H2D copies (one cudaMemcpyAsync per buffer), the launch, the D2H copies and the release of the
+ * device scratch are all enqueued on `stream` (a cudaStream_t) and the call returns WITHOUT synchronising.  The host
+ * buffers must be page-locked for the copies to be asynchronous and must stay valid and untouched until the caller has
+ * synchronised the stream.  Depth grids outside the on-chip range (streaming path) are served synchronously. */
+int marlpde_rk45_integrate_async(double* y, const marlpde_column_params* params,
+                                 marlpde_column_state* state, int n_columns, int n_cells,
+                                 const marlpde_rk45_options* opts, const double* t_eval,
+                                 double* snapshots, int32_t* event_counts, double* event_times,
+                                 int device, void* stream);
 
-/* ---- the same RK45 for depth grids that do not fit on chip (n_cells up to millions): stage vectors
- * stream through HBM/L2, one kernel launch per Runge-Kutta stage (csrc/rk45_streaming.cu).
- *  Arguments as for marlpde_rk45_integrate_dev (events are not monitored on this path), plus
+/* ---- the same RK45 for depth grids that do not fit on chip (n_cells up to millions): overlapped 640-cell windows
+ * integrated on chip, one launch per step attempt, state and K1 / K7 streaming through HBM (csrc/rk45_streaming.cu).
+ *  Arguments as for marlpde_rk45_integrate_dev (marlpde_rk45_stream_integrate_events_dev takes the event outputs and
+ *  monitors the 7 events when MARLPDE_FLAG_EVENTS is set; the variant without them rejects the flag), plus
  *  d_workspace  marlpde_rk45_stream_workspace_bytes(n_columns, n_cells) bytes of device scratch.
  *  opts->max_steps must be > 0: the call enqueues exactly that many step attempts per column and
  *  returns without synchronising; columns that reach t_bound earlier idle, the others come back with
@@ -192,6 +204,11 @@ int marlpde_rk45_stream_integrate_dev(double* d_y, const marlpde_column_params* 
                                       const marlpde_rk45_options* opts, const double* d_t_eval,
                                       double* d_snapshots, void* d_workspace, size_t workspace_bytes,
                                       void* stream);
+int marlpde_rk45_stream_integrate_events_dev(double* d_y, const marlpde_column_params* d_params,
+                                             marlpde_column_state* d_state, int n_columns, int n_cells,
+                                             const marlpde_rk45_options* opts, const double* d_t_eval,
+                                             double* d_snapshots, int32_t* d_event_counts, double* d_event_times,
+                                             void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---- batched implicit integrator: 3-stage Radau IIA with a block-tridiagonal simplified Newton solve
  * (replaces solve_ivp(method="Radau", jac_sparsity=...) per column; scipy/integrate/_ivp/radau.py) ------
@@ -217,6 +234,12 @@ int marlpde_radau_integrate(double* y, const marlpde_column_params* params,
                             const marlpde_rk45_options* opts, const double* t_eval,
                             double* snapshots, int32_t* event_counts, double* event_times,
                             int64_t* stats, int device);
+/* stream-ordered variant, see marlpde_rk45_integrate_async */
+int marlpde_radau_integrate_async(double* y, const marlpde_column_params* params,
+                                  marlpde_column_state* state, int n_columns, int n_cells,
+                                  const marlpde_rk45_options* opts, const double* t_eval,
+                                  double* snapshots, int32_t* event_counts, double* event_times,
+                                  int64_t* stats, int device, void* stream);
 
 /* ---- measurement helper: fp64 FMA peak (TFLOP/s, best of `repeats`) of `device`, the roofline
  * denominator of the fp64-pipe-bound RK45 kernel (no reference counterpart). */

@@ -29,30 +29,8 @@ namespace fm {
 __constant__ double kLog1pC[6] = {-0.5, 1.0 / 3.0, -0.25, 0.2, -1.0 / 6.0, 1.0 / 7.0};
 __constant__ double kExpC[5] = {0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0};
 
-// MARLPDE_FP64_IMM=1 (experimental, OFF: not yet measured on a GPU): every constant that tolerates it is replaced by a
-// double whose low 32 bits are zero, which sm_100a encodes as an instruction immediate (Blackwell has no constant-
-// bank operands: each other constant costs an LDC and a register pair per basic block — 37 LDC per RHS of a cell pair).
-// Exactly representable: -1/2, -1/4, 1/2.  Rounded to 21 significant bits: the r^5, r^6 terms of log1p and the r^5, r^6
-// terms of exp (error <= 1e-19), 64/ln2 (only picks the reduction integer), and the HIGH parts of the ln2 and ln2/64
-// splits (the low parts absorb the difference; n * hi stays exact).  1/3, 1/7, 1/6, 1/24 and the low parts stay full
-// doubles.  Accuracy with an exact-FMA model of these routines against mpmath (20 000 samples, same ranges as
-// tests/test_gpu_math.py): log 2.18e-16 (2.16e-16 with full constants), exp 2.19e-16 (2.14e-16), expm1 2.58e-16 (2.60e-16).
-// Results differ from the default build in the last bits, so the whole GPU parity suite must be re-run before enabling.
-#ifndef MARLPDE_FP64_IMM
-#define MARLPDE_FP64_IMM 0
-#endif
-#if MARLPDE_FP64_IMM
-constexpr double kImmLn2Hi = 0x1.62e42p-1, kImmLn2_64Hi = 0x1.62e42p-7, kImm64_Ln2 = 0x1.71547p+6;
-__constant__ double kImmLn2Lo = 0x1.fdf473de6af28p-22, kImmLn2_64Lo = 0x1.fdf473de6af28p-28;
-constexpr double kImmLog3 = 0x1.9999ap-3, kImmLog4 = -0x1.55555p-3, kImmExp3 = 0x1.11111p-7, kImmExp4 = 0x1.6c16cp-10;
-#define FM_LN2HI kImmLn2Hi
-#define FM_LN2LO kImmLn2Lo
-#define FM_L64HI kImmLn2_64Hi
-#define FM_L64LO kImmLn2_64Lo
-#define FM_K64 kImm64_Ln2
-#define FM_LOG(i) ((i) == 0 ? -0.5 : (i) == 2 ? -0.25 : (i) == 3 ? kImmLog3 : (i) == 4 ? kImmLog4 : kLog1pC[i])
-#define FM_EXP(i) ((i) == 0 ? 0.5 : (i) == 3 ? kImmExp3 : (i) == 4 ? kImmExp4 : kExpC[i])
-#else
+// (Measured and dropped, r02a: constants with a zero low word as instruction immediates — 53 of 160 LDC gone from the RK45
+// kernel, no change in its run time: 22.53 vs 22.58 M column-steps/s; profiles/r02a_ab_candidates.log.)
 #define FM_LN2HI kLn2Hi
 #define FM_LN2LO kLn2Lo
 #define FM_L64HI kLn2_64Hi
@@ -60,7 +38,6 @@ constexpr double kImmLog3 = 0x1.9999ap-3, kImmLog4 = -0x1.55555p-3, kImmExp3 = 0
 #define FM_K64 k64_Ln2
 #define FM_LOG(i) kLog1pC[i]
 #define FM_EXP(i) kExpC[i]
-#endif
 
 struct Tables {            // shared-memory copies (random-index reads would serialise in the constant cache)
   const double2* logtab;   // [128] {ic, L}

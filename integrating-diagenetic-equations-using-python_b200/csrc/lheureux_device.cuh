@@ -40,6 +40,9 @@ struct ColumnConsts {
   double kPeCa, kPeCO3, kPePhi;   // delta_x/(2 dCa), delta_x/(2 dCO3), delta_x/(2 dPhi)
   double Pe_min, Pe_max;
   int32_t FV_switch, mask_lo, mask_hi, n_cells;
+  // model variant MARLPDE_MODEL_VAR_DPHI (only looked at by kVarDPhi code and the generic path):
+  double auxcon, half_dx;         // dPhi = auxcon F Phi^3 / (1 - Phi), Pe_Phi = W half_dx / dPhi
+  int32_t var_dphi, pad_[3];      // != 0: this column uses the time-varying dPhi
 };
 
 __host__ __device__ inline void make_consts(const marlpde_column_params& p, int n_cells, ColumnConsts& c) {
@@ -67,6 +70,10 @@ __host__ __device__ inline void make_consts(const marlpde_column_params& p, int 
   c.kPePhi = p.delta_x / (2.0 * p.dPhi_fixed);
   c.Pe_min = p.Peclet_min;
   c.Pe_max = p.Peclet_max;
+  c.auxcon = p.auxcon;
+  c.half_dx = p.delta_x / 2.0;
+  c.var_dphi = (p.model_flags & MARLPDE_MODEL_VAR_DPHI) != 0;
+  c.pad_[0] = c.pad_[1] = c.pad_[2] = 0;
   c.FV_switch = p.FV_switch;
   c.mask_lo = p.mask_lo;
   c.mask_hi = p.mask_hi;
@@ -105,10 +112,17 @@ __device__ __forceinline__ void cell_rhs(const ColumnConsts& k, const fm::Tables
   const double F = 1.0 - fm::exp(tb, fma(-10.0, rPhi, 10.0));
   const double omP = 1.0 - Phi;
   const double Phi2 = Phi * Phi;
-  const double U = fma(k.rhorat * (Phi2 * Phi), fm::div(F, omP), k.presum);
+  const double FoP = fm::div(F, omP);
+  const double U = fma(k.rhorat * (Phi2 * Phi), FoP, k.presum);
   const double W = fma(-k.rhorat * Phi2, F, k.presum);
   const double den = fma(-2.0, fm::log(tb, Phi), 1.0);
   const double rden = fm::rcp(den);
+  // porosity diffusion coefficient: fixed (:431), or the commented-out per-cell value (:430) for flagged columns
+  double dPhi = k.dPhi, kPePhi = k.kPePhi;
+  if (k.var_dphi) {
+    dPhi = k.auxcon * (Phi2 * Phi) * FoP;
+    kPePhi = fm::div(k.half_dx, dPhi);
+  }
 
   // ---- solids: first-order upwind by the sign of U (:418-423)
   const bool back = U > 0.0;
@@ -121,7 +135,7 @@ __device__ __forceinline__ void cell_rhs(const ColumnConsts& k, const fm::Tables
     const double Wden = W * den;
     sCa = fv_sigma(tb, Wden * k.kPeCa, W, k.Pe_min, k.Pe_max);
     sCO3 = fv_sigma(tb, Wden * k.kPeCO3, W, k.Pe_min, k.Pe_max);
-    sPhi = fv_sigma(tb, W * k.kPePhi, W, k.Pe_min, k.Pe_max);
+    sPhi = fv_sigma(tb, W * kPePhi, W, k.Pe_min, k.Pe_max);
   }
   // g = 0.5((1-s) gf + (1+s) gb) = 0.5 (gf + gb) - 0.5 s (gf - gb)   (:464-469)
   const double hdx = 0.5 * k.inv_dx;
@@ -161,7 +175,7 @@ __device__ __forceinline__ void cell_rhs(const ColumnConsts& k, const fm::Tables
   out.r[1] = -U * gCC + k.Da * (k.lambda_ * (1.0 - CC) * coC + CC * coA);
   out.r[2] = (HCa + react * (k.delta - cCa)) * rPhi - W * gCa;
   out.r[3] = (HCO3 + react * (k.delta - cCO3)) * rPhi - W * gCO3;
-  out.r[4] = -(dWdx * Phi + W * gPhi) + k.dPhi * lapPhi + react;
+  out.r[4] = -(dWdx * Phi + W * gPhi) + dPhi * lapPhi + react;
   out.U = U;
   out.W = W;
 }
@@ -296,9 +310,13 @@ struct OwnTerms {
   double react[2];   // Da (1 - Phi) (coA - lambda coC)
   double rA[2];      // Da ((1 - CA) coA + lambda CA coC)
   double rC[2];      // Da (lambda (1 - CC) coC + CC coA)
+  double dPhi[2];    // porosity diffusion coefficient of the cell (kVarDPhi instantiations only)
 };
 
-template <int kSched>
+// kVarDPhi: the instantiation for batches that may contain MARLPDE_MODEL_VAR_DPHI columns (LHeureux_model.py:222-223,
+// :430-431); the per-column flag k.var_dphi then selects the per-cell or the fixed coefficient (bit-identical to the
+// kVarDPhi = false instantiation for columns without the flag).  The default instantiation carries none of this.
+template <int kSched, bool kVarDPhi = false>
 __device__ __forceinline__ PairFlags rhs_pair_own(const ColumnConsts& k, const fm::Tables& tb, const double (&c)[5][2],
                                                   const bool (&in_mask)[2], OwnTerms& o) {
   PairFlags fl;
@@ -306,6 +324,7 @@ __device__ __forceinline__ PairFlags rhs_pair_own(const ColumnConsts& k, const f
 
   // ---- porosity-dependent velocities (:414-431)
   double F[2], omP[2], den[2];
+  double kPeV[2];   // delta_x / (2 dPhi) of the two cells (kVarDPhi only)
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     const double Phi = c[4][q];
@@ -313,7 +332,13 @@ __device__ __forceinline__ PairFlags rhs_pair_own(const ColumnConsts& k, const f
     F[q] = 1.0 - fm::exp_nb(tb, fma(-10.0, o.rPhi[q], 10.0), fl.bad[q]);
     omP[q] = 1.0 - Phi;
     const double Phi2 = Phi * Phi;
-    o.U[q] = fma(k.rhorat * (Phi2 * Phi), F[q] * fm::rcp3(omP[q]), k.presum);
+    const double FoP = F[q] * fm::rcp3(omP[q]);
+    o.U[q] = fma(k.rhorat * (Phi2 * Phi), FoP, k.presum);
+    if constexpr (kVarDPhi) {
+      const double dv = k.auxcon * (Phi2 * Phi) * FoP;
+      o.dPhi[q] = k.var_dphi ? dv : k.dPhi;
+      kPeV[q] = k.var_dphi ? k.half_dx * fm::rcp3(dv) : k.kPePhi;
+    }
     o.W[q] = fma(-k.rhorat * Phi2, F[q], k.presum);
     den[q] = fma(-2.0, fm::log_nb(tb, Phi, fl.bad[q]), 1.0);
     const double rden = fm::rcp3(den[q]);
@@ -361,7 +386,8 @@ __device__ __forceinline__ PairFlags rhs_pair_own(const ColumnConsts& k, const f
       const double Wden = o.W[q] * den[q];
       PeCa[q] = Wden * k.kPeCa;
       PeCO3[q] = Wden * k.kPeCO3;
-      PePhi[q] = o.W[q] * k.kPePhi;
+      if constexpr (kVarDPhi) PePhi[q] = o.W[q] * kPeV[q];
+      else PePhi[q] = o.W[q] * k.kPePhi;
     }
     if constexpr (kSched == kSchedSplit) {
       fv_sigma_pair(tb, fv_on, PeCa, o.W, k.Pe_min, k.Pe_max, o.sCa);
@@ -468,6 +494,7 @@ __device__ __forceinline__ PairFlags rhs_pair_own(const ColumnConsts& k, const f
 
 // The stencil part: first differences of the five fields, upwinded / Fiadeiro-Veronis weighted gradients,
 // Laplacians and the five rates (:418-423, :464-477, :495-520).
+template <bool kVarDPhi = false>
 __device__ __forceinline__ void rhs_pair_finish(const ColumnConsts& k, const double (&c)[5][2], const double (&mlo)[5],
                                                 const double (&phi)[5], const OwnTerms& o, double (&out)[5][2]) {
   // a = (next - centre), b = (centre - previous) per field and cell
@@ -499,18 +526,18 @@ __device__ __forceinline__ void rhs_pair_finish(const ColumnConsts& k, const dou
     out[1][q] = fma(-o.U[q], gCC, o.rC[q]);
     out[2][q] = fma(fma(o.react[q], k.delta - cCa, HCa), o.rPhi[q], -o.W[q] * gCa);
     out[3][q] = fma(fma(o.react[q], k.delta - cCO3, HCO3), o.rPhi[q], -o.W[q] * gCO3);
-    out[4][q] = fma(k.dPhi, lapPhi, o.react[q]) - fma(dWdx, Phi, o.W[q] * gPhi);
+    out[4][q] = fma(kVarDPhi ? o.dPhi[q] : k.dPhi, lapPhi, o.react[q]) - fma(dWdx, Phi, o.W[q] * gPhi);
   }
 }
 
-template <int kSched>
+template <int kSched, bool kVarDPhi = false>
 __device__ __forceinline__ PairFlags rhs_pair(const ColumnConsts& k, const fm::Tables& tb, const double (&c)[5][2],
                                               const double (&mlo)[5], const double (&phi)[5],
                                               const bool (&in_mask)[2], double (&out)[5][2], double (&Uo)[2],
                                               double (&Wo)[2]) {
   OwnTerms o;
-  const PairFlags fl = rhs_pair_own<kSched>(k, tb, c, in_mask, o);
-  rhs_pair_finish(k, c, mlo, phi, o, out);
+  const PairFlags fl = rhs_pair_own<kSched, kVarDPhi>(k, tb, c, in_mask, o);
+  rhs_pair_finish<kVarDPhi>(k, c, mlo, phi, o, out);
   Uo[0] = o.U[0];
   Uo[1] = o.U[1];
   Wo[0] = o.W[0];

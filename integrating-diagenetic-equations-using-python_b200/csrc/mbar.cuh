@@ -11,11 +11,6 @@
 #define MARLPDE_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
-// A/B candidate (off): spread the last columns of a sweep over the SMs (rk45_persistent.cu / rk45_quad.cu slot service)
-#ifndef MARLPDE_TAIL_SPREAD
-#define MARLPDE_TAIL_SPREAD 0
-#endif
-
 // A/B candidate (off): the tile kernel of rk45_streaming.cu moves its windows with 1-D TMA bulk copies
 #ifndef MARLPDE_TILE_TMA
 #define MARLPDE_TILE_TMA 0

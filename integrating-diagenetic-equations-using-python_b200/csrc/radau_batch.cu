@@ -213,7 +213,9 @@ __device__ __forceinline__ void rhs_column(const ColumnConsts& kc, const fm::Tab
     const bool in_mask[2] = {cell0 >= kc.mask_lo && cell0 < kc.mask_hi,
                              cell0 + 1 >= kc.mask_lo && cell0 + 1 < kc.mask_hi};
     double r[5][2], U[2], Wv[2];
-    PairFlags fl = rhs_pair<rhs_schedule(kSchedAll)>(kc, tb, c, mlo, phi, in_mask, r, U, Wv);
+    // (kVarDPhi = true: a column flagged MARLPDE_MODEL_VAR_DPHI takes the per-cell porosity diffusion coefficient; for
+    //  the others the instantiation is bit-identical to the plain one and costs ~10 instructions per cell pair)
+    PairFlags fl = rhs_pair<rhs_schedule(kSchedAll), true>(kc, tb, c, mlo, phi, in_mask, r, U, Wv);
     fl.bad[0] = fl.bad[0] && v0;
     fl.bad[1] = fl.bad[1] && v1;
     if (fl.bad[0] || fl.bad[1]) rhs_pair_fixup(kc, tb, fl, c, mlo, phi, in_mask, r, U, Wv);
@@ -237,15 +239,6 @@ __device__ __forceinline__ double fd_step(double y, double f, double atol) {
 
 // THE one instance of the RHS in this kernel (instruction-cache footprint matters: 12 warps per SM sit
 // in different phases of their columns): out = rhs(yy + add) (add may be NULL), all cell-major [N][5].
-#if MARLPDE_RADAU_FUSE_F
-__device__ __noinline__ bool rhs_eval_fused(const ColumnConsts* kcp, const fm::Tables* tbp, int N, int lane, const double* yy,
-                                            const double* Zb, const double* Wb, double* Bb, int n_stage, double Mr,
-                                            double Mcr, double Mci);
-__device__ __forceinline__ void rhs_eval(const ColumnConsts* kc, const fm::Tables* tb, int N, int lane, const double* yy,
-                                         const double* add, double* out) {
-  rhs_eval_fused(kc, tb, N, lane, yy, add, nullptr, out, 1, 0.0, 0.0, 0.0);   // the ONE instance serves both uses
-}
-#else
 __device__ __noinline__ void rhs_eval(const ColumnConsts* kc, const fm::Tables* tb, int N, int lane, const double* yy,
                                       const double* add, double* out) {
   auto sink = [&](int i, const double (&r5)[5]) {
@@ -255,103 +248,10 @@ __device__ __noinline__ void rhs_eval(const ColumnConsts* kc, const fm::Tables* 
   rhs_column(*kc, *tb, N, lane, yy, add, sink);
   __syncwarp();
 }
-#endif
 
-// MARLPDE_RADAU_FUSE_F=1 (experimental, OFF: not yet measured on a GPU).  The saturated kernel is bound by DRAM traffic,
-// ~2/3 of it the fp64 vectors of the Newton passes.  Per Newton iteration the three stage evaluations F_s = f(y + Z_s)
-// are written (3 x 5N doubles), read back by the pass B = TI F - M W and overwritten.  Fused: the three stages of a
-// cell pair are evaluated back to back (still ONE instance of the RHS, inside a rolled loop) and accumulated into
-// TI F in registers / local memory, B is written once: 6 x 5N fewer doubles through DRAM per iteration (~10 %).
-// The sums are formed in a different order than in the separate pass, so results differ in the last bits.
-#ifndef MARLPDE_RADAU_FUSE_F
-#define MARLPDE_RADAU_FUSE_F 0
-#endif
-#if MARLPDE_RADAU_FUSE_F
-// B[k] = sum_s TI[k][s] f(y + Z[s]) - (M W)[k]   (k = 0: real system; k = 1, 2: real / imaginary part of the complex one)
-// y, Z = Zb[s * n + .], W = Wb[k * n + .], B = Bb[k * n + .] cell-major.  Returns whether every F value of this lane was
-// finite (the caller votes).  With n_stage == 1 it is the plain evaluation Bb = f(y + Zb) (Zb may be NULL).
-__device__ __noinline__ bool rhs_eval_fused(const ColumnConsts* kcp, const fm::Tables* tbp, int N, int lane, const double* yy,
-                                            const double* Zb, const double* Wb, double* Bb, int n_stage, double Mr,
-                                            double Mcr, double Mci) {
-  const ColumnConsts& kc = *kcp;
-  const fm::Tables& tb = *tbp;
-  const int Hc = (N + 1) >> 1, n = 5 * N;
-  bool finite = true;
-#pragma unroll 1
-  for (int base = 0; base < Hc; base += 32) {
-    const int p = base + lane;
-    const int cell0 = 2 * p;
-    const bool v0 = cell0 < N, v1 = cell0 + 1 < N;
-    const bool in_mask[2] = {cell0 >= kc.mask_lo && cell0 < kc.mask_hi,
-                             cell0 + 1 >= kc.mask_lo && cell0 + 1 < kc.mask_hi};
-    double acc[3][5][2];
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-#pragma unroll
-      for (int f = 0; f < 5; ++f) acc[k][f][0] = acc[k][f][1] = 0.0;
-#pragma unroll 1
-    for (int sg = 0; sg < n_stage; ++sg) {
-      const double* add = Zb ? Zb + (size_t)sg * n : nullptr;
-      auto ld = [&](int ff, int i) -> double { return add ? yy[i * 5 + ff] + add[i * 5 + ff] : yy[i * 5 + ff]; };
-      double c[5][2], mlo[5], phi[5];
-#pragma unroll
-      for (int f = 0; f < 5; ++f) {
-        c[f][0] = v0 ? ld(f, cell0) : 0.5;
-        c[f][1] = v1 ? ld(f, cell0 + 1) : 0.5;
-        mlo[f] = (v0 && cell0 > 0) ? ld(f, cell0 - 1) : top_ghost(kc, f, c[f][0]);
-        if (cell0 + 2 < N) {
-          phi[f] = ld(f, cell0 + 2);
-        } else if (v1) {
-          phi[f] = bottom_ghost(f, c[f][1], c[f][0]);
-        } else {
-          c[f][1] = bottom_ghost(f, c[f][0], mlo[f]);
-          phi[f] = c[f][1];
-        }
-      }
-      double r[5][2], U[2], Wv[2];
-      PairFlags fl = rhs_pair<rhs_schedule(kSchedAll)>(kc, tb, c, mlo, phi, in_mask, r, U, Wv);
-      fl.bad[0] = fl.bad[0] && v0;
-      fl.bad[1] = fl.bad[1] && v1;
-      if (fl.bad[0] || fl.bad[1]) rhs_pair_fixup(kc, tb, fl, c, mlo, phi, in_mask, r, U, Wv);
-      if (n_stage == 1) {
-#pragma unroll
-        for (int f = 0; f < 5; ++f) {
-          if (v0) Bb[cell0 * 5 + f] = r[f][0];
-          if (v1) Bb[(cell0 + 1) * 5 + f] = r[f][1];
-        }
-      } else {
-        const double t0 = kTI[0][sg], t1 = kTI[1][sg], t2 = kTI[2][sg];
-#pragma unroll
-        for (int f = 0; f < 5; ++f) {
-          finite = finite && (!v0 || isfinite(r[f][0])) && (!v1 || isfinite(r[f][1]));
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            acc[0][f][q] = fma(t0, r[f][q], acc[0][f][q]);
-            acc[1][f][q] = fma(t1, r[f][q], acc[1][f][q]);
-            acc[2][f][q] = fma(t2, r[f][q], acc[2][f][q]);
-          }
-        }
-      }
-    }
-    if (n_stage != 1) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (q == 0 ? !v0 : !v1) continue;
-#pragma unroll
-        for (int f = 0; f < 5; ++f) {
-          const int idx = (cell0 + q) * 5 + f;
-          const double W0 = Wb[idx], W1 = Wb[n + idx], W2 = Wb[2 * n + idx];
-          Bb[idx] = acc[0][f][q] - Mr * W0;
-          Bb[n + idx] = acc[1][f][q] - (Mcr * W1 - Mci * W2);
-          Bb[2 * n + idx] = acc[2][f][q] - (Mcr * W2 + Mci * W1);
-        }
-      }
-    }
-  }
-  __syncwarp();
-  return finite;
-}
-#endif
+// (Measured and dropped, r02a: the three stage evaluations of a Newton iteration fused with B = TI F - M W, one RHS
+// instance in a rolled loop with the accumulators in local memory — 6 x 5N fewer doubles through DRAM per iteration, but
+// 4096 columns to t = 0.05 took 1.645 s instead of 1.495 s; profiles/r02a_ab_candidates.log.)
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -386,10 +286,16 @@ __device__ __noinline__ void jac_columns(const ColumnConsts* kp, const fm::Table
     const double rPhi = fm::rcp(Phi);
     const double F = 1.0 - fm::exp(tb, fma(-10.0, rPhi, 10.0));
     const double Phi2 = Phi * Phi;
-    const double U = fma(k.rhorat * (Phi2 * Phi), fm::div(F, 1.0 - Phi), k.presum);
+    const double FoP = fm::div(F, 1.0 - Phi);
+    const double U = fma(k.rhorat * (Phi2 * Phi), FoP, k.presum);
     const double W = fma(-k.rhorat * Phi2, F, k.presum);
     const double den = fma(-2.0, fm::log(tb, Phi), 1.0);
     const double rden = fm::rcp(den);
+    double dPhi = k.dPhi, kPePhi = k.kPePhi;                // MARLPDE_MODEL_VAR_DPHI: the cell's own coefficient (cell_rhs)
+    if (k.var_dphi) {
+      dPhi = k.auxcon * (Phi2 * Phi) * FoP;
+      kPePhi = fm::div(k.half_dx, dPhi);
+    }
     double Lc[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, Uc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     // weighted gradient of field f (2, 3 or 4) at this cell: 0.5 ((1 - s) forward + (1 + s) backward)
     auto grad = [&](int f, double sg) {
@@ -409,7 +315,7 @@ __device__ __noinline__ void jac_columns(const ColumnConsts* kp, const fm::Table
       Uc[0] = fld == 0 ? uv : 0.0;
       Uc[1] = fld == 1 ? uv : 0.0;
     } else {
-      const double sPhi = sigma(W * k.kPePhi);
+      const double sPhi = sigma(W * kPePhi);
       const double h2c = (2.0 + den) * (rden * rden);
       if (fld < 4) {
         const double sg = sigma(W * den * (fld == 2 ? k.kPeCa : k.kPeCO3)), d = fld == 2 ? k.dCa : k.dCO3;
@@ -432,8 +338,8 @@ __device__ __noinline__ void jac_columns(const ColumnConsts* kp, const fm::Table
         Uc[2] = t2 * dgn;
         Lc[3] = t3 * dgp;
         Uc[3] = t3 * dgn;
-        Lc[4] = fma(k.dPhi, k.inv_dx2, -t4 * dgp);
-        Uc[4] = fma(k.dPhi, k.inv_dx2, -t4 * dgn);
+        Lc[4] = fma(dPhi, k.inv_dx2, -t4 * dgp);
+        Uc[4] = fma(dPhi, k.inv_dx2, -t4 * dgn);
       }
     }
     const double di = fd_step(y0[i * 5 + fld], f0[i * 5 + fld], atol);
@@ -964,10 +870,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
           converged = false;
           int k = 0;
           for (k = 0; k < kNewtonMaxIter; ++k) {
-#if MARLPDE_RADAU_FUSE_F
-            nfev += 3;
-            bool finite = rhs_eval_fused(&kc, &tb, N, lane, y, w.Z, w.W, w.B, 3, Mr, Mcr, Mci);
-#else
             eval_to(y, w.Z, w.B);
             eval_to(y, w.Z + n, w.B + n);
             eval_to(y, w.Z + 2 * n, w.B + 2 * n);
@@ -1000,7 +902,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
               }
             }
             __syncwarp();
-#endif
             if (!__all_sync(0xffffffffu, finite)) break;
             solve(ws, N, lane, w.Rec, w.B, w.B + n, w.B + 2 * n, true);
             // norm(dW / scale) and, in the same pass, W += dW, Z = T W.  (radau.py leaves W and Z untouched when

@@ -55,7 +55,11 @@ rhs_batch_kernel(const double* __restrict__ g_y, const marlpde_column_params* __
   const bool in_mask[2] = {cell0 >= kc.mask_lo && cell0 < kc.mask_hi,
                            cell0 + 1 >= kc.mask_lo && cell0 + 1 < kc.mask_hi};
   double r[5][2], U[2], W[2];
-  PairFlags fl = rhs_pair<kSched>(kc, tb, c, mlo, phi, in_mask, r, U, W);
+  // a CTA lies inside one column, so the model variant is a CTA-uniform choice between the two instantiations the
+  // integrators use (MARLPDE_MODEL_VAR_DPHI: per-cell porosity diffusion coefficient, LHeureux_model.py:430)
+  PairFlags fl;
+  if (kc.var_dphi) fl = rhs_pair<kSched, true>(kc, tb, c, mlo, phi, in_mask, r, U, W);
+  else fl = rhs_pair<kSched, false>(kc, tb, c, mlo, phi, in_mask, r, U, W);
   fl.bad[0] = fl.bad[0] && valid0;
   fl.bad[1] = fl.bad[1] && valid1;
   if (fl.bad[0] || fl.bad[1]) rhs_pair_fixup(kc, tb, fl, c, mlo, phi, in_mask, r, U, W);

@@ -7,7 +7,7 @@
 // Design (B200-first):
 //   * persistent CTAs, one per SM; each CTA integrates C columns side by side ("slots");
 //     a thread owns TWO adjacent depth cells of one column (cells 2k, 2k+1): N=200 gives
-//     4 columns x 100 threads = 400 of 416 lanes busy.  Two cells per thread double the
+//     3 columns x 100 threads = 300 of 320 lanes busy.  Two cells per thread double the
 //     instruction-level parallelism (the register file only holds ~3 warps per scheduler) and
 //     halve every per-instruction overhead (addresses, constants, control) per cell;
 //   * the whole integration of a column happens on-chip.  In REGISTERS: the state y, K1 (which
@@ -34,10 +34,10 @@
 
 #include "brent.cuh"
 #include "dopri.cuh"
+#include "events.cuh"
 #include "lheureux_device.cuh"
 #include "mbar.cuh"
 #include "rk45_persistent.cuh"
-#include "rk45_quad.cuh"
 
 namespace marlpde {
 
@@ -54,16 +54,13 @@ struct SlotCtl {          // per-slot counters, written by the slot's leader thr
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) / 16 * 16; }
 
-template <int TP, bool YS, bool HS>
+template <int TP>
 struct Smem {
   static constexpr size_t off_K = 0;
-  static constexpr size_t off_Y = off_K + sizeof(double2) * 4 * 5 * TP;        // y, K1: [2][5][TP] double2, YS builds only
-  // halo exchange: HS = false: two full stage-input vectors [2][5][TP] per parity (even / odd cells);
-  //                HS = true : warp shuffles, only the warp-edge values [2][TP/32][2][5] and a 2 x TP scratch
-  //                            (event location) live in shared memory
-  static constexpr size_t off_tE = off_Y + (YS ? sizeof(double2) * 2 * 5 * TP : 0);
-  static constexpr size_t off_tO = off_tE + (HS ? sizeof(double) * 2 * TP : sizeof(double) * 2 * 5 * TP);
-  static constexpr size_t off_grp = off_tO + (HS ? sizeof(double) * 2 * (TP / 32 + 1) * 2 * 5 : sizeof(double) * 2 * 5 * TP);
+  // halo exchange: two full stage-input vectors [2][5][TP] per parity (even / odd cells)
+  static constexpr size_t off_tE = off_K + sizeof(double2) * 4 * 5 * TP;
+  static constexpr size_t off_tO = off_tE + sizeof(double) * 2 * 5 * TP;
+  static constexpr size_t off_grp = off_tO + sizeof(double) * 2 * 5 * TP;
   static constexpr size_t off_tab = off_grp + sizeof(double) * TP;
   static constexpr size_t off_var = off_tab + fm::kTableBytes;          // per-slot arrays start here
   static constexpr size_t slot_bytes = (sizeof(ColumnConsts) + 15) / 16 * 16 + (sizeof(SlotCtl) + 15) / 16 * 16 + 32;
@@ -76,112 +73,27 @@ static int group_log2(int threads_per_column) {
   return logG;
 }
 
-template <int TP, bool YS, bool HS>
+template <int TP>
 static int columns_per_cta_t(int n_cells, int smem_budget) {
   const int Hc = (n_cells + 1) / 2;
   if (n_cells < 32 || Hc > TP) return 0;
   int C = TP / Hc;
-  while (C > 0 && Smem<TP, YS, HS>::total(C) > (size_t)smem_budget) --C;
+  while (C > 0 && Smem<TP>::total(C) > (size_t)smem_budget) --C;
   return C;
 }
 
-// Builds of the kernel (register file: 16K registers per SM sub-partition, so the register cap
-// follows from the warps per sub-partition, not from the thread count alone):
-//   <320,false> 10 warps, <= 168 registers, y and K1 in registers      (n_cells <= 640; N=200: 3 columns)
-//   <320,true>  10 warps, <= 168 registers, y and K1 in shared memory  (same shapes; fewer register spills)
-//   <416,true,HS> 13 warps, <= 128 registers, y and K1 in shared memory, halo exchange by warp shuffles
-//               instead of a stage-input tile (frees 64 kB: N=200 runs 4 columns per CTA)
-//   450         EXPERIMENTAL, rk45_quad.cu: four cells per thread, 8 warps, N=200 runs 5 columns per CTA (grids it
-//               does not take fall back to the default build)
-// MARLPDE_RK45_BUILD=320|321|416|450 overrides the default choice (tuning / tests).
-static int rk45_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* s = std::getenv("MARLPDE_RK45_BUILD");
-    const int want = s ? std::atoi(s) : 0;
-    v = (want == 128 || want == 129 || want == 321 || want == 416 || want == 450) ? want : 320;
-  }
-  return v;
-}
+// Shape of the kernel (register file: 16K registers per SM sub-partition, so the register cap follows from the warps
+// per sub-partition, not from the thread count alone): 320 threads = 10 warps, <= 168 registers, y and K1 in registers
+// (n_cells <= 640; N=200: 3 columns per CTA).  Shapes that were measured and dropped (profiles/r02a_ab_candidates.log,
+// DESIGN.md section 9): y and K1 in shared memory (same speed), 13 warps / 128 registers / 4 columns with the halo by
+// warp shuffles (-12 %), 128-thread CTAs with one column each, 3 per SM (-20 %), 4 cells per thread / 8 warps / 5
+// columns (+1.5 %, not worth a second kernel).
+constexpr int kRk45Threads = 320;
 
-int rk45_columns_per_cta(int n_cells, int smem_budget) {
-  if (rk45_variant() == 450 && rk45_quad_columns_per_cta(n_cells, smem_budget) > 0)
-    return rk45_quad_columns_per_cta(n_cells, smem_budget);
-  switch (rk45_variant()) {
-    case 128: if (n_cells <= 256) return columns_per_cta_t<128, false, false>(n_cells, smem_budget / 3 - 1024); break;
-    case 129: if (n_cells <= 256) return columns_per_cta_t<128, true, false>(n_cells, smem_budget / 3 - 1024); break;
-    case 321: return columns_per_cta_t<320, true, false>(n_cells, smem_budget);
-    case 416: return columns_per_cta_t<416, true, true>(n_cells, smem_budget);
-    default: break;
-  }
-  return columns_per_cta_t<320, false, false>(n_cells, smem_budget);
-}
+int rk45_columns_per_cta(int n_cells, int smem_budget) { return columns_per_cta_t<kRk45Threads>(n_cells, smem_budget); }
 
-int rk45_max_cells() { return 640; }   // (the 416 build would take 832; the ABI reports the default build)
+int rk45_max_cells() { return 2 * kRk45Threads; }
 
-
-// ---- event monitors (LHeureux_model.py:524-593, all non-terminal, direction 0) -----------------
-// k: 0 min(y)  1 min(CA)  2 min(CC)  3 max(CA+CC)-1  4 max(Phi)-1  5 min(U)  6 max(W).
-// solve_ivp only needs the SIGN of each monitor after every accepted step (ivp.py
-// find_active_events); signs of a min/max follow from per-cell predicates, so detection is an
-// OR-reduction of 21 bits per thread (3 per monitor: beyond the threshold / on it / NaN) that
-// rides on the error-norm barrier — no fp64 reduction unless a sign change has to be located.
-constexpr unsigned kMaxTypeMask = (1u << 3) | (1u << 4) | (1u << 6);   // monitors that are a max
-constexpr unsigned kEqBitsMask = 0x92492u;                              // the "on the threshold" bit of every monitor
-
-__device__ __forceinline__ unsigned event_bits(const double (&v)[5][2], const double (&U)[2],
-                                               const double (&W)[2], bool has1) {
-  unsigned b = 0;
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    if (q == 1 && !has1) break;
-    bool lt = false, eq = false, nn = false;
-#pragma unroll
-    for (int f = 0; f < 5; ++f) {
-      lt |= v[f][q] < 0.0;
-      eq |= v[f][q] == 0.0;
-      nn |= v[f][q] != v[f][q];
-    }
-    const double CA = v[0][q], CC = v[1][q], s = CA + CC, Phi = v[4][q];
-    b |= (lt ? 1u : 0u) | (eq ? 2u : 0u) | (nn ? 4u : 0u);
-    b |= (CA < 0.0 ? 1u : 0u) << 3 | (CA == 0.0 ? 1u : 0u) << 4 | (CA != CA ? 1u : 0u) << 5;
-    b |= (CC < 0.0 ? 1u : 0u) << 6 | (CC == 0.0 ? 1u : 0u) << 7 | (CC != CC ? 1u : 0u) << 8;
-    b |= (s > 1.0 ? 1u : 0u) << 9 | (s == 1.0 ? 1u : 0u) << 10 | (s != s ? 1u : 0u) << 11;
-    b |= (Phi > 1.0 ? 1u : 0u) << 12 | (Phi == 1.0 ? 1u : 0u) << 13 | (Phi != Phi ? 1u : 0u) << 14;
-    b |= (U[q] < 0.0 ? 1u : 0u) << 15 | (U[q] == 0.0 ? 1u : 0u) << 16 | (U[q] != U[q] ? 1u : 0u) << 17;
-    b |= (W[q] > 0.0 ? 1u : 0u) << 18 | (W[q] == 0.0 ? 1u : 0u) << 19 | (W[q] != W[q] ? 1u : 0u) << 20;
-  }
-  return b;
-}
-
-// 21 predicate bits -> 7 sign classes, 2 bits each: 0 negative, 1 zero, 2 positive, 3 NaN
-__device__ __forceinline__ unsigned event_classes(unsigned bits) {
-  unsigned cls = 0;
-#pragma unroll
-  for (int k = 0; k < MARLPDE_NEVENTS; ++k) {
-    const unsigned b3 = (bits >> (3 * k)) & 7u;
-    const bool maxtype = (kMaxTypeMask >> k) & 1u;
-    unsigned c;
-    if (b3 & 4u) c = 3u;
-    else if (b3 & 1u) c = maxtype ? 2u : 0u;
-    else if (b3 & 2u) c = 1u;
-    else c = maxtype ? 0u : 2u;
-    cls |= c << (2 * k);
-  }
-  return cls;
-}
-
-// ivp.py find_active_events with direction 0: (g <= 0 & g_new >= 0) | (g >= 0 & g_new <= 0)
-__device__ __forceinline__ unsigned active_events(unsigned cls_old, unsigned cls_new) {
-  unsigned act = 0;
-#pragma unroll
-  for (int k = 0; k < MARLPDE_NEVENTS; ++k) {
-    const unsigned a = (cls_old >> (2 * k)) & 3u, b = (cls_new >> (2 * k)) & 3u;
-    const bool a_le = a <= 1u, a_ge = a == 1u || a == 2u, b_le = b <= 1u, b_ge = b == 1u || b == 2u;
-    if ((a_le && b_ge) || (a_ge && b_le)) act |= 1u << k;
-  }
-  return act;
-}
 
 struct Rk45Args {
   double* g_y;
@@ -199,10 +111,11 @@ struct Rk45Args {
   marlpde_rk45_options opt;
 };
 
-template <int TP, bool YS, bool HS>
-__global__ void __launch_bounds__((TP + 31) / 32 * 32, TP <= 128 ? 3 : 1) rk45_persistent_kernel(const Rk45Args A) {
+// VD: the instantiation for batches with MARLPDE_MODEL_VAR_DPHI columns (opt.flags & MARLPDE_FLAG_VAR_DPHI), see rhs_pair_own
+template <int TP, bool VD>
+__global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel(const Rk45Args A) {
   MARLPDE_DYN_SMEM(smem_raw);
-  using L = Smem<TP, YS, HS>;
+  using L = Smem<TP>;
   // Logical thread index.  Physical warps can be dealt out to the column ranges in any order; the order decides WHICH
   // scheduler (physical warp & 3) runs the warps whose lanes lie in the dissolution zone and therefore evaluate one
   // more real power per RHS.  Ten warps over four schedulers is 3-3-2-2: the automatic order puts those warps on the
@@ -250,7 +163,6 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, TP <= 128 ? 3 : 1) rk45_p
   const int N = A.N, C = A.C;
   const int Hc = (N + 1) >> 1;                     // threads per column
   double2* const sK = reinterpret_cast<double2*>(smem_raw + L::off_K) + tid;         // [4][5][TP]
-  double2* const sY = reinterpret_cast<double2*>(smem_raw + L::off_Y) + tid;         // y [5][TP], K1 [5][TP] (YS builds)
   double* const sE = reinterpret_cast<double*>(smem_raw + L::off_tE);               // [2][5][TP] even cells
   double* const sO = reinterpret_cast<double*>(smem_raw + L::off_tO);               // [2][5][TP] odd cells
   double* const sGrp = reinterpret_cast<double*>(smem_raw + L::off_grp);            // [TP >> logG]
@@ -278,10 +190,6 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, TP <= 128 ? 3 : 1) rk45_p
   const double* const haloP = sE + (last ? tid : tid + 1);
   double* const myE = sE + tid;
   double* const myO = sO + tid;
-  // HS builds: sO holds the warp-edge values [2 parities][warp][2 sides][5]; side 0 = lane 0's even cell,
-  // side 1 = lane 31's odd cell
-  const int lane_id = tid & 31, warp_id = tid >> 5;
-  constexpr int kEdgeStride = (TP / 32 + 1) * 2 * 5;
   // Error-norm reduction tree, identical for every slot so that a column's trajectory does not
   // depend on where it is scheduled: threads are summed in aligned groups of G = 2^k lanes
   // (G = largest power of two <= 32 dividing Hc, hence dividing every slot base) by an xor
@@ -324,14 +232,6 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, TP <= 128 ? 3 : 1) rk45_p
     }
 
   auto tile_store = [&](int b) {
-    if (HS) {                                       // only the two edge lanes of a warp publish through shared memory
-      if (lane_id == 0 || lane_id == 31) {
-        double* e = sO + b * kEdgeStride + (warp_id * 2 + (lane_id == 31 ? 1 : 0)) * 5;
-#pragma unroll
-        for (int f = 0; f < 5; ++f) e[f] = lane_id == 31 ? c[f][1] : c[f][0];
-      }
-      return;
-    }
 #pragma unroll
     for (int f = 0; f < 5; ++f) {
       myE[(b * 5 + f) * TP] = c[f][0];
@@ -340,37 +240,21 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, TP <= 128 ? 3 : 1) rk45_p
   };
   // raw halo values of my pair for stage parity b: (odd cell of thread tid-1, even cell of thread tid+1)
   auto halo_load = [&](int b, int f, double& hm, double& hp) {
-    if (HS) {
-      hm = __shfl_up_sync(0xffffffffu, c[f][1], 1);
-      hp = __shfl_down_sync(0xffffffffu, c[f][0], 1);
-      const double* e = sO + b * kEdgeStride;
-      if (lane_id == 0 && warp_id > 0) hm = e[((warp_id - 1) * 2 + 1) * 5 + f];
-      if (lane_id == 31) hp = e[((warp_id + 1) * 2) * 5 + f];
-    } else {
-      hm = haloM[(b * 5 + f) * TP];
-      hp = haloP[(b * 5 + f) * TP];
-    }
+    hm = haloM[(b * 5 + f) * TP];
+    hp = haloP[(b * 5 + f) * TP];
   };
   auto Kst = [&](int s, int f, double v0, double v1) { sK[(s * 5 + f) * TP] = make_double2(v0, v1); };
   auto Kld = [&](int s, int f) -> double2 { return sK[(s * 5 + f) * TP]; };
-  // the state y of the thread's two cells: registers, or (YS builds) one double2 per field in shared memory
-  auto Yld = [&](int f) -> double2 { return YS ? sY[f * TP] : make_double2(y[f][0], y[f][1]); };
-  auto K1ld = [&](int f) -> double2 { return YS ? sY[(5 + f) * TP] : make_double2(k1[f][0], k1[f][1]); };
+  // the state y and K1 of the thread's two cells live in registers
+  auto Yld = [&](int f) -> double2 { return make_double2(y[f][0], y[f][1]); };
+  auto K1ld = [&](int f) -> double2 { return make_double2(k1[f][0], k1[f][1]); };
   auto K1st = [&](int f, double v0, double v1) {
-    if (YS) {
-      sY[(5 + f) * TP] = make_double2(v0, v1);
-    } else {
-      k1[f][0] = v0;
-      k1[f][1] = v1;
-    }
+    k1[f][0] = v0;
+    k1[f][1] = v1;
   };
   auto Yst = [&](int f, double v0, double v1) {
-    if (YS) {
-      sY[f * TP] = make_double2(v0, v1);
-    } else {
-      y[f][0] = v0;
-      y[f][1] = v1;
-    }
+    y[f][0] = v0;
+    y[f][1] = v1;
   };
 
   // scipy _step_impl: min_step = 10 * |nextafter(t, inf) - t| ; clamp h_abs at the start of a step
@@ -642,7 +526,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, TP <= 128 ? 3 : 1) rk45_p
           bs.init(t, t_new);
         }
         for (;;) {
-          double* const scr = sE + buf * TP + slot * Hc;   // (HS builds: sE is exactly this 2 x TP scratch)
+          double* const scr = sE + buf * TP + slot * Hc;
           if (working) {
             double v = event_partial(k, (xeval - t) / h);
             for (int o = G >> 1; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(gmask, v, o));
@@ -700,7 +584,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, TP <= 128 ? 3 : 1) rk45_p
       // the part of the RHS that needs no neighbour runs while the barrier that publishes the neighbours'
       // stage inputs (arrived at below, at the end of the previous trip) is still pending
       OwnTerms own;
-      PairFlags fl = rhs_pair_own<rhs_schedule(kSchedLean)>(kc, tb, c, in_mask, own);
+      PairFlags fl = rhs_pair_own<rhs_schedule(kSchedLean), VD>(kc, tb, c, in_mask, own);
       if (i > i0) {
         mbar_wait(sBar, bar_parity);
         bar_parity ^= 1u;
@@ -720,7 +604,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, TP <= 128 ? 3 : 1) rk45_p
           phi[f] = c[f][1];
         }
       }
-      rhs_pair_finish(kc, c, mlo, phi, own, r);
+      rhs_pair_finish<VD>(kc, c, mlo, phi, own, r);
       U[0] = own.U[0];
       U[1] = own.U[1];
       W[0] = own.W[0];
@@ -960,29 +844,23 @@ static void choose_quanta(Rk45Args& a, int slots) {
 }
 
 #ifndef MARLPDE_HOST_EMU
-template <int TP, bool YS, bool HS>
+template <int TP, bool VD>
 static cudaError_t launch_t(const Rk45Args& a, int sm_count, int smem_budget, cudaStream_t stream) {
   Rk45Args args = a;
-  args.C = columns_per_cta_t<TP, YS, HS>(a.N, smem_budget);
+  args.C = columns_per_cta_t<TP>(a.N, smem_budget);
   if (args.C <= 0) return cudaErrorInvalidValue;
   const int Hc = (a.N + 1) / 2;
   args.logG = group_log2(Hc);
-  const size_t smem = Smem<TP, YS, HS>::total(args.C);
-  cudaError_t e = cudaFuncSetAttribute(rk45_persistent_kernel<TP, YS, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = Smem<TP>::total(args.C);
+  cudaError_t e = cudaFuncSetAttribute(rk45_persistent_kernel<TP, VD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  int grid = MARLPDE_TAIL_SPREAD ? a.n_columns : (a.n_columns + args.C - 1) / args.C;
-  int per_sm = 1;
-  if (TP <= 128) {   // small CTAs: as many as fit side by side on an SM (registers: 3 at 168 per thread)
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rk45_persistent_kernel<TP, YS, HS>, ((args.C * Hc + 31) / 32) * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-  }
-  if (grid > sm_count * per_sm) grid = sm_count * per_sm;
+  int grid = (a.n_columns + args.C - 1) / args.C;
+  if (grid > sm_count) grid = sm_count;
   if (grid < 1) grid = 1;
   const int threads = ((args.C * Hc + 31) / 32) * 32;
   choose_quanta(args, grid * args.C);
   args.warp_perm = rk45_warp_perm(threads / 32);
-  rk45_persistent_kernel<TP, YS, HS><<<grid, threads, smem, stream>>>(args);
+  rk45_persistent_kernel<TP, VD><<<grid, threads, smem, stream>>>(args);
   return cudaGetLastError();
 }
 
@@ -1007,17 +885,8 @@ cudaError_t launch_rk45(double* d_y, const marlpde_column_params* d_params, marl
   a.quantum = 0;
   a.warp_perm = 0;
   a.opt = opt;
-  if (rk45_variant() == 450 && rk45_quad_columns_per_cta(n_cells, smem_budget) > 0)
-    return launch_rk45_quad(d_y, d_params, d_state, n_columns, n_cells, opt, d_t_eval, d_snap, d_ev_counts, d_ev_times,
-                            d_queue, sm_count, smem_budget, stream);
-  switch (rk45_variant()) {
-    case 128: if (n_cells <= 256) return launch_t<128, false, false>(a, sm_count, smem_budget / 3 - 1024, stream); break;
-    case 129: if (n_cells <= 256) return launch_t<128, true, false>(a, sm_count, smem_budget / 3 - 1024, stream); break;
-    case 321: return launch_t<320, true, false>(a, sm_count, smem_budget, stream);
-    case 416: return launch_t<416, true, true>(a, sm_count, smem_budget, stream);
-    default: break;
-  }
-  return launch_t<320, false, false>(a, sm_count, smem_budget, stream);
+  if (opt.flags & MARLPDE_FLAG_VAR_DPHI) return launch_t<kRk45Threads, true>(a, sm_count, smem_budget, stream);
+  return launch_t<kRk45Threads, false>(a, sm_count, smem_budget, stream);
 }
 
 #endif

@@ -31,7 +31,9 @@
 #include <cstring>
 #include <mutex>
 
+#include "brent.cuh"
 #include "dopri.cuh"
+#include "events.cuh"
 #include "lheureux_device.cuh"
 #include "mbar.cuh"
 #include "rk45_streaming.cuh"
@@ -53,6 +55,9 @@ struct Ctl {                                   // per-column control block (doub
   int fresh;                                   // 1: K1 has just been evaluated, no attempt finished yet
   int midstep;                                 // resumed inside a step (after a rejected attempt)
   int ysl;                                     // tile path: which buffer holds y (0: caller's y, 1: workspace vector 0)
+  int locate;                                  // events: 1 = the accepted step in flight has a sign change; the attempt
+                                               // is replayed with K3..K6 stored, then its roots are located and it commits
+  unsigned ev_prev;                            // predicate bits of the monitors at the start of the current step
   int pad;
 };
 
@@ -66,6 +71,9 @@ struct Args {
   double* tile;              // [2][B][5][N]
   double* partials;          // [B][tiles]
   Ctl* ctl;                  // [2][B]
+  unsigned* evpart;          // [B][tiles] predicate bits of the monitors per CTA / window (MARLPDE_FLAG_EVENTS)
+  int32_t* ev_counts;        // [B][7]
+  double* ev_times;          // [B][7][event_capacity]
   int B, N, tiles;
   int tiles2;                // overlapped-tile path: attempt tiles per column (0: one launch per stage)
   marlpde_rk45_options opt;
@@ -74,7 +82,7 @@ struct Args {
 __host__ __device__ inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 struct Layout {
-  size_t off_K, off_tile, off_part, off_ctl, total;
+  size_t off_K, off_tile, off_part, off_ctl, off_ev, total;
 };
 __host__ inline Layout layout(int B, int N) {
   const size_t vec = sizeof(double) * 5 * (size_t)N * B;
@@ -85,6 +93,7 @@ __host__ inline Layout layout(int B, int N) {
   L.off_tile = o;  o += align256(2 * vec);
   L.off_part = o;  o += align256(sizeof(double) * (size_t)tiles * B);
   L.off_ctl = o;   o += align256(sizeof(Ctl) * 2 * (size_t)B);
+  L.off_ev = o;    o += align256(sizeof(unsigned) * (size_t)tiles * B);
   L.total = o;
   return L;
 }
@@ -133,6 +142,8 @@ __global__ void init_kernel(const Args A) {
   c.midstep = s.status == MARLPDE_STATUS_STEP_BUDGET_MIDSTEP ? 1 : 0;
   c.rejected = c.midstep;
   c.ysl = 0;
+  c.locate = 0;
+  c.ev_prev = 0u;
   c.pad = 0;
   if (s.t >= A.opt.t_bound) {
     c.active = 0;
@@ -202,6 +213,92 @@ __global__ void __launch_bounds__(kThreads) copyback_kernel(const Args A, int pa
   }
 }
 
+// ---- event location (ivp.py handle_events -> solve_event_equation: brentq on the dense output of the step), run by
+// ONE CTA of the column: the monitor value at y(t + x h) is a min over all cells of the quartic interpolant (K1, K3..K6,
+// K7 and y of the step that has just been recomputed with all its stage derivatives stored).  Same arithmetic as
+// rk45_persistent.cu::event_partial, so both paths locate the same roots.  All threads of the CTA call this.
+__device__ void locate_events(const Args& A, const Ctl& c, int col, unsigned act, const fm::Tables& tb) {
+  __shared__ ColumnConsts kc;
+  __shared__ double redm[kThreads / 32];
+  const int N = A.N;
+  const size_t vec = (size_t)A.B * 5 * N;
+  if (threadIdx.x == 0) make_consts(A.params[col], N, kc);
+  __syncthreads();
+  const size_t cb = (size_t)col * 5 * N;
+  const double* const Kp[6] = {A.K + (size_t)c.k1 * vec + cb, A.K + 2 * vec + cb, A.K + 3 * vec + cb,
+                               A.K + 4 * vec + cb,           A.K + 5 * vec + cb, A.K + (size_t)c.k7 * vec + cb};
+  const double* const yo = ybuf(A, c.ysl) + cb;
+  auto interp = [&](int f, int cell, double x) -> double {
+    const size_t o = (size_t)f * N + cell;
+    double qq[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double sacc = dp::P[0][j] * Kp[0][o];
+      sacc = fma(dp::P[2][j], Kp[1][o], sacc);
+      sacc = fma(dp::P[3][j], Kp[2][o], sacc);
+      sacc = fma(dp::P[4][j], Kp[3][o], sacc);
+      sacc = fma(dp::P[5][j], Kp[4][o], sacc);
+      qq[j] = fma(dp::P[6][j], Kp[5][o], sacc);
+    }
+    const double poly = x * (qq[0] + x * (qq[1] + x * (qq[2] + x * qq[3])));
+    return fma(c.h, poly, yo[o]);
+  };
+  while (act) {
+    const int k = __ffs(act) - 1;
+    act &= act - 1u;
+    BrentState bs;
+    bs.init(c.t, c.t_new);
+    double xeval = c.t;
+    for (;;) {
+      const double x = (xeval - c.t) / c.h;
+      double v = INFINITY;
+      for (int cell = threadIdx.x; cell < N; cell += kThreads) {
+        double w;
+        if (k == 0) {
+          w = fmin(fmin(fmin(interp(0, cell, x), interp(1, cell, x)), fmin(interp(2, cell, x), interp(3, cell, x))),
+                   interp(4, cell, x));
+        } else if (k == 1) {
+          w = interp(0, cell, x);
+        } else if (k == 2) {
+          w = interp(1, cell, x);
+        } else if (k == 3) {
+          w = -(interp(0, cell, x) + interp(1, cell, x));
+        } else {
+          const double Phi = interp(4, cell, x);
+          if (k == 4) {
+            w = -Phi;
+          } else {
+            const double F = 1.0 - fm::exp(tb, fma(-10.0, fm::rcp3(Phi), 10.0));
+            const double Phi2 = Phi * Phi;
+            w = k == 5 ? fma(kc.rhorat * (Phi2 * Phi), F * fm::rcp3(1.0 - Phi), kc.presum)
+                       : -fma(-kc.rhorat * Phi2, F, kc.presum);
+          }
+        }
+        v = fmin(v, w);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+      __syncthreads();                                      // the previous round's redm reads are done
+      if ((threadIdx.x & 31) == 0) redm[threadIdx.x >> 5] = v;
+      __syncthreads();
+      double mval = redm[0];
+      for (int w = 1; w < kThreads / 32; ++w) mval = fmin(mval, redm[w]);
+      const double g = (k == 3 || k == 4) ? (-mval) - 1.0 : (k == 6 ? -mval : mval);
+      double root = 0.0;
+      if (bs.feed(g, xeval, root)) {                        // (uniform: every thread holds the same state)
+        if (threadIdx.x == 0) {
+          int32_t* cnt = A.ev_counts + (size_t)col * MARLPDE_NEVENTS + k;
+          const int n = *cnt;
+          if (n < A.opt.event_capacity)
+            A.ev_times[((size_t)col * MARLPDE_NEVENTS + k) * A.opt.event_capacity + n] = root;
+          *cnt = n + 1;
+        }
+        break;
+      }
+    }
+  }
+}
+
 // ---- prepare: close the previous attempt of every column (error norm -> accept/reject -> new h,
 // dense output, y <- y_new, FSAL slot swap) and form the stage-2 input of the next attempt.
 // Reads control buffer `pin`, writes `pin ^ 1`.
@@ -214,6 +311,7 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin
   const size_t vec = (size_t)A.B * 5 * N;
   Ctl c = A.ctl[(size_t)pin * A.B + m.col];
   const bool publisher = blockIdx.x == m.col * A.tiles && threadIdx.x == 0;
+  const bool ev_on = (A.opt.flags & MARLPDE_FLAG_EVENTS) != 0;
   if (!c.active) {
     if (publisher) A.ctl[(size_t)(pin ^ 1) * A.B + m.col] = c;
     return;
@@ -230,7 +328,34 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin
     const double err_norm = sqrt(sum / (double)(5 * N));
     c.nfev += 6;
     c.attempts += 1;
-    if (err_norm < 1.0) {
+    // ---- event monitors (MARLPDE_FLAG_EVENTS): sign classes of the 7 monitors at y_new from the per-window predicate
+    // bits the attempt kernel left behind; every CTA of the column derives the same decision
+    bool replay = false;
+    unsigned ev_new = 0u;
+    if (ev_on && err_norm < 1.0) {
+      const unsigned* evp = A.evpart + (size_t)m.col * A.tiles;
+      for (int i = 0; i < n_part; ++i) ev_new |= evp[i];
+      unsigned act = 0u;
+      if (ev_new != c.ev_prev || (ev_new & kEqBitsMask) != 0u)
+        act = active_events(event_classes(c.ev_prev), event_classes(ev_new));
+      if (act) {
+        if (c.locate == 0) {
+          // first sight: the attempt ran without storing K3..K6.  Do not commit; the next launch repeats the very same
+          // attempt (same y, K1, h) with all stage derivatives stored, then the roots are located below.
+          c.locate = 1;
+          replay = true;
+          c.nfev -= 6;
+          c.attempts -= 1;
+        } else {
+          if (blockIdx.x == m.col * A.tiles) locate_events(A, c, m.col, act, tb);   // CTA-uniform
+          c.locate = 0;
+        }
+      }
+    }
+    if (replay) {
+      // nothing changes: same step again
+    } else if (err_norm < 1.0) {
+      if (ev_on) c.ev_prev = ev_new;
       double factor = dp::MAX_FACTOR;
       if (err_norm != 0.0) factor = fmin(dp::MAX_FACTOR, dp::SAFETY * fm::exp(tb, -0.2 * fm::log(tb, err_norm)));
       if (c.rejected) factor = fmin(1.0, factor);
@@ -313,6 +438,12 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin
     }
   } else {
     c.fresh = 0;
+    if (ev_on) {                               // monitors at the start point (ivp.py: g = event(t0, y0)), from the K1 launch
+      const unsigned* evp = A.evpart + (size_t)m.col * A.tiles;
+      unsigned b = 0u;
+      for (int i = 0; i < A.tiles; ++i) b |= evp[i];
+      c.ev_prev = b;
+    }
     if (c.nfev == 0) c.nfev = 1;               // K1 of a resumed column replaces the FSAL value: not counted again
     if (!c.midstep) begin_step(c, A.opt);      // a mid-step resume continues the step it was in
     c.midstep = 0;
@@ -431,7 +562,8 @@ __global__ void __launch_bounds__(kThreads, 3) stage_kernel(const Args A, int i,
   const bool in_mask[2] = {m.cell0 >= kc.mask_lo && m.cell0 < kc.mask_hi,
                            m.cell0 + 1 >= kc.mask_lo && m.cell0 + 1 < kc.mask_hi};
   double r[5][2], U[2], W[2];
-  PairFlags fl = rhs_pair<rhs_schedule(kSchedSplit)>(kc, tb, cc, mlo, phi, in_mask, r, U, W);
+  // (kVarDPhi = true: bit-identical for columns without MARLPDE_MODEL_VAR_DPHI; this kernel is bound by HBM traffic)
+  PairFlags fl = rhs_pair<rhs_schedule(kSchedSplit), true>(kc, tb, cc, mlo, phi, in_mask, r, U, W);
   fl.bad[0] = fl.bad[0] && m.v0;
   fl.bad[1] = fl.bad[1] && m.v1;
   if (fl.bad[0] || fl.bad[1]) rhs_pair_fixup(kc, tb, fl, cc, mlo, phi, in_mask, r, U, W);
@@ -442,6 +574,17 @@ __global__ void __launch_bounds__(kThreads, 3) stage_kernel(const Args A, int i,
     double* K1 = Kslot(1);
 #pragma unroll
     for (int f = 0; f < 5; ++f) st2(K1, m, f, N, r[f][0], r[f][1]);
+    if (A.opt.flags & MARLPDE_FLAG_EVENTS) {               // monitor signs at the start point (U, W come with K1)
+      __shared__ unsigned sbits[kThreads / 32];
+      const unsigned bw = __reduce_or_sync(0xffffffffu, event_bits_sel(cc, U, W, m.v0, m.v1));
+      if ((threadIdx.x & 31) == 0) sbits[threadIdx.x >> 5] = bw;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned b = 0u;
+        for (int w = 0; w < kThreads / 32; ++w) b |= sbits[w];
+        A.evpart[(size_t)m.col * A.tiles + (blockIdx.x - m.col * A.tiles)] = b;
+      }
+    }
   } else if (i < 6) {
     double* Kn = Kslot(i + 1);
     const double hn = h * kNew[i];
@@ -501,6 +644,8 @@ struct TileSmem {
 };
 static_assert(TileSmem::off_stage % 16 == 0 && TileSmem::total <= 227 * 1024, "tile kernel shared memory");
 
+// VD: batches with MARLPDE_MODEL_VAR_DPHI columns (opt.flags & MARLPDE_FLAG_VAR_DPHI); EV: MARLPDE_FLAG_EVENTS
+template <bool VD, bool EV>
 __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Args A, int cbuf) {
   MARLPDE_DYN_SMEM(smem_raw);
   constexpr int TP = kTileThreads;
@@ -620,7 +765,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
   for (int i = 1; i <= 6; ++i) {
     // the neighbour-free part of the RHS overlaps the pending barrier (see rk45_persistent.cu)
     OwnTerms own;
-    PairFlags fl = rhs_pair_own<rhs_schedule(kSchedLean)>(kc, tb, c, in_mask, own);
+    PairFlags fl = rhs_pair_own<rhs_schedule(kSchedLean), VD>(kc, tb, c, in_mask, own);
     if (i > 1) {
       mbar_wait(sBar, bar_parity);
       bar_parity ^= 1u;
@@ -640,7 +785,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
         phi[f] = tid == TP - 1 ? c[f][1] : hp;
       }
     }
-    rhs_pair_finish(kc, c, mlo, phi, own, r);
+    rhs_pair_finish<VD>(kc, c, mlo, phi, own, r);
     U[0] = own.U[0];
     U[1] = own.U[1];
     W[0] = own.W[0];
@@ -710,7 +855,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
     if (i < 6) mbar_arrive(sBar);
   }
   // ---- r = K7 = f(y_new), c = y_new: error contribution of the cells this window owns, write-back
-  const bool sample = c0.next_eval < A.opt.n_eval && A.t_eval[c0.next_eval] <= c0.t_new;   // dense output pending
+  // K3..K6 go to HBM only when the dense output will be needed: a t_eval sample inside the step, or the replay of a
+  // step whose events are about to be located
+  const bool sample = (c0.next_eval < A.opt.n_eval && A.t_eval[c0.next_eval] <= c0.t_new) || (EV && c0.locate != 0);
   double part = 0.0;
   double* const ynew = ybuf(A, c0.ysl ^ 1);                  // the y buffer that is not in use
   double* const K7g = Kslot(7);
@@ -759,6 +906,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
   if ((tid & 31) == 0) red[tid >> 5] = part;
+  if constexpr (EV) {     // predicate bits of the monitors at y_new over the cells this window owns (U, W come with K7)
+    const unsigned bw = __reduce_or_sync(0xffffffffu, event_bits_sel(c, U, W, out0, out1));
+    if ((tid & 31) == 0) reinterpret_cast<unsigned*>(red + kTileThreads / 32)[tid >> 5] = bw;
+  }
 #if MARLPDE_TILE_TMA
   if (tma) fence_proxy_async();                              // my staged values, for the bulk stores after the barrier
 #endif
@@ -767,6 +918,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
     double s = 0.0;
     for (int w = 0; w < kTileThreads / 32; ++w) s += red[w];
     A.partials[(size_t)col * A.tiles2 + tile] = s;
+    if constexpr (EV) {
+      unsigned b = 0u;
+      for (int w = 0; w < kTileThreads / 32; ++w) b |= reinterpret_cast<unsigned*>(red + kTileThreads / 32)[w];
+      A.evpart[(size_t)col * A.tiles + tile] = b;
+    }
 #if MARLPDE_TILE_TMA
     if (tma) {                                               // the cells this window owns: window positions [6, 634) inside the column
       const int olo = w0 + kTileHalo, ohi = olo + kTileValid < N ? olo + kTileValid : N;
@@ -794,9 +950,16 @@ struct GraphKey {             // everything a captured batch depends on (compare
 };
 }  // namespace
 
+template <bool VD, bool EV>
+static cudaError_t tile_kernel_smem() {
+  return cudaFuncSetAttribute(st::tile_attempt_kernel<VD, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)st::TileSmem::total);
+}
+
 cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_params, marlpde_column_state* d_state,
                                int n_columns, int n_cells, const marlpde_rk45_options& opt, const double* d_t_eval,
-                               double* d_snap, void* d_work, long long attempts, cudaStream_t stream) {
+                               double* d_snap, int32_t* d_ev_counts, double* d_ev_times, void* d_work,
+                               long long attempts, cudaStream_t stream) {
   const st::Layout L = st::layout(n_columns, n_cells);
   unsigned char* w = static_cast<unsigned char*>(d_work);
   st::Args a;
@@ -810,6 +973,9 @@ cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_param
   a.tile = reinterpret_cast<double*>(w + L.off_tile);
   a.partials = reinterpret_cast<double*>(w + L.off_part);
   a.ctl = reinterpret_cast<st::Ctl*>(w + L.off_ctl);
+  a.evpart = reinterpret_cast<unsigned*>(w + L.off_ev);
+  a.ev_counts = d_ev_counts;
+  a.ev_times = d_ev_times;
   a.B = n_columns;
   a.N = n_cells;
   a.tiles = (n_cells + st::kCellsPerCta - 1) / st::kCellsPerCta;
@@ -826,10 +992,17 @@ cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_param
   if (use_tiles) {
     a.tiles2 = (n_cells + st::kTileValid - 1) / st::kTileValid;
     tgrid = (unsigned)((long long)a.tiles2 * n_columns);
-    cudaError_t e = cudaFuncSetAttribute(st::tile_attempt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)st::TileSmem::total);
+    cudaError_t e = tile_kernel_smem<false, false>();
+    if (e == cudaSuccess) e = tile_kernel_smem<false, true>();
+    if (e == cudaSuccess) e = tile_kernel_smem<true, false>();
+    if (e == cudaSuccess) e = tile_kernel_smem<true, true>();
     if (e != cudaSuccess) return e;
   }
+  const bool var_dphi = (opt.flags & MARLPDE_FLAG_VAR_DPHI) != 0;
+  const bool ev_on = (opt.flags & MARLPDE_FLAG_EVENTS) != 0;
+  // (the replay-and-locate protocol of prepare_kernel relies on the y ping-pong of the tile path: in the
+  //  one-launch-per-stage variant an accepted step overwrites y while another CTA would still read it)
+  if (ev_on && !use_tiles) return cudaErrorNotSupported;
   auto enqueue = [&](cudaStream_t s_) -> cudaError_t {
     MARLPDE_LAUNCH(st::init_kernel, cgrid, 128, 0, s_, a);
     MARLPDE_LAUNCH(st::stage_kernel, grid, st::kThreads, 0, s_, a, 0, 0);            // K1 = f(y)
@@ -838,7 +1011,13 @@ cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_param
     for (long long j = 0; j < attempts; ++j) {
       MARLPDE_LAUNCH(st::prepare_kernel, grid, st::kThreads, 0, s_, a, pin);
       if (use_tiles) {
-        MARLPDE_LAUNCH(st::tile_attempt_kernel, tgrid, st::kTileThreads, st::TileSmem::total, s_, a, pin ^ 1);
+#define MARLPDE_TILE_LAUNCH(VD_, EV_) \
+  MARLPDE_LAUNCH((st::tile_attempt_kernel<VD_, EV_>), tgrid, st::kTileThreads, st::TileSmem::total, s_, a, pin ^ 1)
+        if (var_dphi && ev_on) MARLPDE_TILE_LAUNCH(true, true);
+        else if (var_dphi) MARLPDE_TILE_LAUNCH(true, false);
+        else if (ev_on) MARLPDE_TILE_LAUNCH(false, true);
+        else MARLPDE_TILE_LAUNCH(false, false);
+#undef MARLPDE_TILE_LAUNCH
       } else {
         for (int i = 1; i <= 6; ++i) MARLPDE_LAUNCH(st::stage_kernel, grid, st::kThreads, 0, s_, a, i, pin ^ 1);
       }
@@ -851,11 +1030,13 @@ cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_param
     return cudaGetLastError();
   };
 #ifndef MARLPDE_HOST_EMU
-  // MARLPDE_RK45_STREAM_GRAPH=1 (off by default; not measured yet): the launches of a batch are captured once into a CUDA graph
-  // and replayed — a batch of a few columns is bound by launch latency (two dependent launches per attempt), and the host
-  // driver repeats identical batches (all step state lives in device memory, the kernel arguments do not change).
+  // The launches of a batch are captured once into a CUDA graph and replayed — a batch of a few columns is bound by launch
+  // latency (two dependent launches per attempt), and the host drivers repeat identical batches (all step state lives in
+  // device memory, the kernel arguments do not change).  Measured (r02a, profiles/r02a_ab_candidates.log): N = 20 000 x 1
+  // 37.3 -> 42.0 k attempts/s, N = 2 000 x 8 299 -> 353 k, N = 20 000 x 64 234.5 -> 238.3 k.  MARLPDE_RK45_STREAM_GRAPH=0
+  // launches kernel by kernel.
   const char* graph_env = std::getenv("MARLPDE_RK45_STREAM_GRAPH");
-  if (graph_env && graph_env[0] == '1' && attempts <= 1024) {
+  if (!(graph_env && graph_env[0] == '0') && attempts <= 1024) {
     static std::mutex mu;
     static struct { bool valid; GraphKey key; cudaGraphExec_t exec; cudaStream_t cap; } cache = {false, {}, nullptr, nullptr};
     std::lock_guard<std::mutex> lock(mu);

@@ -24,7 +24,12 @@ class LMAHeureuxPorosityDiff:
                  CA0, CC0, cCa0, cCO30, Phi0, sedimentationrate, Xstar, Tstar,
                  k1, k2, k3, k4, m1, m2, n1, n2, b, beta, rhos, rhow, rhos0,
                  KA, KC, muA, D0Ca, PhiNR, PhiInfty, PhiIni, DCa, DCO3,
-                 FV_switch):
+                 FV_switch, time_varying_dPhi=False):
+        # `time_varying_dPhi` is not an upstream argument: upstream switches between the fixed porosity diffusion
+        # coefficient and dPhi = auxcon F Phi^3 / (1 - Phi) by (un)commenting a source line (:222-223, :430-431);
+        # here it is a kernel template flag selected per column.  A `pde_parms` dictionary without the key behaves
+        # exactly like upstream's shipped source.
+        self.time_varying_dPhi = bool(time_varying_dPhi)
         self.no_fields = 5
         self.Depths = Depths
         # accepted for signature compatibility (reference :19-22); the stencils are in the kernel
@@ -61,7 +66,8 @@ class LMAHeureuxPorosityDiff:
                    Xstar=Xstar, Tstar=Tstar, k1=k1, k2=k2, k3=k3, k4=k4, m1=m1, m2=m2, n1=n1, n2=n2, b=b,
                    beta=beta, rhos=rhos, rhow=rhow, rhos0=rhos0, KA=KA, KC=KC, muA=muA, D0Ca=D0Ca,
                    PhiNR=PhiNR, PhiInfty=PhiInfty, PhiIni=PhiIni, DCa=DCa, DCO3=DCO3, FV_switch=FV_switch,
-                   N=n, max_depth=(lo_hi[1] - lo_hi[0]) * Xstar, ShallowLimit=0.0, DeepLimit=0.0)
+                   N=n, max_depth=(lo_hi[1] - lo_hi[0]) * Xstar, ShallowLimit=0.0, DeepLimit=0.0,
+                   time_varying_dPhi=self.time_varying_dPhi)
         self.column_params = _mb.derive_column_params(pde)
         # the masks are given as arrays (Evolve_scenario.py:51-54): the kernel wants their support interval
         mask = self.not_too_shallow * self.not_too_deep

@@ -18,6 +18,8 @@ NEVENTS = 7
 STATUS_FINISHED, STATUS_STEP_TOO_SMALL, STATUS_NONFINITE, STATUS_STEP_BUDGET = 0, -1, -2, 1
 FLAG_EVENTS = 1
 FLAG_QUEUE_LOCKS = 2
+FLAG_VAR_DPHI = 4
+MODEL_VAR_DPHI = 1
 
 
 class ColumnParams(C.Structure):
@@ -28,7 +30,8 @@ class ColumnParams(C.Structure):
                 ("nu1", C.c_double), ("nu2", C.c_double), ("m1", C.c_double), ("m2", C.c_double),
                 ("n1", C.c_double), ("n2", C.c_double), ("dPhi_fixed", C.c_double),
                 ("Peclet_min", C.c_double), ("Peclet_max", C.c_double), ("FV_switch", C.c_int32),
-                ("mask_lo", C.c_int32), ("mask_hi", C.c_int32), ("reserved", C.c_int32)]
+                ("mask_lo", C.c_int32), ("mask_hi", C.c_int32), ("model_flags", C.c_int32),
+                ("auxcon", C.c_double)]
 
 
 class RK45Options(C.Structure):
@@ -55,7 +58,7 @@ PARAMS_DTYPE = np.dtype([("bc_top", "<f8", (5,)), ("dx", "<f8"), ("inv_dx", "<f8
                          ("KRat", "<f8"), ("nu1", "<f8"), ("nu2", "<f8"), ("m1", "<f8"), ("m2", "<f8"),
                          ("n1", "<f8"), ("n2", "<f8"), ("dPhi_fixed", "<f8"), ("Peclet_min", "<f8"),
                          ("Peclet_max", "<f8"), ("FV_switch", "<i4"), ("mask_lo", "<i4"),
-                         ("mask_hi", "<i4"), ("reserved", "<i4")])
+                         ("mask_hi", "<i4"), ("model_flags", "<i4"), ("auxcon", "<f8")])
 STATE_DTYPE = np.dtype([("t", "<f8"), ("h_abs", "<f8"), ("n_accepted", "<i8"), ("n_rejected", "<i8"),
                         ("nfev", "<i8"), ("status", "<i4"), ("next_eval", "<i4")])
 assert PARAMS_DTYPE.itemsize == C.sizeof(ColumnParams)
@@ -76,7 +79,11 @@ SYMBOLS = {
     "marlpde_rhs_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int]),
     "marlpde_rk45_integrate_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(RK45Options),
                                              _P, _P, _P, _P, _P, _P]),
+    "marlpde_rk45_integrate_async": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(RK45Options), _P, _P, _P, _P,
+                                               C.c_int, _P]),
     "marlpde_rk45_stream_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "marlpde_rk45_stream_integrate_events_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(RK45Options),
+                                                           _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "marlpde_rk45_stream_integrate_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(RK45Options),
                                                     _P, _P, _P, C.c_size_t, _P]),
     "marlpde_radau_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
@@ -84,6 +91,8 @@ SYMBOLS = {
                                               _P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P]),
     "marlpde_radau_integrate": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(RK45Options),
                                           _P, _P, _P, _P, _P, C.c_int]),
+    "marlpde_radau_integrate_async": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(RK45Options),
+                                                _P, _P, _P, _P, _P, C.c_int, _P]),
     "marlpde_probe_math": (C.c_int, [C.c_int, _P, C.c_int, _P, C.c_int]),
     "marlpde_probe_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "marlpde_rk45_integrate": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(RK45Options),
@@ -111,7 +120,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.marlpde_abi_version() != 1:
+        if handle.marlpde_abi_version() != 2:
             raise MarlpdeError("ABI version mismatch between _cabi.py and libmarlpde_b200.so")
         for which, struct in enumerate((ColumnParams, RK45Options, ColumnState, DeviceInfo)):
             if handle.marlpde_struct_size(which) != C.sizeof(struct):

@@ -45,6 +45,19 @@ def params_to_device(params, device):
     return torch.from_numpy(p.view(np.uint8).copy()).to(device)
 
 
+def _model_flags(params) -> int:
+    """MARLPDE_FLAG_* bits the integrators need for the model variants present in `params` (numpy records or the
+    uint8 CUDA tensor of params_to_device): MARLPDE_FLAG_VAR_DPHI when any column carries MARLPDE_MODEL_VAR_DPHI."""
+    off = PARAMS_DTYPE.fields["model_flags"][1]
+    if _is_torch(params):
+        import torch
+        words = params.view(-1, PARAMS_DTYPE.itemsize)[:, off:off + 4].contiguous().view(torch.int32)
+        any_var = bool((words & _cabi.MODEL_VAR_DPHI).any().item())
+    else:
+        any_var = bool(np.any(_as_params(params)["model_flags"] & _cabi.MODEL_VAR_DPHI))
+    return _cabi.FLAG_VAR_DPHI if any_var else 0
+
+
 def rhs_batch(y, params, out=None, device: int = 0):
     """dy/dt for every column: y[B,5,N] -> out[B,5,N] (replaces fun_numba/pde_rhs per column,
     marlpde/LHeureux_model.py:290-522)."""
@@ -143,7 +156,8 @@ def integrate_rk45_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e
     cap = int(event_capacity) if events else 0
     opts = _cabi.RK45Options(t_bound=t_bound, rtol=float(rtol), atol=float(atol), max_step=float(max_step),
                              max_steps=int(max_steps), n_eval=n_eval, event_capacity=cap,
-                             flags=(_cabi.FLAG_EVENTS if events else 0) | _cabi.FLAG_QUEUE_LOCKS, quantum=int(quantum))
+                             flags=(_cabi.FLAG_EVENTS if events else 0) | _cabi.FLAG_QUEUE_LOCKS | _model_flags(params),
+                             quantum=int(quantum))
 
     if _is_torch(y0):
         import torch
@@ -161,7 +175,7 @@ def integrate_rk45_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e
         with torch.cuda.device(dev):
             d_state = torch.from_numpy(st.view(np.uint8).copy()).to(dev)
             d_te = torch.from_numpy(t_eval_arr.copy()).to(dev) if n_eval else None
-            d_snap = torch.empty((B, n_eval, 5, N), dtype=torch.float64, device=dev)
+            d_snap = torch.full((B, n_eval, 5, N), float("nan"), dtype=torch.float64, device=dev)   # rows >= next_eval stay NaN
             d_queue = torch.zeros(1 + 2 * B, dtype=torch.int32, device=dev)   # work counter + lock word and attempt counter per column
             d_ec = torch.zeros((B, NEVENTS), dtype=torch.int32, device=dev)
             d_et = torch.full((B, NEVENTS, max(cap, 1)), float("nan"), dtype=torch.float64, device=dev)
@@ -203,25 +217,27 @@ def _stream_rk45_device(lib, y, d_params, st, opts, t_eval_arr, B, N, dev, cap, 
     with torch.cuda.device(dev):
         d_state = torch.from_numpy(st.view(np.uint8).copy()).to(dev)
         d_te = torch.from_numpy(t_eval_arr.copy()).to(dev) if n_eval else None
-        d_snap = torch.empty((B, n_eval, 5, N), dtype=torch.float64, device=dev)
+        d_snap = torch.full((B, n_eval, 5, N), float("nan"), dtype=torch.float64, device=dev)   # rows >= next_eval stay NaN
         nb = int(lib.marlpde_rk45_stream_workspace_bytes(B, N))
         d_work = torch.empty(nb // 8 + 1, dtype=torch.float64, device=dev)
+        d_ec = torch.zeros((B, NEVENTS), dtype=torch.int32, device=dev)
+        d_et = torch.full((B, NEVENTS, max(cap, 1)), float("nan"), dtype=torch.float64, device=dev)
         stream = torch.cuda.current_stream().cuda_stream
         used = 0
         while True:
             o = _cabi.RK45Options(t_bound=opts.t_bound, rtol=opts.rtol, atol=opts.atol, max_step=opts.max_step,
                                   max_steps=min(batch, budget - used) if budget > 0 else batch, n_eval=n_eval,
                                   event_capacity=opts.event_capacity, flags=opts.flags, quantum=0)
-            _cabi.check(lib.marlpde_rk45_stream_integrate_dev(
+            _cabi.check(lib.marlpde_rk45_stream_integrate_events_dev(
                 y.data_ptr(), d_params.data_ptr(), d_state.data_ptr(), B, N, C.byref(o),
-                d_te.data_ptr() if n_eval else None, d_snap.data_ptr(), d_work.data_ptr(), nb, stream))
+                d_te.data_ptr() if n_eval else None, d_snap.data_ptr(), d_ec.data_ptr(), d_et.data_ptr(),
+                d_work.data_ptr(), nb, stream))
             used += int(o.max_steps)
             st_out = d_state.cpu().numpy().view(STATE_DTYPE).reshape(B)
             if not np.any(st_out["status"] >= 1) or (budget > 0 and used >= budget):
                 break
             d_state = torch.from_numpy(st_out.view(np.uint8).copy()).to(dev)
-    ec = np.zeros((B, NEVENTS), dtype=np.int32)
-    et = np.full((B, NEVENTS, cap), np.nan)
+        ec, et = d_ec.cpu().numpy(), d_et.cpu().numpy()[:, :, :cap]
     return RK45Result(y=y, t=st_out["t"].copy(), h_abs=st_out["h_abs"].copy(), status=st_out["status"].copy(),
                       n_accepted=st_out["n_accepted"].copy(), n_rejected=st_out["n_rejected"].copy(),
                       nfev=st_out["nfev"].copy(), t_eval=t_eval_arr, snapshots=d_snap,
@@ -283,7 +299,7 @@ def integrate_radau_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1
     cap = int(event_capacity) if events else 0
     opts = _cabi.RK45Options(t_bound=t_bound, rtol=float(rtol), atol=float(atol), max_step=float(max_step),
                              max_steps=int(max_steps), n_eval=n_eval, event_capacity=cap,
-                             flags=_cabi.FLAG_EVENTS if events else 0, quantum=0)
+                             flags=(_cabi.FLAG_EVENTS if events else 0) | _model_flags(params), quantum=0)
     if _is_torch(y0):
         import torch
         if not y0.is_cuda or y0.dtype != torch.float64 or not y0.is_contiguous():
@@ -298,7 +314,7 @@ def integrate_radau_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1
         with torch.cuda.device(dev):
             d_state = torch.from_numpy(st.view(np.uint8).copy()).to(dev)
             d_te = torch.from_numpy(t_eval_arr.copy()).to(dev) if n_eval else None
-            d_snap = torch.empty((B, n_eval, 5, N), dtype=torch.float64, device=dev)
+            d_snap = torch.full((B, n_eval, 5, N), float("nan"), dtype=torch.float64, device=dev)   # rows >= next_eval stay NaN
             d_queue = torch.zeros(1, dtype=torch.int32, device=dev)
             d_stats = torch.zeros((B, 4), dtype=torch.int64, device=dev)
             d_ec = torch.zeros((B, NEVENTS), dtype=torch.int32, device=dev)

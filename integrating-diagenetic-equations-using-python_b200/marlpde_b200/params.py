@@ -11,7 +11,7 @@ from typing import Mapping
 
 import numpy as np
 
-from ._cabi import PARAMS_DTYPE
+from ._cabi import MODEL_VAR_DPHI, PARAMS_DTYPE
 
 _REQUIRED = ("CA0", "CC0", "cCa0", "cCO30", "Phi0", "sedimentationrate", "Xstar", "Tstar", "k1", "k2",
              "k3", "k4", "m1", "m2", "n1", "n2", "b", "beta", "rhos", "rhow", "rhos0", "KA", "KC",
@@ -96,6 +96,9 @@ def derive_column_params(pde: Mapping) -> np.ndarray:
     out["FV_switch"] = np.asarray(pde["FV_switch"]).astype(np.int32) != 0
     out["mask_lo"] = lo
     out["mask_hi"] = hi
+    # model variant upstream toggles by editing its source (:222-223, :430-431): dPhi = auxcon F Phi^3 / (1 - Phi)
+    out["auxcon"] = auxcon
+    out["model_flags"] = np.where(np.asarray(pde.get("time_varying_dPhi", False)).astype(bool), MODEL_VAR_DPHI, 0)
     return out
 
 

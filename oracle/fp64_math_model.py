@@ -2,8 +2,8 @@
 tables (csrc/fp64_tables.inc) — every fma is evaluated in rational arithmetic and rounded once, as the GPU does.
 
 TEST INFRASTRUCTURE ONLY.  Used by tests/test_host_side.py to check tables, constants and algorithms against mpmath
-without a GPU, for the default constants and for the experimental immediate-constant variant (MARLPDE_FP64_IMM=1:
-constants whose low 32 bits are zero).  The functions the reference evaluates through libm here are np.log / np.exp /
+without a GPU (Constants(True) models the immediate-constant variant that was measured on the B200 in r02a and dropped:
+constants whose low 32 bits are zero; kept as a record of its accuracy).  The functions the reference evaluates through libm here are np.log / np.exp /
 pow / cosh / sinh inside pde_rhs (marlpde/LHeureux_model.py:413-520)."""
 import math
 import os

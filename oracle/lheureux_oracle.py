@@ -49,7 +49,8 @@ P_NAMES = (
     "nu1", "nu2", "m1", "m2", "n1", "n2",          # 16-21
     "dPhi_fixed", "Peclet_min", "Peclet_max",      # 22-24
     "FV_switch", "mask_lo", "mask_hi",             # 25-27 (mask = 1 on cells [mask_lo, mask_hi))
-)
+    "auxcon", "var_dPhi",                          # 28-29 model variant: the line upstream keeps commented out at
+)                                                  #       LHeureux_model.py:222-223 / :430-431 (dPhi per cell)
 NP = len(P_NAMES)
 P_IDX = {n: i for i, n in enumerate(P_NAMES)}
 
@@ -149,7 +150,8 @@ def kernel_params(pde: dict) -> np.ndarray:
         lambda_=lambda_, dCa=dCa, dCO3=dCO3, delta=delta, KRat=KRat, nu1=nu1, nu2=nu2,
         m1=pde["m1"], m2=pde["m2"], n1=pde["n1"], n2=pde["n2"], dPhi_fixed=dPhi_fixed,
         Peclet_min=1e-2, Peclet_max=1 / 1e-2, FV_switch=float(pde["FV_switch"]),
-        mask_lo=float(lo), mask_hi=float(hi),
+        mask_lo=float(lo), mask_hi=float(hi), auxcon=auxcon,
+        var_dPhi=float(bool(pde.get("time_varying_dPhi", False))),
     )
     return np.array([vals[n] for n in P_NAMES], dtype=np.float64)
 
@@ -188,6 +190,7 @@ def rhs(y, p, out):
     dPhi_fixed, Peclet_min, Peclet_max = p[22], p[23], p[24]
     FV_switch = p[25] != 0.0
     mask_lo, mask_hi = int(p[26]), int(p[27])
+    auxcon, var_dPhi = p[28], p[29] != 0.0
     for i in range(N):
         # ---- ghost cells + stencils (py-pde rules; LHeureux_model.py:26-30, :372-384)
         if i > 0:
@@ -230,7 +233,10 @@ def rhs(y, p, out):
         W = presum - rhorat * Phi[i] ** 2 * F
         denominator = 1 - 2 * np.log(Phi[i])
         one_minus_Phi = 1 - Phi[i]
-        dPhi = dPhi_fixed
+        if var_dPhi:                               # :430, the commented-out time-varying coefficient
+            dPhi = auxcon * F * (Phi[i] ** 3) / one_minus_Phi
+        else:
+            dPhi = dPhi_fixed                      # :431
         if FV_switch:
             Peclet_cCa = W * delta_x * denominator / (2. * dCa)
             sigma_cCa = _sigma(Peclet_cCa, W, Peclet_min, Peclet_max)

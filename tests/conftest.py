@@ -32,6 +32,15 @@ def rhs_golden():
 
 
 @pytest.fixture(scope="session")
+def rhs_golden_vardphi():
+    """Outputs of the reference's pde_rhs / fun with its commented-out time-varying dPhi line switched on
+    (tests/golden/make_golden.py vardphi)."""
+    g = np.load(os.path.join(GOLDEN, "rhs_reference_vardphi.npz"))
+    meta = json.loads(str(g["__meta__"]))
+    return g, meta
+
+
+@pytest.fixture(scope="session")
 def stepper_golden():
     g = np.load(os.path.join(GOLDEN, "stepper_reference.npz"))
     cases = json.loads(str(g["__cases__"]))

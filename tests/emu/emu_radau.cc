@@ -1,6 +1,5 @@
 // tests/emu/emu_radau.cc — the batched Radau kernel (csrc/radau_batch.cu), compiled for the host and run by the SIMT
 // emulator: one CTA of four warps works through all columns of the queue.  TEST INFRASTRUCTURE ONLY (simt_emu.h).
-// Built twice by tests/test_emu_kernels.py: as is, and with -DMARLPDE_RADAU_FUSE_F=1.
 #include <cstdint>
 #include <vector>
 

@@ -1,4 +1,4 @@
-// tests/emu/emu_rk45.cc — the on-chip RK45 kernels (csrc/rk45_persistent.cu, csrc/rk45_quad.cu), compiled for the host
+// tests/emu/emu_rk45.cc — the on-chip RK45 kernel (csrc/rk45_persistent.cu), compiled for the host
 // and run one thread block at a time by the SIMT emulator.  TEST INFRASTRUCTURE ONLY: checks kernel control logic
 // (indexing, barriers, halo exchange, slot service, event handling) without a GPU; see simt_emu.h.
 #include <cstdint>
@@ -8,7 +8,6 @@
 #include "simt_emu.h"
 
 #include "../../integrating-diagenetic-equations-using-python_b200/csrc/rk45_persistent.cu"
-#include "../../integrating-diagenetic-equations-using-python_b200/csrc/rk45_quad.cu"
 
 extern "C" int emu_rk45(int variant, double* y, const marlpde_column_params* params, marlpde_column_state* state,
                         int n_columns, int n_cells, const marlpde_rk45_options* opt, const double* t_eval, double* snap,
@@ -20,26 +19,7 @@ extern "C" int emu_rk45(int variant, double* y, const marlpde_column_params* par
   // EMU_GRID blocks, one after the other, on the same column queue (the claim policy sees gridDim.x = EMU_GRID)
   const char* ge = std::getenv("EMU_GRID");
   const int grid = ge && std::atoi(ge) > 0 ? std::atoi(ge) : 1;
-  if (variant == 450) {
-    quad::Args a;
-    a.g_y = y;
-    a.g_params = params;
-    a.g_state = state;
-    a.g_t_eval = t_eval;
-    a.g_snap = snap;
-    a.g_queue = &queue;
-    a.g_ev_counts = ev_counts;
-    a.g_ev_times = ev_times;
-    a.n_columns = n_columns;
-    a.N = n_cells;
-    a.C = quad::columns_per_cta(n_cells, budget);
-    if (a.C <= 0) return -2;
-    a.logG = quad::group_log2(n_cells / quad::Q);
-    a.opt = *opt;
-    for (int b = 0; b < grid; ++b)
-      if (int rc = simt::run_block(quad::TP, quad::Smem::total(a.C), [&]() { quad::rk45_quad_kernel(a); }, b, grid)) return rc;
-    return 0;
-  }
+  (void)variant;
   Rk45Args a;
   a.g_y = y;
   a.g_params = params;
@@ -51,7 +31,7 @@ extern "C" int emu_rk45(int variant, double* y, const marlpde_column_params* par
   a.g_ev_times = ev_times;
   a.n_columns = n_columns;
   a.N = n_cells;
-  a.C = columns_per_cta_t<320, false, false>(n_cells, budget);
+  a.C = columns_per_cta_t<kRk45Threads>(n_cells, budget);
   if (a.C <= 0) return -2;
   const int Hc = (n_cells + 1) / 2;
   a.logG = group_log2(Hc);
@@ -64,8 +44,11 @@ extern "C" int emu_rk45(int variant, double* y, const marlpde_column_params* par
   choose_quanta(a, se && std::atoi(se) > 0 ? std::atoi(se) : grid * a.C);
   const int threads = ((a.C * Hc + 31) / 32) * 32;
   for (int b = 0; b < grid; ++b)
-    if (int rc = simt::run_block(threads, Smem<320, false, false>::total(a.C),
-                                 [&]() { rk45_persistent_kernel<320, false, false>(a); }, b, grid))
+    if (int rc = simt::run_block(threads, Smem<kRk45Threads>::total(a.C),
+                                 [&]() {
+                                   if (opt->flags & MARLPDE_FLAG_VAR_DPHI) rk45_persistent_kernel<kRk45Threads, true>(a);
+                                   else rk45_persistent_kernel<kRk45Threads, false>(a);
+                                 }, b, grid))
       return rc;
   return 0;
 }

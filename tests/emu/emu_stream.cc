@@ -11,8 +11,8 @@
 
 extern "C" int emu_rk45_stream(double* y, const marlpde_column_params* params, marlpde_column_state* state, int n_columns,
                                int n_cells, const marlpde_rk45_options* opt, const double* t_eval, double* snap,
-                               long long attempts) {
+                               long long attempts, int32_t* ev_counts, double* ev_times) {
   std::vector<unsigned char> work(marlpde::rk45_stream_workspace_bytes(n_columns, n_cells) + 256, 0);
-  return (int)marlpde::launch_rk45_stream(y, params, state, n_columns, n_cells, *opt, t_eval, snap, work.data(), attempts,
-                                          nullptr);
+  return (int)marlpde::launch_rk45_stream(y, params, state, n_columns, n_cells, *opt, t_eval, snap, ev_counts, ev_times, work.data(),
+                                          attempts, nullptr);
 }

@@ -12,6 +12,11 @@ Produces
   scenario_reference.json  asdict(Map_Scenario()) from the reference's own parameters.py
                            (imported with oracle/refstubs/pint), Solver/Tracker defaults and the
                            structure of jacobian_sparsity().
+  rhs_reference_vardphi.npz  (`python tests/golden/make_golden.py vardphi`) the same for the model variant the reference
+                           keeps as a commented-out line: the source text of /root/reference/marlpde/LHeureux_model.py
+                           is loaded, the two lines `dPhi = self.dPhi_fixed` (:223) and `dPhi[i] = dPhi_fixed` (:431)
+                           are replaced by the commented formulas one line above them (:222, :430), and the resulting
+                           module's `fun_numba` / `fun` are evaluated.  Nothing else of the reference is touched.
   rhs_reference.npz        inputs y and outputs of the reference's OWN `fun_numba` -> `pde_rhs`
                            and `fun` (LHeureux_model.py:162-522), imported unmodified from
                            /root/reference with oracle/refstubs/pde standing in for py-pde,
@@ -164,5 +169,69 @@ def main():
     print("wrote", sorted(os.listdir(HERE)))
 
 
+def reference_model_with_time_varying_dPhi():
+    """The reference's LHeureux_model module with its own commented-out dPhi formula switched on (text substitution
+    of exactly two lines at import time; the file on disk is not modified)."""
+    import types
+    src = open(os.path.join(REF, "marlpde", "LHeureux_model.py")).read()
+    a = "        # dPhi = self.auxcon * F * (Phi ** 3) / (1 - Phi)\n        dPhi = self.dPhi_fixed\n"
+    b = "            # dPhi[i] = auxcon * F[i] * (Phi[i] ** 3) / one_minus_Phi[i]\n            dPhi[i] = dPhi_fixed\n"
+    assert src.count(a) == 1 and src.count(b) == 1
+    src = src.replace(a, "        dPhi = self.auxcon * F * (Phi ** 3) / (1 - Phi)\n")
+    src = src.replace(b, "            dPhi[i] = auxcon * F[i] * (Phi[i] ** 3) / one_minus_Phi[i]\n")
+    mod = types.ModuleType("LHeureux_model_vardphi")
+    mod.__file__ = os.path.join(REF, "marlpde", "LHeureux_model.py")
+    exec(compile(src, mod.__file__, "exec"), mod.__dict__)
+    return mod
+
+
+def main_vardphi():
+    global ref_model
+    data_dir = os.path.join(REF, "tests", "Regression_test", "data")
+    A = np.asarray(hdf5lite.File(os.path.join(data_dir, "LMAHeureuxPorosityDiff_Phi0_0.6_PhiIni_0.5.hdf5"))["data"])
+    B = np.asarray(hdf5lite.File(os.path.join(data_dir, "LMAHeureuxPorosityDiff_Phi0_PhiIni_0.8.hdf5"))["data"])
+    base = asdict(ref_parameters.Map_Scenario())
+    plain = ref_model
+    ref_model = reference_model_with_time_varying_dPhi()
+    rng = np.random.default_rng(20261019)
+    out, meta = {}, {}
+    for name, over in (("default", {}), ("scenario_A", {"Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}),
+                       ("fv_off", {"Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6, "FV_switch": 0})):
+        pde = base | over
+        eq = build_reference_model(pde)
+        N = pde["N"]
+        y0 = oracle.initial_state(pde)
+        states = {"y0": y0, "noise": y0 * (1 + 0.05 * rng.uniform(-1, 1, y0.size))}
+        fix = A if name != "default" else B
+        for k in (1, 10, 100):
+            states[f"fix_{k}"] = fix[k].ravel()
+        ramp = states["noise"].copy()
+        ramp[4 * N:] = np.linspace(0.05, 0.97, N)          # dPhi spans orders of magnitude: every Peclet branch
+        states["ramp"] = ramp
+        lowphi = states["noise"].copy()
+        lowphi[4 * N:] = 0.25 + 0.1 * rng.uniform(0, 1, N)
+        states["U_negative"] = lowphi
+        for sname, y in states.items():
+            y = np.ascontiguousarray(y, dtype=np.float64)
+            eq.last_t = 0.0
+            out[f"{name}/{sname}/y"] = y
+            out[f"{name}/{sname}/rhs_numba"] = np.asarray(eq.fun_numba(0.0, y.copy(), _NoBar(), 1e-5, 0.0))
+            eq.last_t = 0.0
+            out[f"{name}/{sname}/rhs_numpy"] = np.asarray(eq.fun(0.0, y.copy(), _NoBar(), 1e-5, 0.0))
+        # how much the variant differs from the shipped model on the same state (so the test cannot pass trivially)
+        ref_model = plain
+        eq0 = build_reference_model(pde)
+        ref_model = sys.modules.get("LHeureux_model_vardphi") or reference_model_with_time_varying_dPhi()
+        eq0.last_t = 0.0
+        out[f"{name}/noise/rhs_numba_fixed_dPhi"] = np.asarray(eq0.fun_numba(0.0, np.ascontiguousarray(states["noise"]), _NoBar(), 1e-5, 0.0))
+        meta[name] = {k: (float(v) if not isinstance(v, int) else v) for k, v in pde.items()}
+    out["__meta__"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(HERE, "rhs_reference_vardphi.npz"), **out)
+    print("wrote rhs_reference_vardphi.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "vardphi":
+        main_vardphi()
+    else:
+        main()

@@ -1,6 +1,5 @@
-"""Kernel control logic on the host: the batched Radau kernel (csrc/radau_batch.cu, as is and with the experimental
--DMARLPDE_RADAU_FUSE_F=1) and the on-chip RK45 kernels (csrc/rk45_persistent.cu — the default build, validated on
-B200 — and csrc/rk45_quad.cu — the experimental 4-cells-per-thread build whose GPU parity suite has not been run yet) are compiled
+"""Kernel control logic on the host: the batched Radau kernel (csrc/radau_batch.cu), the on-chip RK45 kernel
+(csrc/rk45_persistent.cu) and the streaming RK45 path (csrc/rk45_streaming.cu) are compiled
 for the host with g++ and run one thread block at a time by a small SIMT emulator (tests/emu/: one fiber per CUDA thread,
 rendezvous at every barrier / warp collective / mbarrier wait; a missing barrier or a collective that not all named
 lanes reach is reported instead of hanging).
@@ -33,22 +32,15 @@ def emu():
     out = os.path.join(EMU, "_build")
     os.makedirs(out, exist_ok=True)
     srcs = [os.path.join(EMU, f) for f in ("emu_rk45.cc", "simt_emu.cc")]
-    # the default sources, and the experimental compile-time variants: immediate-constant fp64 maths, tail-spreading claim
-    # policy, 4-cell kernel with one RHS instance in a rolled pair loop (compiled side by side)
-    variants = {"": [], "_imm": ["-DMARLPDE_FP64_IMM=1"], "_spread": ["-DMARLPDE_TAIL_SPREAD=1"], "_rolled": ["-DMARLPDE_QUAD_ROLLED=1"]}
-    jobs = {k: subprocess.Popen(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", *flags, "-I", EMU, "-o",
-                                 os.path.join(out, f"libemu_rk45{k}.so")] + srcs, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
-            for k, flags in variants.items()}
-    libs = {}
-    for k, job in jobs.items():
-        log = job.communicate()[0]
-        assert job.returncode == 0, log.decode()
-        libs[k] = C.CDLL(os.path.join(out, f"libemu_rk45{k}.so"))
-        libs[k].emu_rk45.restype = C.c_int
-    lib, lib_imm, lib_spread, lib_rolled = libs[""], libs["_imm"], libs["_spread"], libs["_rolled"]
+    so = os.path.join(out, "libemu_rk45.so")
+    done = subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", "-I", EMU, "-o", so] + srcs,
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert done.returncode == 0, done.stdout.decode()
+    lib = C.CDLL(so)
+    lib.emu_rk45.restype = C.c_int
 
     def run(variant, P, y, t_end, t_eval=(), events=False, first_step=1e-6, max_steps=0, state=None, capacity=16,
-            quantum=None):
+            quantum=None, flags=0):
         y = np.ascontiguousarray(y, dtype=np.float64).copy()
         P = np.ascontiguousarray(P)
         B, _, N = y.shape
@@ -59,11 +51,10 @@ def emu():
         et = np.full((B, 7, capacity), np.nan)
         o = _cabi.RK45Options(t_bound=t_end, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=max_steps,
                               n_eval=te.size, event_capacity=capacity,
-                              flags=(_cabi.FLAG_EVENTS if events else 0) | (0 if quantum is None else _cabi.FLAG_QUEUE_LOCKS),
+                              flags=flags | (_cabi.FLAG_EVENTS if events else 0) | (0 if quantum is None else _cabi.FLAG_QUEUE_LOCKS),
                               quantum=quantum or 0)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
-        which = lib_rolled if variant >= 3000 else lib_spread if variant >= 2000 else lib_imm if variant >= 1000 else lib
-        rc = which.emu_rk45(variant % 1000, p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), p(ec), p(et))
+        rc = lib.emu_rk45(variant, p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), p(ec), p(et))
         assert rc == 0, f"emulated kernel {variant}: rc {rc} (deadlock or mismatched collective, see stderr)"
         return dict(y=y, state=st, snapshots=snap, event_counts=ec, event_times=et)
     return run
@@ -76,7 +67,7 @@ def test_default_kernel_under_emulation_reproduces_scipy(emu):
     """Calibration of the emulator with the kernel that is validated on the GPU."""
     pde = oracle.default_scenario() | SCEN_A
     sol = oracle.integrate(pde, method="RK45", t_span=(0, 2e-4), t_eval=[2e-4], events=False, first_step=1e-6)
-    for variant in (320, 1320, 1450):       # default kernel; default and 4-cell kernels with -DMARLPDE_FP64_IMM=1
+    for variant in (320,):
         res = emu(variant, mb.derive_column_params(pde), mb.initial_state(pde), 2e-4)
         assert res["state"]["status"][0] == 0 and res["state"]["nfev"][0] == sol.nfev, variant
         assert np.max(np.abs(res["y"][0] - sol.y.reshape(5, 200, -1)[:, :, -1])) <= 1e-12, variant
@@ -113,106 +104,21 @@ def test_quantum_major_work_items_are_bit_identical_to_whole_column_claims(emu, 
     assert np.array_equal(auto["state"]["n_accepted"], ref["state"]["n_accepted"])
 
 
-def test_quad_kernel_lattice_dense_output_and_slot_reuse(emu):
-    """Eight columns with different parameters through five slots (queue refills), rejected steps, t_eval samples: the
-    4-cells-per-thread build against the default build and against SciPy."""
-    pde = mb.sweep_lattice(oracle.default_scenario(), 2, 2, 2)
-    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
-    te = [1e-4, 2.5e-4, 4e-4]
-    ref = emu(320, P, y0, 4e-4, t_eval=te, events=True, first_step=5e-7)
-    got = emu(450, P, y0, 4e-4, t_eval=te, events=True, first_step=5e-7)
-    for k in ("nfev", "n_accepted", "n_rejected", "status", "next_eval"):
-        assert np.array_equal(got["state"][k], ref["state"][k]), k
-    assert got["state"]["n_rejected"].min() > 0
-    assert np.max(np.abs(got["y"] - ref["y"])) <= 1e-12 and np.max(np.abs(got["snapshots"] - ref["snapshots"])) <= 1e-12
-    for c in (0, 5):
-        one = {k: (float(v[c]) if np.ndim(v) else v) for k, v in pde.items()}
-        sol = oracle.integrate(one, method="RK45", t_span=(0, 4e-4), t_eval=te, events=False, first_step=5e-7)
-        want = sol.y.reshape(5, 200, -1)
-        assert got["state"]["nfev"][c] == sol.nfev
-        assert np.max(np.abs(got["snapshots"][c] - np.moveaxis(want, 2, 0))) <= 1e-12
-
-
-def test_quad_kernel_events_and_column_independence(emu):
-    """Parked steps, Brent location on the dense output, per-column event lists (the GPU test
-    test_events_synthetic_state_six_monitors_and_capacity, on the emulated experimental kernel)."""
-    pde = oracle.default_scenario() | SCEN_A
-    y0 = mb.initial_state(pde)
-    y0[0, 0, 50] = -2e-3
-    y0[0, 1, 60] = -1e-3
-    y0[0, 0, 100] = 0.705
-    y0[0, 4, 150] = 1.0005
-    t_end = 2.5e-3
-    sol = oracle.integrate(pde, method="RK45", t_span=(0, t_end), t_eval=[0, t_end], events=True, y0=y0[0])
-    want = [len(e) for e in sol.t_events]
-    assert sum(want) >= 5
-    P = mb.derive_column_params(pde)
-    Y = np.concatenate([y0, mb.initial_state(pde), y0])
-    res = emu(450, np.repeat(P, 3), Y, t_end, t_eval=[0, t_end], events=True, capacity=8)
-    assert np.all(res["state"]["status"] == 0) and res["state"]["nfev"][0] == sol.nfev
-    for c in (0, 2):
-        assert list(res["event_counts"][c]) == want
-        for k in range(7):
-            got = np.sort(res["event_times"][c, k, :want[k]])
-            assert np.allclose(got, sol.t_events[k], rtol=0, atol=1e-12)
-    assert np.all(res["event_counts"][1] == 0)
-    assert np.array_equal(res["y"][0], res["y"][2])
-    assert np.max(np.abs(res["y"][0] - sol.y.reshape(5, 200, -1)[:, :, -1])) <= 1e-10
-
-
-def test_quad_kernel_resume_is_bit_identical_and_other_grids(emu):
-    pde = oracle.default_scenario() | SCEN_A
-    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
-    te = np.linspace(0, 6e-4, 4)
-    whole = emu(450, P, y0, 6e-4, t_eval=te)
-    part = emu(450, P, y0, 6e-4, t_eval=te, max_steps=60)
-    hops = 1
-    while part["state"]["status"][0] == 1:
-        nxt = emu(450, P, part["y"], 6e-4, t_eval=te, max_steps=60, state=part["state"])
-        keep = np.isnan(nxt["snapshots"])
-        nxt["snapshots"][keep] = part["snapshots"][keep]
-        part = nxt
-        hops += 1
-    assert hops >= 3 and np.array_equal(part["y"], whole["y"]) and np.array_equal(part["snapshots"], whole["snapshots"])
-    for n_cells in (32, 64, 400):
-        p2 = pde | {"N": n_cells}
-        h0 = 1e-6 * min(1.0, (200 / n_cells) ** 2)
-        t_end = 2e-4 * min(1.0, (200 / n_cells) ** 2)
-        sol = oracle.integrate(p2, method="RK45", t_span=(0, t_end), t_eval=[t_end], events=False, first_step=h0)
-        res = emu(450, np.repeat(mb.derive_column_params(p2), 3), np.repeat(mb.initial_state(p2), 3, 0), t_end, first_step=h0)
-        assert np.all(res["state"]["nfev"] == sol.nfev), n_cells
-        assert np.max(np.abs(res["y"][1] - sol.y.reshape(5, n_cells, -1)[:, :, -1])) <= 1e-12, n_cells
-
-
-def test_quad_kernel_rolled_pair_loop_is_bit_identical(emu):
-    """-DMARLPDE_QUAD_ROLLED=1 (A/B candidate): one RHS instance serves both pairs of a thread in a rolled loop (inputs and
-    outputs change places between the trips) — same bits as the two inlined instances, events and dense output included."""
-    pde = mb.sweep_lattice(oracle.default_scenario(), 2, 2, 2)
-    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
-    a = emu(450, P, y0, 1e-4, t_eval=[5e-5, 1e-4], events=True, first_step=5e-7)
-    b = emu(3450, P, y0, 1e-4, t_eval=[5e-5, 1e-4], events=True, first_step=5e-7)
-    assert np.all(a["state"]["status"] == 0) and a["state"]["n_rejected"].min() > 0
-    assert np.array_equal(a["state"], b["state"]) and np.array_equal(a["y"], b["y"])
-    assert np.array_equal(a["snapshots"], b["snapshots"]) and np.array_equal(a["event_counts"], b["event_counts"])
-
-
-def test_tail_spread_claim_policy_processes_every_column_with_identical_results(emu, monkeypatch):
-    """-DMARLPDE_TAIL_SPREAD=1 (A/B candidate, off by default): slot s of a CTA only claims while more than s * gridDim
-    columns are left.  Eight columns on a grid of three CTAs that share one queue (run one after the other): slots that
-    decline retire for good, CTAs that find the queue empty leave at once, every column is integrated, and — results being
-    independent of the slot a column runs in — bit-identical to the default policy.  Both on-chip kernels."""
-    pde = mb.sweep_lattice(oracle.default_scenario(), 2, 2, 2)
-    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
-    te = [1e-4, 1.5e-4]
-    for variant, grids in ((320, ("3", "8")), (450, ("3",))):
-        monkeypatch.setenv("EMU_GRID", "1")
-        ref = emu(variant, P, y0, 1.5e-4, t_eval=te, events=True, first_step=5e-7)
-        for grid in grids:
-            monkeypatch.setenv("EMU_GRID", grid)
-            got = emu(2000 + variant, P, y0, 1.5e-4, t_eval=te, events=True, first_step=5e-7)
-            assert np.all(got["state"]["status"] == 0) and np.all(got["state"]["t"] == 1.5e-4), (variant, grid)
-            assert np.array_equal(got["state"], ref["state"]) and np.array_equal(got["y"], ref["y"]), (variant, grid)
-            assert np.array_equal(got["snapshots"], ref["snapshots"]) and np.array_equal(got["event_counts"], ref["event_counts"])
+def test_time_varying_dPhi_instantiation_under_emulation(emu):
+    """The kVarDPhi = true instantiation of the on-chip kernel (MARLPDE_FLAG_VAR_DPHI): a flagged column follows SciPy on
+    the oracle's model variant (LHeureux_model.py:430), a plain column in the same launch is bit-identical to the default
+    instantiation."""
+    base = oracle.default_scenario() | SCEN_A
+    var = base | {"time_varying_dPhi": True}
+    P = np.concatenate([mb.derive_column_params(var), mb.derive_column_params(base)])
+    Y = np.repeat(mb.initial_state(base), 2, 0)
+    sol = oracle.integrate(var, method="RK45", t_span=(0, 2e-4), t_eval=[2e-4], events=False, first_step=1e-6)
+    res = emu(320, P, Y, 2e-4, flags=_cabi.FLAG_VAR_DPHI)
+    ref = emu(320, P[1:], Y[1:], 2e-4)
+    assert res["state"]["nfev"][0] == sol.nfev and np.all(res["state"]["status"] == 0)
+    assert np.max(np.abs(res["y"][0] - sol.y.reshape(5, 200, -1)[:, :, -1])) <= 1e-12
+    assert np.array_equal(res["y"][1], ref["y"][0])
+    assert np.max(np.abs(res["y"][0][4] - res["y"][1][4])) > 1e-8
 
 
 # --------------------------------------------------------------------------------------- Radau kernel
@@ -222,16 +128,14 @@ def emu_radau():
         pytest.skip("g++ not available")
     out = os.path.join(EMU, "_build")
     os.makedirs(out, exist_ok=True)
-    libs = {}
-    for fuse in (0, 1):
-        so = os.path.join(out, f"libemu_radau{fuse}.so")
-        srcs = [os.path.join(EMU, f) for f in ("emu_radau.cc", "simt_emu.cc")]
-        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", f"-DMARLPDE_RADAU_FUSE_F={fuse}",
-                        "-I", EMU, "-o", so] + srcs, check=True, capture_output=True)
-        libs[fuse] = C.CDLL(so)
-        libs[fuse].emu_radau.restype = C.c_int
+    so = os.path.join(out, "libemu_radau.so")
+    srcs = [os.path.join(EMU, f) for f in ("emu_radau.cc", "simt_emu.cc")]
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", "-I", EMU, "-o", so] + srcs,
+                   check=True, capture_output=True)
+    lib = C.CDLL(so)
+    lib.emu_radau.restype = C.c_int
 
-    def run(fuse, P, y, t_end, t_eval=(), events=False, first_step=1e-6):
+    def run(P, y, t_end, t_eval=(), events=False, first_step=1e-6):
         y = np.ascontiguousarray(y, dtype=np.float64).copy()
         P = np.ascontiguousarray(P)
         B, _, N = y.shape
@@ -242,16 +146,15 @@ def emu_radau():
         o = _cabi.RK45Options(t_bound=t_end, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=0, n_eval=te.size,
                               event_capacity=16, flags=_cabi.FLAG_EVENTS if events else 0, quantum=0)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
-        rc = libs[fuse].emu_radau(p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), p(stats), p(ec), p(et))
-        assert rc == 0, f"emulated Radau kernel (fuse={fuse}): rc {rc}"
+        rc = lib.emu_radau(p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), p(stats), p(ec), p(et))
+        assert rc == 0, f"emulated Radau kernel: rc {rc}"
         return dict(y=y, state=st, snapshots=snap, stats=stats, event_counts=ec)
     return run
 
 
-def test_radau_kernel_under_emulation_and_fused_stage_evaluation(emu_radau):
+def test_radau_kernel_under_emulation(emu_radau):
     """Scenario A to T* (the reference's regression case) and a lattice of five columns through the four warps of one CTA:
-    the Radau kernel under emulation against SciPy Radau with the reference's sparsity, and the experimental fused stage
-    evaluation against the plain one (same step / LU / Newton counts, solutions equal to 1e-3 tolerance units)."""
+    the Radau kernel under emulation against SciPy Radau with the reference's sparsity."""
     pde = oracle.default_scenario() | SCEN_A
     P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
     te = np.linspace(0, 1, 11)
@@ -259,20 +162,13 @@ def test_radau_kernel_under_emulation_and_fused_stage_evaluation(emu_radau):
                            jac_sparsity=oracle.jacobian_sparsity(200))
     want = np.moveaxis(sol.y.reshape(5, 200, -1), 2, 0)
     unit = 1e-3 + 1e-3 * np.abs(want)
-    res = {f: emu_radau(f, P, y0, 1.0, t_eval=te) for f in (0, 1)}
-    for f in (0, 1):
-        assert res[f]["state"]["status"][0] == 0 and 25 <= res[f]["state"]["n_accepted"][0] <= 80
-        assert np.max(np.abs(res[f]["snapshots"][0] - want) / unit) <= 2.0      # two Radau codes at rtol = 1e-3
-    assert np.array_equal(res[0]["stats"], res[1]["stats"])
-    for k in ("n_accepted", "n_rejected", "nfev", "status", "next_eval"):
-        assert np.array_equal(res[0]["state"][k], res[1]["state"][k]), k
-    assert np.max(np.abs(res[0]["snapshots"] - res[1]["snapshots"]) / unit) <= 1e-3
+    res = emu_radau(P, y0, 1.0, t_eval=te)
+    assert res["state"]["status"][0] == 0 and 25 <= res["state"]["n_accepted"][0] <= 80
+    assert np.max(np.abs(res["snapshots"][0] - want) / unit) <= 2.0      # two Radau codes at rtol = 1e-3
     lat = mb.sweep_lattice(oracle.default_scenario(), 1, 1, 5)
     Pl, yl = mb.derive_column_params(lat), mb.initial_state(lat)
-    a = emu_radau(0, Pl, yl, 0.006, t_eval=[0.006], events=True, first_step=5e-7)
-    b = emu_radau(1, Pl, yl, 0.006, t_eval=[0.006], events=True, first_step=5e-7)
-    assert np.all(a["state"]["status"] == 0) and np.array_equal(a["stats"][:, :2], b["stats"][:, :2])
-    assert np.max(np.abs(a["y"] - b["y"]) / (1e-3 + 1e-3 * np.abs(a["y"]))) <= 1e-3
+    a = emu_radau(Pl, yl, 0.006, t_eval=[0.006], events=True, first_step=5e-7)
+    assert np.all(a["state"]["status"] == 0)
     one = {k: (float(v[4]) if np.ndim(v) else v) for k, v in lat.items()}
     s4 = oracle.integrate(one, method="Radau", t_span=(0, 0.006), t_eval=[0.006], events=False, first_step=5e-7,
                           jac_sparsity=oracle.jacobian_sparsity(200)).y.reshape(5, 200)
@@ -295,7 +191,7 @@ def emu_stream():
         libs[tma] = C.CDLL(so)
         libs[tma].emu_rk45_stream.restype = C.c_int
 
-    def run(P, y, t_end, t_eval, first_step, attempts, state=None, tma=0):
+    def run(P, y, t_end, t_eval, first_step, attempts, state=None, tma=0, events=False, counts=None, times=None, flags=0):
         lib = libs[tma]
         y = np.ascontiguousarray(y, dtype=np.float64).copy()
         P = np.ascontiguousarray(P)
@@ -303,12 +199,14 @@ def emu_stream():
         st = batch.make_state(B, 0.0, first_step) if state is None else state.copy()
         te = np.asarray(t_eval, dtype=np.float64)
         snap = np.full((B, max(1, te.size), 5, N), np.nan)
+        ec = np.zeros((B, 7), np.int32) if counts is None else counts.copy()
+        et = np.full((B, 7, 16), np.nan) if times is None else times.copy()
         o = _cabi.RK45Options(t_bound=t_end, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=attempts,
-                              n_eval=te.size, event_capacity=0, flags=0, quantum=0)
+                              n_eval=te.size, event_capacity=16, flags=flags | (_cabi.FLAG_EVENTS if events else 0), quantum=0)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
-        rc = lib.emu_rk45_stream(p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), C.c_longlong(attempts))
+        rc = lib.emu_rk45_stream(p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), C.c_longlong(attempts), p(ec), p(et))
         assert rc == 0, f"emulated streaming launcher: rc {rc}"
-        return dict(y=y, state=st, snapshots=snap)
+        return dict(y=y, state=st, snapshots=snap, event_counts=ec, event_times=et)
     return run
 
 
@@ -363,3 +261,40 @@ def test_tile_kernel_bulk_copy_windows_are_bit_identical(emu_stream, n_cells, mo
     assert a["state"]["n_accepted"][0] >= 8 and a["state"]["next_eval"][0] == 2
     assert np.array_equal(a["state"], b["state"]) and np.array_equal(a["y"], b["y"])
     assert np.array_equal(a["snapshots"][:, :2], b["snapshots"][:, :2])
+
+
+@pytest.mark.parametrize("n_cells", [16, 1300])
+def test_streaming_events_replay_and_locate_under_emulation(emu_stream, n_cells, monkeypatch):
+    """Event monitors on the streaming path: per-window predicate bits, detection in the prepare kernel, replay of the
+    step with K3..K6 stored, Brent location by the column's first CTA.  Counts and root times equal SciPy's; a run cut
+    into batches of 16 attempts (a batch may end between detection and location; 5 for the 16-cell grid) finds every event exactly once; the
+    trajectory does not depend on monitoring."""
+    monkeypatch.setenv("MARLPDE_RK45_STREAM", "tiles")
+    pde = oracle.default_scenario() | SCEN_A | {"N": n_cells}
+    scale = min(1.0, (200 / n_cells) ** 2)
+    t_end, fs = 90 * 2.6e-6 * scale, 1e-6 * scale
+    y0 = mb.initial_state(pde)
+    pick = lambda frac: min(n_cells - 1, int(frac * n_cells))
+    y0[0, 0, pick(0.25)] = -2e-5 * scale
+    y0[0, 1, pick(0.30)] = -1e-5 * scale
+    y0[0, 4, pick(0.75)] = 1.0 + 5e-6 * scale
+    sol = oracle.integrate(pde, method="RK45", t_span=(0, t_end), t_eval=[0, t_end], events=True, y0=y0[0], first_step=fs)
+    want = [len(e) for e in sol.t_events]
+    assert sum(want) >= 3, want
+    P = mb.derive_column_params(pde)
+    plain = emu_stream(P, y0, t_end, [t_end], fs, 200)
+    assert plain["state"]["status"][0] == 0
+    per_call = 5 if n_cells < 100 else 16
+    r = emu_stream(P, y0, t_end, [t_end], fs, per_call, events=True)
+    times = [list(r["event_times"][0, k, :r["event_counts"][0, k]]) for k in range(7)]
+    hops = 1
+    while r["state"]["status"][0] in (1, 2):
+        r = emu_stream(P, r["y"], t_end, [t_end], fs, per_call, state=r["state"], events=True)
+        for k in range(7):
+            times[k] += list(r["event_times"][0, k, :r["event_counts"][0, k]])
+        hops += 1
+    assert hops >= 3 and r["state"]["status"][0] == 0
+    assert [len(t) for t in times] == want
+    for k in range(7):
+        assert np.allclose(np.sort(times[k]), sol.t_events[k], rtol=0, atol=1e-12)
+    assert np.array_equal(r["y"], plain["y"]) and r["state"]["nfev"][0] == plain["state"]["nfev"][0] == sol.nfev

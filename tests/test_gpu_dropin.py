@@ -97,6 +97,26 @@ def test_rk45_and_scipy_stepper_routes(fixtures_reference, in_tmp_cwd, monkeypat
     assert_allclose(a, c, rtol=0, atol=2e-2)              # LSODA with the reference's lband = uband = 1
 
 
+@pytest.mark.parametrize("n_cells", [16, 1000])
+def test_rk45_drop_in_outside_the_on_chip_grid_range(in_tmp_cwd, n_cells):
+    """integrate_equations(method="RK45") monitors the 7 events at any N like the reference (Evolve_scenario.py:104-109):
+    grids below 32 or above 640 cells run on the streaming kernels, events included."""
+    import lheureux_oracle as oracle
+    scale = min(1.0, (200 / n_cells) ** 2)
+    t_end = 300 * 2.6e-6 * scale
+    scen = asdict(Map_Scenario()) | {"Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6, "N": n_cells}
+    solver = asdict(Solver(method="RK45")) | {"t_span": (0, t_end), "first_step": 1e-6 * scale}
+    tr = asdict(Tracker()) | {"t_eval": np.array([0.0, t_end])}
+    last, covered, depths, xstar, folder = integrate_equations(solver, tr, dict(scen))
+    assert last.shape == (5, n_cells) and covered == pytest.approx(scen["Tstar"] * t_end)
+    sol = oracle.integrate(scen, method="RK45", t_span=(0, t_end), t_eval=[0, t_end], events=True, first_step=1e-6 * scale)
+    assert_allclose(last, sol.y[:, -1].reshape(5, n_cells), rtol=0, atol=1e-9)
+    with hdf5lite.File(os.path.join(folder, "LMAHeureuxPorosityDiff.hdf5"), "r") as f:
+        assert f["solutions"].shape == (5, n_cells, 2)
+        for k in range(7):
+            assert np.asarray(f[f"event_{k}"]).shape == (len(sol.t_events[k]),)
+
+
 def test_batch_entry_point_radau_and_rk45(in_tmp_cwd):
     import marlpde_b200 as mb
     sweep = mb.sweep_lattice(asdict(Map_Scenario()) | {"Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}, 2, 2, 2)

@@ -121,3 +121,22 @@ def test_radau_events_match_scipy():
     assert np.all(np.diff(got[6]) > 0) and np.all((got[6] > 0) & (got[6] <= 0.05))
     plain = mb.integrate_radau_batch(y0, P, t_span=(0, 0.05), first_step=5e-7)
     assert np.array_equal(plain.y, res.y)                              # monitoring does not change the trajectory
+
+
+def test_radau_time_varying_dPhi_model_variant():
+    """MARLPDE_MODEL_VAR_DPHI on the implicit path (per-cell dPhi in the RHS and in the analytic off-diagonal Jacobian
+    blocks) against SciPy Radau on the oracle variant; a plain column in the same launch is unaffected."""
+    base = oracle.default_scenario() | {"Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}
+    var = base | {"time_varying_dPhi": True}
+    P = np.concatenate([mb.derive_column_params(var), mb.derive_column_params(base)])
+    Y = np.repeat(mb.initial_state(base), 2, 0)
+    res = mb.integrate_radau_batch(Y, P, t_span=(0, 0.2), first_step=1e-6, t_eval=[0.2])
+    plain = mb.integrate_radau_batch(Y[1:], P[1:], t_span=(0, 0.2), first_step=1e-6, t_eval=[0.2])
+    assert np.all(res.status == 0) and np.array_equal(res.y[1], plain.y[0])
+    sol = oracle.integrate(var, method="Radau", t_span=(0, 0.2), t_eval=[0.2], events=False, first_step=1e-6,
+                           jac_sparsity=oracle.jacobian_sparsity(200))
+    want = sol.y[:, -1].reshape(5, 200)
+    assert np.max(np.abs(res.y[0] - want) / (ATOL + RTOL * np.abs(want))) <= 2.0
+    assert np.max(np.abs(res.y[0][4] - res.y[1][4])) > 1e-6
+    # Newton converges as well as for the plain model: the analytic off-diagonal blocks carry the cell's own dPhi
+    assert res.newton_failures[0] <= plain.newton_failures[0] + 2

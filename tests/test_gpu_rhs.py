@@ -40,6 +40,41 @@ def test_rhs_matches_reference_golden(rhs_golden, name):
                 assert np.max(np.abs(got[sl] - r_numba[sl])) <= TOL * np.max(np.abs(r_numba[sl])), (sname, f)
 
 
+@pytest.mark.parametrize("name", ["default", "scenario_A", "fv_off"])
+def test_rhs_time_varying_dPhi_matches_reference_variant(rhs_golden_vardphi, name):
+    """Model variant MARLPDE_MODEL_VAR_DPHI against golden outputs of the reference's own pde_rhs with its commented-out
+    dPhi line switched on (LHeureux_model.py:430-431; tests/golden/make_golden.py vardphi)."""
+    g, meta = rhs_golden_vardphi
+    pde = meta[name] | {"time_varying_dPhi": True}
+    P = mb.derive_column_params(pde)
+    po = oracle.kernel_params(pde)
+    keys = sorted(k for k in g.files if k.startswith(name + "/") and k.endswith("/y"))
+    Y = np.stack([g[k].reshape(5, -1) for k in keys])
+    out = mb.rhs_batch(Y, np.repeat(P, len(keys)))
+    for key, got in zip(keys, out):
+        ref = g[key[:-2] + "/rhs_numba"]
+        assert np.array_equal(np.isnan(got.ravel()), np.isnan(ref)), key
+        assert _scaled_err(got.ravel(), ref, g[key], po) <= TOL, key
+    # flagged and plain columns in one launch: the plain ones are what a launch without flagged columns gives
+    P0 = mb.derive_column_params(meta[name])
+    mixed = mb.rhs_batch(np.stack([Y[1], Y[1], Y[1]]), np.concatenate([P, P0, P]))
+    assert np.array_equal(mixed[1], mb.rhs_batch(Y[1:2], P0)[0]) and np.array_equal(mixed[0], out[1])
+    assert not np.array_equal(mixed[0][4], mixed[1][4])
+
+
+def test_rhs_matches_reference_numpy_backend_golden(rhs_golden):
+    """Row a4: `fun` (the reference's NumPy backend, LHeureux_model.py:162-288) computes the same maths re-associated;
+    the CUDA RHS is within the same 1e-12 term-magnitude gate of its golden outputs."""
+    g, meta = rhs_golden
+    for name in ("default", "scenario_A", "lattice_corner"):
+        pde = meta[name]
+        P, po = mb.derive_column_params(pde), oracle.kernel_params(pde)
+        states = list(rhs_states(g, name))
+        out = mb.rhs_batch(np.stack([s[1].reshape(5, -1) for s in states]), np.repeat(P, len(states)))
+        for (sname, y, _r_numba, r_numpy, _ev), got in zip(states, out):
+            assert _scaled_err(got.ravel(), r_numpy, y, po) <= TOL, (name, sname)
+
+
 def test_rhs_sweep_batch_against_oracle():
     """512 lattice columns with different parameters, each on its own perturbed state."""
     base = oracle.default_scenario() | {"Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}

@@ -129,8 +129,8 @@ def test_unsupported_and_degenerate_inputs():
     from marlpde_b200._cabi import MarlpdeError
     pde = oracle.default_scenario()
     P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
-    with pytest.raises(MarlpdeError, match="events"):          # large grids stream through HBM, without event monitors
-        mb.integrate_rk45_batch(np.full((1, 5, 700), 0.5), P, events=True, event_capacity=4)
+    with pytest.raises(MarlpdeError, match="n_cells"):         # the smallest grid has two cells
+        mb.integrate_rk45_batch(np.full((1, 5, 1), 0.5), P)
     res = mb.integrate_rk45_batch(y0[:0], P[:0])
     assert res.y.shape == (0, 5, 200)
     # a state that is already non-finite collapses the step size like SciPy: status -1, never hangs
@@ -303,8 +303,9 @@ def test_streaming_path_resume_device_tensors_and_budget():
 
 
 def test_host_path_scratch_pool_is_reused_and_released():
-    """The host-pointer entry points keep their device scratch between calls (cudaMalloc/cudaFree cost up to
-    130 ms per call on the bench box); results do not depend on it and the pool can be handed back."""
+    """The host-pointer entry points take their device scratch from a stream-ordered pool that keeps blocks between
+    calls (cudaMalloc/cudaFree cost up to 130 ms per call on the bench box); results do not depend on it, the pool can
+    be trimmed, and the calling thread's current device is left alone."""
     from marlpde_b200 import _cabi
     pde = oracle.default_scenario()
     P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
@@ -312,7 +313,134 @@ def test_host_path_scratch_pool_is_reused_and_released():
     a = mb.integrate_rk45_batch(y0, P, t_span=(0, 1e-4), first_step=1e-6)
     b = mb.integrate_rk45_batch(y0, P, t_span=(0, 1e-4), first_step=1e-6)        # served from the pool
     assert np.array_equal(a.y, b.y) and np.array_equal(a.nfev, b.nfev)
-    assert _cabi.lib().marlpde_release_cached_memory() >= 4
-    assert _cabi.lib().marlpde_release_cached_memory() == 0
+    assert _cabi.lib().marlpde_release_cached_memory() >= 1          # number of per-device pools trimmed
     c = mb.integrate_rk45_batch(y0, P, t_span=(0, 1e-4), first_step=1e-6)
     assert np.array_equal(a.y, c.y)
+
+
+def test_streaming_path_20000_cells_matches_scipy():
+    """BASELINE.json configs[3] at its largest grid: N = 20 000, one column and a batch of 8, 600 step attempts from
+    t = 0 against SciPy RK45 on the oracle (1.1 ms per RHS call on the CPU)."""
+    n_cells = 20000
+    pde = oracle.default_scenario() | {"N": n_cells, "Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}
+    scale = (200 / n_cells) ** 2
+    t_end, fs = 500 * 2.6e-6 * scale, 1e-6 * scale
+    te = [0.0, 0.5 * t_end, t_end]
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    sol = oracle.integrate(pde, method="RK45", t_span=(0, t_end), t_eval=te, events=False, first_step=fs)
+    want = sol.y.reshape(5, n_cells, -1)
+    for ncol in (1, 8):
+        res = mb.integrate_rk45_batch(np.repeat(y0, ncol, 0), np.repeat(P, ncol), t_span=(0, t_end), first_step=fs, t_eval=te)
+        assert np.all(res.status == 0) and np.all(res.t == t_end) and np.all(res.next_eval == 3)
+        assert np.all(np.abs(res.nfev - sol.nfev) <= 12), (res.nfev, sol.nfev)
+        assert res.n_attempts[0] >= 400
+        assert_allclose(res.solutions(0), want, rtol=0, atol=1e-9)
+        assert np.array_equal(res.y[0], res.y[-1])
+
+
+@pytest.mark.parametrize("n_cells", [1000, 1257, 16])
+def test_streaming_path_events_match_scipy(n_cells):
+    """The 7 monitors on depth grids outside the on-chip range (the reference monitors at any N,
+    LHeureux_model.py:524-593, Evolve_scenario.py:107-109): a state that starts outside the physical bounds in single
+    cells re-enters them, so monitors 0-4 and 6 fire; counts equal SciPy's, root times to 1e-9 (scaled grid: the
+    explicit step is stability bound, t_end ~ (200/N)^2).  A column without excursions in the same batch stays silent,
+    and monitoring does not change the trajectory."""
+    pde = oracle.default_scenario() | {"N": n_cells, "Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}
+    scale = min(1.0, (200 / n_cells) ** 2)
+    t_end, fs = 1500 * 2.6e-6 * scale, 1e-6 * scale
+    y0 = mb.initial_state(pde)
+    pick = lambda frac: min(n_cells - 1, int(frac * n_cells))
+    y0[0, 0, pick(0.25)] = -2e-3 * scale
+    y0[0, 1, pick(0.30)] = -1e-3 * scale
+    y0[0, 0, pick(0.50)] = 0.7 + 5e-3 * scale
+    y0[0, 4, pick(0.75)] = 1.0 + 5e-4 * scale
+    sol = oracle.integrate(pde, method="RK45", t_span=(0, t_end), t_eval=[0, t_end], events=True, y0=y0[0], first_step=fs)
+    want_counts = [len(e) for e in sol.t_events]
+    assert sum(c > 0 for c in want_counts) >= 4, want_counts
+    P = mb.derive_column_params(pde)
+    Y = np.concatenate([y0, mb.initial_state(pde), y0])
+    res = mb.integrate_rk45_batch(Y, np.repeat(P, 3), t_span=(0, t_end), first_step=fs, t_eval=[0, t_end],
+                                  events=True, event_capacity=8)
+    assert np.all(res.status == 0) and np.all(np.abs(res.nfev - sol.nfev) <= 12)
+    for c in (0, 2):
+        assert list(res.event_counts[c]) == want_counts
+        for got, want in zip(_event_lists(res, c), sol.t_events):
+            assert_allclose(got, want, rtol=0, atol=1e-9 * max(scale, 1e-3))
+    assert np.all(res.event_counts[1] == 0)
+    assert np.array_equal(res.event_times[0], res.event_times[2], equal_nan=True)
+    plain = mb.integrate_rk45_batch(Y, np.repeat(P, 3), t_span=(0, t_end), first_step=fs, t_eval=[0, t_end])
+    assert np.array_equal(plain.y, res.y) and np.array_equal(plain.nfev, res.nfev)
+    assert np.array_equal(plain.snapshots, res.snapshots)
+    # device-tensor route and a run cut into batches (events located in one batch are not located again in the next)
+    import torch
+    dev = mb.integrate_rk45_batch(torch.from_numpy(Y).cuda(), np.repeat(P, 3), t_span=(0, t_end), first_step=fs,
+                                  t_eval=[0, t_end], events=True, event_capacity=8)
+    assert np.array_equal(dev.event_counts, res.event_counts) and np.array_equal(dev.event_times, res.event_times, equal_nan=True)
+    part = mb.integrate_rk45_batch(Y, np.repeat(P, 3), t_span=(0, t_end), first_step=fs, events=True, event_capacity=8,
+                                   max_steps=137)
+    counts = part.event_counts.copy()
+    hops = 1
+    while np.any(part.status >= 1):
+        part = mb.integrate_rk45_batch(part.y, np.repeat(P, 3), t_span=(0, t_end), events=True, event_capacity=8,
+                                       max_steps=137, state=part.state)
+        counts += part.event_counts
+        hops += 1
+    assert hops >= 3 and np.array_equal(counts, res.event_counts) and np.array_equal(part.y, res.y)
+
+
+@pytest.mark.parametrize("n_cells", [200, 1000])
+def test_time_varying_dPhi_model_variant_matches_scipy(n_cells):
+    """the per-cell porosity diffusion coefficient dPhi = auxcon F Phi^3 / (1 - Phi)
+    (LHeureux_model.py:222-223, :430-431) as a kernel template flag, on-chip (N = 200) and streaming (N = 1000) kernels,
+    against SciPy RK45 on the oracle variant; flagged and plain columns share one launch and the plain ones are
+    bit-identical to a launch without any flagged column."""
+    base = oracle.default_scenario() | {"N": n_cells, "Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}
+    var = base | {"time_varying_dPhi": True}
+    scale = min(1.0, (200 / n_cells) ** 2)
+    t_end, fs = 400 * 2.6e-6 * scale, 1e-6 * scale
+    P = np.concatenate([mb.derive_column_params(var), mb.derive_column_params(base), mb.derive_column_params(var)])
+    assert list(P["model_flags"]) == [1, 0, 1] and P["auxcon"][0] > 0
+    Y = np.repeat(mb.initial_state(base), 3, 0)
+    res = mb.integrate_rk45_batch(Y, P, t_span=(0, t_end), first_step=fs, t_eval=[0, t_end], events=True, event_capacity=4)
+    plain = mb.integrate_rk45_batch(Y[:1], P[1:2], t_span=(0, t_end), first_step=fs, t_eval=[0, t_end], events=True,
+                                    event_capacity=4)
+    assert np.all(res.status == 0)
+    assert np.array_equal(res.y[1], plain.y[0]) and res.nfev[1] == plain.nfev[0]
+    assert np.array_equal(res.y[0], res.y[2])
+    sol = oracle.integrate(var, method="RK45", t_span=(0, t_end), t_eval=[0, t_end], events=False, first_step=fs)
+    assert abs(int(res.nfev[0]) - sol.nfev) <= 12
+    assert_allclose(res.y[0], sol.y[:, -1].reshape(5, n_cells), rtol=0, atol=1e-9)
+    assert np.max(np.abs(res.y[0][4] - res.y[1][4])) > 1e-7          # a different model, visibly
+
+
+def test_async_host_entry_point_overlaps_and_matches_sync():
+    """marlpde_rk45_integrate_async: copies, launch and scratch release enqueued on the caller's stream, no
+    synchronisation inside; two batches on two streams give the results of the blocking call."""
+    import ctypes as C
+    import torch
+    from marlpde_b200 import _cabi, batch
+    pde = mb.sweep_lattice(oracle.default_scenario(), 2, 2, 4)
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    want = mb.integrate_rk45_batch(y0, P, t_span=(0, 2e-4), first_step=5e-7, events=True, event_capacity=4)
+    lib = _cabi.lib()
+    o = _cabi.RK45Options(t_bound=2e-4, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=0, n_eval=0,
+                          event_capacity=4, flags=_cabi.FLAG_EVENTS, quantum=0)
+    halves, streams = [], [torch.cuda.Stream(), torch.cuda.Stream()]
+    for k, s in enumerate(streams):
+        sl = slice(8 * k, 8 * k + 8)
+        bufs = dict(y=torch.from_numpy(y0[sl].copy()).pin_memory(),
+                    p=torch.from_numpy(P[sl].view(np.uint8).copy()).pin_memory(),
+                    st=torch.from_numpy(batch.make_state(8, 0.0, 5e-7).view(np.uint8).copy()).pin_memory(),
+                    ec=torch.zeros((8, 7), dtype=torch.int32).pin_memory(),
+                    et=torch.full((8, 7, 4), float("nan"), dtype=torch.float64).pin_memory())
+        _cabi.check(lib.marlpde_rk45_integrate_async(bufs["y"].data_ptr(), bufs["p"].data_ptr(), bufs["st"].data_ptr(), 8, 200,
+                                                     C.byref(o), None, None, bufs["ec"].data_ptr(), bufs["et"].data_ptr(),
+                                                     torch.cuda.current_device(), s.cuda_stream))
+        halves.append(bufs)
+    for s in streams:
+        s.synchronize()
+    got_y = np.concatenate([h["y"].numpy() for h in halves])
+    got_ec = np.concatenate([h["ec"].numpy() for h in halves])
+    assert np.array_equal(got_y, want.y) and np.array_equal(got_ec, want.event_counts)
+    st = np.concatenate([h["st"].numpy().view(_cabi.STATE_DTYPE) for h in halves])
+    assert np.array_equal(st["nfev"], want.nfev) and np.all(st["status"] == 0)

@@ -96,8 +96,8 @@ def test_cabi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     L = _cabi.lib()
-    assert L.marlpde_abi_version() == 1
-    assert L.marlpde_struct_size(0) == _cabi.PARAMS_DTYPE.itemsize == 224
+    assert L.marlpde_abi_version() == 2
+    assert L.marlpde_struct_size(0) == _cabi.PARAMS_DTYPE.itemsize == 232
     assert L.marlpde_struct_size(2) == _cabi.STATE_DTYPE.itemsize == 48
     assert L.marlpde_struct_size(9) == -1
     assert L.marlpde_rk45_max_cells() == 640
@@ -138,9 +138,11 @@ def test_argument_validation_before_any_device_work():
     # ... the host entry point routes them to the streaming path, which validates its own arguments
     rc = _cabi.lib().marlpde_rk45_integrate(None, None, None, 1, 1000, ctypes.byref(opts), None, None, None, None, 0)
     assert rc == -1 and b"NULL" in _cabi.lib().marlpde_last_error()
+    # events are monitored on the streaming path too; the entry point without event outputs says which one to call
     opts.flags = _cabi.FLAG_EVENTS
-    rc = _cabi.lib().marlpde_rk45_integrate(None, None, None, 1, 1000, ctypes.byref(opts), None, None, None, None, 0)
-    assert rc == -4 and b"events" in _cabi.lib().marlpde_last_error()
+    opts.max_steps = 8
+    rc = _cabi.lib().marlpde_rk45_stream_integrate_dev(None, None, None, 1, 1000, ctypes.byref(opts), None, None, None, 0, None)
+    assert rc == -1 and b"marlpde_rk45_stream_integrate_events_dev" in _cabi.lib().marlpde_last_error()
     assert _cabi.lib().marlpde_rk45_stream_workspace_bytes(64, 20000) > 9 * 64 * 5 * 20000 * 8
     assert _cabi.lib().marlpde_radau_workspace_bytes(1, 200) == 8 * 200 * (90 + 76 + 64)
 
@@ -263,15 +265,13 @@ def test_two_ended_block_thomas_against_dense_solve(n_cells):
         assert np.max(np.abs(x - ref)) <= 1e-11 * np.max(np.abs(ref))
 
 
-@pytest.mark.parametrize("imm", [False, True])
-def test_table_driven_fp64_maths_model_against_mpmath(imm):
+def test_table_driven_fp64_maths_model_against_mpmath():
     """Tables (csrc/fp64_tables.inc), constants and algorithms of csrc/fp64_math.cuh, evaluated by an exact-FMA CPU
-    model (oracle/fp64_math_model.py), against mpmath — same ranges and bounds as tests/test_gpu_math.py — for the
-    default constants and for the experimental immediate-constant variant (MARLPDE_FP64_IMM=1)."""
+    model (oracle/fp64_math_model.py), against mpmath — same ranges and bounds as tests/test_gpu_math.py."""
     mp = pytest.importorskip("mpmath")
     import fp64_math_model as fm
     mp.mp.prec = 120
-    c = fm.Constants(imm)
+    c = fm.Constants(False)
     rng = np.random.default_rng(5)
     xs = np.concatenate([rng.uniform(1e-3, 3.0, 300), 10.0 ** rng.uniform(-300, 300, 100), 1 + rng.uniform(-1e-3, 1e-3, 100),
                          [1.0, 0.5, 2.0, np.nextafter(1, 0), np.nextafter(1, 2), 0.8, 0.6]])

@@ -51,6 +51,32 @@ def test_oracle_rhs_is_bit_identical_to_reference_pde_rhs(rhs_golden, name):
     assert n_states >= 4
 
 
+@pytest.mark.parametrize("name", ["default", "scenario_A", "fv_off"])
+def test_oracle_time_varying_dPhi_is_bit_identical_to_reference_variant(rhs_golden_vardphi, name):
+    """dPhi = auxcon F Phi^3 / (1 - Phi) per cell (LHeureux_model.py:222-223, :430-431, commented out
+    upstream).  The golden outputs come from the reference's own source with exactly those two lines switched."""
+    g, meta = rhs_golden_vardphi
+    pde = meta[name] | {"time_varying_dPhi": True}
+    p = oracle.kernel_params(pde)
+    p_fixed = oracle.kernel_params(meta[name])
+    n = 0
+    for key in sorted(k for k in g.files if k.startswith(name + "/") and k.endswith("/y")):
+        stem = key[:-2]
+        y = g[key]
+        out = oracle.rhs(y, p, np.empty_like(y))
+        assert np.array_equal(out, g[stem + "/rhs_numba"], equal_nan=True), stem
+        S = oracle.term_scale(y, p, np.empty_like(y))
+        assert np.nanmax(np.abs(out - g[stem + "/rhs_numpy"]) / S) < 2e-15, stem
+        n += 1
+    assert n >= 6
+    # the variant is a different model: same state, fixed coefficient -> different porosity rates
+    y = g[f"{name}/noise/y"]
+    fixed = oracle.rhs(y, p_fixed, np.empty_like(y))
+    assert np.array_equal(fixed, g[f"{name}/noise/rhs_numba_fixed_dPhi"])
+    assert np.max(np.abs(fixed[800:] - g[f"{name}/noise/rhs_numba"][800:])) > 1e-4 * np.max(np.abs(fixed[800:]))
+    assert np.array_equal(fixed[:400], g[f"{name}/noise/rhs_numba"][:400])      # CA, CC do not see dPhi
+
+
 def test_known_answer_values_default_y0():
     """Sanity values quoted in SURVEY.md §8c for the default scenario at y0."""
     pde = oracle.default_scenario()

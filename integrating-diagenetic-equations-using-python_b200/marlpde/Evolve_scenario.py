@@ -65,9 +65,10 @@ def _gpu_rk45(eq, y0, solver_parms, t_eval, n_cells):
     extra = set(solver_parms) - known
     if extra:
         raise TypeError(f"options not supported by the GPU RK45 path: {sorted(extra)}")
-    if solver_parms.get("dense_output"):
-        raise NotImplementedError("dense_output=True (a callable OdeSolution) is not available on the GPU path; "
-                                  "use t_eval")
+    # `dense_output=True` (parameters.py:221 has False) makes solve_ivp attach a callable OdeSolution as `sol.sol`;
+    # upstream's driver never reads it (Evolve_scenario.py:104-183 uses sol.y, sol.t, sol.t_events only), so the flag is
+    # accepted and stored with the other parameters; intermediate states come from `t_eval`, which IS the dense output
+    # (quartic / cubic interpolant of the step, as SciPy) evaluated on the device.
     te = np.asarray(t_eval, dtype=np.float64) if t_eval is not None else np.array(solver_parms["t_span"], float)
     res = _mb.integrate_rk45_batch(y0.reshape(1, 5, n_cells), eq.column_params, t_span=solver_parms["t_span"],
                                    first_step=solver_parms.get("first_step", 1e-6),
@@ -91,9 +92,10 @@ def _gpu_radau(eq, y0, solver_parms, t_eval, n_cells):
     extra = set(solver_parms) - known
     if extra:
         raise TypeError(f"options not supported by the GPU Radau path: {sorted(extra)}")
-    if solver_parms.get("dense_output"):
-        raise NotImplementedError("dense_output=True (a callable OdeSolution) is not available on the GPU path; "
-                                  "use t_eval")
+    # `dense_output=True` (parameters.py:221 has False) makes solve_ivp attach a callable OdeSolution as `sol.sol`;
+    # upstream's driver never reads it (Evolve_scenario.py:104-183 uses sol.y, sol.t, sol.t_events only), so the flag is
+    # accepted and stored with the other parameters; intermediate states come from `t_eval`, which IS the dense output
+    # (quartic / cubic interpolant of the step, as SciPy) evaluated on the device.
     te = np.asarray(t_eval, dtype=np.float64) if t_eval is not None else np.array(solver_parms["t_span"], float)
     res = _mb.integrate_radau_batch(y0.reshape(1, 5, n_cells), eq.column_params, t_span=solver_parms["t_span"],
                                     first_step=solver_parms.get("first_step", 1e-6),

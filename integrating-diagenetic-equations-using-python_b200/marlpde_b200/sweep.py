@@ -5,7 +5,7 @@ the results after the integration (BASELINE.json configs[2]).
     partition / balanced_assignment   which rank integrates which column
     shard                             a rank's slice of a Map_Scenario sweep dictionary
     gather_columns                    the collective: per-rank [b_r, ...] arrays -> [B, ...] on every rank
-    sweep_rk45                        shard -> integrate_rk45_batch on this rank's GPU -> gather
+    sweep_rk45 / sweep_radau          shard -> integrate_{rk45,radau}_batch on this rank's GPU -> gather
 
 `torch.distributed` is plumbing only (NCCL over NVLink on GPUs; the tests drive the same code with
 gloo on CPU tensors and a stand-in integrator).  The reference has no counterpart: it integrates
@@ -104,14 +104,21 @@ class SweepResult:
     event_counts: np.ndarray  # [B,7]
     owner: np.ndarray        # [B] rank that integrated the column
     t_eval: np.ndarray
+    next_eval: np.ndarray = None   # [B] rows of `snapshots` that hold data (the rest is NaN: column stopped early)
+
+
+def sweep_radau(pde: dict, **kw) -> SweepResult:
+    """The sweep with the implicit integrator (the reference's default Solver, parameters.py:207-221): what a
+    65 536-column sweep to T* uses in practice (4096 columns: ~23 s against ~140 s with RK45)."""
+    return sweep_rk45(pde, method="Radau", **kw)
 
 
 def sweep_rk45(pde: dict, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e-3, atol=1e-3, t_eval=None,
                events: bool = True, balance: bool = True, group=None, device=None, integrate=None,
-               **kw) -> SweepResult:
-    """Integrate every column of the sweep dictionary `pde` with the on-device RK45, sharded over the
-    ranks of `group` (all ranks call this with the same arguments).  `integrate` is the per-rank
-    batched integrator (default: marlpde_b200.integrate_rk45_batch on `device`)."""
+               method: str = "RK45", **kw) -> SweepResult:
+    """Integrate every column of the sweep dictionary `pde` with the on-device RK45 (or, method="Radau", the implicit
+    integrator), sharded over the ranks of `group` (all ranks call this with the same arguments).  `integrate` is the
+    per-rank batched integrator (default: marlpde_b200.integrate_{rk45,radau}_batch on `device`)."""
     import torch
     import torch.distributed as dist
     from . import params as _params
@@ -129,11 +136,14 @@ def sweep_rk45(pde: dict, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e-3, atol=1e
     local = shard(pde, mine) if B > 1 else pde
 
     if integrate is None:
-        from .batch import integrate_rk45_batch
+        from .batch import integrate_radau_batch, integrate_rk45_batch
+        if method not in ("RK45", "Radau"):
+            raise ValueError("method must be 'RK45' or 'Radau'")
+        run = integrate_rk45_batch if method == "RK45" else integrate_radau_batch
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
 
         def integrate(y0, P, **opts):
-            return integrate_rk45_batch(torch.from_numpy(y0).to(dev), P, **opts)
+            return run(torch.from_numpy(y0).to(dev), P, **opts)
     P = _params.derive_column_params(local) if len(mine) else None
     te = np.zeros(0) if t_eval is None else np.asarray(t_eval, dtype=np.float64)
     N = int(pde["N"])
@@ -144,14 +154,16 @@ def sweep_rk45(pde: dict, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e-3, atol=1e
         y_l, snap_l = as_t(res.y), as_t(res.snapshots)
         stats = np.stack([res.t, res.status.astype(np.float64), res.n_accepted.astype(np.float64),
                           res.n_rejected.astype(np.float64), res.nfev.astype(np.float64)], axis=1)
-        stats = np.concatenate([stats, np.asarray(res.event_counts, dtype=np.float64).reshape(len(mine), 7)], axis=1)
+        stats = np.concatenate([stats, np.asarray(res.event_counts, dtype=np.float64).reshape(len(mine), 7),
+                                np.asarray(getattr(res, "next_eval", np.full(len(mine), te.size)), dtype=np.float64)[:, None]],
+                               axis=1)
         dev_l = y_l.device
     else:
         dev_l = torch.device("cuda", torch.cuda.current_device()) if (device is None and torch.cuda.is_available()) \
             else torch.device(device or "cpu")
         y_l = torch.zeros((0, 5, N), dtype=torch.float64, device=dev_l)
         snap_l = torch.zeros((0, te.size, 5, N), dtype=torch.float64, device=dev_l)
-        stats = np.zeros((0, 12))
+        stats = np.zeros((0, 13))
     stats_l = torch.from_numpy(stats).to(dev_l)
 
     # ---- the one collective: end states, snapshots and per-column statistics of every shard
@@ -170,4 +182,4 @@ def sweep_rk45(pde: dict, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e-3, atol=1e
     return SweepResult(y=y_np, snapshots=snap_np, t=st[:, 0], status=st[:, 1].astype(np.int32),
                        n_accepted=st[:, 2].astype(np.int64), n_rejected=st[:, 3].astype(np.int64),
                        nfev=st[:, 4].astype(np.int64), event_counts=st[:, 5:12].astype(np.int64), owner=owner,
-                       t_eval=te)
+                       t_eval=te, next_eval=st[:, 12].astype(np.int64))

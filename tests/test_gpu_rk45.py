@@ -376,13 +376,14 @@ def test_streaming_path_events_match_scipy(n_cells):
     dev = mb.integrate_rk45_batch(torch.from_numpy(Y).cuda(), np.repeat(P, 3), t_span=(0, t_end), first_step=fs,
                                   t_eval=[0, t_end], events=True, event_capacity=8)
     assert np.array_equal(dev.event_counts, res.event_counts) and np.array_equal(dev.event_times, res.event_times, equal_nan=True)
+    per_call = max(4, int(res.n_attempts.max()) // 4)
     part = mb.integrate_rk45_batch(Y, np.repeat(P, 3), t_span=(0, t_end), first_step=fs, events=True, event_capacity=8,
-                                   max_steps=137)
+                                   max_steps=per_call)
     counts = part.event_counts.copy()
     hops = 1
     while np.any(part.status >= 1):
         part = mb.integrate_rk45_batch(part.y, np.repeat(P, 3), t_span=(0, t_end), events=True, event_capacity=8,
-                                       max_steps=137, state=part.state)
+                                       max_steps=per_call, state=part.state)
         counts += part.event_counts
         hops += 1
     assert hops >= 3 and np.array_equal(counts, res.event_counts) and np.array_equal(part.y, res.y)

@@ -11,11 +11,6 @@
 #define MARLPDE_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
-// A/B candidate (off): the tile kernel of rk45_streaming.cu moves its windows with 1-D TMA bulk copies
-#ifndef MARLPDE_TILE_TMA
-#define MARLPDE_TILE_TMA 0
-#endif
-
 // kernel launch (the host emulator runs the blocks of the grid one after the other)
 #ifdef MARLPDE_HOST_EMU
 #define MARLPDE_LAUNCH(kernel, grid, block, smem, stream, ...) \

@@ -76,6 +76,7 @@ struct Args {
   double* ev_times;          // [B][7][event_capacity]
   int B, N, tiles;
   int tiles2;                // overlapped-tile path: attempt tiles per column (0: one launch per stage)
+  int pstride;               // entries per column in `partials` and `evpart`
   marlpde_rk45_options opt;
 };
 
@@ -86,7 +87,7 @@ struct Layout {
 };
 __host__ inline Layout layout(int B, int N) {
   const size_t vec = sizeof(double) * 5 * (size_t)N * B;
-  const int tiles = (N + kCellsPerCta - 1) / kCellsPerCta;
+  const int tiles = (N + 243) / 244 + 1;       // >= CTAs per column of every kernel (256-cell CTAs, 244- / 628-cell windows)
   Layout L;
   size_t o = 0;
   L.off_K = o;     o += align256(7 * vec);
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin
     // ---- error norm of the attempt that just ran: per-CTA partial sums, fixed order
     double sum = 0.0;
     const int n_part = A.tiles2 > 0 ? A.tiles2 : A.tiles;
-    const double* part = A.partials + (size_t)m.col * n_part;
+    const double* part = A.partials + (size_t)m.col * A.pstride;
     for (int i = 0; i < n_part; ++i) sum += part[i];
     const double err_norm = sqrt(sum / (double)(5 * N));
     c.nfev += 6;
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin
     bool replay = false;
     unsigned ev_new = 0u;
     if (ev_on && err_norm < 1.0) {
-      const unsigned* evp = A.evpart + (size_t)m.col * A.tiles;
+      const unsigned* evp = A.evpart + (size_t)m.col * A.pstride;
       for (int i = 0; i < n_part; ++i) ev_new |= evp[i];
       unsigned act = 0u;
       if (ev_new != c.ev_prev || (ev_new & kEqBitsMask) != 0u)
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin
   } else {
     c.fresh = 0;
     if (ev_on) {                               // monitors at the start point (ivp.py: g = event(t0, y0)), from the K1 launch
-      const unsigned* evp = A.evpart + (size_t)m.col * A.tiles;
+      const unsigned* evp = A.evpart + (size_t)m.col * A.pstride;
       unsigned b = 0u;
       for (int i = 0; i < A.tiles; ++i) b |= evp[i];
       c.ev_prev = b;
@@ -582,7 +583,7 @@ __global__ void __launch_bounds__(kThreads, 3) stage_kernel(const Args A, int i,
       if (threadIdx.x == 0) {
         unsigned b = 0u;
         for (int w = 0; w < kThreads / 32; ++w) b |= sbits[w];
-        A.evpart[(size_t)m.col * A.tiles + (blockIdx.x - m.col * A.tiles)] = b;
+        A.evpart[(size_t)m.col * A.pstride + (blockIdx.x - m.col * A.tiles)] = b;
       }
     }
   } else if (i < 6) {
@@ -611,7 +612,7 @@ __global__ void __launch_bounds__(kThreads, 3) stage_kernel(const Args A, int i,
     if (threadIdx.x == 0) {
       double s = 0.0;
       for (int w = 0; w < kThreads / 32; ++w) s += red[w];
-      A.partials[(size_t)m.col * A.tiles + (blockIdx.x - m.col * A.tiles)] = s;
+      A.partials[(size_t)m.col * A.pstride + (blockIdx.x - m.col * A.tiles)] = s;
     }
   }
 }
@@ -626,28 +627,38 @@ __global__ void __launch_bounds__(kThreads, 3) stage_kernel(const Args A, int i,
 // K2..K7 the inner 628 cells are exact and only those are written back.  HBM traffic per attempt drops
 // from 42 to 4 vector passes (read y, K1; write y_new, K7), at 1.9 % redundant arithmetic.
 // =================================================================================================
-constexpr int kTileThreads = 320;
-constexpr int kTileCells = 2 * kTileThreads;
+// Window sizes: 320 threads (640-cell windows, 628 owned cells) when the batch fills the machine; 128 threads (256-cell
+// windows, 244 owned) for small batches — N = 20 000 x 1 is 32 large windows on 148 SMs, and an attempt cannot be
+// faster than one CTA's six stage trips (~5 200 cycles each with 10 warps in lock-step, ~2 500 with one warp per
+// scheduler): more, smaller windows cut that latency at 4.9 % instead of 1.9 % redundant arithmetic.
 constexpr int kTileHalo = 6;
-constexpr int kTileValid = kTileCells - 2 * kTileHalo;
+constexpr int kTileThreadsLarge = 320, kTileThreadsSmall = 128;
+__host__ __device__ constexpr int tile_valid_cells(int threads) { return 2 * threads - 2 * kTileHalo; }
 
-struct TileSmem {
-  static constexpr size_t off_K = 0;                                                   // double2 [4][5][320]
-  static constexpr size_t off_E = off_K + sizeof(double2) * 4 * 5 * kTileThreads;      // double [2][5][320]
-  static constexpr size_t off_O = off_E + sizeof(double) * 2 * 5 * kTileThreads;
-  static constexpr size_t off_tab = off_O + sizeof(double) * 2 * 5 * kTileThreads;
+// TMA: the window loads / write-back go through the TMA unit (1-D bulk copies, UBLKCP) and a shared-memory staging
+// area instead of per-thread loads and stores.  Measured on B200 (r02a): 208 k against 231 k column-steps/s at
+// N = 20 000 x 64 — the kernel is bound by the fp64 pipe and its DRAM traffic already equals the algorithmic traffic, so
+// the staging hop only adds shared-memory traffic.  Shipped and selectable (MARLPDE_RK45_TILE_TMA=1), off by default.
+template <int TT, bool TMA>
+struct TileSmemT {
+  static constexpr size_t off_K = 0;                                                   // double2 [4][5][TT]
+  static constexpr size_t off_E = off_K + sizeof(double2) * 4 * 5 * TT;                // double [2][5][TT]
+  static constexpr size_t off_O = off_E + sizeof(double) * 2 * 5 * TT;
+  static constexpr size_t off_tab = off_O + sizeof(double) * 2 * 5 * TT;
   static constexpr size_t off_kc = off_tab + fm::kTableBytes;
   static constexpr size_t off_red = off_kc + (sizeof(ColumnConsts) + 15) / 16 * 16;
   static constexpr size_t off_bar = off_red + 16 * sizeof(double);                      // two mbarriers
-  static constexpr size_t off_stage = off_bar + 16;                                    // double [2][5][640] (MARLPDE_TILE_TMA)
-  static constexpr size_t total = off_stage + (MARLPDE_TILE_TMA ? sizeof(double) * 2 * 5 * kTileCells : 0);
+  static constexpr size_t off_stage = off_bar + 16;                                    // double [2][5][2 TT] (TMA)
+  static constexpr size_t total = off_stage + (TMA ? sizeof(double) * 2 * 5 * 2 * TT : 0);
+  static_assert(off_stage % 16 == 0 && total <= 227 * 1024, "tile kernel shared memory");
 };
-static_assert(TileSmem::off_stage % 16 == 0 && TileSmem::total <= 227 * 1024, "tile kernel shared memory");
 
 // VD: batches with MARLPDE_MODEL_VAR_DPHI columns (opt.flags & MARLPDE_FLAG_VAR_DPHI); EV: MARLPDE_FLAG_EVENTS
-template <bool VD, bool EV>
-__global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Args A, int cbuf) {
+template <bool VD, bool EV, int TT, bool TMA>
+__global__ void __launch_bounds__(TT, 1) tile_attempt_kernel(const Args A, int cbuf) {
   MARLPDE_DYN_SMEM(smem_raw);
+  using TileSmem = TileSmemT<TT, TMA>;
+  constexpr int kTileThreads = TT, kTileCells = 2 * TT, kTileValid = tile_valid_cells(TT);
   constexpr int TP = kTileThreads;
   const int tid = threadIdx.x;
   const int col = blockIdx.x / A.tiles2;
@@ -667,16 +678,15 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
   if (tid == 0) make_consts(A.params[col], N, kc);
   const size_t vec = (size_t)A.B * 5 * N;
   const double h = c0.h;
-#if MARLPDE_TILE_TMA
   // Window loads and write-back by the TMA unit: ten 1-D bulk copies each way (5 fields x {y, K1} in, {y_new, K7} out) issued
   // by one thread, in flight while the tables and the column constants are set up.  Every row start and length is a
   // multiple of 16 bytes when N is even (window starts and the 628-cell stride are even); odd N keeps the plain loads.
   double* const sStage = reinterpret_cast<double*>(smem_raw + TileSmem::off_stage);
   uint64_t* const sLoad = sBar + 1;
-  const bool tma = (N & 1) == 0 && ((reinterpret_cast<uintptr_t>(A.y) | reinterpret_cast<uintptr_t>(A.K) |
-                                      reinterpret_cast<uintptr_t>(A.tile)) & 15) == 0;   // (a caller's view may be 8-byte aligned)
+  const bool tma = TMA && (N & 1) == 0 && ((reinterpret_cast<uintptr_t>(A.y) | reinterpret_cast<uintptr_t>(A.K) |
+                                             reinterpret_cast<uintptr_t>(A.tile)) & 15) == 0;   // (a caller's view may be 8-byte aligned)
   const int w0 = tile * kTileValid - kTileHalo;              // global cell of window position 0
-  if (tma && tid == 0) {
+  if (TMA && tma && tid == 0) {
     const int lo = w0 < 0 ? 0 : w0, hi = w0 + kTileCells < N ? w0 + kTileCells : N;
     const unsigned bytes = (unsigned)(hi - lo) * 8u;
     mbar_init(sLoad, 1);
@@ -690,7 +700,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
       bulk_g2s(sStage + (5 + f) * kTileCells + (lo - w0), ksrc + (size_t)f * N, bytes, sLoad);
     }
   }
-#endif
 
   const int e0 = 2 * tid;                                   // position inside the window
   const int g0 = tile * kTileValid - kTileHalo + e0;        // global cell of my first cell (always even)
@@ -713,8 +722,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
   auto Kld = [&](int s, int f) -> double2 { return sK[(s * 5 + f) * TP]; };
 
   double y[5][2], k1[5][2], c[5][2], r[5][2];
-#if MARLPDE_TILE_TMA
-  if (tma) {
+  if (TMA && tma) {
     __syncthreads();                                        // the load barrier is initialised
     mbar_wait(sLoad, 0);                                    // ... and the ten rows have landed
 #pragma unroll
@@ -726,9 +734,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
       k1[f][0] = in0 ? kv.x : 0.0;
       k1[f][1] = in1 ? kv.y : 0.0;
     }
-  } else
-#endif
-  {
+  } else {
     const double* K1g = Kslot(1);
 #pragma unroll
     for (int f = 0; f < 5; ++f) {
@@ -872,13 +878,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
     if (out0) part = fma(z0, z0, part);
     if (out1) part = fma(z1, z1, part);
     const size_t o = base + (size_t)f * N;
-#if MARLPDE_TILE_TMA
-    if (tma) {                                               // staged; one thread stores the owned range below
+    if (TMA && tma) {                                        // staged; one thread stores the owned range below
       *reinterpret_cast<double2*>(sStage + f * kTileCells + e0) = make_double2(c[f][0], c[f][1]);
       *reinterpret_cast<double2*>(sStage + (5 + f) * kTileCells + e0) = make_double2(r[f][0], r[f][1]);
-    } else
-#endif
-    {
+    } else {
       if (out0) {
         ynew[o] = c[f][0];
         K7g[o] = r[f][0];
@@ -910,21 +913,18 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
     const unsigned bw = __reduce_or_sync(0xffffffffu, event_bits_sel(c, U, W, out0, out1));
     if ((tid & 31) == 0) reinterpret_cast<unsigned*>(red + kTileThreads / 32)[tid >> 5] = bw;
   }
-#if MARLPDE_TILE_TMA
-  if (tma) fence_proxy_async();                              // my staged values, for the bulk stores after the barrier
-#endif
+  if (TMA && tma) fence_proxy_async();                       // my staged values, for the bulk stores after the barrier
   __syncthreads();
   if (tid == 0) {
     double s = 0.0;
     for (int w = 0; w < kTileThreads / 32; ++w) s += red[w];
-    A.partials[(size_t)col * A.tiles2 + tile] = s;
+    A.partials[(size_t)col * A.pstride + tile] = s;
     if constexpr (EV) {
       unsigned b = 0u;
       for (int w = 0; w < kTileThreads / 32; ++w) b |= reinterpret_cast<unsigned*>(red + kTileThreads / 32)[w];
-      A.evpart[(size_t)col * A.tiles + tile] = b;
+      A.evpart[(size_t)col * A.pstride + tile] = b;
     }
-#if MARLPDE_TILE_TMA
-    if (tma) {                                               // the cells this window owns: window positions [6, 634) inside the column
+    if (TMA && tma) {                                        // the cells this window owns: window positions [6, 2 TT - 6) inside the column
       const int olo = w0 + kTileHalo, ohi = olo + kTileValid < N ? olo + kTileValid : N;
       const unsigned bytes = (unsigned)(ohi - olo) * 8u;
       const size_t row0 = (size_t)col * 5 * N + (size_t)olo;
@@ -934,7 +934,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_attempt_kernel(const Arg
       }
       bulk_commit_wait();
     }
-#endif
   }
 }
 
@@ -946,14 +945,37 @@ namespace {
 struct GraphKey {             // everything a captured batch depends on (compared bytewise)
   st::Args a;
   long long attempts;
-  int use_tiles, device;
+  int use_tiles, device, small_tiles, tile_tma;
 };
 }  // namespace
 
-template <bool VD, bool EV>
-static cudaError_t tile_kernel_smem() {
-  return cudaFuncSetAttribute(st::tile_attempt_kernel<VD, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)st::TileSmem::total);
+// the tile kernel instantiations: model variant x events x window size, plus the TMA-staged build of the plain one
+template <bool VD, bool EV, int TT, bool TMA>
+static cudaError_t tile_launch(const st::Args& a, unsigned tgrid, int cbuf, cudaStream_t s_) {
+#ifndef MARLPDE_HOST_EMU
+  static bool configured = false;               // (per instantiation; the attribute is sticky per device context)
+  static int configured_device = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured || configured_device != dev) {
+    cudaError_t e = cudaFuncSetAttribute(st::tile_attempt_kernel<VD, EV, TT, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)st::TileSmemT<TT, TMA>::total);
+    if (e != cudaSuccess) return e;
+    configured = true;
+    configured_device = dev;
+  }
+#endif
+  MARLPDE_LAUNCH((st::tile_attempt_kernel<VD, EV, TT, TMA>), tgrid, TT, (st::TileSmemT<TT, TMA>::total), s_, a, cbuf);
+  return cudaSuccess;
+}
+
+template <int TT>
+static cudaError_t tile_dispatch(bool vd, bool ev, bool tma, const st::Args& a, unsigned tgrid, int cbuf, cudaStream_t s_) {
+  if (tma && !vd && !ev && TT == st::kTileThreadsLarge) return tile_launch<false, false, st::kTileThreadsLarge, true>(a, tgrid, cbuf, s_);
+  if (vd && ev) return tile_launch<true, true, TT, false>(a, tgrid, cbuf, s_);
+  if (vd) return tile_launch<true, false, TT, false>(a, tgrid, cbuf, s_);
+  if (ev) return tile_launch<false, true, TT, false>(a, tgrid, cbuf, s_);
+  return tile_launch<false, false, TT, false>(a, tgrid, cbuf, s_);
 }
 
 cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_params, marlpde_column_state* d_state,
@@ -979,6 +1001,7 @@ cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_param
   a.B = n_columns;
   a.N = n_cells;
   a.tiles = (n_cells + st::kCellsPerCta - 1) / st::kCellsPerCta;
+  a.pstride = (n_cells + 243) / 244 + 1;
   a.opt = opt;
   a.tiles2 = 0;
   const long long blocks = (long long)a.tiles * n_columns;
@@ -989,14 +1012,26 @@ cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_param
   const char* mode_env = std::getenv("MARLPDE_RK45_STREAM");
   const int use_tiles = (mode_env && mode_env[0] == 's') ? 0 : 1;
   unsigned tgrid = 0;
+  // window size: small windows while the large ones would leave more than half of the SMs without a CTA
+  // (MARLPDE_RK45_TILE=small|large overrides); MARLPDE_RK45_TILE_TMA=1 selects the TMA-staged build of the large window
+  bool small_tiles = false, tile_tma = false;
   if (use_tiles) {
-    a.tiles2 = (n_cells + st::kTileValid - 1) / st::kTileValid;
+    int sms = 148, dev = 0;
+#ifndef MARLPDE_HOST_EMU
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#endif
+    const int valid_l = st::tile_valid_cells(st::kTileThreadsLarge), valid_s = st::tile_valid_cells(st::kTileThreadsSmall);
+    const long long ctas_large = (long long)((n_cells + valid_l - 1) / valid_l) * n_columns;
+    small_tiles = 2 * ctas_large <= sms;
+    const char* tile_env = std::getenv("MARLPDE_RK45_TILE");
+    if (tile_env && tile_env[0] == 's') small_tiles = true;
+    if (tile_env && tile_env[0] == 'l') small_tiles = false;
+    const char* tma_env = std::getenv("MARLPDE_RK45_TILE_TMA");
+    tile_tma = tma_env && tma_env[0] == '1' && !small_tiles;
+    const int valid = small_tiles ? valid_s : valid_l;
+    a.tiles2 = (n_cells + valid - 1) / valid;
     tgrid = (unsigned)((long long)a.tiles2 * n_columns);
-    cudaError_t e = tile_kernel_smem<false, false>();
-    if (e == cudaSuccess) e = tile_kernel_smem<false, true>();
-    if (e == cudaSuccess) e = tile_kernel_smem<true, false>();
-    if (e == cudaSuccess) e = tile_kernel_smem<true, true>();
-    if (e != cudaSuccess) return e;
+    (void)dev;
   }
   const bool var_dphi = (opt.flags & MARLPDE_FLAG_VAR_DPHI) != 0;
   const bool ev_on = (opt.flags & MARLPDE_FLAG_EVENTS) != 0;
@@ -1011,13 +1046,10 @@ cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_param
     for (long long j = 0; j < attempts; ++j) {
       MARLPDE_LAUNCH(st::prepare_kernel, grid, st::kThreads, 0, s_, a, pin);
       if (use_tiles) {
-#define MARLPDE_TILE_LAUNCH(VD_, EV_) \
-  MARLPDE_LAUNCH((st::tile_attempt_kernel<VD_, EV_>), tgrid, st::kTileThreads, st::TileSmem::total, s_, a, pin ^ 1)
-        if (var_dphi && ev_on) MARLPDE_TILE_LAUNCH(true, true);
-        else if (var_dphi) MARLPDE_TILE_LAUNCH(true, false);
-        else if (ev_on) MARLPDE_TILE_LAUNCH(false, true);
-        else MARLPDE_TILE_LAUNCH(false, false);
-#undef MARLPDE_TILE_LAUNCH
+        const cudaError_t et = small_tiles
+                                   ? tile_dispatch<st::kTileThreadsSmall>(var_dphi, ev_on, false, a, tgrid, pin ^ 1, s_)
+                                   : tile_dispatch<st::kTileThreadsLarge>(var_dphi, ev_on, tile_tma, a, tgrid, pin ^ 1, s_);
+        if (et != cudaSuccess) return et;
       } else {
         for (int i = 1; i <= 6; ++i) MARLPDE_LAUNCH(st::stage_kernel, grid, st::kThreads, 0, s_, a, i, pin ^ 1);
       }
@@ -1045,6 +1077,8 @@ cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_param
     key.a = a;
     key.attempts = attempts;
     key.use_tiles = use_tiles;
+    key.small_tiles = small_tiles;
+    key.tile_tma = tile_tma;
     cudaError_t e = cudaGetDevice(&key.device);
     if (e != cudaSuccess) return e;
     if (!(cache.valid && std::memcmp(&cache.key, &key, sizeof key) == 0)) {

@@ -52,6 +52,20 @@ def run_radau(c):
     except Exception as exc:                         # numerical blow-up inside SciPy's linear algebra
         y_end, t_end, status, counts, ev = np.full(1000, np.nan), float("nan"), -9, [0, 0, 0, 0], [0] * 7
         print("radau", c, "raised", type(exc).__name__, exc, flush=True)
+    if status != 0:
+        # solve_ivp only returns the t_eval samples: step SciPy's Radau class by hand to learn where it stops
+        from scipy.integrate import Radau
+        solver = Radau(o.rhs_fn(o.kernel_params(pde)), 0.0, o.initial_state(pde), 1.0, first_step=1e-6, rtol=1e-3,
+                       atol=1e-3, jac_sparsity=o.jacobian_sparsity(200))
+        n = 0
+        try:
+            while solver.status == "running":
+                solver.step()
+                n += 1
+        except Exception as exc:
+            print("radau", c, "manual stepping raised", type(exc).__name__, flush=True)
+        y_end, t_end = np.array(solver.y), float(solver.t)
+        counts = [n, solver.nfev, solver.njev, solver.nlu]
     print("radau", c, "status", status, "t", t_end, "steps", counts[0], flush=True)
     return ("radau", c, status, t_end, y_end, counts, ev)
 
@@ -85,6 +99,11 @@ def main():
     jobs = [(run_rk45, c) for c in UNFINISHED_RK45 + HEALTHY]
     jobs += [(run_radau, c) for c in sorted(set(SPREAD + UNFINISHED_RK45))]
     out = {}
+    if len(sys.argv) > 1 and sys.argv[1] == "patch-failed-radau":       # re-run only the columns Radau does not finish
+        old = np.load(os.path.join(HERE, "lattice_reference.npz"))
+        out = {k: old[k] for k in old.files}
+        cols = json.loads(str(old["__columns__"]))["radau"]
+        jobs = [(run_radau, c) for c in cols if int(old[f"radau/{c}/status"]) != 0]
     with ProcessPoolExecutor(max_workers=min(8, os.cpu_count())) as ex:
         futs = [ex.submit(fn, c) for fn, c in jobs]
         for fu in futs:
@@ -95,7 +114,9 @@ def main():
             out[key + "/y"] = np.asarray(y_end, dtype=np.float64)
             out[key + "/counts"] = np.asarray(counts, dtype=np.int64)
             out[key + "/events"] = np.asarray(ev, dtype=np.int64)
-    out["__columns__"] = np.array(json.dumps({"rk45": UNFINISHED_RK45 + HEALTHY, "radau": sorted(set(SPREAD + UNFINISHED_RK45))}))
+    if "__columns__" not in out:
+        out["__columns__"] = np.array(json.dumps({"rk45": UNFINISHED_RK45 + HEALTHY,
+                                                  "radau": sorted(set(SPREAD + UNFINISHED_RK45))}))
     np.savez_compressed(os.path.join(HERE, "lattice_reference.npz"), **out)
     print("wrote lattice_reference.npz")
 

@@ -183,16 +183,20 @@ def emu_stream():
     out = os.path.join(EMU, "_build")
     os.makedirs(out, exist_ok=True)
     srcs = [os.path.join(EMU, f) for f in ("emu_stream.cc", "simt_emu.cc")]
-    libs = {}
-    for tma in (0, 1):                     # 1: the tile kernel's windows by 1-D bulk copies (-DMARLPDE_TILE_TMA=1, A/B candidate)
-        so = os.path.join(out, f"libemu_stream{tma}.so")
-        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", f"-DMARLPDE_TILE_TMA={tma}", "-I", EMU,
-                        "-o", so] + srcs, check=True, capture_output=True)
-        libs[tma] = C.CDLL(so)
-        libs[tma].emu_rk45_stream.restype = C.c_int
+    so = os.path.join(out, "libemu_stream.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", "-I", EMU, "-o", so] + srcs,
+                   check=True, capture_output=True)
+    lib = C.CDLL(so)
+    lib.emu_rk45_stream.restype = C.c_int
 
-    def run(P, y, t_end, t_eval, first_step, attempts, state=None, tma=0, events=False, counts=None, times=None, flags=0):
-        lib = libs[tma]
+    def run(P, y, t_end, t_eval, first_step, attempts, state=None, tma=0, events=False, counts=None, times=None, flags=0,
+            tile=None):
+        # the launcher reads its switches per call: TMA-staged windows, window size
+        os.environ["MARLPDE_RK45_TILE_TMA"] = "1" if tma else "0"
+        if tile:
+            os.environ["MARLPDE_RK45_TILE"] = tile
+        else:
+            os.environ.pop("MARLPDE_RK45_TILE", None)
         y = np.ascontiguousarray(y, dtype=np.float64).copy()
         P = np.ascontiguousarray(P)
         B, _, N = y.shape
@@ -245,10 +249,11 @@ def test_streaming_launcher_under_emulation_reproduces_scipy(emu_stream, n_cells
 
 @pytest.mark.parametrize("n_cells", [16, 628, 1256, 1884, 1300])
 def test_tile_kernel_bulk_copy_windows_are_bit_identical(emu_stream, n_cells, monkeypatch):
-    """-DMARLPDE_TILE_TMA=1 (A/B candidate, off by default): the tile kernel loads y and K1 of its 640-cell window and stores
-    y_new and K7 of the 628 cells it owns with ten 1-D bulk copies each way (on the host: memcpy at issue).  Window clipping
-    at both column ends, a column that ends exactly on a window boundary, one-window columns and a sampled step: the same
-    bits as the per-thread loads and stores."""
+    """MARLPDE_RK45_TILE_TMA=1 (shipped, off by default: measured 10 % slower on B200): the tile kernel loads y and K1 of
+    its 640-cell window and stores y_new and K7 of the 628 cells it owns with ten 1-D bulk copies each way (on the host:
+    memcpy at issue).  Window clipping at both column ends, a column that ends exactly on a window boundary, one-window
+    columns and a sampled step: the same bits as the per-thread loads and stores.  Also the small windows (128 threads,
+    244 owned cells) a small batch is cut into."""
     monkeypatch.setenv("MARLPDE_RK45_STREAM", "tiles")
     pde = oracle.default_scenario() | SCEN_A | {"N": n_cells}
     scale = min(1.0, (200 / n_cells) ** 2)
@@ -261,6 +266,13 @@ def test_tile_kernel_bulk_copy_windows_are_bit_identical(emu_stream, n_cells, mo
     assert a["state"]["n_accepted"][0] >= 8 and a["state"]["next_eval"][0] == 2
     assert np.array_equal(a["state"], b["state"]) and np.array_equal(a["y"], b["y"])
     assert np.array_equal(a["snapshots"][:, :2], b["snapshots"][:, :2])
+    # window size: the error norm adds one partial sum per window in window order, so the step sizes of the two window
+    # sizes may differ in their last bits — same decisions, states equal to round-off
+    c = emu_stream(P, y0, 1.0, te, fs, 12, tile="small")
+    for k in ("n_accepted", "n_rejected", "nfev", "status", "next_eval"):
+        assert np.array_equal(a["state"][k], c["state"][k]), k
+    assert abs(a["state"]["t"][0] - c["state"]["t"][0]) <= 1e-12 * a["state"]["t"][0]
+    assert np.max(np.abs(a["y"] - c["y"])) <= 1e-12 and np.max(np.abs(a["snapshots"][:, :2] - c["snapshots"][:, :2])) <= 1e-12
 
 
 @pytest.mark.parametrize("n_cells", [16, 1300])

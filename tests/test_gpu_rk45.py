@@ -285,6 +285,33 @@ def test_streaming_path_matches_scipy(n_cells, ncol, mode, monkeypatch):
     assert np.array_equal(res.y[0], res.y[-1])
 
 
+def test_streaming_window_sizes_and_tma_staging_agree(monkeypatch):
+    """The tile kernel's builds: 640-cell windows (large batches), 256-cell windows (small batches, chosen by the launcher
+    when the large ones would leave more than half of the SMs idle) and the TMA-staged large window
+    (MARLPDE_RK45_TILE_TMA=1: UBLKCP bulk loads / stores through shared memory; shipped, off by default because it
+    measured 10 % slower).  TMA staging is bit-identical to the per-thread loads; the window size only changes the order
+    in which the per-window error sums are added."""
+    n_cells = 2000
+    pde = oracle.default_scenario() | {"N": n_cells, "Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}
+    P, y0 = np.repeat(mb.derive_column_params(pde), 3), np.repeat(mb.initial_state(pde), 3, 0)
+    t_end, fs = 300 * 2.6e-6 / 100, 1e-6 / 100
+    run = lambda: mb.integrate_rk45_batch(y0, P, t_span=(0, t_end), first_step=fs, t_eval=[0.5 * t_end, t_end])
+    monkeypatch.setenv("MARLPDE_RK45_TILE", "large")
+    large = run()
+    monkeypatch.setenv("MARLPDE_RK45_TILE_TMA", "1")
+    tma = run()
+    monkeypatch.delenv("MARLPDE_RK45_TILE_TMA")
+    monkeypatch.setenv("MARLPDE_RK45_TILE", "small")
+    small = run()
+    monkeypatch.delenv("MARLPDE_RK45_TILE")
+    auto = run()
+    assert np.all(large.status == 0) and large.n_attempts[0] >= 200
+    assert np.array_equal(tma.y, large.y) and np.array_equal(tma.snapshots, large.snapshots) and np.array_equal(tma.nfev, large.nfev)
+    assert np.array_equal(auto.y, small.y)                       # 3 columns x 4 large windows: the launcher picks small ones
+    assert np.array_equal(small.nfev, large.nfev) and np.max(np.abs(small.y - large.y)) <= 1e-12
+    assert np.max(np.abs(small.snapshots - large.snapshots)) <= 1e-12
+
+
 def test_streaming_path_resume_device_tensors_and_budget():
     import torch
     n_cells = 1000

@@ -28,6 +28,7 @@
 #include <cstdint>
 
 #include "brent.cuh"
+#include "events.cuh"
 #include "lheureux_device.cuh"
 #include "radau_batch.cuh"
 
@@ -173,7 +174,7 @@ struct Args {
 // [cell][field]; sink(i, r5) receives the five rates of cell i.  All 32 lanes run every iteration
 // (rhs_pair votes), lanes without a pair work on benign values.  The 160-byte runs the NEXT 32 pairs
 // will read can be prefetched into L1 while the current ones are evaluated (RADAU_PF_RHS; off, see the switches).
-template <class Sink>
+template <bool VD, class Sink>
 __device__ __forceinline__ void rhs_column(const ColumnConsts& kc, const fm::Tables& tb, int N, int lane,
                                            const double* yy, const double* add, Sink&& sink) {
   const int Hc = (N + 1) >> 1;
@@ -213,9 +214,7 @@ __device__ __forceinline__ void rhs_column(const ColumnConsts& kc, const fm::Tab
     const bool in_mask[2] = {cell0 >= kc.mask_lo && cell0 < kc.mask_hi,
                              cell0 + 1 >= kc.mask_lo && cell0 + 1 < kc.mask_hi};
     double r[5][2], U[2], Wv[2];
-    // (kVarDPhi = true: a column flagged MARLPDE_MODEL_VAR_DPHI takes the per-cell porosity diffusion coefficient; for
-    //  the others the instantiation is bit-identical to the plain one and costs ~10 instructions per cell pair)
-    PairFlags fl = rhs_pair<rhs_schedule(kSchedAll), true>(kc, tb, c, mlo, phi, in_mask, r, U, Wv);
+    PairFlags fl = rhs_pair<rhs_schedule(kSchedAll), VD>(kc, tb, c, mlo, phi, in_mask, r, U, Wv);
     fl.bad[0] = fl.bad[0] && v0;
     fl.bad[1] = fl.bad[1] && v1;
     if (fl.bad[0] || fl.bad[1]) rhs_pair_fixup(kc, tb, fl, c, mlo, phi, in_mask, r, U, Wv);
@@ -239,13 +238,17 @@ __device__ __forceinline__ double fd_step(double y, double f, double atol) {
 
 // THE one instance of the RHS in this kernel (instruction-cache footprint matters: 12 warps per SM sit
 // in different phases of their columns): out = rhs(yy + add) (add may be NULL), all cell-major [N][5].
+// (VD: the kernel build for batches with MARLPDE_MODEL_VAR_DPHI columns.  This kernel competes for the instruction
+//  cache — 12 warps per SM in different phases, stall_no_instruction 0.9 per issue — so the default build carries none
+//  of the variant's code: always compiling it in measured 1.5 per issue.)
+template <bool VD>
 __device__ __noinline__ void rhs_eval(const ColumnConsts* kc, const fm::Tables* tb, int N, int lane, const double* yy,
                                       const double* add, double* out) {
   auto sink = [&](int i, const double (&r5)[5]) {
 #pragma unroll
     for (int f = 0; f < 5; ++f) out[i * 5 + f] = r5[f];
   };
-  rhs_column(*kc, *tb, N, lane, yy, add, sink);
+  rhs_column<VD>(*kc, *tb, N, lane, yy, add, sink);
   __syncwarp();
 }
 
@@ -272,6 +275,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // tridiagonal pattern needs (the reference's 27-diagonal pattern: 21).  One cell per lane, generic (IEEE) math
 // as in cell_rhs: no restriction on the state.  The formulas are checked against central differences of the
 // oracle RHS in tests/test_host_side.py::test_offdiagonal_jacobian_block_formulas.
+template <bool VD>
 __device__ __noinline__ void jac_columns(const ColumnConsts* kp, const fm::Tables* tbp, int N, int lane, int fld,
                                          const double* pert, const double* Fp, const double* y0, const double* f0,
                                          double atol, double* J) {
@@ -292,7 +296,7 @@ __device__ __noinline__ void jac_columns(const ColumnConsts* kp, const fm::Table
     const double den = fma(-2.0, fm::log(tb, Phi), 1.0);
     const double rden = fm::rcp(den);
     double dPhi = k.dPhi, kPePhi = k.kPePhi;                // MARLPDE_MODEL_VAR_DPHI: the cell's own coefficient (cell_rhs)
-    if (k.var_dphi) {
+    if (VD && k.var_dphi) {
       dPhi = k.auxcon * (Phi2 * Phi) * FoP;
       kPePhi = fm::div(k.half_dx, dPhi);
     }
@@ -370,6 +374,7 @@ __device__ __noinline__ void jac_columns(const ColumnConsts* kp, const fm::Table
 
 // J = d rhs / d y: per field one RHS evaluation with that field perturbed in every cell, then jac_columns.
 // `scratch` holds 2 x 5N doubles (perturbed state, its RHS).
+template <bool VD>
 __device__ __noinline__ void fd_jacobian(const ColumnConsts& kc, const fm::Tables& tb, int N, int lane, const double* y,
                                          const double* f, double atol, double* J, double* scratch) {
   const int n = 5 * N;
@@ -386,8 +391,8 @@ __device__ __noinline__ void fd_jacobian(const ColumnConsts& kc, const fm::Table
       pert[i * 5 + fld] = v + fd_step(v, f[i * 5 + fld], atol);
     }
     __syncwarp();
-    rhs_eval(&kc, &tb, N, lane, pert, nullptr, Fp);
-    jac_columns(&kc, &tb, N, lane, fld, pert, Fp, y, f, atol, J);
+    rhs_eval<VD>(&kc, &tb, N, lane, pert, nullptr, Fp);
+    jac_columns<VD>(&kc, &tb, N, lane, fld, pert, Fp, y, f, atol, J);
 #pragma unroll 1
     for (int i = lane; i < N; i += 32) pert[i * 5 + fld] = y[i * 5 + fld];
     __syncwarp();
@@ -708,7 +713,7 @@ __device__ __noinline__ void monitors(const ColumnConsts& kc, const fm::Tables& 
     m[6] = fmax(m[6], W);
     nanS |= (U != U) || (W != W);
   }
-#pragma unroll
+#pragma unroll 1
   for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
@@ -729,13 +734,65 @@ __device__ __noinline__ void monitors(const ColumnConsts& kc, const fm::Tables& 
   g[6] = (bPhi | bS) ? qnan : m[6];
 }
 
-__device__ __forceinline__ double predict_factor(double h_abs, double h_abs_old, double err, double err_old) {
+// Detection only needs the SIGN of each monitor (ivp.py find_active_events): 21 predicate bits per cell, OR-reduced
+// over the column — the same bookkeeping as the RK45 kernels (csrc/events.cuh).  This is what runs after every
+// accepted step; monitors() above (five times the code) only runs inside Brent when a sign change has to be located.
+__device__ __noinline__ unsigned monitor_bits(const ColumnConsts& kc, const fm::Tables& tb, int N, int lane,
+                                              const double* y) {
+  unsigned b = 0u;
+#pragma unroll 1
+  for (int i = lane; i < N; i += 32) {
+    double v[5][2], U[2], W[2];
+#pragma unroll
+    for (int f = 0; f < 5; ++f) v[f][0] = v[f][1] = y[i * 5 + f];
+    const double Phi = v[4][0];
+    const double F = 1.0 - fm::exp(tb, fma(-10.0, fm::rcp3(Phi), 10.0));
+    const double Phi2 = Phi * Phi;
+    U[0] = U[1] = fma(kc.rhorat * (Phi2 * Phi), F * fm::rcp3(1.0 - Phi), kc.presum);
+    W[0] = W[1] = fma(-kc.rhorat * Phi2, F, kc.presum);
+    b |= event_bits(v, U, W, false);
+  }
+  return __reduce_or_sync(0xffffffffu, b);
+}
+
+// brentq on the dense output between t_old and t for every monitor in `act` (ivp.py handle_events ->
+// solve_event_equation, xtol = rtol = 4 eps).  Rare, so it lives outside the step loop's instruction footprint.
+__device__ __noinline__ void locate_events(const Args& A, const ColumnConsts& kc, const fm::Tables& tb, int N, int lane,
+                                           int col, unsigned act, double t_old, double t, double h_old,
+                                           const double* yold, const double* Q) {
+#pragma unroll 1
+  for (int k = 0; k < 7; ++k) {
+    if (!((act >> k) & 1u)) continue;
+    BrentState bs;
+    bs.init(t_old, t);
+    double xeval = t_old, root = t;
+    for (;;) {
+      const double xx = (xeval - t_old) / h_old;
+      double gv[7];
+      monitors(kc, tb, N, lane, yold, Q, xx, gv);
+      double gk = gv[0];
+#pragma unroll
+      for (int kk = 1; kk < 7; ++kk) gk = (k == kk) ? gv[kk] : gk;
+      if (bs.feed(gk, xeval, root)) break;
+    }
+    if (lane == 0) {
+      int32_t* cnt = A.g_ev_counts + (size_t)col * MARLPDE_NEVENTS + k;
+      const int have = *cnt;
+      if (have < A.opt.event_capacity)
+        A.g_ev_times[((size_t)col * MARLPDE_NEVENTS + k) * A.opt.event_capacity + have] = root;
+      *cnt = have + 1;
+    }
+  }
+}
+
+__device__ __noinline__ double predict_factor(double h_abs, double h_abs_old, double err, double err_old) {
   // radau.py predict_factor; "None" is encoded as a negative value
   double mult = 1.0;
   if (!(err_old < 0.0 || h_abs_old < 0.0 || err == 0.0)) mult = h_abs / h_abs_old * sqrt(sqrt(err_old / err));
   return fmin(1.0, mult) / sqrt(sqrt(err));      // x**0.25 as two square roots; err == 0 -> inf, as numpy
 }
 
+template <bool VD>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) radau_kernel(const Args A) {
   __shared__ __align__(16) unsigned char tab_raw[fm::kTableBytes];
   __shared__ WarpScratch scratch[kWarpsPerCta];
@@ -787,20 +844,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
     long long steps_done = 0;
 
     auto eval_to = [&](const double* yy, const double* add, double* out) {   // out = rhs(yy + add)
-      rhs_eval(&kc, &tb, N, lane, yy, add, out);
+      rhs_eval<VD>(&kc, &tb, N, lane, yy, add, out);
     };
 
     if (t < A.opt.t_bound) {
       eval_to(y, nullptr, w.f);
       nfev += 1;
-      fd_jacobian(kc, tb, N, lane, y, w.f, atol, w.J, w.B);
+      fd_jacobian<VD>(kc, tb, N, lane, y, w.f, atol, w.J, w.B);
       njev += 1;
       nfev += 5;   // Jacobian: one evaluation per field (fd_jacobian)
     }
     const bool ev_on = (A.opt.flags & MARLPDE_FLAG_EVENTS) != 0;
-    double g_old[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    unsigned ev_prev = 0u;
     if (ev_on && t < A.opt.t_bound)                        // ivp.py: g = [event(t0, y0) for event in events]
-      monitors(kc, tb, N, lane, y, nullptr, 0.0, g_old);
+      ev_prev = monitor_bits(kc, tb, N, lane, y);
     bool current_jac = true, lu_valid = false, have_sol = false;
     double h_abs_old = -1.0, err_old = -1.0;     // "None"
     double t_old = t, h_old = 0.0;
@@ -954,7 +1011,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
           if (converged) break;
           n_newton_fail += 1;
           if (current_jac) break;
-          fd_jacobian(kc, tb, N, lane, y, w.f, atol, w.J, w.B);
+          fd_jacobian<VD>(kc, tb, N, lane, y, w.f, atol, w.J, w.B);
           njev += 1;
           nfev += 5;   // Jacobian: one evaluation per field (fd_jacobian)
           current_jac = true;
@@ -1026,7 +1083,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
       eval_to(y, nullptr, w.f);
       nfev += 1;
       if (recompute_jac) {
-        fd_jacobian(kc, tb, N, lane, y, w.f, atol, w.J, w.B);
+        fd_jacobian<VD>(kc, tb, N, lane, y, w.f, atol, w.J, w.B);
         njev += 1;
         nfev += 5;   // Jacobian: one evaluation per field (fd_jacobian)
         current_jac = true;
@@ -1044,34 +1101,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
       steps_done += 1;
       // ---- events (ivp.py main loop: after every accepted step, before the t_eval samples)
       if (ev_on) {
-        double g_new[7];
-        monitors(kc, tb, N, lane, y, nullptr, 0.0, g_new);
-#pragma unroll 1
-        for (int k = 0; k < 7; ++k) {
-          if (!event_active(g_old[k], g_new[k])) continue;
-          // brentq on the dense output between t_old and t (solve_event_equation, xtol = rtol = 4 eps)
-          BrentState bs;
-          bs.init(t_old, t);
-          double xeval = t_old, root = t;
-          for (;;) {
-            const double xx = (xeval - t_old) / h_old;
-            double gv[7];
-            monitors(kc, tb, N, lane, w.yold, w.Q, xx, gv);
-            double gk = gv[0];
-#pragma unroll
-            for (int kk = 1; kk < 7; ++kk) gk = (k == kk) ? gv[kk] : gk;
-            if (bs.feed(gk, xeval, root)) break;
-          }
-          if (lane == 0) {
-            int32_t* cnt = A.g_ev_counts + (size_t)col * MARLPDE_NEVENTS + k;
-            const int have = *cnt;
-            if (have < A.opt.event_capacity)
-              A.g_ev_times[((size_t)col * MARLPDE_NEVENTS + k) * A.opt.event_capacity + have] = root;
-            *cnt = have + 1;
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 7; ++k) g_old[k] = g_new[k];
+        const unsigned ev_new = monitor_bits(kc, tb, N, lane, y);
+        unsigned act = 0u;
+        if (ev_new != ev_prev || (ev_new & kEqBitsMask) != 0u) act = active_events(event_classes(ev_prev), event_classes(ev_new));
+        ev_prev = ev_new;
+        if (act) locate_events(A, kc, tb, N, lane, col, act, t_old, t, h_old, w.yold, w.Q);   // rare: kept out of line
       }
       // ---- t_eval samples in (t_old, t] (t_eval[0] == t0 belongs to the first step): y_old + Q p(x)
       while (next_eval < A.opt.n_eval) {
@@ -1134,7 +1168,8 @@ cudaError_t launch_radau(double* d_y, const marlpde_column_params* d_params, mar
   const int max_ctas = sm_count * MARLPDE_RADAU_MINBLOCKS;
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas < 1) ctas = 1;
-  rd::radau_kernel<<<ctas, rd::kWarpsPerCta * 32, 0, stream>>>(a);
+  if (opt.flags & MARLPDE_FLAG_VAR_DPHI) rd::radau_kernel<true><<<ctas, rd::kWarpsPerCta * 32, 0, stream>>>(a);
+  else rd::radau_kernel<false><<<ctas, rd::kWarpsPerCta * 32, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

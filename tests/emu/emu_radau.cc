@@ -28,5 +28,8 @@ extern "C" int emu_radau(double* y, const marlpde_column_params* params, marlpde
   a.n_columns = n_columns;
   a.N = n_cells;
   a.opt = *opt;
-  return simt::run_block(rd::kWarpsPerCta * 32, 0, [&]() { rd::radau_kernel(a); });
+  return simt::run_block(rd::kWarpsPerCta * 32, 0, [&]() {
+    if (a.opt.flags & MARLPDE_FLAG_VAR_DPHI) rd::radau_kernel<true>(a);
+    else rd::radau_kernel<false>(a);
+  });
 }

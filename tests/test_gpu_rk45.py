@@ -388,7 +388,7 @@ def test_streaming_path_events_match_scipy(n_cells):
     Y = np.concatenate([y0, mb.initial_state(pde), y0])
     res = mb.integrate_rk45_batch(Y, np.repeat(P, 3), t_span=(0, t_end), first_step=fs, t_eval=[0, t_end],
                                   events=True, event_capacity=8)
-    assert np.all(res.status == 0) and np.all(np.abs(res.nfev - sol.nfev) <= 12)
+    assert np.all(res.status == 0) and np.all(np.abs(res.nfev[[0, 2]] - sol.nfev) <= 12)
     for c in (0, 2):
         assert list(res.event_counts[c]) == want_counts
         for got, want in zip(_event_lists(res, c), sol.t_events):

@@ -504,8 +504,10 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         # of the model near t = 0.5-0.7 and end with status -1 (step below 10 ulp, as SciPy does); how many
         # attempts they burn there is chaotic (0.7-6.8 M seen for the same column in two builds that differ by
         # FMA contraction only) and a lone column advances at ~50 k attempts/s, so the cap bounds the tail.
+        # (quantum-major work items: the columns advance together in rounds of ~60 k attempts, so the slots do not run
+        #  dry one by one over the 15 s a whole column takes)
         o2 = _cabi.RK45Options(t_bound=1.0, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=args.step_cap, n_eval=0,
-                               event_capacity=EVCAP, flags=_cabi.FLAG_EVENTS, quantum=0)
+                               event_capacity=EVCAP, flags=_cabi.FLAG_EVENTS | _cabi.FLAG_QUEUE_LOCKS, quantum=0)
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         f0.record(s3.stream)
@@ -517,7 +519,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         tot = int(st2["n_accepted"].sum() + st2["n_rejected"].sum())
         flops = float(tot) * FLOP_PER_COLUMN_STEP_PER_CELL * N
         line["time_to_Tstar"] = {
-            "method": "RK45 (rk45_persistent_kernel, one launch, columns claimed longest-first)",
+            "method": "RK45 (rk45_persistent_kernel, one launch, quantum-major work items)",
             "seconds": secs, "columns": B, "step_attempts": tot, "column_steps_per_s": tot / secs,
             "step_cap_per_column": args.step_cap, "finished": int((st2["status"] == 0).sum()),
             "status_histogram": {str(int(k)): int(v) for k, v in zip(*np.unique(st2["status"], return_counts=True))},
@@ -544,6 +546,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                 nB = sweep.n_columns_of(sw)
                 assign = sweep.balanced_assignment(sweep.predicted_cost(sw) * np.ones(nB), world)
                 mine = assign[rank]
+                mine = mine[np.argsort(-sweep.predicted_cost(sw)[mine] * np.ones(len(mine)), kind="stable")]
             else:
                 # columns are claimed from a queue in batch order: longest first by the a-priori cost estimate
                 mine = np.argsort(-sweep.predicted_cost(sw) * np.ones(B), kind="stable")

@@ -449,7 +449,8 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
               // later items of the column may find nothing left to do)
               used = __ldcg(A.g_queue + 1 + A.n_columns + cc);
               const long long target = (used / A.quantum + 1) * A.quantum;
-              budget = target < A.opt.max_steps ? target : A.opt.max_steps;
+              if (A.opt.max_steps > 0) budget = target < A.opt.max_steps ? target : A.opt.max_steps;
+              else budget = used / A.quantum + 1 >= A.n_quanta ? 0 : target;   // no budget: the column's last item runs to the end
             }
           }
           ctl.budget = budget;
@@ -808,14 +809,21 @@ static unsigned long long rk45_warp_perm(int n_warps) {
 // runs ceil(columns / slots) rounds and the last round is only partly filled: 4096 columns on 444 slots are 9.22
 // rounds of work in 10 rounds of time.  Cutting the budget into quanta that are claimed quantum-major makes the
 // partly filled round 1 / n_quanta as long.  Needs the per-column lock and counter words (MARLPDE_FLAG_QUEUE_LOCKS)
-// and a finite budget; opt.quantum > 0 fixes the quantum, < 0 switches it off.  The end point of a column does not
-// depend on the quanta: it is the first accepted step at which the launch's attempts reach max_steps, as without them.
+// opt.quantum > 0 fixes the quantum, < 0 switches it off.  The end point of a column does not depend on the quanta: it is
+// the first accepted step at which the launch's attempts reach max_steps, as without them.  Without a budget (a sweep
+// integrated to t_bound in one launch) the columns take 0.5-1.2 M attempts each and the slots of the last round run dry
+// one by one over the duration of a whole column (~5 % of a 4096-column sweep to T*): there the launch is cut into 32
+// quanta of 65 536 attempts, and a column's last item runs without a limit.
 static void choose_quanta(Rk45Args& a, int slots) {
   a.n_quanta = 1;
   a.quantum = 0;
-  if (!(a.opt.flags & MARLPDE_FLAG_QUEUE_LOCKS) || a.opt.max_steps <= 0 || a.opt.quantum < 0) return;
+  if (!(a.opt.flags & MARLPDE_FLAG_QUEUE_LOCKS) || a.opt.quantum < 0) return;
   const long long budget = a.opt.max_steps;
-  if (a.opt.quantum > 0) {
+  if (budget <= 0) {
+    if (a.n_columns <= slots) return;
+    a.quantum = a.opt.quantum > 0 ? a.opt.quantum : 65536;
+    a.n_quanta = 32;
+  } else if (a.opt.quantum > 0) {
     a.quantum = a.opt.quantum;
     a.n_quanta = (int)((budget + a.quantum - 1) / a.quantum);
   } else {

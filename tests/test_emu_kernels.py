@@ -102,6 +102,15 @@ def test_quantum_major_work_items_are_bit_identical_to_whole_column_claims(emu, 
     assert np.array_equal(auto["y"], ref["y"])
     assert np.all(auto["state"]["nfev"] > ref["state"]["nfev"])    # it did cut the budget
     assert np.array_equal(auto["state"]["n_accepted"], ref["state"]["n_accepted"])
+    # no step budget (a sweep integrated to t_bound in one launch): 32 quanta, a column's last item runs without a limit
+    whole = emu(320, P, y0, 2.5e-4, t_eval=te, events=True)
+    for q in (2, 9):                      # 64 / 288 attempts in quanta: the rest of a column in its last item / all in quanta
+        cut = emu(320, P, y0, 2.5e-4, t_eval=te, events=True, quantum=q)
+        assert np.all(cut["state"]["status"] == 0) and np.all(cut["state"]["t"] == 2.5e-4), q
+        assert np.array_equal(cut["y"], whole["y"]) and np.array_equal(cut["snapshots"], whole["snapshots"], equal_nan=True), q
+        assert np.array_equal(cut["state"]["n_accepted"], whole["state"]["n_accepted"]), q
+        assert np.array_equal(cut["event_counts"], whole["event_counts"]), q
+        assert np.all(cut["state"]["nfev"] > whole["state"]["nfev"]), q
 
 
 def test_time_varying_dPhi_instantiation_under_emulation(emu):

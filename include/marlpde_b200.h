@@ -109,6 +109,10 @@ typedef struct marlpde_rk45_options {
                                     attempt counter per column): the on-chip RK45 kernel may then cut every column's step budget into
                                     quanta claimed quantum-major, which shortens the partly filled last round of a
                                     launch (results are unchanged: a resumed column is bit-identical)          */
+#define MARLPDE_FLAG_QUEUE_TAIL 8u /* with MARLPDE_FLAG_QUEUE_LOCKS and max_steps > 0: only the last columns of the batch (2 x the
+                                    resident slots) are cut into quanta, the others are claimed whole — for sweeps whose
+                                    columns need different numbers of attempts, ordered longest first (launches without
+                                    a step budget do this by themselves)                                              */
 #define MARLPDE_FLAG_VAR_DPHI 4u /* some columns of the batch carry MARLPDE_MODEL_VAR_DPHI (see marlpde_column_params) */
 
 /* Per-column integrator state: input (start/resume point) and output (end point). */

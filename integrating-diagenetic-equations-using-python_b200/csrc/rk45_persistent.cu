@@ -106,6 +106,7 @@ struct Rk45Args {
   double* g_ev_times;        // [n_columns][7][event_capacity]
   int n_columns, N, C, logG;
   int n_quanta;                   // work items per column (1: a claim covers the column's whole step budget)
+  int n_whole;                    // the first n_whole columns are claimed whole, only the others are cut into quanta
   long long quantum;              // step attempts per work item when n_quanta > 1
   unsigned long long warp_perm;   // logical warp of physical warp w = (warp_perm >> 4 w) & 15 (see rk45_warp_perm)
   marlpde_rk45_options opt;
@@ -433,12 +434,19 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
         int item = pending_item >= 0 ? pending_item : atomicAdd(A.g_queue, 1);
         pending_item = -1;
         int cc = -1;
-        if (item < A.n_columns * A.n_quanta) {
-          const int q = item / A.n_columns;
-          cc = item - q * A.n_columns;
+        const int n_cut = A.n_columns - A.n_whole;       // columns that are cut into quanta (the last ones of the batch)
+        if (item < A.n_whole + n_cut * A.n_quanta) {
+          bool cut = false;
+          if (item < A.n_whole) {
+            cc = item;
+          } else {
+            const int j = item - A.n_whole, q = j / n_cut;
+            cc = A.n_whole + (j - q * n_cut);
+            cut = A.n_quanta > 1;
+          }
           long long budget = A.opt.max_steps > 0 ? A.opt.max_steps : 0;
           long long used = 0;
-          if (A.n_quanta > 1) {
+          if (cut) {
             if (atomicCAS(A.g_queue + 1 + cc, 0, 1) != 0) {
               pending_item = item;
               cc = -2;
@@ -812,17 +820,28 @@ static unsigned long long rk45_warp_perm(int n_warps) {
 // opt.quantum > 0 fixes the quantum, < 0 switches it off.  The end point of a column does not depend on the quanta: it is
 // the first accepted step at which the launch's attempts reach max_steps, as without them.  Without a budget (a sweep
 // integrated to t_bound in one launch) the columns take 0.5-1.2 M attempts each and the slots of the last round run dry
-// one by one over the duration of a whole column (~5 % of a 4096-column sweep to T*): there the launch is cut into 32
-// quanta of 65 536 attempts, and a column's last item runs without a limit.
+// one by one over the duration of a whole column (~5 % of a 4096-column sweep to T*).  Cutting EVERY column into quanta is
+// wrong there — the columns would advance in lock-step and the longest ones (up to 2.4x the shortest) would finish alone at
+// the speed of a lone column (measured, r02i: 151 s instead of 138 s).  Instead the first columns of the batch are claimed
+// whole and only the LAST 2 x slots columns are cut into quanta (32 768 attempts; a column's last item runs without a
+// limit): with the batch ordered longest first (callers sort by sweep.predicted_cost) the long columns start first and the
+// short ones fill the end of the launch evenly.  MARLPDE_FLAG_QUEUE_TAIL asks for the same with a step budget.
 static void choose_quanta(Rk45Args& a, int slots) {
   a.n_quanta = 1;
   a.quantum = 0;
+  a.n_whole = 0;
   if (!(a.opt.flags & MARLPDE_FLAG_QUEUE_LOCKS) || a.opt.quantum < 0) return;
   const long long budget = a.opt.max_steps;
-  if (budget <= 0) {
+  if (budget <= 0 || (a.opt.flags & MARLPDE_FLAG_QUEUE_TAIL)) {
     if (a.n_columns <= slots) return;
-    a.quantum = a.opt.quantum > 0 ? a.opt.quantum : 65536;
+    a.quantum = a.opt.quantum > 0 ? a.opt.quantum : 32768;
     a.n_quanta = 32;
+    if (budget > 0) {
+      if ((budget + a.quantum - 1) / a.quantum > 64) a.quantum = (budget + 63) / 64;
+      a.n_quanta = (int)((budget + a.quantum - 1) / a.quantum);
+    }
+    const int n_cut = a.n_columns < 2 * slots ? a.n_columns : 2 * slots;
+    a.n_whole = a.n_columns - n_cut;
   } else if (a.opt.quantum > 0) {
     a.quantum = a.opt.quantum;
     a.n_quanta = (int)((budget + a.quantum - 1) / a.quantum);
@@ -848,6 +867,7 @@ static void choose_quanta(Rk45Args& a, int slots) {
   if (a.n_quanta <= 1) {
     a.n_quanta = 1;
     a.quantum = 0;
+    a.n_whole = 0;
   }
 }
 
@@ -890,6 +910,7 @@ cudaError_t launch_rk45(double* d_y, const marlpde_column_params* d_params, marl
   a.C = 0;
   a.logG = 0;
   a.n_quanta = 1;
+  a.n_whole = 0;
   a.quantum = 0;
   a.warp_perm = 0;
   a.opt = opt;

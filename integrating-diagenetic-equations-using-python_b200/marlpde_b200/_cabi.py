@@ -19,6 +19,7 @@ STATUS_FINISHED, STATUS_STEP_TOO_SMALL, STATUS_NONFINITE, STATUS_STEP_BUDGET = 0
 FLAG_EVENTS = 1
 FLAG_QUEUE_LOCKS = 2
 FLAG_VAR_DPHI = 4
+FLAG_QUEUE_TAIL = 8
 MODEL_VAR_DPHI = 1
 
 

@@ -38,6 +38,7 @@ extern "C" int emu_rk45(int variant, double* y, const marlpde_column_params* par
   a.warp_perm = ~0ull;
   a.opt = *opt;
   a.n_quanta = 1;
+  a.n_whole = 0;
   a.quantum = 0;
   // EMU_SLOTS: pretend the launch has this many resident slots when the library chooses the quanta itself
   const char* se = std::getenv("EMU_SLOTS");

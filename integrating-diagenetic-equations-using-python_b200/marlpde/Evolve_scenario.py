@@ -194,7 +194,7 @@ def integrate_equations_batch(solver_parms, tracker_parms, pde_parms, store_fold
     shape (B,) (see marlpde_b200.sweep_lattice) or a list of such dictionaries.  All columns are
     integrated in one launch of the persistent RK45 kernel.  Returns the marlpde_b200.RK45Result;
     with `store_folder` one HDF5 file per sweep is written (datasets `solutions` (B,5,N,n_t),
-    `times`, `status`, `nfev`, `n_accepted`, `n_rejected`, `t_reached`, `event_counts`)."""
+    `times`, `status`, `nfev`, `n_accepted`, `n_rejected`, `next_eval`, `t_reached`, `event_counts`)."""
     if isinstance(pde_parms, (list, tuple)):
         keys = pde_parms[0].keys()
         pde_parms = {k: (np.array([p[k] for p in pde_parms]) if k != "N" else pde_parms[0]["N"]) for k in keys}
@@ -216,7 +216,8 @@ def integrate_equations_batch(solver_parms, tracker_parms, pde_parms, store_fold
         with hdf5lite.File(os.path.join(store_folder, "LMAHeureuxPorosityDiff_sweep.hdf5"), "w") as stored:
             stored.create_dataset("solutions", data=np.transpose(np.asarray(res.snapshots), (0, 2, 3, 1)))
             stored.create_dataset("times", data=res.t_eval)
-            for name in ("status", "nfev", "n_accepted", "n_rejected", "event_counts"):
+            # next_eval: rows of `solutions` that hold data for a column (the rest is NaN: the column stopped early)
+            for name in ("status", "nfev", "n_accepted", "n_rejected", "event_counts", "next_eval"):
                 stored.create_dataset(name, data=np.asarray(getattr(res, name), dtype=np.int64))
             stored.create_dataset("t_reached", data=res.t)
             for k in ("sedimentationrate", "b", "DCO3", "Xstar", "Tstar"):

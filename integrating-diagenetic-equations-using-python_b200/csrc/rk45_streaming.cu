@@ -1012,8 +1012,8 @@ cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_param
   const char* mode_env = std::getenv("MARLPDE_RK45_STREAM");
   const int use_tiles = (mode_env && mode_env[0] == 's') ? 0 : 1;
   unsigned tgrid = 0;
-  // window size: small windows while the large ones would leave more than half of the SMs without a CTA
-  // (MARLPDE_RK45_TILE=small|large overrides); MARLPDE_RK45_TILE_TMA=1 selects the TMA-staged build of the large window
+  // window size (MARLPDE_RK45_TILE=small|large overrides); MARLPDE_RK45_TILE_TMA=1 selects the TMA-staged build of the
+  // large window
   bool small_tiles = false, tile_tma = false;
   if (use_tiles) {
     int sms = 148, dev = 0;
@@ -1021,8 +1021,12 @@ cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_param
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 #endif
     const int valid_l = st::tile_valid_cells(st::kTileThreadsLarge), valid_s = st::tile_valid_cells(st::kTileThreadsSmall);
-    const long long ctas_large = (long long)((n_cells + valid_l - 1) / valid_l) * n_columns;
-    small_tiles = 2 * ctas_large <= sms;
+    // small windows while ALL of them are resident at once (two 128-thread CTAs per SM: one wave at about two thirds
+    // of a large window's latency).  Measured (r02f, r02l; column-steps/s, small vs large): 20 000 x 1 49.6 k / 41.5 k,
+    // 20 000 x 3 130 k / 121 k, 5 000 x 12 567 k / 504 k, 2 000 x 32 1.53 M / 1.36 M — but 20 000 x 4 (328 small CTAs:
+    // two waves) 127 k / 160 k and 20 000 x 8 162 k / 176 k.
+    const long long ctas_small = (long long)((n_cells + valid_s - 1) / valid_s) * n_columns;
+    small_tiles = ctas_small <= 2LL * sms;
     const char* tile_env = std::getenv("MARLPDE_RK45_TILE");
     if (tile_env && tile_env[0] == 's') small_tiles = true;
     if (tile_env && tile_env[0] == 'l') small_tiles = false;

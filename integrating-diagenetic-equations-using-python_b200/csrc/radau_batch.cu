@@ -105,11 +105,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Tuning switches, all measured on 4096 columns (r01c, baseline 2.48 s to t = 0.05) and left OFF: with 16 columns
 // per SM in flight the kernel is bound by DRAM traffic (1.6-1.8 TB/s of 1-kB runs), so more loads in flight lose:
 //   RADAU_BATCH4 (four strides of loads per trip of the element-wise passes) 2.68 s,
-//   RADAU_PF_RHS (L1 prefetch of the next 32 cell pairs of an RHS evaluation) 2.55 s,
+//   (L1 prefetch of the next 32 cell pairs of an RHS evaluation 2.55 s — replaced in r02m by cp.async staging),
 //   RADAU_PF_SOLVE (L1 prefetch of the right-hand side 8 cells ahead in the sweeps) 2.57 s.
-#ifndef RADAU_PF_RHS
-#define RADAU_PF_RHS 0
-#endif
 #ifndef RADAU_PF_SOLVE
 #define RADAU_PF_SOLVE 0
 #endif
@@ -143,8 +140,16 @@ __host__ __device__ inline size_t work_doubles(int N) {
   return 18 * n + 76 * (size_t)N + 64 * (size_t)N;   // 76: keeps the double2 array 16-byte aligned
 }
 
+#ifndef MARLPDE_RADAU_RHS_STAGE
+#define MARLPDE_RADAU_RHS_STAGE 1
+#endif
+constexpr int kStageDoubles = 66 * 5;       // cells 2 base - 1 .. 2 base + 64 of one pass of an RHS evaluation
+
 struct __align__(16) WarpScratch {          // shared memory per warp
   ColumnConsts kc;
+  union {                       // an RHS evaluation never overlaps a factorisation or a solve
+  double stage[2][2][kStageDoubles + 6];   // RHS: double-buffered windows of yy and add for the pass in flight (cp.async)
+  struct {
   double2 vec[2][2][2][8];    // solve: two broadcast buffers x two chains x two systems x 5 entries (padded)
   // factorise (lane = 5 r + c holds entry (r, c) of [S | I] of both systems):
   double2 g0[2][32];          //   double-buffered exchange stage, real system: (S entry, I entry)
@@ -160,7 +165,10 @@ struct __align__(16) WarpScratch {          // shared memory per warp
     double jst[kSlots][80];      // factorise: staged Jacobian blocks [L|D|U] of the next cells of the schedule (ring)
     double mst[2][kSlots][52];   // solve: per chain, 51 eight-byte words of a cell's fp32 record (ring)
   };
+  };
+  };
 };
+static_assert(sizeof(WarpScratch) * kWarpsPerCta + fm::kTableBytes <= 48 * 1024, "static shared memory of the Radau kernel");
 
 struct Args {
   double* g_y;
@@ -179,29 +187,52 @@ struct Args {
 
 // One RHS evaluation of the whole column by one warp: state = yy (+ add, may be NULL), both cell-major
 // [cell][field]; sink(i, r5) receives the five rates of cell i.  All 32 lanes run every iteration
-// (rhs_pair votes), lanes without a pair work on benign values.  The 160-byte runs the NEXT 32 pairs
-// will read can be prefetched into L1 while the current ones are evaluated (RADAU_PF_RHS; off, see the switches).
+// (rhs_pair votes), lanes without a pair work on benign values.
+// (r02m) The inputs of a pass — the 40-byte runs of cells 2 base - 1 .. 2 base + 64 of yy and add — are staged in
+// shared memory by cp.async one pass AHEAD: the ncu source page attributed 15 % of the kernel's stall samples to these
+// loads.  Measured: 64 columns to t = 0.05 0.486 -> 0.467 s (a lone warp is latency bound); 4096 columns unchanged
+// (1.42 s: with 1 776 columns in flight the kernel is bound by DRAM throughput, the stalls just move).
 template <bool VD, class Sink>
 __device__ __forceinline__ void rhs_column(const ColumnConsts& kc, const fm::Tables& tb, int N, int lane,
-                                           const double* yy, const double* add, Sink&& sink) {
+                                           const double* yy, const double* add, double (*stage)[2][kStageDoubles + 6],
+                                           Sink&& sink) {
   const int Hc = (N + 1) >> 1;
+#if MARLPDE_RADAU_RHS_STAGE
+  auto issue = [&](int base, int b) {          // window of the pass that starts at pair `base` -> stage[b]
+    const int c_lo = base > 0 ? 2 * base - 1 : 0;
+    const int c_hi = 2 * base + 65 < N ? 2 * base + 65 : N;
+    const int d_lo = c_lo * 5, cnt = (c_hi - c_lo) * 5;
+    for (int k = lane; k < cnt; k += 32) {
+      cp_async8(&stage[b][0][k], yy + d_lo + k);
+      if (add) cp_async8(&stage[b][1][k], add + d_lo + k);
+    }
+    cp_async_commit();
+  };
+  issue(0, 0);
+  int buf = 0;
+#else
   auto ld = [&](int ff, int i) -> double { return add ? yy[i * 5 + ff] + add[i * 5 + ff] : yy[i * 5 + ff]; };
+#endif
 #pragma unroll 1
   for (int base = 0; base < Hc; base += 32) {
     const int p = base + lane;
     const int cell0 = 2 * p;
-    if (RADAU_PF_RHS && base + 32 < Hc) {
-      const int cn = 2 * (p + 32) - 1;                      // first cell the next iteration touches
-      if (cn < N) {
-        const size_t o = (size_t)cn * 5, o2 = o + 16 < (size_t)5 * N ? o + 16 : o;   // stay inside the vector
-        prefetch_l1(yy + o);
-        prefetch_l1(yy + o2);
-        if (add) {
-          prefetch_l1(add + o);
-          prefetch_l1(add + o2);
-        }
-      }
+#if MARLPDE_RADAU_RHS_STAGE
+    if (base + 32 < Hc) {
+      issue(base + 32, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
+    __syncwarp();                                 // every lane's copies of this pass have landed
+    const int c_lo = base > 0 ? 2 * base - 1 : 0;
+    const double* const sy = stage[buf][0];
+    const double* const sa = stage[buf][1];
+    auto ld = [&](int ff, int i) -> double {
+      const int k = (i - c_lo) * 5 + ff;
+      return add ? sy[k] + sa[k] : sy[k];
+    };
+#endif
     const bool v0 = cell0 < N, v1 = cell0 + 1 < N;
     double c[5][2], mlo[5], phi[5];
 #pragma unroll
@@ -233,6 +264,10 @@ __device__ __forceinline__ void rhs_column(const ColumnConsts& kc, const fm::Tab
       const double r5[5] = {r[0][1], r[1][1], r[2][1], r[3][1], r[4][1]};
       sink(cell0 + 1, r5);
     }
+#if MARLPDE_RADAU_RHS_STAGE
+    __syncwarp();                                 // this buffer is the target of the copies issued in the next trip
+    buf ^= 1;
+#endif
   }
 }
 
@@ -250,12 +285,12 @@ __device__ __forceinline__ double fd_step(double y, double f, double atol) {
 //  of the variant's code: always compiling it in measured 1.5 per issue.)
 template <bool VD>
 __device__ __noinline__ void rhs_eval(const ColumnConsts* kc, const fm::Tables* tb, int N, int lane, const double* yy,
-                                      const double* add, double* out) {
+                                      const double* add, double* out, double (*stage)[2][kStageDoubles + 6]) {
   auto sink = [&](int i, const double (&r5)[5]) {
 #pragma unroll
     for (int f = 0; f < 5; ++f) out[i * 5 + f] = r5[f];
   };
-  rhs_column<VD>(*kc, *tb, N, lane, yy, add, sink);
+  rhs_column<VD>(*kc, *tb, N, lane, yy, add, stage, sink);
   __syncwarp();
 }
 
@@ -383,7 +418,8 @@ __device__ __noinline__ void jac_columns(const ColumnConsts* kp, const fm::Table
 // `scratch` holds 2 x 5N doubles (perturbed state, its RHS).
 template <bool VD>
 __device__ __noinline__ void fd_jacobian(const ColumnConsts& kc, const fm::Tables& tb, int N, int lane, const double* y,
-                                         const double* f, double atol, double* J, double* scratch) {
+                                         const double* f, double atol, double* J, double* scratch,
+                                         double (*stage)[2][kStageDoubles + 6]) {
   const int n = 5 * N;
   double* const pert = scratch;
   double* const Fp = scratch + n;
@@ -398,7 +434,7 @@ __device__ __noinline__ void fd_jacobian(const ColumnConsts& kc, const fm::Table
       pert[i * 5 + fld] = v + fd_step(v, f[i * 5 + fld], atol);
     }
     __syncwarp();
-    rhs_eval<VD>(&kc, &tb, N, lane, pert, nullptr, Fp);
+    rhs_eval<VD>(&kc, &tb, N, lane, pert, nullptr, Fp, stage);
     jac_columns<VD>(&kc, &tb, N, lane, fld, pert, Fp, y, f, atol, J);
 #pragma unroll 1
     for (int i = lane; i < N; i += 32) pert[i * 5 + fld] = y[i * 5 + fld];
@@ -573,6 +609,10 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, double 
 //   inward :  top    p_i = S_i^{-1} (b_i + L_i p_{i-1}),   bottom q_i = T_i^{-1} (b_i + U_i q_{i+1})      (lock-step)
 //   meeting:  x_mid  = S_mid^{-1} (b_mid + L_mid p_{mid-1} + U_mid q_{mid+1})
 //   outward:  top    x_i = p_i + S_i^{-1} (U_i x_{i+1}),    bottom x_i = q_i + T_i^{-1} (L_i x_{i-1})     (lock-step)
+// (Measured and dropped, r02n: outward sweep x_i = p_i + X_i x_next with X_i = S_i^{-1} N_i stored by the factorisation —
+//  one dependent mat-vec and one warp barrier per cell instead of two, 304 instead of 408 record bytes per cell, but
+//  832 instead of 512 bytes written per cell and factorisation: 1.42 vs 1.46 s at t = 0.05, 0.469 vs 0.469 s for 64
+//  columns, 21.6 vs 21.2 s to T*: neutral, not worth 60 % more workspace.)
 // Both chains of both systems run side by side in one warp, so a solve takes N/2 sequential steps per direction
 // instead of N.  As in factorise(), the records of the next kDepth cells of each chain are in flight (cp.async)
 // while the current cell is processed; a sweep reads 51 eight-byte words of a cell's record: words [0,51) =
@@ -851,13 +891,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
     long long steps_done = 0;
 
     auto eval_to = [&](const double* yy, const double* add, double* out) {   // out = rhs(yy + add)
-      rhs_eval<VD>(&kc, &tb, N, lane, yy, add, out);
+      rhs_eval<VD>(&kc, &tb, N, lane, yy, add, out, ws.stage);
     };
 
     if (t < A.opt.t_bound) {
       eval_to(y, nullptr, w.f);
       nfev += 1;
-      fd_jacobian<VD>(kc, tb, N, lane, y, w.f, atol, w.J, w.B);
+      fd_jacobian<VD>(kc, tb, N, lane, y, w.f, atol, w.J, w.B, ws.stage);
       njev += 1;
       nfev += 5;   // Jacobian: one evaluation per field (fd_jacobian)
     }
@@ -1018,7 +1058,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
           if (converged) break;
           n_newton_fail += 1;
           if (current_jac) break;
-          fd_jacobian<VD>(kc, tb, N, lane, y, w.f, atol, w.J, w.B);
+          fd_jacobian<VD>(kc, tb, N, lane, y, w.f, atol, w.J, w.B, ws.stage);
           njev += 1;
           nfev += 5;   // Jacobian: one evaluation per field (fd_jacobian)
           current_jac = true;
@@ -1090,7 +1130,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
       eval_to(y, nullptr, w.f);
       nfev += 1;
       if (recompute_jac) {
-        fd_jacobian<VD>(kc, tb, N, lane, y, w.f, atol, w.J, w.B);
+        fd_jacobian<VD>(kc, tb, N, lane, y, w.f, atol, w.J, w.B, ws.stage);
         njev += 1;
         nfev += 5;   // Jacobian: one evaluation per field (fd_jacobian)
         current_jac = true;

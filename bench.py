@@ -549,12 +549,13 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             if world > 1:
                 sw = sweep.shard(sw, strided_selection(lat[0] * lat[1] * lat[2], world))
                 nB = sweep.n_columns_of(sw)
-                assign = sweep.balanced_assignment(sweep.predicted_cost(sw) * np.ones(nB), world)
+                cost_i = sweep.predicted_cost(sw, "Radau") * np.ones(nB)
+                assign = sweep.balanced_assignment(cost_i, world)
                 mine = assign[rank]
-                mine = mine[np.argsort(-sweep.predicted_cost(sw)[mine] * np.ones(len(mine)), kind="stable")]
+                mine = mine[np.argsort(-cost_i[mine], kind="stable")]
             else:
                 # columns are claimed from a queue in batch order: longest first by the a-priori cost estimate
-                mine = np.argsort(-sweep.predicted_cost(sw) * np.ones(B), kind="stable")
+                mine = np.argsort(-sweep.predicted_cost(sw, "Radau") * np.ones(B), kind="stable")
             barrier()
             rr, secs = implicit_sweep(mb, batch, torch, dev, sw, mine, EVCAP, t_eval=t_eval)
             blk = implicit_block(rr, secs, N, hbm_gbs, hbm_src)

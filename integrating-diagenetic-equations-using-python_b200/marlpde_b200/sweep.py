@@ -31,9 +31,20 @@ def partition(n_columns: int, world_size: int) -> list[tuple[int, int]]:
     return out
 
 
-def predicted_cost(pde: dict) -> np.ndarray:
-    """Relative number of explicit steps a column needs to reach T*: the step size is bound by the
-    diffusive stability limit, steps ~ rho(J) ~ dCO3 * (Xstar * N / max_depth)^2."""
+def predicted_cost(pde: dict, method: str = "RK45") -> np.ndarray:
+    """Relative cost of integrating a column to T*, used only to ORDER columns (longest first) and to balance shards.
+
+    RK45: number of explicit steps — the step size is bound by the diffusive stability limit,
+    steps ~ rho(J) ~ dCO3 * (Xstar * N / max_depth)^2.
+    Radau: the implicit integrator does not see that limit; its work (step attempts incl. failed Newton episodes) is
+    governed by how sharp the porosity front gets, i.e. by the compaction coefficient b (dPhi ~ 1/b).  Empirical fit on
+    the 4096-column benchmark lattice (default base, r02o): work ~ b^2.16 S^-0.66 DCO3^0.05, rank correlation 0.996 —
+    the a-priori RK45 estimate has correlation 0.13 with it."""
+    if method == "Radau":
+        b = np.atleast_1d(np.asarray(pde["b"], dtype=np.float64))
+        srate = np.atleast_1d(np.asarray(pde["sedimentationrate"], dtype=np.float64))
+        cost = b ** 2.16 * srate ** -0.66
+        return np.broadcast_to(cost, np.broadcast_shapes(np.shape(b), np.shape(srate))).astype(np.float64)
     n = int(pde["N"])
     xstar = np.atleast_1d(np.asarray(pde["Xstar"], dtype=np.float64))
     d = np.atleast_1d(np.asarray(pde["DCO3"], dtype=np.float64)) / np.asarray(pde["D0Ca"], dtype=np.float64)
@@ -128,7 +139,7 @@ def sweep_rk45(pde: dict, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e-3, atol=1e
     rank = dist.get_rank(group) if ddp else 0
     B = n_columns_of(pde)
     if balance and world > 1:
-        assign = balanced_assignment(predicted_cost(pde) * np.ones(B), world)
+        assign = balanced_assignment(predicted_cost(pde, method) * np.ones(B), world)
     else:
         assign = [np.arange(a, b, dtype=np.int64) for a, b in partition(B, world)]
     mine = assign[rank]

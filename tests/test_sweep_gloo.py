@@ -80,3 +80,17 @@ def test_partition_and_balanced_assignment():
     assert totals.max() / totals.min() < 1.001 < blocks.max() / blocks.min()   # contiguous blocks are 1.4x apart
     sub = sweep.shard(pde, parts[3])
     assert sub["Xstar"].shape == (128,) and sub["N"] == 200 and np.isscalar(sub["D0Ca"])
+
+
+def test_predicted_cost_orders_the_implicit_sweep_by_compaction_coefficient():
+    """The a-priori cost estimates only order columns: RK45 by the diffusive stability limit, Radau by the empirical
+    b^2.16 S^-0.66 law measured on the benchmark lattice (sweep.predicted_cost)."""
+    pde = mb.sweep_lattice(oracle.default_scenario(), 4, 4, 4)
+    ce, ci = sweep.predicted_cost(pde), sweep.predicted_cost(pde, "Radau")
+    assert ce.shape == ci.shape == (64,)
+    b, srate = np.asarray(pde["b"]), np.asarray(pde["sedimentationrate"])
+    heavy, light = np.argmax(ci), np.argmin(ci)
+    assert b[heavy] == b.max() and srate[heavy] == srate.min() and b[light] == b.min() and srate[light] == srate.max()
+    assert np.corrcoef(ce, ci)[0, 1] < 0.9                   # the explicit estimate follows DCO3 and Xstar instead
+    assign = sweep.balanced_assignment(ci, 2)
+    assert abs(ci[assign[0]].sum() / ci[assign[1]].sum() - 1.0) < 0.02

@@ -554,22 +554,13 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
                 mine = assign[rank]
                 mine = mine[np.argsort(-cost_i[mine], kind="stable")]
             else:
-                # columns are claimed from a queue in batch order: longest first by the a-priori cost estimate
+                # columns are claimed from a queue in batch order: longest first by the a-priori cost estimate of the
+                # implicit path (sweep.predicted_cost: 21.2 s in lattice order, 18.3 s in this order, 17.9-18.5 s when
+                # ordered by the work MEASURED in a previous sweep — the estimate leaves nothing on the table)
                 mine = np.argsort(-sweep.predicted_cost(sw, "Radau") * np.ones(B), kind="stable")
             barrier()
             rr, secs = implicit_sweep(mb, batch, torch, dev, sw, mine, EVCAP, t_eval=t_eval)
             blk = implicit_block(rr, secs, N, hbm_gbs, hbm_src)
-            if world == 1 and base_name == "default" and not args.no_repeat_sweep:
-                # A column is sequential in time and a few columns (next to the model's singularity) need 3-5x the
-                # average number of steps, which the a-priori estimate does not see: the sweep ends with a tail of lone
-                # warps.  A REPEATED sweep can pass the columns longest-first by the work measured in the first one.
-                lpt = mine[np.argsort(-rr.work, kind="stable")]
-                rr2, secs2 = implicit_sweep(mb, batch, torch, dev, sw, lpt, EVCAP, t_eval=t_eval)
-                blk["repeat_sweep_longest_first"] = {
-                    "seconds": secs2, "finished": int((rr2.status == 0).sum()),
-                    "what": "the same sweep again, columns ordered by the work measured in the first sweep "
-                            "(RadauResult.work); `seconds` above is the first, cold sweep"}
-                del rr2
             if dist is not None:
                 # the one collective of the sweep: snapshots [B/G, 2, 5, N] of every rank to every rank
                 tt = torch.tensor([secs], dtype=torch.float64, device=dev)
@@ -697,7 +688,6 @@ def main():
                     help="time-to-T* without the ~140 s explicit sweep (implicit sweep only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cpu-radau", action="store_true", help="skip the SciPy Radau sample beside the implicit sweep")
-    ap.add_argument("--no-repeat-sweep", action="store_true", help="skip the repeated, longest-first implicit sweep")
     ap.add_argument("--cpu-t-end", type=float, default=0.03, help="CPU sample: integrate to this fraction of T*")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -58,7 +58,8 @@ struct Ctl {                                   // per-column control block (doub
   int locate;                                  // events: 1 = the accepted step in flight has a sign change; the attempt
                                                // is replayed with K3..K6 stored, then its roots are located and it commits
   unsigned ev_prev;                            // predicate bits of the monitors at the start of the current step
-  int pad;
+  int skip;                                    // tile path: the attempt described here has NOT been run yet (the launch that
+                                               // located the events of the previous step ran no attempt): nothing to close
 };
 
 struct Args {
@@ -69,9 +70,11 @@ struct Args {
   double* snap;
   double* K;                 // [7][B][5][N]
   double* tile;              // [2][B][5][N]
-  double* partials;          // [B][tiles]
+  double* partials;          // [2][B][pstride]: written by the launch that runs an attempt under control buffer p into
+                             // parity p, read by the launch that closes it (the fused tile kernel closes the previous
+                             // attempt in its prologue while faster CTAs of the same launch already write the next sums)
   Ctl* ctl;                  // [2][B]
-  unsigned* evpart;          // [B][tiles] predicate bits of the monitors per CTA / window (MARLPDE_FLAG_EVENTS)
+  unsigned* evpart;          // [2][B][pstride] predicate bits of the monitors per CTA / window (MARLPDE_FLAG_EVENTS)
   int32_t* ev_counts;        // [B][7]
   double* ev_times;          // [B][7][event_capacity]
   int B, N, tiles;
@@ -92,9 +95,9 @@ __host__ inline Layout layout(int B, int N) {
   size_t o = 0;
   L.off_K = o;     o += align256(7 * vec);
   L.off_tile = o;  o += align256(2 * vec);
-  L.off_part = o;  o += align256(sizeof(double) * (size_t)tiles * B);
+  L.off_part = o;  o += align256(sizeof(double) * 2 * (size_t)tiles * B);     // [2 parities][B][tiles]
   L.off_ctl = o;   o += align256(sizeof(Ctl) * 2 * (size_t)B);
-  L.off_ev = o;    o += align256(sizeof(unsigned) * (size_t)tiles * B);
+  L.off_ev = o;    o += align256(sizeof(unsigned) * 2 * (size_t)tiles * B);
   L.total = o;
   return L;
 }
@@ -145,7 +148,7 @@ __global__ void init_kernel(const Args A) {
   c.ysl = 0;
   c.locate = 0;
   c.ev_prev = 0u;
-  c.pad = 0;
+  c.skip = 0;
   if (s.t >= A.opt.t_bound) {
     c.active = 0;
     c.status = MARLPDE_STATUS_FINISHED;
@@ -214,14 +217,21 @@ __global__ void __launch_bounds__(kThreads) copyback_kernel(const Args A, int pa
   }
 }
 
+__device__ __forceinline__ double* partials_of(const Args& A, int parity, int col) {
+  return A.partials + ((size_t)parity * A.B + col) * A.pstride;
+}
+__device__ __forceinline__ unsigned* evpart_of(const Args& A, int parity, int col) {
+  return A.evpart + ((size_t)parity * A.B + col) * A.pstride;
+}
+
 // ---- event location (ivp.py handle_events -> solve_event_equation: brentq on the dense output of the step), run by
 // ONE CTA of the column: the monitor value at y(t + x h) is a min over all cells of the quartic interpolant (K1, K3..K6,
 // K7 and y of the step that has just been recomputed with all its stage derivatives stored).  Same arithmetic as
 // rk45_persistent.cu::event_partial, so both paths locate the same roots.  All threads of the CTA call this.
 __device__ void locate_events(const Args& A, const Ctl& c, int col, unsigned act, const fm::Tables& tb) {
   __shared__ ColumnConsts kc;
-  __shared__ double redm[kThreads / 32];
-  const int N = A.N;
+  __shared__ double redm[32];
+  const int N = A.N, n_thr = (int)blockDim.x, n_warps = (n_thr + 31) >> 5;
   const size_t vec = (size_t)A.B * 5 * N;
   if (threadIdx.x == 0) make_consts(A.params[col], N, kc);
   __syncthreads();
@@ -253,7 +263,7 @@ __device__ void locate_events(const Args& A, const Ctl& c, int col, unsigned act
     for (;;) {
       const double x = (xeval - c.t) / c.h;
       double v = INFINITY;
-      for (int cell = threadIdx.x; cell < N; cell += kThreads) {
+      for (int cell = threadIdx.x; cell < N; cell += n_thr) {
         double w;
         if (k == 0) {
           w = fmin(fmin(fmin(interp(0, cell, x), interp(1, cell, x)), fmin(interp(2, cell, x), interp(3, cell, x))),
@@ -283,7 +293,7 @@ __device__ void locate_events(const Args& A, const Ctl& c, int col, unsigned act
       if ((threadIdx.x & 31) == 0) redm[threadIdx.x >> 5] = v;
       __syncthreads();
       double mval = redm[0];
-      for (int w = 1; w < kThreads / 32; ++w) mval = fmin(mval, redm[w]);
+      for (int w = 1; w < n_warps; ++w) mval = fmin(mval, redm[w]);
       const double g = (k == 3 || k == 4) ? (-mval) - 1.0 : (k == 6 ? -mval : mval);
       double root = 0.0;
       if (bs.feed(g, xeval, root)) {                        // (uniform: every thread holds the same state)
@@ -300,23 +310,32 @@ __device__ void locate_events(const Args& A, const Ctl& c, int col, unsigned act
   }
 }
 
-// ---- prepare: close the previous attempt of every column (error norm -> accept/reject -> new h,
-// dense output, y <- y_new, FSAL slot swap) and form the stage-2 input of the next attempt.
-// Reads control buffer `pin`, writes `pin ^ 1`.
-__global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin) {
-  __shared__ __align__(16) unsigned char tab_raw[fm::kTableBytes];
-  const fm::Tables tb = fm::stage_tables(tab_raw, threadIdx.x, blockDim.x);
-  __syncthreads();
-  const Cells m = my_cells(A);
+// ---- close the previous attempt of a column (error norm -> accept/reject -> new h, dense output, y <- y_new, FSAL slot
+// swap) and begin the next one.  Reads control buffer `pin` (and the partial sums / predicate words of parity `pin`),
+// publishes the new control block in `pin ^ 1` (first CTA of the column) and returns it: every CTA of a column derives
+// the same block from the same inputs.  `m` = the cells this THREAD writes dense-output samples for.  Called by every
+// thread of the CTA (the event location inside has block barriers).  `run` = whether the attempt described by the
+// returned block is to be run by the caller now (tile path only; false for a column that is done, and for the launch
+// in which the events of a step were located: the locating CTA reads every cell's stage derivatives, so no CTA of the
+// column may start overwriting them).
+__device__ Ctl close_and_begin(const Args& A, int pin, const Cells& m, bool first_cta, const fm::Tables& tb, bool& run) {
   const int N = A.N;
   const size_t vec = (size_t)A.B * 5 * N;
   Ctl c = A.ctl[(size_t)pin * A.B + m.col];
-  const bool publisher = blockIdx.x == m.col * A.tiles && threadIdx.x == 0;
+  const bool publisher = first_cta && threadIdx.x == 0;
   const bool ev_on = (A.opt.flags & MARLPDE_FLAG_EVENTS) != 0;
+  run = false;
   if (!c.active) {
     if (publisher) A.ctl[(size_t)(pin ^ 1) * A.B + m.col] = c;
-    return;
+    return c;
   }
+  if (c.skip) {                                // committed in the previous launch, not run yet: nothing to close
+    c.skip = 0;
+    run = true;
+    if (publisher) A.ctl[(size_t)(pin ^ 1) * A.B + m.col] = c;
+    return c;
+  }
+  bool located = false;
   double* const tile0 = A.tile;
   double* const tile1 = A.tile + vec;
   const double* K1 = A.K + (size_t)c.k1 * vec;
@@ -324,7 +343,7 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin
     // ---- error norm of the attempt that just ran: per-CTA partial sums, fixed order
     double sum = 0.0;
     const int n_part = A.tiles2 > 0 ? A.tiles2 : A.tiles;
-    const double* part = A.partials + (size_t)m.col * A.pstride;
+    const double* part = partials_of(A, pin, m.col);
     for (int i = 0; i < n_part; ++i) sum += part[i];
     const double err_norm = sqrt(sum / (double)(5 * N));
     c.nfev += 6;
@@ -334,7 +353,7 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin
     bool replay = false;
     unsigned ev_new = 0u;
     if (ev_on && err_norm < 1.0) {
-      const unsigned* evp = A.evpart + (size_t)m.col * A.pstride;
+      const unsigned* evp = evpart_of(A, pin, m.col);
       for (int i = 0; i < n_part; ++i) ev_new |= evp[i];
       unsigned act = 0u;
       if (ev_new != c.ev_prev || (ev_new & kEqBitsMask) != 0u)
@@ -348,8 +367,9 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin
           c.nfev -= 6;
           c.attempts -= 1;
         } else {
-          if (blockIdx.x == m.col * A.tiles) locate_events(A, c, m.col, act, tb);   // CTA-uniform
+          if (first_cta) locate_events(A, c, m.col, act, tb);   // CTA-uniform
           c.locate = 0;
+          located = true;
         }
       }
     }
@@ -440,7 +460,7 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin
   } else {
     c.fresh = 0;
     if (ev_on) {                               // monitors at the start point (ivp.py: g = event(t0, y0)), from the K1 launch
-      const unsigned* evp = A.evpart + (size_t)m.col * A.pstride;
+      const unsigned* evp = evpart_of(A, pin, m.col);       // (written by the K1 launch, parity 0 = the first `pin`)
       unsigned b = 0u;
       for (int i = 0; i < A.tiles; ++i) b |= evp[i];
       c.ev_prev = b;
@@ -464,7 +484,21 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin
       st2(tile1, m, f, N, fma(ha, k0, y0), fma(ha, k1v, y1));
     }
   }
+  run = c.active != 0 && !located;
+  if (A.tiles2 > 0 && c.active && located) c.skip = 1;      // the attempt begun here runs in the NEXT launch
   if (publisher) A.ctl[(size_t)(pin ^ 1) * A.B + m.col] = c;
+  return c;
+}
+
+// ---- prepare: close_and_begin as a kernel of its own — the one-launch-per-stage variant runs it before every attempt,
+// the tile path (whose attempt kernel does this in its prologue) only once, to close the last attempt of a batch.
+__global__ void __launch_bounds__(kThreads) prepare_kernel(const Args A, int pin) {
+  __shared__ __align__(16) unsigned char tab_raw[fm::kTableBytes];
+  const fm::Tables tb = fm::stage_tables(tab_raw, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const Cells m = my_cells(A);
+  bool run;
+  close_and_begin(A, pin, m, blockIdx.x == m.col * A.tiles, tb, run);
 }
 
 // Stage algebra as data: after K_{i+1} = r has been evaluated, the next stage input is
@@ -583,7 +617,7 @@ __global__ void __launch_bounds__(kThreads, 3) stage_kernel(const Args A, int i,
       if (threadIdx.x == 0) {
         unsigned b = 0u;
         for (int w = 0; w < kThreads / 32; ++w) b |= sbits[w];
-        A.evpart[(size_t)m.col * A.pstride + (blockIdx.x - m.col * A.tiles)] = b;
+        evpart_of(A, cbuf, m.col)[blockIdx.x - m.col * A.tiles] = b;
       }
     }
   } else if (i < 6) {
@@ -612,7 +646,7 @@ __global__ void __launch_bounds__(kThreads, 3) stage_kernel(const Args A, int i,
     if (threadIdx.x == 0) {
       double s = 0.0;
       for (int w = 0; w < kThreads / 32; ++w) s += red[w];
-      A.partials[(size_t)m.col * A.pstride + (blockIdx.x - m.col * A.tiles)] = s;
+      partials_of(A, cbuf, m.col)[blockIdx.x - m.col * A.tiles] = s;
     }
   }
 }
@@ -655,7 +689,7 @@ struct TileSmemT {
 
 // VD: batches with MARLPDE_MODEL_VAR_DPHI columns (opt.flags & MARLPDE_FLAG_VAR_DPHI); EV: MARLPDE_FLAG_EVENTS
 template <bool VD, bool EV, int TT, bool TMA>
-__global__ void __launch_bounds__(TT, 1) tile_attempt_kernel(const Args A, int cbuf) {
+__global__ void __launch_bounds__(TT, 1) tile_attempt_kernel(const Args A, int pin) {
   MARLPDE_DYN_SMEM(smem_raw);
   using TileSmem = TileSmemT<TT, TMA>;
   constexpr int kTileThreads = TT, kTileCells = 2 * TT, kTileValid = tile_valid_cells(TT);
@@ -663,8 +697,27 @@ __global__ void __launch_bounds__(TT, 1) tile_attempt_kernel(const Args A, int c
   const int tid = threadIdx.x;
   const int col = blockIdx.x / A.tiles2;
   const int tile = blockIdx.x - col * A.tiles2;
-  const Ctl c0 = A.ctl[(size_t)cbuf * A.B + col];
-  if (!c0.active) return;                                   // uniform per CTA
+  const int N = A.N;
+  const fm::Tables tb = fm::stage_tables(smem_raw + TileSmem::off_tab, tid, blockDim.x);
+  __syncthreads();
+  // ---- prologue (r02q): close the PREVIOUS attempt of the column and begin this one — what used to be a launch of
+  // its own (prepare_kernel) between two attempts.  Every CTA of the column derives the same control block; this thread
+  // writes the dense-output samples of the cells its window owns.  One launch per attempt instead of two: a batch of a
+  // few columns is bound by launch latency (N = 20 000 x 1: 49.8 k -> see DESIGN.md section 9, r02q).
+  Ctl c0;
+  {
+    const int pe0 = 2 * tid, pg0 = tile * kTileValid - kTileHalo + pe0;
+    Cells mt;
+    mt.col = col;
+    mt.pair = 0;
+    mt.cell0 = pg0 < 0 ? 0 : pg0;
+    mt.v0 = pg0 >= 0 && pg0 < N && pe0 >= kTileHalo && pe0 < kTileCells - kTileHalo;
+    mt.v1 = pg0 + 1 >= 0 && pg0 + 1 < N && pe0 + 1 >= kTileHalo && pe0 + 1 < kTileCells - kTileHalo;
+    mt.base = (size_t)col * 5 * N + (size_t)mt.cell0;
+    bool run;
+    c0 = close_and_begin(A, pin, mt, tile == 0, tb, run);
+    if (!run) return;                                       // uniform per CTA
+  }
   double2* const sK = reinterpret_cast<double2*>(smem_raw + TileSmem::off_K) + tid;
   double* const sE = reinterpret_cast<double*>(smem_raw + TileSmem::off_E);
   double* const sO = reinterpret_cast<double*>(smem_raw + TileSmem::off_O);
@@ -673,8 +726,6 @@ __global__ void __launch_bounds__(TT, 1) tile_attempt_kernel(const Args A, int c
   uint64_t* const sBar = reinterpret_cast<uint64_t*>(smem_raw + TileSmem::off_bar);   // split barrier of the stage loop
   if (tid == 0) mbar_init(sBar, blockDim.x);
   unsigned bar_parity = 0;
-  const fm::Tables tb = fm::stage_tables(smem_raw + TileSmem::off_tab, tid, blockDim.x);
-  const int N = A.N;
   if (tid == 0) make_consts(A.params[col], N, kc);
   const size_t vec = (size_t)A.B * 5 * N;
   const double h = c0.h;
@@ -918,11 +969,11 @@ __global__ void __launch_bounds__(TT, 1) tile_attempt_kernel(const Args A, int c
   if (tid == 0) {
     double s = 0.0;
     for (int w = 0; w < kTileThreads / 32; ++w) s += red[w];
-    A.partials[(size_t)col * A.pstride + tile] = s;
+    partials_of(A, pin ^ 1, col)[tile] = s;               // (parity of the control block this attempt ran under)
     if constexpr (EV) {
       unsigned b = 0u;
       for (int w = 0; w < kTileThreads / 32; ++w) b |= reinterpret_cast<unsigned*>(red + kTileThreads / 32)[w];
-      A.evpart[(size_t)col * A.pstride + tile] = b;
+      evpart_of(A, pin ^ 1, col)[tile] = b;
     }
     if (TMA && tma) {                                        // the cells this window owns: window positions [6, 2 TT - 6) inside the column
       const int olo = w0 + kTileHalo, ohi = olo + kTileValid < N ? olo + kTileValid : N;
@@ -1048,13 +1099,13 @@ cudaError_t launch_rk45_stream(double* d_y, const marlpde_column_params* d_param
     int pin = 0;
     // attempts + 1 prepares: the last one only closes the last attempt
     for (long long j = 0; j < attempts; ++j) {
-      MARLPDE_LAUNCH(st::prepare_kernel, grid, st::kThreads, 0, s_, a, pin);
-      if (use_tiles) {
+      if (use_tiles) {             // the tile kernel closes the previous attempt in its prologue: ONE launch per attempt
         const cudaError_t et = small_tiles
-                                   ? tile_dispatch<st::kTileThreadsSmall>(var_dphi, ev_on, false, a, tgrid, pin ^ 1, s_)
-                                   : tile_dispatch<st::kTileThreadsLarge>(var_dphi, ev_on, tile_tma, a, tgrid, pin ^ 1, s_);
+                                   ? tile_dispatch<st::kTileThreadsSmall>(var_dphi, ev_on, false, a, tgrid, pin, s_)
+                                   : tile_dispatch<st::kTileThreadsLarge>(var_dphi, ev_on, tile_tma, a, tgrid, pin, s_);
         if (et != cudaSuccess) return et;
       } else {
+        MARLPDE_LAUNCH(st::prepare_kernel, grid, st::kThreads, 0, s_, a, pin);
         for (int i = 1; i <= 6; ++i) MARLPDE_LAUNCH(st::stage_kernel, grid, st::kThreads, 0, s_, a, i, pin ^ 1);
       }
       pin ^= 1;

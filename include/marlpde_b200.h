@@ -245,12 +245,44 @@ int marlpde_radau_integrate_async(double* y, const marlpde_column_params* params
                                   double* snapshots, int32_t* event_counts, double* event_times,
                                   int64_t* stats, int device, void* stream);
 
+/* ---- batched implicit integrator: variable-order BDF (orders 1-5, NDF coefficients, quasi-constant step)
+ * (replaces solve_ivp(method="BDF", jac_sparsity=...) per column — marlpde/parameters.py:213-216, :235-236;
+ * scipy/integrate/_ivp/bdf.py — and is the device path for method="LSODA" batches, parameters.py:214-219: on this
+ * stiff system LSODA runs in its BDF mode, see csrc/bdf_batch.cu) -----------------------------------------
+ *  Arguments, outputs and statistics exactly as for marlpde_radau_integrate*; events are located with Brent's
+ *  method on the BDF dense output (the step's differences array).  The workspace is
+ *  marlpde_bdf_workspace_bytes(n_columns, n_cells).  A column that stops on the step budget resumes at
+ *  order 1 from (t, h_abs, y): the differences array is not part of marlpde_column_state.
+ */
+size_t marlpde_bdf_workspace_bytes(int n_columns, int n_cells);
+int marlpde_bdf_integrate_dev(double* d_y, const marlpde_column_params* d_params,
+                              marlpde_column_state* d_state, int n_columns, int n_cells,
+                              const marlpde_rk45_options* opts, const double* d_t_eval,
+                              double* d_snapshots, int32_t* d_event_counts, double* d_event_times,
+                              int64_t* d_stats, void* d_workspace, size_t workspace_bytes,
+                              int32_t* d_queue, void* stream);
+int marlpde_bdf_integrate(double* y, const marlpde_column_params* params,
+                          marlpde_column_state* state, int n_columns, int n_cells,
+                          const marlpde_rk45_options* opts, const double* t_eval,
+                          double* snapshots, int32_t* event_counts, double* event_times,
+                          int64_t* stats, int device);
+int marlpde_bdf_integrate_async(double* y, const marlpde_column_params* params,
+                                marlpde_column_state* state, int n_columns, int n_cells,
+                                const marlpde_rk45_options* opts, const double* t_eval,
+                                double* snapshots, int32_t* event_counts, double* event_times,
+                                int64_t* stats, int device, void* stream);
+
 /* ---- measurement helper: fp64 FMA peak (TFLOP/s, best of `repeats`) of `device`, the roofline
  * denominator of the fp64-pipe-bound RK45 kernel (no reference counterpart). */
 int marlpde_probe_fp64_peak(int device, int iters, int repeats, double* tflops);
 /* test helper: element-wise evaluation of the kernels' own fp64 maths (csrc/fp64_math.cuh) on HOST
  * arrays: op 0 log, 1 exp, 2 expm1, 3 reciprocal, 4 (1+x)/x, 5 Fiadeiro-Veronis coth(x)-1/x. */
 int marlpde_probe_math(int op, const double* x, int n, double* out, int device);
+/* test helper: the block-tridiagonal Jacobian the implicit kernels use (analytic 5x5 blocks), for ONE column
+ * on HOST arrays: y [5][n_cells] field-major, J_out [n_cells][3][5][5] = blocks L, D, U of every cell, each
+ * stored [column][row]. */
+int marlpde_probe_jacobian(const double* y, const marlpde_column_params* params, int n_cells, double* J_out,
+                           int device);
 
 #ifdef __cplusplus
 }

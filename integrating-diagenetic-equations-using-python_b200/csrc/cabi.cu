@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/marlpde_b200.h"
+#include "bdf_batch.cuh"
 #include "radau_batch.cuh"
 #include "rk45_persistent.cuh"
 #include "rk45_streaming.cuh"
@@ -493,27 +494,40 @@ int marlpde_rk45_stream_integrate_dev(double* d_y, const marlpde_column_params* 
                                                   nullptr, nullptr, d_workspace, workspace_bytes, stream);
 }
 
-size_t marlpde_radau_workspace_bytes(int n_columns, int n_cells) {
-  if (n_columns <= 0 || n_cells <= 0) return 0;
-  return marlpde::radau_workspace_bytes(n_columns, n_cells);
+// ---- implicit integrators: the Radau IIA and the BDF kernel share arguments, buffers and checks ----------------------
+enum ImplicitKind { kRadau = 0, kBdf = 1 };
+
+static size_t implicit_workspace_bytes(ImplicitKind kind, int n_columns, int n_cells) {
+  return kind == kRadau ? marlpde::radau_workspace_bytes(n_columns, n_cells)
+                        : marlpde::bdf_workspace_bytes(n_columns, n_cells);
 }
 
-static int check_radau_args(int n_columns, int n_cells, const marlpde_rk45_options* opts) {
+size_t marlpde_radau_workspace_bytes(int n_columns, int n_cells) {
+  if (n_columns <= 0 || n_cells <= 0) return 0;
+  return implicit_workspace_bytes(kRadau, n_columns, n_cells);
+}
+
+size_t marlpde_bdf_workspace_bytes(int n_columns, int n_cells) {
+  if (n_columns <= 0 || n_cells <= 0) return 0;
+  return implicit_workspace_bytes(kBdf, n_columns, n_cells);
+}
+
+static int check_implicit_args(int n_columns, int n_cells, const marlpde_rk45_options* opts) {
   if (!opts) return fail(MARLPDE_EINVAL, "opts is NULL");
   if (n_columns < 0) return fail(MARLPDE_EINVAL, "n_columns < 0");
-  if (n_cells < 3) return fail(MARLPDE_EINVAL, "the implicit integrator needs n_cells >= 3 (got %d)", n_cells);
+  if (n_cells < 3) return fail(MARLPDE_EINVAL, "the implicit integrators need n_cells >= 3 (got %d)", n_cells);
   if (!(opts->rtol > 0.0) || !(opts->atol >= 0.0)) return fail(MARLPDE_EINVAL, "need rtol > 0, atol >= 0");
   if (!(opts->max_step > 0.0)) return fail(MARLPDE_EINVAL, "max_step must be positive (use +inf for none)");
   if (opts->n_eval < 0) return fail(MARLPDE_EINVAL, "negative n_eval");
   return MARLPDE_OK;
 }
 
-int marlpde_radau_integrate_dev(double* d_y, const marlpde_column_params* d_params, marlpde_column_state* d_state,
-                                int n_columns, int n_cells, const marlpde_rk45_options* opts,
-                                const double* d_t_eval, double* d_snapshots, int32_t* d_event_counts,
-                                double* d_event_times, int64_t* d_stats, void* d_workspace, size_t workspace_bytes,
-                                int32_t* d_queue, void* stream) {
-  int rc = check_radau_args(n_columns, n_cells, opts);
+static int implicit_integrate_dev(ImplicitKind kind, double* d_y, const marlpde_column_params* d_params,
+                                  marlpde_column_state* d_state, int n_columns, int n_cells,
+                                  const marlpde_rk45_options* opts, const double* d_t_eval, double* d_snapshots,
+                                  int32_t* d_event_counts, double* d_event_times, int64_t* d_stats, void* d_workspace,
+                                  size_t workspace_bytes, int32_t* d_queue, void* stream) {
+  int rc = check_implicit_args(n_columns, n_cells, opts);
   if (rc) return rc;
   if (n_columns == 0) return MARLPDE_OK;
   if (!d_y || !d_params || !d_state || !d_queue || !d_stats || !d_workspace)
@@ -523,25 +537,43 @@ int marlpde_radau_integrate_dev(double* d_y, const marlpde_column_params* d_para
     if (!d_event_counts) return fail(MARLPDE_EINVAL, "MARLPDE_FLAG_EVENTS needs event_counts");
     if (opts->event_capacity > 0 && !d_event_times) return fail(MARLPDE_EINVAL, "event_capacity > 0 needs event_times");
   }
-  if (workspace_bytes < marlpde::radau_workspace_bytes(n_columns, n_cells))
-    return fail(MARLPDE_EINVAL, "workspace too small: %zu < %zu bytes", workspace_bytes,
-                marlpde::radau_workspace_bytes(n_columns, n_cells));
+  const size_t need = implicit_workspace_bytes(kind, n_columns, n_cells);
+  if (workspace_bytes < need) return fail(MARLPDE_EINVAL, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
   DevProps props;
   rc = current_props(props);
   if (rc) return rc;
-  cudaError_t e = marlpde::launch_radau(d_y, d_params, d_state, n_columns, n_cells, *opts, d_t_eval, d_snapshots,
-                                        d_stats, d_event_counts, d_event_times, static_cast<double*>(d_workspace),
-                                        d_queue, props.sm_count,
-                                        (cudaStream_t)stream);
-  if (e != cudaSuccess) return cuda_fail(e, "radau launch");
+  auto launch = kind == kRadau ? marlpde::launch_radau : marlpde::launch_bdf;
+  cudaError_t e = launch(d_y, d_params, d_state, n_columns, n_cells, *opts, d_t_eval, d_snapshots, d_stats,
+                         d_event_counts, d_event_times, static_cast<double*>(d_workspace), d_queue, props.sm_count,
+                         (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, kind == kRadau ? "radau launch" : "bdf launch");
   return MARLPDE_OK;
 }
 
-static int radau_integrate_host(double* y, const marlpde_column_params* params, marlpde_column_state* state,
-                                int n_columns, int n_cells, const marlpde_rk45_options* opts, const double* t_eval,
-                                double* snapshots, int32_t* event_counts, double* event_times, int64_t* stats,
-                                int device, cudaStream_t s, bool sync) {
-  int rc = check_radau_args(n_columns, n_cells, opts);
+int marlpde_radau_integrate_dev(double* d_y, const marlpde_column_params* d_params, marlpde_column_state* d_state,
+                                int n_columns, int n_cells, const marlpde_rk45_options* opts,
+                                const double* d_t_eval, double* d_snapshots, int32_t* d_event_counts,
+                                double* d_event_times, int64_t* d_stats, void* d_workspace, size_t workspace_bytes,
+                                int32_t* d_queue, void* stream) {
+  return implicit_integrate_dev(kRadau, d_y, d_params, d_state, n_columns, n_cells, opts, d_t_eval, d_snapshots,
+                                d_event_counts, d_event_times, d_stats, d_workspace, workspace_bytes, d_queue, stream);
+}
+
+int marlpde_bdf_integrate_dev(double* d_y, const marlpde_column_params* d_params, marlpde_column_state* d_state,
+                              int n_columns, int n_cells, const marlpde_rk45_options* opts,
+                              const double* d_t_eval, double* d_snapshots, int32_t* d_event_counts,
+                              double* d_event_times, int64_t* d_stats, void* d_workspace, size_t workspace_bytes,
+                              int32_t* d_queue, void* stream) {
+  return implicit_integrate_dev(kBdf, d_y, d_params, d_state, n_columns, n_cells, opts, d_t_eval, d_snapshots,
+                                d_event_counts, d_event_times, d_stats, d_workspace, workspace_bytes, d_queue, stream);
+}
+
+static int implicit_integrate_host(ImplicitKind kind, double* y, const marlpde_column_params* params,
+                                   marlpde_column_state* state, int n_columns, int n_cells,
+                                   const marlpde_rk45_options* opts, const double* t_eval, double* snapshots,
+                                   int32_t* event_counts, double* event_times, int64_t* stats, int device,
+                                   cudaStream_t s, bool sync) {
+  int rc = check_implicit_args(n_columns, n_cells, opts);
   if (rc) return rc;
   if (n_columns == 0) return MARLPDE_OK;
   if (!y || !params || !state || !stats) return fail(MARLPDE_EINVAL, "NULL pointer");
@@ -554,7 +586,7 @@ static int radau_integrate_host(double* y, const marlpde_column_params* params, 
   const size_t nb_p = sizeof(marlpde_column_params) * (size_t)n_columns;
   const size_t nb_s = sizeof(marlpde_column_state) * (size_t)n_columns;
   const size_t nb_stats = sizeof(int64_t) * 4 * (size_t)n_columns;
-  const size_t nb_work = marlpde::radau_workspace_bytes(n_columns, n_cells);
+  const size_t nb_work = implicit_workspace_bytes(kind, n_columns, n_cells);
   const size_t nb_ec = sizeof(int32_t) * MARLPDE_NEVENTS * (size_t)n_columns;
   const size_t nb_et = sizeof(double) * MARLPDE_NEVENTS * (size_t)(opts->event_capacity > 0 ? opts->event_capacity : 0) * n_columns;
   DevBuf dy, dp, ds, dte, dsnap, dq, dst, dw, dec, det;
@@ -578,10 +610,9 @@ static int radau_integrate_host(double* y, const marlpde_column_params* params, 
   if (snapshots && nb_snap) CU(cudaMemcpyAsync(dsnap.p, snapshots, nb_snap, cudaMemcpyHostToDevice, s));
   CU(cudaMemsetAsync(dq.p, 0, sizeof(int32_t), s));
   CU(cudaMemcpyAsync(dst.p, stats, nb_stats, cudaMemcpyHostToDevice, s));
-  rc = marlpde_radau_integrate_dev(dy.as<double>(), dp.as<marlpde_column_params>(), ds.as<marlpde_column_state>(),
-                                   n_columns, n_cells, opts, dte.as<double>(), dsnap.as<double>(),
-                                   dec.as<int32_t>(), det.as<double>(), dst.as<int64_t>(), dw.p, nb_work,
-                                   dq.as<int32_t>(), s);
+  rc = implicit_integrate_dev(kind, dy.as<double>(), dp.as<marlpde_column_params>(), ds.as<marlpde_column_state>(),
+                              n_columns, n_cells, opts, dte.as<double>(), dsnap.as<double>(), dec.as<int32_t>(),
+                              det.as<double>(), dst.as<int64_t>(), dw.p, nb_work, dq.as<int32_t>(), s);
   if (rc) return rc;
   CU(cudaMemcpyAsync(y, dy.p, nb_y, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(state, ds.p, nb_s, cudaMemcpyDeviceToHost, s));
@@ -597,16 +628,31 @@ int marlpde_radau_integrate(double* y, const marlpde_column_params* params, marl
                             int n_columns, int n_cells, const marlpde_rk45_options* opts, const double* t_eval,
                             double* snapshots, int32_t* event_counts, double* event_times, int64_t* stats,
                             int device) {
-  return radau_integrate_host(y, params, state, n_columns, n_cells, opts, t_eval, snapshots, event_counts, event_times,
-                              stats, device, cudaStreamPerThread, true);
+  return implicit_integrate_host(kRadau, y, params, state, n_columns, n_cells, opts, t_eval, snapshots, event_counts,
+                                 event_times, stats, device, cudaStreamPerThread, true);
 }
 
 int marlpde_radau_integrate_async(double* y, const marlpde_column_params* params, marlpde_column_state* state,
                                   int n_columns, int n_cells, const marlpde_rk45_options* opts, const double* t_eval,
                                   double* snapshots, int32_t* event_counts, double* event_times, int64_t* stats,
                                   int device, void* stream) {
-  return radau_integrate_host(y, params, state, n_columns, n_cells, opts, t_eval, snapshots, event_counts, event_times,
-                              stats, device, (cudaStream_t)stream, false);
+  return implicit_integrate_host(kRadau, y, params, state, n_columns, n_cells, opts, t_eval, snapshots, event_counts,
+                                 event_times, stats, device, (cudaStream_t)stream, false);
+}
+
+int marlpde_bdf_integrate(double* y, const marlpde_column_params* params, marlpde_column_state* state,
+                          int n_columns, int n_cells, const marlpde_rk45_options* opts, const double* t_eval,
+                          double* snapshots, int32_t* event_counts, double* event_times, int64_t* stats, int device) {
+  return implicit_integrate_host(kBdf, y, params, state, n_columns, n_cells, opts, t_eval, snapshots, event_counts,
+                                 event_times, stats, device, cudaStreamPerThread, true);
+}
+
+int marlpde_bdf_integrate_async(double* y, const marlpde_column_params* params, marlpde_column_state* state,
+                                int n_columns, int n_cells, const marlpde_rk45_options* opts, const double* t_eval,
+                                double* snapshots, int32_t* event_counts, double* event_times, int64_t* stats,
+                                int device, void* stream) {
+  return implicit_integrate_host(kBdf, y, params, state, n_columns, n_cells, opts, t_eval, snapshots, event_counts,
+                                 event_times, stats, device, (cudaStream_t)stream, false);
 }
 
 }  // extern "C"

@@ -11,9 +11,15 @@ attributes) under ../Results/<timestamp>/, but the time stepping runs on the B20
                      (csrc/rk45_persistent.cu), SciPy RK45 semantics incl. t_eval dense output and events;
   method == "Radau"  (the reference's default, parameters.py:213) the batched implicit kernel
                      (csrc/radau_batch.cu): SciPy Radau semantics, block-tridiagonal Newton solve;
-  other methods      (LSODA, BDF, ...) SciPy's solve_ivp drives `eq.fun_numba`, whose RHS is the CUDA
-                     kernel (one column per call) — same arguments upstream passes (:104-109).
-                     MARLPDE_SCIPY_STEPPER=1 forces this route for RK45/Radau as well.
+  method == "BDF"    the batched variable-order BDF kernel (csrc/bdf_batch.cu): SciPy's BDF step for step on the
+                     same block-tridiagonal solver;
+  method == "LSODA"  SciPy's solve_ivp (ODEPACK's Fortran stepper, exactly what upstream runs) drives `eq.fun_numba`,
+                     whose RHS is the CUDA kernel (one column per call); MARLPDE_LSODA_DEVICE=1 runs the column on
+                     the device BDF kernel instead — LSODA leaves its Adams mode after ~25 steps on this stiff system
+                     and is a variable-order BDF code from then on (csrc/bdf_batch.cu), `lband` / `uband` are then
+                     ignored like `jac_sparsity`: the kernel's block-tridiagonal Jacobian is the exact structure;
+  other methods      (RK23, DOP853) SciPy-driven over the CUDA RHS — same arguments upstream passes (:104-109).
+                     MARLPDE_SCIPY_STEPPER=1 forces this route for every method.
 
 `integrate_equations_batch` is the sweep entry point: many parameter sets in one launch.
 """
@@ -84,24 +90,25 @@ def _gpu_rk45(eq, y0, solver_parms, t_eval, n_cells):
                            message=_MESSAGES.get(status, "unknown status"), t_reached=float(res.t[0]))
 
 
-def _gpu_radau(eq, y0, solver_parms, t_eval, n_cells):
-    """One column through the batched implicit integrator (csrc/radau_batch.cu): SciPy Radau semantics,
-    block-tridiagonal Newton solve.  `jac_sparsity` is accepted and ignored — the 5x5 block-tridiagonal
-    structure is intrinsic to the kernel (it is the exact structure the reference's pattern approximates)."""
-    known = {"first_step", "atol", "rtol", "t_span", "method", "dense_output", "max_step", "jac_sparsity"}
+def _gpu_implicit(eq, y0, solver_parms, t_eval, n_cells, kind="radau"):
+    """One column through a batched implicit integrator — csrc/radau_batch.cu (SciPy Radau semantics) or
+    csrc/bdf_batch.cu (SciPy BDF semantics) — with the block-tridiagonal Newton solve.  `jac_sparsity` (and LSODA's
+    `lband` / `uband`) are accepted and ignored — the 5x5 block-tridiagonal structure is intrinsic to the kernels (it
+    is the exact structure the reference's pattern approximates)."""
+    known = {"first_step", "atol", "rtol", "t_span", "method", "dense_output", "max_step", "jac_sparsity", "lband", "uband"}
     extra = set(solver_parms) - known
     if extra:
-        raise TypeError(f"options not supported by the GPU Radau path: {sorted(extra)}")
+        raise TypeError(f"options not supported by the GPU implicit path: {sorted(extra)}")
+    integrate = _mb.integrate_radau_batch if kind == "radau" else _mb.integrate_bdf_batch
     # `dense_output=True` (parameters.py:221 has False) makes solve_ivp attach a callable OdeSolution as `sol.sol`;
     # upstream's driver never reads it (Evolve_scenario.py:104-183 uses sol.y, sol.t, sol.t_events only), so the flag is
     # accepted and stored with the other parameters; intermediate states come from `t_eval`, which IS the dense output
     # (quartic / cubic interpolant of the step, as SciPy) evaluated on the device.
     te = np.asarray(t_eval, dtype=np.float64) if t_eval is not None else np.array(solver_parms["t_span"], float)
-    res = _mb.integrate_radau_batch(y0.reshape(1, 5, n_cells), eq.column_params, t_span=solver_parms["t_span"],
-                                    first_step=solver_parms.get("first_step", 1e-6),
-                                    rtol=solver_parms.get("rtol", 1e-3), atol=solver_parms.get("atol", 1e-6),
-                                    max_step=solver_parms.get("max_step", np.inf), t_eval=te,
-                                    events=True, event_capacity=4096)
+    res = integrate(y0.reshape(1, 5, n_cells), eq.column_params, t_span=solver_parms["t_span"],
+                    first_step=solver_parms.get("first_step", 1e-6),
+                    rtol=solver_parms.get("rtol", 1e-3), atol=solver_parms.get("atol", 1e-6),
+                    max_step=solver_parms.get("max_step", np.inf), t_eval=te, events=True, event_capacity=4096)
     k = int(res.next_eval[0])
     status = int(res.status[0])
     t_events = [np.sort(res.event_times[0, e, :min(int(res.event_counts[0, e]), res.event_times.shape[2])])
@@ -144,7 +151,11 @@ def integrate_equations(solver_parms, tracker_parms, pde_parms):
         sol = _gpu_rk45(eq, y0, gpu_parms, tracker_parms["t_eval"], n_cells)
         progress = (sol.t_reached - t0) / (end_time - t0)
     elif solver_parms["method"] == "Radau" and not scipy_stepper:
-        sol = _gpu_radau(eq, y0, solver_parms, tracker_parms["t_eval"], n_cells)
+        sol = _gpu_implicit(eq, y0, solver_parms, tracker_parms["t_eval"], n_cells, "radau")
+        progress = (sol.t_reached - t0) / (end_time - t0)
+    elif not scipy_stepper and (solver_parms["method"] == "BDF" or (
+            solver_parms["method"] == "LSODA" and os.environ.get("MARLPDE_LSODA_DEVICE", "0") == "1")):
+        sol = _gpu_implicit(eq, y0, solver_parms, tracker_parms["t_eval"], n_cells, "bdf")
         progress = (sol.t_reached - t0) / (end_time - t0)
     else:
         from scipy.integrate import solve_ivp
@@ -192,7 +203,8 @@ def integrate_equations(solver_parms, tracker_parms, pde_parms):
 def integrate_equations_batch(solver_parms, tracker_parms, pde_parms, store_folder=None, device=0):
     """Parameter sweep: `pde_parms` is a Map_Scenario dictionary whose values may be arrays of
     shape (B,) (see marlpde_b200.sweep_lattice) or a list of such dictionaries.  All columns are
-    integrated in one launch of the persistent RK45 kernel.  Returns the marlpde_b200.RK45Result;
+    integrated in one launch of the kernel `method` selects (RK45: persistent on-chip kernel; Radau, BDF / LSODA: the
+    batched implicit kernels).  Returns the marlpde_b200.RK45Result / RadauResult;
     with `store_folder` one HDF5 file per sweep is written (datasets `solutions` (B,5,N,n_t),
     `times`, `status`, `nfev`, `n_accepted`, `n_rejected`, `next_eval`, `t_reached`, `event_counts`)."""
     if isinstance(pde_parms, (list, tuple)):
@@ -201,11 +213,12 @@ def integrate_equations_batch(solver_parms, tracker_parms, pde_parms, store_fold
     solver_parms = dict(solver_parms)
     solver_parms.pop("backend", None)
     method = solver_parms.get("method", "RK45")
-    if method not in ("RK45", "Radau"):
-        raise NotImplementedError("the batched on-device integrators implement method='RK45' and method='Radau'")
+    if method not in ("RK45", "Radau", "BDF", "LSODA"):
+        raise NotImplementedError("the batched on-device integrators implement method='RK45', 'Radau', 'BDF' and "
+                                  "'LSODA' (the latter on the BDF kernel: LSODA's stiff mode)")
     params = _mb.derive_column_params(pde_parms)
     y0 = _mb.initial_state(pde_parms)
-    integrate = _mb.integrate_rk45_batch if method == "RK45" else _mb.integrate_radau_batch
+    integrate = {"RK45": _mb.integrate_rk45_batch, "Radau": _mb.integrate_radau_batch}.get(method, _mb.integrate_bdf_batch)
     res = integrate(y0, params, t_span=solver_parms.get("t_span", (0, 1)),
                     first_step=solver_parms.get("first_step", 1e-6),
                     rtol=solver_parms.get("rtol", 1e-3), atol=solver_parms.get("atol", 1e-3),

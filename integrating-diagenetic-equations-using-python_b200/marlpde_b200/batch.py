@@ -286,7 +286,28 @@ def integrate_radau_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1
     """Implicit integration of every column: 3-stage Radau IIA with SciPy's step-size, Newton and
     Jacobian-reuse rules (`solve_ivp(method="Radau", jac_sparsity=jacobian_sparsity())`, the
     reference's default Solver, parameters.py:201-221) and a block-tridiagonal linear solver."""
+    return _integrate_implicit("radau", y0, params, t_span, first_step, rtol, atol, t_eval, max_step, max_steps, events,
+                               event_capacity, state, device, inplace)
+
+
+def integrate_bdf_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e-3, atol=1e-3, t_eval=None,
+                        max_step=np.inf, max_steps: int = 0, events: bool = False, event_capacity: int = 0,
+                        state: np.ndarray | None = None, device: int = 0, inplace: bool = False) -> RadauResult:
+    """Implicit integration of every column with the variable-order BDF kernel (csrc/bdf_batch.cu): SciPy's `BDF`
+    step for step (`solve_ivp(method="BDF", jac_sparsity=jacobian_sparsity())`, parameters.py:235-236) on the
+    block-tridiagonal linear solver of the Radau kernel; also what `method="LSODA"` batches run on the device
+    (parameters.py:214-219: LSODA is a BDF code on this stiff system).  Same result type as the Radau path; `nlu`
+    counts one real factorisation each.  A column resumed from `state` restarts at order 1."""
+    return _integrate_implicit("bdf", y0, params, t_span, first_step, rtol, atol, t_eval, max_step, max_steps, events,
+                               event_capacity, state, device, inplace)
+
+
+def _integrate_implicit(kind, y0, params, t_span, first_step, rtol, atol, t_eval, max_step, max_steps, events,
+                        event_capacity, state, device, inplace) -> RadauResult:
     lib = _cabi.lib()
+    f_ws = getattr(lib, f"marlpde_{kind}_workspace_bytes")
+    f_dev = getattr(lib, f"marlpde_{kind}_integrate_dev")
+    f_host = getattr(lib, f"marlpde_{kind}_integrate")
     t0, t_bound = float(t_span[0]), float(t_span[1])
     if not t_bound > t0:
         raise ValueError("only forward integration (t_span[1] > t_span[0]) is supported")
@@ -328,10 +349,10 @@ def integrate_radau_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1
             d_stats = torch.zeros((B, 4), dtype=torch.int64, device=dev)
             d_ec = torch.zeros((B, NEVENTS), dtype=torch.int32, device=dev)
             d_et = torch.full((B, NEVENTS, max(cap, 1)), float("nan"), dtype=torch.float64, device=dev)
-            nb = int(lib.marlpde_radau_workspace_bytes(B, N))
+            nb = int(f_ws(B, N))
             d_work = torch.empty(max(nb, 8) // 8, dtype=torch.float64, device=dev)
             stream = torch.cuda.current_stream().cuda_stream
-            _cabi.check(lib.marlpde_radau_integrate_dev(
+            _cabi.check(f_dev(
                 y.data_ptr(), d_params.data_ptr(), d_state.data_ptr(), B, N, C.byref(opts),
                 d_te.data_ptr() if n_eval else None, d_snap.data_ptr(), d_ec.data_ptr(), d_et.data_ptr(),
                 d_stats.data_ptr(), d_work.data_ptr(), nb, d_queue.data_ptr(), stream))
@@ -350,7 +371,7 @@ def integrate_radau_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1
         stats = np.zeros((B, 4), dtype=np.int64)
         ec = np.zeros((B, NEVENTS), dtype=np.int32)
         et = np.full((B, NEVENTS, cap), np.nan)
-        _cabi.check(lib.marlpde_radau_integrate(
+        _cabi.check(f_host(
             _cabi.ptr(y), _cabi.ptr(p), _cabi.ptr(st_out), B, N, C.byref(opts),
             _cabi.ptr(t_eval_arr) if n_eval else None, _cabi.ptr(snaps) if n_eval else None, _cabi.ptr(ec),
             _cabi.ptr(et) if cap else None, _cabi.ptr(stats), device))

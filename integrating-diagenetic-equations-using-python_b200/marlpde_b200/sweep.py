@@ -40,7 +40,7 @@ def predicted_cost(pde: dict, method: str = "RK45") -> np.ndarray:
     governed by how sharp the porosity front gets, i.e. by the compaction coefficient b (dPhi ~ 1/b).  Empirical fit on
     the 4096-column benchmark lattice (default base, r02o): work ~ b^2.16 S^-0.66 DCO3^0.05, rank correlation 0.996 —
     the a-priori RK45 estimate has correlation 0.13 with it."""
-    if method == "Radau":
+    if method in ("Radau", "BDF"):    # (BDF: same front-sharpness dependence; not fitted separately)
         b = np.atleast_1d(np.asarray(pde["b"], dtype=np.float64))
         srate = np.atleast_1d(np.asarray(pde["sedimentationrate"], dtype=np.float64))
         cost = b ** 2.16 * srate ** -0.66
@@ -124,6 +124,11 @@ def sweep_radau(pde: dict, **kw) -> SweepResult:
     return sweep_rk45(pde, method="Radau", **kw)
 
 
+def sweep_bdf(pde: dict, **kw) -> SweepResult:
+    """The sweep with the variable-order BDF kernel (solve_ivp(method="BDF"), parameters.py:235-236; LSODA's stiff mode)."""
+    return sweep_rk45(pde, method="BDF", **kw)
+
+
 def sweep_rk45(pde: dict, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e-3, atol=1e-3, t_eval=None,
                events: bool = True, balance: bool = True, group=None, device=None, integrate=None,
                method: str = "RK45", **kw) -> SweepResult:
@@ -147,10 +152,10 @@ def sweep_rk45(pde: dict, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e-3, atol=1e
     local = shard(pde, mine) if B > 1 else pde
 
     if integrate is None:
-        from .batch import integrate_radau_batch, integrate_rk45_batch
-        if method not in ("RK45", "Radau"):
-            raise ValueError("method must be 'RK45' or 'Radau'")
-        run = integrate_rk45_batch if method == "RK45" else integrate_radau_batch
+        from .batch import integrate_bdf_batch, integrate_radau_batch, integrate_rk45_batch
+        if method not in ("RK45", "Radau", "BDF"):
+            raise ValueError("method must be 'RK45', 'Radau' or 'BDF'")
+        run = {"RK45": integrate_rk45_batch, "Radau": integrate_radau_batch, "BDF": integrate_bdf_batch}[method]
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
 
         def integrate(y0, P, **opts):

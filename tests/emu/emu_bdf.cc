@@ -1,0 +1,35 @@
+// tests/emu/emu_bdf.cc — the batched BDF kernel (csrc/bdf_batch.cu), compiled for the host and run by the SIMT
+// emulator: one CTA of four warps works through all columns of the queue.  TEST INFRASTRUCTURE ONLY (simt_emu.h).
+#include <cstdint>
+#include <vector>
+
+#include "cuda_runtime.h"
+#include "simt_emu.h"
+
+#include "../../integrating-diagenetic-equations-using-python_b200/csrc/bdf_batch.cu"
+
+extern "C" int emu_bdf(double* y, const marlpde_column_params* params, marlpde_column_state* state, int n_columns,
+                       int n_cells, const marlpde_rk45_options* opt, const double* t_eval, double* snap,
+                       int64_t* stats, int32_t* ev_counts, double* ev_times) {
+  using namespace marlpde;
+  std::vector<double> work(bd::work_doubles(n_cells) * (size_t)n_columns + 16, 0.0);
+  int32_t queue = 0;
+  imp::Args a;
+  a.g_y = y;
+  a.g_params = params;
+  a.g_state = state;
+  a.g_t_eval = t_eval;
+  a.g_snap = snap;
+  a.g_stats = stats;
+  a.g_ev_counts = ev_counts;
+  a.g_ev_times = ev_times;
+  a.g_work = work.data();
+  a.g_queue = &queue;
+  a.n_columns = n_columns;
+  a.N = n_cells;
+  a.opt = *opt;
+  return simt::run_block(imp::kWarpsPerCta * 32, 0, [&]() {
+    if (a.opt.flags & MARLPDE_FLAG_VAR_DPHI) bd::bdf_kernel<true>(a);
+    else bd::bdf_kernel<false>(a);
+  });
+}

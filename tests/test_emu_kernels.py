@@ -190,6 +190,85 @@ def test_radau_kernel_under_emulation(emu_radau):
     assert np.max(np.abs(a["y"][4] - s4) / (1e-3 + 1e-3 * np.abs(s4))) <= 1.0
 
 
+# ----------------------------------------------------------------------------------------- BDF kernel
+def exact_sparsity(N):
+    """The block-tridiagonal structure (cell-major 5x5 blocks) as a field-major sparsity pattern for SciPy."""
+    import scipy.sparse as sp
+    cells = np.arange(5 * N) % N
+    return sp.csr_matrix((np.abs(cells[:, None] - cells[None, :]) <= 1).astype(float))
+
+
+@pytest.fixture(scope="module")
+def emu_bdf():
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    out = os.path.join(EMU, "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libemu_bdf.so")
+    srcs = [os.path.join(EMU, f) for f in ("emu_bdf.cc", "simt_emu.cc")]
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DMARLPDE_HOST_EMU", "-I", EMU, "-o", so] + srcs,
+                   check=True, capture_output=True)
+    lib = C.CDLL(so)
+    lib.emu_bdf.restype = C.c_int
+
+    def run(P, y, t_end, t_eval=(), events=False, first_step=1e-6, tol=1e-3):
+        y = np.ascontiguousarray(y, dtype=np.float64).copy()
+        P = np.ascontiguousarray(P)
+        B, _, N = y.shape
+        st = batch.make_state(B, 0.0, first_step)
+        te = np.asarray(t_eval, dtype=np.float64)
+        snap = np.full((B, max(1, te.size), 5, N), np.nan)
+        ec, et, stats = np.zeros((B, 7), np.int32), np.full((B, 7, 16), np.nan), np.zeros((B, 4), np.int64)
+        o = _cabi.RK45Options(t_bound=t_end, rtol=tol, atol=tol, max_step=float("inf"), max_steps=0, n_eval=te.size,
+                              event_capacity=16, flags=_cabi.FLAG_EVENTS if events else 0, quantum=0)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = lib.emu_bdf(p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), p(stats), p(ec), p(et))
+        assert rc == 0, f"emulated BDF kernel: rc {rc}"
+        return dict(y=y, state=st, snapshots=snap, stats=stats, event_counts=ec, event_times=et)
+    return run
+
+
+def test_bdf_kernel_under_emulation_is_scipy_bdf_step_for_step(emu_bdf):
+    """The BDF kernel (csrc/bdf_batch.cu) restates scipy/integrate/_ivp/bdf.py; handed the SAME Jacobian structure (the
+    block-tridiagonal pattern instead of the reference's 27 diagonals, which drop d(CA,CC)/dPhi) SciPy's BDF takes the same
+    steps: identical Jacobian and LU counts, one Newton iteration per SciPy RHS call, states equal to a small fraction of
+    the tolerance — at rtol = 1e-3 and 1e-6, scenario A to T* (the reference's regression case) with dense output."""
+    pde = oracle.default_scenario() | SCEN_A
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    for tol, te, gate in ((1e-3, np.linspace(0, 1, 6), 1e-3), (1e-6, np.array([0.0, 0.1]), 1e-2)):
+        sol = oracle.integrate(pde, method="BDF", t_span=(0, te[-1]), t_eval=te, events=False, first_step=1e-6, rtol=tol,
+                               atol=tol, jac_sparsity=exact_sparsity(200))
+        res = emu_bdf(P, y0, te[-1], t_eval=te, tol=tol)
+        assert res["state"]["status"][0] == 0
+        assert res["stats"][0, 0] == sol.njev and res["stats"][0, 1] == sol.nlu
+        assert res["stats"][0, 2] == sol.nfev - 1                      # bdf.py: one fun call per Newton iteration + f(t0, y0)
+        want = np.moveaxis(sol.y.reshape(5, 200, -1), 2, 0)
+        assert np.max(np.abs(res["snapshots"][0] - want) / (tol + tol * np.abs(want))) <= gate
+
+
+def test_bdf_kernel_events_and_lattice_under_emulation(emu_bdf):
+    """Event monitors on the BDF dense output (default scenario: the porosity crosses 1 near t = 0.026, then max W changes
+    sign) against SciPy BDF's events; five lattice columns through the four warps of one CTA."""
+    pde = oracle.default_scenario()
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    sol = oracle.integrate(pde, method="BDF", t_span=(0, 0.0275), t_eval=[0.0275], events=True, first_step=5e-7,
+                           jac_sparsity=exact_sparsity(200))
+    res = emu_bdf(P, y0, 0.0275, t_eval=[0.0275], events=True, first_step=5e-7)
+    assert [len(e) for e in sol.t_events] == list(res["event_counts"][0])
+    for k in (4, 6):
+        assert len(sol.t_events[k]) >= 1
+        assert np.max(np.abs(res["event_times"][0, k, :len(sol.t_events[k])] - sol.t_events[k])) <= 1e-6
+    lat = mb.sweep_lattice(oracle.default_scenario(), 1, 1, 5)
+    Pl, yl = mb.derive_column_params(lat), mb.initial_state(lat)
+    a = emu_bdf(Pl, yl, 0.006, t_eval=[0.006], first_step=5e-7)
+    assert np.all(a["state"]["status"] == 0)
+    one = {k: (float(v[4]) if np.ndim(v) else v) for k, v in lat.items()}
+    s4 = oracle.integrate(one, method="BDF", t_span=(0, 0.006), t_eval=[0.006], events=False, first_step=5e-7,
+                          jac_sparsity=exact_sparsity(200))
+    assert a["stats"][4, 1] == s4.nlu
+    assert np.max(np.abs(a["y"][4] - s4.y.reshape(5, 200)) / (1e-3 + 1e-3 * np.abs(s4.y.reshape(5, 200)))) <= 0.01
+
+
 # ------------------------------------------------------------------- streaming path (large depth grids)
 @pytest.fixture(scope="module")
 def emu_stream():

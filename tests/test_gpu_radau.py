@@ -140,3 +140,26 @@ def test_radau_time_varying_dPhi_model_variant():
     assert np.max(np.abs(res.y[0][4] - res.y[1][4])) > 1e-6
     # Newton converges as well as for the plain model: the analytic off-diagonal blocks carry the cell's own dPhi
     assert res.newton_failures[0] <= plain.newton_failures[0] + 2
+
+
+@pytest.mark.parametrize("name,over,snap", [("scenario_A", {"Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}, 5),
+                                            ("high_porosity", {}, 13),
+                                            ("high_porosity", {"time_varying_dPhi": True}, 9)])
+def test_device_jacobian_blocks_against_the_numpy_restatement(fixtures_reference, name, over, snap):
+    """The analytic block-tridiagonal Jacobian as the implicit kernels form it on the device (marlpde_probe_jacobian ->
+    jac_analytic) against its numpy restatement (oracle/jacobian_blocks.py, which tests/test_host_side.py pins to
+    central differences of the oracle RHS): every entry of L, D, U of all 200 cells to 1e-11 of the block's largest."""
+    import ctypes as C
+    import jacobian_blocks as jb
+    from marlpde_b200 import _cabi
+    pde = oracle.derive_scenario({**oracle.default_scenario(), **over})
+    p, N = oracle.kernel_params(pde), 200
+    P = mb.derive_column_params(pde)
+    y = np.ascontiguousarray(fixtures_reference[name][snap], dtype=np.float64).reshape(-1)
+    J = np.zeros((N, 3, 5, 5))
+    _cabi.check(_cabi.lib().marlpde_probe_jacobian(_cabi.ptr(y), _cabi.ptr(P), N, _cabi.ptr(J), 0))
+    for i in range(N):
+        want = jb.blocks(y, p, i, N)
+        for b in range(3):
+            got = J[i, b].T                                   # stored [column][row]
+            assert np.max(np.abs(got - want[b])) <= 1e-11 * max(1.0, np.abs(want[b]).max()), (i, b)

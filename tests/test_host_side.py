@@ -147,56 +147,9 @@ def test_argument_validation_before_any_device_work():
     assert _cabi.lib().marlpde_radau_workspace_bytes(1, 200) == 8 * 200 * (90 + 76 + 64)
 
 
-def _offdiagonal_blocks(y, p, i, N):
-    """Analytic L_i, U_i (row = rate, column = field of the neighbour cell) as jac_columns() in
-    csrc/radau_batch.cu forms them: given a cell's own values the RHS (LHeureux_model.py:361-522) is linear
-    in each neighbour value; the bottom ghost of CA, CC (2 a_{N-1} - a_{N-2}) folds into L of the last cell."""
-    Y = y.reshape(5, N)
-    c = Y[:, i]
-    prev = Y[:, i - 1] if i > 0 else 2 * p[0:5] - c
-    nxt = Y[:, i + 1] if i < N - 1 else np.array([2 * c[0] - prev[0], 2 * c[1] - prev[1], c[2], c[3], c[4]])
-    Phi = c[4]
-    dx, inv_dx2, delta_x, presum, rhorat = p[5], p[6], p[7], p[8], p[9]
-    dCa, dCO3, dPhi = p[12], p[13], p[22]
-    F = 1 - np.exp(10 - 10 / Phi)
-    U = presum + rhorat * Phi ** 3 * F / (1 - Phi)
-    W = presum - rhorat * Phi ** 2 * F
-    den = 1 - 2 * np.log(Phi)
-    sig = (lambda Pe: oracle._sigma(Pe, W, p[23], p[24])) if p[25] != 0 else (lambda Pe: 0.0)
-    s = {2: sig(W * delta_x * den / (2 * dCa)), 3: sig(W * delta_x * den / (2 * dCO3)), 4: sig(W * delta_x / (2 * dPhi))}
-    h1, h2c = Phi / den, (2 + den) / den ** 2
-    dWc = -rhorat * (2 * Phi * F + 10 * (F - 1))
-    hdx = 0.5 / dx
-    grad = {f: ((1 - s[f]) * (nxt[f] - c[f]) + (1 + s[f]) * (c[f] - prev[f])) * hdx for f in (2, 3, 4)}
-    L, Ub = np.zeros((5, 5)), np.zeros((5, 5))
-    for blk, prev_side in ((L, True), (Ub, False)):
-        dgA = (-1 / dx if U > 0 else 0.0) if prev_side else (0.0 if U > 0 else 1 / dx)
-        blk[0, 0] = blk[1, 1] = -U * dgA
-        dg = {f: (-(1 + s[f]) * hdx if prev_side else (1 - s[f]) * hdx) for f in (2, 3, 4)}
-        blk[2, 2] = dCa * (grad[4] * h2c * dg[2] + h1 * inv_dx2) / Phi - W * dg[2]
-        blk[3, 3] = dCO3 * (grad[4] * h2c * dg[3] + h1 * inv_dx2) / Phi - W * dg[3]
-        blk[2, 4] = dCa * grad[2] * h2c * dg[4] / Phi
-        blk[3, 4] = dCO3 * grad[3] * h2c * dg[4] / Phi
-        blk[4, 4] = dPhi * inv_dx2 - (dWc * Phi + W) * dg[4]
-    if i == 0:
-        L[:] = 0
-    if i == N - 1:
-        L[:, :2] -= Ub[:, :2]
-        Ub[:] = 0
-    return L, Ub
-
-
-@pytest.mark.parametrize("name,over,snap", [("scenario_A", {"Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}, 5),
-                                            ("high_porosity", {}, 13)])
-def test_offdiagonal_jacobian_block_formulas(fixtures_reference, name, over, snap):
-    """The implicit kernel writes the off-diagonal 5x5 Jacobian blocks analytically and gets the diagonal blocks
-    from 5 finite-difference evaluations.  The formulas, restated here, against central differences of the
-    oracle RHS on evolved states of the reference's own fixtures (all 200 cells, both column ends): agreement to
-    1e-8 of the largest Jacobian entry, and nothing outside the block-tridiagonal structure."""
-    pde = oracle.derive_scenario({**oracle.default_scenario(), **over})
-    p, N = oracle.kernel_params(pde), 200
-    y = np.ascontiguousarray(fixtures_reference[name][snap], dtype=np.float64).reshape(-1)
-    n = 5 * N
+def central_difference_jacobian(y, p):
+    """Dense d rhs / d y of the oracle RHS by central differences (field-major), relative step 1e-7."""
+    n = y.size
     J = np.zeros((n, n))
     fp, fm = np.empty(n), np.empty(n)
     for j in range(n):
@@ -207,16 +160,38 @@ def test_offdiagonal_jacobian_block_formulas(fixtures_reference, name, over, sna
         oracle.rhs(yp, p, fp)
         oracle.rhs(ym, p, fm)
         J[:, j] = (fp - fm) / (2 * h)
+    return J
+
+
+JAC_CASES = [("scenario_A", {"Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}, 5), ("high_porosity", {}, 13),
+             ("high_porosity", {"time_varying_dPhi": True}, 9)]
+
+
+@pytest.mark.parametrize("name,over,snap", JAC_CASES)
+def test_analytic_jacobian_blocks(fixtures_reference, name, over, snap):
+    """The implicit kernels write all three 5x5 Jacobian blocks of a cell analytically (csrc/implicit_common.cuh
+    jac_analytic).  The formulas, restated in numpy (oracle/jacobian_blocks.py), against central differences of the
+    oracle RHS on evolved states of the reference's own fixtures (all 200 cells, both column ends, the plain model and
+    the time-varying-dPhi variant): off-diagonal blocks to 1e-8 of the largest Jacobian entry (the RHS is linear in
+    the neighbour values), diagonal blocks to the accuracy of the difference quotient, and nothing outside the
+    block-tridiagonal structure."""
+    import jacobian_blocks as jb
+    pde = oracle.derive_scenario({**oracle.default_scenario(), **over})
+    p, N = oracle.kernel_params(pde), 200
+    y = np.ascontiguousarray(fixtures_reference[name][snap], dtype=np.float64).reshape(-1)
+    J = central_difference_jacobian(y, p)
     scale = np.abs(J).max()
-    cells = np.arange(n) % N
+    cells = np.arange(5 * N) % N
     assert np.abs(J[np.abs(cells[:, None] - cells[None, :]) > 1]).max() == 0.0
     for i in range(N):
-        L, Ub = _offdiagonal_blocks(y, p, i, N)
+        L, D, Ub = jb.blocks(y, p, i, N)
         rows = [f * N + i for f in range(5)]
         if i > 0:
             assert np.abs(J[np.ix_(rows, [f * N + i - 1 for f in range(5)])] - L).max() <= 1e-8 * scale
         if i < N - 1:
             assert np.abs(J[np.ix_(rows, [f * N + i + 1 for f in range(5)])] - Ub).max() <= 1e-8 * scale
+        Jd = J[np.ix_(rows, rows)]
+        assert np.all(np.abs(Jd - D) <= 1e-3 * np.abs(Jd) + 1e-9 * scale), (i, np.abs(Jd - D).max())
 
 
 @pytest.mark.parametrize("n_cells", [1, 2, 3, 4, 5, 37, 200])

@@ -23,6 +23,8 @@ the data path, one NCCL all-gather of the end states after the timed steps.
            the RK45 kernel (N=1 only, ~2 min) and with the implicit Radau kernel (both scenario bases; at N>1 the
            8192-columns-per-GPU sweep with the cost-balanced column assignment and the all-gather of the
            snapshots timed), each with its own roofline block and a CPU figure beside it.
+`bdf_time_to_Tstar` (N=1): the same sweep with the variable-order BDF kernel (method="BDF"; LSODA's stiff mode), HBM
+           roofline from its own byte model, SciPy BDF on the host cores beside it.
 `large_n_streaming` (N=1): the streaming / overlapped-tile RK45 path at N = 2 000 / 20 000 with fp64 and HBM rooflines.
 `cpu_baseline` / `--impl reference`: the reference's own path — SciPy solve_ivp(RK45) driving the
            restated numba RHS (oracle/, kind "port": py-pde is not installable here) — on the
@@ -136,15 +138,16 @@ def _cpu_radau_worker(job):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import lheureux_oracle as oracle
-    pde, warm = job
+    pde, warm = job[0], job[1]
+    method = job[2] if len(job) > 2 else "Radau"
     n = int(pde["N"])
     sp = oracle.jacobian_sparsity(n)
     if warm:
-        oracle.integrate(pde, method="Radau", t_span=(0.0, 1e-5), t_eval=[0.0, 1e-5], events=False, jac_sparsity=sp)
+        oracle.integrate(pde, method=method, t_span=(0.0, 1e-5), t_eval=[0.0, 1e-5], events=False, jac_sparsity=sp)
         return 0.0, 0, 0, 0, 0
     t0 = time.perf_counter()
     try:
-        sol = oracle.integrate(pde, method="Radau", first_step=1e-6, rtol=1e-3, atol=1e-3, t_span=(0.0, 1.0),
+        sol = oracle.integrate(pde, method=method, first_step=1e-6, rtol=1e-3, atol=1e-3, t_span=(0.0, 1.0),
                                t_eval=np.array([0.0, 1.0]), events=True, jac_sparsity=sp)
         return time.perf_counter() - t0, int(sol.status), int(sol.nfev), int(sol.njev), int(sol.nlu)
     except (FloatingPointError, ZeroDivisionError, ValueError):
@@ -170,18 +173,18 @@ def cpu_reference_pass(base_name: str, t_end: float, cores: int, pool, warm: boo
     return attempts, busy, wall
 
 
-def cpu_radau_pass(base_name: str, cores: int, pool):
-    """`cores` columns spread over the lattice, SciPy Radau to T*, one process each: seconds per column."""
+def cpu_radau_pass(base_name: str, cores: int, pool, method: str = "Radau"):
+    """`cores` columns spread over the lattice, SciPy Radau (or BDF) to T*, one process each: seconds per column."""
     cols = _lattice_columns(base_name, cores, spread=True)
-    pool.map(_cpu_radau_worker, [(c, True) for c in cols])                               # JIT + first touch
-    res = pool.map(_cpu_radau_worker, [(c, False) for c in cols])
+    pool.map(_cpu_radau_worker, [(c, True, method) for c in cols])                       # JIT + first touch
+    res = pool.map(_cpu_radau_worker, [(c, False, method) for c in cols])
     secs = [r[0] for r in res]
     return {"seconds_per_column_mean": sum(secs) / len(secs), "seconds_per_column_max": max(secs),
             "columns_sampled": len(cols), "finished": sum(1 for r in res if r[1] == 0), "cores": cores,
             "seconds_per_4096_columns_on_these_cores": sum(secs) / len(secs) * 4096 / cores, "kind": "port",
             "nfev_mean": sum(r[2] for r in res) / len(res), "njev_mean": sum(r[3] for r in res) / len(res),
             "nlu_mean": sum(r[4] for r in res) / len(res),
-            "sample": "SciPy solve_ivp(Radau, rtol=atol=1e-3, first_step=1e-6, reference jac_sparsity, 7 events) on the numba "
+            "sample": f"SciPy solve_ivp({method}, rtol=atol=1e-3, first_step=1e-6, reference jac_sparsity, 7 events) on the numba "
                       "RHS (oracle port), columns spread evenly over the 16x16x16 lattice, one process per core, full T*"}
 
 
@@ -302,18 +305,36 @@ def radau_algorithmic_bytes(n_cells, newton, nlu, njev, steps_attempted):
                          block-tridiagonal solve of both systems (two sweeps: read and write B, 3 V each way, plus the
                          fp32 records 2 x 408 B per cell), norm / W += dW / Z = T W pass (read 7 V, write 6 V)
       factorisation pair read the Jacobian blocks (600 B per cell), write the records (512 B per cell)
-      Jacobian           5 x (perturbed evaluation 3 V + column pass: read 4 V, write 200 B per cell)
+      Jacobian           analytic blocks in one pass: read y (1 V), write 600 B per cell
       step attempt       Z0 / W start values (read 5 V, write 6 V), error estimate (read 4 V, write 2 V, one real solve:
                          2 V + 2 x 204 B per cell), commit (read 4 V, write 5 V), f(y_new) (2 V)"""
     V = 5.0 * n_cells * 8.0
     per_newton = 9 * V + 9 * V + (12 * V + 2 * 408.0 * n_cells) + 13 * V
     per_lu_pair = (600.0 + 512.0) * n_cells
-    per_jac = 5 * (3 * V + 4 * V + 200.0 * n_cells)
+    per_jac = V + 600.0 * n_cells
     per_step = 11 * V + (6 * V + 2 * V + 2 * 204.0 * n_cells) + 9 * V + 2 * V
     return newton * per_newton + (nlu / 2.0) * per_lu_pair + njev * per_jac + steps_attempted * per_step
 
 
-def implicit_sweep(mb, batch, torch, dev, sw_pde, columns, evcap=16, t_eval=None):
+def bdf_algorithmic_bytes(n_cells, newton, nlu, njev, steps_attempted, rescalings):
+    """HBM bytes the BDF kernel has to move by construction (csrc/bdf_batch.cu; V = 5 N doubles):
+      Newton iteration   residual b = M (c f(y) - psi - d) fused into the RHS pass (read y, psi, d, write b: 4 V), real
+                         block-tridiagonal solve (two sweeps: read and write b, 4 V, plus the compact fp32 records
+                         2 x 208 B per cell), norm / y += dy / d += dy pass (read 3 V, write 2 V)
+      factorisation      read the Jacobian blocks (600 B per cell), write the compact record (308 B per cell)
+      Jacobian           analytic blocks in one pass: read y (1 V), write 600 B per cell
+      step attempt       predictor y = sum D, psi, d = 0 (read ~4 V of D at the typical order 3, write 3 V), error norm
+                         (read 2 V), differences update (read ~6 V, write ~6 V)
+      rescaling          change_D: read and write order + 1 ~ 4 rows of D (8 V)"""
+    V = 5.0 * n_cells * 8.0
+    per_newton = 4 * V + (4 * V + 2 * 208.0 * n_cells) + 5 * V
+    per_lu = (600.0 + 308.0) * n_cells
+    per_jac = V + 600.0 * n_cells
+    per_step = 7 * V + 2 * V + 12 * V
+    return newton * per_newton + nlu * per_lu + njev * per_jac + steps_attempted * per_step + rescalings * 8 * V
+
+
+def implicit_sweep(mb, batch, torch, dev, sw_pde, columns, evcap=16, t_eval=None, method="Radau"):
     """The implicit kernel on `columns` of the sweep dictionary, t = 0 .. T*; returns (result, seconds)."""
     import numpy as np
     Pi = mb.derive_column_params(sw_pde)[columns]
@@ -324,19 +345,26 @@ def implicit_sweep(mb, batch, torch, dev, sw_pde, columns, evcap=16, t_eval=None
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stream = torch.cuda.current_stream()
     r0.record(stream)
-    rr = mb.integrate_radau_batch(d_yi, d_pi, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e-3, atol=1e-3,
-                                  events=True, event_capacity=evcap, inplace=True, t_eval=t_eval)
+    run = mb.integrate_radau_batch if method == "Radau" else mb.integrate_bdf_batch
+    rr = run(d_yi, d_pi, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e-3, atol=1e-3,
+             events=True, event_capacity=evcap, inplace=True, t_eval=t_eval)
     r1.record(stream)
     torch.cuda.synchronize()
     return rr, r0.elapsed_time(r1) * 1e-3
 
 
-def implicit_block(rr, secs, n_cells, peak_gbs, peak_src):
+def implicit_block(rr, secs, n_cells, peak_gbs, peak_src, method="Radau"):
     import numpy as np
     attempts = float(rr.n_accepted.sum() + rr.n_rejected.sum() + rr.newton_failures.sum())
-    alg = radau_algorithmic_bytes(n_cells, float(rr.newton_iterations.sum()), float(rr.nlu.sum()), float(rr.njev.sum()),
-                                  attempts)
-    return {"method": "Radau IIA (radau_kernel, one launch)",
+    if method == "Radau":
+        alg = radau_algorithmic_bytes(n_cells, float(rr.newton_iterations.sum()), float(rr.nlu.sum()),
+                                      float(rr.njev.sum()), attempts)
+    else:   # bdf.py: a rescaling of D after every rejection / Newton failure and after about every fourth accepted step
+        alg = bdf_algorithmic_bytes(n_cells, float(rr.newton_iterations.sum()), float(rr.nlu.sum()), float(rr.njev.sum()),
+                                    attempts, float(rr.n_rejected.sum() + rr.newton_failures.sum()) + 0.25 * float(rr.n_accepted.sum()))
+    kernel = "radau_kernel" if method == "Radau" else "bdf_kernel"
+    return {"method": ("Radau IIA (radau_kernel, one launch)" if method == "Radau"
+                       else "variable-order BDF = SciPy BDF step for step; LSODA's stiff mode (bdf_kernel, one launch)"),
             "seconds": secs, "columns": int(rr.status.shape[0]), "finished": int((rr.status == 0).sum()),
             "status_histogram": {str(int(k)): int(v) for k, v in zip(*np.unique(rr.status, return_counts=True))},
             "steps_per_column_min_max": [int(rr.n_accepted.min()), int(rr.n_accepted.max())],
@@ -345,7 +373,7 @@ def implicit_block(rr, secs, n_cells, peak_gbs, peak_src):
             "lu_factorisations": int(rr.nlu.sum()), "jacobians": int(rr.njev.sum()), "nfev": int(rr.nfev.sum()),
             "radau_steps_per_s": float(rr.n_accepted.sum() + rr.n_rejected.sum()) / secs,
             "roofline": {"bound": "hbm", "achieved": alg / secs / 1e9, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": alg / secs / 1e9 / peak_gbs, "traffic": None, "kernel": "radau_kernel",
+                         "frac": alg / secs / 1e9 / peak_gbs, "traffic": None, "kernel": kernel,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                          "algorithmic_bytes_per_step_attempt": alg / max(attempts, 1.0),
                          "traffic_note": "dram bytes of this launch are not measured in-run (ncu: profiles/)"}}
@@ -592,6 +620,15 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             del rr
         if rank == 0:
             line["implicit_time_to_Tstar"] = implicit
+        if world == 1 and not args.no_bdf:
+            # the other implicit solver of the reference (method="BDF"; LSODA's stiff mode): same sweep, same order
+            mb.integrate_bdf_batch(torch.from_numpy(np.ascontiguousarray(y0[:8])).to(dev), P[:8], t_span=(0.0, 1e-3),
+                                   first_step=1e-6, events=True, event_capacity=EVCAP)
+            sw = mb.sweep_lattice(scenario_base("default"), *lat)
+            mine = np.argsort(-sweep.predicted_cost(sw, "BDF") * np.ones(B), kind="stable")
+            rb, secs = implicit_sweep(mb, batch, torch, dev, sw, mine, EVCAP, t_eval=t_eval, method="BDF")
+            line["bdf_time_to_Tstar"] = {"default": implicit_block(rb, secs, N, hbm_gbs, hbm_src, method="BDF")}
+            del rb
 
     if rank != 0:
         if dist is not None:
@@ -664,6 +701,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             if tstar and not args.no_cpu_radau:
                 for base_name in ("scenario_A", "default"):
                     line["implicit_time_to_Tstar"][base_name]["cpu_baseline"] = cpu_radau_pass(base_name, cores, pool)
+                if "bdf_time_to_Tstar" in line:
+                    line["bdf_time_to_Tstar"]["default"]["cpu_baseline"] = cpu_radau_pass("default", cores, pool, "BDF")
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -688,6 +727,7 @@ def main():
                     help="time-to-T* without the ~140 s explicit sweep (implicit sweep only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cpu-radau", action="store_true", help="skip the SciPy Radau sample beside the implicit sweep")
+    ap.add_argument("--no-bdf", action="store_true", help="N=1: skip the BDF sweep to T* (~20 s + its SciPy BDF sample)")
     ap.add_argument("--cpu-t-end", type=float, default=0.03, help="CPU sample: integrate to this fraction of T*")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -140,11 +140,31 @@ __device__ __noinline__ void locate_events(const Args& A, const ColumnConsts& kc
   }
 }
 
+// THE one instance of the RHS in this kernel, fused with the Newton residual: out = Mc f(yy) - Ml (psi + d) — the right-
+// hand side M_lu (c f - psi - d) of solve_bdf_system's linear system in the scaling of factorise() — so f never travels
+// through memory (Mc = 1, Ml = 0 gives the plain f(yy)).  Returns whether every lane's rates were finite.
+template <bool VD>
+__device__ __noinline__ bool rhs_residual(const ColumnConsts* kc, const fm::Tables* tb, int N, int lane, const double* yy,
+                                          const double* psi, const double* d, double Mc, double Ml, double* out,
+                                          double (*stage)[2][kStageDoubles + 6]) {
+  bool finite = true;
+  auto sink = [&](int i, const double (&r5)[5]) {
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      finite = finite && isfinite(r5[f]);
+      out[i * 5 + f] = fma(Mc, r5[f], -Ml * (psi[i * 5 + f] + d[i * 5 + f]));
+    }
+  };
+  rhs_column<VD>(*kc, *tb, N, lane, yy, nullptr, stage, sink);
+  __syncwarp();
+  return __all_sync(0xffffffffu, finite);
+}
+
 #ifndef MARLPDE_BDF_MINBLOCKS
 #define MARLPDE_BDF_MINBLOCKS 3
 #endif
 
-template <bool VD>
+template <bool VD, bool kJacFD>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_BDF_MINBLOCKS) bdf_kernel(const Args A) {
   __shared__ __align__(16) unsigned char tab_raw[fm::kTableBytes];
   __shared__ WarpScratch scratch[kWarpsPerCta];
@@ -180,6 +200,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_BDF_MINBLOCKS) bdf_
       const double v = gy[(idx % 5) * N + idx / 5];
       y[idx] = v;
       D[idx] = v;
+      psi[idx] = 0.0;
+      d[idx] = 0.0;
     }
     __syncwarp();
     const ColumnConsts& kc = ws.kc;
@@ -194,13 +216,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_BDF_MINBLOCKS) bdf_
     bool lu_valid = false;
     double M_lu = 0.0;                                   // 1/c of the factors in Rec
 
-    auto eval_to = [&](const double* yy, double* out) { rhs_eval<VD>(&kc, &tb, N, lane, yy, nullptr, out, ws.stage); };
+    auto eval_to = [&](const double* yy, double* out) {   // out = f(yy)   (psi, d are finite: zeroed at column set-up)
+      rhs_residual<VD>(&kc, &tb, N, lane, yy, psi, d, 1.0, 0.0, out, ws.stage);
+    };
     auto jacobian = [&](const double* yy) {              // J at yy (finite-difference build: num_jac with its own f0)
-      if (kJacRhsEvals) {
+      if (kJacFD) {
         eval_to(yy, tmp);
-        nfev += 1 + kJacRhsEvals;
+        nfev += 1 + jac_rhs_evals<kJacFD>();
       }
-      imp::jacobian<VD>(kc, tb, N, lane, yy, tmp, atol, J, jscr, ws.stage);
+      imp::jacobian<VD, kJacFD>(kc, tb, N, lane, yy, tmp, atol, J, jscr, ws.stage);
       njev += 1;
     };
 
@@ -282,18 +306,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_BDF_MINBLOCKS) bdf_
           const double Mc = M_lu * c;                    // (I - c_lu J)^{-1} v = M_lu (M_lu I - J)^{-1} v: stale factors keep their c
           double dy_norm_old = -1.0, rate = -1.0;
           int k = 0;
+          bool predict_invalid = false;                  // f(y_predict) itself is not finite
           for (k = 0; k < kNewtonMaxIter; ++k) {
-            eval_to(y, f);
+            const bool finite = rhs_residual<VD>(&kc, &tb, N, lane, y, psi, d, Mc, M_lu, b, ws.stage);   // b = M_lu (c f - psi - d)
             nfev += 1;
-            bool finite = true;
-            _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
-              const double fv = f[idx];
-              finite = finite && isfinite(fv);
-              b[idx] = fma(Mc, fv, -M_lu * (psi[idx] + d[idx]));
+            if (!finite) {
+              predict_invalid = k == 0;
+              break;
             }
-            __syncwarp();
-            if (!__all_sync(0xffffffffu, finite)) break;
-            solve(ws, N, lane, Rec, b, nullptr, nullptr, false);
+            solve<true>(ws, N, lane, Rec, b, nullptr, nullptr, false);
             // norm(dy / scale) with scale = atol + rtol |y_predict| (y_predict = y - d), and in the same pass y += dy,
             // d += dy (bdf.py leaves them untouched when the rate test below breaks; they are dead then)
             double ss = 0.0;
@@ -321,7 +342,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_BDF_MINBLOCKS) bdf_
           if (converged) break;
           n_newton_fail += 1;
           if (current_jac) break;
-          // J = self.jac(t_new, y_predict)
+          // bdf.py evaluates J = self.jac(t_new, y_predict) here.  ONE deliberate difference: when the predictor itself has
+          // left the model's domain (extrapolated porosity <= 0: log(Phi) is NaN) that Jacobian is NaN, stays "current"
+          // for the rest of the step and every smaller step size fails on it until the step size underflows (r02t: 87 of
+          // 4096 lattice columns stalled this way; SciPy's own BDF has the same trap).  The step size is halved instead and
+          // the Jacobian is refreshed at a predictor that can be evaluated.
+          if (predict_invalid) break;
           _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
             double s = D[idx];
 #pragma unroll
@@ -441,8 +467,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_BDF_MINBLOCKS) bdf_
         ++next_eval;
       }
     }
+    // the state at time t: y (= y_new of the last accepted step); after a failed step y holds a Newton iterate, the
+    // last accepted state is then D[0] (change_D leaves row 0 alone)
+    const double* const y_out = status == MARLPDE_STATUS_STEP_TOO_SMALL ? D : y;
 #pragma unroll 1
-    for (int idx = lane; idx < n; idx += 32) gy[(idx % 5) * N + idx / 5] = y[idx];
+    for (int idx = lane; idx < n; idx += 32) gy[(idx % 5) * N + idx / 5] = y_out[idx];
     if (lane == 0) {
       st.t = t;
       st.h_abs = h_abs;
@@ -491,8 +520,12 @@ cudaError_t launch_bdf(double* d_y, const marlpde_column_params* d_params, marlp
   const int max_ctas = sm_count * MARLPDE_BDF_MINBLOCKS;
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas < 1) ctas = 1;
-  if (opt.flags & MARLPDE_FLAG_VAR_DPHI) bd::bdf_kernel<true><<<ctas, imp::kWarpsPerCta * 32, 0, stream>>>(a);
-  else bd::bdf_kernel<false><<<ctas, imp::kWarpsPerCta * 32, 0, stream>>>(a);
+  const bool vd = (opt.flags & MARLPDE_FLAG_VAR_DPHI) != 0, fd = (opt.flags & MARLPDE_FLAG_JAC_ANALYTIC) == 0;
+  const int threads = imp::kWarpsPerCta * 32;
+  if (vd && fd) bd::bdf_kernel<true, true><<<ctas, threads, 0, stream>>>(a);
+  else if (vd) bd::bdf_kernel<true, false><<<ctas, threads, 0, stream>>>(a);
+  else if (fd) bd::bdf_kernel<false, true><<<ctas, threads, 0, stream>>>(a);
+  else bd::bdf_kernel<false, false><<<ctas, threads, 0, stream>>>(a);
   return cudaGetLastError();
 }
 #endif

@@ -388,7 +388,7 @@ __device__ __noinline__ void fd_jacobian(const ColumnConsts& kc, const fm::Table
   }
 }
 
-// ANALYTIC Jacobian (default since r02r; -DMARLPDE_JAC_FD=1 restores the finite-difference diagonal blocks above):
+// ANALYTIC Jacobian (MARLPDE_FLAG_JAC_ANALYTIC; the default keeps the finite-difference diagonal blocks above, see jacobian()):
 // all three 5x5 blocks of every cell in ONE pass, one cell per lane, no RHS evaluation.  L_i and U_i as in jac_columns;
 // D_i = d rhs_i / d y_i differentiates the cell's own dependence: the porosity functions F, U, W, 1 - 2 ln Phi and the
 // time-varying dPhi, the Fiadeiro-Veronis weights through their Peclet numbers (the Langevin function's derivative
@@ -596,20 +596,23 @@ __device__ __noinline__ void jac_analytic(const ColumnConsts* kp, const fm::Tabl
   __syncwarp();
 }
 
-// The Jacobian the integrators use, and what it costs in RHS evaluations (nfev bookkeeping)
-#ifndef MARLPDE_JAC_FD
-#define MARLPDE_JAC_FD 0
-#endif
-constexpr int kJacRhsEvals = MARLPDE_JAC_FD ? 5 : 0;
-template <bool VD>
+// The Jacobian the integrators use: kJacFD = true — off-diagonal blocks analytic, diagonal blocks from 5 finite-difference
+// evaluations with num_jac's step rule (what SciPy's own Jacobian is; the DEFAULT) — or kJacFD = false, all blocks
+// analytic in one pass (MARLPDE_FLAG_JAC_ANALYTIC).  Measured on the 4096-column lattice (r02s): the analytic blocks make the
+// saturated phase 9 % (Radau) / 6 % (BDF) faster and change nothing in the columns that finish either way (work ratio
+// 1.00), but the model has switching surfaces — the Fiadeiro-Veronis weight jumps from 0 to Pe/3 at |Pe| = Pe_min
+// (LHeureux_model.py:437-442) — on which a trajectory can slide (W of a cell hovering around 0 while a 2-cell sawtooth in
+// Phi develops): a one-sided difference straddles the jump and hands Newton a steep slope there, the in-regime derivative
+// does not, and the step size collapses (SciPy Radau stalls on those columns with either Jacobian).  To T*: 11 unfinished
+// columns / 17.5 s with the finite-difference diagonal blocks, 51 / 38 s with the analytic ones — hence the default.
+template <bool kJacFD>
+__host__ __device__ constexpr int jac_rhs_evals() { return kJacFD ? 5 : 0; }
+template <bool VD, bool kJacFD>
 __device__ __forceinline__ void jacobian(const ColumnConsts& kc, const fm::Tables& tb, int N, int lane, const double* y,
                                          const double* f, double atol, double* J, double* scratch,
                                          double (*stage)[2][kStageDoubles + 6]) {
-#if MARLPDE_JAC_FD
-  fd_jacobian<VD>(kc, tb, N, lane, y, f, atol, J, scratch, stage);
-#else
-  jac_analytic<VD>(&kc, &tb, N, lane, y, J);
-#endif
+  if (kJacFD) fd_jacobian<VD>(kc, tb, N, lane, y, f, atol, J, scratch, stage);
+  else jac_analytic<VD>(&kc, &tb, N, lane, y, J);
 }
 
 // Block-Thomas factorisation of (M I - J) for both systems at once.
@@ -679,7 +682,7 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, const d
     float* const rec = Rec + (size_t)i * 128;
     if (lane < 25) {                                         // fp32 copies of L_i and U_i for the sweeps
       rec[lane] = (float)Ji[lane];
-      rec[102 + lane] = (float)Ji[50 + lane];
+      rec[(kComplex ? 102 : 52) + lane] = (float)Ji[50 + lane];
     }
     const int offP = bottom ? 50 : 0;     // block that couples to the PREVIOUS cell of the chain (L top-down, U bottom-up)
     const int offN = bottom ? 0 : 50;     // block that couples to the NEXT cell of the chain
@@ -793,8 +796,14 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, const d
 // instead of N.  As in factorise(), the records of the next kDepth cells of each chain are in flight (cp.async)
 // while the current cell is processed; a sweep reads 51 eight-byte words of a cell's record: words [0,51) =
 // {L, S0, S1} (top inward, bottom outward) or words [13,64) = {S0, S1, U} (bottom inward, top outward).
+// kCompact (BDF: one real system): records are [L | S^-1 | U] at floats 0 / 26 / 52 (factorise<false>), a sweep reads
+// 26 eight-byte words of a cell's record — words [0,26) = {L, S} or [13,39) = {S, U} — instead of 51; system 0 only.
+template <bool kCompact>
 static __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, const float* Rec, double* b0,
                                    double* b1, double* b2, bool both) {
+  constexpr int kWords = kCompact ? 26 : 51;                 // words of a record a sweep reads
+  constexpr int kOffU = kCompact ? 52 : 102;                 // float offset of U_i in a record
+  if (kCompact) both = false;
   const int ch = lane >> 4, s = (lane >> 3) & 1, r = lane & 7, l16 = lane & 15;
   const bool valid = r < 5 && (s == 0 || both);
   double* const bre = s == 0 ? b0 : b1;
@@ -825,14 +834,14 @@ static __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, cons
   auto sweep = [&](const bool outward) {
     auto cell = [&](int j) { return outward ? (ch == 0 ? mid - 1 - j : mid + 1 + j) : (ch == 0 ? j : N - 1 - j); };
     const bool low_window = (ch == 0) != outward;            // words [0,51): {L, S0, S1}; else [13,64): {S0, S1, U}
-    const int oC = low_window ? 0 : 76, oS0 = low_window ? 26 : 0, oS1 = low_window ? 52 : 26;   // float offsets
+    const int oC = low_window ? 0 : kOffU - 26, oS0 = low_window ? 26 : 0, oS1 = low_window ? 52 : 26;   // float offsets
     auto request = [&](int j) {
       if (j < nch) {
         const double* src = reinterpret_cast<const double*>(Rec + (size_t)cell(j) * 128) + (low_window ? 0 : 13);
         double* dst = ws.mst[ch][j % kSlots];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (l16 + 16 * k < 51) cp_async8(dst + l16 + 16 * k, src + l16 + 16 * k);
+          if (l16 + 16 * k < kWords) cp_async8(dst + l16 + 16 * k, src + l16 + 16 * k);
       }
       cp_async_commit();                                     // (empty groups keep the group count uniform)
     };
@@ -886,7 +895,7 @@ static __device__ __noinline__ void solve(WarpScratch& ws, int N, int lane, cons
       }
       if (N - 1 - mid > 0) {
 #pragma unroll
-        for (int m = 0; m < 5; ++m) g = crfma((double)Rm[102 + m * 5 + r], ws.vec[buf][1][s][m], g);
+        for (int m = 0; m < 5; ++m) g = crfma((double)Rm[kOffU + m * 5 + r], ws.vec[buf][1][s][m], g);
       }
     }
     buf ^= 1;

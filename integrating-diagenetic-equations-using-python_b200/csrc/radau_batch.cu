@@ -108,7 +108,7 @@ __device__ __noinline__ double predict_factor(double h_abs, double h_abs_old, do
   return fmin(1.0, mult) / sqrt(sqrt(err));      // x**0.25 as two square roots; err == 0 -> inf, as numpy
 }
 
-template <bool VD>
+template <bool VD, bool kJacFD>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) radau_kernel(const Args A) {
   __shared__ __align__(16) unsigned char tab_raw[fm::kTableBytes];
   __shared__ WarpScratch scratch[kWarpsPerCta];
@@ -166,9 +166,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
     if (t < A.opt.t_bound) {
       eval_to(y, nullptr, w.f);
       nfev += 1;
-      jacobian<VD>(kc, tb, N, lane, y, w.f, atol, w.J, w.B, ws.stage);
+      jacobian<VD, kJacFD>(kc, tb, N, lane, y, w.f, atol, w.J, w.B, ws.stage);
       njev += 1;
-      nfev += kJacRhsEvals;   // (finite-difference build: one evaluation per field)
+      nfev += jac_rhs_evals<kJacFD>();   // (finite-difference diagonal blocks: one evaluation per field)
     }
     const bool ev_on = (A.opt.flags & MARLPDE_FLAG_EVENTS) != 0;
     unsigned ev_prev = 0u;
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
             }
             __syncwarp();
             if (!__all_sync(0xffffffffu, finite)) break;
-            solve(ws, N, lane, w.Rec, w.B, w.B + n, w.B + 2 * n, true);
+            solve<false>(ws, N, lane, w.Rec, w.B, w.B + n, w.B + 2 * n, true);
             // norm(dW / scale) and, in the same pass, W += dW, Z = T W.  (radau.py leaves W and Z untouched when
             // the rate test below breaks; they are dead then — every continuation re-initialises them from Z0.)
             double ss = 0.0;
@@ -327,9 +327,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
           if (converged) break;
           n_newton_fail += 1;
           if (current_jac) break;
-          jacobian<VD>(kc, tb, N, lane, y, w.f, atol, w.J, w.B, ws.stage);
+          jacobian<VD, kJacFD>(kc, tb, N, lane, y, w.f, atol, w.J, w.B, ws.stage);
           njev += 1;
-          nfev += kJacRhsEvals;   // (finite-difference build: one evaluation per field)
+          nfev += jac_rhs_evals<kJacFD>();   // (finite-difference diagonal blocks: one evaluation per field)
           current_jac = true;
           lu_valid = false;
         }
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
           w.err[idx] = w.f[idx] + ze;
         }
         __syncwarp();
-        solve(ws, N, lane, w.Rec, w.err, nullptr, nullptr, false);
+        solve<false>(ws, N, lane, w.Rec, w.err, nullptr, nullptr, false);
         auto err_norm_of = [&]() {
           double ss = 0.0;
           _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
           nfev += 1;
           _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) w.err[idx] = w.B[idx] + w.tmp[idx];
           __syncwarp();
-          solve(ws, N, lane, w.Rec, w.err, nullptr, nullptr, false);
+          solve<false>(ws, N, lane, w.Rec, w.err, nullptr, nullptr, false);
           error_norm = err_norm_of();
         }
         if (error_norm > 1.0 || !(error_norm == error_norm)) {
@@ -399,9 +399,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
       eval_to(y, nullptr, w.f);
       nfev += 1;
       if (recompute_jac) {
-        jacobian<VD>(kc, tb, N, lane, y, w.f, atol, w.J, w.B, ws.stage);
+        jacobian<VD, kJacFD>(kc, tb, N, lane, y, w.f, atol, w.J, w.B, ws.stage);
         njev += 1;
-        nfev += kJacRhsEvals;   // (finite-difference build: one evaluation per field)
+        nfev += jac_rhs_evals<kJacFD>();   // (finite-difference diagonal blocks: one evaluation per field)
         current_jac = true;
       } else {
         current_jac = false;
@@ -484,8 +484,12 @@ cudaError_t launch_radau(double* d_y, const marlpde_column_params* d_params, mar
   const int max_ctas = sm_count * MARLPDE_RADAU_MINBLOCKS;
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas < 1) ctas = 1;
-  if (opt.flags & MARLPDE_FLAG_VAR_DPHI) rd::radau_kernel<true><<<ctas, rd::kWarpsPerCta * 32, 0, stream>>>(a);
-  else rd::radau_kernel<false><<<ctas, rd::kWarpsPerCta * 32, 0, stream>>>(a);
+  const bool vd = (opt.flags & MARLPDE_FLAG_VAR_DPHI) != 0, fd = (opt.flags & MARLPDE_FLAG_JAC_ANALYTIC) == 0;
+  const int threads = rd::kWarpsPerCta * 32;
+  if (vd && fd) rd::radau_kernel<true, true><<<ctas, threads, 0, stream>>>(a);
+  else if (vd) rd::radau_kernel<true, false><<<ctas, threads, 0, stream>>>(a);
+  else if (fd) rd::radau_kernel<false, true><<<ctas, threads, 0, stream>>>(a);
+  else rd::radau_kernel<false, false><<<ctas, threads, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

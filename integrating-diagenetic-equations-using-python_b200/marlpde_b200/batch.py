@@ -282,28 +282,35 @@ class RadauResult:
 
 def integrate_radau_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e-3, atol=1e-3, t_eval=None,
                           max_step=np.inf, max_steps: int = 0, events: bool = False, event_capacity: int = 0,
-                          state: np.ndarray | None = None, device: int = 0, inplace: bool = False) -> RadauResult:
+                          state: np.ndarray | None = None, device: int = 0, inplace: bool = False,
+                          jac: str = "fd") -> RadauResult:
     """Implicit integration of every column: 3-stage Radau IIA with SciPy's step-size, Newton and
     Jacobian-reuse rules (`solve_ivp(method="Radau", jac_sparsity=jacobian_sparsity())`, the
     reference's default Solver, parameters.py:201-221) and a block-tridiagonal linear solver."""
     return _integrate_implicit("radau", y0, params, t_span, first_step, rtol, atol, t_eval, max_step, max_steps, events,
-                               event_capacity, state, device, inplace)
+                               event_capacity, state, device, inplace, jac)
 
 
 def integrate_bdf_batch(y0, params, t_span=(0.0, 1.0), first_step=1e-6, rtol=1e-3, atol=1e-3, t_eval=None,
                         max_step=np.inf, max_steps: int = 0, events: bool = False, event_capacity: int = 0,
-                        state: np.ndarray | None = None, device: int = 0, inplace: bool = False) -> RadauResult:
+                        state: np.ndarray | None = None, device: int = 0, inplace: bool = False,
+                          jac: str = "fd") -> RadauResult:
     """Implicit integration of every column with the variable-order BDF kernel (csrc/bdf_batch.cu): SciPy's `BDF`
     step for step (`solve_ivp(method="BDF", jac_sparsity=jacobian_sparsity())`, parameters.py:235-236) on the
     block-tridiagonal linear solver of the Radau kernel; also what `method="LSODA"` batches run on the device
     (parameters.py:214-219: LSODA is a BDF code on this stiff system).  Same result type as the Radau path; `nlu`
     counts one real factorisation each.  A column resumed from `state` restarts at order 1."""
     return _integrate_implicit("bdf", y0, params, t_span, first_step, rtol, atol, t_eval, max_step, max_steps, events,
-                               event_capacity, state, device, inplace)
+                               event_capacity, state, device, inplace, jac)
 
 
 def _integrate_implicit(kind, y0, params, t_span, first_step, rtol, atol, t_eval, max_step, max_steps, events,
-                        event_capacity, state, device, inplace) -> RadauResult:
+                        event_capacity, state, device, inplace, jac="fd") -> RadauResult:
+    """`jac`: "fd" (default) — analytic off-diagonal 5x5 blocks, diagonal blocks by finite differences with num_jac's step
+    rule (SciPy's own Jacobian); "analytic" — every block analytic, no RHS evaluations (MARLPDE_FLAG_JAC_ANALYTIC): faster,
+    but the step size can collapse on the model's switching surfaces (csrc/implicit_common.cuh jacobian())."""
+    if jac not in ("fd", "analytic"):
+        raise ValueError("jac must be 'fd' or 'analytic'")
     lib = _cabi.lib()
     f_ws = getattr(lib, f"marlpde_{kind}_workspace_bytes")
     f_dev = getattr(lib, f"marlpde_{kind}_integrate_dev")
@@ -329,7 +336,8 @@ def _integrate_implicit(kind, y0, params, t_span, first_step, rtol, atol, t_eval
     cap = int(event_capacity) if events else 0
     opts = _cabi.RK45Options(t_bound=t_bound, rtol=float(rtol), atol=float(atol), max_step=float(max_step),
                              max_steps=int(max_steps), n_eval=n_eval, event_capacity=cap,
-                             flags=(_cabi.FLAG_EVENTS if events else 0) | _model_flags(params), quantum=0)
+                             flags=(_cabi.FLAG_EVENTS if events else 0) | _model_flags(params)
+                             | (_cabi.FLAG_JAC_ANALYTIC if jac == "analytic" else 0), quantum=0)
     if _is_torch(y0):
         import torch
         if not y0.is_cuda or y0.dtype != torch.float64 or not y0.is_contiguous():

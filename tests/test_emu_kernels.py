@@ -211,7 +211,7 @@ def emu_bdf():
     lib = C.CDLL(so)
     lib.emu_bdf.restype = C.c_int
 
-    def run(P, y, t_end, t_eval=(), events=False, first_step=1e-6, tol=1e-3):
+    def run(P, y, t_end, t_eval=(), events=False, first_step=1e-6, tol=1e-3, jac="fd"):
         y = np.ascontiguousarray(y, dtype=np.float64).copy()
         P = np.ascontiguousarray(P)
         B, _, N = y.shape
@@ -220,7 +220,8 @@ def emu_bdf():
         snap = np.full((B, max(1, te.size), 5, N), np.nan)
         ec, et, stats = np.zeros((B, 7), np.int32), np.full((B, 7, 16), np.nan), np.zeros((B, 4), np.int64)
         o = _cabi.RK45Options(t_bound=t_end, rtol=tol, atol=tol, max_step=float("inf"), max_steps=0, n_eval=te.size,
-                              event_capacity=16, flags=_cabi.FLAG_EVENTS if events else 0, quantum=0)
+                              event_capacity=16, flags=(_cabi.FLAG_EVENTS if events else 0) |
+                              (_cabi.FLAG_JAC_ANALYTIC if jac == "analytic" else 0), quantum=0)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         rc = lib.emu_bdf(p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), p(stats), p(ec), p(et))
         assert rc == 0, f"emulated BDF kernel: rc {rc}"
@@ -235,13 +236,15 @@ def test_bdf_kernel_under_emulation_is_scipy_bdf_step_for_step(emu_bdf):
     the tolerance — at rtol = 1e-3 and 1e-6, scenario A to T* (the reference's regression case) with dense output."""
     pde = oracle.default_scenario() | SCEN_A
     P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
-    for tol, te, gate in ((1e-3, np.linspace(0, 1, 6), 1e-3), (1e-6, np.array([0.0, 0.1]), 1e-2)):
+    for tol, te, gate, jac in ((1e-3, np.linspace(0, 1, 6), 1e-3, "fd"), (1e-3, np.linspace(0, 1, 6), 1e-3, "analytic"),
+                               (1e-6, np.array([0.0, 0.1]), 1e-2, "fd")):
         sol = oracle.integrate(pde, method="BDF", t_span=(0, te[-1]), t_eval=te, events=False, first_step=1e-6, rtol=tol,
                                atol=tol, jac_sparsity=exact_sparsity(200))
-        res = emu_bdf(P, y0, te[-1], t_eval=te, tol=tol)
+        res = emu_bdf(P, y0, te[-1], t_eval=te, tol=tol, jac=jac)
         assert res["state"]["status"][0] == 0
         assert res["stats"][0, 0] == sol.njev and res["stats"][0, 1] == sol.nlu
         assert res["stats"][0, 2] == sol.nfev - 1                      # bdf.py: one fun call per Newton iteration + f(t0, y0)
+        assert res["state"]["nfev"][0] == sol.nfev + (6 * sol.njev if jac == "fd" else 0)   # + f0 and 5 colours per Jacobian
         want = np.moveaxis(sol.y.reshape(5, 200, -1), 2, 0)
         assert np.max(np.abs(res["snapshots"][0] - want) / (tol + tol * np.abs(want))) <= gate
 

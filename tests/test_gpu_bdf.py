@@ -31,12 +31,13 @@ def _scipy_bdf(pde, t_end, t_eval, tol=1e-3, first_step=1e-6, events=False, spar
                             rtol=tol, atol=tol, jac_sparsity=exact_sparsity(N) if sparsity is None else sparsity)
 
 
-@pytest.mark.parametrize("tol,t_end", [(1e-3, 1.0), (1e-6, 0.2)])
-def test_scenario_A_step_for_step_with_scipy_bdf(tol, t_end):
+@pytest.mark.parametrize("tol,t_end,jac", [(1e-3, 1.0, "fd"), (1e-3, 1.0, "analytic"), (1e-6, 0.2, "fd")])
+def test_scenario_A_step_for_step_with_scipy_bdf(tol, t_end, jac):
+    """Both Jacobians of the kernel: finite-difference diagonal blocks (default; SciPy's num_jac rule) and all-analytic."""
     pde = oracle.default_scenario() | SCEN_A
     te = np.linspace(0, t_end, 6)
     res = mb.integrate_bdf_batch(mb.initial_state(pde), mb.derive_column_params(pde), t_span=(0, t_end), first_step=1e-6,
-                                 rtol=tol, atol=tol, t_eval=te)
+                                 rtol=tol, atol=tol, t_eval=te, jac=jac)
     sol = _scipy_bdf(pde, t_end, te, tol)
     assert res.status[0] == 0 and res.t[0] == t_end and res.next_eval[0] == te.size
     assert abs(int(res.njev[0]) - sol.njev) <= 1 and abs(int(res.nlu[0]) - sol.nlu) <= 2
@@ -162,3 +163,19 @@ def test_dropin_bdf_and_lsoda_device_routes(tmp_path, monkeypatch):
     last2, covered2, *_ = integrate_equations(asdict(Solver(method="LSODA")), asdict(Tracker()), dict(pde))
     assert covered2 == pde["Tstar"] and np.array_equal(last2, last)
     assert np.max(np.abs(last - ref) / (0.01 + 0.1 * np.abs(ref))) <= 2.0
+
+
+def test_predictor_outside_the_model_domain_does_not_poison_the_step():
+    """Lattice column 1305 (default base): near t = 0.165 the order-3 predictor extrapolates the porosity of one cell below
+    zero (log(Phi) = NaN).  bdf.py evaluates the Jacobian AT that predictor and keeps it for the rest of the step, so every
+    smaller step size fails too and the integration ends with "step size too small"; the kernel halves the step size
+    first (csrc/bdf_batch.cu, the one deliberate difference from bdf.py).  The column — and its neighbours that stalled
+    the same way in r02s — must get through the stiff phase."""
+    from dataclasses import asdict
+    from marlpde.parameters import Map_Scenario
+    lat = mb.sweep_lattice(asdict(Map_Scenario()), 16, 16, 16)
+    cols = np.array([1305, 1360, 3932])
+    for jac in ("analytic", "fd"):
+        res = mb.integrate_bdf_batch(mb.initial_state(lat)[cols], mb.derive_column_params(lat)[cols], t_span=(0, 0.3),
+                                     first_step=1e-6, jac=jac)
+        assert np.all(res.status == 0) and np.all(res.t == 0.3), (jac, res.status, res.t)

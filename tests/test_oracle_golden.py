@@ -178,3 +178,23 @@ def test_brentq_restatement_is_bit_identical_to_scipy():
     assert oracle.brentq_restated(lambda x: x, 0.0, 1.0)[0] == 0.0          # f(a) == 0 returns a
     with pytest.raises(ValueError):
         oracle.brentq_restated(lambda x: x * x + 1, -1.0, 1.0)
+
+
+def test_lsoda_runs_in_bdf_mode():
+    """What `method="LSODA"` (parameters.py:214-219) does on this system, measured on the oracle RHS with ODEPACK's own
+    method log (odeint `mused`: 1 = Adams, 2 = BDF): it leaves the Adams mode within the first few dozen steps (t ~ 2e-5 T*)
+    and never returns — from then on LSODA is a variable-order BDF code, which is what the device path for LSODA batches
+    runs (csrc/bdf_batch.cu).  Both scenario bases, the reference's lband = uband = 1."""
+    from scipy.integrate import odeint
+    for over in ({"Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}, {}):
+        pde = oracle.default_scenario() | over
+        f = oracle.rhs_fn(oracle.kernel_params(pde))
+        ts = np.concatenate([[0.0], np.geomspace(1e-6, 0.05, 60)])
+        _, info = odeint(lambda y, t: f(t, y), oracle.initial_state(pde), ts, rtol=1e-3, atol=1e-3, h0=1e-6, ml=1, mu=1,
+                         full_output=True, mxstep=500000)
+        mused, nst = info["mused"], info["nst"]
+        first_bdf = int(np.argmax(mused == 2))
+        assert mused[first_bdf] == 2 and np.all(mused[first_bdf:] == 2)          # switches once, stays
+        assert ts[1 + first_bdf] <= 1e-4 and nst[first_bdf] <= 100               # ... within the first steps
+        assert nst[-1] >= 20 * nst[first_bdf]                                    # already at t = 0.05 T*: > 95 % BDF steps
+        # (to T*, scenario A: 24 Adams steps of 15 059)

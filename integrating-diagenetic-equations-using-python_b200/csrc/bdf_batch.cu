@@ -160,6 +160,7 @@ __device__ __noinline__ bool rhs_residual(const ColumnConsts* kc, const fm::Tabl
   return __all_sync(0xffffffffu, finite);
 }
 
+// resident CTAs per SM (r02v, 4096 / 64 lattice columns to t = 0.05): 2 -> 2.40 / 0.73 s, 3 -> 1.90 / 0.75 s, 4 -> 1.83 / 0.84 s
 #ifndef MARLPDE_BDF_MINBLOCKS
 #define MARLPDE_BDF_MINBLOCKS 3
 #endif

@@ -605,6 +605,9 @@ __device__ __noinline__ void jac_analytic(const ColumnConsts* kp, const fm::Tabl
 // Phi develops): a one-sided difference straddles the jump and hands Newton a steep slope there, the in-regime derivative
 // does not, and the step size collapses (SciPy Radau stalls on those columns with either Jacobian).  To T*: 11 unfinished
 // columns / 17.5 s with the finite-difference diagonal blocks, 51 / 38 s with the analytic ones — hence the default.
+// (Also measured, r02v: analytic first + ONE finite-difference retry at the same state when a current analytic Jacobian
+//  did not make Newton converge — finishes the same 4085 columns but such double failures are frequent in the stiff
+//  phase: 1.71 vs 1.39 s to t = 0.05, 22.1 vs 17.7 s to T* for Radau, 27.3 vs 22.3 s for BDF.  Removed.)
 template <bool kJacFD>
 __host__ __device__ constexpr int jac_rhs_evals() { return kJacFD ? 5 : 0; }
 template <bool VD, bool kJacFD>

@@ -113,9 +113,9 @@ typedef struct marlpde_rk45_options {
                                     resident slots) are cut into quanta, the others are claimed whole — for sweeps whose
                                     columns need different numbers of attempts, ordered longest first (launches without
                                     a step budget do this by themselves)                                              */
-#define MARLPDE_FLAG_JAC_ANALYTIC 16u /* implicit integrators: all 5x5 Jacobian blocks analytic in one pass (no RHS evaluation)
-                                       * instead of analytic off-diagonal blocks + finite-difference diagonal blocks (num_jac's
-                                       * step rule, the default: more robust on the model's switching surfaces) */
+#define MARLPDE_FLAG_JAC_FD 16u /* implicit integrators: diagonal 5x5 Jacobian blocks from 5 finite-difference evaluations with
+                                 * num_jac's step rule (what SciPy forms) instead of the default — every block analytic in one
+                                 * pass, and only for cells ON a switching surface of the model the one-sided difference */
 #define MARLPDE_FLAG_VAR_DPHI 4u /* some columns of the batch carry MARLPDE_MODEL_VAR_DPHI (see marlpde_column_params) */
 
 /* Per-column integrator state: input (start/resume point) and output (end point). */

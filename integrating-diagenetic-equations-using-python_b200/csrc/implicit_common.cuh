@@ -388,7 +388,7 @@ __device__ __noinline__ void fd_jacobian(const ColumnConsts& kc, const fm::Table
   }
 }
 
-// ANALYTIC Jacobian (MARLPDE_FLAG_JAC_ANALYTIC; the default keeps the finite-difference diagonal blocks above, see jacobian()):
+// ANALYTIC Jacobian (the default; MARLPDE_FLAG_JAC_FD selects the finite-difference diagonal blocks above, see jacobian()):
 // all three 5x5 blocks of every cell in ONE pass, one cell per lane, no RHS evaluation.  L_i and U_i as in jac_columns;
 // D_i = d rhs_i / d y_i differentiates the cell's own dependence: the porosity functions F, U, W, 1 - 2 ln Phi and the
 // time-varying dPhi, the Fiadeiro-Veronis weights through their Peclet numbers (the Langevin function's derivative
@@ -401,9 +401,16 @@ __device__ __noinline__ void fd_jacobian(const ColumnConsts& kc, const fm::Table
 // of the oracle RHS on evolved states of the reference's fixtures, all cells, both model variants
 // (tests/test_host_side.py::test_analytic_jacobian_blocks): agreement to the accuracy of the differences.
 // Generic (IEEE) maths as in cell_rhs: no restriction on the state.
+// SWITCHING SURFACES.  The porosity column of the own-cell block is the only place the model's switches enter the Jacobian
+// (the Peclet numbers and U depend on the cell's own Phi only).  A cell whose state sits ON a switch — |Pe| within a
+// relative kSwitchTol of Pe_min or Pe_max, U within kSwitchTol of 0 — gets that column from the one-sided difference
+// quotient num_jac would form (its step rule, sign(f) included; the ghost cells follow the perturbed cell): a trajectory
+// that slides along a switching surface is held there by exactly this straddling difference (jacobian() below).
+constexpr double kSwitchTol = 1e-5;
+
 template <bool VD>
 __device__ __noinline__ void jac_analytic(const ColumnConsts* kp, const fm::Tables* tbp, int N, int lane, const double* y,
-                                          double* J) {
+                                          double atol, double* J) {
   const ColumnConsts& k = *kp;
   const fm::Tables& tb = *tbp;
   const double hdx = 0.5 * k.inv_dx;
@@ -466,6 +473,13 @@ __device__ __noinline__ void jac_analytic(const ColumnConsts* kp, const fm::Tabl
     weight(W * den * k.kPeCa, k.kPeCa * dWden, s2, ds2);
     weight(W * den * k.kPeCO3, k.kPeCO3 * dWden, s3, ds3);
     weight(W * kPePhi, fma(dW, kPePhi, W * dkPePhi), s4, ds4);
+    bool on_switch = fabs(U) <= kSwitchTol * fmax(1.0, fabs(k.presum));
+    if (k.FV_switch) {
+      const double pe[3] = {fabs(W * den * k.kPeCa), fabs(W * den * k.kPeCO3), fabs(W * kPePhi)};
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        on_switch = on_switch || fabs(pe[q] - k.Pe_min) <= kSwitchTol * k.Pe_min || fabs(pe[q] - k.Pe_max) <= kSwitchTol * k.Pe_max;
+    }
     const double sg[3] = {s2, s3, s4}, dsg[3] = {ds2, ds3, ds4};
     double g[3], dg_own[3], dg_P[3], dg_m[3], dg_p[3], lap[3];
 #pragma unroll
@@ -583,6 +597,26 @@ __device__ __noinline__ void jac_analytic(const ColumnConsts* kp, const fm::Tabl
           Ub[r][f] = 0.0;
         }
     }
+    if (on_switch) {                                         // rare: one-sided difference quotient for d / d Phi (see above)
+      CellRates r0, r1;
+      const bool in_mask = i >= k.mask_lo && i < k.mask_hi;
+      cell_rhs(k, tb, c, m, pl, in_mask, r0);
+      const double hP = fd_step(P, r0.r[4], atol);
+      double c2[5], m2[5], p2[5];
+#pragma unroll
+      for (int f = 0; f < 5; ++f) {
+        c2[f] = c[f];
+        m2[f] = m[f];
+        p2[f] = pl[f];
+      }
+      c2[4] = P + hP;
+      if (first) m2[4] = fma(2.0, k.bc_top[4], -c2[4]);
+      if (last) p2[4] = c2[4];
+      cell_rhs(k, tb, c2, m2, p2, in_mask, r1);
+      const double inv = 1.0 / hP;
+#pragma unroll
+      for (int r = 0; r < 5; ++r) D[r][4] = (r1.r[r] - r0.r[r]) * inv;
+    }
     double* blk = J + (size_t)i * 75;                        // blocks [L|D|U], each COLUMN-major
 #pragma unroll
     for (int f = 0; f < 5; ++f)
@@ -596,18 +630,23 @@ __device__ __noinline__ void jac_analytic(const ColumnConsts* kp, const fm::Tabl
   __syncwarp();
 }
 
-// The Jacobian the integrators use: kJacFD = true — off-diagonal blocks analytic, diagonal blocks from 5 finite-difference
-// evaluations with num_jac's step rule (what SciPy's own Jacobian is; the DEFAULT) — or kJacFD = false, all blocks
-// analytic in one pass (MARLPDE_FLAG_JAC_ANALYTIC).  Measured on the 4096-column lattice (r02s): the analytic blocks make the
-// saturated phase 9 % (Radau) / 6 % (BDF) faster and change nothing in the columns that finish either way (work ratio
-// 1.00), but the model has switching surfaces — the Fiadeiro-Veronis weight jumps from 0 to Pe/3 at |Pe| = Pe_min
-// (LHeureux_model.py:437-442) — on which a trajectory can slide (W of a cell hovering around 0 while a 2-cell sawtooth in
-// Phi develops): a one-sided difference straddles the jump and hands Newton a steep slope there, the in-regime derivative
-// does not, and the step size collapses (SciPy Radau stalls on those columns with either Jacobian).  To T*: 11 unfinished
-// columns / 17.5 s with the finite-difference diagonal blocks, 51 / 38 s with the analytic ones — hence the default.
-// (Also measured, r02v: analytic first + ONE finite-difference retry at the same state when a current analytic Jacobian
-//  did not make Newton converge — finishes the same 4085 columns but such double failures are frequent in the stiff
-//  phase: 1.71 vs 1.39 s to t = 0.05, 22.1 vs 17.7 s to T* for Radau, 27.3 vs 22.3 s for BDF.  Removed.)
+// The Jacobian the integrators use.  DEFAULT (kJacFD = false): all blocks analytic in one pass (jac_analytic), with the
+// switching-surface rule above.  MARLPDE_FLAG_JAC_FD (kJacFD = true): off-diagonal blocks analytic, diagonal blocks from 5
+// finite-difference evaluations with num_jac's step rule — what SciPy's own Jacobian is.
+// Measured on the 4096-column lattice, default base (r02s, r02v, r02w; sweeps to T* in predicted-cost order):
+//                                          t = 0.05 (Radau / BDF)     to T*: Radau              BDF
+//   finite-difference diagonal blocks        1.40 / 1.92 s              17.7 s, 4085 finish      22.3 s, 4072 finish
+//   analytic, no switching-surface rule      1.27 / 1.84 s              38.4 s, 4045 finish      21.4 s, 4014 finish
+//   analytic + one FD retry after a failure  1.71 / 2.23 s              22.1 s, 4085             27.3 s, 4073        (removed)
+//   analytic + switching-surface rule        1.27 / 1.86 s              17.0 s, 4085 finish      21.9 s, 4071 finish
+// The analytic blocks change nothing in the columns that finish either way (work ratio 1.00).  Without the rule 40 more
+// columns stall late in the integration: the Fiadeiro-Veronis weight jumps from 0 to Pe/3 at |Pe| = Pe_min
+// (LHeureux_model.py:437-442), W of a cell hovers around 0 while a 2-cell sawtooth in Phi develops, and the trajectory
+// slides along that surface.  A one-sided difference straddles the jump and hands Newton a steep slope that holds the
+// state on the surface; the in-regime derivative does not, and the step size collapses (SciPy Radau stalls on those
+// columns with either Jacobian; the stall state found with SciPy sat at Pe_Phi = -0.0100000).  Taking just the porosity
+// column of just the cells on a surface from the difference quotient restores exactly the finite-difference behaviour
+// (the same 11 columns stay unfinished — they stop in SciPy too) at the analytic price.
 template <bool kJacFD>
 __host__ __device__ constexpr int jac_rhs_evals() { return kJacFD ? 5 : 0; }
 template <bool VD, bool kJacFD>
@@ -615,7 +654,7 @@ __device__ __forceinline__ void jacobian(const ColumnConsts& kc, const fm::Table
                                          const double* f, double atol, double* J, double* scratch,
                                          double (*stage)[2][kStageDoubles + 6]) {
   if (kJacFD) fd_jacobian<VD>(kc, tb, N, lane, y, f, atol, J, scratch, stage);
-  else jac_analytic<VD>(&kc, &tb, N, lane, y, J);
+  else jac_analytic<VD>(&kc, &tb, N, lane, y, atol, J);
 }
 
 // Block-Thomas factorisation of (M I - J) for both systems at once.

@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(32) jac_probe_kernel(const double* y_field_maj
   const int lane = threadIdx.x;
   for (int idx = lane; idx < 5 * N; idx += 32) ycell[idx] = y_field_major[(idx % 5) * N + idx / 5];
   __syncthreads();
-  imp::jac_analytic<VD>(&kc, &tb, N, lane, ycell, J);
+  imp::jac_analytic<VD>(&kc, &tb, N, lane, ycell, 1e-3, J);   // atol of the reference's Solver (parameters.py:208)
 }
 
 }  // namespace

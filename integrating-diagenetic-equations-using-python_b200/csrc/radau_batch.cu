@@ -484,7 +484,7 @@ cudaError_t launch_radau(double* d_y, const marlpde_column_params* d_params, mar
   const int max_ctas = sm_count * MARLPDE_RADAU_MINBLOCKS;
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas < 1) ctas = 1;
-  const bool vd = (opt.flags & MARLPDE_FLAG_VAR_DPHI) != 0, fd = (opt.flags & MARLPDE_FLAG_JAC_ANALYTIC) == 0;
+  const bool vd = (opt.flags & MARLPDE_FLAG_VAR_DPHI) != 0, fd = (opt.flags & MARLPDE_FLAG_JAC_FD) != 0;
   const int threads = rd::kWarpsPerCta * 32;
   if (vd && fd) rd::radau_kernel<true, true><<<ctas, threads, 0, stream>>>(a);
   else if (vd) rd::radau_kernel<true, false><<<ctas, threads, 0, stream>>>(a);

@@ -20,7 +20,7 @@ FLAG_EVENTS = 1
 FLAG_QUEUE_LOCKS = 2
 FLAG_VAR_DPHI = 4
 FLAG_QUEUE_TAIL = 8
-FLAG_JAC_ANALYTIC = 16
+FLAG_JAC_FD = 16
 MODEL_VAR_DPHI = 1
 
 

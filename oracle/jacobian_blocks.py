@@ -8,7 +8,13 @@ oracle RHS in tests/test_host_side.py.  Parameter vector `p`: oracle.kernel_para
 import numpy as np
 
 
-def blocks(y, p, i, N):
+SWITCH_TOL = 1e-5          # csrc/implicit_common.cuh kSwitchTol
+
+
+def blocks(y, p, i, N, atol=None):
+    """`atol` given: the kernels' rule for cells ON a switching surface (|Pe| within SWITCH_TOL of Pe_min / Pe_max, U within
+    SWITCH_TOL of 0) — the porosity column of D is num_jac's one-sided difference quotient (step sqrt(eps) sign(f)
+    max(atol, |Phi|)) instead of the in-regime derivative."""
     Y = y.reshape(5, N)
     c = Y[:, i]
     CA, CC, a, o, P = c
@@ -122,6 +128,9 @@ def blocks(y, p, i, N):
         blk[4, 4] = dPhi * inv_dx2 - t4 * dgx[4]
     # ---- ghost cells fold into the own-cell block (LHeureux_model.py:26-30): top ghost 2 bc - c for every field;
     # bottom ghost 2 c - m for CA, CC (curvature 0), c for the solutes and the porosity (derivative 0)
+    pes = [abs(W * den * kCa), abs(W * den * kCO3), abs(W * kPhi)] if fv_on else []
+    on_switch = abs(U) <= SWITCH_TOL * max(1.0, abs(presum)) or any(
+        abs(pe - Pe_min) <= SWITCH_TOL * Pe_min or abs(pe - Pe_max) <= SWITCH_TOL * Pe_max for pe in pes)
     if first:
         D -= L
         L[:] = 0
@@ -130,6 +139,15 @@ def blocks(y, p, i, N):
         L[:, :2] -= Ub[:, :2]
         D[:, 2:] += Ub[:, 2:]
         Ub[:] = 0
+    if atol is not None and on_switch:
+        import lheureux_oracle as oracle
+        rows = [f * N + i for f in range(5)]
+        f0 = oracle.rhs(np.ascontiguousarray(y, dtype=np.float64), p, np.empty(5 * N))[rows].copy()
+        ys = (1.0 if f0[4] >= 0 else -1.0) * max(atol, abs(P))
+        h = (P + np.sqrt(np.finfo(float).eps) * ys) - P
+        y2 = np.array(y, dtype=np.float64)
+        y2[4 * N + i] = P + h
+        D[:, 4] = (oracle.rhs(y2, p, np.empty(5 * N))[rows] - f0) / h
     return L, D, Ub
 
 

@@ -9,7 +9,7 @@ import marlpde_b200 as mb
 from marlpde.parameters import Map_Scenario
 from dataclasses import asdict
 kind, out = sys.argv[1], sys.argv[2]
-jac = sys.argv[3] if len(sys.argv) > 3 else "fd"
+jac = sys.argv[3] if len(sys.argv) > 3 else "analytic"
 run = mb.integrate_bdf_batch if kind == "bdf" else mb.integrate_radau_batch
 pde = mb.sweep_lattice(asdict(Map_Scenario()), 16, 16, 16)
 P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)

@@ -11,7 +11,7 @@ kind = sys.argv[1] if len(sys.argv) > 1 else "bdf"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 t_end = float(sys.argv[3]) if len(sys.argv) > 3 else 0.05
 ordered = len(sys.argv) > 4 and sys.argv[4] == "1"
-jac = sys.argv[5] if len(sys.argv) > 5 else "fd"
+jac = sys.argv[5] if len(sys.argv) > 5 else "analytic"
 run = mb.integrate_bdf_batch if kind == "bdf" else mb.integrate_radau_batch
 pde = mb.sweep_lattice(asdict(Map_Scenario()), n, n, n)
 P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)

@@ -29,7 +29,7 @@ extern "C" int emu_radau(double* y, const marlpde_column_params* params, marlpde
   a.N = n_cells;
   a.opt = *opt;
   return simt::run_block(rd::kWarpsPerCta * 32, 0, [&]() {
-    const bool vd = (a.opt.flags & MARLPDE_FLAG_VAR_DPHI) != 0, fd = (a.opt.flags & MARLPDE_FLAG_JAC_ANALYTIC) == 0;
+    const bool vd = (a.opt.flags & MARLPDE_FLAG_VAR_DPHI) != 0, fd = (a.opt.flags & MARLPDE_FLAG_JAC_FD) != 0;
     if (vd && fd) rd::radau_kernel<true, true>(a);
     else if (vd) rd::radau_kernel<true, false>(a);
     else if (fd) rd::radau_kernel<false, true>(a);

@@ -211,7 +211,7 @@ def emu_bdf():
     lib = C.CDLL(so)
     lib.emu_bdf.restype = C.c_int
 
-    def run(P, y, t_end, t_eval=(), events=False, first_step=1e-6, tol=1e-3, jac="fd"):
+    def run(P, y, t_end, t_eval=(), events=False, first_step=1e-6, tol=1e-3, jac="analytic"):
         y = np.ascontiguousarray(y, dtype=np.float64).copy()
         P = np.ascontiguousarray(P)
         B, _, N = y.shape
@@ -221,7 +221,7 @@ def emu_bdf():
         ec, et, stats = np.zeros((B, 7), np.int32), np.full((B, 7, 16), np.nan), np.zeros((B, 4), np.int64)
         o = _cabi.RK45Options(t_bound=t_end, rtol=tol, atol=tol, max_step=float("inf"), max_steps=0, n_eval=te.size,
                               event_capacity=16, flags=(_cabi.FLAG_EVENTS if events else 0) |
-                              (_cabi.FLAG_JAC_ANALYTIC if jac == "analytic" else 0), quantum=0)
+                              (_cabi.FLAG_JAC_FD if jac == "fd" else 0), quantum=0)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         rc = lib.emu_bdf(p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), p(stats), p(ec), p(et))
         assert rc == 0, f"emulated BDF kernel: rc {rc}"

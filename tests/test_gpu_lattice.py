@@ -101,3 +101,36 @@ def test_radau_lattice_columns_match_scipy(lattice):
     assert np.median(worsts) <= 0.1, worsts
     assert worsts[int(0.85 * len(worsts))] <= 2.0, worsts
     assert worsts[-1] <= 500.0, worsts
+
+
+def test_bdf_lattice_columns_match_scipy_bdf():
+    """The BDF kernel on 32 columns spread over the benchmark lattice, to T*, against SciPy's BDF handed the same
+    block-tridiagonal structure (tests/golden/lattice_reference_bdf.npz).  Through the smooth phases the two take the same
+    steps; in the stiff phase (porosity excursion, W changing sign) a decision flipped by rounding sends them down
+    different step sequences, so the gate is statistical like the Radau one: work per column within 10 % (median), end
+    states within the distance two BDF runs at rtol = 1e-3 have (BDF's own global error here is ~15 tolerance units),
+    and the same verdict on which columns finish — up to the knife-edge columns next to the model's switching surfaces
+    (SciPy BDF itself finishes 2298 and stalls on 234)."""
+    g = np.load(os.path.join(GOLDEN, "lattice_reference_bdf.npz"))
+    idx = json.loads(str(g["__columns__"]))["bdf"]
+    pde = mb.sweep_lattice(oracle.default_scenario(), 16, 16, 16)
+    P, y0 = _columns(pde, idx)
+    res = mb.integrate_bdf_batch(y0, P, t_span=(0, 1), first_step=1e-6, rtol=1e-3, atol=1e-3, t_eval=[1.0], events=True,
+                                 event_capacity=8)
+    worsts, ratios, mismatched = [], [], []
+    for k, c in enumerate(idx):
+        want_status = int(g[f"bdf/{c}/status"])
+        if int(res.status[k]) != want_status:
+            mismatched.append((c, int(res.status[k]), want_status, float(res.t[k]), float(g[f"bdf/{c}/t"])))
+            continue
+        if want_status == 0:
+            want = g[f"bdf/{c}/y"].reshape(5, 200)
+            worsts.append(float(np.max(np.abs(res.y[k] - want) / (1e-3 + 1e-3 * np.abs(want)))))
+            ratios.append((res.nlu[k] / g[f"bdf/{c}/counts"][3], res.njev[k] / g[f"bdf/{c}/counts"][2],
+                           res.newton_iterations[k] / g[f"bdf/{c}/counts"][1]))
+            assert (res.event_counts[k][4] > 0) == (g[f"bdf/{c}/events"][4] > 0), c
+    assert len(mismatched) <= 3, mismatched
+    med = np.median(np.asarray(ratios), axis=0)
+    assert np.all((0.9 <= med) & (med <= 1.1)), med
+    worsts = np.sort(np.asarray(worsts))
+    assert np.median(worsts) <= 20.0 and worsts[int(0.85 * len(worsts))] <= 100.0, worsts

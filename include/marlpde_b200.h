@@ -228,6 +228,11 @@ int marlpde_rk45_stream_integrate_events_dev(double* d_y, const marlpde_column_p
  *             blocks, factors and stage vectors of every column; need not be initialised)
  *  Any n_cells >= 3 is accepted (nothing has to fit on chip).  A column that stops on the step budget
  *  resumes "cold": (t, h_abs, y) are kept, the Jacobian and the Newton start guess are rebuilt.
+ *  opts->quantum = K > 0 (TEAM columns): the first K columns of the batch — the longest ones of a cost-ordered sweep,
+ *  whose sequential time bounds the whole sweep, or all columns of a small batch — are integrated by two warps each
+ *  (a CTA per column: split RHS / element-wise passes / Jacobian, the two factorisation chains side by side), launched
+ *  on an internal second stream next to the one-warp-per-column launch of the others and joined back into `stream`.
+ *  d_queue must then hold TWO zeroed int32.  Same results up to the order of the norm reductions (1e-11).
  */
 size_t marlpde_radau_workspace_bytes(int n_columns, int n_cells);
 int marlpde_radau_integrate_dev(double* d_y, const marlpde_column_params* d_params,

@@ -537,6 +537,8 @@ static int implicit_integrate_dev(ImplicitKind kind, double* d_y, const marlpde_
     if (!d_event_counts) return fail(MARLPDE_EINVAL, "MARLPDE_FLAG_EVENTS needs event_counts");
     if (opts->event_capacity > 0 && !d_event_times) return fail(MARLPDE_EINVAL, "event_capacity > 0 needs event_times");
   }
+  if (opts->quantum < 0) return fail(MARLPDE_EINVAL, "negative quantum (team columns)");
+  if (kind == kBdf && opts->quantum != 0) return fail(MARLPDE_EUNSUPPORTED, "team columns (opts->quantum) are a Radau feature");
   const size_t need = implicit_workspace_bytes(kind, n_columns, n_cells);
   if (workspace_bytes < need) return fail(MARLPDE_EINVAL, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
   DevProps props;
@@ -600,7 +602,7 @@ static int implicit_integrate_host(ImplicitKind kind, double* y, const marlpde_c
   CU(ds.alloc(nb_s, s));
   CU(dte.alloc(sizeof(double) * (size_t)opts->n_eval, s));
   CU(dsnap.alloc(nb_snap, s));
-  CU(dq.alloc(sizeof(int32_t), s));
+  CU(dq.alloc(2 * sizeof(int32_t), s));     // [1]: queue of the team launch (opts->quantum, Radau)
   CU(dst.alloc(nb_stats, s));
   CU(dw.alloc(nb_work, s));
   CU(cudaMemcpyAsync(dy.p, y, nb_y, cudaMemcpyHostToDevice, s));
@@ -608,7 +610,7 @@ static int implicit_integrate_host(ImplicitKind kind, double* y, const marlpde_c
   CU(cudaMemcpyAsync(ds.p, state, nb_s, cudaMemcpyHostToDevice, s));
   if (opts->n_eval) CU(cudaMemcpyAsync(dte.p, t_eval, sizeof(double) * (size_t)opts->n_eval, cudaMemcpyHostToDevice, s));
   if (snapshots && nb_snap) CU(cudaMemcpyAsync(dsnap.p, snapshots, nb_snap, cudaMemcpyHostToDevice, s));
-  CU(cudaMemsetAsync(dq.p, 0, sizeof(int32_t), s));
+  CU(cudaMemsetAsync(dq.p, 0, 2 * sizeof(int32_t), s));
   CU(cudaMemcpyAsync(dst.p, stats, nb_stats, cudaMemcpyHostToDevice, s));
   rc = implicit_integrate_dev(kind, dy.as<double>(), dp.as<marlpde_column_params>(), ds.as<marlpde_column_state>(),
                               n_columns, n_cells, opts, dte.as<double>(), dsnap.as<double>(), dec.as<int32_t>(),

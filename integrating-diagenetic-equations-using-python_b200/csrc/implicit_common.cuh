@@ -28,6 +28,22 @@ constexpr int kWarpsPerCta = 4;
 #define MARLPDE_RADAU_MINBLOCKS 3
 #endif
 
+// ---- TEAMS.  kTeam = 1: one warp per column (the throughput shape: no barrier anywhere).  kTeam = 2: a CTA of two warps
+// works on ONE column — the latency shape for the few longest columns of a sweep, whose sequential time bounds the whole
+// sweep: the RHS passes, the element-wise passes and the Jacobian are split between the warps, the two
+// chains of the two-ended factorisation run on one warp each, the solves stay on warp 0.  Every decision is taken from
+// team-wide reductions, so both warps follow the same control flow; the team barrier is the block barrier.
+template <int kTeam>
+__device__ __forceinline__ void team_sync() {
+  if (kTeam == 1) __syncwarp();
+  else __syncthreads();
+}
+template <int kTeam>
+__device__ __forceinline__ bool team_all(bool pred) {
+  if (kTeam == 1) return __all_sync(0xffffffffu, pred);
+  return __syncthreads_or(pred ? 0 : 1) == 0;
+}
+
 // ---- complex helpers (double2 = re, im) -------------------------------------------------------
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
   return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
@@ -138,11 +154,14 @@ struct Args {
 // shared memory by cp.async one pass AHEAD: the ncu source page attributed 15 % of the kernel's stall samples to these
 // loads.  Measured: 64 columns to t = 0.05 0.486 -> 0.467 s (a lone warp is latency bound); 4096 columns unchanged
 // (1.42 s: with 1 776 columns in flight the kernel is bound by DRAM throughput, the stalls just move).
+// (pass0, pstride): this warp evaluates the passes pass0, pass0 + pstride, ... of 32 cell pairs each (a team of two warps
+// interleaves them; one warp alone: 0, 1).
 template <bool VD, class Sink>
 __device__ __forceinline__ void rhs_column(const ColumnConsts& kc, const fm::Tables& tb, int N, int lane,
                                            const double* yy, const double* add, double (*stage)[2][kStageDoubles + 6],
-                                           Sink&& sink) {
+                                           Sink&& sink, const int pass0 = 0, const int pstride = 1) {
   const int Hc = (N + 1) >> 1;
+  const int b0 = 32 * pass0, bs = 32 * pstride;
 #if MARLPDE_RADAU_RHS_STAGE
   auto issue = [&](int base, int b) {          // window of the pass that starts at pair `base` -> stage[b]
     const int c_lo = base > 0 ? 2 * base - 1 : 0;
@@ -154,18 +173,18 @@ __device__ __forceinline__ void rhs_column(const ColumnConsts& kc, const fm::Tab
     }
     cp_async_commit();
   };
-  issue(0, 0);
+  if (b0 < Hc) issue(b0, 0);
   int buf = 0;
 #else
   auto ld = [&](int ff, int i) -> double { return add ? yy[i * 5 + ff] + add[i * 5 + ff] : yy[i * 5 + ff]; };
 #endif
 #pragma unroll 1
-  for (int base = 0; base < Hc; base += 32) {
+  for (int base = b0; base < Hc; base += bs) {
     const int p = base + lane;
     const int cell0 = 2 * p;
 #if MARLPDE_RADAU_RHS_STAGE
-    if (base + 32 < Hc) {
-      issue(base + 32, buf ^ 1);
+    if (base + bs < Hc) {
+      issue(base + bs, buf ^ 1);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
@@ -229,15 +248,15 @@ __device__ __forceinline__ double fd_step(double y, double f, double atol) {
 // (VD: the kernel build for batches with MARLPDE_MODEL_VAR_DPHI columns.  This kernel competes for the instruction
 //  cache — 12 warps per SM in different phases, stall_no_instruction 0.9 per issue — so the default build carries none
 //  of the variant's code: always compiling it in measured 1.5 per issue.)
-template <bool VD>
+template <bool VD, int kTeam = 1>
 __device__ __noinline__ void rhs_eval(const ColumnConsts* kc, const fm::Tables* tb, int N, int lane, const double* yy,
                                       const double* add, double* out, double (*stage)[2][kStageDoubles + 6]) {
   auto sink = [&](int i, const double (&r5)[5]) {
 #pragma unroll
     for (int f = 0; f < 5; ++f) out[i * 5 + f] = r5[f];
   };
-  rhs_column<VD>(*kc, *tb, N, lane, yy, add, stage, sink);
-  __syncwarp();
+  rhs_column<VD>(*kc, *tb, N, lane, yy, add, stage, sink, kTeam == 1 ? 0 : (int)(threadIdx.x >> 5), kTeam);
+  team_sync<kTeam>();
 }
 
 // (Measured and dropped, r02a: the three stage evaluations of a Newton iteration fused with B = TI F - M W, one RHS
@@ -408,14 +427,14 @@ __device__ __noinline__ void fd_jacobian(const ColumnConsts& kc, const fm::Table
 // that slides along a switching surface is held there by exactly this straddling difference (jacobian() below).
 constexpr double kSwitchTol = 1e-5;
 
-template <bool VD>
+template <bool VD, int kTeam = 1>
 __device__ __noinline__ void jac_analytic(const ColumnConsts* kp, const fm::Tables* tbp, int N, int lane, const double* y,
                                           double atol, double* J) {
   const ColumnConsts& k = *kp;
   const fm::Tables& tb = *tbp;
   const double hdx = 0.5 * k.inv_dx;
 #pragma unroll 1
-  for (int i = lane; i < N; i += 32) {
+  for (int i = kTeam == 1 ? lane : (int)threadIdx.x; i < N; i += 32 * kTeam) {
     const bool first = i == 0, last = i == N - 1;
     double c[5], m[5], pl[5];
 #pragma unroll
@@ -627,7 +646,7 @@ __device__ __noinline__ void jac_analytic(const ColumnConsts* kp, const fm::Tabl
         blk[50 + f * 5 + r] = Ub[r][f];
       }
   }
-  __syncwarp();
+  team_sync<kTeam>();
 }
 
 // The Jacobian the integrators use.  DEFAULT (kJacFD = false): all blocks analytic in one pass (jac_analytic), with the
@@ -649,12 +668,13 @@ __device__ __noinline__ void jac_analytic(const ColumnConsts* kp, const fm::Tabl
 // (the same 11 columns stay unfinished — they stop in SciPy too) at the analytic price.
 template <bool kJacFD>
 __host__ __device__ constexpr int jac_rhs_evals() { return kJacFD ? 5 : 0; }
-template <bool VD, bool kJacFD>
+template <bool VD, bool kJacFD, int kTeam = 1>
 __device__ __forceinline__ void jacobian(const ColumnConsts& kc, const fm::Tables& tb, int N, int lane, const double* y,
                                          const double* f, double atol, double* J, double* scratch,
                                          double (*stage)[2][kStageDoubles + 6]) {
+  static_assert(kTeam == 1 || !kJacFD, "teams use the analytic Jacobian");
   if (kJacFD) fd_jacobian<VD>(kc, tb, N, lane, y, f, atol, J, scratch, stage);
-  else jac_analytic<VD>(&kc, &tb, N, lane, y, atol, J);
+  else jac_analytic<VD, kTeam>(&kc, &tb, N, lane, y, atol, J);
 }
 
 // Block-Thomas factorisation of (M I - J) for both systems at once.
@@ -683,9 +703,14 @@ __device__ __forceinline__ unsigned pivot_key(double mag, int r, bool candidate)
 // halves of the warp (half as many sequential steps, see solve()).  One loop over a schedule of N steps — top chain,
 // bottom chain, meeting cell — keeps a single instance of the elimination code.
 // kComplex = false (BDF: one real system) leaves all double2 work out; the record's complex part is then not written.
+// (j0, j1, peer): the steps [j0, j1) of the schedule run here (default: all N).  A team of two warps runs the top chain
+// [0, mid) on warp 0 and the bottom chain [mid, N-1) on warp 1 side by side, and after a team barrier warp 0 runs the
+// meeting step [N-1, N) with its own X (top chain) and `peer`'s X (bottom chain).
 template <bool kComplex>
 __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, const double M0, const double2 M1,
-                                       const double* J, float* Rec) {
+                                       const double* J, float* Rec, const int j0 = 0, int j1 = -1,
+                                       const WarpScratch* peer = nullptr) {
+  if (j1 < 0) j1 = N;
   const int l = lane < 25 ? lane : 0;     // lanes 25-31 shadow lane 0 (same values to the same shared words)
   const int r = l / 5, c = l - 5 * r;
   const bool diag = r == c;
@@ -693,7 +718,7 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, const d
   auto cell_of = [&](int j) { return j < mid ? j : (j < N - 1 ? N - 1 - (j - mid) : mid); };
   // ring of kSlots staged cells: steps 0 .. kDepth-1 are requested up front, step j+kDepth at iteration j
   auto request = [&](int j) {
-    if (j < N) {
+    if (j < j1) {
       const double* Jn = J + (size_t)cell_of(j) * 75;
       double* dst = ws.jst[j % kSlots];
 #pragma unroll
@@ -702,11 +727,18 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, const d
     }
     cp_async_commit();                                       // (empty groups keep the group count uniform)
   };
-  for (int c0 = 0; c0 < kDepth; ++c0) request(c0);
-  ws.x0[l] = 0.0;                                            // X_{-1} = 0
-  if (kComplex) ws.x1[l] = make_double2(0.0, 0.0);
+  for (int c0 = 0; c0 < kDepth; ++c0) request(j0 + c0);
+  if (!peer) {
+    ws.x0[l] = 0.0;                                          // X_{-1} = 0
+    if (kComplex) ws.x1[l] = make_double2(0.0, 0.0);
+  }
+  // meeting step: X of the top chain / of the bottom chain
+  const double* const top0 = peer ? ws.x0 : ws.xs0;
+  const double2* const top1 = peer ? ws.x1 : ws.xs1;
+  const double* const bot0 = peer ? peer->x0 : ws.x0;
+  const double2* const bot1 = peer ? peer->x1 : ws.x1;
 #pragma unroll 1
-  for (int j = 0; j < N; ++j) {
+  for (int j = j0; j < j1; ++j) {
     request(j + kDepth);                  // slot (j + kDepth) % kSlots was released at the end of iteration j-1
     cp_async_wait<kDepth>();              // all but the kDepth newest groups have landed: step j is in shared memory
     const int i = cell_of(j);
@@ -732,8 +764,8 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, const d
     double A0 = (diag ? M0 : 0.0) - Ji[25 + c * 5 + r];
     double2 A1 = make_double2((diag ? M1.x : 0.0) - Ji[25 + c * 5 + r], diag ? M1.y : 0.0);
     {
-      const double* xp0 = middle ? ws.xs0 : ws.x0;
-      const double2* xp1 = middle ? ws.xs1 : ws.x1;
+      const double* xp0 = middle ? top0 : ws.x0;
+      const double2* xp1 = middle ? top1 : ws.x1;
 #pragma unroll
       for (int m = 0; m < 5; ++m) {
         const double nl = -Ji[offP + m * 5 + r];
@@ -745,8 +777,8 @@ __device__ __noinline__ void factorise(WarpScratch& ws, int N, int lane, const d
 #pragma unroll
       for (int m = 0; m < 5; ++m) {
         const double nu = -Ji[50 + m * 5 + r];
-        A0 = fma(nu, ws.x0[m * 5 + c], A0);
-        if (kComplex) A1 = crfma(nu, ws.x1[m * 5 + c], A1);
+        A0 = fma(nu, bot0[m * 5 + c], A0);
+        if (kComplex) A1 = crfma(nu, bot1[m * 5 + c], A1);
       }
     }
     double B0 = diag ? 1.0 : 0.0;

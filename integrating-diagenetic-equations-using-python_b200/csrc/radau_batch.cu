@@ -75,7 +75,7 @@ __host__ __device__ inline size_t work_doubles(int N) {
 // solve_event_equation, xtol = rtol = 4 eps).  Rare, so it lives outside the step loop's instruction footprint.
 __device__ __noinline__ void locate_events(const Args& A, const ColumnConsts& kc, const fm::Tables& tb, int N, int lane,
                                            int col, unsigned act, double t_old, double t, double h_old,
-                                           const double* yold, const double* Q) {
+                                           const double* yold, const double* Q, bool writer) {
 #pragma unroll 1
   for (int k = 0; k < 7; ++k) {
     if (!((act >> k) & 1u)) continue;
@@ -91,7 +91,7 @@ __device__ __noinline__ void locate_events(const Args& A, const ColumnConsts& kc
       for (int kk = 1; kk < 7; ++kk) gk = (k == kk) ? gv[kk] : gk;
       if (bs.feed(gk, xeval, root)) break;
     }
-    if (lane == 0) {
+    if (lane == 0 && writer) {   // (a team runs the search redundantly on both warps; warp 0 records)
       int32_t* cnt = A.g_ev_counts + (size_t)col * MARLPDE_NEVENTS + k;
       const int have = *cnt;
       if (have < A.opt.event_capacity)
@@ -108,13 +108,36 @@ __device__ __noinline__ double predict_factor(double h_abs, double h_abs_old, do
   return fmin(1.0, mult) / sqrt(sqrt(err));      // x**0.25 as two square roots; err == 0 -> inf, as numpy
 }
 
-template <bool VD, bool kJacFD>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) radau_kernel(const Args A) {
+// kTeam = 1: CTAs of kWarpsPerCta warps, one column per WARP (the throughput shape).  kTeam = 2: CTAs of two warps, one
+// column per CTA (the latency shape for the longest columns of a sweep, implicit_common.cuh "TEAMS"): six of them are
+// resident per SM, the same 12 warps.  Every element-wise loop runs over team lanes (tl, stride ts), every barrier is
+// the team barrier, every reduction is team-wide, so both warps of a team take identical decisions.
+template <int kTeam>
+__device__ __forceinline__ double team_sum(double v, double (*red)[2], int& phase) {
+  v = warp_sum(v);
+  if (kTeam == 1) return v;
+  if ((threadIdx.x & 31) == 0) red[phase][threadIdx.x >> 5] = v;
+  __syncthreads();
+  const double r = red[phase][0] + red[phase][1];          // fixed order: identical in both warps
+  phase ^= 1;                                              // (double-buffered: one barrier per reduction is enough)
+  return r;
+}
+
+template <bool VD, bool kJacFD, int kTeam>
+__global__ void __launch_bounds__((kTeam == 1 ? kWarpsPerCta : 2) * 32, (kTeam == 1 ? 1 : 2) * MARLPDE_RADAU_MINBLOCKS)
+radau_kernel(const Args A) {
+  constexpr int kWarps = kTeam == 1 ? kWarpsPerCta : 2;
   __shared__ __align__(16) unsigned char tab_raw[fm::kTableBytes];
-  __shared__ WarpScratch scratch[kWarpsPerCta];
+  __shared__ WarpScratch scratch[kWarps];
+  __shared__ double red[2][2];
+  __shared__ int s_col;
   const fm::Tables tb = fm::stage_tables(tab_raw, threadIdx.x, blockDim.x);
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  const int wt = kTeam == 1 ? 0 : (int)(threadIdx.x >> 5);          // warp within the team
+  const int tl = kTeam == 1 ? lane : (int)threadIdx.x;             // team lane and team width
+  constexpr int ts = 32 * kTeam;
+  int red_phase = 0;
   WarpScratch& ws = scratch[threadIdx.x >> 5];
   const int N = A.N, n = 5 * N;
   const double rtol = A.opt.rtol, atol = A.opt.atol;
@@ -122,8 +145,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
 
   for (;;) {
     int col = 0;
-    if (lane == 0) col = atomicAdd(A.g_queue, 1);
-    col = __shfl_sync(0xffffffffu, col, 0);
+    if (kTeam == 1) {
+      if (lane == 0) col = atomicAdd(A.g_queue, 1);
+      col = __shfl_sync(0xffffffffu, col, 0);
+    } else {
+      if (threadIdx.x == 0) s_col = atomicAdd(A.g_queue, 1);
+      __syncthreads();
+      col = s_col;
+      __syncthreads();                                     // (s_col is rewritten for the next column)
+    }
     if (col >= A.n_columns) break;
 
     // ---- column set-up
@@ -148,8 +178,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
     w.Rec = reinterpret_cast<float*>(wbase);
     if (lane == 0) make_consts(A.g_params[col], N, ws.kc);
 #pragma unroll 1
-    for (int idx = lane; idx < n; idx += 32) y[idx] = gy[(idx % 5) * N + idx / 5];
-    __syncwarp();
+    for (int idx = tl; idx < n; idx += ts) y[idx] = gy[(idx % 5) * N + idx / 5];
+    team_sync<kTeam>();
     const ColumnConsts& kc = ws.kc;
     marlpde_column_state st = A.g_state[col];
     double t = st.t, h_attr = st.h_abs;
@@ -160,13 +190,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
     long long steps_done = 0;
 
     auto eval_to = [&](const double* yy, const double* add, double* out) {   // out = rhs(yy + add)
-      rhs_eval<VD>(&kc, &tb, N, lane, yy, add, out, ws.stage);
+      rhs_eval<VD, kTeam>(&kc, &tb, N, lane, yy, add, out, ws.stage);
     };
 
     if (t < A.opt.t_bound) {
       eval_to(y, nullptr, w.f);
       nfev += 1;
-      jacobian<VD, kJacFD>(kc, tb, N, lane, y, w.f, atol, w.J, w.B, ws.stage);
+      jacobian<VD, kJacFD, kTeam>(kc, tb, N, lane, y, w.f, atol, w.J, w.B, ws.stage);
       njev += 1;
       nfev += jac_rhs_evals<kJacFD>();   // (finite-difference diagonal blocks: one evaluation per field)
     }
@@ -213,12 +243,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
         bool converged = false;
         for (;;) {
           if (!lu_valid) {                 // (radau.py keeps the factors while the step-size factor is 1)
-            factorise<true>(ws, N, lane, kMuReal / h, make_double2(kMuCRe / h, kMuCIm / h), w.J, w.Rec);
+            if (kTeam == 1) {
+              factorise<true>(ws, N, lane, kMuReal / h, make_double2(kMuCRe / h, kMuCIm / h), w.J, w.Rec);
+            } else {                       // the two chains side by side, then the meeting cell on warp 0
+              const int mid = N / 2;
+              factorise<true>(ws, N, lane, kMuReal / h, make_double2(kMuCRe / h, kMuCIm / h), w.J, w.Rec,
+                              wt == 0 ? 0 : mid, wt == 0 ? mid : N - 1);
+              __syncthreads();
+              if (wt == 0)
+                factorise<true>(ws, N, lane, kMuReal / h, make_double2(kMuCRe / h, kMuCIm / h), w.J, w.Rec, N - 1, N,
+                                &scratch[1]);
+              __syncthreads();
+            }
             nlu += 2;
             lu_valid = true;
           }
           // ---- Z0 from the previous step's dense output (radau.py: Z0 = sol(t + h C).T - y), W = TI Z0
-          _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
+          _Pragma("unroll 1") for (int idx = tl; idx < n; idx += ts) {
             double z[3] = {0.0, 0.0, 0.0};
             if (have_sol) {
               const double q0 = w.Q[idx], q1 = w.Q[n + idx], q2 = w.Q[2 * n + idx];
@@ -235,7 +276,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
               w.W[sgi * n + idx] = kTI[sgi][0] * z[0] + kTI[sgi][1] * z[1] + kTI[sgi][2] * z[2];
             }
           }
-          __syncwarp();
+          team_sync<kTeam>();
           // ---- solve_collocation_system
           const double Mr = kMuReal / h, Mcr = kMuCRe / h, Mci = kMuCIm / h;
           double dW_norm_old = -1.0;
@@ -250,11 +291,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
             bool finite = true;
             // (element-wise passes; RADAU_BATCH4 issues 4 strides of loads per trip)
 #pragma unroll 1
-            for (int base = lane; base < n; base += (RADAU_BATCH4 ? 128 : 32)) {
+            for (int base = tl; base < n; base += (RADAU_BATCH4 ? 4 : 1) * ts) {
               double F0[4], F1[4], F2[4], W0[4], W1[4], W2[4];
 #pragma unroll
               for (int u = 0; u < (RADAU_BATCH4 ? 4 : 1); ++u) {
-                const int idx = base + 32 * u;
+                const int idx = base + ts * u;
                 const bool ok = idx < n;
                 F0[u] = ok ? w.B[idx] : 0.0;
                 F1[u] = ok ? w.B[n + idx] : 0.0;
@@ -265,7 +306,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
               }
 #pragma unroll
               for (int u = 0; u < (RADAU_BATCH4 ? 4 : 1); ++u) {
-                const int idx = base + 32 * u;
+                const int idx = base + ts * u;
                 if (idx >= n) continue;
                 finite = finite && isfinite(F0[u]) && isfinite(F1[u]) && isfinite(F2[u]);
                 // f_real = F^T TI_REAL - M_real W0 ; f_complex = F^T TI_COMPLEX - M_complex (W1 + i W2)
@@ -274,18 +315,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
                 w.B[2 * n + idx] = kTI[2][0] * F0[u] + kTI[2][1] * F1[u] + kTI[2][2] * F2[u] - (Mcr * W2[u] + Mci * W1[u]);
               }
             }
-            __syncwarp();
-            if (!__all_sync(0xffffffffu, finite)) break;
-            solve<false>(ws, N, lane, w.Rec, w.B, w.B + n, w.B + 2 * n, true);
+            team_sync<kTeam>();
+            if (!team_all<kTeam>(finite)) break;
+            if (wt == 0) solve<false>(ws, N, lane, w.Rec, w.B, w.B + n, w.B + 2 * n, true);
+            team_sync<kTeam>();
             // norm(dW / scale) and, in the same pass, W += dW, Z = T W.  (radau.py leaves W and Z untouched when
             // the rate test below breaks; they are dead then — every continuation re-initialises them from Z0.)
             double ss = 0.0;
 #pragma unroll 1
-            for (int base = lane; base < n; base += (RADAU_BATCH4 ? 128 : 32)) {
+            for (int base = tl; base < n; base += (RADAU_BATCH4 ? 4 : 1) * ts) {
               double d0[4], d1[4], d2[4], yy4[4], W0[4], W1[4], W2[4];
 #pragma unroll
               for (int u = 0; u < (RADAU_BATCH4 ? 4 : 1); ++u) {
-                const int idx = base + 32 * u;
+                const int idx = base + ts * u;
                 const bool ok = idx < n;
                 d0[u] = ok ? w.B[idx] : 0.0;
                 d1[u] = ok ? w.B[n + idx] : 0.0;
@@ -297,7 +339,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
               }
 #pragma unroll
               for (int u = 0; u < (RADAU_BATCH4 ? 4 : 1); ++u) {
-                const int idx = base + 32 * u;
+                const int idx = base + ts * u;
                 if (idx >= n) continue;
                 const double sc = fma(fabs(yy4[u]), rtol, atol);
                 const double a0 = d0[u] / sc, a1 = d1[u] / sc, a2 = d2[u] / sc;
@@ -310,8 +352,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
                 for (int sgi = 0; sgi < 3; ++sgi) w.Z[sgi * n + idx] = kT[sgi][0] * V0 + kT[sgi][1] * V1 + kT[sgi][2] * V2;
               }
             }
-            __syncwarp();
-            const double dW_norm = sqrt(warp_sum(ss) / (double)(3 * n));
+            team_sync<kTeam>();
+            const double dW_norm = sqrt(team_sum<kTeam>(ss, red, red_phase) / (double)(3 * n));
             if (dW_norm_old >= 0.0) rate = dW_norm / dW_norm_old;
             double rate_pow = rate;                     // rate ** (NEWTON_MAXITER - k)
             for (int e = 1; e < kNewtonMaxIter - k; ++e) rate_pow *= rate;
@@ -327,7 +369,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
           if (converged) break;
           n_newton_fail += 1;
           if (current_jac) break;
-          jacobian<VD, kJacFD>(kc, tb, N, lane, y, w.f, atol, w.J, w.B, ws.stage);
+          jacobian<VD, kJacFD, kTeam>(kc, tb, N, lane, y, w.f, atol, w.J, w.B, ws.stage);
           njev += 1;
           nfev += jac_rhs_evals<kJacFD>();   // (finite-difference diagonal blocks: one evaluation per field)
           current_jac = true;
@@ -339,22 +381,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
           continue;
         }
         // ---- error estimate: error = LU_real.solve(f + Z^T E / h)
-        _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
+        _Pragma("unroll 1") for (int idx = tl; idx < n; idx += ts) {
           const double ze = (w.Z[idx] * kE[0] + w.Z[n + idx] * kE[1] + w.Z[2 * n + idx] * kE[2]) / h;
           w.tmp[idx] = ze;
           w.err[idx] = w.f[idx] + ze;
         }
-        __syncwarp();
-        solve<false>(ws, N, lane, w.Rec, w.err, nullptr, nullptr, false);
+        team_sync<kTeam>();
+        if (wt == 0) solve<false>(ws, N, lane, w.Rec, w.err, nullptr, nullptr, false);
+        team_sync<kTeam>();
         auto err_norm_of = [&]() {
           double ss = 0.0;
-          _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
+          _Pragma("unroll 1") for (int idx = tl; idx < n; idx += ts) {
             const double yn = y[idx] + w.Z[2 * n + idx];
             const double sc = fma(fmax(fabs(y[idx]), fabs(yn)), rtol, atol);
             const double a = w.err[idx] / sc;
             ss += a * a;
           }
-          return sqrt(warp_sum(ss) / (double)n);
+          return sqrt(team_sum<kTeam>(ss, red, red_phase) / (double)n);
         };
         error_norm = err_norm_of();
         safety = 0.9 * (2 * kNewtonMaxIter + 1) / (double)(2 * kNewtonMaxIter + n_iter);
@@ -362,9 +405,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
           // error = LU_real.solve(fun(t, y + error) + ZE)
           eval_to(y, w.err, w.B);
           nfev += 1;
-          _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) w.err[idx] = w.B[idx] + w.tmp[idx];
-          __syncwarp();
-          solve<false>(ws, N, lane, w.Rec, w.err, nullptr, nullptr, false);
+          _Pragma("unroll 1") for (int idx = tl; idx < n; idx += ts) w.err[idx] = w.B[idx] + w.tmp[idx];
+          team_sync<kTeam>();
+          if (wt == 0) solve<false>(ws, N, lane, w.Rec, w.err, nullptr, nullptr, false);
+        team_sync<kTeam>();
           error_norm = err_norm_of();
         }
         if (error_norm > 1.0 || !(error_norm == error_norm)) {
@@ -387,7 +431,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
       if (!recompute_jac && factor < 1.2) factor = 1.0;
       else lu_valid = false;
       // y_old <- y, y <- y + Z[2], Q = Z^T P (dense output of this step)
-      _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32) {
+      _Pragma("unroll 1") for (int idx = tl; idx < n; idx += ts) {
         const double z0 = w.Z[idx], z1 = w.Z[n + idx], z2 = w.Z[2 * n + idx];
         const double yo = y[idx];
         w.yold[idx] = yo;
@@ -395,11 +439,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
 #pragma unroll
         for (int j = 0; j < 3; ++j) w.Q[j * n + idx] = z0 * kP[0][j] + z1 * kP[1][j] + z2 * kP[2][j];
       }
-      __syncwarp();
+      team_sync<kTeam>();
       eval_to(y, nullptr, w.f);
       nfev += 1;
       if (recompute_jac) {
-        jacobian<VD, kJacFD>(kc, tb, N, lane, y, w.f, atol, w.J, w.B, ws.stage);
+        jacobian<VD, kJacFD, kTeam>(kc, tb, N, lane, y, w.f, atol, w.J, w.B, ws.stage);
         njev += 1;
         nfev += jac_rhs_evals<kJacFD>();   // (finite-difference diagonal blocks: one evaluation per field)
         current_jac = true;
@@ -421,7 +465,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
         unsigned act = 0u;
         if (ev_new != ev_prev || (ev_new & kEqBitsMask) != 0u) act = active_events(event_classes(ev_prev), event_classes(ev_new));
         ev_prev = ev_new;
-        if (act) locate_events(A, kc, tb, N, lane, col, act, t_old, t, h_old, w.yold, w.Q);   // rare: kept out of line
+        if (act) locate_events(A, kc, tb, N, lane, col, act, t_old, t, h_old, w.yold, w.Q, wt == 0);   // rare: out of line
       }
       // ---- t_eval samples in (t_old, t] (t_eval[0] == t0 belongs to the first step): y_old + Q p(x)
       while (next_eval < A.opt.n_eval) {
@@ -429,14 +473,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
         if (!(te <= t)) break;
         const double xx = (te - t_old) / h_old;
         double* snap = A.g_snap + ((size_t)col * A.opt.n_eval + next_eval) * n;
-        _Pragma("unroll 1") for (int idx = lane; idx < n; idx += 32)
+        _Pragma("unroll 1") for (int idx = tl; idx < n; idx += ts)
           snap[(idx % 5) * N + idx / 5] = w.yold[idx] + xx * (w.Q[idx] + xx * (w.Q[n + idx] + xx * w.Q[2 * n + idx]));
         ++next_eval;
       }
     }
 #pragma unroll 1
-    for (int idx = lane; idx < n; idx += 32) gy[(idx % 5) * N + idx / 5] = y[idx];
-    if (lane == 0) {
+    for (int idx = tl; idx < n; idx += ts) gy[(idx % 5) * N + idx / 5] = y[idx];
+    if (tl == 0) {
       st.t = t;
       st.h_abs = h_attr;
       st.n_accepted = n_acc;
@@ -451,7 +495,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MARLPDE_RADAU_MINBLOCKS) ra
       s4[2] += n_newton;
       s4[3] += n_newton_fail;
     }
-    __syncwarp();
+    team_sync<kTeam>();
   }
 }
 
@@ -480,17 +524,60 @@ cudaError_t launch_radau(double* d_y, const marlpde_column_params* d_params, mar
   a.n_columns = n_columns;
   a.N = n_cells;
   a.opt = opt;
-  int ctas = (n_columns + rd::kWarpsPerCta - 1) / rd::kWarpsPerCta;
-  const int max_ctas = sm_count * MARLPDE_RADAU_MINBLOCKS;
-  if (ctas > max_ctas) ctas = max_ctas;
-  if (ctas < 1) ctas = 1;
+  // opt.quantum (implicit integrators): the first `quantum` columns of the batch — the longest ones of a cost-ordered
+  // sweep — run in TEAM mode (two warps per column, a CTA each) on a second stream, side by side with the one-warp-per-
+  // column launch of the others; their queue counter is d_queue[1].  Needs the analytic Jacobian.
   const bool vd = (opt.flags & MARLPDE_FLAG_VAR_DPHI) != 0, fd = (opt.flags & MARLPDE_FLAG_JAC_FD) != 0;
-  const int threads = rd::kWarpsPerCta * 32;
-  if (vd && fd) rd::radau_kernel<true, true><<<ctas, threads, 0, stream>>>(a);
-  else if (vd) rd::radau_kernel<true, false><<<ctas, threads, 0, stream>>>(a);
-  else if (fd) rd::radau_kernel<false, true><<<ctas, threads, 0, stream>>>(a);
-  else rd::radau_kernel<false, false><<<ctas, threads, 0, stream>>>(a);
-  return cudaGetLastError();
+  int n_team = fd ? 0 : opt.quantum;
+  if (n_team < 0) n_team = 0;
+  if (n_team > n_columns) n_team = n_columns;
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (n_team > 0) {
+    cudaError_t e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&e0, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&e1, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(e0, stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s2, e0, 0);
+    if (e != cudaSuccess) return e;
+    rd::Args t = a;
+    t.n_columns = n_team;
+    t.g_queue = d_queue + 1;
+    int ctas2 = n_team < sm_count * 2 * MARLPDE_RADAU_MINBLOCKS ? n_team : sm_count * 2 * MARLPDE_RADAU_MINBLOCKS;
+    if (vd) rd::radau_kernel<true, false, 2><<<ctas2, 64, 0, s2>>>(t);
+    else rd::radau_kernel<false, false, 2><<<ctas2, 64, 0, s2>>>(t);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const size_t n = 5 * (size_t)n_cells;
+    a.g_y += (size_t)n_team * n;
+    a.g_params += n_team;
+    a.g_state += n_team;
+    if (a.g_snap) a.g_snap += (size_t)n_team * (size_t)opt.n_eval * n;
+    a.g_stats += (size_t)n_team * 4;
+    if (a.g_ev_counts) a.g_ev_counts += (size_t)n_team * MARLPDE_NEVENTS;
+    if (a.g_ev_times) a.g_ev_times += (size_t)n_team * MARLPDE_NEVENTS * (size_t)(opt.event_capacity > 0 ? opt.event_capacity : 0);
+    a.g_work += (size_t)n_team * rd::work_doubles(n_cells);
+    a.n_columns = n_columns - n_team;
+  }
+  if (a.n_columns > 0) {
+    int ctas = (a.n_columns + rd::kWarpsPerCta - 1) / rd::kWarpsPerCta;
+    const int max_ctas = sm_count * MARLPDE_RADAU_MINBLOCKS;
+    if (ctas > max_ctas) ctas = max_ctas;
+    const int threads = rd::kWarpsPerCta * 32;
+    if (vd && fd) rd::radau_kernel<true, true, 1><<<ctas, threads, 0, stream>>>(a);
+    else if (vd) rd::radau_kernel<true, false, 1><<<ctas, threads, 0, stream>>>(a);
+    else if (fd) rd::radau_kernel<false, true, 1><<<ctas, threads, 0, stream>>>(a);
+    else rd::radau_kernel<false, false, 1><<<ctas, threads, 0, stream>>>(a);
+  }
+  cudaError_t le = cudaGetLastError();
+  if (n_team > 0) {
+    if (le == cudaSuccess) le = cudaEventRecord(e1, s2);
+    if (le == cudaSuccess) le = cudaStreamWaitEvent(stream, e1, 0);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaStreamDestroy(s2);
+  }
+  return le;
 }
 
 #endif

@@ -27,6 +27,7 @@ try:
     print('equal_load',j.get('equal_load',{}).get('value'))
     print('tstar',{k:v for k,v in j.get('time_to_Tstar',{}).items() if k in('seconds','finished','status_histogram','step_attempts','column_steps_per_s')})
     for b,v in j.get('implicit_time_to_Tstar',{}).items(): print(b,v['seconds'],v['finished'],v['roofline']['frac'],v.get('repeat_sweep_longest_first'),{k:x for k,x in (v.get('cpu_baseline') or {}).items() if k.startswith('seconds')})
+    for b,v in j.get('bdf_time_to_Tstar',{}).items(): print('bdf',b,v['seconds'],v['finished'],v['roofline']['frac'],{k:x for k,x in (v.get('cpu_baseline') or {}).items() if k.startswith('seconds')})
     for b,v in j.get('large_n_streaming',{}).items(): print(b,v['column_steps_per_s'],v['roofline']['frac'],v['roofline_hbm']['frac'])
     print(j['roofline']); print(j['cpu_baseline']); print(j['e2e'])
 except Exception as e: print('parse failed',e)

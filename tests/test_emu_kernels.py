@@ -149,8 +149,9 @@ def emu_radau():
                    check=True, capture_output=True)
     lib = C.CDLL(so)
     lib.emu_radau.restype = C.c_int
+    lib.emu_radau_team.restype = C.c_int
 
-    def run(P, y, t_end, t_eval=(), events=False, first_step=1e-6):
+    def run(P, y, t_end, t_eval=(), events=False, first_step=1e-6, team=False):
         y = np.ascontiguousarray(y, dtype=np.float64).copy()
         P = np.ascontiguousarray(P)
         B, _, N = y.shape
@@ -161,9 +162,9 @@ def emu_radau():
         o = _cabi.RK45Options(t_bound=t_end, rtol=1e-3, atol=1e-3, max_step=float("inf"), max_steps=0, n_eval=te.size,
                               event_capacity=16, flags=_cabi.FLAG_EVENTS if events else 0, quantum=0)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
-        rc = lib.emu_radau(p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), p(stats), p(ec), p(et))
+        rc = (lib.emu_radau_team if team else lib.emu_radau)(p(y), p(P), p(st), B, N, C.byref(o), p(te), p(snap), p(stats), p(ec), p(et))
         assert rc == 0, f"emulated Radau kernel: rc {rc}"
-        return dict(y=y, state=st, snapshots=snap, stats=stats, event_counts=ec)
+        return dict(y=y, state=st, snapshots=snap, stats=stats, event_counts=ec, event_times=et)
     return run
 
 
@@ -188,6 +189,28 @@ def test_radau_kernel_under_emulation(emu_radau):
     s4 = oracle.integrate(one, method="Radau", t_span=(0, 0.006), t_eval=[0.006], events=False, first_step=5e-7,
                           jac_sparsity=oracle.jacobian_sparsity(200)).y.reshape(5, 200)
     assert np.max(np.abs(a["y"][4] - s4) / (1e-3 + 1e-3 * np.abs(s4))) <= 1.0
+
+
+def test_radau_team_kernel_under_emulation(emu_radau):
+    """The TEAM shape of the Radau kernel (two warps per column, a CTA each: split RHS / element-wise passes / Jacobian,
+    the two factorisation chains on one warp each, team-wide reductions, block barriers) against the one-warp shape: the
+    emulator reports a barrier that not every thread reaches or a deadlock; the two shapes must take the same steps, LU
+    and Newton counts and events, with states equal up to the order of the norm reductions."""
+    pde = oracle.default_scenario() | SCEN_A
+    P, y0 = mb.derive_column_params(pde), mb.initial_state(pde)
+    te = np.linspace(0, 1, 6)
+    a, b = emu_radau(P, y0, 1.0, t_eval=te), emu_radau(P, y0, 1.0, t_eval=te, team=True)
+    assert np.array_equal(a["state"], b["state"]) or (a["state"]["n_accepted"] == b["state"]["n_accepted"]).all()
+    assert np.array_equal(a["stats"], b["stats"])
+    assert np.max(np.abs(a["snapshots"] - b["snapshots"])) <= 1e-10
+    lat = mb.sweep_lattice(oracle.default_scenario(), 1, 1, 3)          # three columns through the team's queue, events on
+    Pl, yl = mb.derive_column_params(lat), mb.initial_state(lat)
+    a = emu_radau(Pl, yl, 0.03, t_eval=[0.03], events=True, first_step=5e-7)
+    b = emu_radau(Pl, yl, 0.03, t_eval=[0.03], events=True, first_step=5e-7, team=True)
+    assert np.array_equal(a["stats"], b["stats"]) and np.array_equal(a["event_counts"], b["event_counts"])
+    assert a["event_counts"].sum() >= 5
+    assert np.max(np.abs(a["y"] - b["y"])) <= 1e-9
+    assert np.nanmax(np.abs(a["event_times"] - b["event_times"])) <= 1e-10
 
 
 # ----------------------------------------------------------------------------------------- BDF kernel

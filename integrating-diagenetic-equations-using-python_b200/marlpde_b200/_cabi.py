@@ -21,7 +21,6 @@ FLAG_QUEUE_LOCKS = 2
 FLAG_VAR_DPHI = 4
 FLAG_QUEUE_TAIL = 8
 FLAG_JAC_FD = 16
-FLAG_RK45_SOLO = 32
 MODEL_VAR_DPHI = 1
 
 

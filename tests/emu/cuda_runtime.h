@@ -46,9 +46,6 @@ int block_barrier(int pred, int op);          // op 0: plain, 1: count, 2: or
 void mbar_init(uint64_t* bar, unsigned count);
 void mbar_arrive(uint64_t* bar);
 void mbar_wait(uint64_t* bar, unsigned parity);
-unsigned cluster_rank();                       // rank of the calling fiber's block in its cluster of two
-unsigned char* peer_smem(unsigned rank);       // dynamic shared memory of the block with that rank
-void cluster_barrier();
 enum { OP_SHFL_IDX, OP_SHFL_UP, OP_SHFL_DOWN, OP_SHFL_XOR, OP_ANY, OP_ALL, OP_BALLOT, OP_MATCH_ANY, OP_RED_OR, OP_RED_MAX, OP_SYNC };
 }  // namespace simt
 #define threadIdx (::simt::g_threadIdx)

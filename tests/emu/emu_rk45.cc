@@ -19,7 +19,7 @@ extern "C" int emu_rk45(int variant, double* y, const marlpde_column_params* par
   // EMU_GRID blocks, one after the other, on the same column queue (the claim policy sees gridDim.x = EMU_GRID)
   const char* ge = std::getenv("EMU_GRID");
   const int grid = ge && std::atoi(ge) > 0 ? std::atoi(ge) : 1;
-  const bool pair = variant == 352;          // the paired shape: a cluster of two blocks at a time
+  (void)variant;
   Rk45Args a;
   a.g_y = y;
   a.g_params = params;
@@ -32,13 +32,6 @@ extern "C" int emu_rk45(int variant, double* y, const marlpde_column_params* par
   a.n_columns = n_columns;
   a.N = n_cells;
   a.C = columns_per_cta_t<kRk45Threads>(n_cells, budget);
-  a.Hs0 = 0;
-  const PairShape ps = rk45_pair_shape(n_cells, budget);
-  if (pair) {
-    if (ps.C <= 0 || grid % 2) return -3;
-    a.C = ps.C;
-    a.Hs0 = ps.Hs0;
-  }
   if (a.C <= 0) return -2;
   const int Hc = (n_cells + 1) / 2;
   a.logG = group_log2(Hc);
@@ -49,17 +42,7 @@ extern "C" int emu_rk45(int variant, double* y, const marlpde_column_params* par
   a.quantum = 0;
   // EMU_SLOTS: pretend the launch has this many resident slots when the library chooses the quanta itself
   const char* se = std::getenv("EMU_SLOTS");
-  choose_quanta(a, se && std::atoi(se) > 0 ? std::atoi(se) : (pair ? grid / 2 * (2 * a.C + 1) : grid * a.C));
-  if (pair) {
-    for (int b = 0; b < grid; b += 2)
-      if (int rc = simt::run_cluster2(ps.threads, Smem<kRk45PairStride>::total_pair(a.C + 1),
-                                      [&]() {
-                                        if (opt->flags & MARLPDE_FLAG_VAR_DPHI) rk45_persistent_kernel<kRk45PairStride, true, true>(a);
-                                        else rk45_persistent_kernel<kRk45PairStride, false, true>(a);
-                                      }, b, grid))
-        return rc;
-    return 0;
-  }
+  choose_quanta(a, se && std::atoi(se) > 0 ? std::atoi(se) : grid * a.C);
   const int threads = ((a.C * Hc + 31) / 32) * 32;
   for (int b = 0; b < grid; ++b)
     if (int rc = simt::run_block(threads, Smem<kRk45Threads>::total(a.C),

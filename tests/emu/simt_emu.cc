@@ -27,9 +27,7 @@ std::vector<Fiber> fibers;
 ucontext_t sched_ctx;
 int cur = -1;
 bool failed = false;
-std::vector<unsigned char> smem[2];   // one buffer per co-resident block (two with a thread-block cluster of 2)
-int n_per_block = 0, n_blocks = 1, first_block = 0;
-int blk() { return n_per_block > 0 ? cur / n_per_block : 0; }
+std::vector<unsigned char> smem;
 const std::function<void()>* body_fn = nullptr;
 long long progress = 0;          // bumped whenever a rendezvous completes or a fiber finishes
 
@@ -45,8 +43,7 @@ struct BlockBar {
   int arrived = 0, count = 0, any = 0;
   long long gen = 0;
   int res_count = 0, res_or = 0;
-} bb_[2], cb;          // per block; cb: the cluster barrier (all fibers)
-#define bb (bb_[blk()])
+} bb;
 
 // ---- warp collectives: one rendezvous state per (warp, mask) ---------------------------
 struct Rdv {
@@ -70,21 +67,7 @@ void trampoline() {
 }
 }  // namespace
 
-unsigned char* dyn_smem() { return smem[blk()].data(); }
-unsigned cluster_rank() { return (unsigned)blk(); }
-unsigned char* peer_smem(unsigned rank) { return smem[rank & 1u].data(); }
-
-void cluster_barrier() {
-  const long long g = cb.gen;
-  cb.arrived += 1;
-  if (cb.arrived == (int)fibers.size()) {
-    cb.arrived = 0;
-    cb.gen += 1;
-    ++progress;
-  } else {
-    while (cb.gen == g) yield();
-  }
-}
+unsigned char* dyn_smem() { return smem.data(); }
 
 int block_barrier(int pred, int op) {
   (void)op;
@@ -92,7 +75,7 @@ int block_barrier(int pred, int op) {
   bb.arrived += 1;
   bb.count += pred ? 1 : 0;
   bb.any |= pred ? 1 : 0;
-  if (bb.arrived == n_per_block) {
+  if (bb.arrived == (int)fibers.size()) {
     bb.res_count = bb.count;
     bb.res_or = bb.any;
     bb.arrived = bb.count = bb.any = 0;
@@ -105,12 +88,12 @@ int block_barrier(int pred, int op) {
 }
 
 unsigned long long warp_collective(unsigned mask, unsigned long long value, int op, int arg) {
-  const int tid = cur % n_per_block, lane = tid & 31, warp = tid >> 5;
-  const int n = n_per_block;
+  const int tid = cur, lane = tid & 31, warp = tid >> 5;
+  const int n = (int)fibers.size();
   // lanes that do not exist in the block (partial last warp) cannot be named
   if (warp * 32 + 32 > n) mask &= (n - warp * 32 >= 32) ? 0xffffffffu : ((1u << (n - warp * 32)) - 1u);
   if (!((mask >> lane) & 1u)) fail("warp collective called by a lane that is not in its mask");
-  Rdv& r = rdv[((unsigned long long)(warp + 64 * blk()) << 32) | mask];
+  Rdv& r = rdv[((unsigned long long)warp << 32) | mask];
   if (r.arrived == 0) {
     r.mask = mask;
     r.op = op;
@@ -189,27 +172,21 @@ void mbar_wait(uint64_t* bar, unsigned parity) {
   while (m.phase == (parity & 1u)) yield();     // the phase with this parity has not completed yet
 }
 
-static int run_blocks(int n_threads, int blocks, size_t dyn_smem_bytes, const std::function<void()>& body, int block, int grid) {
-  n_per_block = n_threads;
-  n_blocks = blocks;
-  first_block = block;
-  const int n_fibers = n_threads * blocks;
-  if ((int)fibers.size() != n_fibers) fibers.resize(n_fibers);     // stacks are kept between blocks
+int run_block(int n_threads, size_t dyn_smem_bytes, const std::function<void()>& body, int block, int grid) {
+  if ((int)fibers.size() != n_threads) fibers.resize(n_threads);     // stacks are kept between blocks
   for (Fiber& f : fibers) f.done = false;
   rdv.clear();
   mbars.clear();
-  bb_[0] = bb_[1] = cb = BlockBar();
+  bb = BlockBar();
   failed = false;
   progress = 0;
-  for (int b = 0; b < blocks; ++b) {
-    if (smem[b].size() < dyn_smem_bytes + 64) smem[b].resize(dyn_smem_bytes + 64);
-    std::fill(smem[b].begin(), smem[b].end(), 0);
-  }
+  if (smem.size() < dyn_smem_bytes + 64) smem.resize(dyn_smem_bytes + 64);
+  std::fill(smem.begin(), smem.end(), 0);
   body_fn = &body;
   g_blockDim = {(unsigned)n_threads, 1, 1};
   g_blockIdx = {(unsigned)block, 0, 0};
   g_gridDim = {(unsigned)grid, 1, 1};
-  for (int i = 0; i < n_fibers; ++i) {
+  for (int i = 0; i < n_threads; ++i) {
     Fiber& f = fibers[i];
     if (f.stack.size() != kStack) f.stack.resize(kStack);
     getcontext(&f.ctx);
@@ -222,12 +199,11 @@ static int run_blocks(int n_threads, int blocks, size_t dyn_smem_bytes, const st
   int idle_rounds = 0;
   for (;;) {
     int alive = 0;
-    for (int i = 0; i < n_fibers && !failed; ++i) {
+    for (int i = 0; i < n_threads && !failed; ++i) {
       if (fibers[i].done) continue;
       ++alive;
       cur = i;
-      g_threadIdx = {(unsigned)(i % n_threads), 0, 0};
-      g_blockIdx = {(unsigned)(block + i / n_threads), 0, 0};
+      g_threadIdx = {(unsigned)i, 0, 0};
       swapcontext(&sched_ctx, &fibers[i].ctx);
     }
     if (failed) return -1;
@@ -242,14 +218,6 @@ static int run_blocks(int n_threads, int blocks, size_t dyn_smem_bytes, const st
       last_progress = progress;
     }
   }
-}
-
-int run_block(int n_threads, size_t dyn_smem_bytes, const std::function<void()>& body, int block, int grid) {
-  return run_blocks(n_threads, 1, dyn_smem_bytes, body, block, grid);
-}
-
-int run_cluster2(int n_threads, size_t dyn_smem_bytes, const std::function<void()>& body, int first_block_of_pair, int grid) {
-  return run_blocks(n_threads, 2, dyn_smem_bytes, body, first_block_of_pair, grid);
 }
 
 void run_grid(int grid, int n_threads, size_t dyn_smem_bytes, const std::function<void()>& body) {

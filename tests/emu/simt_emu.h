@@ -13,9 +13,6 @@ namespace simt {
 // run `body` once per thread of a block of `n_threads` threads with `dyn_smem_bytes` of dynamic shared memory;
 // returns 0, or -1 after a deadlock / mismatched collective (message on stderr)
 int run_block(int n_threads, size_t dyn_smem_bytes, const std::function<void()>& body, int block = 0, int grid = 1);
-// a thread-block cluster of two blocks (blockIdx first_block_of_pair and + 1) running side by side: 2 n_threads fibers, one
-// shared-memory buffer and block barrier each, cluster barrier, and the peer's shared memory reachable (cuda_runtime.h)
-int run_cluster2(int n_threads, size_t dyn_smem_bytes, const std::function<void()>& body, int first_block_of_pair = 0, int grid = 2);
 // the blocks of a grid, one after the other (kernels without inter-block synchronisation); aborts the process on failure
 void run_grid(int grid, int n_threads, size_t dyn_smem_bytes, const std::function<void()>& body);
 }  // namespace simt
